@@ -1,0 +1,213 @@
+"""
+ORACLE TOOLING -- TEST INFRASTRUCTURE ONLY (build container only; needs /root/reference).
+
+Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+`train_soft_intro_vae()` (soft_intro_vae/train_soft_intro_vae.py:337-702, and the bootstrap twin)
+for exactly one introspective iteration on CPU, and recording everything at its boundary:
+
+  * the model's state_dict right after construction (SoftIntroVAE ctor, :442)
+  * the real batch, the `noise_batch` draw (:547) and the five reparameterisation draws
+    (:560,567,568,602,605) -- captured by wrapping `torch.randn` / `ref.reparameterize`
+  * encoder grads at `optimizer_e.step()` (:589) and decoder grads at `optimizer_d.step()` (:624)
+    -- captured by a recording subclass of optim.Adam
+  * the logged scalars (tqdm postfix :629-631 and the pickle :695-697)
+  * the state_dict right after optimizer_d.step() (snapshotted inside the tqdm `set_postfix` call, :629)
+
+No reference source is copied: the reference module is imported from /root/reference and only its
+module globals are patched (dataset class, matplotlib stub, model hyper-parameters for the tiny
+config).  Usage:  python oracle/make_golden.py   (writes tests/golden/*.pt, ~6 MB total)
+"""
+import hashlib
+import os
+import pickle
+import sys
+import tempfile
+from unittest.mock import MagicMock
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _import_reference(subdir: str, modname: str):
+    """Import the reference trainer unmodified (container lacks matplotlib; no network)."""
+    mpl, plt = MagicMock(), MagicMock()
+    plt.subplots = lambda *a, **k: (MagicMock(), MagicMock())
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = plt
+    mpl.pyplot = plt
+    for m in ("dataset", "metrics", "metrics.fid_score", "metrics.inception", modname):
+        sys.modules.pop(m, None)
+    sys.path.insert(0, os.path.join(REF, subdir))
+    try:
+        mod = __import__(modname)
+    finally:
+        sys.path.pop(0)
+    return mod
+
+
+def run_reference_iteration(subdir, modname, fn_name, *, tiny, batch, z_dim, seed, beta_neg, extra_kwargs=None,
+                            data_seed=1234, image_size=32):
+    ref = _import_reference(subdir, modname)
+    rec = {"eps": [], "noise": [], "grads": [], "postfix": None}
+
+    class FakeCIFAR(torch.utils.data.Dataset):       # ref.CIFAR10 is looked up as a module global (:379)
+        def __init__(self, root=None, train=True, download=False, transform=None):
+            self.x = torch.rand(batch, 3, image_size, image_size, generator=torch.Generator().manual_seed(data_seed))
+
+        def __len__(self):
+            return len(self.x)
+
+        def __getitem__(self, i):
+            return self.x[i], 0
+
+    ref.CIFAR10 = FakeCIFAR
+
+    holder = {}
+    orig_init = ref.SoftIntroVAE.__init__           # the class itself stays the reference's
+
+    def patched_init(self, cdim=3, zdim=512, channels=(64, 128, 256, 512, 512, 512), image_size=256, **kw):
+        if tiny is not None:                         # only the architecture hyper-parameters are substituted
+            channels, image_size = tiny["channels"], tiny["image_size"]
+        orig_init(self, cdim=cdim, zdim=zdim, channels=channels, image_size=image_size, **kw)
+        holder["model"] = self
+        holder["init"] = {k: v.detach().clone() for k, v in self.state_dict().items()}
+        holder["arch"] = dict(cdim=cdim, zdim=zdim, channels=list(channels), image_size=image_size)
+
+    ref.SoftIntroVAE.__init__ = patched_init
+
+    def reparameterize(mu, logvar):                 # same maths as :254-265, draw recorded
+        eps = torch.randn_like(logvar)
+        rec["eps"].append(eps.detach().clone())
+        return mu + eps * torch.exp(0.5 * logvar)
+
+    ref.reparameterize = reparameterize
+
+    orig_randn = torch.randn
+
+    def randn(*a, **k):
+        t = orig_randn(*a, **k)
+        if k.get("size", None) is not None and tuple(k["size"]) == (batch, z_dim):
+            rec["noise"].append(t.detach().clone())
+        return t
+
+    class RecAdam(torch.optim.Adam):
+        def step(self, closure=None):
+            g = {}
+            for grp in self.param_groups:
+                for p in grp["params"]:
+                    g[id(p)] = None if p.grad is None else p.grad.detach().clone()
+            rec["grads"].append(g)
+            return super().step(closure)
+
+    ref.optim.Adam = RecAdam
+
+    class Bar:                                       # stands in for tqdm(iterable=loader), :506
+        def __init__(self, iterable=None, **k):
+            self.it = iterable
+
+        def __iter__(self):
+            for b in self.it:                        # the loader shuffles (:458): record the batch actually seen
+                rec["real"] = b[0].detach().clone()
+                yield b
+
+        def set_description_str(self, *a, **k):
+            pass
+
+        def set_postfix(self, **k):
+            # called at :629-631, i.e. after optimizer_d.step() (:624) and BEFORE the iteration-0 sample figure
+            # (:641-646, a train-mode forward that also moves the BN running stats) -- snapshot here.
+            rec["postfix"] = dict(k)
+            holder["post"] = {n: v.detach().clone() for n, v in holder["model"].state_dict().items()}
+
+        def close(self):
+            pass
+
+    ref.tqdm = Bar
+
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="sivae_golden_")
+    os.chdir(tmp)
+    torch.set_num_threads(8)
+    try:
+        torch.randn = randn
+        kwargs = dict(dataset="cifar10", z_dim=z_dim, batch_size=batch, num_workers=0, num_epochs=1, num_vae=0,
+                      beta_kl=1.0, beta_neg=beta_neg, beta_rec=1.0, device=torch.device("cpu"), seed=seed,
+                      test_iter=10 ** 9, save_interval=50, start_epoch=0, lr_e=2e-4, lr_d=2e-4)
+        kwargs.update(extra_kwargs or {})
+        getattr(ref, fn_name)(**kwargs)
+    finally:
+        torch.randn = orig_randn
+        ref.optim.Adam = torch.optim.Adam
+        os.chdir(cwd)
+    with open(os.path.join(tmp, "soft_intro_train_graphs_data.pickle"), "rb") as fp:
+        graphs = pickle.load(fp)
+    model = holder["model"]
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert len(rec["grads"]) == 2, len(rec["grads"])
+    grads_e = {names[i]: g for i, g in rec["grads"][0].items() if g is not None}
+    grads_d = {names[i]: g for i, g in rec["grads"][1].items() if g is not None}
+    post = holder["post"]
+    # the first (batch, z) torch.randn call is noise_batch (:547); a second one happens at the end-of-run
+    # sample grid (:679) and is not part of the iteration.
+    out = dict(
+        arch=holder["arch"], batch=batch, seed=seed, data_seed=data_seed,
+        hyper=dict(beta_kl=1.0, beta_rec=1.0, beta_neg=float(beta_neg), gamma_r=float(kwargs.get("gamma_r", 1e-8 if "bootstrap" not in modname else 1.0)),
+                   scale=1.0 / (3 * 32 ** 2), lr_e=2e-4, lr_d=2e-4),
+        real=rec["real"], noise=rec["noise"][0], eps=rec["eps"][:5],
+        init=holder["init"], post=post, grads_e=grads_e, grads_d=grads_d,
+        scalars=dict(r_loss=rec["postfix"]["r_loss"], kl=rec["postfix"]["kl"], diff_kl=rec["postfix"]["diff_kl"],
+                     expelbo_f=rec["postfix"]["expelbo_f"],
+                     kl_real=float(graphs["kl_real"][0]), kl_fake=float(graphs["kl_fake"][0]),
+                     kl_rec=float(graphs["kl_rec"][0]), rec_err=float(graphs["rec_err"][0])),
+        torch_version=torch.__version__, threads=torch.get_num_threads(),
+        reference_commit="b6dbf16",
+    )
+    assert len(rec["eps"]) >= 5
+    return out
+
+
+def summarise(full):
+    """Large-config fixture: keep inputs that cannot be regenerated from a seed (noise, eps), the scalars, and
+    per-tensor fingerprints of init / grads / post-step state instead of the tensors themselves."""
+    def fp(d):
+        return {k: (float(v.double().sum()), float(v.double().abs().sum()), float(v.double().norm()))
+                for k, v in d.items() if v.is_floating_point()}
+    out = {k: full[k] for k in ("arch", "batch", "seed", "data_seed", "hyper", "real", "noise", "eps", "scalars",
+                                "torch_version", "threads", "reference_commit")}
+    out["init_fp"] = fp(full["init"])
+    out["post_fp"] = fp(full["post"])
+    out["grads_e_fp"] = fp(full["grads_e"])
+    out["grads_d_fp"] = fp(full["grads_d"])
+    out["nbt_post"] = {k: int(v) for k, v in full["post"].items() if k.endswith("num_batches_tracked")}
+    # a few full tensors that are small: fc biases and BN stats of the last encoder block
+    out["post_small"] = {k: v for k, v in full["post"].items() if v.numel() <= 512}
+    out["grads_small"] = {k: v for k, v in list(full["grads_e"].items()) + list(full["grads_d"].items()) if v.numel() <= 512}
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    tiny = dict(channels=[32, 64], image_size=16)
+    g = run_reference_iteration("soft_intro_vae", "train_soft_intro_vae", "train_soft_intro_vae",
+                                tiny=tiny, batch=8, z_dim=16, seed=0, beta_neg=256, image_size=16)
+    torch.save(g, os.path.join(OUT, "tiny_std.pt"))
+    print("tiny_std", g["scalars"])
+    g = run_reference_iteration("soft_intro_vae_bootstrap", "train_soft_intro_vae_bootstrap", "train_soft_intro_vae",
+                                tiny=tiny, batch=8, z_dim=16, seed=0, beta_neg=256, image_size=16,
+                                extra_kwargs=dict(gamma_r=1.0, copy_to_target_freq=1))
+    torch.save(g, os.path.join(OUT, "tiny_bootstrap.pt"))
+    print("tiny_bootstrap", g["scalars"])
+    g = run_reference_iteration("soft_intro_vae", "train_soft_intro_vae", "train_soft_intro_vae",
+                                tiny=None, batch=8, z_dim=128, seed=0, beta_neg=256, image_size=32)
+    torch.save(summarise(g), os.path.join(OUT, "cifar_std_summary.pt"))
+    print("cifar_std", g["scalars"])
+    for f in sorted(os.listdir(OUT)):
+        p = os.path.join(OUT, f)
+        print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:16])
+
+
+if __name__ == "__main__":
+    main()

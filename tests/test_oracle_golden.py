@@ -1,0 +1,88 @@
+"""Pins oracle/sivae_oracle.py (the CPU restatement) against outputs of the UNMODIFIED reference
+(tests/golden/*.pt, produced by oracle/make_golden.py from /root/reference in the build container)."""
+import os
+
+import pytest
+import torch
+
+from oracle import sivae_oracle as O
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _run(g, bootstrap):
+    torch.set_num_threads(g["threads"])
+    arch = O.Arch(**g["arch"])
+    sd = O.clone_sd(g["init"])
+    hp = O.Hyper(**g["hyper"])
+    st_e, st_d = O.AdamState(), O.AdamState()
+    scal, ge, gd, te, td = O.full_iteration(sd, arch, g["real"], g["noise"], g["eps"], hp, st_e, st_d, bootstrap)
+    return sd, scal, ge, gd
+
+
+def _relerr(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize("name,bootstrap", [("tiny_std.pt", False), ("tiny_bootstrap.pt", True)])
+def test_oracle_matches_reference_full(golden_dir, name, bootstrap):
+    g = _load(golden_dir, name)
+    sd, scal, ge, gd = _run(g, bootstrap)
+    s = g["scalars"]
+    # same ops, same thread count => agreement to fp32 round-off
+    assert scal["loss_rec"] == pytest.approx(s["rec_err"], rel=1e-6)
+    assert scal["lossE_real_kl"] == pytest.approx(s["kl_real"], rel=1e-6)
+    assert scal["lossD_fake_kl"] == pytest.approx(s["kl_fake"], rel=1e-6)
+    assert scal["lossD_rec_kl"] == pytest.approx(s["kl_rec"], rel=1e-6)
+    assert scal["expelbo_fake"] == pytest.approx(s["expelbo_f"], rel=1e-5)
+    assert set(ge) == set(g["grads_e"]) and set(gd) == set(g["grads_d"])
+    for k in ge:
+        assert _relerr(ge[k], g["grads_e"][k]) < 1e-5, k
+    for k in gd:
+        assert _relerr(gd[k], g["grads_d"][k]) < 1e-5, k
+    for k, v in g["post"].items():
+        if k.startswith("target_decoder") and not bootstrap:
+            continue
+        if v.is_floating_point():
+            assert torch.allclose(sd[k], v, rtol=1e-5, atol=1e-7), k
+        else:
+            assert int(sd[k]) == int(v), k      # num_batches_tracked: exact
+
+
+def test_make_state_dict_is_reference_init(golden_dir):
+    """index/shape work + RNG order: the oracle's own constructor reproduces the reference init bit-exactly."""
+    for name, boot in (("tiny_std.pt", False), ("tiny_bootstrap.pt", True)):
+        g = _load(golden_dir, name)
+        sd = O.make_state_dict(O.Arch(**g["arch"]), seed=g["seed"], bootstrap=boot)
+        assert list(sd.keys()) == list(g["init"].keys())
+        for k, v in g["init"].items():
+            assert sd[k].shape == v.shape and torch.equal(sd[k], v), k
+
+
+def test_oracle_matches_reference_cifar_summary(golden_dir):
+    g = _load(golden_dir, "cifar_std_summary.pt")
+    arch = O.Arch(**g["arch"])
+    sd = O.make_state_dict(arch, seed=g["seed"])
+    for k, (s, a, n) in g["init_fp"].items():
+        assert float(sd[k].double().sum()) == pytest.approx(s, rel=1e-12, abs=1e-12), k
+    torch.set_num_threads(g["threads"])
+    real = g["real"]
+    hp = O.Hyper(**g["hyper"])
+    scal, ge, gd, _, _ = O.full_iteration(sd, arch, real, g["noise"], g["eps"], hp, O.AdamState(), O.AdamState())
+    s = g["scalars"]
+    assert scal["loss_rec"] == pytest.approx(s["rec_err"], rel=1e-6)
+    assert scal["lossE_real_kl"] == pytest.approx(s["kl_real"], rel=1e-6)
+    assert scal["lossD_fake_kl"] == pytest.approx(s["kl_fake"], rel=1e-6)
+    assert scal["lossD_rec_kl"] == pytest.approx(s["kl_rec"], rel=1e-6)
+    assert scal["expelbo_fake"] == pytest.approx(s["expelbo_f"], rel=1e-5)
+    for k, (ssum, sabs, nrm) in g["grads_e_fp"].items():
+        assert float(ge[k].double().norm()) == pytest.approx(nrm, rel=1e-4), k
+    for k, (ssum, sabs, nrm) in g["grads_d_fp"].items():
+        assert float(gd[k].double().norm()) == pytest.approx(nrm, rel=1e-4), k
+    for k, v in g["nbt_post"].items():
+        assert int(sd[k]) == v, k
+    for k, v in g["post_small"].items():
+        if v.is_floating_point():
+            assert torch.allclose(sd[k], v, rtol=1e-4, atol=1e-6), k
