@@ -1,0 +1,147 @@
+/*
+ * sivae.h -- C ABI of the B200-native Soft-IntroVAE training engine (libsivae_b200.so).
+ *
+ * The reference (taldatech/soft-intro-vae-pytorch) has no native code and no FFI: its hot path is the
+ * Python function train_soft_intro_vae() calling torch.nn modules.  This header is therefore the
+ * boundary a maintainer would bind with ctypes from the reference's own module
+ * (see INTEGRATION.md); each entry point names the reference lines it replaces, relative to
+ * soft_intro_vae/train_soft_intro_vae.py unless stated otherwise.
+ *
+ * Conventions
+ *   - plain C types only; all tensor arguments are raw DEVICE pointers (fp32 unless noted) owned by the
+ *     caller (torch allocations on the Python side).  The library never allocates or frees caller
+ *     memory; its scratch lives in the caller-provided workspace (sivae_bind_workspace).
+ *   - every function returns 0 on success, <0 for an engine error, >0 for a cudaError_t; the text is
+ *     available from sivae_last_error().  No C++ exception crosses the boundary.
+ *   - all work is enqueued on the caller's stream (void* = cudaStream_t); nothing synchronises except
+ *     where stated.  One engine per GPU/process; an engine is not thread-safe.
+ *   - image tensors at the boundary are NCHW like the reference; inside the engine everything is NHWC.
+ *   - net ids: 0 = encoder, 1 = decoder, 2 = target decoder (bootstrap variant only).
+ */
+#ifndef SIVAE_H_
+#define SIVAE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sivae_engine sivae_engine;
+
+enum { SIVAE_NET_ENCODER = 0, SIVAE_NET_DECODER = 1, SIVAE_NET_TARGET = 2 };
+enum { SIVAE_CONV_AUTO = 0, SIVAE_CONV_SIMT = 1, SIVAE_CONV_TCGEN05 = 2 };
+enum { SIVAE_T_CONV = 0, SIVAE_T_BN_WEIGHT = 1, SIVAE_T_BN_BIAS = 2, SIVAE_T_LINEAR = 3, SIVAE_T_BIAS = 4 };
+
+/* SoftIntroVAE(cdim, zdim, channels, image_size) -- ctor :173-184; Encoder :79-109; Decoder :126-159 */
+typedef struct {
+  int cdim, zdim, image_size, n_channels;
+  int channels[16];
+  int max_batch;     /* largest batch the workspace is sized for */
+  int variant;       /* 0 = standard, 1 = bootstrap (soft_intro_vae_bootstrap/...:192-217) */
+  int conv_backend;  /* SIVAE_CONV_* */
+} sivae_config;
+
+/* beta_kl, beta_rec, beta_neg, gamma_r kwargs (:340-341) and scale = 1/(ch*image_size^2) (:456) */
+typedef struct { float beta_kl, beta_rec, beta_neg, gamma_r, scale; } sivae_hyper;
+
+/* One parameter tensor, in the reference's registration (= state_dict / optimiser) order. */
+typedef struct {
+  char name[96];        /* key relative to the net prefix, e.g. "main.res_in_16.conv1.weight" */
+  int kind;             /* SIVAE_T_* */
+  long long offset;     /* in floats, into the net's flat parameter buffer */
+  long long numel;
+  int shape[4];         /* logical (reference) shape: conv [Cout,Cin,kh,kw] (memory order Cout,kh,kw,Cin =
+                           torch.channels_last), linear [out,in], vectors [C] */
+  int ndim;
+} sivae_tensor_info;
+
+/* One BatchNorm2d: running_mean at bn_offset, running_var at bn_offset + channels (flat float buffer),
+   num_batches_tracked at index `index` of the int64 buffer. */
+typedef struct { char name[96]; int channels; long long bn_offset; int index; } sivae_bn_info;
+
+const char* sivae_last_error(void);
+int sivae_version(void);
+
+/* model construction (:442) */
+int sivae_create(const sivae_config* cfg, sivae_engine** out);
+void sivae_destroy(sivae_engine* e);
+int sivae_num_tensors(const sivae_engine* e, int net);
+int sivae_tensor(const sivae_engine* e, int net, int i, sivae_tensor_info* out);
+long long sivae_param_count(const sivae_engine* e, int net);
+int sivae_num_bn(const sivae_engine* e, int net);
+int sivae_bn(const sivae_engine* e, int net, int i, sivae_bn_info* out);
+long long sivae_bn_floats(const sivae_engine* e, int net);
+long long sivae_workspace_bytes(const sivae_engine* e);
+
+/* memory hand-over: flat fp32 buffers of sivae_param_count floats each (params, grads, Adam m, Adam v),
+   BN running stats (sivae_bn_floats floats) and num_batches_tracked (int64[sivae_num_bn]).
+   grads/m/v may be NULL for a net that is never optimised (target decoder). */
+int sivae_bind_net(sivae_engine* e, int net, float* params, float* grads, float* adam_m, float* adam_v,
+                   float* bn_running, long long* bn_nbt);
+int sivae_bind_workspace(sivae_engine* e, void* ws, long long bytes);
+/* tell the engine that parameters of `net` were modified by the caller (load_state_dict, target copy) so
+   derived operand copies (tf32-rounded / transposed filters) are refreshed before next use */
+int sivae_params_changed(sivae_engine* e, int net);
+
+/* Update-E half of the introspective iteration (:551-588): all forwards, the loss and the backward that
+   fills the encoder's flat grad buffer.  real: [B,cdim,S,S] NCHW; noise: [B,z] (:547); eps: [3,B,z] the
+   reparameterisation draws in the order of :560,:567,:568.  stats (device, 16 floats) receives
+   [0]=loss_rec [1]=lossE_real_kl [2]=expelbo_rec [3]=expelbo_fake [4]=lossE [15]=nan flag. */
+int sivae_e_step(sivae_engine* e, const float* real_nchw, const float* noise, const float* eps, int batch,
+                 const sivae_hyper* hp, float* stats, void* stream);
+/* Update-D half (:591-623); reuses real, noise and z of the preceding sivae_e_step (:597-598).
+   eps: [2,B,z] (:602,:605).  stats[5]=loss_rec [6]=lossD_rec_kl [7]=lossD_fake_kl [8]=loss_rec_rec
+   [9]=loss_fake_rec [10]=lossD [15]=nan flag (the isnan guard of :625). */
+int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper* hp, float* stats, void* stream);
+/* vanilla VAE warm-up step (:512-536): grads of encoder AND decoder. eps: [B,z].
+   stats[11]=loss_rec [12]=loss_kl [13]=loss */
+int sivae_vae_step(sivae_engine* e, const float* real_nchw, const float* eps, int batch, const sivae_hyper* hp,
+                   float* stats, void* stream);
+/* optim.Adam.step (:450-451, :589, :624): p -= lr/bc1 * m/(sqrt(v)/sqrt(bc2)+1e-8) on the flat buffers with
+   g = grad*grad_scale (grad_scale = 1/world_size after the NCCL all-reduce). Keeps its own step counter. */
+int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_scale, void* stream);
+int sivae_adam_set_step(sivae_engine* e, int net, long long step);
+long long sivae_adam_get_step(const sivae_engine* e, int net);
+
+/* model.encode / model.decode / model.sample (:203-223): mu, logvar: [B,z]; out: [B,cdim,S,S] NCHW.
+   train != 0 uses batch statistics and moves the running stats like the reference in model.train(). */
+int sivae_encode(sivae_engine* e, const float* x_nchw, int batch, float* mu, float* logvar, int train, void* stream);
+int sivae_decode(sivae_engine* e, int net, const float* z, int batch, float* out_nchw, int train, void* stream);
+
+/* decoder outputs of the last half step as NCHW [B,cdim,S,S]: slot 0 = fake, 1 = rec, 2 = rec_rec, 3 = rec_fake
+   (what the reference keeps in the Python variables of the same names, used for the sample grid :641-646) */
+int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void* stream);
+int sivae_last_batch(const sivae_engine* e);
+
+/* ---- single-kernel entry points (unit parity tests; NHWC activations, [Cout][kh][kw][Cin] filters) ---- */
+/* nn.Conv2d(k, stride 1, pad k/2) forward (:51,56,60,89,159); bias/addend may be NULL; y = conv + bias + addend */
+int sivae_conv2d_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,
+                     int N, int H, int W, int Cin, int Cout, int ksize, int backend, void* stream);
+/* dgrad of the same conv: dx = conv_transpose(dy, w) + addend */
+int sivae_conv2d_dgrad(const float* dy, const float* w, const float* addend, float* dx,
+                       int N, int H, int W, int Cin, int Cout, int ksize, int backend, void* workspace,
+                       long long ws_bytes, void* stream);
+/* wgrad: dw (+)= sum_pixels dy (x) x ; accumulate != 0 adds to dw */
+int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                       int ksize, int accumulate, int backend, void* workspace, long long ws_bytes, void* stream);
+/* train-mode BatchNorm2d + LeakyReLU(0.2) [+ residual add] [+ AvgPool2d(2) | nearest x2] (:65-75, :90-92,98,155)
+   mode 0 none, 1 pool, 2 upsample.  Writes mean/invstd (2*C floats) and updates running stats. */
+int sivae_bn_act_fwd(const float* t, const float* identity, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, long long* nbt, float* mean_invstd, float* out,
+                     int N, int H, int W, int C, int mode, int train, void* workspace, long long ws_bytes, void* stream);
+/* its backward: dt (and g = grad w.r.t. the identity branch, may be NULL), dgamma/dbeta (may be NULL) */
+int sivae_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* gamma, const float* beta,
+                     const float* mean_invstd, float* dt, float* g, float* dgamma, float* dbeta, int accumulate,
+                     int N, int H, int W, int C, int mode, void* workspace, long long ws_bytes, void* stream);
+/* fused loss pass (:563-586 / :599-620): per-sample squared-error sums of (rec-real), (rec_rec-rec),
+   (rec_fake-fake) in one read of the five images; out: [B,3] */
+int sivae_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
+               float* out, int batch, long long per_sample, void* workspace, long long ws_bytes, void* stream);
+/* calc_kl(reduce='none') (:231-251) and reparameterize (:254-265) on [B,2z] encoder outputs */
+int sivae_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int batch, int zdim, void* stream);
+int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
+                    long long step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIVAE_H_ */

@@ -1,0 +1,876 @@
+// Native runtime of the Soft-IntroVAE step: model description (parameter / buffer layout in the reference's
+// registration order), workspace carving, the forward / hand-written backward traversal of encoder and decoder
+// passes, the E-step / D-step / VAE-step graphs of train_soft_intro_vae.py:512-624 and the C ABI (include/sivae.h).
+#include "../../include/sivae.h"
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sivae;
+
+static thread_local std::string g_err;
+extern "C" const char* sivae_last_error(void) { return g_err.c_str(); }
+extern "C" int sivae_version(void) { return 100; }
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CHECK_CUDA_RET()                                                             \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) return fail((int)_e, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+namespace {
+
+struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1; };
+struct Bn { int c = 0; long long g_off = -1, b_off = -1, rm_off = -1; int idx = -1; };
+struct Lin { int fin = 0, fout = 0; long long w_off = -1, b_off = -1; };
+struct Block { int inc = 0, outc = 0, size = 0, mode = RS_NONE; bool expand = false; Conv ce, c1, c2; Bn bn1, bn2; };
+
+struct Net {
+  int id = 0;
+  bool enc = false;
+  Conv stem; Bn stem_bn;    // encoder only
+  Conv predict;             // decoder only
+  Lin fc;
+  std::vector<Block> blocks;
+  std::vector<sivae_tensor_info> tinfo;
+  std::vector<sivae_bn_info> binfo;
+  long long n_params = 0, bn_floats = 0, derived_floats = 0;
+  float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *bn = nullptr, *derived = nullptr;
+  long long* nbt = nullptr;
+  bool dirty = true;
+  long long adam_step = 0;
+  bool present = false;
+};
+
+struct BlockAct { float *id = nullptr, *t1 = nullptr, *a1 = nullptr, *t2 = nullptr, *out = nullptr, *mi1 = nullptr, *mi2 = nullptr; const float* x = nullptr; };
+struct EncPass {
+  const float* img = nullptr;
+  float *t0 = nullptr, *mi0 = nullptr, *a0 = nullptr, *feat = nullptr, *ml = nullptr, *z = nullptr, *kl = nullptr;
+  std::vector<BlockAct> blk;
+};
+struct DecPass {
+  const float* zin = nullptr;
+  float *h = nullptr, *x0 = nullptr, *y = nullptr;
+  std::vector<BlockAct> blk;
+};
+
+struct Bump {
+  char* base = nullptr; size_t off = 0;
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+struct sivae_engine {
+  sivae_config cfg;
+  Net nets[3];
+  int C_last = 0, hw_last = 0;     // conv_output_size = (C_last, hw_last, hw_last)
+  long long feat = 0;              // C_last*hw_last^2
+  bool tc = false;                 // tcgen05 backend in use (activations pre-rounded to tf32)
+  // workspace
+  void* ws = nullptr; size_t ws_bytes = 0, ws_need = 0;
+  EncPass ep[3]; DecPass dp[4];
+  float *real = nullptr, *noise = nullptr, *z_keep = nullptr;
+  float* sb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // backward scratch, max activation size each
+  float *d_rec = nullptr, *d_rec_rec = nullptr, *d_rec_fake = nullptr, *d_fake = nullptr;
+  float *dml = nullptr, *dz = nullptr, *dfeat = nullptr, *dfeat2 = nullptr, *coef = nullptr, *ckl_a = nullptr, *ckl_b = nullptr, *mse = nullptr;
+  float *out_tmp = nullptr;
+  void* red = nullptr; size_t red_bytes = 0;
+  int cur_batch = 0;
+  bool have_e_state = false;
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// model description
+// -------------------------------------------------------------------------------------------------------------
+static void add_tensor(Net& n, const std::string& name, int kind, long long numel, std::initializer_list<int> shape, long long* off_out) {
+  sivae_tensor_info ti;
+  memset(&ti, 0, sizeof(ti));
+  snprintf(ti.name, sizeof(ti.name), "%s", name.c_str());
+  ti.kind = kind;
+  ti.offset = n.n_params;
+  ti.numel = numel;
+  ti.ndim = (int)shape.size();
+  int i = 0;
+  for (int s : shape) ti.shape[i++] = s;
+  *off_out = n.n_params;
+  // keep every tensor 16-byte aligned in the flat buffer (float4 kernels, TMA): round sizes up to 4 floats
+  n.n_params += (numel + 3) / 4 * 4;
+  n.tinfo.push_back(ti);
+}
+static void add_conv(Net& n, const std::string& name, Conv& c, int cin, int cout, int k, bool bias) {
+  c.cin = cin; c.cout = cout; c.k = k;
+  add_tensor(n, name + ".weight", SIVAE_T_CONV, (long long)cout * cin * k * k, {cout, cin, k, k}, &c.w_off);
+  if (bias) add_tensor(n, name + ".bias", SIVAE_T_BIAS, cout, {cout}, &c.b_off);
+  c.wd_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
+  c.wr_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
+}
+static void add_bn(Net& n, const std::string& name, Bn& b, int c) {
+  b.c = c;
+  add_tensor(n, name + ".weight", SIVAE_T_BN_WEIGHT, c, {c}, &b.g_off);
+  add_tensor(n, name + ".bias", SIVAE_T_BN_BIAS, c, {c}, &b.b_off);
+  sivae_bn_info bi;
+  memset(&bi, 0, sizeof(bi));
+  snprintf(bi.name, sizeof(bi.name), "%s", name.c_str());
+  bi.channels = c;
+  bi.bn_offset = n.bn_floats;
+  bi.index = (int)n.binfo.size();
+  b.rm_off = n.bn_floats;
+  b.idx = bi.index;
+  n.bn_floats += 2LL * c;
+  n.binfo.push_back(bi);
+}
+static void add_block(Net& n, const std::string& p, Block& b, int inc, int outc, int size, int mode) {
+  b.inc = inc; b.outc = outc; b.size = size; b.mode = mode; b.expand = inc != outc;
+  if (b.expand) add_conv(n, p + ".conv_expand", b.ce, inc, outc, 1, false);
+  add_conv(n, p + ".conv1", b.c1, inc, outc, 3, false);
+  add_bn(n, p + ".bn1", b.bn1, outc);
+  add_conv(n, p + ".conv2", b.c2, outc, outc, 3, false);
+  add_bn(n, p + ".bn2", b.bn2, outc);
+}
+static void add_lin(Net& n, const std::string& name, Lin& l, int fin, int fout) {
+  l.fin = fin; l.fout = fout;
+  add_tensor(n, name + ".weight", SIVAE_T_LINEAR, (long long)fin * fout, {fout, fin}, &l.w_off);
+  add_tensor(n, name + ".bias", SIVAE_T_BIAS, fout, {fout}, &l.b_off);
+}
+
+// Encoder.__init__ (:79-109) -- same module order, names `res_in_{sz}`
+static void build_encoder(sivae_engine* e, Net& n) {
+  const sivae_config& c = e->cfg;
+  n.enc = true; n.present = true;
+  int cc = c.channels[0];
+  add_conv(n, "main.0", n.stem, c.cdim, cc, 5, false);
+  add_bn(n, "main.1", n.stem_bn, cc);
+  int sz = c.image_size / 2;
+  for (int i = 1; i < c.n_channels; ++i) {
+    Block b;
+    add_block(n, "main.res_in_" + std::to_string(sz), b, cc, c.channels[i], sz, RS_POOL);
+    n.blocks.push_back(b);
+    cc = c.channels[i]; sz /= 2;
+  }
+  Block b;
+  add_block(n, "main.res_in_" + std::to_string(sz), b, cc, cc, sz, RS_NONE);
+  n.blocks.push_back(b);
+  e->C_last = cc; e->hw_last = sz; e->feat = (long long)cc * sz * sz;
+  add_lin(n, "fc", n.fc, (int)e->feat, 2 * c.zdim);
+}
+// Decoder.__init__ (:126-159) -- names count from 4, real size starts at conv_output_size
+static void build_decoder(sivae_engine* e, Net& n) {
+  const sivae_config& c = e->cfg;
+  n.enc = false; n.present = true;
+  add_lin(n, "fc.0", n.fc, c.zdim, (int)e->feat);
+  int cc = c.channels[c.n_channels - 1];
+  int name_sz = 4, real = e->hw_last;
+  for (int i = c.n_channels - 1; i >= 0; --i) {
+    Block b;
+    add_block(n, "main.res_in_" + std::to_string(name_sz), b, cc, c.channels[i], real, RS_UP);
+    n.blocks.push_back(b);
+    cc = c.channels[i]; name_sz *= 2; real *= 2;
+  }
+  Block b;
+  add_block(n, "main.res_in_" + std::to_string(name_sz), b, cc, cc, real, RS_NONE);
+  n.blocks.push_back(b);
+  add_conv(n, "main.predict", n.predict, cc, c.cdim, 5, true);
+}
+
+static long long max_act_elems(const sivae_engine* e) {
+  const sivae_config& c = e->cfg;
+  long long B = c.max_batch, S = c.image_size;
+  long long m = B * S * S * c.channels[0];
+  for (int ni = 0; ni < 2; ++ni)
+    for (const Block& b : e->nets[ni].blocks) {
+      long long v = B * b.size * b.size * (long long)(b.outc > b.inc ? b.outc : b.inc);
+      if (b.mode == RS_UP) v = B * 4LL * b.size * b.size * b.outc;
+      if (v > m) m = v;
+    }
+  return m;
+}
+
+static size_t reduce_scratch_bytes(const sivae_engine* e) {
+  const sivae_config& c = e->cfg;
+  long long B = c.max_batch, S = c.image_size;
+  size_t m = bn_scratch_bytes(B * S * S, c.channels[0]);
+  size_t v = mse3_scratch_bytes((int)B, (long long)c.cdim * S * S);
+  if (v > m) m = v;
+  auto upd_conv = [&](const Conv& cv, int size) {
+    if (cv.k == 0) return;
+    ConvShape s{(int)B, size, size, cv.cin, cv.cout, cv.k};
+    size_t a = conv_wgrad_simt_scratch_bytes(s);
+    if (a > m) m = a;
+    if (conv_tc_supported_wgrad(s)) { size_t t = conv_wgrad_tc_scratch_bytes(s); if (t > m) m = t; }
+  };
+  for (int ni = 0; ni < 2; ++ni) {
+    const Net& n = e->nets[ni];
+    for (const Block& b : n.blocks) {
+      size_t a = bn_scratch_bytes(B * b.size * b.size, b.outc);
+      if (a > m) m = a;
+      upd_conv(b.ce, b.size); upd_conv(b.c1, b.size); upd_conv(b.c2, b.size);
+    }
+  }
+  upd_conv(e->nets[0].stem, (int)S);
+  upd_conv(e->nets[1].predict, (int)S);
+  return m;
+}
+
+// carve the workspace; with base == nullptr only computes the size
+static size_t carve(sivae_engine* e, char* base) {
+  const sivae_config& c = e->cfg;
+  Bump bp; bp.base = base;
+  const long long B = c.max_batch, S = c.image_size, z = c.zdim;
+  for (int ni = 0; ni < 3; ++ni)
+    if (e->nets[ni].present) e->nets[ni].derived = bp.take<float>(e->nets[ni].derived_floats);
+  e->real = bp.take<float>(B * S * S * c.cdim);
+  e->noise = bp.take<float>(B * z);
+  e->z_keep = bp.take<float>(B * z);
+  const Net& en = e->nets[0];
+  const Net& dn = e->nets[1];
+  for (int s = 0; s < 3; ++s) {
+    EncPass& p = e->ep[s];
+    p.t0 = bp.take<float>(B * S * S * c.channels[0]);
+    p.mi0 = bp.take<float>(2 * c.channels[0]);
+    p.a0 = bp.take<float>(B * (S / 2) * (S / 2) * c.channels[0]);
+    p.blk.assign(en.blocks.size(), BlockAct());
+    for (size_t i = 0; i < en.blocks.size(); ++i) {
+      const Block& b = en.blocks[i];
+      long long full = B * b.size * b.size * b.outc;
+      long long os = b.mode == RS_POOL ? b.size / 2 : b.size;
+      BlockAct& a = p.blk[i];
+      if (b.expand) a.id = bp.take<float>(full);
+      a.t1 = bp.take<float>(full); a.a1 = bp.take<float>(full); a.t2 = bp.take<float>(full);
+      a.out = bp.take<float>(B * os * os * b.outc);
+      a.mi1 = bp.take<float>(2 * b.outc); a.mi2 = bp.take<float>(2 * b.outc);
+    }
+    p.feat = bp.take<float>(B * e->feat);
+    p.ml = bp.take<float>(B * 2 * z);
+    p.z = bp.take<float>(B * z);
+    p.kl = bp.take<float>(B);
+  }
+  for (int s = 0; s < 4; ++s) {
+    DecPass& p = e->dp[s];
+    p.h = bp.take<float>(B * e->feat);
+    p.x0 = bp.take<float>(B * e->feat);
+    p.blk.assign(dn.blocks.size(), BlockAct());
+    for (size_t i = 0; i < dn.blocks.size(); ++i) {
+      const Block& b = dn.blocks[i];
+      long long full = B * b.size * b.size * b.outc;
+      long long os = b.mode == RS_UP ? b.size * 2 : b.size;
+      BlockAct& a = p.blk[i];
+      if (b.expand) a.id = bp.take<float>(full);
+      a.t1 = bp.take<float>(full); a.a1 = bp.take<float>(full); a.t2 = bp.take<float>(full);
+      a.out = bp.take<float>(B * os * os * b.outc);
+      a.mi1 = bp.take<float>(2 * b.outc); a.mi2 = bp.take<float>(2 * b.outc);
+    }
+    p.y = bp.take<float>(B * S * S * c.cdim);
+  }
+  long long ma = max_act_elems(e);
+  for (int i = 0; i < 5; ++i) e->sb[i] = bp.take<float>(ma);
+  long long img = B * S * S * c.cdim;
+  e->d_rec = bp.take<float>(img); e->d_rec_rec = bp.take<float>(img); e->d_rec_fake = bp.take<float>(img); e->d_fake = bp.take<float>(img);
+  e->out_tmp = bp.take<float>(img);
+  e->dml = bp.take<float>(B * 2 * z); e->dz = bp.take<float>(B * z);
+  e->dfeat = bp.take<float>(B * e->feat); e->dfeat2 = bp.take<float>(B * e->feat);
+  e->coef = bp.take<float>(4 * B); e->ckl_a = bp.take<float>(B); e->ckl_b = bp.take<float>(B); e->mse = bp.take<float>(3 * B);
+  e->red_bytes = reduce_scratch_bytes(e);
+  e->red = bp.take<char>(e->red_bytes);
+  return bp.off + 256;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// conv dispatch
+// -------------------------------------------------------------------------------------------------------------
+static bool use_tc(const sivae_engine* e, const ConvShape& s) {
+  return e->tc && conv_tc_supported_fwd(s);
+}
+static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
+  if (!n.dirty) return 0;
+  auto one = [&](const Conv& c) {
+    if (c.k == 0) return;
+    // dgrad filters (as a forward conv over dy): rounded to tf32 when the tcgen05 path consumes them
+    launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, e->tc, st);
+    if (e->tc) launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, (long long)c.cout * c.cin * c.k * c.k, st);
+  };
+  if (n.enc) one(n.stem); else one(n.predict);
+  for (const Block& b : n.blocks) { one(b.ce); one(b.c1); one(b.c2); }
+  n.dirty = false;
+  CHECK_CUDA_RET();
+  return 0;
+}
+// y = conv(x, W) (+bias) (+addend)
+static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, float* y, const float* addend, int B, int size, cudaStream_t st) {
+  ConvShape s{B, size, size, c.cin, c.cout, c.k};
+  const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
+  if (use_tc(e, s)) {
+    int r = launch_conv_fwd_tc(x, n.derived + c.wr_off, bias, addend, y, s, st);
+    if (r) return fail(r, "tcgen05 conv fwd launch failed");
+  } else {
+    launch_conv_fwd_simt(x, n.params + c.w_off, bias, addend, y, s, st);
+  }
+  return 0;
+}
+// dx = conv_transpose(dy, W) (+addend): a forward conv over dy with the packed dgrad filters
+static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
+  ConvShape s{B, size, size, c.cout, c.cin, c.k};
+  if (use_tc(e, s)) {
+    int r = launch_conv_fwd_tc(dy, n.derived + c.wd_off, nullptr, addend, dx, s, st);
+    if (r) return fail(r, "tcgen05 conv dgrad launch failed");
+  } else {
+    launch_conv_fwd_simt(dy, n.derived + c.wd_off, nullptr, addend, dx, s, st);
+  }
+  return 0;
+}
+static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
+  ConvShape s{B, size, size, c.cin, c.cout, c.k};
+  if (e->tc && conv_tc_supported_wgrad(s)) {
+    int r = launch_conv_wgrad_tc(x, dy, n.grads + c.w_off, s, true, e->red, e->red_bytes, st);
+    if (r) return fail(r, "tcgen05 conv wgrad launch failed");
+  } else {
+    launch_conv_wgrad_simt(x, dy, n.grads + c.w_off, s, true, e->red, e->red_bytes, st);
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// forward passes
+// -------------------------------------------------------------------------------------------------------------
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+static int bn_forward_stats(sivae_engine* e, Net& n, const Bn& bn, const float* t, long long rows, float* mi, bool train, cudaStream_t st) {
+  if (train)
+    launch_bn_stats(t, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, e->red, e->red_bytes, st);
+  else
+    launch_bn_eval_stats(n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, bn.c, mi, st);
+  return 0;
+}
+
+// ResidualBlock.forward (:65-75) + the AvgPool2d / Upsample that follows it in `main` (:98,155)
+static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* x, int B, bool train, cudaStream_t st) {
+  a.x = x;
+  const int s = b.size;
+  const long long rows = (long long)B * s * s;
+  const float* idn = x;
+  if (b.expand) { TRY(conv_fwd(e, n, b.ce, x, a.id, nullptr, B, s, st)); idn = a.id; }
+  TRY(conv_fwd(e, n, b.c1, x, a.t1, nullptr, B, s, st));
+  bn_forward_stats(e, n, b.bn1, a.t1, rows, a.mi1, train, st);
+  launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->tc, st);
+  TRY(conv_fwd(e, n, b.c2, a.a1, a.t2, nullptr, B, s, st));
+  bn_forward_stats(e, n, b.bn2, a.t2, rows, a.mi2, train, st);
+  launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->tc, st);
+  return 0;
+}
+
+// Encoder.forward (:116-122): img is NHWC [B,S,S,cdim]; result p.ml = [B,2z] (mu | logvar)
+static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, int B, bool train, cudaStream_t st) {
+  const sivae_config& c = e->cfg;
+  const int S = c.image_size;
+  p.img = img;
+  TRY(conv_fwd(e, n, n.stem, img, p.t0, nullptr, B, S, st));
+  bn_forward_stats(e, n, n.stem_bn, p.t0, (long long)B * S * S, p.mi0, train, st);
+  launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->tc, st);
+  const float* x = p.a0;
+  for (size_t i = 0; i < n.blocks.size(); ++i) {
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
+    x = p.blk[i].out;
+  }
+  // .view(B, -1) of the NCHW tensor (:117)
+  launch_nhwc_to_nchw(x, p.feat, B, e->C_last, e->hw_last, e->hw_last, st);
+  launch_linear_fwd(p.feat, n.params + n.fc.w_off, n.params + n.fc.b_off, p.ml, B, n.fc.fin, n.fc.fout, false, st);
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+// Decoder.forward (:161-169): z [B,zdim] -> p.y NHWC [B,S,S,cdim]
+static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int B, bool train, cudaStream_t st) {
+  const sivae_config& c = e->cfg;
+  p.zin = z;
+  launch_linear_fwd(z, n.params + n.fc.w_off, n.params + n.fc.b_off, p.h, B, n.fc.fin, n.fc.fout, true, st);
+  launch_nchw_to_nhwc(p.h, p.x0, B, e->C_last, e->hw_last, e->hw_last, st);
+  if (e->tc) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
+  const float* x = p.x0;
+  for (size_t i = 0; i < n.blocks.size(); ++i) {
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
+    x = p.blk[i].out;
+  }
+  TRY(conv_fwd(e, n, n.predict, x, p.y, nullptr, B, c.image_size, st));
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// backward passes (hand-written autograd of the above; dgrad-only when wgrad == false)
+// -------------------------------------------------------------------------------------------------------------
+// dout: gradient w.r.t. the block's (resampled) output; writes the gradient w.r.t. the block input into dx
+static int block_backward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* dout, float* dx, bool wgrad, int B, cudaStream_t st) {
+  const int s = b.size;
+  float* DT = e->sb[2];
+  float* G2 = e->sb[3];
+  float* DA1 = e->sb[4];
+  const float* idn = b.expand ? a.id : a.x;
+  float* g = n.grads;
+  launch_bn_act_bwd(dout, a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, DT, G2,
+                    wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->tc,
+                    e->red, e->red_bytes, st);
+  if (wgrad) TRY(conv_wgrad(e, n, b.c2, a.a1, DT, B, s, st));
+  TRY(conv_dgrad(e, n, b.c2, DT, DA1, nullptr, B, s, st));
+  launch_bn_act_bwd(DA1, a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, DT, nullptr,
+                    wgrad ? g + b.bn1.g_off : nullptr, wgrad ? g + b.bn1.b_off : nullptr, true, B, s, s, b.outc, RS_NONE, e->tc,
+                    e->red, e->red_bytes, st);
+  if (wgrad) {
+    TRY(conv_wgrad(e, n, b.c1, a.x, DT, B, s, st));
+    if (b.expand) TRY(conv_wgrad(e, n, b.ce, a.x, G2, B, s, st));
+  }
+  if (b.expand) {
+    TRY(conv_dgrad(e, n, b.c1, DT, dx, nullptr, B, s, st));
+    TRY(conv_dgrad(e, n, b.ce, G2, dx, dx, B, s, st));
+  } else {
+    TRY(conv_dgrad(e, n, b.c1, DT, dx, G2, B, s, st));
+  }
+  return 0;
+}
+
+// dml: gradient w.r.t. the fc output [B,2z].  d_img (nullable): receives d loss / d input image (NHWC), plus
+// d_img_addend if given (may alias d_img).
+static int enc_backward(sivae_engine* e, Net& n, EncPass& p, const float* dml, bool wgrad, float* d_img, const float* d_img_addend, int B, cudaStream_t st) {
+  const sivae_config& c = e->cfg;
+  const int S = c.image_size;
+  if (wgrad) launch_linear_wgrad(p.feat, dml, n.grads + n.fc.w_off, n.grads + n.fc.b_off, B, n.fc.fin, n.fc.fout, true, st);
+  launch_linear_dgrad(dml, n.params + n.fc.w_off, e->dfeat, B, n.fc.fin, n.fc.fout, st);
+  float* cur = e->sb[0];
+  float* nxt = e->sb[1];
+  launch_nchw_to_nhwc(e->dfeat, cur, B, e->C_last, e->hw_last, e->hw_last, st);
+  for (int i = (int)n.blocks.size() - 1; i >= 0; --i) {
+    TRY(block_backward(e, n, n.blocks[i], p.blk[i], cur, nxt, wgrad, B, st));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // stem: conv5x5 + BN + LeakyReLU + AvgPool (:89-92)
+  float* DT = e->sb[2];
+  launch_bn_act_bwd(cur, p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, DT, nullptr,
+                    wgrad ? n.grads + n.stem_bn.g_off : nullptr, wgrad ? n.grads + n.stem_bn.b_off : nullptr, true, B, S, S,
+                    n.stem.cout, RS_POOL, e->tc, e->red, e->red_bytes, st);
+  if (wgrad) TRY(conv_wgrad(e, n, n.stem, p.img, DT, B, S, st));
+  if (d_img) TRY(conv_dgrad(e, n, n.stem, DT, d_img, d_img_addend, B, S, st));
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+// dy: gradient w.r.t. the decoder output (NHWC).  dz (nullable): gradient w.r.t. the latent input.
+static int dec_backward(sivae_engine* e, Net& n, DecPass& p, const float* dy, bool wgrad, float* dz, int B, cudaStream_t st) {
+  const sivae_config& c = e->cfg;
+  const int S = c.image_size;
+  float* cur = e->sb[0];
+  float* nxt = e->sb[1];
+  const float* xlast = p.blk.back().out;
+  if (wgrad) {
+    launch_colsum(dy, n.grads + n.predict.b_off, (long long)B * S * S, c.cdim, true, st);
+    TRY(conv_wgrad(e, n, n.predict, xlast, dy, B, S, st));
+  }
+  TRY(conv_dgrad(e, n, n.predict, dy, cur, nullptr, B, S, st));
+  for (int i = (int)n.blocks.size() - 1; i >= 0; --i) {
+    TRY(block_backward(e, n, n.blocks[i], p.blk[i], cur, nxt, wgrad, B, st));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // view + ReLU + fc (:146-147, :166-167)
+  launch_nhwc_to_nchw(cur, e->dfeat2, B, e->C_last, e->hw_last, e->hw_last, st);
+  launch_relu_bwd(p.h, e->dfeat2, (long long)B * e->feat, st);
+  if (wgrad) launch_linear_wgrad(p.zin, e->dfeat2, n.grads + n.fc.w_off, n.grads + n.fc.b_off, B, n.fc.fin, n.fc.fout, true, st);
+  if (dz) launch_linear_dgrad(e->dfeat2, n.params + n.fc.w_off, dz, B, n.fc.fin, n.fc.fout, st);
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------------------
+extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  if (cfg->n_channels < 1 || cfg->n_channels > 16) return fail(-2, "n_channels must be in [1,16]");
+  if (cfg->cdim < 1 || cfg->zdim < 1 || cfg->max_batch < 1) return fail(-2, "bad cdim/zdim/max_batch");
+  int S = cfg->image_size;
+  if (S < 2 || (S % (1 << cfg->n_channels)) != 0) return fail(-2, "image_size must be divisible by 2^len(channels)");
+  for (int i = 0; i < cfg->n_channels; ++i)
+    if (cfg->channels[i] < 4 || cfg->channels[i] % 4 != 0 || cfg->channels[i] > 1024) return fail(-2, "channels must be multiples of 4 in [4,1024]");
+  if ((cfg->cdim * S * S) % 4 != 0) return fail(-2, "cdim*image_size^2 must be a multiple of 4");
+  sivae_engine* e = new sivae_engine();
+  e->cfg = *cfg;
+  for (int i = 0; i < 3; ++i) e->nets[i].id = i;
+  build_encoder(e, e->nets[0]);
+  build_decoder(e, e->nets[1]);
+  if (cfg->variant == 1) build_decoder(e, e->nets[2]);
+  e->tc = cfg->conv_backend != SIVAE_CONV_SIMT;
+  e->ws_need = carve(e, nullptr);
+  *out = e;
+  return 0;
+}
+extern "C" void sivae_destroy(sivae_engine* e) { delete e; }
+static Net* get_net(sivae_engine* e, int net) {
+  if (!e || net < 0 || net > 2 || !e->nets[net].present) return nullptr;
+  return &e->nets[net];
+}
+extern "C" int sivae_num_tensors(const sivae_engine* e, int net) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  return n ? (int)n->tinfo.size() : -1;
+}
+extern "C" int sivae_tensor(const sivae_engine* e, int net, int i, sivae_tensor_info* out) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  if (!n || i < 0 || i >= (int)n->tinfo.size() || !out) return fail(-1, "bad tensor index");
+  *out = n->tinfo[i];
+  return 0;
+}
+extern "C" long long sivae_param_count(const sivae_engine* e, int net) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  return n ? n->n_params : -1;
+}
+extern "C" int sivae_num_bn(const sivae_engine* e, int net) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  return n ? (int)n->binfo.size() : -1;
+}
+extern "C" int sivae_bn(const sivae_engine* e, int net, int i, sivae_bn_info* out) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  if (!n || i < 0 || i >= (int)n->binfo.size() || !out) return fail(-1, "bad bn index");
+  *out = n->binfo[i];
+  return 0;
+}
+extern "C" long long sivae_bn_floats(const sivae_engine* e, int net) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  return n ? n->bn_floats : -1;
+}
+extern "C" long long sivae_workspace_bytes(const sivae_engine* e) { return e ? (long long)e->ws_need : -1; }
+
+extern "C" int sivae_bind_net(sivae_engine* e, int net, float* params, float* grads, float* m, float* v, float* bn, long long* nbt) {
+  Net* n = get_net(e, net);
+  if (!n) return fail(-1, "bad net id");
+  if (!params || !bn || !nbt) return fail(-1, "params / bn buffers must not be null");
+  n->params = params; n->grads = grads; n->m = m; n->v = v; n->bn = bn; n->nbt = nbt;
+  n->dirty = true;
+  return 0;
+}
+extern "C" int sivae_bind_workspace(sivae_engine* e, void* ws, long long bytes) {
+  if (!e || !ws) return fail(-1, "null argument");
+  if ((size_t)bytes < e->ws_need) return fail(-3, "workspace too small");
+  if (((uintptr_t)ws & 255) != 0) return fail(-3, "workspace must be 256-byte aligned");
+  e->ws = ws; e->ws_bytes = (size_t)bytes;
+  carve(e, (char*)ws);
+  for (int i = 0; i < 3; ++i) e->nets[i].dirty = true;
+  e->have_e_state = false;
+  return 0;
+}
+extern "C" int sivae_params_changed(sivae_engine* e, int net) {
+  Net* n = get_net(e, net);
+  if (!n) return fail(-1, "bad net id");
+  n->dirty = true;
+  return 0;
+}
+static int check_ready(sivae_engine* e, int batch) {
+  if (!e) return fail(-1, "null engine");
+  if (!e->ws) return fail(-4, "workspace not bound");
+  for (int i = 0; i < 3; ++i)
+    if (e->nets[i].present && !e->nets[i].params) return fail(-4, "net not bound");
+  if (batch < 1 || batch > e->cfg.max_batch) return fail(-5, "batch out of range");
+  return 0;
+}
+
+extern "C" int sivae_e_step(sivae_engine* e, const float* real_nchw, const float* noise, const float* eps, int B,
+                            const sivae_hyper* hp, float* stats, void* stream) {
+  TRY(check_ready(e, B));
+  if (!real_nchw || !noise || !eps || !hp || !stats) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sivae_config& c = e->cfg;
+  const int S = c.image_size, z = c.zdim;
+  const long long per = (long long)c.cdim * S * S;
+  const bool boot = c.variant == 1;
+  Net& en = e->nets[0];
+  Net& dn = e->nets[1];
+  Net& tn = boot ? e->nets[2] : e->nets[1];
+  if (!en.grads) return fail(-4, "encoder grads not bound");
+  TRY(refresh_derived(e, en, st)); TRY(refresh_derived(e, dn, st));
+  if (boot) TRY(refresh_derived(e, tn, st));
+  launch_nchw_to_nhwc(real_nchw, e->real, B, c.cdim, S, S, st);
+  cudaMemcpyAsync(e->noise, noise, sizeof(float) * B * z, cudaMemcpyDeviceToDevice, st);
+  const float *eps1 = eps, *eps2 = eps + (long long)B * z, *eps3 = eps + 2LL * B * z;
+  EncPass &E1 = e->ep[0], &E2 = e->ep[1], &E3 = e->ep[2];
+  DecPass &D1 = e->dp[0], &D2 = e->dp[1], &D3 = e->dp[2], &D4 = e->dp[3];
+  // forwards in the reference's per-net order (BN running stats are order dependent): :557-568
+  TRY(dec_forward(e, dn, D1, e->noise, B, true, st));                 // fake
+  TRY(enc_forward(e, en, E1, e->real, B, true, st));
+  launch_kl_reparam(E1.ml, eps1, e->z_keep, E1.kl, B, z, st);          // z (kept for the D half, :598)
+  TRY(dec_forward(e, dn, D2, e->z_keep, B, true, st));                // rec
+  TRY(enc_forward(e, en, E2, D2.y, B, true, st));                     // model(rec.detach())
+  launch_kl_reparam(E2.ml, eps2, E2.z, E2.kl, B, z, st);
+  TRY(dec_forward(e, tn, D3, E2.z, B, true, st));                     // rec_rec
+  TRY(enc_forward(e, en, E3, D1.y, B, true, st));                     // model(fake.detach())
+  launch_kl_reparam(E3.ml, eps3, E3.z, E3.kl, B, z, st);
+  TRY(dec_forward(e, tn, D4, E3.z, B, true, st));                     // rec_fake
+  // losses :563-586
+  launch_mse3(e->real, D2.y, D3.y, D1.y, D4.y, e->mse, B, per, e->red, e->red_bytes, st);
+  launch_e_loss_finalize(e->mse, E1.kl, E2.kl, E3.kl, B, hp->beta_kl, hp->beta_rec, hp->beta_neg, hp->scale, stats,
+                         e->coef, e->ckl_a, e->ckl_b, st);
+  const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
+  launch_loss_seed(e->real, D2.y, D3.y, D1.y, D4.y, a_rec, e->coef + B, 0.f, e->coef + 2 * B, 0.f, /*rec not detached :573*/ true,
+                   e->d_rec, e->d_rec_rec, e->d_rec_fake, nullptr, B, per, st);
+  // backward :587-588 -- only the encoder accumulates parameter grads; decoders are dgrad-only
+  cudaMemsetAsync(en.grads, 0, sizeof(float) * en.n_params, st);
+  TRY(dec_backward(e, tn, D3, e->d_rec_rec, false, e->dz, B, st));
+  launch_latent_bwd(E2.ml, eps2, e->dz, e->ckl_a, 0.f, e->dml, B, z, st);
+  TRY(enc_backward(e, en, E2, e->dml, true, nullptr, nullptr, B, st));
+  TRY(dec_backward(e, tn, D4, e->d_rec_fake, false, e->dz, B, st));
+  launch_latent_bwd(E3.ml, eps3, e->dz, e->ckl_b, 0.f, e->dml, B, z, st);
+  TRY(enc_backward(e, en, E3, e->dml, true, nullptr, nullptr, B, st));
+  TRY(dec_backward(e, dn, D2, e->d_rec, false, e->dz, B, st));
+  launch_latent_bwd(E1.ml, eps1, e->dz, nullptr, hp->scale * hp->beta_kl / (float)B, e->dml, B, z, st);
+  TRY(enc_backward(e, en, E1, e->dml, true, nullptr, nullptr, B, st));
+  CHECK_CUDA_RET();
+  e->cur_batch = B;
+  e->have_e_state = true;
+  return 0;
+}
+
+extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper* hp, float* stats, void* stream) {
+  if (!e || !e->have_e_state) return fail(-6, "sivae_d_step requires a preceding sivae_e_step");
+  const int B = e->cur_batch;
+  TRY(check_ready(e, B));
+  if (!eps || !hp || !stats) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sivae_config& c = e->cfg;
+  const int S = c.image_size, z = c.zdim;
+  const long long per = (long long)c.cdim * S * S;
+  const bool boot = c.variant == 1;
+  Net& en = e->nets[0];
+  Net& dn = e->nets[1];
+  Net& tn = boot ? e->nets[2] : e->nets[1];
+  if (!dn.grads) return fail(-4, "decoder grads not bound");
+  TRY(refresh_derived(e, en, st)); TRY(refresh_derived(e, dn, st));
+  if (boot) TRY(refresh_derived(e, tn, st));
+  const float *eps4 = eps, *eps5 = eps + (long long)B * z;
+  EncPass &E4 = e->ep[0], &E5 = e->ep[1];
+  DecPass &D5 = e->dp[0], &D6 = e->dp[1], &D7 = e->dp[2], &D8 = e->dp[3];
+  TRY(dec_forward(e, dn, D5, e->noise, B, true, st));                 // fake :597
+  TRY(dec_forward(e, dn, D6, e->z_keep, B, true, st));                // rec  :598
+  TRY(enc_forward(e, en, E4, D6.y, B, true, st));                     // :601
+  launch_kl_reparam(E4.ml, eps4, E4.z, E4.kl, B, z, st);
+  TRY(enc_forward(e, en, E5, D5.y, B, true, st));                     // :604
+  launch_kl_reparam(E5.ml, eps5, E5.z, E5.kl, B, z, st);
+  TRY(dec_forward(e, tn, D7, E4.z, B, true, st));                     // rec_rec :607
+  TRY(dec_forward(e, tn, D8, E5.z, B, true, st));                     // rec_fake :608
+  launch_mse3(e->real, D6.y, D7.y, D5.y, D8.y, e->mse, B, per, e->red, e->red_bytes, st);
+  launch_d_loss_finalize(e->mse, E4.kl, E5.kl, B, hp->beta_kl, hp->beta_rec, hp->gamma_r, hp->scale, stats, st);
+  const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
+  const float a_t = hp->scale * hp->gamma_r * hp->beta_rec / (float)B;     // 2 * (scale * gamma_r/2 * beta_rec / B)
+  const float ckl = hp->scale * 0.5f * hp->beta_kl / (float)B;
+  // standard: targets detached (:610-613); bootstrap: nothing detached (bootstrap :635-641)
+  launch_loss_seed(e->real, D6.y, D7.y, D5.y, D8.y, a_rec, nullptr, a_t, nullptr, a_t, boot, e->d_rec, e->d_rec_rec,
+                   e->d_rec_fake, boot ? e->d_fake : nullptr, B, per, st);
+  cudaMemsetAsync(dn.grads, 0, sizeof(float) * dn.n_params, st);
+  if (!boot) {
+    TRY(dec_backward(e, dn, D7, e->d_rec_rec, true, nullptr, B, st));
+    TRY(dec_backward(e, dn, D8, e->d_rec_fake, true, nullptr, B, st));
+    launch_latent_bwd(E4.ml, eps4, nullptr, nullptr, ckl, e->dml, B, z, st);
+    TRY(enc_backward(e, en, E4, e->dml, false, e->d_rec, e->d_rec, B, st));
+    launch_latent_bwd(E5.ml, eps5, nullptr, nullptr, ckl, e->dml, B, z, st);
+    TRY(enc_backward(e, en, E5, e->dml, false, e->d_fake, nullptr, B, st));
+  } else {
+    TRY(dec_backward(e, tn, D7, e->d_rec_rec, false, e->dz, B, st));
+    launch_latent_bwd(E4.ml, eps4, e->dz, nullptr, ckl, e->dml, B, z, st);
+    TRY(enc_backward(e, en, E4, e->dml, false, e->d_rec, e->d_rec, B, st));
+    TRY(dec_backward(e, tn, D8, e->d_rec_fake, false, e->dz, B, st));
+    launch_latent_bwd(E5.ml, eps5, e->dz, nullptr, ckl, e->dml, B, z, st);
+    TRY(enc_backward(e, en, E5, e->dml, false, e->d_fake, e->d_fake, B, st));
+  }
+  TRY(dec_backward(e, dn, D6, e->d_rec, true, nullptr, B, st));
+  TRY(dec_backward(e, dn, D5, e->d_fake, true, nullptr, B, st));
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+extern "C" int sivae_vae_step(sivae_engine* e, const float* real_nchw, const float* eps, int B, const sivae_hyper* hp,
+                              float* stats, void* stream) {
+  TRY(check_ready(e, B));
+  if (!real_nchw || !eps || !hp || !stats) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sivae_config& c = e->cfg;
+  const int S = c.image_size, z = c.zdim;
+  const long long per = (long long)c.cdim * S * S;
+  Net& en = e->nets[0];
+  Net& dn = e->nets[1];
+  if (!en.grads || !dn.grads) return fail(-4, "grads not bound");
+  TRY(refresh_derived(e, en, st)); TRY(refresh_derived(e, dn, st));
+  launch_nchw_to_nhwc(real_nchw, e->real, B, c.cdim, S, S, st);
+  EncPass& E1 = e->ep[0];
+  DecPass& D1 = e->dp[0];
+  TRY(enc_forward(e, en, E1, e->real, B, true, st));                  // model(real_batch) :518
+  launch_kl_reparam(E1.ml, eps, E1.z, E1.kl, B, z, st);
+  TRY(dec_forward(e, dn, D1, E1.z, B, true, st));
+  launch_mse3(e->real, D1.y, nullptr, nullptr, nullptr, e->mse, B, per, e->red, e->red_bytes, st);
+  launch_vae_loss_finalize(e->mse, E1.kl, B, hp->beta_kl, hp->beta_rec, stats, st);
+  launch_loss_seed(e->real, D1.y, nullptr, nullptr, nullptr, 2.f * hp->beta_rec / (float)B, nullptr, 0.f, nullptr, 0.f, false,
+                   e->d_rec, nullptr, nullptr, nullptr, B, per, st);
+  cudaMemsetAsync(en.grads, 0, sizeof(float) * en.n_params, st);
+  cudaMemsetAsync(dn.grads, 0, sizeof(float) * dn.n_params, st);
+  TRY(dec_backward(e, dn, D1, e->d_rec, true, e->dz, B, st));
+  launch_latent_bwd(E1.ml, eps, e->dz, nullptr, hp->beta_kl / (float)B, e->dml, B, z, st);
+  TRY(enc_backward(e, en, E1, e->dml, true, nullptr, nullptr, B, st));
+  CHECK_CUDA_RET();
+  e->have_e_state = false;
+  return 0;
+}
+
+extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_scale, void* stream) {
+  Net* n = get_net(e, net);
+  if (!n) return fail(-1, "bad net id");
+  if (!n->grads || !n->m || !n->v) return fail(-4, "optimiser buffers not bound");
+  n->adam_step += 1;
+  launch_adam(n->params, n->grads, n->m, n->v, n->n_params, lr, grad_scale, 0.9f, 0.999f, 1e-8f, n->adam_step, (cudaStream_t)stream);
+  n->dirty = true;
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_adam_set_step(sivae_engine* e, int net, long long step) {
+  Net* n = get_net(e, net);
+  if (!n) return fail(-1, "bad net id");
+  n->adam_step = step;
+  return 0;
+}
+extern "C" long long sivae_adam_get_step(const sivae_engine* e, int net) {
+  Net* n = get_net(const_cast<sivae_engine*>(e), net);
+  return n ? n->adam_step : -1;
+}
+
+extern "C" int sivae_encode(sivae_engine* e, const float* x_nchw, int B, float* mu, float* logvar, int train, void* stream) {
+  TRY(check_ready(e, B));
+  if (!x_nchw || !mu || !logvar) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sivae_config& c = e->cfg;
+  Net& en = e->nets[0];
+  TRY(refresh_derived(e, en, st));
+  launch_nchw_to_nhwc(x_nchw, e->out_tmp, B, c.cdim, c.image_size, c.image_size, st);
+  EncPass& p = e->ep[2];
+  TRY(enc_forward(e, en, p, e->out_tmp, B, train != 0, st));
+  cudaMemcpy2DAsync(mu, sizeof(float) * c.zdim, p.ml, sizeof(float) * 2 * c.zdim, sizeof(float) * c.zdim, B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpy2DAsync(logvar, sizeof(float) * c.zdim, p.ml + c.zdim, sizeof(float) * 2 * c.zdim, sizeof(float) * c.zdim, B, cudaMemcpyDeviceToDevice, st);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_decode(sivae_engine* e, int net, const float* z, int B, float* out_nchw, int train, void* stream) {
+  TRY(check_ready(e, B));
+  Net* n = get_net(e, net);
+  if (!n || n->enc) return fail(-1, "bad decoder net id");
+  if (!z || !out_nchw) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const sivae_config& c = e->cfg;
+  TRY(refresh_derived(e, *n, st));
+  DecPass& p = e->dp[3];
+  TRY(dec_forward(e, *n, p, z, B, train != 0, st));
+  launch_nhwc_to_nchw(p.y, out_nchw, B, c.cdim, c.image_size, c.image_size, st);
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+extern "C" int sivae_last_batch(const sivae_engine* e) { return e ? e->cur_batch : -1; }
+extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void* stream) {
+  if (!e || !e->ws || slot < 0 || slot > 3 || !out_nchw || e->cur_batch < 1) return fail(-1, "bad argument / no step run yet");
+  const sivae_config& c = e->cfg;
+  launch_nhwc_to_nchw(e->dp[slot].y, out_nchw, e->cur_batch, c.cdim, c.image_size, c.image_size, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+
+// ---- single-kernel entry points ------------------------------------------------------------------------------
+extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y, int N, int H,
+                                int W, int Cin, int Cout, int k, int backend, void* stream) {
+  ConvShape s{N, H, W, Cin, Cout, k};
+  if (backend == SIVAE_CONV_TCGEN05) {
+    if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
+    int r = launch_conv_fwd_tc(x, w, bias, addend, y, s, (cudaStream_t)stream);
+    if (r) return fail(r, "tcgen05 conv launch failed");
+  } else {
+    launch_conv_fwd_simt(x, w, bias, addend, y, s, (cudaStream_t)stream);
+  }
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* addend, float* dx, int N, int H, int W, int Cin,
+                                  int Cout, int k, int backend, void* workspace, long long ws_bytes, void* stream) {
+  size_t need = (size_t)Cout * Cin * k * k * sizeof(float);
+  if (!workspace || (size_t)ws_bytes < need) return fail(-3, "workspace too small for the packed dgrad filter");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* wd = (float*)workspace;
+  launch_pack_dgrad_filter(w, wd, Cout, Cin, k, backend == SIVAE_CONV_TCGEN05, st);
+  ConvShape s{N, H, W, Cout, Cin, k};
+  if (backend == SIVAE_CONV_TCGEN05) {
+    if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
+    int r = launch_conv_fwd_tc(dy, wd, nullptr, addend, dx, s, st);
+    if (r) return fail(r, "tcgen05 conv launch failed");
+  } else {
+    launch_conv_fwd_simt(dy, wd, nullptr, addend, dx, s, st);
+  }
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k,
+                                  int accumulate, int backend, void* workspace, long long ws_bytes, void* stream) {
+  ConvShape s{N, H, W, Cin, Cout, k};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backend == SIVAE_CONV_TCGEN05) {
+    if (!conv_tc_supported_wgrad(s)) return fail(-7, "shape not supported by the tcgen05 wgrad kernel");
+    if ((size_t)ws_bytes < conv_wgrad_tc_scratch_bytes(s)) return fail(-3, "workspace too small");
+    int r = launch_conv_wgrad_tc(x, dy, dw, s, accumulate != 0, workspace, (size_t)ws_bytes, st);
+    if (r) return fail(r, "tcgen05 wgrad launch failed");
+  } else {
+    if ((size_t)ws_bytes < conv_wgrad_simt_scratch_bytes(s)) return fail(-3, "workspace too small");
+    launch_conv_wgrad_simt(x, dy, dw, s, accumulate != 0, workspace, (size_t)ws_bytes, st);
+  }
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_bn_act_fwd(const float* t, const float* identity, const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, long long* nbt, float* mean_invstd, float* out, int N, int H, int W, int C,
+                                int mode, int train, void* workspace, long long ws_bytes, void* stream) {
+  if (C % 4 != 0) return fail(-2, "C must be a multiple of 4");
+  long long rows = (long long)N * H * W;
+  if ((size_t)ws_bytes < bn_scratch_bytes(rows, C)) return fail(-3, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (train) launch_bn_stats(t, rows, C, mean_invstd, running_mean, running_var, nbt, workspace, (size_t)ws_bytes, st);
+  else launch_bn_eval_stats(running_mean, running_var, C, mean_invstd, st);
+  launch_bn_act_fwd(t, identity, mean_invstd, gamma, beta, out, N, H, W, C, mode, false, st);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* gamma, const float* beta,
+                                const float* mean_invstd, float* dt, float* g, float* dgamma, float* dbeta, int accumulate, int N,
+                                int H, int W, int C, int mode, void* workspace, long long ws_bytes, void* stream) {
+  if (C % 4 != 0) return fail(-2, "C must be a multiple of 4");
+  if ((size_t)ws_bytes < bn_scratch_bytes((long long)N * H * W, C)) return fail(-3, "workspace too small");
+  launch_bn_act_bwd(dout, t, identity, mean_invstd, gamma, beta, dt, g, dgamma, dbeta, accumulate != 0, N, H, W, C, mode, false,
+                    workspace, (size_t)ws_bytes, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
+                          float* out, int B, long long per_sample, void* workspace, long long ws_bytes, void* stream) {
+  if ((size_t)ws_bytes < mse3_scratch_bytes(B, per_sample)) return fail(-3, "workspace too small");
+  launch_mse3(real, rec, rec_rec, fake, rec_fake, out, B, per_sample, workspace, (size_t)ws_bytes, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int B, int zdim, void* stream) {
+  launch_kl_reparam(mu_logvar, eps, z, kl, B, zdim, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
+                               long long step, void* stream) {
+  launch_adam(p, g, m, v, n, lr, grad_scale, 0.9f, 0.999f, 1e-8f, step, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}

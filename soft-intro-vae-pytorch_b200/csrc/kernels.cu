@@ -1,0 +1,1030 @@
+// Memory-bound kernels of the Soft-IntroVAE step (layout, train-mode BatchNorm + LeakyReLU + residual + pool /
+// upsample and their backward, linear layers, the fused loss pass, Adam) and the exact fp32 SIMT implicit-GEMM
+// convolution used for the 3-channel stem / predict layers and as the on-device cross-check of the tcgen05 path.
+// Reference semantics: soft_intro_vae/train_soft_intro_vae.py (lines cited per kernel).
+#include "kernels.h"
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace sivae {
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+__device__ __forceinline__ float round_tf32_dev(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float lrelu(float y) { return y > 0.f ? y : kSlope * y; }
+
+// =====================================================================================================
+// layout
+// =====================================================================================================
+__global__ void k_nchw_to_nhwc(const float* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W) {
+  long long total = (long long)N * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the NHWC output (coalesced writes); reads are strided by H*W but C is small / tensor is tiny
+    int c = (int)(i % C);
+    long long p = i / C;
+    int w = (int)(p % W);
+    long long q = p / W;
+    int h = (int)(q % H);
+    int n = (int)(q / H);
+    out[i] = in[(((long long)n * C + c) * H + h) * W + w];
+  }
+}
+__global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W) {
+  long long total = (long long)N * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the NCHW output
+    int w = (int)(i % W);
+    long long q = i / W;
+    int h = (int)(q % H);
+    q /= H;
+    int c = (int)(q % C);
+    int n = (int)(q / C);
+    out[i] = in[(((long long)n * H + h) * W + w) * C + c];
+  }
+}
+void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st) {
+  long long total = (long long)N * C * H * W;
+  if (total == 0) return;
+  k_nchw_to_nhwc<<<min(cdiv(total, 256), 148u * 16), 256, 0, st>>>(in, out, N, C, H, W);
+}
+void launch_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st) {
+  long long total = (long long)N * C * H * W;
+  if (total == 0) return;
+  k_nhwc_to_nchw<<<min(cdiv(total, 256), 148u * 16), 256, 0, st>>>(in, out, N, C, H, W);
+}
+__global__ void k_fill(float* p, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill(float* p, float v, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  k_fill<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(p, v, n);
+}
+__global__ void k_round_tf32(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = round_tf32_dev(in[i]);
+}
+void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  k_round_tf32<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(in, out, n);
+}
+__global__ void k_pack_dgrad(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int k, int rnd) {
+  long long total = (long long)Cout * Cin * k * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // i indexes wd[ci][r'][s'][co]
+    int co = (int)(i % Cout);
+    long long q = i / Cout;
+    int s2 = (int)(q % k);
+    q /= k;
+    int r2 = (int)(q % k);
+    int ci = (int)(q / k);
+    float v = w[(((long long)co * k + (k - 1 - r2)) * k + (k - 1 - s2)) * Cin + ci];
+    wd[i] = rnd ? round_tf32_dev(v) : v;
+  }
+}
+void launch_pack_dgrad_filter(const float* w, float* wd, int Cout, int Cin, int k, bool rnd, cudaStream_t st) {
+  long long total = (long long)Cout * Cin * k * k;
+  k_pack_dgrad<<<min(cdiv(total, 256), 148u * 8), 256, 0, st>>>(w, wd, Cout, Cin, k, rnd ? 1 : 0);
+}
+
+// =====================================================================================================
+// SIMT implicit-GEMM convolution, fp32 exact.  GEMM view: M = N*H*W pixels, N = Cout, K = k*k*Cin.
+// 128x64 tile, BK = 16, 256 threads, 8x4 micro-tile.
+// =====================================================================================================
+constexpr int CS_BM = 128, CS_BN = 64, CS_BK = 16;
+
+__global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* addend,
+                                                       float* y, int N, int H, int W, int Cin, int Cout, int ks) {
+  __shared__ float As[CS_BK][CS_BM + 4];
+  __shared__ float Bs[CS_BK][CS_BN + 4];
+  const int tid = threadIdx.x;
+  const long long M = (long long)N * H * W;
+  const int Ktot = ks * ks * Cin;
+  const int pad = ks / 2;
+  const long long m0 = (long long)blockIdx.x * CS_BM;
+  const int n0 = blockIdx.y * CS_BN;
+
+  // A loader: thread -> (kk = tid%16, rows tid/16 + 16*j)
+  const int a_kk = tid & 15;
+  const int a_r0 = tid >> 4;
+  int an[8], ah[8], aw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    long long m = m0 + a_r0 + 16 * j;
+    if (m < M) {
+      int wq = (int)(m % W);
+      long long q = m / W;
+      ah[j] = (int)(q % H);
+      an[j] = (int)(q / H);
+      aw[j] = wq;
+    } else {
+      an[j] = -1; ah[j] = 0; aw[j] = 0;
+    }
+  }
+  // B loader: thread -> (kk = tid%16, cols tid/16 + 16*j), j<4
+  const int b_kk = tid & 15;
+  const int b_c0 = tid >> 4;
+
+  const int tx = tid & 15;   // column group (4 cols)
+  const int ty = tid >> 4;   // row group (8 rows)
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += CS_BK) {
+    {
+      int k = k0 + a_kk;
+      int tap = 0, ci = 0, r = 0, s = 0;
+      bool kvalid = k < Ktot;
+      if (kvalid) { tap = k / Cin; ci = k - tap * Cin; r = tap / ks; s = tap - r * ks; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+        if (kvalid && an[j] >= 0) {
+          int hh = ah[j] + r - pad, ww = aw[j] + s - pad;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[(((long long)an[j] * H + hh) * W + ww) * Cin + ci];
+        }
+        As[a_kk][a_r0 + 16 * j] = v;
+      }
+    }
+    {
+      int k = k0 + b_kk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int co = n0 + b_c0 + 16 * j;
+        Bs[b_kk][b_c0 + 16 * j] = (k < Ktot && co < Cout) ? w[(long long)co * Ktot + k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < CS_BK; ++kk) {
+      float a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long long m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int co = n0 + tx * 4 + j;
+      if (co >= Cout) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[co];
+      if (addend) v += addend[m * Cout + co];
+      y[m * Cout + co] = v;
+    }
+  }
+}
+void launch_conv_fwd_simt(const float* x, const float* w, const float* bias, const float* addend, float* y,
+                          const ConvShape& s, cudaStream_t st) {
+  long long M = s.pixels();
+  if (M == 0) return;
+  dim3 grid(cdiv(M, CS_BM), cdiv(s.Cout, CS_BN));
+  k_conv_fwd_simt<<<grid, 256, 0, st>>>(x, w, bias, addend, y, s.N, s.H, s.W, s.Cin, s.Cout, s.k);
+}
+
+// wgrad: D[co][k] = sum_p dy[p][co] * A(p,k).  64(co) x 64(k) tile, pixel chunks of 16, split over pixels.
+constexpr int WG_BM = 64, WG_BN = 64, WG_BP = 16;
+__global__ void __launch_bounds__(256) k_conv_wgrad_simt(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ part, int N, int H, int W, int Cin,
+                                                         int Cout, int ks, long long pix_per_split) {
+  __shared__ float Ds[WG_BP][WG_BM + 4];   // dy tile  [pixel][co]
+  __shared__ float Xs[WG_BP][WG_BN + 4];   // im2col tile [pixel][k]
+  const int tid = threadIdx.x;
+  const long long M = (long long)N * H * W;
+  const int Ktot = ks * ks * Cin;
+  const int pad = ks / 2;
+  const int co0 = blockIdx.y * WG_BM;
+  const int k0 = blockIdx.x * WG_BN;
+  const long long p_begin = (long long)blockIdx.z * pix_per_split;
+  const long long p_end = min(M, p_begin + pix_per_split);
+
+  // loaders: thread -> column (tid%64), pixel rows tid/64 + 4*j (j<4)
+  const int lc = tid & 63;
+  const int lr0 = tid >> 6;
+  const int kcol = k0 + lc;
+  int tap = 0, ci = 0, r = 0, s = 0;
+  const bool kvalid = kcol < Ktot;
+  if (kvalid) { tap = kcol / Cin; ci = kcol - tap * Cin; r = tap / ks; s = tap - r * ks; }
+  const int co_l = co0 + lc;
+
+  const int tx = tid & 15, ty = tid >> 4;   // 4x4 micro tile: rows (co) ty*4.., cols (k) tx*4..
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long p0 = p_begin; p0 < p_end; p0 += WG_BP) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int pr = lr0 + 4 * j;
+      long long p = p0 + pr;
+      float dv = 0.f, xv = 0.f;
+      if (p < p_end) {
+        if (co_l < Cout) dv = dy[p * Cout + co_l];
+        if (kvalid) {
+          int wq = (int)(p % W);
+          long long q = p / W;
+          int hq = (int)(q % H);
+          int nq = (int)(q / H);
+          int hh = hq + r - pad, ww = wq + s - pad;
+          if (hh >= 0 && hh < H && ww >= 0 && ww < W) xv = x[(((long long)nq * H + hh) * W + ww) * Cin + ci];
+        }
+      }
+      Ds[pr][lc] = dv;
+      Xs[pr][lc] = xv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < WG_BP; ++pp) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Ds[pp][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Xs[pp][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = part + (long long)blockIdx.z * Cout * Ktot;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = k0 + tx * 4 + j;
+      if (k < Ktot) dst[(long long)co * Ktot + k] = acc[i][j];
+    }
+  }
+}
+__global__ void k_splitk_reduce(const float* __restrict__ part, float* __restrict__ out, long long n, int splits, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long long)z * n + i];   // fixed order: deterministic
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+static int wgrad_simt_splits(const ConvShape& s) {
+  long long tiles = (long long)cdiv(s.ktot(), WG_BN) * cdiv(s.Cout, WG_BM);
+  long long want = (148 * 4 + tiles - 1) / tiles;
+  long long maxs = (s.pixels() + 255) / 256;
+  long long sp = want < maxs ? want : maxs;
+  if (sp < 1) sp = 1;
+  if (sp > 256) sp = 256;
+  return (int)sp;
+}
+size_t conv_wgrad_simt_scratch_bytes(const ConvShape& s) {
+  return (size_t)wgrad_simt_splits(s) * s.Cout * s.ktot() * sizeof(float);
+}
+void launch_conv_wgrad_simt(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
+                            void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  int splits = wgrad_simt_splits(s);
+  long long M = s.pixels();
+  long long pps = (M + splits - 1) / splits;
+  pps = (pps + WG_BP - 1) / WG_BP * WG_BP;
+  dim3 grid(cdiv(s.ktot(), WG_BN), cdiv(s.Cout, WG_BM), splits);
+  float* part = (float*)scratch;
+  k_conv_wgrad_simt<<<grid, 256, 0, st>>>(x, dy, part, s.N, s.H, s.W, s.Cin, s.Cout, s.k, pps);
+  long long n = (long long)s.Cout * s.ktot();
+  k_splitk_reduce<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(part, dw, n, splits, accumulate ? 1 : 0);
+}
+
+__global__ void k_colsum(const float* __restrict__ in, float* __restrict__ out, long long rows, int C, int accumulate) {
+  // one block per channel; generic (C may be 3)
+  int c = blockIdx.x;
+  double s = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) s += (double)in[r * C + c];
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = accumulate ? out[c] + (float)sh[0] : (float)sh[0];
+}
+void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, cudaStream_t st) {
+  k_colsum<<<C, 256, 0, st>>>(in, out, rows, C, accumulate ? 1 : 0);
+}
+
+// =====================================================================================================
+// BatchNorm2d in train mode (:58,62,90; eps 1e-5, momentum 0.1): batch statistics over N*H*W
+// =====================================================================================================
+constexpr int BN_ROWS_PER_BLOCK = 1024;
+static int bn_nblocks(long long rows) { return (int)cdiv(rows, BN_ROWS_PER_BLOCK); }
+size_t bn_scratch_bytes(long long rows, int C) {
+  // partial sums: [nblk][2][C] floats, plus 2*C floats of finalized sums for the backward
+  return ((size_t)bn_nblocks(rows) * 2 * C + 2 * (size_t)C) * sizeof(float);
+}
+
+// each block: BN_ROWS_PER_BLOCK rows; threads: cvec = C/4 lanes over channels x (256/cvec) row lanes
+__global__ void __launch_bounds__(256) k_bn_stats_partial(const float* __restrict__ t, long long rows, int C,
+                                                          float* __restrict__ part) {
+  extern __shared__ float sh[];   // [rl][2][C]
+  const int cvec = C >> 2;
+  const int rl_n = 256 / cvec;
+  const int cl = threadIdx.x % cvec;
+  const int rl = threadIdx.x / cvec;
+  float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  if (rl < rl_n) {
+    long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK;
+    long long r1 = min(rows, r0 + BN_ROWS_PER_BLOCK);
+    for (long long r = r0 + rl; r < r1; r += rl_n) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + cl);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    float* d = sh + (size_t)rl * 2 * C;
+    reinterpret_cast<float4*>(d)[cl] = s;
+    reinterpret_cast<float4*>(d + C)[cl] = q;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float a = 0.f;
+    for (int k = 0; k < rl_n; ++k) a += sh[(size_t)k * 2 * C + i];
+    part[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+__global__ void k_bn_stats_finalize(const float* __restrict__ part, int nblk, long long rows, int C,
+                                    float* __restrict__ mean_invstd, float* running_mean, float* running_var,
+                                    long long* nbt) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)part[(size_t)b * 2 * C + c];
+    q += (double)part[(size_t)b * 2 * C + C + c];
+  }
+  double mean = s / (double)rows;
+  double var = q / (double)rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+  if (running_mean) {
+    double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_mean[c] = (float)((1.0 - kBnMomentum) * (double)running_mean[c] + kBnMomentum * mean);
+    running_var[c] = (float)((1.0 - kBnMomentum) * (double)running_var[c] + kBnMomentum * unb);
+  }
+}
+void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, float* running_mean,
+                     float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  int nblk = bn_nblocks(rows);
+  float* part = (float*)scratch;
+  int cvec = C / 4;
+  int rl_n = 256 / cvec;
+  size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
+  k_bn_stats_partial<<<nblk, 256, shmem, st>>>(t, rows, C, part);
+  k_bn_stats_finalize<<<cdiv(C, 128), 128, 0, st>>>(part, nblk, rows, C, mean_invstd, running_mean, running_var, nbt);
+}
+__global__ void k_bn_eval_stats(const float* rm, const float* rv, int C, float* mi) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mi[c] = rm[c]; mi[C + c] = rsqrtf(rv[c] + kBnEps); }
+}
+void launch_bn_eval_stats(const float* rm, const float* rv, int C, float* mi, cudaStream_t st) {
+  k_bn_eval_stats<<<cdiv(C, 128), 128, 0, st>>>(rm, rv, C, mi);
+}
+
+// out = resample(lrelu(bn(t) + identity)).  One thread per float4 of the OUTPUT for NONE/POOL, per float4 of the
+// INPUT for UP.  (:65-75 ResidualBlock.forward, :90-92 stem, :98 AvgPool2d(2), :155 Upsample nearest x2)
+template <int MODE, bool ROUND>
+__global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t, const float* __restrict__ idn,
+                                                    const float* __restrict__ mi, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ out, int N,
+                                                    int H, int W, int C) {
+  const int cvec = C >> 2;
+  const int Ho = MODE == RS_POOL ? H / 2 : H, Wo = MODE == RS_POOL ? W / 2 : W;
+  const long long total = (long long)N * Ho * Wo * cvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % cvec);
+    long long p = i / cvec;
+    int w = (int)(p % Wo);
+    long long q = p / Wo;
+    int h = (int)(q % Ho);
+    int n = (int)(q / Ho);
+    float4 mean = __ldg(reinterpret_cast<const float4*>(mi) + c4);
+    float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + c4);
+    float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 sc = make_float4(g.x * istd.x, g.y * istd.y, g.z * istd.z, g.w * istd.w);
+    float4 sf = make_float4(b.x - mean.x * sc.x, b.y - mean.y * sc.y, b.z - mean.z * sc.z, b.w - mean.w * sc.w);
+    auto eval = [&](long long pix) -> float4 {
+      float4 v = __ldg(reinterpret_cast<const float4*>(t + pix * C) + c4);
+      float4 y = make_float4(fmaf(v.x, sc.x, sf.x), fmaf(v.y, sc.y, sf.y), fmaf(v.z, sc.z, sf.z), fmaf(v.w, sc.w, sf.w));
+      if (idn) {
+        float4 d = __ldg(reinterpret_cast<const float4*>(idn + pix * C) + c4);
+        y.x += d.x; y.y += d.y; y.z += d.z; y.w += d.w;
+      }
+      return make_float4(lrelu(y.x), lrelu(y.y), lrelu(y.z), lrelu(y.w));
+    };
+    if (MODE == RS_NONE) {
+      long long pix = ((long long)n * H + h) * W + w;
+      float4 y = eval(pix);
+      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
+      reinterpret_cast<float4*>(out + pix * C)[c4] = y;
+    } else if (MODE == RS_POOL) {
+      long long p00 = ((long long)n * H + 2 * h) * W + 2 * w;
+      float4 a = eval(p00), b2 = eval(p00 + 1), c2 = eval(p00 + W), d2 = eval(p00 + W + 1);
+      float4 y = make_float4((a.x + b2.x + c2.x + d2.x) * 0.25f, (a.y + b2.y + c2.y + d2.y) * 0.25f,
+                             (a.z + b2.z + c2.z + d2.z) * 0.25f, (a.w + b2.w + c2.w + d2.w) * 0.25f);
+      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
+      long long po = ((long long)n * Ho + h) * Wo + w;
+      reinterpret_cast<float4*>(out + po * C)[c4] = y;
+    } else {
+      long long pix = ((long long)n * H + h) * W + w;
+      float4 y = eval(pix);
+      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
+      long long po = ((long long)n * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+      reinterpret_cast<float4*>(out + po * C)[c4] = y;
+      reinterpret_cast<float4*>(out + (po + 1) * C)[c4] = y;
+      reinterpret_cast<float4*>(out + (po + 2 * W) * C)[c4] = y;
+      reinterpret_cast<float4*>(out + (po + 2 * W + 1) * C)[c4] = y;
+    }
+  }
+}
+void launch_bn_act_fwd(const float* t, const float* identity, const float* mi, const float* gamma, const float* beta,
+                       float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st) {
+  int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
+  long long total = (long long)N * Ho * Wo * (C / 4);
+  if (total == 0) return;
+  unsigned grid = min(cdiv(total, 256), 148u * 32);
+#define LAUNCH(M, R) k_bn_act_fwd<M, R><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C)
+  if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
+  else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
+  else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }
+#undef LAUNCH
+}
+
+// ---- backward -----------------------------------------------------------------------------------------
+// upstream gradient at full resolution pixel (n,h,w): NONE: dout; POOL: dout[n,h/2,w/2]/4; UP: sum of the 4 children
+template <int MODE>
+__device__ __forceinline__ float4 upstream(const float* __restrict__ dout, int n, int h, int w, int H, int W, int C, int c4) {
+  if (MODE == RS_NONE) {
+    return __ldg(reinterpret_cast<const float4*>(dout + (((long long)n * H + h) * W + w) * C) + c4);
+  } else if (MODE == RS_POOL) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(dout + (((long long)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C) + c4);
+    return make_float4(v.x * 0.25f, v.y * 0.25f, v.z * 0.25f, v.w * 0.25f);
+  } else {
+    long long po = ((long long)n * (2 * H) + 2 * h) * (2 * W) + 2 * w;
+    float4 a = __ldg(reinterpret_cast<const float4*>(dout + po * C) + c4);
+    float4 b = __ldg(reinterpret_cast<const float4*>(dout + (po + 1) * C) + c4);
+    float4 c = __ldg(reinterpret_cast<const float4*>(dout + (po + 2 * W) * C) + c4);
+    float4 d = __ldg(reinterpret_cast<const float4*>(dout + (po + 2 * W + 1) * C) + c4);
+    return make_float4(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z, a.w + b.w + c.w + d.w);
+  }
+}
+__device__ __forceinline__ float lrelu_grad(float y, float d) { return y > 0.f ? d : kSlope * d; }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ dout, const float* __restrict__ t,
+                                                       const float* __restrict__ idn, const float* __restrict__ mi,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int N, int H, int W, int C, float* __restrict__ part) {
+  extern __shared__ float sh[];
+  const int cvec = C >> 2;
+  const int rl_n = 256 / cvec;
+  const int cl = threadIdx.x % cvec;
+  const int rl = threadIdx.x / cvec;
+  const long long rows = (long long)N * H * W;
+  float4 sg = make_float4(0, 0, 0, 0), sx = make_float4(0, 0, 0, 0);
+  if (rl < rl_n) {
+    float4 mean = __ldg(reinterpret_cast<const float4*>(mi) + cl);
+    float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + cl);
+    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cl);
+    float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cl);
+    long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK;
+    long long r1 = min(rows, r0 + BN_ROWS_PER_BLOCK);
+    for (long long r = r0 + rl; r < r1; r += rl_n) {
+      int w = (int)(r % W);
+      long long q = r / W;
+      int h = (int)(q % H);
+      int n = (int)(q / H);
+      float4 d = upstream<MODE>(dout, n, h, w, H, W, C, cl);
+      float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + cl);
+      float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
+      float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
+      if (idn) {
+        float4 e = __ldg(reinterpret_cast<const float4*>(idn + r * C) + cl);
+        y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+      }
+      float4 g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
+      sg.x += g.x; sg.y += g.y; sg.z += g.z; sg.w += g.w;
+      sx.x = fmaf(g.x, xh.x, sx.x); sx.y = fmaf(g.y, xh.y, sx.y); sx.z = fmaf(g.z, xh.z, sx.z); sx.w = fmaf(g.w, xh.w, sx.w);
+    }
+    float* dd = sh + (size_t)rl * 2 * C;
+    reinterpret_cast<float4*>(dd)[cl] = sg;
+    reinterpret_cast<float4*>(dd + C)[cl] = sx;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float a = 0.f;
+    for (int k = 0; k < rl_n; ++k) a += sh[(size_t)k * 2 * C + i];
+    part[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+__global__ void k_bn_bwd_finalize(const float* __restrict__ part, int nblk, long long rows, int C,
+                                  float* __restrict__ sums, float* dgamma, float* dbeta, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)part[(size_t)b * 2 * C + c];
+    q += (double)part[(size_t)b * 2 * C + C + c];
+  }
+  sums[c] = (float)(s / (double)rows);       // mean of g
+  sums[C + c] = (float)(q / (double)rows);   // mean of g * xhat
+  if (dgamma) {
+    dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
+    dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+  }
+}
+template <int MODE, bool ROUND>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ dout, const float* __restrict__ t,
+                                                      const float* __restrict__ idn, const float* __restrict__ mi,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ sums, float* __restrict__ dt,
+                                                      float* __restrict__ gout, int N, int H, int W, int C) {
+  const int cvec = C >> 2;
+  const long long total = (long long)N * H * W * cvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % cvec);
+    long long r = i / cvec;
+    int w = (int)(r % W);
+    long long q = r / W;
+    int h = (int)(q % H);
+    int n = (int)(q / H);
+    float4 mean = __ldg(reinterpret_cast<const float4*>(mi) + c4);
+    float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + c4);
+    float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 mg = __ldg(reinterpret_cast<const float4*>(sums) + c4);
+    float4 mx = __ldg(reinterpret_cast<const float4*>(sums + C) + c4);
+    float4 d = upstream<MODE>(dout, n, h, w, H, W, C, c4);
+    float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + c4);
+    float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
+    float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
+    if (idn) {
+      float4 e = __ldg(reinterpret_cast<const float4*>(idn + r * C) + c4);
+      y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+    }
+    float4 g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
+    float4 o;
+    o.x = ga.x * istd.x * (g.x - mg.x - xh.x * mx.x);
+    o.y = ga.y * istd.y * (g.y - mg.y - xh.y * mx.y);
+    o.z = ga.z * istd.z * (g.z - mg.z - xh.z * mx.z);
+    o.w = ga.w * istd.w * (g.w - mg.w - xh.w * mx.w);
+    if (ROUND) {
+      o.x = round_tf32_dev(o.x); o.y = round_tf32_dev(o.y); o.z = round_tf32_dev(o.z); o.w = round_tf32_dev(o.w);
+    }
+    reinterpret_cast<float4*>(dt + r * C)[c4] = o;
+    if (gout) {
+      if (ROUND) { g.x = round_tf32_dev(g.x); g.y = round_tf32_dev(g.y); g.z = round_tf32_dev(g.z); g.w = round_tf32_dev(g.w); }
+      reinterpret_cast<float4*>(gout + r * C)[c4] = g;
+    }
+  }
+}
+void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mi, const float* gamma,
+                       const float* beta, float* dt, float* g, float* dgamma, float* dbeta, bool accumulate, int N,
+                       int H, int W, int C, int mode, bool rnd, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  long long rows = (long long)N * H * W;
+  if (rows == 0) return;
+  int nblk = bn_nblocks(rows);
+  float* part = (float*)scratch;
+  float* sums = part + (size_t)nblk * 2 * C;
+  int cvec = C / 4, rl_n = 256 / cvec;
+  size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
+  if (mode == RS_NONE) k_bn_bwd_reduce<RS_NONE><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part);
+  else if (mode == RS_POOL) k_bn_bwd_reduce<RS_POOL><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part);
+  else k_bn_bwd_reduce<RS_UP><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part);
+  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, st>>>(part, nblk, rows, C, sums, dgamma, dbeta, accumulate ? 1 : 0);
+  long long total = rows * cvec;
+  unsigned grid = min(cdiv(total, 256), 148u * 32);
+#define LAUNCH(M, R) k_bn_bwd_apply<M, R><<<grid, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, sums, dt, g, N, H, W, C)
+  if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
+  else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
+  else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }
+#undef LAUNCH
+}
+
+// =====================================================================================================
+// nn.Linear (encoder fc :109, decoder fc + ReLU :145-148).  Batch is tiny (<= 128): weight-streaming kernels.
+// =====================================================================================================
+constexpr int LF_OT = 4, LF_BT = 8;
+__global__ void __launch_bounds__(256) k_linear_fwd(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ b, float* __restrict__ y, int B, int F,
+                                                    int O, int relu) {
+  const int o0 = blockIdx.x * LF_OT, b0 = blockIdx.y * LF_BT;
+  float acc[LF_OT][LF_BT];
+#pragma unroll
+  for (int i = 0; i < LF_OT; ++i)
+#pragma unroll
+    for (int j = 0; j < LF_BT; ++j) acc[i][j] = 0.f;
+  for (int f = threadIdx.x; f < F; f += 256) {
+    float wv[LF_OT], xv[LF_BT];
+#pragma unroll
+    for (int i = 0; i < LF_OT; ++i) wv[i] = (o0 + i < O) ? __ldg(w + (long long)(o0 + i) * F + f) : 0.f;
+#pragma unroll
+    for (int j = 0; j < LF_BT; ++j) xv[j] = (b0 + j < B) ? __ldg(x + (long long)(b0 + j) * F + f) : 0.f;
+#pragma unroll
+    for (int i = 0; i < LF_OT; ++i)
+#pragma unroll
+      for (int j = 0; j < LF_BT; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+  }
+  __shared__ float red[8][LF_OT * LF_BT];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < LF_OT; ++i)
+#pragma unroll
+    for (int j = 0; j < LF_BT; ++j) {
+      float v = acc[i][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wid][i * LF_BT + j] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < LF_OT * LF_BT) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    int i = threadIdx.x / LF_BT, j = threadIdx.x % LF_BT;
+    if (o0 + i < O && b0 + j < B) {
+      if (b) v += b[o0 + i];
+      if (relu) v = fmaxf(v, 0.f);
+      y[(long long)(b0 + j) * O + o0 + i] = v;
+    }
+  }
+}
+void launch_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, bool relu, cudaStream_t st) {
+  dim3 grid(cdiv(O, LF_OT), cdiv(B, LF_BT));
+  k_linear_fwd<<<grid, 256, 0, st>>>(x, w, b, y, B, F, O, relu ? 1 : 0);
+}
+constexpr int LD_BT = 8;
+__global__ void __launch_bounds__(256) k_linear_dgrad(const float* __restrict__ dy, const float* __restrict__ w,
+                                                      float* __restrict__ dx, int B, int F, int O) {
+  extern __shared__ float sdy[];   // [LD_BT][O]
+  const int b0 = blockIdx.y * LD_BT;
+  for (int i = threadIdx.x; i < LD_BT * O; i += 256) {
+    int j = i / O, o = i - j * O;
+    sdy[i] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o] : 0.f;
+  }
+  __syncthreads();
+  int f = blockIdx.x * 256 + threadIdx.x;
+  if (f >= F) return;
+  float acc[LD_BT];
+#pragma unroll
+  for (int j = 0; j < LD_BT; ++j) acc[j] = 0.f;
+  for (int o = 0; o < O; ++o) {
+    float wv = __ldg(w + (long long)o * F + f);
+#pragma unroll
+    for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[j * O + o], wv, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < LD_BT; ++j)
+    if (b0 + j < B) dx[(long long)(b0 + j) * F + f] = acc[j];
+}
+void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, cudaStream_t st) {
+  dim3 grid(cdiv(F, 256), cdiv(B, LD_BT));
+  size_t shmem = (size_t)LD_BT * O * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_linear_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  k_linear_dgrad<<<grid, 256, shmem, st>>>(dy, w, dx, B, F, O);
+}
+constexpr int LW_OT = 8;
+__global__ void __launch_bounds__(256) k_linear_wgrad(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      float* __restrict__ dw, float* __restrict__ db, int B, int F,
+                                                      int O, int accumulate) {
+  extern __shared__ float sdy[];   // [B][LW_OT]
+  const int o0 = blockIdx.y * LW_OT;
+  for (int i = threadIdx.x; i < B * LW_OT; i += 256) {
+    int bb = i / LW_OT, oo = i - bb * LW_OT;
+    sdy[i] = (o0 + oo < O) ? dy[(long long)bb * O + o0 + oo] : 0.f;
+  }
+  __syncthreads();
+  int f = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x == 0 && db && threadIdx.x < LW_OT && o0 + threadIdx.x < O) {
+    float s = 0.f;
+    for (int bb = 0; bb < B; ++bb) s += sdy[bb * LW_OT + threadIdx.x];
+    db[o0 + threadIdx.x] = accumulate ? db[o0 + threadIdx.x] + s : s;
+  }
+  if (f >= F) return;
+  float acc[LW_OT];
+#pragma unroll
+  for (int i = 0; i < LW_OT; ++i) acc[i] = 0.f;
+  for (int bb = 0; bb < B; ++bb) {
+    float xv = __ldg(x + (long long)bb * F + f);
+#pragma unroll
+    for (int i = 0; i < LW_OT; ++i) acc[i] = fmaf(sdy[bb * LW_OT + i], xv, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < LW_OT; ++i)
+    if (o0 + i < O) {
+      long long idx = (long long)(o0 + i) * F + f;
+      dw[idx] = accumulate ? dw[idx] + acc[i] : acc[i];
+    }
+}
+void launch_linear_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int F, int O, bool accumulate, cudaStream_t st) {
+  dim3 grid(cdiv(F, 256), cdiv(O, LW_OT));
+  size_t shmem = (size_t)B * LW_OT * sizeof(float);
+  k_linear_wgrad<<<grid, 256, shmem, st>>>(x, dy, dw, db, B, F, O, accumulate ? 1 : 0);
+}
+__global__ void k_relu_bwd(const float* __restrict__ y, float* __restrict__ dy, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+void launch_relu_bwd(const float* y, float* dy, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  k_relu_bwd<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(y, dy, n);
+}
+
+// =====================================================================================================
+// Fused loss pass.  calc_reconstruction_loss('mse', reduction none) for the three image pairs of one half
+// iteration in ONE read of the five images (:563,573,576 / :599,610,612), vectorised 128-bit loads,
+// warp-shuffle + block reduction, deterministic two-stage sum (no atomics).
+// =====================================================================================================
+constexpr int MSE_CHUNK = 8192;   // floats per block
+static int mse_blocks_per_sample(long long per_sample) { return (int)cdiv(per_sample, MSE_CHUNK); }
+size_t mse3_scratch_bytes(int B, long long per_sample) {
+  return (size_t)B * mse_blocks_per_sample(per_sample) * 3 * sizeof(float);
+}
+__device__ __forceinline__ float sq4(float4 a, float4 b) {
+  float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+  return fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+}
+__global__ void __launch_bounds__(256) k_mse3_partial(const float* __restrict__ real, const float* __restrict__ rec,
+                                                      const float* __restrict__ rec_rec, const float* __restrict__ fake,
+                                                      const float* __restrict__ rec_fake, float* __restrict__ part,
+                                                      long long per_sample, int nblk) {
+  const int b = blockIdx.y;
+  const long long base = (long long)b * per_sample;
+  const long long e0 = (long long)blockIdx.x * MSE_CHUNK;
+  const long long e1 = min(per_sample, e0 + MSE_CHUNK);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  const bool vec = ((per_sample & 3) == 0);
+  if (vec) {
+    for (long long e = e0 + 4 * threadIdx.x; e < e1; e += 4 * 256) {
+      float4 r = __ldg(reinterpret_cast<const float4*>(rec + base + e));
+      if (real) s0 += sq4(r, __ldg(reinterpret_cast<const float4*>(real + base + e)));
+      if (rec_rec) s1 += sq4(__ldg(reinterpret_cast<const float4*>(rec_rec + base + e)), r);
+      if (fake) s2 += sq4(__ldg(reinterpret_cast<const float4*>(rec_fake + base + e)), __ldg(reinterpret_cast<const float4*>(fake + base + e)));
+    }
+  } else {
+    for (long long e = e0 + threadIdx.x; e < e1; e += 256) {
+      float r = rec[base + e];
+      if (real) { float d = r - real[base + e]; s0 = fmaf(d, d, s0); }
+      if (rec_rec) { float d = rec_rec[base + e] - r; s1 = fmaf(d, d, s1); }
+      if (fake) { float d = rec_fake[base + e] - fake[base + e]; s2 = fmaf(d, d, s2); }
+    }
+  }
+  __shared__ float red[8][3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[wid][0] = s0; red[wid][1] = s1; red[wid][2] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    part[((long long)b * nblk + blockIdx.x) * 3 + threadIdx.x] = v;
+  }
+}
+__global__ void k_mse3_final(const float* __restrict__ part, float* __restrict__ out, int B, int nblk) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;   // over B*3
+  if (i >= B * 3) return;
+  int b = i / 3, j = i - 3 * b;
+  double s = 0.0;
+  for (int k = 0; k < nblk; ++k) s += (double)part[((long long)b * nblk + k) * 3 + j];
+  out[i] = (float)s;
+}
+void launch_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
+                 float* out, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  int nblk = mse_blocks_per_sample(per_sample);
+  float* part = (float*)scratch;
+  dim3 grid(nblk, B);
+  k_mse3_partial<<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, part, per_sample, nblk);
+  k_mse3_final<<<cdiv(B * 3, 128), 128, 0, st>>>(part, out, B, nblk);
+}
+
+// calc_kl(reduce='none') (:231-251, mu_o = logvar_o = 0) + reparameterize (:254-265); one warp per sample
+__global__ void k_kl_reparam(const float* __restrict__ ml, const float* __restrict__ eps, float* __restrict__ z,
+                             float* __restrict__ kl, int B, int zd) {
+  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* mu = ml + (long long)b * 2 * zd;
+  const float* lv = mu + zd;
+  float s = 0.f;
+  for (int j = lane; j < zd; j += 32) {
+    float m = mu[j], l = lv[j];
+    s += 1.f + l - m * m - expf(l);
+    if (z) z[(long long)b * zd + j] = fmaf(eps[(long long)b * zd + j], expf(0.5f * l), m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0 && kl) kl[b] = -0.5f * s;
+}
+void launch_kl_reparam(const float* ml, const float* eps, float* z, float* kl, int B, int zd, cudaStream_t st) {
+  k_kl_reparam<<<cdiv(B, 4), 128, 0, st>>>(ml, eps, z, kl, B, zd);
+}
+__global__ void k_latent_bwd(const float* __restrict__ ml, const float* __restrict__ eps, const float* __restrict__ dz,
+                             const float* __restrict__ ckl, float ckl_const, float* __restrict__ dml, int B, int zd) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * zd) return;
+  int b = (int)(i / zd), j = (int)(i - (long long)b * zd);
+  float m = ml[(long long)b * 2 * zd + j], l = ml[(long long)b * 2 * zd + zd + j];
+  float c = ckl ? ckl[b] : ckl_const;
+  float dmu = c * m;
+  float dlv = c * 0.5f * (expf(l) - 1.f);
+  if (dz) {
+    float d = dz[i];
+    dmu += d;
+    dlv += d * eps[i] * 0.5f * expf(0.5f * l);
+  }
+  dml[(long long)b * 2 * zd + j] = dmu;
+  dml[(long long)b * 2 * zd + zd + j] = dlv;
+}
+void launch_latent_bwd(const float* ml, const float* eps, const float* dz, const float* ckl, float ckl_const,
+                       float* dml, int B, int zd, cudaStream_t st) {
+  long long n = (long long)B * zd;
+  k_latent_bwd<<<cdiv(n, 256), 256, 0, st>>>(ml, eps, dz, ckl, ckl_const, dml, B, zd);
+}
+
+// block-wide sum of one value per thread (blockDim = 256), result valid in all threads
+__device__ float block_sum_256(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r += sh[k];
+  return r;
+}
+// E-step scalars (:563-586) and the per-sample backward coefficients of the exp-ELBO terms
+__global__ void __launch_bounds__(256) k_e_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl_real,
+                                                         const float* __restrict__ kl_rec, const float* __restrict__ kl_fake,
+                                                         int B, float beta_kl, float beta_rec, float beta_neg, float scale,
+                                                         float* stats, float* coef, float* ckl_rec, float* ckl_fake) {
+  __shared__ float sh[8];
+  float s_r = 0.f, s_k = 0.f, s_er = 0.f, s_ef = 0.f;
+  const float invB = 1.f / (float)B;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    float r = mse[b * 3 + 0], rr = mse[b * 3 + 1], rf = mse[b * 3 + 2];
+    float er = expf(-2.f * scale * (beta_rec * rr + beta_neg * kl_rec[b]));
+    float ef = expf(-2.f * scale * (beta_rec * rf + beta_neg * kl_fake[b]));
+    s_r += r; s_k += kl_real[b]; s_er += er; s_ef += ef;
+    // d lossE / d rr_b = 0.25/B * er * (-2 scale beta_rec); image seed uses 2x that (d/dx of (x-y)^2)
+    float c_rr = 0.25f * invB * er * (-2.f * scale * beta_rec);
+    float c_rf = 0.25f * invB * ef * (-2.f * scale * beta_rec);
+    coef[1 * B + b] = 2.f * c_rr;
+    coef[2 * B + b] = 2.f * c_rf;
+    ckl_rec[b] = 0.25f * invB * er * (-2.f * scale * beta_neg);
+    ckl_fake[b] = 0.25f * invB * ef * (-2.f * scale * beta_neg);
+  }
+  float loss_rec = block_sum_256(s_r, sh) * invB;
+  float kl = block_sum_256(s_k, sh) * invB;
+  float e_rec = block_sum_256(s_er, sh) * invB;
+  float e_fake = block_sum_256(s_ef, sh) * invB;
+  if (threadIdx.x == 0) {
+    float lossE = scale * (beta_rec * loss_rec + beta_kl * kl) + 0.25f * (e_rec + e_fake);
+    stats[0] = loss_rec; stats[1] = kl; stats[2] = e_rec; stats[3] = e_fake; stats[4] = lossE;
+    stats[15] = (lossE != lossE) ? 1.f : 0.f;
+  }
+}
+void launch_e_loss_finalize(const float* mse, const float* kl_real, const float* kl_rec, const float* kl_fake, int B,
+                            float beta_kl, float beta_rec, float beta_neg, float scale, float* stats, float* coef,
+                            float* ckl_rec, float* ckl_fake, cudaStream_t st) {
+  k_e_loss_finalize<<<1, 256, 0, st>>>(mse, kl_real, kl_rec, kl_fake, B, beta_kl, beta_rec, beta_neg, scale, stats, coef, ckl_rec, ckl_fake);
+}
+__global__ void __launch_bounds__(256) k_d_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl_rec,
+                                                         const float* __restrict__ kl_fake, int B, float beta_kl,
+                                                         float beta_rec, float gamma_r, float scale, float* stats) {
+  __shared__ float sh[8];
+  float s_r = 0.f, s_rr = 0.f, s_rf = 0.f, s_kr = 0.f, s_kf = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    s_r += mse[b * 3]; s_rr += mse[b * 3 + 1]; s_rf += mse[b * 3 + 2]; s_kr += kl_rec[b]; s_kf += kl_fake[b];
+  }
+  const float invB = 1.f / (float)B;
+  float loss_rec = block_sum_256(s_r, sh) * invB, lrr = block_sum_256(s_rr, sh) * invB, lrf = block_sum_256(s_rf, sh) * invB;
+  float kr = block_sum_256(s_kr, sh) * invB, kf = block_sum_256(s_kf, sh) * invB;
+  if (threadIdx.x == 0) {
+    float lossD = scale * (loss_rec * beta_rec + (kr + kf) * 0.5f * beta_kl + gamma_r * 0.5f * beta_rec * (lrr + lrf));
+    stats[5] = loss_rec; stats[6] = kr; stats[7] = kf; stats[8] = lrr; stats[9] = lrf; stats[10] = lossD;
+    if (lossD != lossD) stats[15] = 1.f;
+  }
+}
+void launch_d_loss_finalize(const float* mse, const float* kl_rec, const float* kl_fake, int B, float beta_kl,
+                            float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st) {
+  k_d_loss_finalize<<<1, 256, 0, st>>>(mse, kl_rec, kl_fake, B, beta_kl, beta_rec, gamma_r, scale, stats);
+}
+__global__ void __launch_bounds__(256) k_vae_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl,
+                                                           int B, float beta_kl, float beta_rec, float* stats) {
+  __shared__ float sh[8];
+  float s_r = 0.f, s_k = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) { s_r += mse[b * 3]; s_k += kl[b]; }
+  const float invB = 1.f / (float)B;
+  float lr = block_sum_256(s_r, sh) * invB, lk = block_sum_256(s_k, sh) * invB;
+  if (threadIdx.x == 0) {
+    float loss = beta_rec * lr + beta_kl * lk;
+    stats[11] = lr; stats[12] = lk; stats[13] = loss;
+    stats[15] = (loss != loss) ? 1.f : 0.f;
+  }
+}
+void launch_vae_loss_finalize(const float* mse, const float* kl, int B, float beta_kl, float beta_rec, float* stats, cudaStream_t st) {
+  k_vae_loss_finalize<<<1, 256, 0, st>>>(mse, kl, B, beta_kl, beta_rec, stats);
+}
+
+__global__ void __launch_bounds__(256) k_loss_seed(const float* __restrict__ real, const float* __restrict__ rec,
+                                                   const float* __restrict__ rec_rec, const float* __restrict__ fake,
+                                                   const float* __restrict__ rec_fake, float a_rec,
+                                                   const float* __restrict__ a_t_arr, float a_t_c,
+                                                   const float* __restrict__ a_f_arr, float a_f_c, int tgt_rec,
+                                                   float* __restrict__ d_rec, float* __restrict__ d_rec_rec,
+                                                   float* __restrict__ d_rec_fake, float* __restrict__ d_fake,
+                                                   long long per_sample4) {
+  const int b = blockIdx.y;
+  const float a_t = a_t_arr ? a_t_arr[b] : a_t_c;
+  const float a_f = a_f_arr ? a_f_arr[b] : a_f_c;
+  const long long base = (long long)b * per_sample4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample4; i += (long long)gridDim.x * blockDim.x) {
+    float4 r = __ldg(reinterpret_cast<const float4*>(rec) + base + i);
+    float4 x = __ldg(reinterpret_cast<const float4*>(real) + base + i);
+    float4 o = make_float4(a_rec * (r.x - x.x), a_rec * (r.y - x.y), a_rec * (r.z - x.z), a_rec * (r.w - x.w));
+    if (rec_rec) {
+      float4 q = __ldg(reinterpret_cast<const float4*>(rec_rec) + base + i);
+      float4 d = make_float4(a_t * (q.x - r.x), a_t * (q.y - r.y), a_t * (q.z - r.z), a_t * (q.w - r.w));
+      if (d_rec_rec) reinterpret_cast<float4*>(d_rec_rec)[base + i] = d;
+      if (tgt_rec) { o.x -= d.x; o.y -= d.y; o.z -= d.z; o.w -= d.w; }
+    }
+    if (d_rec) reinterpret_cast<float4*>(d_rec)[base + i] = o;
+    if (fake) {
+      float4 f = __ldg(reinterpret_cast<const float4*>(fake) + base + i);
+      float4 q = __ldg(reinterpret_cast<const float4*>(rec_fake) + base + i);
+      float4 d = make_float4(a_f * (q.x - f.x), a_f * (q.y - f.y), a_f * (q.z - f.z), a_f * (q.w - f.w));
+      if (d_rec_fake) reinterpret_cast<float4*>(d_rec_fake)[base + i] = d;
+      if (d_fake) reinterpret_cast<float4*>(d_fake)[base + i] = make_float4(-d.x, -d.y, -d.z, -d.w);
+    }
+  }
+}
+void launch_loss_seed(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
+                      float a_rec, const float* a_t_arr, float a_t, const float* a_f_arr, float a_f, bool target_grad_rec,
+                      float* d_rec, float* d_rec_rec, float* d_rec_fake, float* d_fake, int B, long long per_sample,
+                      cudaStream_t st) {
+  long long ps4 = per_sample / 4;   // per_sample = cdim*S*S with even S: multiple of 4
+  dim3 grid(min(cdiv(ps4, 256), 148u * 4), B);
+  k_loss_seed<<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, a_rec, a_t_arr, a_t, a_f_arr, a_f,
+                                    target_grad_rec ? 1 : 0, d_rec, d_rec_rec, d_rec_fake, d_fake, ps4);
+}
+
+// =====================================================================================================
+// torch.optim.Adam (:450-451): betas (.9,.999), eps 1e-8, bias-corrected, no weight decay -- flat buffers
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, long long n, float step_size, float grad_scale,
+                                              float b1, float b2, float eps, float sqrt_bc2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);            // exp_avg.lerp_(grad, 1-beta1)
+    float vi = fmaf(gi * gi, 1.f - b2, v[i] * b2);         // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / sqrt_bc2 + eps;             // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale, float b1,
+                 float b2, float eps, long long step, cudaStream_t st) {
+  if (n <= 0) return;
+  double bc1 = 1.0 - pow((double)b1, (double)step);
+  double bc2 = 1.0 - pow((double)b2, (double)step);
+  float step_size = (float)((double)lr / bc1);
+  float sqrt_bc2 = (float)sqrt(bc2);
+  k_adam<<<min(cdiv(n, 256), 148u * 16), 256, 0, st>>>(p, g, m, v, n, step_size, grad_scale, b1, b2, eps, sqrt_bc2);
+}
+
+}  // namespace sivae

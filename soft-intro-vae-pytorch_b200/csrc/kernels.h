@@ -1,0 +1,116 @@
+// Internal launch API shared by the translation units of libsivae_b200.so.  All pointers are device
+// pointers, all launches go to `st`.  NHWC activations, [Cout][kh][kw][Cin] filters.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+
+namespace sivae {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+constexpr float kSlope = 0.2f;
+
+enum ResampleMode { RS_NONE = 0, RS_POOL = 1, RS_UP = 2 };
+
+struct ConvShape {
+  int N, H, W, Cin, Cout, k;   // stride 1, pad k/2
+  long long pixels() const { return (long long)N * H * W; }
+  long long ktot() const { return (long long)k * k * Cin; }
+};
+
+// ---------------- layout ----------------
+void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st);
+void launch_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st);
+void launch_fill(float* p, float v, long long n, cudaStream_t st);
+void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st);
+// wd[ci][k-1-r][k-1-s][co] = w[co][r][s][ci]  (filters for dgrad as a forward conv); optional tf32 rounding
+void launch_pack_dgrad_filter(const float* w, float* wd, int Cout, int Cin, int k, bool round_tf32, cudaStream_t st);
+
+// ---------------- SIMT fp32 implicit-GEMM convolution (exact path; also stem / predict shapes) ----------
+// y[p][co] = sum_{tap,ci} x[p+tap][ci] * w[co][tap][ci] + bias[co] + addend[p][co]
+void launch_conv_fwd_simt(const float* x, const float* w, const float* bias, const float* addend, float* y,
+                          const ConvShape& s, cudaStream_t st);
+// dw[co][tap][ci] (+)= sum_p dy[p][co] * x[p+tap][ci];  scratch: split partials
+size_t conv_wgrad_simt_scratch_bytes(const ConvShape& s);
+void launch_conv_wgrad_simt(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
+                            void* scratch, size_t scratch_bytes, cudaStream_t st);
+// out[c] (+)= sum_rows in[row][c]
+void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, cudaStream_t st);
+
+// ---------------- tcgen05 TF32 implicit-GEMM convolution (conv_tc.cu) ----------------
+bool conv_tc_supported_fwd(const ConvShape& s);
+// returns cudaError / driver error code (0 ok)
+int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y,
+                       const ConvShape& s, cudaStream_t st);
+bool conv_tc_supported_wgrad(const ConvShape& s);
+size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s);
+int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
+                         void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+// ---------------- train-mode BatchNorm (+LeakyReLU, +residual, +pool / upsample) ----------------
+size_t bn_scratch_bytes(long long rows, int C);
+// batch statistics of t[rows][C] -> mean_invstd[0..C) = mean, [C..2C) = invstd; running-stat EMA + nbt++
+void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, float* running_mean,
+                     float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st);
+// eval-mode: mean_invstd from running stats
+void launch_bn_eval_stats(const float* running_mean, const float* running_var, int C, float* mean_invstd, cudaStream_t st);
+// out = resample(lrelu(bn(t) + identity)); identity may be null. (N,H,W) are the dims of t.
+void launch_bn_act_fwd(const float* t, const float* identity, const float* mean_invstd, const float* gamma,
+                       const float* beta, float* out, int N, int H, int W, int C, int mode, bool round_tf32,
+                       cudaStream_t st);
+// backward. dout has the shape of the resampled output.  sums: 2*C floats scratch inside `scratch`.
+void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mean_invstd,
+                       const float* gamma, const float* beta, float* dt, float* g, float* dgamma, float* dbeta,
+                       bool accumulate, int N, int H, int W, int C, int mode, bool round_tf32, void* scratch,
+                       size_t scratch_bytes, cudaStream_t st);
+
+// ---------------- linear ----------------
+// y[B][O] = act(x[B][F] . w[O][F]^T + b[O]);  relu optional
+void launch_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, bool relu,
+                       cudaStream_t st);
+// dx[B][F] = dy[B][O] . w[O][F]
+void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, cudaStream_t st);
+// dw[O][F] (+)= dy^T . x ; db[O] (+)= sum_b dy
+void launch_linear_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int F, int O, bool accumulate,
+                         cudaStream_t st);
+// dy *= (y > 0)  (ReLU backward through the saved post-activation)
+void launch_relu_bwd(const float* y, float* dy, long long n, cudaStream_t st);
+
+// ---------------- losses ----------------
+size_t mse3_scratch_bytes(int B, long long per_sample);
+void launch_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
+                 float* out /*[B][3]*/, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st);
+// mu_logvar [B][2z]; z = mu + eps*exp(.5 lv); kl[b] = -.5 sum(1 + lv - mu^2 - e^lv)
+void launch_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int B, int zdim, cudaStream_t st);
+// d(mu_logvar)[B][2z] = dz-path + ckl[b]*KL-path.   dz may be null (no decoder path), ckl may be null
+void launch_latent_bwd(const float* mu_logvar, const float* eps, const float* dz, const float* ckl, float ckl_const,
+                       float* dml, int B, int zdim, cudaStream_t st);
+
+struct StepCoefs;   // device-side per-sample coefficients, see loss kernels
+// E-step scalar assembly (:563-586): consumes mse[B][3] and kl_real/kl_rec/kl_fake [B] each
+void launch_e_loss_finalize(const float* mse, const float* kl_real, const float* kl_rec, const float* kl_fake, int B,
+                            float beta_kl, float beta_rec, float beta_neg, float scale, float* stats,
+                            float* coef /*[4][B]: c_rec, c_rr, c_rf, (unused)*/, float* ckl_rec, float* ckl_fake,
+                            cudaStream_t st);
+// D-step scalar assembly (:599-620)
+void launch_d_loss_finalize(const float* mse, const float* kl_rec, const float* kl_fake, int B, float beta_kl,
+                            float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st);
+// vae-step scalar assembly (:520-523)
+void launch_vae_loss_finalize(const float* mse, const float* kl, int B, float beta_kl, float beta_rec, float* stats,
+                              cudaStream_t st);
+// gradient seeds on images (NHWC, per_sample floats each):
+//   d_rec      = a_rec[b]*(rec-real) + a_t[b]*(rec_rec-rec)*(-1)      (a_* may be per-sample arrays or constants)
+//   d_rec_rec  = a_t[b]*(rec_rec-rec)
+//   d_rec_fake = a_f[b]*(rec_fake-fake);   d_fake = -a_f[b]*(rec_fake-fake) if d_fake != null
+// a_rec is a constant; a_t / a_f are per-sample arrays when *_arr != null else constants.
+void launch_loss_seed(const float* real, const float* rec, const float* rec_rec, const float* fake,
+                      const float* rec_fake, float a_rec, const float* a_t_arr, float a_t, const float* a_f_arr,
+                      float a_f, bool target_grad_rec, float* d_rec, float* d_rec_rec, float* d_rec_fake, float* d_fake,
+                      int B, long long per_sample, cudaStream_t st);
+
+// ---------------- optimiser ----------------
+void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
+                 float b1, float b2, float eps, long long step, cudaStream_t st);
+
+}  // namespace sivae

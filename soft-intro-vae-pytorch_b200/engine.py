@@ -1,0 +1,171 @@
+"""Torch-side owner of the memory the native engine borrows.
+
+torch is plumbing here: it allocates the flat fp32 parameter / gradient / Adam / BN buffers and the workspace
+arena, exposes them as ``nn.Parameter`` views with the reference's logical shapes (conv filters are
+``[Cout,Cin,kh,kw]`` views with channels_last strides over the engine's ``[Cout][kh][kw][Cin]`` storage), supplies
+the CUDA stream, and (multi-GPU) all-reduces the flat gradient buffers over NCCL.  All compute is in
+libsivae_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+def make_hyper(beta_kl, beta_rec, beta_neg, gamma_r, scale):
+    return L.Hyper(float(beta_kl), float(beta_rec), float(beta_neg), float(gamma_r), float(scale))
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NetMemory:
+    """Flat buffers of one net (encoder / decoder / target decoder)."""
+
+    def __init__(self, handle, net, device, trainable=True):
+        lib = L.load()
+        self.net = net
+        n = lib.sivae_param_count(handle, net)
+        self.params = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=device) if trainable else None
+        self.m = torch.zeros(n, dtype=torch.float32, device=device) if trainable else None
+        self.v = torch.zeros(n, dtype=torch.float32, device=device) if trainable else None
+        self.bn = torch.zeros(lib.sivae_bn_floats(handle, net), dtype=torch.float32, device=device)
+        self.nbt = torch.zeros(max(1, lib.sivae_num_bn(handle, net)), dtype=torch.int64, device=device)
+        self.tensors = []
+        for i in range(lib.sivae_num_tensors(handle, net)):
+            ti = L.TensorInfo()
+            L.check(lib.sivae_tensor(handle, net, i, C.byref(ti)), "sivae_tensor")
+            self.tensors.append((ti.name.decode(), ti.kind, ti.offset, ti.numel, tuple(ti.shape[:ti.ndim])))
+        self.bns = []
+        for i in range(lib.sivae_num_bn(handle, net)):
+            bi = L.BnInfo()
+            L.check(lib.sivae_bn(handle, net, i, C.byref(bi)), "sivae_bn")
+            self.bns.append((bi.name.decode(), bi.channels, bi.bn_offset, bi.index))
+
+    @staticmethod
+    def view(flat, kind, off, numel, shape):
+        v = flat[off:off + numel]
+        if kind == L.T_CONV:
+            co, ci, kh, kw = shape
+            return v.view(co, kh, kw, ci).permute(0, 3, 1, 2)      # logical [Cout,Cin,kh,kw], channels_last strides
+        return v.view(*shape)
+
+
+class Engine:
+    """One native engine instance bound to the modules of a SoftIntroVAE."""
+
+    def __init__(self, cdim, zdim, channels, image_size, max_batch, device, bootstrap=False, conv_backend=L.CONV_AUTO):
+        lib = L.load()
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("the B200 engine runs on CUDA devices only (no CPU fallback); got %s" % (device,))
+        self.device = torch.device(device)
+        self.cfg = L.Config()
+        self.cfg.cdim, self.cfg.zdim, self.cfg.image_size = int(cdim), int(zdim), int(image_size)
+        self.cfg.n_channels = len(channels)
+        for i, c in enumerate(channels):
+            self.cfg.channels[i] = int(c)
+        self.cfg.max_batch = int(max_batch)
+        self.cfg.variant = 1 if bootstrap else 0
+        self.cfg.conv_backend = int(conv_backend)
+        self.bootstrap = bootstrap
+        self.handle = C.c_void_p()
+        L.check(lib.sivae_create(C.byref(self.cfg), C.byref(self.handle)), "sivae_create")
+        with torch.cuda.device(self.device):
+            self.mem = {L.NET_ENCODER: NetMemory(self.handle, L.NET_ENCODER, self.device),
+                        L.NET_DECODER: NetMemory(self.handle, L.NET_DECODER, self.device)}
+            if bootstrap:
+                self.mem[L.NET_TARGET] = NetMemory(self.handle, L.NET_TARGET, self.device, trainable=False)
+            self.stats = torch.zeros(16, dtype=torch.float32, device=self.device)
+            self._bind()
+
+    def _bind(self):
+        lib = L.load()
+        for net, m in self.mem.items():
+            L.check(lib.sivae_bind_net(self.handle, net, L.ptr(m.params), L.ptr(m.grads), L.ptr(m.m), L.ptr(m.v),
+                                       L.ptr(m.bn), L.ptr(m.nbt)), "sivae_bind_net")
+        nbytes = lib.sivae_workspace_bytes(self.handle)
+        self.workspace = torch.empty(nbytes + 512, dtype=torch.uint8, device=self.device)
+        base = self.workspace.data_ptr()
+        self._ws_ptr = (base + 255) // 256 * 256
+        L.check(lib.sivae_bind_workspace(self.handle, C.c_void_p(self._ws_ptr), nbytes), "sivae_bind_workspace")
+        self.workspace_bytes = nbytes
+
+    @property
+    def max_batch(self):
+        return self.cfg.max_batch
+
+    def grow(self, max_batch):
+        """Re-create the native handle with a larger workspace; parameter / optimiser memory is kept."""
+        lib = L.load()
+        steps = {net: lib.sivae_adam_get_step(self.handle, net) for net in self.mem}
+        lib.sivae_destroy(self.handle)
+        self.cfg.max_batch = int(max_batch)
+        self.handle = C.c_void_p()
+        L.check(lib.sivae_create(C.byref(self.cfg), C.byref(self.handle)), "sivae_create")
+        self.workspace = None
+        with torch.cuda.device(self.device):
+            self._bind()
+        for net, s in steps.items():
+            lib.sivae_adam_set_step(self.handle, net, s)
+
+    def close(self):
+        if self.handle:
+            L.load().sivae_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- steps --------------------------------------------------------------------------------------------
+    def params_changed(self, net=None):
+        lib = L.load()
+        for n in (self.mem if net is None else [net]):
+            L.check(lib.sivae_params_changed(self.handle, n), "sivae_params_changed")
+
+    def e_step(self, real, noise, eps3, hp):
+        B = real.shape[0]
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_e_step(self.handle, L.ptr(real), L.ptr(noise), L.ptr(eps3), B, C.byref(hp),
+                                          L.ptr(self.stats), _stream()), "sivae_e_step")
+
+    def d_step(self, eps2, hp):
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_d_step(self.handle, L.ptr(eps2), C.byref(hp), L.ptr(self.stats), _stream()), "sivae_d_step")
+
+    def vae_step(self, real, eps, hp):
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_vae_step(self.handle, L.ptr(real), L.ptr(eps), real.shape[0], C.byref(hp),
+                                            L.ptr(self.stats), _stream()), "sivae_vae_step")
+
+    def adam(self, net, lr, grad_scale=1.0):
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_adam_step(self.handle, net, float(lr), float(grad_scale), _stream()), "sivae_adam_step")
+
+    def encode(self, x, train):
+        B = x.shape[0]
+        mu = torch.empty(B, self.cfg.zdim, dtype=torch.float32, device=self.device)
+        lv = torch.empty_like(mu)
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_encode(self.handle, L.ptr(x), B, L.ptr(mu), L.ptr(lv), 1 if train else 0, _stream()), "sivae_encode")
+        return mu, lv
+
+    def decode(self, z, train, net=L.NET_DECODER):
+        B = z.shape[0]
+        out = torch.empty(B, self.cfg.cdim, self.cfg.image_size, self.cfg.image_size, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_decode(self.handle, net, L.ptr(z), B, L.ptr(out), 1 if train else 0, _stream()), "sivae_decode")
+        return out
+
+    def last_image(self, slot):
+        """decoder output of the last half step as NCHW: 0 = fake, 1 = rec, 2 = rec_rec, 3 = rec_fake"""
+        B = L.load().sivae_last_batch(self.handle)
+        out = torch.empty(B, self.cfg.cdim, self.cfg.image_size, self.cfg.image_size, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_last_image(self.handle, int(slot), L.ptr(out), _stream()), "sivae_last_image")
+        return out

@@ -1,0 +1,122 @@
+"""Shared harness: run one teacher-forced introspective iteration (E half, Adam, D half, Adam) through the engine's
+C ABI and through the oracle from identical state and inputs, and compare.  Used by the -m gpu parity tests and by
+__graft_entry__.smoke().  (Test infrastructure: the only place besides bench.py's baseline legs that touches oracle/.)"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "soft-intro-vae-pytorch_b200"
+
+
+def mods(bootstrap=False):
+    L = importlib.import_module(PKG + ".lib")
+    name = ".train_soft_intro_vae_bootstrap" if bootstrap else ".train_soft_intro_vae"
+    return L, importlib.import_module(PKG + name)
+
+
+def make_inputs(cfg, batch, seed):
+    g = torch.Generator().manual_seed(1000 + seed)
+    real = torch.rand(batch, cfg["cdim"], cfg["image_size"], cfg["image_size"], generator=g)
+    noise = torch.randn(batch, cfg["zdim"], generator=g)
+    eps = torch.randn(5, batch, cfg["zdim"], generator=g)
+    return real, noise, eps
+
+
+DEFAULT_HP = dict(beta_kl=1.0, beta_rec=1.0, beta_neg=256.0, gamma_r=1e-8, lr_e=2e-4, lr_d=2e-4)
+
+
+def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=None, inputs=None, hp=None, device="cuda:0"):
+    L, M = mods(bootstrap)
+    E = importlib.import_module(PKG + ".engine")
+    hp = dict(DEFAULT_HP, **(hp or {}))
+    if "scale" not in hp:
+        hp["scale"] = 1.0 / (cfg["cdim"] * cfg["image_size"] ** 2)
+    if bootstrap and "gamma_r" not in (hp or {}):
+        pass
+    torch.manual_seed(seed)
+    model = M.SoftIntroVAE(cdim=cfg["cdim"], zdim=cfg["zdim"], channels=cfg["channels"], image_size=cfg["image_size"])
+    if init_sd is not None:
+        model.load_state_dict(init_sd)
+    model._conv_backend = backend
+    init = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(device)
+    real, noise, eps = inputs if inputs is not None else make_inputs(cfg, batch, seed)
+    real, noise, eps = real.to(device), noise.to(device), eps.to(device).contiguous()
+    eng = model.reserve(batch)
+    h = E.make_hyper(hp["beta_kl"], hp["beta_rec"], hp["beta_neg"], hp["gamma_r"], hp["scale"])
+    eng.e_step(real, noise, eps[:3].contiguous(), h)
+    torch.cuda.synchronize()
+    grads_e = {"encoder." + n: p.grad.detach().clone().cpu().contiguous() for n, p in model.encoder.named_parameters()}
+    imgs_e = {k: eng.last_image(i).cpu() for i, k in enumerate(["fake", "rec", "rec_rec", "rec_fake"])}
+    eng.adam(L.NET_ENCODER, hp["lr_e"])
+    eng.d_step(eps[3:].contiguous(), h)
+    torch.cuda.synchronize()
+    grads_d = {"decoder." + n: p.grad.detach().clone().cpu().contiguous() for n, p in model.decoder.named_parameters()}
+    eng.adam(L.NET_DECODER, hp["lr_d"])
+    torch.cuda.synchronize()
+    st = eng.stats.cpu()
+    scal = dict(loss_rec_e=st[0].item(), lossE_real_kl=st[1].item(), expelbo_rec=st[2].item(), expelbo_fake=st[3].item(),
+                lossE=st[4].item(), loss_rec=st[5].item(), lossD_rec_kl=st[6].item(), lossD_fake_kl=st[7].item(),
+                loss_rec_rec=st[8].item(), loss_fake_rec=st[9].item(), lossD=st[10].item(), nan=st[15].item())
+    post = {k: v.detach().clone().cpu().contiguous() for k, v in model.state_dict().items()}
+    return dict(scalars=scal, grads_e=grads_e, grads_d=grads_d, post=post, init=init, images_e=imgs_e, model=model)
+
+
+def run_oracle_iteration(cfg, batch, seed, bootstrap=False, init_sd=None, inputs=None, hp=None, dtype=torch.float64):
+    from oracle import sivae_oracle as O
+    hp = dict(DEFAULT_HP, **(hp or {}))
+    if "scale" not in hp:
+        hp["scale"] = 1.0 / (cfg["cdim"] * cfg["image_size"] ** 2)
+    arch = O.Arch(cdim=cfg["cdim"], zdim=cfg["zdim"], channels=cfg["channels"], image_size=cfg["image_size"])
+    sd = O.clone_sd(init_sd if init_sd is not None else O.make_state_dict(arch, seed=seed, bootstrap=bootstrap), dtype)
+    real, noise, eps = inputs if inputs is not None else make_inputs(cfg, batch, seed)
+    real, noise, eps = real.to(dtype), noise.to(dtype), [e.to(dtype) for e in eps]
+    ohp = O.Hyper(beta_kl=hp["beta_kl"], beta_rec=hp["beta_rec"], beta_neg=hp["beta_neg"], gamma_r=hp["gamma_r"],
+                  scale=hp["scale"], lr_e=hp["lr_e"], lr_d=hp["lr_d"])
+    scal, ge, gd, te, td = O.full_iteration(sd, arch, real, noise, eps, ohp, O.AdamState(), O.AdamState(), bootstrap)
+    return dict(scalars=scal, grads_e=ge, grads_d=gd, post=sd, images_e=te)
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def compare(eng, ora, tol, label="", lr=2e-4, verbose=True):
+    """tol: relative tolerance for scalars and relative-L2 tolerance for tensors (gradients, BN statistics)."""
+    worst = {}
+    es, os_ = eng["scalars"], ora["scalars"]
+    assert es.get("nan", 0.0) == 0.0, label + ": NaN flag set"
+    for k in ("loss_rec_e", "lossE_real_kl", "expelbo_rec", "expelbo_fake", "lossE", "loss_rec", "lossD_rec_kl",
+              "lossD_fake_kl", "loss_rec_rec", "loss_fake_rec", "lossD"):
+        r = abs(es[k] - os_[k]) / (abs(os_[k]) + 1e-30)
+        worst["scalar:" + k] = r
+        assert r < tol, "%s: scalar %s engine %.8g oracle %.8g rel %.3g > %.3g" % (label, k, es[k], os_[k], r, tol)
+    for name in ("grads_e", "grads_d"):
+        assert set(eng[name]) == set(ora[name]), label + ": gradient key sets differ"
+        for k in ora[name]:
+            r = rel_l2(eng[name][k], ora[name][k])
+            worst[name + ":" + k] = r
+            assert r < 10 * tol, "%s: %s[%s] rel-L2 %.3g > %.3g" % (label, name, k, r, 10 * tol)
+    for k, v in ora["post"].items():
+        e = eng["post"][k]
+        if k.endswith("num_batches_tracked"):
+            assert int(e) == int(v), "%s: %s %d != %d" % (label, k, int(e), int(v))     # integer work: exact
+        elif k.endswith(("running_mean", "running_var")):
+            r = float((e.double() - v.double()).abs().max() / (v.double().abs().max() + 1e-12))
+            worst["bn:" + k] = r
+            assert r < 10 * tol, "%s: %s max-rel %.3g" % (label, k, r)
+        else:
+            # one Adam step from zero moments moves each weight by ~lr*sign(g): bounded check here, the Adam kernel
+            # itself is unit-tested against torch.optim.Adam with identical gradients
+            d = float((e.double() - v.double()).abs().max())
+            assert d <= 2.05 * lr + 1e-7, "%s: post-step %s differs by %.3g" % (label, k, d)
+    if verbose:
+        top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+        print("[%s] worst deviations: %s" % (label, ", ".join("%s=%.2e" % kv for kv in top)))
+    return worst

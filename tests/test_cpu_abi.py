@@ -1,0 +1,125 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/sivae.h declares, the model
+description queried through it matches the reference's state_dict schema, the Python boundary mirrors the
+reference module's names/signatures, and the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes as C
+import importlib
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from tests.step_harness import PKG, ROOT
+
+L = importlib.import_module(PKG + ".lib")
+M = importlib.import_module(PKG + ".train_soft_intro_vae")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sivae.h")).read()
+    declared = set(re.findall(r"\b(sivae_[a-z0-9_]+)\s*\(", header))
+    lib = L.load()
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libsivae_b200.so does not export " + name
+    assert declared == set(L.EXPORTS), (declared ^ set(L.EXPORTS))
+    assert lib.sivae_version() >= 100
+
+
+def _engine_schema(cfg, variant=0):
+    lib = L.load()
+    c = L.Config()
+    c.cdim, c.zdim, c.image_size, c.n_channels = cfg["cdim"], cfg["zdim"], cfg["image_size"], len(cfg["channels"])
+    for i, ch in enumerate(cfg["channels"]):
+        c.channels[i] = ch
+    c.max_batch, c.variant, c.conv_backend = 4, variant, 0
+    h = C.c_void_p()
+    L.check(lib.sivae_create(C.byref(c), C.byref(h)), "create")
+    out = {}
+    for net, prefix in ((0, "encoder."), (1, "decoder.")) + (((2, "target_decoder."),) if variant else ()):
+        for i in range(lib.sivae_num_tensors(h, net)):
+            ti = L.TensorInfo()
+            L.check(lib.sivae_tensor(h, net, i, C.byref(ti)), "tensor")
+            out[prefix + ti.name.decode()] = tuple(ti.shape[:ti.ndim])
+    ws = lib.sivae_workspace_bytes(h)
+    lib.sivae_destroy(h)
+    return out, ws
+
+
+@pytest.mark.parametrize("cfg", [dict(cdim=3, zdim=128, channels=[64, 128, 256], image_size=32),
+                                 dict(cdim=3, zdim=512, channels=[64, 128, 256, 512, 512, 512], image_size=256),
+                                 dict(cdim=1, zdim=32, channels=[64, 128], image_size=28 + 4)])
+def test_engine_schema_equals_reference_state_dict(cfg):
+    """index / shape work must be bit-exact: names, order and shapes of every parameter"""
+    from oracle import sivae_oracle as O
+    sd = O.make_state_dict(O.Arch(**cfg), seed=0)
+    want = {k: tuple(v.shape) for k, v in sd.items() if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
+    got, ws = _engine_schema(cfg)
+    assert list(got.keys()) == list(want.keys())
+    assert got == want
+    assert ws > 0
+
+
+def test_create_rejects_bad_configs():
+    lib = L.load()
+    c = L.Config()
+    c.cdim, c.zdim, c.image_size, c.n_channels, c.max_batch = 3, 8, 30, 2, 1      # 30 not divisible by 4
+    c.channels[0], c.channels[1] = 32, 64
+    h = C.c_void_p()
+    assert lib.sivae_create(C.byref(c), C.byref(h)) != 0
+    assert b"image_size" in lib.sivae_last_error()
+
+
+def test_boundary_mirrors_reference_signatures():
+    want = {
+        "train_soft_intro_vae": ["dataset", "z_dim", "lr_e", "lr_d", "batch_size", "num_workers", "start_epoch",
+                                 "exit_on_negative_diff", "num_epochs", "num_vae", "save_interval", "recon_loss_type",
+                                 "beta_kl", "beta_rec", "beta_neg", "test_iter", "seed", "pretrained", "device", "num_row",
+                                 "gamma_r", "with_fid"],
+        "calc_kl": ["logvar", "mu", "mu_o", "logvar_o", "reduce"],
+        "reparameterize": ["mu", "logvar"],
+        "calc_reconstruction_loss": ["x", "recon_x", "loss_type", "reduction"],
+        "load_model": ["model", "pretrained", "device"],
+        "save_checkpoint": ["model", "epoch", "iteration", "prefix"],
+    }
+    for fn, args in want.items():
+        assert list(inspect.signature(getattr(M, fn)).parameters) == args, fn
+    d = inspect.signature(M.train_soft_intro_vae).parameters
+    assert d["gamma_r"].default == 1e-8 and d["batch_size"].default == 128 and d["num_epochs"].default == 250
+    assert list(inspect.signature(M.SoftIntroVAE.__init__).parameters)[1:] == ["cdim", "zdim", "channels", "image_size", "conditional", "cond_dim"]
+    assert list(inspect.signature(M.Decoder.__init__).parameters)[1:] == ["cdim", "zdim", "channels", "image_size", "conditional", "conv_input_size", "cond_dim"]
+    assert list(inspect.signature(M.ResidualBlock.__init__).parameters)[1:] == ["inc", "outc", "groups", "scale"]
+
+
+def test_model_init_is_bit_identical_to_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "tiny_std.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    model = M.SoftIntroVAE(**g["arch"])
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g["init"].keys())
+    for k, v in g["init"].items():
+        assert torch.equal(sd[k], v), k
+
+
+def test_no_cpu_fallback():
+    model = M.SoftIntroVAE(cdim=3, zdim=8, channels=[32, 32], image_size=8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(RuntimeError, match="cuda"):
+        M.train_soft_intro_vae(dataset="synthetic32", device=torch.device("cpu"), num_epochs=1)
+
+
+def test_helpers_match_oracle():
+    from oracle import sivae_oracle as O
+    mu, lv = torch.randn(5, 7), torch.randn(5, 7) * 0.3
+    for red in ("sum", "mean", "none"):
+        assert torch.allclose(M.calc_kl(lv, mu, reduce=red), O.calc_kl(lv, mu, red), rtol=1e-6)
+    x, y = torch.rand(4, 3, 8, 8), torch.rand(4, 3, 8, 8)
+    for red in ("sum", "mean", "none"):
+        assert torch.allclose(M.calc_reconstruction_loss(x, y, "mse", red), O.rec_loss(x, y, red), rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        M.calc_reconstruction_loss(x, y, "mse", "bogus")
+    with pytest.raises(NotImplementedError):
+        M.calc_reconstruction_loss(x, y, "huber", "sum")
+    assert M.str_to_list("1,2,3") == [1, 2, 3] and M.is_image_file("a.png") and not M.is_image_file("a.txt")

@@ -1,0 +1,214 @@
+"""-m gpu: single-kernel parity through the C ABI against plain torch fp32/fp64 references of the same op."""
+import ctypes as C
+import importlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.step_harness import PKG
+
+pytestmark = pytest.mark.gpu
+L = importlib.import_module(PKG + ".lib")
+DEV = "cuda:0"
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _nhwc(x):           # NCHW tensor -> contiguous NHWC storage
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _krsc(w):           # [Cout,Cin,kh,kw] -> [Cout,kh,kw,Cin]
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _round_tf32(x):
+    # round-to-nearest (ties away, like cvt.rna) to 10 mantissa bits
+    i = x.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF)
+    return r.view(torch.float32)
+
+
+CONV_SHAPES = [
+    # N, H, W, Cin, Cout, k
+    (2, 8, 8, 3, 32, 5),       # stem-like
+    (2, 8, 8, 32, 3, 5),       # predict-like
+    (3, 16, 16, 32, 64, 3),
+    (2, 4, 4, 64, 64, 3),
+    (5, 8, 8, 32, 64, 1),      # conv_expand
+    (1, 6, 10, 8, 12, 3),      # ragged / non-power-of-two
+]
+
+
+def _conv_case(N, H, W, Cin, Cout, k, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    dy = torch.randn(N, Cout, H, W, generator=g)
+    return x, w, dy
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("backend", [L.CONV_SIMT, L.CONV_TCGEN05])
+def test_conv_fwd_dgrad_wgrad(shape, backend):
+    lib = L.load()
+    N, H, W, Cin, Cout, k = shape
+    x, w, dy = _conv_case(*shape)
+    tc = backend == L.CONV_TCGEN05
+    if tc:
+        x, w, dy = _round_tf32(x), _round_tf32(w), _round_tf32(dy)      # operands exactly representable in tf32
+    xd, wd, dyd = x.double(), w.double(), dy.double()
+    xd.requires_grad_(True)
+    wd.requires_grad_(True)
+    bias = torch.randn(Cout)
+    addend = torch.randn(N, Cout, H, W)
+    y_ref = F.conv2d(xd, wd, bias.double(), 1, k // 2) + addend.double()
+    y_ref.backward(dyd)
+    tol = 2e-5
+    xg, wg, dyg = _nhwc(x).to(DEV), _krsc(w).to(DEV), _nhwc(dy).to(DEV)
+    bg, ag = bias.to(DEV), _nhwc(addend).to(DEV)
+    y = torch.empty(N, H, W, Cout, device=DEV)
+    rc = lib.sivae_conv2d_fwd(L.ptr(xg), L.ptr(wg), L.ptr(bg), L.ptr(ag), L.ptr(y), N, H, W, Cin, Cout, k, backend, _s())
+    if tc and rc == -7:
+        pytest.skip("shape not eligible for the tcgen05 kernel (SIMT handles it)")
+    L.check(rc, "conv fwd")
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), _nhwc(y_ref.detach())) < tol
+    # dgrad
+    ws = torch.empty(max(1 << 22, Cout * Cin * k * k * 4 * 64), dtype=torch.uint8, device=DEV)
+    dx = torch.empty(N, H, W, Cin, device=DEV)
+    rc = lib.sivae_conv2d_dgrad(L.ptr(dyg), L.ptr(wg), None, L.ptr(dx), N, H, W, Cin, Cout, k, backend, L.ptr(ws), ws.numel(), _s())
+    if not (tc and rc == -7):
+        L.check(rc, "conv dgrad")
+        torch.cuda.synchronize()
+        assert _rel(dx.cpu(), _nhwc(xd.grad)) < tol
+    # wgrad (accumulate on top of a known value)
+    dw = torch.full((Cout, k, k, Cin), 0.5, device=DEV)
+    rc = lib.sivae_conv2d_wgrad(L.ptr(xg), L.ptr(dyg), L.ptr(dw), N, H, W, Cin, Cout, k, 1, backend, L.ptr(ws), ws.numel(), _s())
+    if not (tc and rc == -7):
+        L.check(rc, "conv wgrad")
+        torch.cuda.synchronize()
+        assert _rel(dw.cpu() - 0.5, _krsc(wd.grad)) < tol
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("with_id", [False, True])
+def test_bn_act_fwd_bwd(mode, with_id):
+    lib = L.load()
+    N, H, W, Cc = 3, 8, 8, 32
+    g = torch.Generator().manual_seed(5)
+    t = torch.randn(N, Cc, H, W, generator=g) * 2 + 0.3
+    idn = torch.randn(N, Cc, H, W, generator=g) if with_id else None
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.1
+    rm, rv = torch.randn(Cc, generator=g) * 0.1, torch.rand(Cc, generator=g) + 0.5
+    td = t.double().requires_grad_(True)
+    idd = idn.double().requires_grad_(True) if with_id else None
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rmd, rvd = rm.double().clone(), rv.double().clone()
+    y = F.batch_norm(td, rmd, rvd, gd, bd, True, 0.1, 1e-5)
+    if with_id:
+        y = y + idd
+    y = F.leaky_relu(y, 0.2)
+    if mode == 1:
+        y = F.avg_pool2d(y, 2)
+    elif mode == 2:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    dout = torch.randn(y.shape, generator=g)
+    y.backward(dout.double())
+    tg = _nhwc(t).to(DEV)
+    ig = _nhwc(idn).to(DEV) if with_id else None
+    gg, bg, rmg, rvg = gamma.to(DEV), beta.to(DEV), rm.to(DEV), rv.to(DEV)
+    nbt = torch.zeros(1, dtype=torch.int64, device=DEV)
+    mi = torch.empty(2 * Cc, device=DEV)
+    out = torch.empty(_nhwc(y.detach()).shape, device=DEV)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    L.check(lib.sivae_bn_act_fwd(L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(rmg), L.ptr(rvg), L.ptr(nbt), L.ptr(mi),
+                                 L.ptr(out), N, H, W, Cc, mode, 1, L.ptr(ws), ws.numel(), _s()), "bn fwd")
+    torch.cuda.synchronize()
+    assert _rel(out.cpu(), _nhwc(y.detach())) < 1e-5
+    assert torch.allclose(rmg.cpu().double(), rmd, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rvg.cpu().double(), rvd, rtol=1e-5, atol=1e-6)
+    assert int(nbt) == 1
+    dt = torch.empty_like(tg)
+    gi = torch.empty_like(tg)
+    dgam, dbet = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    L.check(lib.sivae_bn_act_bwd(L.ptr(_nhwc(dout).to(DEV)), L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(mi), L.ptr(dt),
+                                 L.ptr(gi), L.ptr(dgam), L.ptr(dbet), 0, N, H, W, Cc, mode, L.ptr(ws), ws.numel(), _s()), "bn bwd")
+    torch.cuda.synchronize()
+    assert _rel(dt.cpu(), _nhwc(td.grad)) < 2e-5
+    assert _rel(dgam.cpu(), gd.grad) < 2e-5 and _rel(dbet.cpu(), bd.grad) < 2e-5
+    if with_id:
+        assert _rel(gi.cpu(), _nhwc(idd.grad)) < 2e-5
+
+
+def test_bn_eval_mode():
+    lib = L.load()
+    N, H, W, Cc = 2, 4, 4, 8
+    t = torch.randn(N, Cc, H, W)
+    gamma, beta, rm, rv = torch.rand(Cc) + 0.5, torch.randn(Cc), torch.randn(Cc), torch.rand(Cc) + 0.5
+    y = F.leaky_relu(F.batch_norm(t, rm.clone(), rv.clone(), gamma, beta, False, 0.1, 1e-5), 0.2)
+    tg = _nhwc(t).to(DEV)
+    rmg, rvg = rm.to(DEV), rv.to(DEV)
+    mi = torch.empty(2 * Cc, device=DEV)
+    out = torch.empty_like(tg)
+    ws = torch.empty(1 << 16, dtype=torch.uint8, device=DEV)
+    L.check(lib.sivae_bn_act_fwd(L.ptr(tg), None, L.ptr(gamma.to(DEV)), L.ptr(beta.to(DEV)), L.ptr(rmg), L.ptr(rvg), None,
+                                 L.ptr(mi), L.ptr(out), N, H, W, Cc, 0, 0, L.ptr(ws), ws.numel(), _s()), "bn eval")
+    torch.cuda.synchronize()
+    assert _rel(out.cpu(), _nhwc(y)) < 1e-5
+    assert torch.equal(rmg.cpu(), rm) and torch.equal(rvg.cpu(), rv)       # eval mode must not touch the buffers
+
+
+@pytest.mark.parametrize("B,per", [(4, 3 * 32 * 32), (3, 3 * 16 * 16), (2, 3 * 128 * 128), (1, 4)])
+def test_mse3_fused_loss(B, per):
+    lib = L.load()
+    g = torch.Generator().manual_seed(B)
+    t = [torch.rand(B, per, generator=g) for _ in range(5)]
+    real, rec, rec_rec, fake, rec_fake = t
+    ref = torch.stack([(rec.double() - real.double()).pow(2).sum(1), (rec_rec.double() - rec.double()).pow(2).sum(1),
+                       (rec_fake.double() - fake.double()).pow(2).sum(1)], 1)
+    d = [x.to(DEV) for x in t]
+    out = torch.empty(B, 3, device=DEV)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    L.check(lib.sivae_mse3(*[L.ptr(x) for x in d], L.ptr(out), B, per, L.ptr(ws), ws.numel(), _s()), "mse3")
+    torch.cuda.synchronize()
+    assert torch.allclose(out.cpu().double(), ref, rtol=2e-6)
+
+
+def test_kl_reparam():
+    lib = L.load()
+    B, z = 7, 48
+    ml = torch.randn(B, 2 * z) * 0.5
+    eps = torch.randn(B, z)
+    mu, lv = ml[:, :z].double(), ml[:, z:].double()
+    kl_ref = -0.5 * (1 + lv - mu.pow(2) - lv.exp()).sum(1)
+    z_ref = mu + eps.double() * torch.exp(0.5 * lv)
+    zz, kl = torch.empty(B, z, device=DEV), torch.empty(B, device=DEV)
+    L.check(lib.sivae_kl_reparam(L.ptr(ml.to(DEV)), L.ptr(eps.to(DEV)), L.ptr(zz), L.ptr(kl), B, z, _s()), "kl")
+    torch.cuda.synchronize()
+    assert torch.allclose(kl.cpu().double(), kl_ref, rtol=1e-5)
+    assert torch.allclose(zz.cpu().double(), z_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_adam_matches_torch_optim():
+    lib = L.load()
+    n = 10007
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.randn(n, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=2e-4)
+    p, m, v = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * 10.0 ** float(torch.randint(-6, 2, (1,), generator=g))
+        p_ref.grad = grad.clone()
+        opt.step()
+        L.check(lib.sivae_adam_flat(L.ptr(p), L.ptr((grad * 4).to(DEV)), L.ptr(m), L.ptr(v), n, 2e-4, 0.25, step, _s()), "adam")
+    torch.cuda.synchronize()
+    assert torch.allclose(p.cpu(), p_ref.detach(), rtol=0, atol=2e-7)

@@ -1,0 +1,125 @@
+"""-m gpu: the parity tests proper -- one teacher-forced introspective iteration through the C ABI compared with
+(a) the committed golden vectors of the UNMODIFIED reference and (b) the fp64 oracle on seeded inputs.
+
+Tolerances (relative; tensors: relative L2):
+  SIMT fp32 path      scalars 2e-5, gradients / BN statistics 2e-4   (fp32 summation-order noise only)
+  tcgen05 TF32 path   scalars 1e-3 (exp-ELBO terms amplify operand rounding by 2*scale*beta_neg*kl), gradients 1e-2
+"""
+import os
+
+import pytest
+import torch
+
+from tests.step_harness import compare, run_engine_iteration, run_oracle_iteration
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = {1: 2e-5, 0: 1e-3}    # backend id -> scalar tolerance (tensor tolerance is 10x)
+
+
+def _golden_as_oracle(g, bootstrap=False):
+    s = g["scalars"]
+    scal = dict(loss_rec=s["rec_err"], lossE_real_kl=s["kl_real"], lossD_fake_kl=s["kl_fake"], lossD_rec_kl=s["kl_rec"],
+                expelbo_fake=s["expelbo_f"])
+    return scal
+
+
+@pytest.mark.parametrize("backend", [1, 0])
+def test_tiny_step_vs_reference_golden(backend):
+    """engine vs the unmodified reference (tests/golden/tiny_std.pt: init, inputs, grads, post-step state)"""
+    g = torch.load(os.path.join(GOLD, "tiny_std.pt"), weights_only=False)
+    cfg = dict(g["arch"])
+    inputs = (g["real"], g["noise"], torch.stack(g["eps"]))
+    out = run_engine_iteration(cfg, g["batch"], g["seed"], backend=backend, init_sd=g["init"], inputs=inputs, hp=g["hyper"])
+    ora = run_oracle_iteration(cfg, g["batch"], g["seed"], init_sd=g["init"], inputs=inputs, hp=g["hyper"])
+    # the five scalars the reference logs, straight from the golden file
+    for k, v in _golden_as_oracle(g).items():
+        assert out["scalars"][k] == pytest.approx(v, rel=TOL[backend]), k
+    # gradients / BN buffers / num_batches_tracked against the reference's own tensors
+    ref = dict(scalars=ora["scalars"], grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
+    compare(out, ref, TOL[backend], label="tiny golden backend %d" % backend)
+
+
+@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("cfg,batch", [
+    (dict(cdim=3, zdim=128, channels=[64, 128, 256], image_size=32), 8),          # BASELINE config C (CIFAR shape)
+    (dict(cdim=3, zdim=32, channels=[32, 64, 64], image_size=32), 5),             # odd batch, identity + expand blocks
+])
+def test_step_vs_oracle(cfg, batch, backend):
+    out = run_engine_iteration(cfg, batch, seed=11, backend=backend)
+    ora = run_oracle_iteration(cfg, batch, seed=11)
+    compare(out, ora, TOL[backend], label="cfg %s backend %d" % (cfg["channels"], backend))
+
+
+def test_init_matches_golden_fingerprint():
+    """constructor RNG order + flat-buffer views: state_dict after .to(cuda) equals the reference init bit-exactly"""
+    g = torch.load(os.path.join(GOLD, "cifar_std_summary.pt"), weights_only=False)
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    torch.manual_seed(g["seed"])
+    model = M.SoftIntroVAE(**{k: g["arch"][k] for k in ("cdim", "zdim", "channels", "image_size")}).to("cuda:0")
+    model.reserve(2)
+    sd = model.state_dict()
+    for k, (s, a, n) in g["init_fp"].items():
+        assert float(sd[k].double().sum()) == pytest.approx(s, rel=1e-12, abs=1e-12), k
+        assert float(sd[k].double().abs().sum()) == pytest.approx(a, rel=1e-12, abs=1e-12), k
+
+
+def test_vae_step_vs_oracle():
+    import importlib
+    from oracle import sivae_oracle as O
+    from tests.step_harness import PKG, make_inputs
+    L = importlib.import_module(PKG + ".lib")
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    torch.manual_seed(2)
+    model = M.SoftIntroVAE(**cfg)
+    model._conv_backend = 1
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to("cuda:0")
+    real, _, eps = make_inputs(cfg, 6, 2)
+    eng = model.reserve(6)
+    hp = E.make_hyper(0.7, 1.3, 256.0, 1e-8, 1.0 / (3 * 32 * 32))
+    eng.vae_step(real.cuda(), eps[0].cuda().contiguous(), hp)
+    torch.cuda.synchronize()
+    sd = O.clone_sd(init, torch.float64)
+    scal, ge, gd = O.vae_step(sd, O.Arch(**cfg), real.double(), eps[0].double(), O.Hyper(beta_kl=0.7, beta_rec=1.3))
+    st = eng.stats.cpu()
+    assert st[11].item() == pytest.approx(scal["loss_rec"], rel=2e-5)
+    assert st[12].item() == pytest.approx(scal["loss_kl"], rel=2e-5)
+    assert st[13].item() == pytest.approx(scal["loss"], rel=2e-5)
+    for n, p in model.encoder.named_parameters():
+        r = (p.grad.cpu().double() - ge["encoder." + n]).norm() / (ge["encoder." + n].norm() + 1e-30)
+        assert r < 2e-4, n
+    for n, p in model.decoder.named_parameters():
+        r = (p.grad.cpu().double() - gd["decoder." + n]).norm() / (gd["decoder." + n].norm() + 1e-30)
+        assert r < 2e-4, n
+
+
+def test_inference_api_train_and_eval():
+    """model(x) / model.sample(z) through the engine in train and eval mode vs the oracle forward"""
+    import importlib
+    from oracle import sivae_oracle as O
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    cfg = dict(cdim=3, zdim=16, channels=[32, 64], image_size=16)
+    torch.manual_seed(4)
+    model = M.SoftIntroVAE(**cfg)
+    model._conv_backend = 1
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to("cuda:0")
+    x = torch.rand(4, 3, 16, 16)
+    arch = O.Arch(**cfg)
+    for train in (True, False):
+        model.train(train)
+        sd = O.clone_sd(init, torch.float64)
+        mu_o, lv_o = O.encoder_forward(sd, arch, x.double(), train=train)
+        y_o = O.decoder_forward(sd, arch, mu_o, train=train)
+        model.load_state_dict(init)
+        mu, lv, z, y = model(x.cuda(), deterministic=True)
+        assert torch.allclose(mu.cpu().double(), mu_o, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(lv.cpu().double(), lv_o, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(y.cpu().double(), y_o, rtol=1e-3, atol=1e-4)
+        assert y.shape == (4, 3, 16, 16)
