@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the Soft-IntroVAE introspective E+D step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--config H|M|C|Bs] [--impl reference]
+
+A "step" = one full introspective iteration: E half (4 decoder + 3 encoder forwards, loss, backward), NCCL all-reduce
+of the flat encoder gradient, Adam(encoder), D half (4 decoder + 2 encoder forwards, loss, backward), all-reduce of the
+decoder gradient, Adam(decoder) -- reference soft_intro_vae/train_soft_intro_vae.py:542-624.
+Default workload: config H = CelebA-HQ-shaped synthetic 256x256x3, z=512, channels [64,128,256,512,512,512],
+batch 32 per GPU (weak scaling), random-init weights, uniform [0,1) images.
+
+Output: ONE JSON line on rank 0 (contract in the task description): value = whole-job images/s with inputs resident
+in HBM (CUDA-event timed, max over ranks); e2e = same metric through the public Python API with host (pinned) inputs
+and the statistics read back every step; roofline of the dominant kernel class (tcgen05 conv) from CUDA events
+recorded around every convolution launch inside the timed region; cpu_baseline = the oracle (CPU restatement of the
+reference step) timed on the host cores on a bounded sample.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port; the unmodified reference
+needs /root/reference which does not exist on the GPU box) on the host cores with the same JSON shape.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "soft-intro-vae-pytorch_b200"
+
+CONFIGS = {
+    # name: (image_size, zdim, channels, per-GPU batch, beta_neg, bootstrap, GFLOP per image per iteration [SURVEY 8d])
+    "C": (32, 128, [64, 128, 256], 128, 256.0, False, 9.80),
+    "M": (128, 256, [64, 128, 256, 512, 512], 64, 256.0, False, 204.0),
+    "H": (256, 512, [64, 128, 256, 512, 512, 512], 32, 1024.0, False, 820.6),
+    "Bs": (256, 512, [64, 128, 256, 512, 512, 512], 16, 1024.0, True, 770.3),
+}
+WORKLOAD_NAMES = {"C": "CIFAR-10-shaped synthetic 32x32x3 z128 [64,128,256]",
+                  "M": "CelebA-shaped synthetic 128x128x3 z256 [64,128,256,512,512]",
+                  "H": "CelebA-HQ-shaped synthetic 256x256x3 z512 [64,128,256,512,512,512]",
+                  "Bs": "FFHQ-shaped synthetic 256x256x3 bootstrap (target decoder)"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), bf16_burst=d.get("bf16_tflops", 1590.0),
+                    bf16_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(self.rows))
+
+
+def build_model(cfg_name, device, batch):
+    import torch
+    size, zdim, channels, _, beta_neg, boot, _ = CONFIGS[cfg_name]
+    mod = importlib.import_module(PKG + (".train_soft_intro_vae_bootstrap" if boot else ".train_soft_intro_vae"))
+    torch.manual_seed(0)
+    stdout, sys.stdout = sys.stdout, open(os.devnull, "w")
+    try:
+        model = mod.SoftIntroVAE(cdim=3, zdim=zdim, channels=channels, image_size=size).to(device)
+    finally:
+        sys.stdout = stdout
+    model.train()
+    model.reserve(batch)
+    return mod, model
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    L = importlib.import_module(PKG + ".lib")
+    E = importlib.import_module(PKG + ".engine")
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[args.config]
+    batch = args.batch or batch
+    mod, model = build_model(args.config, device, batch)
+    eng = model._engine
+    lib = L.load()
+    hp = E.make_hyper(1.0, 1.0, beta_neg, 1.0 if boot else 1e-8, 1.0 / (3 * size * size))
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4        # distinct host batches cycled through (inputs larger than L2 at config H: 4 x 25 MB)
+    host_real = [torch.rand(batch, 3, size, size, generator=g).pin_memory() for _ in range(n_host)]
+    dev_real = [h.to(device) for h in host_real]
+    noise_d = torch.randn(batch, zdim, device=device)
+    eps_d = torch.randn(5, batch, zdim, device=device)
+    stats_host = torch.empty(16).pin_memory()
+
+    def step_resident(i):
+        mod.introspective_iteration(model, dev_real[i % n_host], noise_d, eps_d, hp, 2e-4, 2e-4)
+
+    def step_e2e(i):
+        noise = torch.randn(size=(batch, zdim)).pin_memory().to(device, non_blocking=True)     # CPU generator, :547
+        real = host_real[i % n_host].to(device, non_blocking=True)                           # H2D of the batch, :549
+        for k in range(5):
+            torch.randn((batch, zdim), out=eps_d[k])                                          # device draws
+        st = mod.introspective_iteration(model, real, noise, eps_d, hp, 2e-4, 2e-4)
+        stats_host.copy_(st, non_blocking=True)                                               # the logged scalars, :628
+        torch.cuda.current_stream().synchronize()
+        return stats_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.sivae_launch_count()
+    lib.sivae_profile_enable(1)
+    ms_total = timed(step_resident, args.steps)
+    prof = (C.c_double * 12)()
+    lib.sivae_profile_read(prof)
+    lib.sivae_profile_enable(0)
+    launches = lib.sivae_launch_count() - launches0
+    for i in range(max(1, min(args.warmup, 2))):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    st = stats_host.clone()
+    ms_step = ms_total / args.steps
+    value = world * batch / (ms_step / 1e3)
+    e2e_value = world * batch / (ms_e2e / args.steps / 1e3)
+    peaks = measured_peaks()
+    # dominant kernel class: tcgen05 implicit-GEMM conv (fwd + dgrad launches); TF32 runs at half the bf16 rate
+    tc_ms, tc_flops, tc_n = prof[0], prof[1], prof[2]
+    wg_ms, wg_flops, wg_n = prof[3], prof[4], prof[5]
+    simt_ms = prof[6] + prof[9]
+    roof = None
+    if tc_n > 0 and tc_ms > 0:
+        achieved = tc_flops / (tc_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="k_conv_fwd_tc (tcgen05 kind::tf32 implicit-GEMM conv, fwd+dgrad)",
+                    achieved=round(achieved, 2), peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                    frac=round(achieved / peaks["bf16_sustained"], 4),
+                    peak_note="MEASURED_PEAKS bf16_tflops_sustained (%s); kind::tf32 issues at half the bf16 rate, so "
+                              "frac<=0.5 by construction" % peaks["source"],
+                    launches_per_step=tc_n / args.steps, ms_per_step=round(tc_ms / args.steps, 3),
+                    share_of_step=round(tc_ms / ms_total, 4), traffic=_traffic("fwd"),
+                    wgrad=dict(achieved=round(wg_flops / (wg_ms * 1e-3) / 1e12, 2) if wg_ms > 0 else None,
+                               ms_per_step=round(wg_ms / args.steps, 3), launches_per_step=wg_n / args.steps),
+                    simt_conv_ms_per_step=round(simt_ms / args.steps, 3))
+    line = dict(metric="images/sec per introspective E+D step", value=round(value, 2), unit="images/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_step, 3), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="tf32 operands (fp32 storage, fp32 accumulate, fp32 BN/loss/Adam)", data="synthetic",
+                config=dict(workload=WORKLOAD_NAMES[args.config], image_size=size, z_dim=zdim, channels=channels,
+                            batch_per_gpu=batch, global_batch=batch * world, parallelism="dp%d" % world,
+                            l2_policy="inputs cycle over %d distinct batches; activations per step (>20 GB) far exceed the 126 MB L2" % n_host,
+                            algorithmic_gflop_per_image=gflop_img,
+                            step_tflops=round(gflop_img * batch * world / ms_step, 2)),
+                e2e=dict(value=round(e2e_value, 2), unit="images/s", ms_per_step=round(ms_e2e / args.steps, 3),
+                         h2d_bytes_per_step=batch * 3 * size * size * 4 + batch * zdim * 4, d2h_bytes_per_step=64),
+                gpu_launches=int(launches), roofline=roof, clocks=sampler.summary() if rank == 0 else None,
+                last_stats=dict(loss_rec=float(st[5]), kl_real=float(st[1]), lossE=float(st[4]), lossD=float(st[10])))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.config, budget_s=args.cpu_budget)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _traffic(kind):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kind)
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(cfg_name, budget_s=25.0, steps=1, warmup=0):
+    """the oracle port of the reference step on the host cores, on a bounded sample (small batch) of the workload"""
+    import torch
+    from oracle import sivae_oracle as O
+    size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[cfg_name]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # sample size: ~1.5 GFLOP/s/core sustained in fp32 conv -> images that fit the budget, at least 2 (BN needs >1)
+    est_rate = 1.5e9 * cores
+    b = int(max(2, min(batch, budget_s * est_rate / (gflop_img * 1e9))))
+    arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
+    sd = O.make_state_dict(arch, seed=0, bootstrap=boot)
+    g = torch.Generator().manual_seed(1234)
+    real = torch.rand(b, 3, size, size, generator=g)
+    noise = torch.randn(b, zdim, generator=g)
+    eps = list(torch.randn(5, b, zdim, generator=g))
+    hp = O.Hyper(beta_neg=beta_neg, gamma_r=1.0 if boot else 1e-8, scale=1.0 / (3 * size * size))
+    se, sdd = O.AdamState(), O.AdamState()
+    for _ in range(warmup):
+        O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
+    t0 = time.time()
+    for _ in range(steps):
+        O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
+    dt = (time.time() - t0) / steps
+    return dict(value=round(b / dt, 4), unit="images/s", cores=cores, kind="port",
+                sample="%d full E+D iteration(s) of the oracle at batch %d (of %d) on torch CPU fp32, %d threads; %.1f s/iter"
+                       % (steps, b, batch, cores, dt))
+
+
+def run_reference(args):
+    """reference arm: the reference's CPU implementation of the path = the oracle port, all host threads"""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    t0 = time.time()
+    # bounded: every step is one iteration on a small batch; cap the number of steps to stay within minutes
+    steps = max(1, min(args.steps, 3))
+    cb = cpu_baseline(args.config, budget_s=args.cpu_budget, steps=steps, warmup=1 if args.warmup > 0 else 0)
+    line = dict(impl="reference", metric="images/sec per introspective E+D step", value=cb["value"], unit="images/s",
+                n_gpus=world, steps=steps, warmup=1 if args.warmup > 0 else 0, ms_per_step=None, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
+                config=dict(workload=WORKLOAD_NAMES[args.config], image_size=size, z_dim=zdim, channels=channels,
+                            batch_per_gpu=batch, note="CPU path: bounded sample, see cpu_baseline.sample"),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, wall_s=round(time.time() - t0, 1))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="H", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

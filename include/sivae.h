@@ -112,6 +112,14 @@ int sivae_decode(sivae_engine* e, int net, const float* z, int batch, float* out
 int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void* stream);
 int sivae_last_batch(const sivae_engine* e);
 
+/* instrumentation for bench.py: number of kernels this library has enqueued so far; optional CUDA-event timing of
+   every convolution launch on its stream, summed per kernel class by sivae_profile_read (which synchronises):
+   out[class*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches}; class 0 = tcgen05 conv fwd/dgrad,
+   1 = tcgen05 wgrad, 2 = SIMT conv fwd/dgrad, 3 = SIMT wgrad */
+unsigned long long sivae_launch_count(void);
+int sivae_profile_enable(int on);
+int sivae_profile_read(double* out);
+
 /* ---- single-kernel entry points (unit parity tests; NHWC activations, [Cout][kh][kw][Cin] filters) ---- */
 /* nn.Conv2d(k, stride 1, pad k/2) forward (:51,56,60,89,159); bias/addend may be NULL; y = conv + bias + addend */
 int sivae_conv2d_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,

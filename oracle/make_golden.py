@@ -209,5 +209,40 @@ def main():
         print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:16])
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--toy" not in sys.argv:
     main()
+
+
+def run_reference_toy(n_iter=12, num_vae=4, batch=64, seed=92):
+    """2-D toy (BASELINE config 1): the UNMODIFIED reference `train_soft_intro_vae_toy` for a few iterations; records the
+    lines it prints (test_iter=1) and fingerprints of the final weights."""
+    import contextlib
+    import io
+    ref = _import_reference("soft_intro_vae_2d", "train_soft_intro_vae_2d")
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="sivae_golden2d_")
+    os.chdir(tmp)
+    buf = io.StringIO()
+    try:
+        torch.set_num_threads(8)
+        with contextlib.redirect_stdout(buf):
+            model = ref.train_soft_intro_vae_toy(z_dim=2, lr_e=2e-4, lr_d=2e-4, batch_size=batch, n_iter=n_iter, num_vae=num_vae,
+                                                 save_interval=5000, recon_loss_type="mse", beta_kl=0.3, beta_rec=0.2,
+                                                 beta_neg=0.9, test_iter=1, seed=seed, scale=1, device=torch.device("cpu"),
+                                                 dataset="8Gaussians")
+        res_line = open("results_log_soft_intro_vae.txt").read().strip()
+    finally:
+        os.chdir(cwd)
+    lines = [l.strip() for l in buf.getvalue().splitlines() if l.startswith("Iter:")]
+    import re
+    lines = [re.sub(r"time:\s*[\d.]+:\s*", "", l) for l in lines]                      # drop the wall-clock field
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return dict(n_iter=n_iter, num_vae=num_vae, batch=batch, seed=seed, lines=lines, state=sd, results_line=res_line,
+                torch_version=torch.__version__)
+
+
+if __name__ == "__main__" and "--toy" in sys.argv:
+    g = run_reference_toy()
+    torch.save(g, os.path.join(OUT, "toy2d.pt"))
+    print("\n".join(g["lines"]))
+    print(g["results_line"])

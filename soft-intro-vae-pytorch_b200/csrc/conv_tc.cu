@@ -1,9 +1,586 @@
-// tcgen05 TF32 implicit-GEMM convolution -- placeholder until the kernels land (everything routes to SIMT).
+// tcgen05 (5th-gen tensor core) TF32 implicit-GEMM convolution for sm_100a.
+//
+//   forward / dgrad :  D[M = 128 pixels][N = Cout tile] = sum_{tap, ci}  X[pixel + tap][ci] * Wp[co][tap][ci]
+//       A tile  = 128 pixels x 32 channels (one filter tap), fetched by ONE 4-D TMA box {32c, bw, bh, bn} of the
+//                 NHWC activation at the tap-shifted coordinate; the zero padding of the convolution is the TMA
+//                 out-of-bounds fill, so there is no im2col buffer and no bounds logic in the kernel.
+//       B tile  = BLOCK_N filters x 32 channels, 2-D TMA box of the packed filter matrix [Cout][kh*kw*Cin].
+//       both K-major, 128-byte swizzle; UMMA 128 x BLOCK_N x 8 (kind::tf32), fp32 accumulator in TMEM.
+//   wgrad           :  D[M = 128 (tap,ci)][N = Cout tile] = sum_pixels X[pixel + tap][ci] * dY[pixel][co]
+//       the reduction runs over pixels, which is the SLOW dimension of both NHWC operands, so both operands are
+//       MN-major: A = four {32c x 32 pixel} TMA boxes (tap-shifted, OOB zero fill), B = BLOCK_N/32 boxes of dY.
+//       split over pixel ranges, partial tiles reduced in fixed order (deterministic).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  smem ring of STAGES {A,B} slots with full/empty
+// mbarriers; tcgen05.commit releases slots and signals the epilogue.
+// Operands are expected to be pre-rounded to TF32 by their producers (the tensor core truncates fp32 -> tf32).
 #include "kernels.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
 namespace sivae {
-bool conv_tc_supported_fwd(const ConvShape&) { return false; }
-int launch_conv_fwd_tc(const float*, const float*, const float*, const float*, float*, const ConvShape&, cudaStream_t) { return -100; }
-bool conv_tc_supported_wgrad(const ConvShape&) { return false; }
-size_t conv_wgrad_tc_scratch_bytes(const ConvShape&) { return 0; }
-int launch_conv_wgrad_tc(const float*, const float*, float*, const ConvShape&, bool, void*, size_t, cudaStream_t) { return -100; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
 }
+// NHWC fp32 tensor [N][H][W][C] -> 4-D map, box {32, bw, bh, bn}, 128B swizzle, OOB -> 0
+static int make_map_nhwc(CUtensorMap* m, const float* base, int N, int H, int W, int C, int bw, int bh, int bn,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return -101;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -102;
+}
+// row-major fp32 matrix [rows][cols] -> 2-D map, box {32, box_rows}
+static int make_map_2d(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return -101;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -102;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(addr, parity)) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz: far beyond any legitimate wait in these kernels
+      printf("sivae: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp receives row (lane base + i), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm_100 UMMA): start address, leading / stride byte offsets (>>4), version 1,
+// layout type 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only layout the
+// tensor core accepts for MN-major 32-bit operands)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor: D fp32, A/B tf32, majors, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct FwdParams {
+  int N, H, W, Cin, Cout, ks;
+  int bw, bh, bn;            // pixel tile = bn x bh x bw = 128
+  int tiles_w, tiles_h;      // W/bw, H/bh
+  const float* bias;
+  const float* addend;
+  float* y;
+};
+constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 32 fp32
+
+template <int BLOCK_N, int STAGES>
+struct FwdSmem {
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) k_conv_fwd_tc(const __grid_constant__ CUtensorMap map_x,
+                                                     const __grid_constant__ CUtensorMap map_w, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = FwdSmem<BLOCK_N, STAGES>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+  const int col0 = blockIdx.y * BLOCK_N;
+  const int cchunks = p.Cin >> 5;
+  const int num_kb = p.ks * p.ks * cchunks;
+  const int pad = p.ks >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], SM::STAGE_BYTES);
+        const int tap = kb / cchunks, c0 = (kb - tap * cchunks) << 5;
+        const int r = tap / p.ks, s = tap - r * p.ks;
+        uint8_t* sa = smem + st * SM::STAGE_BYTES;
+        tma_load_4d(sa, &map_x, &full[st], c0, w0 + s - pad, h0 + r - pad, n0);
+        tma_load_2d(sa + TC_A_BYTES, &map_w, &full[st], tap * p.Cin + c0, col0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int st = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
+        const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // K-major, 128B swizzle: rows 128 B apart, 8-row groups 1024 B apart; advance 8 tf32 (32 B) per MMA
+          uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
+          uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);                      // slot free once these MMAs have read it
+        if (kb == num_kb - 1) umma_commit(tmem_full); // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dw = row % p.bw, dh = (row / p.bw) % p.bh, dn = row / (p.bw * p.bh);
+    const int n = n0 + dn;
+    const bool valid = n < p.N;
+    const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (valid) {
+        float* dst = p.y + pix * p.Cout + col0 + c;
+        const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col0 + c + j < p.Cout) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (p.bias) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (add) {
+              float4 a = *reinterpret_cast<const float4*>(add + j);
+              o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+}
+
+static void pick_tile(int H, int W, int* bw, int* bh, int* bn) {
+  int w = 1;
+  while (w * 2 <= 16 && W % (w * 2) == 0) w *= 2;
+  int h = 1;
+  while (h * 2 <= 128 / w && H % (h * 2) == 0) h *= 2;
+  *bw = w; *bh = h; *bn = 128 / (w * h);
+}
+
+bool conv_tc_supported_fwd(const ConvShape& s) {
+  if (s.Cin % 32 != 0 || s.Cout % 4 != 0 || s.Cout < 16) return false;
+  if (s.k != 1 && s.k != 3 && s.k != 5) return false;
+  int bw, bh, bn;
+  pick_tile(s.H, s.W, &bw, &bh, &bn);
+  if (bn > 256) return false;
+  return true;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_fwd_t(const CUtensorMap& mx, const CUtensorMap& mw, const FwdParams& p, int m_tiles, cudaStream_t st) {
+  using SM = FwdSmem<BLOCK_N, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_fwd_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  dim3 grid(m_tiles, (p.Cout + BLOCK_N - 1) / BLOCK_N);
+  g_launches += 1;
+  k_conv_fwd_tc<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, p);
+  return (int)cudaGetLastError();
+}
+
+int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                       cudaStream_t st) {
+  FwdParams p;
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
+  pick_tile(s.H, s.W, &p.bw, &p.bh, &p.bn);
+  p.tiles_w = s.W / p.bw; p.tiles_h = s.H / p.bh;
+  p.bias = bias; p.addend = addend; p.y = y;
+  const int tiles_n = (s.N + p.bn - 1) / p.bn;
+  const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  const int block_n = s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32);
+  CUtensorMap mx, mw;
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
+  if (r) return r;
+  r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
+  if (r) return r;
+  if (block_n == 128) return launch_fwd_t<128, 3>(mx, mw, p, m_tiles, st);
+  if (block_n == 64) return launch_fwd_t<64, 4>(mx, mw, p, m_tiles, st);
+  return launch_fwd_t<32, 4>(mx, mw, p, m_tiles, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad kernel: D[m = tap*Cin + ci][n = co] = sum_pixels X[pixel + tap][ci] * dY[pixel][co]   (both MN-major)
+// ---------------------------------------------------------------------------------------------------------------
+struct WgParams {
+  int N, H, W, Cin, Cout, ks;
+  int pw, ph, pn;              // pixel block (K block) = pn x ph x pw = 32 pixels
+  int tiles_w, tiles_h;        // W/pw, H/ph
+  long long kb_total;          // number of pixel blocks
+  long long kb_per_split;
+  int Ktot;                    // ks*ks*Cin
+  float* part;                 // [splits][Cout][Ktot]
+};
+constexpr int WG_CHUNK_BYTES = 32 * 128;    // 32 pixel rows x 32 channels fp32 (one TMA box)
+
+template <int BLOCK_N, int STAGES>
+struct WgSmem {
+  static constexpr int A_BYTES = 4 * WG_CHUNK_BYTES;
+  static constexpr int B_BYTES = (BLOCK_N / 32) * WG_CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) k_conv_wgrad_tc(const __grid_constant__ CUtensorMap map_x,
+                                                       const __grid_constant__ CUtensorMap map_dy, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = WgSmem<BLOCK_N, STAGES>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;            // first (tap,ci) row of this tile
+  const int col0 = blockIdx.y * BLOCK_N;      // first co
+  const long long kb_begin = (long long)blockIdx.z * p.kb_per_split;
+  long long kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.kb_total) kb_end = p.kb_total;
+  const int num_kb = (int)(kb_end - kb_begin);
+  const int pad = p.ks >> 1;
+  // number of valid 32-row chunks of A in this tile
+  int a_chunks = (p.Ktot - m0 + 31) / 32;
+  if (a_chunks > 4) a_chunks = 4;
+  int b_chunks = (p.Cout - col0 + 31) / 32;
+  if (b_chunks > BLOCK_N / 32) b_chunks = BLOCK_N / 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)(a_chunks + b_chunks) * WG_CHUNK_BYTES);
+        const long long kb = kb_begin + i;
+        const int tw = (int)(kb % p.tiles_w);
+        const int th = (int)((kb / p.tiles_w) % p.tiles_h);
+        const int tn = (int)(kb / ((long long)p.tiles_w * p.tiles_h));
+        const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.pn;
+        uint8_t* sa = smem + st * SM::STAGE_BYTES;
+        for (int j = 0; j < a_chunks; ++j) {
+          const int m = m0 + 32 * j;
+          const int tap = m / p.Cin, c0 = m - tap * p.Cin;
+          const int r = tap / p.ks, s = tap - r * p.ks;
+          tma_load_4d(sa + j * WG_CHUNK_BYTES, &map_x, &full[st], c0, w0 + s - pad, h0 + r - pad, n0);
+        }
+        uint8_t* sb = sa + SM::A_BYTES;
+        for (int j = 0; j < b_chunks; ++j)
+          tma_load_4d(sb + j * WG_CHUNK_BYTES, &map_dy, &full[st], col0 + 32 * j, w0, h0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
+    for (int i = 0; i < num_kb; ++i) {
+      const int st = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
+        const uint32_t sb = sa + SM::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // MN-major fp32: SWIZZLE_128B_BASE32B.  32 MN elements (128 B) contiguous per K row, K rows 128 B apart,
+          // swizzle atom = 4 K rows (512 B = SBO), next 32-wide MN chunk one TMA box (4096 B) further (LBO);
+          // one MMA consumes 8 K rows = two atoms; advance 1024 B per MMA
+          uint64_t ad = make_smem_desc(sa + k * 1024, WG_CHUNK_BYTES, 512, 1);
+          uint64_t bd = make_smem_desc(sb + k * 1024, WG_CHUNK_BYTES, 512, 1);
+          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+        if (i == num_kb - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool valid = m < p.Ktot && num_kb > 0;
+    float* dst = p.part + (long long)blockIdx.z * p.Cout * p.Ktot;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (m < p.Ktot) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = col0 + c + j;
+          if (co < p.Cout) dst[(long long)co * p.Ktot + m] = valid ? __uint_as_float(v[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+}
+
+__global__ void k_wg_reduce(const float* __restrict__ part, float* __restrict__ out, long long n, int splits, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long long)z * n + i];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+static void pick_pixel_block(int H, int W, int* pw, int* ph, int* pn) {
+  int w = 1;
+  while (w * 2 <= 32 && W % (w * 2) == 0) w *= 2;
+  int h = 1;
+  while (h * 2 <= 32 / w && H % (h * 2) == 0) h *= 2;
+  *pw = w; *ph = h; *pn = 32 / (w * h);
+}
+static int wg_block_n(int Cout) { return Cout > 128 ? 256 : (Cout > 64 ? 128 : 64); }
+static void wg_plan(const ConvShape& s, int* splits, long long* kb_total, long long* kb_per_split) {
+  int pw, ph, pn;
+  pick_pixel_block(s.H, s.W, &pw, &ph, &pn);
+  long long kbt = (long long)(s.W / pw) * (s.H / ph) * ((s.N + pn - 1) / pn);
+  int bn = wg_block_n(s.Cout);
+  long long tiles = (long long)((s.ktot() + 127) / 128) * ((s.Cout + bn - 1) / bn);
+  long long want = (148 * 2 + tiles - 1) / tiles;
+  long long maxs = (kbt + 15) / 16;       // at least 16 pixel blocks per CTA
+  long long sp = want < maxs ? want : maxs;
+  if (sp < 1) sp = 1;
+  if (sp > 512) sp = 512;
+  long long per = (kbt + sp - 1) / sp;
+  sp = (kbt + per - 1) / per;
+  *splits = (int)sp; *kb_total = kbt; *kb_per_split = per;
+}
+bool conv_tc_supported_wgrad(const ConvShape& s) {
+  if (s.Cin % 32 != 0 || s.Cout % 32 != 0) return false;
+  if (s.k != 1 && s.k != 3) return false;
+  int pw, ph, pn;
+  pick_pixel_block(s.H, s.W, &pw, &ph, &pn);
+  if (pn > 256) return false;
+  return true;
+}
+size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s) {
+  int splits; long long kbt, per;
+  wg_plan(s, &splits, &kbt, &per);
+  return (size_t)splits * s.Cout * s.ktot() * sizeof(float);
+}
+template <int BLOCK_N, int STAGES>
+static int launch_wg_t(const CUtensorMap& mx, const CUtensorMap& mdy, const WgParams& p, int splits, cudaStream_t st) {
+  using SM = WgSmem<BLOCK_N, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_tc<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  dim3 grid((p.Ktot + 127) / 128, (p.Cout + BLOCK_N - 1) / BLOCK_N, splits);
+  g_launches += 2;
+  k_conv_wgrad_tc<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
+  return (int)cudaGetLastError();
+}
+int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate, void* scratch,
+                         size_t scratch_bytes, cudaStream_t st) {
+  WgParams p;
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
+  pick_pixel_block(s.H, s.W, &p.pw, &p.ph, &p.pn);
+  p.tiles_w = s.W / p.pw; p.tiles_h = s.H / p.ph;
+  int splits;
+  wg_plan(s, &splits, &p.kb_total, &p.kb_per_split);
+  p.Ktot = (int)s.ktot();
+  p.part = (float*)scratch;
+  if (scratch_bytes < (size_t)splits * s.Cout * s.ktot() * sizeof(float)) return -103;
+  CUtensorMap mx, mdy;
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.pw, p.ph, p.pn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (r) return r;
+  r = make_map_nhwc(&mdy, dy, s.N, s.H, s.W, s.Cout, p.pw, p.ph, p.pn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (r) return r;
+  const int bn = wg_block_n(s.Cout);
+  if (bn == 256) r = launch_wg_t<256, 3>(mx, mdy, p, splits, st);
+  else if (bn == 128) r = launch_wg_t<128, 4>(mx, mdy, p, splits, st);
+  else r = launch_wg_t<64, 4>(mx, mdy, p, splits, st);
+  if (r) return r;
+  long long n = (long long)s.Cout * s.ktot();
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148u * 8) blocks = 148u * 8;
+  k_wg_reduce<<<blocks, 256, 0, st>>>(p.part, dw, n, splits, accumulate ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace sivae

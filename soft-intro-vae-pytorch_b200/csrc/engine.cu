@@ -294,6 +294,31 @@ static size_t carve(sivae_engine* e, char* base) {
 static bool use_tc(const sivae_engine* e, const ConvShape& s) {
   return e->tc && conv_tc_supported_fwd(s);
 }
+
+// ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
+enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_COUNT = 4 };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+struct Prof {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  size_t used = 0;
+};
+static Prof g_prof;
+struct ProfScope {
+  cudaStream_t st; ProfRec* r = nullptr;
+  ProfScope(int cls, const ConvShape& s, cudaStream_t st_) : st(st_) {
+    if (!g_prof.on) return;
+    if (g_prof.used == g_prof.recs.size()) {
+      ProfRec n; cudaEventCreate(&n.a); cudaEventCreate(&n.b); n.cls = 0; n.flops = 0;
+      g_prof.recs.push_back(n);
+    }
+    r = &g_prof.recs[g_prof.used++];
+    r->cls = cls;
+    r->flops = 2.0 * (double)s.pixels() * (double)s.Cout * (double)s.ktot();
+    cudaEventRecord(r->a, st);
+  }
+  ~ProfScope() { if (r) cudaEventRecord(r->b, st); }
+};
 static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
   if (!n.dirty) return 0;
   auto one = [&](const Conv& c) {
@@ -313,9 +338,11 @@ static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, floa
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
   if (use_tc(e, s)) {
+    ProfScope ps(PC_TC_FWD, s, st);
     int r = launch_conv_fwd_tc(x, n.derived + c.wr_off, bias, addend, y, s, st);
     if (r) return fail(r, "tcgen05 conv fwd launch failed");
   } else {
+    ProfScope ps(PC_SIMT_FWD, s, st);
     launch_conv_fwd_simt(x, n.params + c.w_off, bias, addend, y, s, st);
   }
   return 0;
@@ -324,9 +351,11 @@ static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, floa
 static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cout, c.cin, c.k};
   if (use_tc(e, s)) {
+    ProfScope ps(PC_TC_FWD, s, st);
     int r = launch_conv_fwd_tc(dy, n.derived + c.wd_off, nullptr, addend, dx, s, st);
     if (r) return fail(r, "tcgen05 conv dgrad launch failed");
   } else {
+    ProfScope ps(PC_SIMT_FWD, s, st);
     launch_conv_fwd_simt(dy, n.derived + c.wd_off, nullptr, addend, dx, s, st);
   }
   return 0;
@@ -334,9 +363,11 @@ static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, f
 static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   if (e->tc && conv_tc_supported_wgrad(s)) {
+    ProfScope ps(PC_TC_WGRAD, s, st);
     int r = launch_conv_wgrad_tc(x, dy, n.grads + c.w_off, s, true, e->red, e->red_bytes, st);
     if (r) return fail(r, "tcgen05 conv wgrad launch failed");
   } else {
+    ProfScope ps(PC_SIMT_WGRAD, s, st);
     launch_conv_wgrad_simt(x, dy, n.grads + c.w_off, s, true, e->red, e->red_bytes, st);
   }
   return 0;
@@ -776,6 +807,29 @@ extern "C" int sivae_decode(sivae_engine* e, int net, const float* z, int B, flo
   return 0;
 }
 
+extern "C" unsigned long long sivae_launch_count(void) { return sivae::g_launches; }
+extern "C" int sivae_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  return 0;
+}
+// out[class][3] = {milliseconds, flops, launches} for class 0 = tcgen05 conv fwd/dgrad, 1 = tcgen05 wgrad,
+// 2 = SIMT conv fwd/dgrad, 3 = SIMT wgrad.  Synchronises the device.
+extern "C" int sivae_profile_read(double* out) {
+  if (!out) return fail(-1, "null argument");
+  cudaDeviceSynchronize();
+  for (int i = 0; i < PC_COUNT * 3; ++i) out[i] = 0.0;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof.recs[i].a, g_prof.recs[i].b) != cudaSuccess) continue;
+    out[g_prof.recs[i].cls * 3 + 0] += ms;
+    out[g_prof.recs[i].cls * 3 + 1] += g_prof.recs[i].flops;
+    out[g_prof.recs[i].cls * 3 + 2] += 1.0;
+  }
+  g_prof.used = 0;
+  CHECK_CUDA_RET();
+  return 0;
+}
 extern "C" int sivae_last_batch(const sivae_engine* e) { return e ? e->cur_batch : -1; }
 extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void* stream) {
   if (!e || !e->ws || slot < 0 || slot > 3 || !out_nchw || e->cur_batch < 1) return fail(-1, "bad argument / no step run yet");

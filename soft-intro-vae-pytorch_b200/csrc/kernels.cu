@@ -8,6 +8,7 @@
 
 namespace sivae {
 
+unsigned long long g_launches = 0;   // number of kernels enqueued by this library (bench.py reports it)
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 __device__ __forceinline__ float round_tf32_dev(float x) {
@@ -47,11 +48,13 @@ __global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__
   }
 }
 void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st) {
+  g_launches += 1;
   long long total = (long long)N * C * H * W;
   if (total == 0) return;
   k_nchw_to_nhwc<<<min(cdiv(total, 256), 148u * 16), 256, 0, st>>>(in, out, N, C, H, W);
 }
 void launch_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st) {
+  g_launches += 1;
   long long total = (long long)N * C * H * W;
   if (total == 0) return;
   k_nhwc_to_nchw<<<min(cdiv(total, 256), 148u * 16), 256, 0, st>>>(in, out, N, C, H, W);
@@ -60,6 +63,7 @@ __global__ void k_fill(float* p, float v, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 void launch_fill(float* p, float v, long long n, cudaStream_t st) {
+  g_launches += 1;
   if (n <= 0) return;
   k_fill<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(p, v, n);
 }
@@ -68,6 +72,7 @@ __global__ void k_round_tf32(const float* __restrict__ in, float* __restrict__ o
     out[i] = round_tf32_dev(in[i]);
 }
 void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st) {
+  g_launches += 1;
   if (n <= 0) return;
   k_round_tf32<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(in, out, n);
 }
@@ -86,6 +91,7 @@ __global__ void k_pack_dgrad(const float* __restrict__ w, float* __restrict__ wd
   }
 }
 void launch_pack_dgrad_filter(const float* w, float* wd, int Cout, int Cin, int k, bool rnd, cudaStream_t st) {
+  g_launches += 1;
   long long total = (long long)Cout * Cin * k * k;
   k_pack_dgrad<<<min(cdiv(total, 256), 148u * 8), 256, 0, st>>>(w, wd, Cout, Cin, k, rnd ? 1 : 0);
 }
@@ -131,11 +137,13 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
 
   const int tx = tid & 15;   // column group (4 cols)
   const int ty = tid >> 4;   // row group (8 rows)
-  float acc[8][4];
+  // exact path: every 16-deep K chunk is accumulated in fp32 and folded into an fp64 running sum, so the result is
+  // correct to fp32 round-off independent of K (this kernel is the on-device reference of the tensor-core path)
+  double acc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (int k0 = 0; k0 < Ktot; k0 += CS_BK) {
     {
@@ -162,6 +170,11 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
       }
     }
     __syncthreads();
+    float part[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < CS_BK; ++kk) {
       float a[8], b[4];
@@ -172,8 +185,12 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += (double)part[i][j];
     __syncthreads();
   }
 #pragma unroll
@@ -184,15 +201,16 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
     for (int j = 0; j < 4; ++j) {
       int co = n0 + tx * 4 + j;
       if (co >= Cout) continue;
-      float v = acc[i][j];
-      if (bias) v += bias[co];
-      if (addend) v += addend[m * Cout + co];
-      y[m * Cout + co] = v;
+      double v = acc[i][j];
+      if (bias) v += (double)bias[co];
+      if (addend) v += (double)addend[m * Cout + co];
+      y[m * Cout + co] = (float)v;
     }
   }
 }
 void launch_conv_fwd_simt(const float* x, const float* w, const float* bias, const float* addend, float* y,
                           const ConvShape& s, cudaStream_t st) {
+  g_launches += 1;
   long long M = s.pixels();
   if (M == 0) return;
   dim3 grid(cdiv(M, CS_BM), cdiv(s.Cout, CS_BN));
@@ -225,11 +243,11 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(const float* __restrict
   const int co_l = co0 + lc;
 
   const int tx = tid & 15, ty = tid >> 4;   // 4x4 micro tile: rows (co) ty*4.., cols (k) tx*4..
-  float acc[4][4];
+  double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (long long p0 = p_begin; p0 < p_end; p0 += WG_BP) {
 #pragma unroll
@@ -252,6 +270,11 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(const float* __restrict
       Xs[pr][lc] = xv;
     }
     __syncthreads();
+    float part4[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part4[i][j] = 0.f;
 #pragma unroll
     for (int pp = 0; pp < WG_BP; ++pp) {
       float a[4], b[4];
@@ -262,8 +285,12 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(const float* __restrict
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part4[i][j] = fmaf(a[i], b[j], part4[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += (double)part4[i][j];
     __syncthreads();
   }
   float* dst = part + (long long)blockIdx.z * Cout * Ktot;
@@ -274,15 +301,15 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_simt(const float* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = k0 + tx * 4 + j;
-      if (k < Ktot) dst[(long long)co * Ktot + k] = acc[i][j];
+      if (k < Ktot) dst[(long long)co * Ktot + k] = (float)acc[i][j];
     }
   }
 }
 __global__ void k_splitk_reduce(const float* __restrict__ part, float* __restrict__ out, long long n, int splits, int accumulate) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(long long)z * n + i];   // fixed order: deterministic
-    out[i] = accumulate ? out[i] + s : s;
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += (double)part[(long long)z * n + i];   // fixed order: deterministic
+    out[i] = accumulate ? (float)((double)out[i] + s) : (float)s;
   }
 }
 static int wgrad_simt_splits(const ConvShape& s) {
@@ -299,6 +326,7 @@ size_t conv_wgrad_simt_scratch_bytes(const ConvShape& s) {
 }
 void launch_conv_wgrad_simt(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
                             void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  g_launches += 2;
   int splits = wgrad_simt_splits(s);
   long long M = s.pixels();
   long long pps = (M + splits - 1) / splits;
@@ -325,6 +353,7 @@ __global__ void k_colsum(const float* __restrict__ in, float* __restrict__ out, 
   if (threadIdx.x == 0) out[c] = accumulate ? out[c] + (float)sh[0] : (float)sh[0];
 }
 void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, cudaStream_t st) {
+  g_launches += 1;
   k_colsum<<<C, 256, 0, st>>>(in, out, rows, C, accumulate ? 1 : 0);
 }
 
@@ -390,6 +419,7 @@ __global__ void k_bn_stats_finalize(const float* __restrict__ part, int nblk, lo
 }
 void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, float* running_mean,
                      float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  g_launches += 2;
   int nblk = bn_nblocks(rows);
   float* part = (float*)scratch;
   int cvec = C / 4;
@@ -403,6 +433,7 @@ __global__ void k_bn_eval_stats(const float* rm, const float* rv, int C, float* 
   if (c < C) { mi[c] = rm[c]; mi[C + c] = rsqrtf(rv[c] + kBnEps); }
 }
 void launch_bn_eval_stats(const float* rm, const float* rv, int C, float* mi, cudaStream_t st) {
+  g_launches += 1;
   k_bn_eval_stats<<<cdiv(C, 128), 128, 0, st>>>(rm, rv, C, mi);
 }
 
@@ -465,6 +496,7 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
 }
 void launch_bn_act_fwd(const float* t, const float* identity, const float* mi, const float* gamma, const float* beta,
                        float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st) {
+  g_launches += 1;
   int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
   long long total = (long long)N * Ho * Wo * (C / 4);
   if (total == 0) return;
@@ -607,6 +639,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
 void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mi, const float* gamma,
                        const float* beta, float* dt, float* g, float* dgamma, float* dbeta, bool accumulate, int N,
                        int H, int W, int C, int mode, bool rnd, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  g_launches += 3;
   long long rows = (long long)N * H * W;
   if (rows == 0) return;
   int nblk = bn_nblocks(rows);
@@ -676,39 +709,45 @@ __global__ void __launch_bounds__(256) k_linear_fwd(const float* __restrict__ x,
   }
 }
 void launch_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, bool relu, cudaStream_t st) {
+  g_launches += 1;
   dim3 grid(cdiv(O, LF_OT), cdiv(B, LF_BT));
   k_linear_fwd<<<grid, 256, 0, st>>>(x, w, b, y, B, F, O, relu ? 1 : 0);
 }
-constexpr int LD_BT = 8;
+constexpr int LD_BT = 8, LD_OC = 1024;
 __global__ void __launch_bounds__(256) k_linear_dgrad(const float* __restrict__ dy, const float* __restrict__ w,
                                                       float* __restrict__ dx, int B, int F, int O) {
-  extern __shared__ float sdy[];   // [LD_BT][O]
+  __shared__ float sdy[LD_BT][LD_OC];   // dy chunk, broadcast to all f
   const int b0 = blockIdx.y * LD_BT;
-  for (int i = threadIdx.x; i < LD_BT * O; i += 256) {
-    int j = i / O, o = i - j * O;
-    sdy[i] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o] : 0.f;
-  }
-  __syncthreads();
-  int f = blockIdx.x * 256 + threadIdx.x;
-  if (f >= F) return;
+  const int f = blockIdx.x * 256 + threadIdx.x;
   float acc[LD_BT];
 #pragma unroll
   for (int j = 0; j < LD_BT; ++j) acc[j] = 0.f;
-  for (int o = 0; o < O; ++o) {
-    float wv = __ldg(w + (long long)o * F + f);
+  for (int o0 = 0; o0 < O; o0 += LD_OC) {
+    const int oc = min(LD_OC, O - o0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < LD_BT * oc; i += 256) {
+      int j = i / oc, o = i - j * oc;
+      sdy[j][o] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o0 + o] : 0.f;
+    }
+    __syncthreads();
+    if (f < F) {
+      for (int o = 0; o < oc; ++o) {
+        float wv = __ldg(w + (long long)(o0 + o) * F + f);
 #pragma unroll
-    for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[j * O + o], wv, acc[j]);
+        for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[j][o], wv, acc[j]);
+      }
+    }
   }
+  if (f < F) {
 #pragma unroll
-  for (int j = 0; j < LD_BT; ++j)
-    if (b0 + j < B) dx[(long long)(b0 + j) * F + f] = acc[j];
+    for (int j = 0; j < LD_BT; ++j)
+      if (b0 + j < B) dx[(long long)(b0 + j) * F + f] = acc[j];
+  }
 }
 void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, cudaStream_t st) {
+  g_launches += 1;
   dim3 grid(cdiv(F, 256), cdiv(B, LD_BT));
-  size_t shmem = (size_t)LD_BT * O * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_linear_dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-  k_linear_dgrad<<<grid, 256, shmem, st>>>(dy, w, dx, B, F, O);
+  k_linear_dgrad<<<grid, 256, 0, st>>>(dy, w, dx, B, F, O);
 }
 constexpr int LW_OT = 8;
 __global__ void __launch_bounds__(256) k_linear_wgrad(const float* __restrict__ x, const float* __restrict__ dy,
@@ -744,6 +783,7 @@ __global__ void __launch_bounds__(256) k_linear_wgrad(const float* __restrict__ 
     }
 }
 void launch_linear_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int F, int O, bool accumulate, cudaStream_t st) {
+  g_launches += 1;
   dim3 grid(cdiv(F, 256), cdiv(O, LW_OT));
   size_t shmem = (size_t)B * LW_OT * sizeof(float);
   k_linear_wgrad<<<grid, 256, shmem, st>>>(x, dy, dw, db, B, F, O, accumulate ? 1 : 0);
@@ -753,6 +793,7 @@ __global__ void k_relu_bwd(const float* __restrict__ y, float* __restrict__ dy, 
     if (!(y[i] > 0.f)) dy[i] = 0.f;
 }
 void launch_relu_bwd(const float* y, float* dy, long long n, cudaStream_t st) {
+  g_launches += 1;
   if (n <= 0) return;
   k_relu_bwd<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(y, dy, n);
 }
@@ -823,6 +864,7 @@ __global__ void k_mse3_final(const float* __restrict__ part, float* __restrict__
 }
 void launch_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
                  float* out, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  g_launches += 2;
   int nblk = mse_blocks_per_sample(per_sample);
   float* part = (float*)scratch;
   dim3 grid(nblk, B);
@@ -849,6 +891,7 @@ __global__ void k_kl_reparam(const float* __restrict__ ml, const float* __restri
   if (lane == 0 && kl) kl[b] = -0.5f * s;
 }
 void launch_kl_reparam(const float* ml, const float* eps, float* z, float* kl, int B, int zd, cudaStream_t st) {
+  g_launches += 1;
   k_kl_reparam<<<cdiv(B, 4), 128, 0, st>>>(ml, eps, z, kl, B, zd);
 }
 __global__ void k_latent_bwd(const float* __restrict__ ml, const float* __restrict__ eps, const float* __restrict__ dz,
@@ -870,6 +913,7 @@ __global__ void k_latent_bwd(const float* __restrict__ ml, const float* __restri
 }
 void launch_latent_bwd(const float* ml, const float* eps, const float* dz, const float* ckl, float ckl_const,
                        float* dml, int B, int zd, cudaStream_t st) {
+  g_launches += 1;
   long long n = (long long)B * zd;
   k_latent_bwd<<<cdiv(n, 256), 256, 0, st>>>(ml, eps, dz, ckl, ckl_const, dml, B, zd);
 }
@@ -920,6 +964,7 @@ __global__ void __launch_bounds__(256) k_e_loss_finalize(const float* __restrict
 void launch_e_loss_finalize(const float* mse, const float* kl_real, const float* kl_rec, const float* kl_fake, int B,
                             float beta_kl, float beta_rec, float beta_neg, float scale, float* stats, float* coef,
                             float* ckl_rec, float* ckl_fake, cudaStream_t st) {
+  g_launches += 1;
   k_e_loss_finalize<<<1, 256, 0, st>>>(mse, kl_real, kl_rec, kl_fake, B, beta_kl, beta_rec, beta_neg, scale, stats, coef, ckl_rec, ckl_fake);
 }
 __global__ void __launch_bounds__(256) k_d_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl_rec,
@@ -941,6 +986,7 @@ __global__ void __launch_bounds__(256) k_d_loss_finalize(const float* __restrict
 }
 void launch_d_loss_finalize(const float* mse, const float* kl_rec, const float* kl_fake, int B, float beta_kl,
                             float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st) {
+  g_launches += 1;
   k_d_loss_finalize<<<1, 256, 0, st>>>(mse, kl_rec, kl_fake, B, beta_kl, beta_rec, gamma_r, scale, stats);
 }
 __global__ void __launch_bounds__(256) k_vae_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl,
@@ -957,6 +1003,7 @@ __global__ void __launch_bounds__(256) k_vae_loss_finalize(const float* __restri
   }
 }
 void launch_vae_loss_finalize(const float* mse, const float* kl, int B, float beta_kl, float beta_rec, float* stats, cudaStream_t st) {
+  g_launches += 1;
   k_vae_loss_finalize<<<1, 256, 0, st>>>(mse, kl, B, beta_kl, beta_rec, stats);
 }
 
@@ -996,6 +1043,7 @@ void launch_loss_seed(const float* real, const float* rec, const float* rec_rec,
                       float a_rec, const float* a_t_arr, float a_t, const float* a_f_arr, float a_f, bool target_grad_rec,
                       float* d_rec, float* d_rec_rec, float* d_rec_fake, float* d_fake, int B, long long per_sample,
                       cudaStream_t st) {
+  g_launches += 1;
   long long ps4 = per_sample / 4;   // per_sample = cdim*S*S with even S: multiple of 4
   dim3 grid(min(cdiv(ps4, 256), 148u * 4), B);
   k_loss_seed<<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, a_rec, a_t_arr, a_t, a_f_arr, a_f,
@@ -1019,6 +1067,7 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
 }
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale, float b1,
                  float b2, float eps, long long step, cudaStream_t st) {
+  g_launches += 1;
   if (n <= 0) return;
   double bc1 = 1.0 - pow((double)b1, (double)step);
   double bc2 = 1.0 - pow((double)b2, (double)step);

@@ -11,6 +11,8 @@ constexpr float kBnEps = 1e-5f;
 constexpr float kBnMomentum = 0.1f;
 constexpr float kSlope = 0.2f;
 
+extern unsigned long long g_launches;
+
 enum ResampleMode { RS_NONE = 0, RS_POOL = 1, RS_UP = 2 };
 
 struct ConvShape {

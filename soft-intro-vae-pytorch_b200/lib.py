@@ -54,6 +54,9 @@ _SIGS = {
     "sivae_adam_get_step": (C.c_longlong, [_P, C.c_int]),
     "sivae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     "sivae_decode": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "sivae_launch_count": (C.c_ulonglong, []),
+    "sivae_profile_enable": (C.c_int, [C.c_int]),
+    "sivae_profile_read": (C.c_int, [C.POINTER(C.c_double)]),
     "sivae_last_image": (C.c_int, [_P, C.c_int, _P, _P]),
     "sivae_last_batch": (C.c_int, [_P]),
     "sivae_conv2d_fwd": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 7 + [_P]),

@@ -511,6 +511,15 @@ def train_soft_intro_vae(dataset='cifar10', z_dim=128, lr_e=2e-4, lr_d=2e-4, bat
     """Train a Soft-IntroVAE on the B200 engine.  Arguments, defaults, printed lines, output files
     (./figures_<dataset>/image_<iter>.jpg, ./saves/*.pth, ./soft_intro_train_graphs.jpg + _data.pickle) and the
     SystemError contract (NaN loss; negative KL difference) follow the reference function of the same name."""
+    return _run_training(SoftIntroVAE, None, dataset, z_dim, lr_e, lr_d, batch_size, num_workers, start_epoch,
+                         exit_on_negative_diff, num_epochs, num_vae, save_interval, recon_loss_type, beta_kl, beta_rec,
+                         beta_neg, test_iter, seed, pretrained, device, num_row, gamma_r, with_fid)
+
+
+def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, batch_size, num_workers, start_epoch,
+                  exit_on_negative_diff, num_epochs, num_vae, save_interval, recon_loss_type, beta_kl, beta_rec,
+                  beta_neg, test_iter, seed, pretrained, device, num_row, gamma_r, with_fid):
+    """shared driver of the standard and the bootstrap (copy_to_target_freq is not None) trainers"""
     if recon_loss_type != "mse":
         raise NotImplementedError("the B200 engine implements recon_loss_type='mse' (the only type the CLI passes)")
     device = torch.device(device)
@@ -525,7 +534,7 @@ def train_soft_intro_vae(dataset='cifar10', z_dim=128, lr_e=2e-4, lr_d=2e-4, bat
         print("random seed: ", seed)
 
     train_set, image_size, channels, ch, labelled = _build_dataset(dataset)
-    model = SoftIntroVAE(cdim=ch, zdim=z_dim, channels=channels, image_size=image_size).to(device)
+    model = model_cls(cdim=ch, zdim=z_dim, channels=channels, image_size=image_size).to(device)
     if pretrained is not None:
         load_model(model, pretrained, device)
     print(model)
@@ -612,6 +621,9 @@ def train_soft_intro_vae(dataset='cifar10', z_dim=128, lr_e=2e-4, lr_d=2e-4, bat
                     _save_grid([real_batch[:k], rec_det[:k], fake[:k]], '{}/image_{}.jpg'.format(fig_dir, cur_iter), num_row)
             cur_iter += 1
         pbar.close()
+        if copy_to_target_freq is not None and epoch % copy_to_target_freq == 0:
+            # bootstrap: the frozen target decoder follows the decoder, lagging by up to copy_to_target_freq epochs
+            model.target_decoder.load_state_dict(model.decoder.state_dict())
         diff_kls = track.cur["diff_kl"]
         if exit_on_negative_diff and epoch > 50 and np.mean(diff_kls) < -1.0:
             print(f'the kl difference [{np.mean(diff_kls):.3f}] between fake and real is negative (no sampling improvement)')

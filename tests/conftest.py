@@ -13,6 +13,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a dead-locked kernel must not hold the GPU box: bound every GPU test (pytest-timeout kills the process)
+    for item in items:
+        if item.get_closest_marker("gpu") is not None and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(240))
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

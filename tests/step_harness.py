@@ -30,14 +30,13 @@ def make_inputs(cfg, batch, seed):
 DEFAULT_HP = dict(beta_kl=1.0, beta_rec=1.0, beta_neg=256.0, gamma_r=1e-8, lr_e=2e-4, lr_d=2e-4)
 
 
-def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=None, inputs=None, hp=None, device="cuda:0"):
+def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=None, inputs=None, hp=None, device="cuda:0",
+                         teacher_enc=None):
     L, M = mods(bootstrap)
     E = importlib.import_module(PKG + ".engine")
     hp = dict(DEFAULT_HP, **(hp or {}))
     if "scale" not in hp:
         hp["scale"] = 1.0 / (cfg["cdim"] * cfg["image_size"] ** 2)
-    if bootstrap and "gamma_r" not in (hp or {}):
-        pass
     torch.manual_seed(seed)
     model = M.SoftIntroVAE(cdim=cfg["cdim"], zdim=cfg["zdim"], channels=cfg["channels"], image_size=cfg["image_size"])
     if init_sd is not None:
@@ -54,6 +53,16 @@ def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=N
     grads_e = {"encoder." + n: p.grad.detach().clone().cpu().contiguous() for n, p in model.encoder.named_parameters()}
     imgs_e = {k: eng.last_image(i).cpu() for i, k in enumerate(["fake", "rec", "rec_rec", "rec_fake"])}
     eng.adam(L.NET_ENCODER, hp["lr_e"])
+    torch.cuda.synchronize()
+    enc_after_e = {k: v.detach().clone().cpu().contiguous() for k, v in model.encoder.state_dict().items()}
+    if teacher_enc is not None:
+        # teacher forcing of the D half: Adam's first step moves every weight by ~lr*sign(g), which turns round-off
+        # in tiny gradients into O(lr) weight differences; loading the comparison run's post-E-step encoder weights
+        # makes the D half a function of identical state (the free-running variant is tested separately).
+        with torch.no_grad():
+            for n, p in model.encoder.named_parameters():
+                p.copy_(teacher_enc["encoder." + n].to(device=device, dtype=torch.float32))
+        model.params_changed()
     eng.d_step(eps[3:].contiguous(), h)
     torch.cuda.synchronize()
     grads_d = {"decoder." + n: p.grad.detach().clone().cpu().contiguous() for n, p in model.decoder.named_parameters()}
@@ -64,7 +73,8 @@ def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=N
                 lossE=st[4].item(), loss_rec=st[5].item(), lossD_rec_kl=st[6].item(), lossD_fake_kl=st[7].item(),
                 loss_rec_rec=st[8].item(), loss_fake_rec=st[9].item(), lossD=st[10].item(), nan=st[15].item())
     post = {k: v.detach().clone().cpu().contiguous() for k, v in model.state_dict().items()}
-    return dict(scalars=scal, grads_e=grads_e, grads_d=grads_d, post=post, init=init, images_e=imgs_e, model=model)
+    return dict(scalars=scal, grads_e=grads_e, grads_d=grads_d, post=post, init=init, images_e=imgs_e, model=model,
+                enc_after_e=enc_after_e)
 
 
 def run_oracle_iteration(cfg, batch, seed, bootstrap=False, init_sd=None, inputs=None, hp=None, dtype=torch.float64):
@@ -88,35 +98,54 @@ def rel_l2(a, b):
 
 
 def compare(eng, ora, tol, label="", lr=2e-4, verbose=True):
-    """tol: relative tolerance for scalars and relative-L2 tolerance for tensors (gradients, BN statistics)."""
-    worst = {}
+    """tol: relative tolerance for scalars; tensors (gradients, BN statistics) get 10*tol as relative-L2 / max-rel.
+    All deviations are measured first (and appended to gpurun_out/parity_report.jsonl), then asserted."""
+    import json
+    dev, fails = {}, []
     es, os_ = eng["scalars"], ora["scalars"]
-    assert es.get("nan", 0.0) == 0.0, label + ": NaN flag set"
+    if es.get("nan", 0.0) != 0.0:
+        fails.append("NaN flag set")
     for k in ("loss_rec_e", "lossE_real_kl", "expelbo_rec", "expelbo_fake", "lossE", "loss_rec", "lossD_rec_kl",
               "lossD_fake_kl", "loss_rec_rec", "loss_fake_rec", "lossD"):
+        if k not in os_:
+            continue
         r = abs(es[k] - os_[k]) / (abs(os_[k]) + 1e-30)
-        worst["scalar:" + k] = r
-        assert r < tol, "%s: scalar %s engine %.8g oracle %.8g rel %.3g > %.3g" % (label, k, es[k], os_[k], r, tol)
+        dev["scalar:" + k] = r
+        if not r < tol:
+            fails.append("scalar %s engine %.8g oracle %.8g rel %.3g > %.3g" % (k, es[k], os_[k], r, tol))
     for name in ("grads_e", "grads_d"):
-        assert set(eng[name]) == set(ora[name]), label + ": gradient key sets differ"
+        if set(eng[name]) != set(ora[name]):
+            fails.append(name + ": key sets differ")
+            continue
         for k in ora[name]:
             r = rel_l2(eng[name][k], ora[name][k])
-            worst[name + ":" + k] = r
-            assert r < 10 * tol, "%s: %s[%s] rel-L2 %.3g > %.3g" % (label, name, k, r, 10 * tol)
+            dev[name + ":" + k] = r
+            if not r < 10 * tol:
+                fails.append("%s[%s] rel-L2 %.3g > %.3g" % (name, k, r, 10 * tol))
     for k, v in ora["post"].items():
         e = eng["post"][k]
         if k.endswith("num_batches_tracked"):
-            assert int(e) == int(v), "%s: %s %d != %d" % (label, k, int(e), int(v))     # integer work: exact
+            if int(e) != int(v):                                   # integer work: exact
+                fails.append("%s %d != %d" % (k, int(e), int(v)))
         elif k.endswith(("running_mean", "running_var")):
             r = float((e.double() - v.double()).abs().max() / (v.double().abs().max() + 1e-12))
-            worst["bn:" + k] = r
-            assert r < 10 * tol, "%s: %s max-rel %.3g" % (label, k, r)
+            dev["bn:" + k] = r
+            if not r < 10 * tol:
+                fails.append("%s max-rel %.3g" % (k, r))
         else:
             # one Adam step from zero moments moves each weight by ~lr*sign(g): bounded check here, the Adam kernel
             # itself is unit-tested against torch.optim.Adam with identical gradients
             d = float((e.double() - v.double()).abs().max())
-            assert d <= 2.05 * lr + 1e-7, "%s: post-step %s differs by %.3g" % (label, k, d)
+            if not d <= 2.05 * lr + 1e-7:
+                fails.append("post-step %s differs by %.3g" % (k, d))
+    top = sorted(dev.items(), key=lambda kv: -kv[1])
     if verbose:
-        top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
-        print("[%s] worst deviations: %s" % (label, ", ".join("%s=%.2e" % kv for kv in top)))
-    return worst
+        print("[%s] worst deviations: %s" % (label, ", ".join("%s=%.2e" % kv for kv in top[:6])))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(dict(label=label, tol=tol, fails=fails, dev=dict(top))) + "\n")
+    except OSError:
+        pass
+    assert not fails, "%s: %d deviations over tolerance; first: %s" % (label, len(fails), "; ".join(fails[:4]))
+    return dev

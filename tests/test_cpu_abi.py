@@ -123,3 +123,19 @@ def test_helpers_match_oracle():
     with pytest.raises(NotImplementedError):
         M.calc_reconstruction_loss(x, y, "huber", "sum")
     assert M.str_to_list("1,2,3") == [1, 2, 3] and M.is_image_file("a.png") and not M.is_image_file("a.txt")
+
+
+def test_bootstrap_model_init_is_bit_identical_to_reference(golden_dir):
+    MB = importlib.import_module(PKG + ".train_soft_intro_vae_bootstrap")
+    g = torch.load(os.path.join(golden_dir, "tiny_bootstrap.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    model = MB.SoftIntroVAE(**g["arch"])
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g["init"].keys())
+    for k, v in g["init"].items():
+        assert torch.equal(sd[k], v), k
+    sig = list(inspect.signature(MB.train_soft_intro_vae).parameters)
+    assert "copy_to_target_freq" in sig and inspect.signature(MB.train_soft_intro_vae).parameters["gamma_r"].default == 1.0
+    got, _ = _engine_schema(g["arch"], variant=1)
+    want = {k: tuple(v.shape) for k, v in g["init"].items() if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))}
+    assert got == want

@@ -139,7 +139,8 @@ def test_bn_act_fwd_bwd(mode, with_id):
     dt = torch.empty_like(tg)
     gi = torch.empty_like(tg)
     dgam, dbet = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
-    L.check(lib.sivae_bn_act_bwd(L.ptr(_nhwc(dout).to(DEV)), L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(mi), L.ptr(dt),
+    doutg = _nhwc(dout).to(DEV)
+    L.check(lib.sivae_bn_act_bwd(L.ptr(doutg), L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(mi), L.ptr(dt),
                                  L.ptr(gi), L.ptr(dgam), L.ptr(dbet), 0, N, H, W, Cc, mode, L.ptr(ws), ws.numel(), _s()), "bn bwd")
     torch.cuda.synchronize()
     assert _rel(dt.cpu(), _nhwc(td.grad)) < 2e-5
@@ -159,7 +160,8 @@ def test_bn_eval_mode():
     mi = torch.empty(2 * Cc, device=DEV)
     out = torch.empty_like(tg)
     ws = torch.empty(1 << 16, dtype=torch.uint8, device=DEV)
-    L.check(lib.sivae_bn_act_fwd(L.ptr(tg), None, L.ptr(gamma.to(DEV)), L.ptr(beta.to(DEV)), L.ptr(rmg), L.ptr(rvg), None,
+    gg, bg = gamma.to(DEV), beta.to(DEV)       # keep the device tensors alive while the kernel runs
+    L.check(lib.sivae_bn_act_fwd(L.ptr(tg), None, L.ptr(gg), L.ptr(bg), L.ptr(rmg), L.ptr(rvg), None,
                                  L.ptr(mi), L.ptr(out), N, H, W, Cc, 0, 0, L.ptr(ws), ws.numel(), _s()), "bn eval")
     torch.cuda.synchronize()
     assert _rel(out.cpu(), _nhwc(y)) < 1e-5
@@ -191,7 +193,8 @@ def test_kl_reparam():
     kl_ref = -0.5 * (1 + lv - mu.pow(2) - lv.exp()).sum(1)
     z_ref = mu + eps.double() * torch.exp(0.5 * lv)
     zz, kl = torch.empty(B, z, device=DEV), torch.empty(B, device=DEV)
-    L.check(lib.sivae_kl_reparam(L.ptr(ml.to(DEV)), L.ptr(eps.to(DEV)), L.ptr(zz), L.ptr(kl), B, z, _s()), "kl")
+    mlg, epg = ml.to(DEV), eps.to(DEV)
+    L.check(lib.sivae_kl_reparam(L.ptr(mlg), L.ptr(epg), L.ptr(zz), L.ptr(kl), B, z, _s()), "kl")
     torch.cuda.synchronize()
     assert torch.allclose(kl.cpu().double(), kl_ref, rtol=1e-5)
     assert torch.allclose(zz.cpu().double(), z_ref, rtol=1e-5, atol=1e-6)
@@ -209,6 +212,8 @@ def test_adam_matches_torch_optim():
         grad = torch.randn(n, generator=g) * 10.0 ** float(torch.randint(-6, 2, (1,), generator=g))
         p_ref.grad = grad.clone()
         opt.step()
-        L.check(lib.sivae_adam_flat(L.ptr(p), L.ptr((grad * 4).to(DEV)), L.ptr(m), L.ptr(v), n, 2e-4, 0.25, step, _s()), "adam")
+        gdev = (grad * 4).to(DEV)
+        L.check(lib.sivae_adam_flat(L.ptr(p), L.ptr(gdev), L.ptr(m), L.ptr(v), n, 2e-4, 0.25, step, _s()), "adam")
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     assert torch.allclose(p.cpu(), p_ref.detach(), rtol=0, atol=2e-7)
