@@ -159,6 +159,17 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step_resident(i)
+    graph_ms = None
+    if args.graph:
+        # optional: the same step replayed from a CUDA graph (removes ~1100 kernel-launch latencies per step at the
+        # small configs).  Captured on a side stream; the Adam step counters live on the device, so replays advance.
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            step_resident(0)
+        for _ in range(2):
+            g_.replay()
+        graph_ms = timed(lambda i: g_.replay(), args.steps) / args.steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -207,6 +218,8 @@ def run_ours(args):
                          h2d_bytes_per_step=batch * 3 * size * size * 4 + batch * zdim * 4, d2h_bytes_per_step=64),
                 gpu_launches=int(launches), roofline=roof, clocks=sampler.summary() if rank == 0 else None,
                 last_stats=dict(loss_rec=float(st[5]), kl_real=float(st[1]), lossE=float(st[4]), lossD=float(st[10])))
+    if graph_ms is not None:
+        line["cuda_graph"] = dict(ms_per_step=round(graph_ms, 3), value=round(world * batch / (graph_ms / 1e3), 2))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, budget_s=args.cpu_budget)
     if rank == 0:
@@ -232,8 +245,9 @@ def cpu_baseline(cfg_name, budget_s=25.0, steps=1, warmup=0):
     size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # sample size: ~1.5 GFLOP/s/core sustained in fp32 conv -> images that fit the budget, at least 2 (BN needs >1)
-    est_rate = 1.5e9 * cores
+    # sample size: the torch CPU path sustains only ~20-50 GFLOP/s on this step regardless of core count (measured:
+    # 62.9 s for 1.25 TFLOP on 128 threads) -> images that fit the budget, at least 2 (train-mode BN needs > 1)
+    est_rate = 30e9
     b = int(max(2, min(batch, budget_s * est_rate / (gflop_img * 1e9))))
     arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
     sd = O.make_state_dict(arch, seed=0, bootstrap=boot)
@@ -284,6 +298,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     if args.impl == "reference":

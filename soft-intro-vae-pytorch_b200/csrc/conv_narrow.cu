@@ -1,0 +1,226 @@
+// fp32 CUDA-core kernels for the two image-facing 5x5 convolutions whose narrow side (cdim = 1..4 channels) does not
+// fill a tensor-core tile: the encoder stem (cdim -> c0, reference :89) and the decoder's `predict` (c0 -> cdim, :159).
+//   k_narrow_in_fwd   y[p][co] = sum_{tap,a} x[p+tap][a] * w[co][tap][a]          stem forward, predict dgrad
+//   k_narrow_corr     G[tap][a][c] = sum_p nar[p][a] * wide[p+tap][c]             stem wgrad, predict wgrad
+// (the wide->narrow direction, predict forward / stem dgrad, runs on the tcgen05 kernel with a masked epilogue.)
+// Both are FMA-bound direct convolutions with the halo tile staged in shared memory; exact fp32 (no tf32 rounding).
+#include "kernels.h"
+
+namespace sivae {
+
+static inline unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// narrow-in forward: one thread = one output pixel x all Cout channels (COUT_T <= 64 per pass)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NI_T = 16;   // 16x16 pixel tile
+template <int KS>
+__global__ void __launch_bounds__(256) k_narrow_in_fwd(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* addend, float* y, int N,
+                                                       int H, int W, int A, int Cout) {
+  extern __shared__ float sm[];
+  constexpr int HT = NI_T + KS - 1;
+  float* sx = sm;                              // [HT][HT][A]
+  float* sw = sm + HT * HT * 4;                // [tap][a][Cout]  (transposed so that 4 consecutive co are one LDS.128)
+  const int tiles_w = (W + NI_T - 1) / NI_T, tiles_h = (H + NI_T - 1) / NI_T;
+  const int tile = blockIdx.x;
+  const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
+  const int w0 = tw * NI_T, h0 = th * NI_T, pad = KS / 2;
+  const int taps = KS * KS;
+  for (int i = threadIdx.x; i < Cout * taps * A; i += 256) {
+    int a = i % A, t = (i / A) % taps, co = i / (A * taps);
+    sw[(t * A + a) * Cout + co] = w[i];
+  }
+  for (int i = threadIdx.x; i < HT * HT * A; i += 256) {
+    int a = i % A, cx = (i / A) % HT, cy = i / (A * HT);
+    int hh = h0 + cy - pad, ww = w0 + cx - pad;
+    sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)n * H + hh) * W + ww) * A + a] : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % NI_T, ty = threadIdx.x / NI_T;
+  const int ho = h0 + ty, wo = w0 + tx;
+  const bool valid = ho < H && wo < W;
+  const long long pix = ((long long)n * H + ho) * W + wo;
+  for (int c0 = 0; c0 < Cout; c0 += 64) {
+    const int cn = min(64, Cout - c0);          // multiple of 4
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int r = 0; r < KS; ++r)
+      for (int s = 0; s < KS; ++s) {
+        const float* xp = sx + ((ty + r) * HT + tx + s) * A;
+        const float* wp = sw + (r * KS + s) * A * Cout + c0;
+        for (int a = 0; a < A; ++a) {
+          const float xv = xp[a];
+          const float4* w4 = reinterpret_cast<const float4*>(wp + a * Cout);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (4 * j < cn) {
+              float4 q = w4[j];
+              acc[4 * j] = fmaf(xv, q.x, acc[4 * j]);
+              acc[4 * j + 1] = fmaf(xv, q.y, acc[4 * j + 1]);
+              acc[4 * j + 2] = fmaf(xv, q.z, acc[4 * j + 2]);
+              acc[4 * j + 3] = fmaf(xv, q.w, acc[4 * j + 3]);
+            }
+          }
+        }
+      }
+    if (valid) {
+      float* dst = y + pix * Cout + c0;
+      const float* add = addend ? addend + pix * Cout + c0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (4 * j < cn) {
+          float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          if (bias) {
+            o.x += bias[c0 + 4 * j]; o.y += bias[c0 + 4 * j + 1]; o.z += bias[c0 + 4 * j + 2]; o.w += bias[c0 + 4 * j + 3];
+          }
+          if (add) {
+            float4 q = *reinterpret_cast<const float4*>(add + 4 * j);
+            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+          }
+          *reinterpret_cast<float4*>(dst + 4 * j) = o;
+        }
+      }
+    }
+  }
+}
+
+bool conv_narrow_in_supported(const ConvShape& s) {
+  return s.Cin >= 1 && s.Cin <= 4 && s.Cout % 4 == 0 && s.Cout <= 256 && (s.k == 5 || s.k == 3) && s.N * (long long)s.H * s.W > 0;
+}
+void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,
+                               const ConvShape& s, cudaStream_t st) {
+  g_launches += 1;
+  const int HT = NI_T + s.k - 1;
+  size_t shmem = ((size_t)HT * HT * 4 + (size_t)s.Cout * s.k * s.k * s.Cin) * sizeof(float);
+  unsigned grid = (unsigned)(cdivu(s.W, NI_T) * cdivu(s.H, NI_T) * s.N);
+  if (s.k == 5) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_narrow_in_fwd<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    k_narrow_in_fwd<5><<<grid, 256, shmem, st>>>(x, w, bias, addend, y, s.N, s.H, s.W, s.Cin, s.Cout);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_narrow_in_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    k_narrow_in_fwd<3><<<grid, 256, shmem, st>>>(x, w, bias, addend, y, s.N, s.H, s.W, s.Cin, s.Cout);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// narrow x wide correlation (wgrad of both image-facing layers)
+//   G[tap][a][c] = sum_{n,h,w} nar[n,h,w][a] * wide[n, h + r - pad, w + s - pad][c]
+// persistent blocks loop over pixel tiles of TR x 32; thread = (channel c, tap group); partial G per block, fixed-order
+// reduction (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NC_TW = 32;
+template <int C, int KS>
+struct NarrowCorrCfg {
+  static constexpr int GROUPS = 256 / C;                          // tap groups
+  static constexpr int TAPS = KS * KS;
+  static constexpr int TPG = (TAPS + GROUPS - 1) / GROUPS;        // taps per group
+  static constexpr int TR = (C <= 64) ? 8 : 4;                    // tile rows
+  static constexpr int HTH = TR + KS - 1, HTW = NC_TW + KS - 1;
+  static constexpr size_t SMEM = ((size_t)HTH * HTW * C + (size_t)TR * NC_TW * 4) * sizeof(float);
+};
+template <int C, int KS>
+__global__ void __launch_bounds__(256) k_narrow_corr(const float* __restrict__ nar, const float* __restrict__ wide,
+                                                     float* __restrict__ part, int N, int H, int W, int A) {
+  using CF = NarrowCorrCfg<C, KS>;
+  extern __shared__ float sm[];
+  float* swd = sm;                                  // [HTH][HTW][C]
+  float* snr = sm + CF::HTH * CF::HTW * C;          // [TR][32][4]
+  const int c = threadIdx.x % C, grp = threadIdx.x / C;
+  const int t_begin = grp * CF::TPG;
+  const int pad = KS / 2;
+  float acc[CF::TPG][4];
+#pragma unroll
+  for (int i = 0; i < CF::TPG; ++i)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc[i][a] = 0.f;
+  const int tiles_w = (W + NC_TW - 1) / NC_TW, tiles_h = (H + CF::TR - 1) / CF::TR;
+  const long long n_tiles = (long long)tiles_w * tiles_h * N;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tw = (int)(tile % tiles_w), th = (int)((tile / tiles_w) % tiles_h), n = (int)(tile / ((long long)tiles_w * tiles_h));
+    const int w0 = tw * NC_TW, h0 = th * CF::TR;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CF::HTH * CF::HTW * (C / 4); i += 256) {
+      int c4 = i % (C / 4), cx = (i / (C / 4)) % CF::HTW, cy = i / ((C / 4) * CF::HTW);
+      int hh = h0 + cy - pad, ww = w0 + cx - pad;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(reinterpret_cast<const float4*>(wide + (((long long)n * H + hh) * W + ww) * C) + c4);
+      reinterpret_cast<float4*>(swd)[i] = v;
+    }
+    for (int i = threadIdx.x; i < CF::TR * NC_TW * 4; i += 256) {
+      int a = i & 3, px = (i >> 2) % NC_TW, py = i / (4 * NC_TW);
+      int hh = h0 + py, ww = w0 + px;
+      snr[i] = (a < A && hh < H && ww < W) ? nar[(((long long)n * H + hh) * W + ww) * A + a] : 0.f;
+    }
+    __syncthreads();
+    for (int py = 0; py < CF::TR; ++py)
+      for (int px = 0; px < NC_TW; ++px) {
+        const float4 nv = *reinterpret_cast<const float4*>(snr + (py * NC_TW + px) * 4);   // broadcast
+#pragma unroll
+        for (int i = 0; i < CF::TPG; ++i) {
+          const int t = t_begin + i;
+          if (t < CF::TAPS) {
+            const int r = t / KS, s = t - r * KS;
+            const float wv = swd[((py + r) * CF::HTW + px + s) * C + c];
+            acc[i][0] = fmaf(nv.x, wv, acc[i][0]);
+            acc[i][1] = fmaf(nv.y, wv, acc[i][1]);
+            acc[i][2] = fmaf(nv.z, wv, acc[i][2]);
+            acc[i][3] = fmaf(nv.w, wv, acc[i][3]);
+          }
+        }
+      }
+  }
+  // part[block][tap][a(4)][C]
+  float* dst = part + (long long)blockIdx.x * CF::TAPS * 4 * C;
+#pragma unroll
+  for (int i = 0; i < CF::TPG; ++i) {
+    const int t = t_begin + i;
+    if (t < CF::TAPS) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) dst[(t * 4 + a) * C + c] = acc[i][a];
+    }
+  }
+}
+// mode 0 (predict wgrad): dw[a][tap][c]   = G[tap][a][c]             (nar = dy (A = Cout), wide = x)
+// mode 1 (stem wgrad):    dw[c][tap][a]   = G[mirror(tap)][a][c]     (nar = x  (A = Cin),  wide = dy)
+__global__ void k_narrow_corr_reduce(const float* __restrict__ part, float* __restrict__ dw, int nblk, int taps, int A, int C,
+                                     int mode, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;     // over taps*A*C outputs in G order
+  if (i >= taps * A * C) return;
+  int c = i % C, a = (i / C) % A, t = i / (C * A);
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)part[((long long)b * taps + t) * 4 * C + a * C + c];
+  long long o = mode == 0 ? ((long long)a * taps + t) * C + c : ((long long)c * taps + (taps - 1 - t)) * A + a;
+  dw[o] = accumulate ? (float)((double)dw[o] + s) : (float)s;
+}
+
+static int narrow_corr_blocks() { return 148 * 2; }
+bool conv_narrow_corr_supported(int wideC, int narrowA, int k) {
+  return (wideC == 32 || wideC == 64 || wideC == 128) && narrowA >= 1 && narrowA <= 4 && k == 5;
+}
+size_t conv_narrow_corr_scratch_bytes(int wideC, int k) { return (size_t)narrow_corr_blocks() * k * k * 4 * wideC * sizeof(float); }
+
+template <int C>
+static void launch_corr_t(const float* nar, const float* wide, float* part, int N, int H, int W, int A, int nblk, cudaStream_t st) {
+  using CF = NarrowCorrCfg<C, 5>;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_narrow_corr<C, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM); attr = true; }
+  k_narrow_corr<C, 5><<<nblk, 256, CF::SMEM, st>>>(nar, wide, part, N, H, W, A);
+}
+void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int N, int H, int W, int A, int C, int k, int mode,
+                             bool accumulate, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  g_launches += 2;
+  float* part = (float*)scratch;
+  long long tiles = (long long)cdivu(W, NC_TW) * cdivu(H, C <= 64 ? 8 : 4) * N;
+  int nblk = (int)(tiles < narrow_corr_blocks() ? tiles : narrow_corr_blocks());
+  if (C == 32) launch_corr_t<32>(nar, wide, part, N, H, W, A, nblk, st);
+  else if (C == 64) launch_corr_t<64>(nar, wide, part, N, H, W, A, nblk, st);
+  else launch_corr_t<128>(nar, wide, part, N, H, W, A, nblk, st);
+  int total = k * k * A * C;
+  k_narrow_corr_reduce<<<cdivu(total, 128), 128, 0, st>>>(part, dw, nblk, k * k, A, C, mode, accumulate ? 1 : 0);
+}
+
+}  // namespace sivae

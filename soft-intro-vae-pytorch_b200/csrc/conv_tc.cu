@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 namespace sivae {
 
@@ -278,7 +279,20 @@ __global__ void __launch_bounds__(192) k_conv_fwd_tc(const __grid_constant__ CUt
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (valid) {
+      if (valid && (p.Cout & 3) != 0) {
+        // narrow output (e.g. the 3-channel predict layer / stem dgrad): scalar stores of the first Cout columns
+        float* dst = p.y + pix * p.Cout + col0 + c;
+        const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + c + j < p.Cout) {
+            float o = __uint_as_float(v[j]);
+            if (p.bias) o += __ldg(p.bias + col0 + c + j);
+            if (add) o += add[j];
+            dst[j] = o;
+          }
+        }
+      } else if (valid) {
         float* dst = p.y + pix * p.Cout + col0 + c;
         const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
 #pragma unroll
@@ -313,7 +327,8 @@ static void pick_tile(int H, int W, int* bw, int* bh, int* bn) {
 }
 
 bool conv_tc_supported_fwd(const ConvShape& s) {
-  if (s.Cin % 32 != 0 || s.Cout % 4 != 0 || s.Cout < 16) return false;
+  // Cout need not fill a UMMA tile: filter rows beyond Cout are TMA out-of-bounds zeros and the epilogue masks them
+  if (s.Cin % 32 != 0 || s.Cout < 1) return false;
   if (s.k != 1 && s.k != 3 && s.k != 5) return false;
   int bw, bh, bn;
   pick_tile(s.H, s.W, &bw, &bh, &bn);
@@ -336,6 +351,199 @@ static int launch_fwd_t(const CUtensorMap& mx, const CUtensorMap& mw, const FwdP
   return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// forward / dgrad kernel v2: persistent (one CTA per SM loops over output tiles), double-buffered TMEM accumulator
+// so that the epilogue of tile i overlaps the mainloop of tile i+1; BLOCK_N up to 256 (A tile re-read halves).
+// Tile order: n-tiles of one pixel tile are adjacent (they share the A tile through L2).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int BLOCK_N, int STAGES>
+struct Fwd2Smem {
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__ CUtensorMap map_x,
+                                                         const __grid_constant__ CUtensorMap map_w, const FwdParams p,
+                                                         const int n_tiles, const int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = Fwd2Smem<BLOCK_N, STAGES>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cchunks = p.Cin >> 5;
+  const int num_kb = p.ks * p.ks * cchunks;
+  const int pad = p.ks >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;                                          // global k-block counter of this CTA (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, col0 = nt * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_expect_tx(&full[st], SM::STAGE_BYTES);
+          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) << 5;
+          const int r = tap / p.ks, s = tap - r * p.ks;
+          uint8_t* sa = smem + st * SM::STAGE_BYTES;
+          tma_load_4d(sa, &map_x, &full[st], c0, w0 + s - pad, h0 + r - pad, n0);
+          tma_load_2d(sa + TC_A_BYTES, &map_w, &full[st], tap * p.Cin + c0, col0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+    int it = 0, lt = 0;                                    // lt = local tile counter
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);    // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int st = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
+          const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
+            uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+            umma_tf32(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dw = row % p.bw, dh = (row / p.bw) % p.bh, dn = row / (p.bw * p.bh);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, col0 = nt * BLOCK_N;
+      const int n = n0 + dn;
+      const bool valid = n < p.N;
+      const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        if (col0 + c >= p.Cout) break;                     // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        if (valid && (p.Cout & 3) != 0) {
+          float* dst = p.y + pix * p.Cout + col0 + c;
+          const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + c + j < p.Cout) {
+              float o = __uint_as_float(v[j]);
+              if (p.bias) o += __ldg(p.bias + col0 + c + j);
+              if (add) o += add[j];
+              dst[j] = o;
+            }
+          }
+        } else if (valid) {
+          float* dst = p.y + pix * p.Cout + col0 + c;
+          const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + c + j < p.Cout) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (p.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (add) {
+                float4 a = *reinterpret_cast<const float4*>(add + j);
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+      }
+      // this warp is done reading the accumulator: release it to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<SM::TMEM_COLS>(tmem_base);
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+template <int BLOCK_N, int STAGES>
+static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const FwdParams& p, int m_tiles, cudaStream_t st) {
+  using SM = Fwd2Smem<BLOCK_N, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_fwd_tc2<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+  const int total = m_tiles * n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  g_launches += 1;
+  k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, p, n_tiles, total);
+  return (int)cudaGetLastError();
+}
+static int fwd_kernel_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_FWD");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        cudaStream_t st) {
   FwdParams p;
@@ -345,15 +553,26 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   p.bias = bias; p.addend = addend; p.y = y;
   const int tiles_n = (s.N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  const int block_n = s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32);
   CUtensorMap mx, mw;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
   if (r) return r;
+  if (fwd_kernel_version() == 1) {
+    const int block_n = s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32);
+    r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
+    if (r) return r;
+    if (block_n == 128) return launch_fwd_t<128, 3>(mx, mw, p, m_tiles, st);
+    if (block_n == 64) return launch_fwd_t<64, 4>(mx, mw, p, m_tiles, st);
+    return launch_fwd_t<32, 4>(mx, mw, p, m_tiles, st);
+  }
+  // v2: widest N tile that the layer fills; few-tile problems prefer narrower tiles (more CTAs busy)
+  int block_n = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32));
+  while (block_n > 64 && (long long)m_tiles * ((s.Cout + block_n - 1) / block_n) < num_sms()) block_n >>= 1;
   r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
   if (r) return r;
-  if (block_n == 128) return launch_fwd_t<128, 3>(mx, mw, p, m_tiles, st);
-  if (block_n == 64) return launch_fwd_t<64, 4>(mx, mw, p, m_tiles, st);
-  return launch_fwd_t<32, 4>(mx, mw, p, m_tiles, st);
+  if (block_n == 256) return launch_fwd2_t<256, 4>(mx, mw, p, m_tiles, st);
+  if (block_n == 128) return launch_fwd2_t<128, 6>(mx, mw, p, m_tiles, st);
+  if (block_n == 64) return launch_fwd2_t<64, 8>(mx, mw, p, m_tiles, st);
+  return launch_fwd2_t<32, 8>(mx, mw, p, m_tiles, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -46,7 +46,9 @@ struct Net {
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *bn = nullptr, *derived = nullptr;
   long long* nbt = nullptr;
   bool dirty = true;
-  long long adam_step = 0;
+  long long* step_dev = nullptr;   // device-side Adam step counter + 2 floats of bias-correction scratch (workspace)
+  float* coef_dev = nullptr;
+  long long step_pending = 0;      // value to load into step_dev at the next workspace bind
   bool present = false;
 };
 
@@ -80,6 +82,7 @@ struct sivae_engine {
   int C_last = 0, hw_last = 0;     // conv_output_size = (C_last, hw_last, hw_last)
   long long feat = 0;              // C_last*hw_last^2
   bool tc = false;                 // tcgen05 backend in use (activations pre-rounded to tf32)
+  bool fast = false;               // cdim-facing narrow CUDA-core kernels in use (false: generic exact SIMT everywhere)
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0, ws_need = 0;
   EncPass ep[3]; DecPass dp[4];
@@ -205,12 +208,20 @@ static size_t reduce_scratch_bytes(const sivae_engine* e) {
   size_t m = bn_scratch_bytes(B * S * S, c.channels[0]);
   size_t v = mse3_scratch_bytes((int)B, (long long)c.cdim * S * S);
   if (v > m) m = v;
+  v = colsum_scratch_bytes(c.cdim);
+  if (v > m) m = v;
+  v = linear_dgrad_scratch_bytes((int)B, (int)e->feat, 2 * c.zdim);
+  if (v > m) m = v;
+  v = linear_dgrad_scratch_bytes((int)B, c.zdim, (int)e->feat);
+  if (v > m) m = v;
   auto upd_conv = [&](const Conv& cv, int size) {
     if (cv.k == 0) return;
     ConvShape s{(int)B, size, size, cv.cin, cv.cout, cv.k};
     size_t a = conv_wgrad_simt_scratch_bytes(s);
     if (a > m) m = a;
     if (conv_tc_supported_wgrad(s)) { size_t t = conv_wgrad_tc_scratch_bytes(s); if (t > m) m = t; }
+    if (cv.cin <= 4 && conv_narrow_corr_supported(cv.cout, cv.cin, cv.k)) { size_t t = conv_narrow_corr_scratch_bytes(cv.cout, cv.k); if (t > m) m = t; }
+    if (cv.cout <= 4 && conv_narrow_corr_supported(cv.cin, cv.cout, cv.k)) { size_t t = conv_narrow_corr_scratch_bytes(cv.cin, cv.k); if (t > m) m = t; }
   };
   for (int ni = 0; ni < 2; ++ni) {
     const Net& n = e->nets[ni];
@@ -231,7 +242,11 @@ static size_t carve(sivae_engine* e, char* base) {
   Bump bp; bp.base = base;
   const long long B = c.max_batch, S = c.image_size, z = c.zdim;
   for (int ni = 0; ni < 3; ++ni)
-    if (e->nets[ni].present) e->nets[ni].derived = bp.take<float>(e->nets[ni].derived_floats);
+    if (e->nets[ni].present) {
+      e->nets[ni].derived = bp.take<float>(e->nets[ni].derived_floats);
+      e->nets[ni].step_dev = bp.take<long long>(2);
+      e->nets[ni].coef_dev = bp.take<float>(4);
+    }
   e->real = bp.take<float>(B * S * S * c.cdim);
   e->noise = bp.take<float>(B * z);
   e->z_keep = bp.take<float>(B * z);
@@ -291,9 +306,6 @@ static size_t carve(sivae_engine* e, char* base) {
 // -------------------------------------------------------------------------------------------------------------
 // conv dispatch
 // -------------------------------------------------------------------------------------------------------------
-static bool use_tc(const sivae_engine* e, const ConvShape& s) {
-  return e->tc && conv_tc_supported_fwd(s);
-}
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
 enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_COUNT = 4 };
@@ -319,13 +331,20 @@ struct ProfScope {
   }
   ~ProfScope() { if (r) cudaEventRecord(r->b, st); }
 };
+// which implementation serves a convolution (exact = SIMT-only engine; narrow = cdim-facing CUDA-core kernels)
+static bool fwd_on_tc(const sivae_engine* e, const ConvShape& s) { return e->tc && conv_tc_supported_fwd(s); }
+static bool fwd_on_narrow(const sivae_engine* e, const ConvShape& s) { return e->fast && conv_narrow_in_supported(s); }
+
 static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
   if (!n.dirty) return 0;
   auto one = [&](const Conv& c) {
     if (c.k == 0) return;
-    // dgrad filters (as a forward conv over dy): rounded to tf32 when the tcgen05 path consumes them
-    launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, e->tc, st);
-    if (e->tc) launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, (long long)c.cout * c.cin * c.k * c.k, st);
+    // dgrad filters (a dgrad is a forward conv over dy): rounded to tf32 only when the tensor core consumes them
+    ConvShape sd{1, 8, 8, c.cout, c.cin, c.k};
+    launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, fwd_on_tc(e, sd) && !fwd_on_narrow(e, sd), st);
+    ConvShape sf{1, 8, 8, c.cin, c.cout, c.k};
+    if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf))
+      launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, (long long)c.cout * c.cin * c.k * c.k, st);
   };
   if (n.enc) one(n.stem); else one(n.predict);
   for (const Block& b : n.blocks) { one(b.ce); one(b.c1); one(b.c2); }
@@ -333,42 +352,48 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
   CHECK_CUDA_RET();
   return 0;
 }
-// y = conv(x, W) (+bias) (+addend)
+// y = conv(x, filt) (+bias) (+addend).  w_master: fp32 filter [Cout][k][k][Cin]; w_tc: its tf32-rounded copy
+static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const float* w_master, const float* w_tc,
+                    const float* bias, const float* addend, float* y, cudaStream_t st) {
+  if (fwd_on_narrow(e, s)) {
+    ProfScope ps(PC_SIMT_FWD, s, st);
+    launch_conv_narrow_in_fwd(x, w_master, bias, addend, y, s, st);
+  } else if (fwd_on_tc(e, s)) {
+    ProfScope ps(PC_TC_FWD, s, st);
+    int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st);
+    if (r) return fail(r, "tcgen05 conv launch failed");
+  } else {
+    ProfScope ps(PC_SIMT_FWD, s, st);
+    launch_conv_fwd_simt(x, w_master, bias, addend, y, s, st);
+  }
+  return 0;
+}
 static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, float* y, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
-  if (use_tc(e, s)) {
-    ProfScope ps(PC_TC_FWD, s, st);
-    int r = launch_conv_fwd_tc(x, n.derived + c.wr_off, bias, addend, y, s, st);
-    if (r) return fail(r, "tcgen05 conv fwd launch failed");
-  } else {
-    ProfScope ps(PC_SIMT_FWD, s, st);
-    launch_conv_fwd_simt(x, n.params + c.w_off, bias, addend, y, s, st);
-  }
-  return 0;
+  return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st);
 }
 // dx = conv_transpose(dy, W) (+addend): a forward conv over dy with the packed dgrad filters
 static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cout, c.cin, c.k};
-  if (use_tc(e, s)) {
-    ProfScope ps(PC_TC_FWD, s, st);
-    int r = launch_conv_fwd_tc(dy, n.derived + c.wd_off, nullptr, addend, dx, s, st);
-    if (r) return fail(r, "tcgen05 conv dgrad launch failed");
-  } else {
-    ProfScope ps(PC_SIMT_FWD, s, st);
-    launch_conv_fwd_simt(dy, n.derived + c.wd_off, nullptr, addend, dx, s, st);
-  }
-  return 0;
+  return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st);
 }
 static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
-  if (e->tc && conv_tc_supported_wgrad(s)) {
+  float* dw = n.grads + c.w_off;
+  if (e->fast && c.cin <= 4 && conv_narrow_corr_supported(c.cout, c.cin, c.k)) {            // stem
+    ProfScope ps(PC_SIMT_WGRAD, s, st);
+    launch_conv_narrow_corr(x, dy, dw, B, size, size, c.cin, c.cout, c.k, 1, true, e->red, e->red_bytes, st);
+  } else if (e->fast && c.cout <= 4 && conv_narrow_corr_supported(c.cin, c.cout, c.k)) {     // predict
+    ProfScope ps(PC_SIMT_WGRAD, s, st);
+    launch_conv_narrow_corr(dy, x, dw, B, size, size, c.cout, c.cin, c.k, 0, true, e->red, e->red_bytes, st);
+  } else if (e->tc && conv_tc_supported_wgrad(s)) {
     ProfScope ps(PC_TC_WGRAD, s, st);
-    int r = launch_conv_wgrad_tc(x, dy, n.grads + c.w_off, s, true, e->red, e->red_bytes, st);
+    int r = launch_conv_wgrad_tc(x, dy, dw, s, true, e->red, e->red_bytes, st);
     if (r) return fail(r, "tcgen05 conv wgrad launch failed");
   } else {
     ProfScope ps(PC_SIMT_WGRAD, s, st);
-    launch_conv_wgrad_simt(x, dy, n.grads + c.w_off, s, true, e->red, e->red_bytes, st);
+    launch_conv_wgrad_simt(x, dy, dw, s, true, e->red, e->red_bytes, st);
   }
   return 0;
 }
@@ -477,7 +502,7 @@ static int enc_backward(sivae_engine* e, Net& n, EncPass& p, const float* dml, b
   const sivae_config& c = e->cfg;
   const int S = c.image_size;
   if (wgrad) launch_linear_wgrad(p.feat, dml, n.grads + n.fc.w_off, n.grads + n.fc.b_off, B, n.fc.fin, n.fc.fout, true, st);
-  launch_linear_dgrad(dml, n.params + n.fc.w_off, e->dfeat, B, n.fc.fin, n.fc.fout, st);
+  launch_linear_dgrad(dml, n.params + n.fc.w_off, e->dfeat, B, n.fc.fin, n.fc.fout, e->red, st);
   float* cur = e->sb[0];
   float* nxt = e->sb[1];
   launch_nchw_to_nhwc(e->dfeat, cur, B, e->C_last, e->hw_last, e->hw_last, st);
@@ -504,7 +529,7 @@ static int dec_backward(sivae_engine* e, Net& n, DecPass& p, const float* dy, bo
   float* nxt = e->sb[1];
   const float* xlast = p.blk.back().out;
   if (wgrad) {
-    launch_colsum(dy, n.grads + n.predict.b_off, (long long)B * S * S, c.cdim, true, st);
+    launch_colsum(dy, n.grads + n.predict.b_off, (long long)B * S * S, c.cdim, true, e->red, st);
     TRY(conv_wgrad(e, n, n.predict, xlast, dy, B, S, st));
   }
   TRY(conv_dgrad(e, n, n.predict, dy, cur, nullptr, B, S, st));
@@ -516,7 +541,7 @@ static int dec_backward(sivae_engine* e, Net& n, DecPass& p, const float* dy, bo
   launch_nhwc_to_nchw(cur, e->dfeat2, B, e->C_last, e->hw_last, e->hw_last, st);
   launch_relu_bwd(p.h, e->dfeat2, (long long)B * e->feat, st);
   if (wgrad) launch_linear_wgrad(p.zin, e->dfeat2, n.grads + n.fc.w_off, n.grads + n.fc.b_off, B, n.fc.fin, n.fc.fout, true, st);
-  if (dz) launch_linear_dgrad(e->dfeat2, n.params + n.fc.w_off, dz, B, n.fc.fin, n.fc.fout, st);
+  if (dz) launch_linear_dgrad(e->dfeat2, n.params + n.fc.w_off, dz, B, n.fc.fin, n.fc.fout, e->red, st);
   CHECK_CUDA_RET();
   return 0;
 }
@@ -527,7 +552,7 @@ static int dec_backward(sivae_engine* e, Net& n, DecPass& p, const float* dy, bo
 extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   if (!cfg || !out) return fail(-1, "null argument");
   if (cfg->n_channels < 1 || cfg->n_channels > 16) return fail(-2, "n_channels must be in [1,16]");
-  if (cfg->cdim < 1 || cfg->zdim < 1 || cfg->max_batch < 1) return fail(-2, "bad cdim/zdim/max_batch");
+  if (cfg->cdim < 1 || cfg->cdim > 8 || cfg->zdim < 1 || cfg->max_batch < 1) return fail(-2, "bad cdim (1..8) / zdim / max_batch");
   int S = cfg->image_size;
   if (S < 2 || (S % (1 << cfg->n_channels)) != 0) return fail(-2, "image_size must be divisible by 2^len(channels)");
   for (int i = 0; i < cfg->n_channels; ++i)
@@ -540,6 +565,7 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   build_decoder(e, e->nets[1]);
   if (cfg->variant == 1) build_decoder(e, e->nets[2]);
   e->tc = cfg->conv_backend != SIVAE_CONV_SIMT;
+  e->fast = cfg->conv_backend != SIVAE_CONV_SIMT;
   e->ws_need = carve(e, nullptr);
   *out = e;
   return 0;
@@ -593,7 +619,10 @@ extern "C" int sivae_bind_workspace(sivae_engine* e, void* ws, long long bytes) 
   if (((uintptr_t)ws & 255) != 0) return fail(-3, "workspace must be 256-byte aligned");
   e->ws = ws; e->ws_bytes = (size_t)bytes;
   carve(e, (char*)ws);
-  for (int i = 0; i < 3; ++i) e->nets[i].dirty = true;
+  for (int i = 0; i < 3; ++i) {
+    e->nets[i].dirty = true;
+    if (e->nets[i].present) cudaMemcpy(e->nets[i].step_dev, &e->nets[i].step_pending, sizeof(long long), cudaMemcpyHostToDevice);
+  }
   e->have_e_state = false;
   return 0;
 }
@@ -760,8 +789,9 @@ extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_sc
   Net* n = get_net(e, net);
   if (!n) return fail(-1, "bad net id");
   if (!n->grads || !n->m || !n->v) return fail(-4, "optimiser buffers not bound");
-  n->adam_step += 1;
-  launch_adam(n->params, n->grads, n->m, n->v, n->n_params, lr, grad_scale, 0.9f, 0.999f, 1e-8f, n->adam_step, (cudaStream_t)stream);
+  if (!n->step_dev) return fail(-4, "workspace not bound");
+  launch_adam(n->params, n->grads, n->m, n->v, n->n_params, lr, grad_scale, 0.9f, 0.999f, 1e-8f, n->step_dev, n->coef_dev,
+              (cudaStream_t)stream);
   n->dirty = true;
   CHECK_CUDA_RET();
   return 0;
@@ -769,12 +799,19 @@ extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_sc
 extern "C" int sivae_adam_set_step(sivae_engine* e, int net, long long step) {
   Net* n = get_net(e, net);
   if (!n) return fail(-1, "bad net id");
-  n->adam_step = step;
+  n->step_pending = step;
+  if (n->step_dev) cudaMemcpy(n->step_dev, &step, sizeof(long long), cudaMemcpyHostToDevice);
   return 0;
 }
+// synchronises (reads the device counter)
 extern "C" long long sivae_adam_get_step(const sivae_engine* e, int net) {
   Net* n = get_net(const_cast<sivae_engine*>(e), net);
-  return n ? n->adam_step : -1;
+  if (!n) return -1;
+  if (!n->step_dev) return n->step_pending;
+  long long s = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(&s, n->step_dev, sizeof(long long), cudaMemcpyDeviceToHost);
+  return s;
 }
 
 extern "C" int sivae_encode(sivae_engine* e, const float* x_nchw, int B, float* mu, float* logvar, int train, void* stream) {
@@ -840,15 +877,21 @@ extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void
 }
 
 // ---- single-kernel entry points ------------------------------------------------------------------------------
+// backend: SIVAE_CONV_SIMT = generic exact fp32 kernel; SIVAE_CONV_TCGEN05 = tensor-core kernel or error -7;
+// SIVAE_CONV_AUTO = what the engine would pick for this shape (narrow CUDA-core kernel, tensor core, generic)
 extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y, int N, int H,
                                 int W, int Cin, int Cout, int k, int backend, void* stream) {
   ConvShape s{N, H, W, Cin, Cout, k};
+  cudaStream_t st = (cudaStream_t)stream;
   if (backend == SIVAE_CONV_TCGEN05) {
     if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
-    int r = launch_conv_fwd_tc(x, w, bias, addend, y, s, (cudaStream_t)stream);
+    int r = launch_conv_fwd_tc(x, w, bias, addend, y, s, st);
     if (r) return fail(r, "tcgen05 conv launch failed");
+  } else if (backend == SIVAE_CONV_AUTO) {
+    sivae_engine tmp; tmp.tc = tmp.fast = true;
+    TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st));
   } else {
-    launch_conv_fwd_simt(x, w, bias, addend, y, s, (cudaStream_t)stream);
+    launch_conv_fwd_simt(x, w, bias, addend, y, s, st);
   }
   CHECK_CUDA_RET();
   return 0;
@@ -859,12 +902,16 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
   if (!workspace || (size_t)ws_bytes < need) return fail(-3, "workspace too small for the packed dgrad filter");
   cudaStream_t st = (cudaStream_t)stream;
   float* wd = (float*)workspace;
-  launch_pack_dgrad_filter(w, wd, Cout, Cin, k, backend == SIVAE_CONV_TCGEN05, st);
   ConvShape s{N, H, W, Cout, Cin, k};
+  sivae_engine tmp; tmp.tc = tmp.fast = (backend == SIVAE_CONV_AUTO);
+  const bool on_tc = backend == SIVAE_CONV_TCGEN05 || (backend == SIVAE_CONV_AUTO && !fwd_on_narrow(&tmp, s) && fwd_on_tc(&tmp, s));
+  launch_pack_dgrad_filter(w, wd, Cout, Cin, k, on_tc, st);
   if (backend == SIVAE_CONV_TCGEN05) {
     if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
     int r = launch_conv_fwd_tc(dy, wd, nullptr, addend, dx, s, st);
     if (r) return fail(r, "tcgen05 conv launch failed");
+  } else if (backend == SIVAE_CONV_AUTO) {
+    TRY(conv_any(&tmp, s, dy, wd, wd, nullptr, addend, dx, st));
   } else {
     launch_conv_fwd_simt(dy, wd, nullptr, addend, dx, s, st);
   }
@@ -875,14 +922,21 @@ extern "C" int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, in
                                   int accumulate, int backend, void* workspace, long long ws_bytes, void* stream) {
   ConvShape s{N, H, W, Cin, Cout, k};
   cudaStream_t st = (cudaStream_t)stream;
-  if (backend == SIVAE_CONV_TCGEN05) {
+  const bool acc = accumulate != 0;
+  if (backend == SIVAE_CONV_AUTO && Cin <= 4 && conv_narrow_corr_supported(Cout, Cin, k)) {
+    if ((size_t)ws_bytes < conv_narrow_corr_scratch_bytes(Cout, k)) return fail(-3, "workspace too small");
+    launch_conv_narrow_corr(x, dy, dw, N, H, W, Cin, Cout, k, 1, acc, workspace, (size_t)ws_bytes, st);
+  } else if (backend == SIVAE_CONV_AUTO && Cout <= 4 && conv_narrow_corr_supported(Cin, Cout, k)) {
+    if ((size_t)ws_bytes < conv_narrow_corr_scratch_bytes(Cin, k)) return fail(-3, "workspace too small");
+    launch_conv_narrow_corr(dy, x, dw, N, H, W, Cout, Cin, k, 0, acc, workspace, (size_t)ws_bytes, st);
+  } else if (backend == SIVAE_CONV_TCGEN05 || (backend == SIVAE_CONV_AUTO && conv_tc_supported_wgrad(s))) {
     if (!conv_tc_supported_wgrad(s)) return fail(-7, "shape not supported by the tcgen05 wgrad kernel");
     if ((size_t)ws_bytes < conv_wgrad_tc_scratch_bytes(s)) return fail(-3, "workspace too small");
-    int r = launch_conv_wgrad_tc(x, dy, dw, s, accumulate != 0, workspace, (size_t)ws_bytes, st);
+    int r = launch_conv_wgrad_tc(x, dy, dw, s, acc, workspace, (size_t)ws_bytes, st);
     if (r) return fail(r, "tcgen05 wgrad launch failed");
   } else {
     if ((size_t)ws_bytes < conv_wgrad_simt_scratch_bytes(s)) return fail(-3, "workspace too small");
-    launch_conv_wgrad_simt(x, dy, dw, s, accumulate != 0, workspace, (size_t)ws_bytes, st);
+    launch_conv_wgrad_simt(x, dy, dw, s, acc, workspace, (size_t)ws_bytes, st);
   }
   CHECK_CUDA_RET();
   return 0;
@@ -924,7 +978,13 @@ extern "C" int sivae_kl_reparam(const float* mu_logvar, const float* eps, float*
 }
 extern "C" int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
                                long long step, void* stream) {
-  launch_adam(p, g, m, v, n, lr, grad_scale, 0.9f, 0.999f, 1e-8f, step, (cudaStream_t)stream);
+  static long long* sdev = nullptr;
+  static float* cdev = nullptr;
+  if (!sdev) { cudaMalloc(&sdev, 16); cudaMalloc(&cdev, 16); }     // 32 bytes of library-owned scratch for this test entry point
+  long long prev = step - 1;
+  cudaMemcpyAsync(sdev, &prev, sizeof(long long), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  launch_adam(p, g, m, v, n, lr, grad_scale, 0.9f, 0.999f, 1e-8f, sdev, cdev, (cudaStream_t)stream);
   CHECK_CUDA_RET();
   return 0;
 }

@@ -338,38 +338,72 @@ void launch_conv_wgrad_simt(const float* x, const float* dy, float* dw, const Co
   k_splitk_reduce<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(part, dw, n, splits, accumulate ? 1 : 0);
 }
 
-__global__ void k_colsum(const float* __restrict__ in, float* __restrict__ out, long long rows, int C, int accumulate) {
-  // one block per channel; generic (C may be 3)
-  int c = blockIdx.x;
-  double s = 0.0;
-  for (long long r = threadIdx.x; r < rows; r += blockDim.x) s += (double)in[r * C + c];
-  __shared__ double sh[256];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
+// out[c] (+)= sum_rows in[row][c] for a small channel count (predict bias gradient, C = cdim <= 8): two-stage,
+// fixed-order (deterministic).  scratch: COLSUM_BLOCKS * C floats.
+constexpr int COLSUM_BLOCKS = 148 * 2;
+__global__ void __launch_bounds__(256) k_colsum_partial(const float* __restrict__ in, float* __restrict__ part, long long rows, int C) {
+  __shared__ float sh[8][8];
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = min(rows, r0 + per);
+  for (long long r = r0 + threadIdx.x; r < r1; r += 256)
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) acc[c] += in[r * C + c];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[wid][c] = v;
   }
-  if (threadIdx.x == 0) out[c] = accumulate ? out[c] + (float)sh[0] : (float)sh[0];
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sh[k][threadIdx.x];
+    part[(size_t)blockIdx.x * C + threadIdx.x] = v;
+  }
 }
-void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, cudaStream_t st) {
-  g_launches += 1;
-  k_colsum<<<C, 256, 0, st>>>(in, out, rows, C, accumulate ? 1 : 0);
+__global__ void k_colsum_final(const float* __restrict__ part, float* __restrict__ out, int nblk, int C, int accumulate) {
+  int c = threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)part[(size_t)b * C + c];
+  out[c] = accumulate ? out[c] + (float)s : (float)s;
+}
+size_t colsum_scratch_bytes(int C) { return (size_t)COLSUM_BLOCKS * C * sizeof(float); }
+void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, void* scratch, cudaStream_t st) {
+  g_launches += 2;
+  int nblk = (int)min((long long)COLSUM_BLOCKS, (rows + 255) / 256);
+  if (nblk < 1) nblk = 1;
+  k_colsum_partial<<<nblk, 256, 0, st>>>(in, (float*)scratch, rows, C);
+  k_colsum_final<<<1, 32, 0, st>>>((const float*)scratch, out, nblk, C, accumulate ? 1 : 0);
 }
 
 // =====================================================================================================
 // BatchNorm2d in train mode (:58,62,90; eps 1e-5, momentum 0.1): batch statistics over N*H*W
 // =====================================================================================================
-constexpr int BN_ROWS_PER_BLOCK = 1024;
-static int bn_nblocks(long long rows) { return (int)cdiv(rows, BN_ROWS_PER_BLOCK); }
+// rows handled by one block of the per-channel reductions: sized so that the grid is ~4 waves of 148 SMs even for the
+// low-resolution layers (a fixed 1024 rows/block left the 4x4..16x16 layers on 1..8 SMs)
+constexpr int BN_MAX_BLOCKS = 148 * 4;
+static int bn_rows_per_block(long long rows) {
+  long long r = (rows + BN_MAX_BLOCKS - 1) / BN_MAX_BLOCKS;
+  if (r < 16) r = 16;
+  return (int)((r + 15) / 16 * 16);
+}
+static int bn_nblocks(long long rows) { return (int)cdiv(rows, bn_rows_per_block(rows)); }
 size_t bn_scratch_bytes(long long rows, int C) {
   // partial sums: [nblk][2][C] floats, plus 2*C floats of finalized sums for the backward
   return ((size_t)bn_nblocks(rows) * 2 * C + 2 * (size_t)C) * sizeof(float);
 }
 
-// each block: BN_ROWS_PER_BLOCK rows; threads: cvec = C/4 lanes over channels x (256/cvec) row lanes
+// each block: rpb rows; threads: cvec = C/4 lanes over channels x (256/cvec) row lanes
 __global__ void __launch_bounds__(256) k_bn_stats_partial(const float* __restrict__ t, long long rows, int C,
-                                                          float* __restrict__ part) {
+                                                          float* __restrict__ part, int rpb) {
   extern __shared__ float sh[];   // [rl][2][C]
   const int cvec = C >> 2;
   const int rl_n = 256 / cvec;
@@ -377,8 +411,8 @@ __global__ void __launch_bounds__(256) k_bn_stats_partial(const float* __restric
   const int rl = threadIdx.x / cvec;
   float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
   if (rl < rl_n) {
-    long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK;
-    long long r1 = min(rows, r0 + BN_ROWS_PER_BLOCK);
+    long long r0 = (long long)blockIdx.x * rpb;
+    long long r1 = min(rows, r0 + rpb);
     for (long long r = r0 + rl; r < r1; r += rl_n) {
       float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + cl);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -395,17 +429,25 @@ __global__ void __launch_bounds__(256) k_bn_stats_partial(const float* __restric
     part[(size_t)blockIdx.x * 2 * C + i] = a;
   }
 }
+// one warp per channel: lanes stride over the per-block partials (fp64), shuffle-reduce, lane 0 finalises
 __global__ void k_bn_stats_finalize(const float* __restrict__ part, int nblk, long long rows, int C,
                                     float* __restrict__ mean_invstd, float* running_mean, float* running_var,
                                     long long* nbt) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) *nbt += 1;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c == 0 && lane == 0 && nbt) *nbt += 1;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     s += (double)part[(size_t)b * 2 * C + c];
     q += (double)part[(size_t)b * 2 * C + C + c];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane != 0) return;
   double mean = s / (double)rows;
   double var = q / (double)rows - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -425,8 +467,8 @@ void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, 
   int cvec = C / 4;
   int rl_n = 256 / cvec;
   size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
-  k_bn_stats_partial<<<nblk, 256, shmem, st>>>(t, rows, C, part);
-  k_bn_stats_finalize<<<cdiv(C, 128), 128, 0, st>>>(part, nblk, rows, C, mean_invstd, running_mean, running_var, nbt);
+  k_bn_stats_partial<<<nblk, 256, shmem, st>>>(t, rows, C, part, bn_rows_per_block(rows));
+  k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, mean_invstd, running_mean, running_var, nbt);
 }
 __global__ void k_bn_eval_stats(const float* rm, const float* rv, int C, float* mi) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,16 +486,21 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
                                                     const float* __restrict__ mi, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float* __restrict__ out, int N,
                                                     int H, int W, int C) {
-  const int cvec = C >> 2;
-  const int Ho = MODE == RS_POOL ? H / 2 : H, Wo = MODE == RS_POOL ? W / 2 : W;
-  const long long total = (long long)N * Ho * Wo * cvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % cvec);
-    long long p = i / cvec;
-    int w = (int)(p % Wo);
-    long long q = p / Wo;
-    int h = (int)(q % Ho);
-    int n = (int)(q / Ho);
+  // 32-bit index arithmetic (tensor sizes are < 2^31 float4s; checked by the launcher): 64-bit div/mod per element
+  // would make this HBM-bound kernel instruction-bound
+  const unsigned cvec = (unsigned)C >> 2;
+  const unsigned Ho = MODE == RS_POOL ? H / 2 : H, Wo = MODE == RS_POOL ? W / 2 : W;
+  const unsigned total = (unsigned)N * Ho * Wo * cvec;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % cvec;
+    const unsigned p = i / cvec;
+    unsigned w = 0, h = 0, n = 0;
+    if (MODE != RS_NONE) {
+      w = p % Wo;
+      const unsigned q = p / Wo;
+      h = q % Ho;
+      n = q / Ho;
+    }
     float4 mean = __ldg(reinterpret_cast<const float4*>(mi) + c4);
     float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + c4);
     float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
@@ -470,7 +517,7 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
       return make_float4(lrelu(y.x), lrelu(y.y), lrelu(y.z), lrelu(y.w));
     };
     if (MODE == RS_NONE) {
-      long long pix = ((long long)n * H + h) * W + w;
+      long long pix = p;
       float4 y = eval(pix);
       if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
       reinterpret_cast<float4*>(out + pix * C)[c4] = y;
@@ -511,9 +558,9 @@ void launch_bn_act_fwd(const float* t, const float* identity, const float* mi, c
 // ---- backward -----------------------------------------------------------------------------------------
 // upstream gradient at full resolution pixel (n,h,w): NONE: dout; POOL: dout[n,h/2,w/2]/4; UP: sum of the 4 children
 template <int MODE>
-__device__ __forceinline__ float4 upstream(const float* __restrict__ dout, int n, int h, int w, int H, int W, int C, int c4) {
+__device__ __forceinline__ float4 upstream(const float* __restrict__ dout, long long row, int n, int h, int w, int H, int W, int C, int c4) {
   if (MODE == RS_NONE) {
-    return __ldg(reinterpret_cast<const float4*>(dout + (((long long)n * H + h) * W + w) * C) + c4);
+    return __ldg(reinterpret_cast<const float4*>(dout + row * C) + c4);
   } else if (MODE == RS_POOL) {
     float4 v = __ldg(reinterpret_cast<const float4*>(dout + (((long long)n * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C) + c4);
     return make_float4(v.x * 0.25f, v.y * 0.25f, v.z * 0.25f, v.w * 0.25f);
@@ -532,7 +579,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ dout, const float* __restrict__ t,
                                                        const float* __restrict__ idn, const float* __restrict__ mi,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       int N, int H, int W, int C, float* __restrict__ part) {
+                                                       int N, int H, int W, int C, float* __restrict__ part, int rpb) {
   extern __shared__ float sh[];
   const int cvec = C >> 2;
   const int rl_n = 256 / cvec;
@@ -545,14 +592,18 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
     float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + cl);
     float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cl);
     float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cl);
-    long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK;
-    long long r1 = min(rows, r0 + BN_ROWS_PER_BLOCK);
+    long long r0 = (long long)blockIdx.x * rpb;
+    long long r1 = min(rows, r0 + rpb);
     for (long long r = r0 + rl; r < r1; r += rl_n) {
-      int w = (int)(r % W);
-      long long q = r / W;
-      int h = (int)(q % H);
-      int n = (int)(q / H);
-      float4 d = upstream<MODE>(dout, n, h, w, H, W, C, cl);
+      int w = 0, h = 0, n = 0;
+      if (MODE != RS_NONE) {
+        const unsigned ru = (unsigned)r;
+        w = (int)(ru % (unsigned)W);
+        const unsigned q = ru / (unsigned)W;
+        h = (int)(q % (unsigned)H);
+        n = (int)(q / (unsigned)H);
+      }
+      float4 d = upstream<MODE>(dout, r, n, h, w, H, W, C, cl);
       float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + cl);
       float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
       float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
@@ -577,13 +628,20 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
 }
 __global__ void k_bn_bwd_finalize(const float* __restrict__ part, int nblk, long long rows, int C,
                                   float* __restrict__ sums, float* dgamma, float* dbeta, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     s += (double)part[(size_t)b * 2 * C + c];
     q += (double)part[(size_t)b * 2 * C + C + c];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane != 0) return;
   sums[c] = (float)(s / (double)rows);       // mean of g
   sums[C + c] = (float)(q / (double)rows);   // mean of g * xhat
   if (dgamma) {
@@ -597,22 +655,25 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ sums, float* __restrict__ dt,
                                                       float* __restrict__ gout, int N, int H, int W, int C) {
-  const int cvec = C >> 2;
-  const long long total = (long long)N * H * W * cvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % cvec);
-    long long r = i / cvec;
-    int w = (int)(r % W);
-    long long q = r / W;
-    int h = (int)(q % H);
-    int n = (int)(q / H);
+  const unsigned cvec = (unsigned)C >> 2;
+  const unsigned total = (unsigned)N * H * W * cvec;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % cvec);
+    const unsigned r = i / cvec;
+    int w = 0, h = 0, n = 0;
+    if (MODE != RS_NONE) {
+      w = (int)(r % (unsigned)W);
+      const unsigned q = r / (unsigned)W;
+      h = (int)(q % (unsigned)H);
+      n = (int)(q / (unsigned)H);
+    }
     float4 mean = __ldg(reinterpret_cast<const float4*>(mi) + c4);
     float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + c4);
     float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
     float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
     float4 mg = __ldg(reinterpret_cast<const float4*>(sums) + c4);
     float4 mx = __ldg(reinterpret_cast<const float4*>(sums + C) + c4);
-    float4 d = upstream<MODE>(dout, n, h, w, H, W, C, c4);
+    float4 d = upstream<MODE>(dout, (long long)r, n, h, w, H, W, C, c4);
     float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + c4);
     float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
     float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
@@ -643,14 +704,15 @@ void launch_bn_act_bwd(const float* dout, const float* t, const float* identity,
   long long rows = (long long)N * H * W;
   if (rows == 0) return;
   int nblk = bn_nblocks(rows);
+  const int rpb = bn_rows_per_block(rows);
   float* part = (float*)scratch;
   float* sums = part + (size_t)nblk * 2 * C;
   int cvec = C / 4, rl_n = 256 / cvec;
   size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
-  if (mode == RS_NONE) k_bn_bwd_reduce<RS_NONE><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part);
-  else if (mode == RS_POOL) k_bn_bwd_reduce<RS_POOL><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part);
-  else k_bn_bwd_reduce<RS_UP><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part);
-  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, st>>>(part, nblk, rows, C, sums, dgamma, dbeta, accumulate ? 1 : 0);
+  if (mode == RS_NONE) k_bn_bwd_reduce<RS_NONE><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb);
+  else if (mode == RS_POOL) k_bn_bwd_reduce<RS_POOL><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb);
+  else k_bn_bwd_reduce<RS_UP><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb);
+  k_bn_bwd_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, sums, dgamma, dbeta, accumulate ? 1 : 0);
   long long total = rows * cvec;
   unsigned grid = min(cdiv(total, 256), 148u * 32);
 #define LAUNCH(M, R) k_bn_bwd_apply<M, R><<<grid, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, sums, dt, g, N, H, W, C)
@@ -713,41 +775,49 @@ void launch_linear_fwd(const float* x, const float* w, const float* b, float* y,
   dim3 grid(cdiv(O, LF_OT), cdiv(B, LF_BT));
   k_linear_fwd<<<grid, 256, 0, st>>>(x, w, b, y, B, F, O, relu ? 1 : 0);
 }
-constexpr int LD_BT = 8, LD_OC = 1024;
+constexpr int LD_BT = 8, LD_OC = 512;
+// dx[B][F] = dy[B][O] . w[O][F]; O is split over blockIdx.z in chunks of LD_OC (partials in scratch, reduced in fixed order)
 __global__ void __launch_bounds__(256) k_linear_dgrad(const float* __restrict__ dy, const float* __restrict__ w,
-                                                      float* __restrict__ dx, int B, int F, int O) {
-  __shared__ float sdy[LD_BT][LD_OC];   // dy chunk, broadcast to all f
+                                                      float* __restrict__ part, int B, int F, int O) {
+  __shared__ float sdy[LD_BT][LD_OC];
   const int b0 = blockIdx.y * LD_BT;
   const int f = blockIdx.x * 256 + threadIdx.x;
+  const int o0 = blockIdx.z * LD_OC;
+  const int oc = min(LD_OC, O - o0);
+  for (int i = threadIdx.x; i < LD_BT * oc; i += 256) {
+    int j = i / oc, o = i - j * oc;
+    sdy[j][o] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o0 + o] : 0.f;
+  }
+  __syncthreads();
+  if (f >= F) return;
   float acc[LD_BT];
 #pragma unroll
   for (int j = 0; j < LD_BT; ++j) acc[j] = 0.f;
-  for (int o0 = 0; o0 < O; o0 += LD_OC) {
-    const int oc = min(LD_OC, O - o0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < LD_BT * oc; i += 256) {
-      int j = i / oc, o = i - j * oc;
-      sdy[j][o] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o0 + o] : 0.f;
-    }
-    __syncthreads();
-    if (f < F) {
-      for (int o = 0; o < oc; ++o) {
-        float wv = __ldg(w + (long long)(o0 + o) * F + f);
+  for (int o = 0; o < oc; ++o) {
+    float wv = __ldg(w + (long long)(o0 + o) * F + f);
 #pragma unroll
-        for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[j][o], wv, acc[j]);
-      }
-    }
+    for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[j][o], wv, acc[j]);
   }
-  if (f < F) {
+  float* dst = part + (long long)blockIdx.z * B * F;
 #pragma unroll
-    for (int j = 0; j < LD_BT; ++j)
-      if (b0 + j < B) dx[(long long)(b0 + j) * F + f] = acc[j];
+  for (int j = 0; j < LD_BT; ++j)
+    if (b0 + j < B) dst[(long long)(b0 + j) * F + f] = acc[j];
+}
+__global__ void k_linear_dgrad_reduce(const float* __restrict__ part, float* __restrict__ dx, long long n, int splits) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long long)z * n + i];
+    dx[i] = s;
   }
 }
-void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, cudaStream_t st) {
-  g_launches += 1;
-  dim3 grid(cdiv(F, 256), cdiv(B, LD_BT));
-  k_linear_dgrad<<<grid, 256, 0, st>>>(dy, w, dx, B, F, O);
+size_t linear_dgrad_scratch_bytes(int B, int F, int O) { return (size_t)cdiv(O, LD_OC) * B * F * sizeof(float); }
+void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, void* scratch, cudaStream_t st) {
+  g_launches += 2;
+  const int splits = (int)cdiv(O, LD_OC);
+  dim3 grid(cdiv(F, 256), cdiv(B, LD_BT), splits);
+  k_linear_dgrad<<<grid, 256, 0, st>>>(dy, w, (float*)scratch, B, F, O);
+  long long n = (long long)B * F;
+  k_linear_dgrad_reduce<<<min(cdiv(n, 256), 148u * 4), 256, 0, st>>>((const float*)scratch, dx, n, splits);
 }
 constexpr int LW_OT = 8;
 __global__ void __launch_bounds__(256) k_linear_wgrad(const float* __restrict__ x, const float* __restrict__ dy,
@@ -1053,9 +1123,20 @@ void launch_loss_seed(const float* real, const float* rec, const float* rec_rec,
 // =====================================================================================================
 // torch.optim.Adam (:450-451): betas (.9,.999), eps 1e-8, bias-corrected, no weight decay -- flat buffers
 // =====================================================================================================
+// coef[0] = lr / (1 - b1^step), coef[1] = sqrt(1 - b2^step); the step counter lives on the device so that a captured
+// CUDA graph of the iteration replays with the correct bias correction
+__global__ void k_adam_prep(long long* step, float lr, float b1, float b2, float* coef) {
+  long long t = *step + 1;
+  *step = t;
+  double bc1 = 1.0 - pow((double)b1, (double)t);
+  double bc2 = 1.0 - pow((double)b2, (double)t);
+  coef[0] = (float)((double)lr / bc1);
+  coef[1] = (float)sqrt(bc2);
+}
 __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                              float* __restrict__ v, long long n, float step_size, float grad_scale,
-                                              float b1, float b2, float eps, float sqrt_bc2) {
+                                              float* __restrict__ v, long long n, const float* __restrict__ coef,
+                                              float grad_scale, float b1, float b2, float eps) {
+  const float step_size = coef[0], sqrt_bc2 = coef[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
     float mi = m[i] + (gi - m[i]) * (1.f - b1);            // exp_avg.lerp_(grad, 1-beta1)
@@ -1065,15 +1146,13 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     p[i] = p[i] - step_size * (mi / denom);
   }
 }
+// step_dev: device int64 counter (incremented here); coef_dev: 2 floats of device scratch
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale, float b1,
-                 float b2, float eps, long long step, cudaStream_t st) {
-  g_launches += 1;
+                 float b2, float eps, long long* step_dev, float* coef_dev, cudaStream_t st) {
+  g_launches += 2;
   if (n <= 0) return;
-  double bc1 = 1.0 - pow((double)b1, (double)step);
-  double bc2 = 1.0 - pow((double)b2, (double)step);
-  float step_size = (float)((double)lr / bc1);
-  float sqrt_bc2 = (float)sqrt(bc2);
-  k_adam<<<min(cdiv(n, 256), 148u * 16), 256, 0, st>>>(p, g, m, v, n, step_size, grad_scale, b1, b2, eps, sqrt_bc2);
+  k_adam_prep<<<1, 1, 0, st>>>(step_dev, lr, b1, b2, coef_dev);
+  k_adam<<<min(cdiv(n, 256), 148u * 16), 256, 0, st>>>(p, g, m, v, n, coef_dev, grad_scale, b1, b2, eps);
 }
 
 }  // namespace sivae

@@ -38,7 +38,18 @@ size_t conv_wgrad_simt_scratch_bytes(const ConvShape& s);
 void launch_conv_wgrad_simt(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
                             void* scratch, size_t scratch_bytes, cudaStream_t st);
 // out[c] (+)= sum_rows in[row][c]
-void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, cudaStream_t st);
+size_t colsum_scratch_bytes(int C);
+void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, void* scratch, cudaStream_t st);
+
+// ---------------- cdim-facing 5x5 convolutions on CUDA cores (conv_narrow.cu) ----------------
+bool conv_narrow_in_supported(const ConvShape& s);            // Cin <= 4: stem forward, predict dgrad
+void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,
+                               const ConvShape& s, cudaStream_t st);
+bool conv_narrow_corr_supported(int wideC, int narrowA, int k);
+size_t conv_narrow_corr_scratch_bytes(int wideC, int k);
+// mode 0: dw[a][tap][c] (predict wgrad: nar = dy, wide = x); mode 1: dw[c][tap][a] (stem wgrad: nar = x, wide = dy)
+void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int N, int H, int W, int A, int C, int k, int mode,
+                             bool accumulate, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 // ---------------- tcgen05 TF32 implicit-GEMM convolution (conv_tc.cu) ----------------
 bool conv_tc_supported_fwd(const ConvShape& s);
@@ -72,7 +83,8 @@ void launch_bn_act_bwd(const float* dout, const float* t, const float* identity,
 void launch_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, bool relu,
                        cudaStream_t st);
 // dx[B][F] = dy[B][O] . w[O][F]
-void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, cudaStream_t st);
+size_t linear_dgrad_scratch_bytes(int B, int F, int O);
+void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, void* scratch, cudaStream_t st);
 // dw[O][F] (+)= dy^T . x ; db[O] (+)= sum_b dy
 void launch_linear_wgrad(const float* x, const float* dy, float* dw, float* db, int B, int F, int O, bool accumulate,
                          cudaStream_t st);
@@ -113,6 +125,6 @@ void launch_loss_seed(const float* real, const float* rec, const float* rec_rec,
 
 // ---------------- optimiser ----------------
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
-                 float b1, float b2, float eps, long long step, cudaStream_t st);
+                 float b1, float b2, float eps, long long* step_dev, float* coef_dev, cudaStream_t st);
 
 }  // namespace sivae

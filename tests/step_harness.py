@@ -97,10 +97,11 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def compare(eng, ora, tol, label="", lr=2e-4, verbose=True):
+def compare(eng, ora, tol, label="", lr=2e-4, verbose=True, tensor_tol=None):
     """tol: relative tolerance for scalars; tensors (gradients, BN statistics) get 10*tol as relative-L2 / max-rel.
     All deviations are measured first (and appended to gpurun_out/parity_report.jsonl), then asserted."""
     import json
+    ttol = 10 * tol if tensor_tol is None else tensor_tol
     dev, fails = {}, []
     es, os_ = eng["scalars"], ora["scalars"]
     if es.get("nan", 0.0) != 0.0:
@@ -120,8 +121,8 @@ def compare(eng, ora, tol, label="", lr=2e-4, verbose=True):
         for k in ora[name]:
             r = rel_l2(eng[name][k], ora[name][k])
             dev[name + ":" + k] = r
-            if not r < 10 * tol:
-                fails.append("%s[%s] rel-L2 %.3g > %.3g" % (name, k, r, 10 * tol))
+            if not r < ttol:
+                fails.append("%s[%s] rel-L2 %.3g > %.3g" % (name, k, r, ttol))
     for k, v in ora["post"].items():
         e = eng["post"][k]
         if k.endswith("num_batches_tracked"):
@@ -130,7 +131,7 @@ def compare(eng, ora, tol, label="", lr=2e-4, verbose=True):
         elif k.endswith(("running_mean", "running_var")):
             r = float((e.double() - v.double()).abs().max() / (v.double().abs().max() + 1e-12))
             dev["bn:" + k] = r
-            if not r < 10 * tol:
+            if not r < ttol:
                 fails.append("%s max-rel %.3g" % (k, r))
         else:
             # one Adam step from zero moments moves each weight by ~lr*sign(g): bounded check here, the Adam kernel
