@@ -176,6 +176,18 @@ def run_ours(args):
     launches0 = lib.sivae_launch_count()
     lib.sivae_profile_enable(1)
     ms_total = timed(step_resident, args.steps)
+    if args.layers and rank == 0:
+        buf = C.create_string_buffer(1 << 16)
+        lib.sivae_profile_dump(buf, len(buf))
+        names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad"}
+        rows = [l.split() for l in buf.value.decode().splitlines()]
+        rows.sort(key=lambda r: -float(r[8]))
+        with open(args.layers, "w") as f:
+            f.write("| class | N | H | W | Cin | Cout | k | launches/step | ms/step | ms/launch | TFLOP/s |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+            for r in rows:
+                n, ms, gf = int(r[7]), float(r[8]), float(r[9])
+                f.write("| %s | %s | %s | %s | %s | %s | %s | %.1f | %.3f | %.4f | %.1f |\n" % (
+                    names[int(r[0])], r[1], r[2], r[3], r[4], r[5], r[6], n / args.steps, ms / args.steps, ms / n, gf / ms if ms > 0 else 0))
     prof = (C.c_double * 12)()
     lib.sivae_profile_read(prof)
     lib.sivae_profile_enable(0)
@@ -247,8 +259,9 @@ def cpu_baseline(cfg_name, budget_s=25.0, steps=1, warmup=0):
     torch.set_num_threads(cores)
     # sample size: the torch CPU path sustains only ~20-50 GFLOP/s on this step regardless of core count (measured:
     # 62.9 s for 1.25 TFLOP on 128 threads) -> images that fit the budget, at least 2 (train-mode BN needs > 1)
-    est_rate = 30e9
-    b = int(max(2, min(batch, budget_s * est_rate / (gflop_img * 1e9))))
+    # and only ~9 GFLOP/s at 256x256 with a batch of 2 (measured 189.8 s / iteration) -> one image there
+    est_rate = 30e9 if size <= 64 else 9e9
+    b = int(max(1 if size > 64 else 2, min(batch, budget_s * est_rate / (gflop_img * 1e9))))
     arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
     sd = O.make_state_dict(arch, seed=0, bootstrap=boot)
     g = torch.Generator().manual_seed(1234)
@@ -277,10 +290,10 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     t0 = time.time()
     # bounded: every step is one iteration on a small batch; cap the number of steps to stay within minutes
-    steps = max(1, min(args.steps, 3))
-    cb = cpu_baseline(args.config, budget_s=args.cpu_budget, steps=steps, warmup=1 if args.warmup > 0 else 0)
+    steps = max(1, min(args.steps, 3)) if size <= 64 else 1
+    cb = cpu_baseline(args.config, budget_s=args.cpu_budget, steps=steps, warmup=1 if (args.warmup > 0 and size <= 64) else 0)
     line = dict(impl="reference", metric="images/sec per introspective E+D step", value=cb["value"], unit="images/s",
-                n_gpus=world, steps=steps, warmup=1 if args.warmup > 0 else 0, ms_per_step=None, higher_is_better=True,
+                n_gpus=world, steps=steps, warmup=1 if (args.warmup > 0 and size <= 64) else 0, ms_per_step=None, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
                 config=dict(workload=WORKLOAD_NAMES[args.config], image_size=size, z_dim=zdim, channels=channels,
                             batch_per_gpu=batch, note="CPU path: bounded sample, see cpu_baseline.sample"),
@@ -299,6 +312,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
+    ap.add_argument("--layers", default="", help="write the per-conv-shape timing table (CUDA events) to this file")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -119,6 +119,8 @@ int sivae_last_batch(const sivae_engine* e);
 unsigned long long sivae_launch_count(void);
 int sivae_profile_enable(int on);
 int sivae_profile_read(double* out);
+/* text table "class N H W Cin Cout k launches ms gflop" per distinct conv shape; call before sivae_profile_read */
+int sivae_profile_dump(char* buf, int len);
 
 /* ---- single-kernel entry points (unit parity tests; NHWC activations, [Cout][kh][kw][Cin] filters) ---- */
 /* nn.Conv2d(k, stride 1, pad k/2) forward (:51,56,60,89,159); bias/addend may be NULL; y = conv + bias + addend */

@@ -4,6 +4,10 @@
 //   k_narrow_corr     G[tap][a][c] = sum_p nar[p][a] * wide[p+tap][c]             stem wgrad, predict wgrad
 // (the wide->narrow direction, predict forward / stem dgrad, runs on the tcgen05 kernel with a masked epilogue.)
 // Both are FMA-bound direct convolutions with the halo tile staged in shared memory; exact fp32 (no tf32 rounding).
+// The inner loops are arranged for a high FMA : shared-load ratio (the first versions were LSU-bound at 19-30 % of the
+// fp32 peak, profiles/r01a_launches_H.md): forward = 2 pixels x 32 output channels per thread and 128-bit broadcast
+// filter loads (64 FMA per 10 LDS); correlation = one filter row per thread with a 5-wide sliding register window
+// (15 FMA per 2 LDS).
 #include "kernels.h"
 
 namespace sivae {
@@ -11,75 +15,81 @@ namespace sivae {
 static inline unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// narrow-in forward: one thread = one output pixel x all Cout channels (COUT_T <= 64 per pass)
+// narrow-in forward.  Block = 16 rows x 32 cols of output pixels, 256 threads, thread = pixels (ty, tx) and (ty, tx+16)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NI_T = 16;   // 16x16 pixel tile
+constexpr int NI_TH = 16, NI_TW = 32;
 template <int KS>
 __global__ void __launch_bounds__(256) k_narrow_in_fwd(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* addend, float* y, int N,
                                                        int H, int W, int A, int Cout) {
   extern __shared__ float sm[];
-  constexpr int HT = NI_T + KS - 1;
-  float* sx = sm;                              // [HT][HT][A]
-  float* sw = sm + HT * HT * 4;                // [tap][a][Cout]  (transposed so that 4 consecutive co are one LDS.128)
-  const int tiles_w = (W + NI_T - 1) / NI_T, tiles_h = (H + NI_T - 1) / NI_T;
+  constexpr int HTH = NI_TH + KS - 1, HTW = NI_TW + KS - 1;
+  float* sx = sm;                                   // [HTH][HTW][A]
+  float* sw = sm + ((HTH * HTW * 4 + 3) & ~3);      // [tap][a][Cout]: 4 consecutive co = one LDS.128
+  const int tiles_w = (W + NI_TW - 1) / NI_TW, tiles_h = (H + NI_TH - 1) / NI_TH;
   const int tile = blockIdx.x;
   const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
-  const int w0 = tw * NI_T, h0 = th * NI_T, pad = KS / 2;
-  const int taps = KS * KS;
+  const int w0 = tw * NI_TW, h0 = th * NI_TH, pad = KS / 2;
+  constexpr int taps = KS * KS;
   for (int i = threadIdx.x; i < Cout * taps * A; i += 256) {
     int a = i % A, t = (i / A) % taps, co = i / (A * taps);
     sw[(t * A + a) * Cout + co] = w[i];
   }
-  for (int i = threadIdx.x; i < HT * HT * A; i += 256) {
-    int a = i % A, cx = (i / A) % HT, cy = i / (A * HT);
+  for (int i = threadIdx.x; i < HTH * HTW * A; i += 256) {
+    int a = i % A, cx = (i / A) % HTW, cy = i / (A * HTW);
     int hh = h0 + cy - pad, ww = w0 + cx - pad;
     sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)n * H + hh) * W + ww) * A + a] : 0.f;
   }
   __syncthreads();
-  const int tx = threadIdx.x % NI_T, ty = threadIdx.x / NI_T;
-  const int ho = h0 + ty, wo = w0 + tx;
-  const bool valid = ho < H && wo < W;
-  const long long pix = ((long long)n * H + ho) * W + wo;
-  for (int c0 = 0; c0 < Cout; c0 += 64) {
-    const int cn = min(64, Cout - c0);          // multiple of 4
-    float acc[64];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int ho = h0 + ty;
+  const int wo[2] = {w0 + tx, w0 + tx + 16};
+  for (int c0 = 0; c0 < Cout; c0 += 32) {
+    const int cn = min(32, Cout - c0);          // multiple of 4
+    float acc[2][32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[p][j] = 0.f;
     for (int r = 0; r < KS; ++r)
       for (int s = 0; s < KS; ++s) {
-        const float* xp = sx + ((ty + r) * HT + tx + s) * A;
+        const float* xp0 = sx + ((ty + r) * HTW + tx + s) * A;
+        const float* xp1 = xp0 + 16 * A;
         const float* wp = sw + (r * KS + s) * A * Cout + c0;
         for (int a = 0; a < A; ++a) {
-          const float xv = xp[a];
+          const float x0 = xp0[a], x1 = xp1[a];
           const float4* w4 = reinterpret_cast<const float4*>(wp + a * Cout);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 8; ++j) {
             if (4 * j < cn) {
-              float4 q = w4[j];
-              acc[4 * j] = fmaf(xv, q.x, acc[4 * j]);
-              acc[4 * j + 1] = fmaf(xv, q.y, acc[4 * j + 1]);
-              acc[4 * j + 2] = fmaf(xv, q.z, acc[4 * j + 2]);
-              acc[4 * j + 3] = fmaf(xv, q.w, acc[4 * j + 3]);
+              const float4 q = w4[j];
+              acc[0][4 * j] = fmaf(x0, q.x, acc[0][4 * j]);         acc[1][4 * j] = fmaf(x1, q.x, acc[1][4 * j]);
+              acc[0][4 * j + 1] = fmaf(x0, q.y, acc[0][4 * j + 1]); acc[1][4 * j + 1] = fmaf(x1, q.y, acc[1][4 * j + 1]);
+              acc[0][4 * j + 2] = fmaf(x0, q.z, acc[0][4 * j + 2]); acc[1][4 * j + 2] = fmaf(x1, q.z, acc[1][4 * j + 2]);
+              acc[0][4 * j + 3] = fmaf(x0, q.w, acc[0][4 * j + 3]); acc[1][4 * j + 3] = fmaf(x1, q.w, acc[1][4 * j + 3]);
             }
           }
         }
       }
-    if (valid) {
-      float* dst = y + pix * Cout + c0;
-      const float* add = addend ? addend + pix * Cout + c0 : nullptr;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (4 * j < cn) {
-          float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          if (bias) {
-            o.x += bias[c0 + 4 * j]; o.y += bias[c0 + 4 * j + 1]; o.z += bias[c0 + 4 * j + 2]; o.w += bias[c0 + 4 * j + 3];
+    for (int p = 0; p < 2; ++p) {
+      if (ho < H && wo[p] < W) {
+        const long long pix = ((long long)n * H + ho) * W + wo[p];
+        float* dst = y + pix * Cout + c0;
+        const float* add = addend ? addend + pix * Cout + c0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (4 * j < cn) {
+            float4 o = make_float4(acc[p][4 * j], acc[p][4 * j + 1], acc[p][4 * j + 2], acc[p][4 * j + 3]);
+            if (bias) {
+              o.x += bias[c0 + 4 * j]; o.y += bias[c0 + 4 * j + 1]; o.z += bias[c0 + 4 * j + 2]; o.w += bias[c0 + 4 * j + 3];
+            }
+            if (add) {
+              float4 q = *reinterpret_cast<const float4*>(add + 4 * j);
+              o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            *reinterpret_cast<float4*>(dst + 4 * j) = o;
           }
-          if (add) {
-            float4 q = *reinterpret_cast<const float4*>(add + 4 * j);
-            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-          }
-          *reinterpret_cast<float4*>(dst + 4 * j) = o;
         }
       }
     }
@@ -92,9 +102,9 @@ bool conv_narrow_in_supported(const ConvShape& s) {
 void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,
                                const ConvShape& s, cudaStream_t st) {
   g_launches += 1;
-  const int HT = NI_T + s.k - 1;
-  size_t shmem = ((size_t)HT * HT * 4 + (size_t)s.Cout * s.k * s.k * s.Cin) * sizeof(float);
-  unsigned grid = (unsigned)(cdivu(s.W, NI_T) * cdivu(s.H, NI_T) * s.N);
+  const int HTH = NI_TH + s.k - 1, HTW = NI_TW + s.k - 1;
+  size_t shmem = ((size_t)((HTH * HTW * 4 + 3) & ~3) + (size_t)s.Cout * s.k * s.k * s.Cin) * sizeof(float);
+  unsigned grid = (unsigned)(cdivu(s.W, NI_TW) * cdivu(s.H, NI_TH) * s.N);
   if (s.k == 5) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_narrow_in_fwd<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
@@ -109,32 +119,32 @@ void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias
 // ---------------------------------------------------------------------------------------------------------------
 // narrow x wide correlation (wgrad of both image-facing layers)
 //   G[tap][a][c] = sum_{n,h,w} nar[n,h,w][a] * wide[n, h + r - pad, w + s - pad][c]
-// persistent blocks loop over pixel tiles of TR x 32; thread = (channel c, tap group); partial G per block, fixed-order
-// reduction (deterministic).
+// Persistent blocks loop over pixel tiles of TR x 32.  Thread = (wide channel c, filter row r): it owns the KS taps
+// (r, 0..KS-1) and walks along the image row with a KS-wide sliding window of wide[.][c] kept in registers, so each
+// step costs one new shared load + one broadcast load of the narrow pixel for KS*A FMAs.  Per-block partial G, reduced
+// in fixed order (deterministic).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int NC_TW = 32;
 template <int C, int KS>
 struct NarrowCorrCfg {
-  static constexpr int GROUPS = 256 / C;                          // tap groups
+  static constexpr int THREADS = C * KS;
   static constexpr int TAPS = KS * KS;
-  static constexpr int TPG = (TAPS + GROUPS - 1) / GROUPS;        // taps per group
   static constexpr int TR = (C <= 64) ? 8 : 4;                    // tile rows
   static constexpr int HTH = TR + KS - 1, HTW = NC_TW + KS - 1;
   static constexpr size_t SMEM = ((size_t)HTH * HTW * C + (size_t)TR * NC_TW * 4) * sizeof(float);
 };
 template <int C, int KS>
-__global__ void __launch_bounds__(256) k_narrow_corr(const float* __restrict__ nar, const float* __restrict__ wide,
-                                                     float* __restrict__ part, int N, int H, int W, int A) {
+__global__ void __launch_bounds__(C* KS) k_narrow_corr(const float* __restrict__ nar, const float* __restrict__ wide,
+                                                       float* __restrict__ part, int N, int H, int W, int A) {
   using CF = NarrowCorrCfg<C, KS>;
   extern __shared__ float sm[];
   float* swd = sm;                                  // [HTH][HTW][C]
   float* snr = sm + CF::HTH * CF::HTW * C;          // [TR][32][4]
-  const int c = threadIdx.x % C, grp = threadIdx.x / C;
-  const int t_begin = grp * CF::TPG;
+  const int c = threadIdx.x % C, r = threadIdx.x / C;
   const int pad = KS / 2;
-  float acc[CF::TPG][4];
+  float acc[KS][4];
 #pragma unroll
-  for (int i = 0; i < CF::TPG; ++i)
+  for (int i = 0; i < KS; ++i)
 #pragma unroll
     for (int a = 0; a < 4; ++a) acc[i][a] = 0.f;
   const int tiles_w = (W + NC_TW - 1) / NC_TW, tiles_h = (H + CF::TR - 1) / CF::TR;
@@ -143,46 +153,46 @@ __global__ void __launch_bounds__(256) k_narrow_corr(const float* __restrict__ n
     const int tw = (int)(tile % tiles_w), th = (int)((tile / tiles_w) % tiles_h), n = (int)(tile / ((long long)tiles_w * tiles_h));
     const int w0 = tw * NC_TW, h0 = th * CF::TR;
     __syncthreads();
-    for (int i = threadIdx.x; i < CF::HTH * CF::HTW * (C / 4); i += 256) {
+    for (int i = threadIdx.x; i < CF::HTH * CF::HTW * (C / 4); i += CF::THREADS) {
       int c4 = i % (C / 4), cx = (i / (C / 4)) % CF::HTW, cy = i / ((C / 4) * CF::HTW);
       int hh = h0 + cy - pad, ww = w0 + cx - pad;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(reinterpret_cast<const float4*>(wide + (((long long)n * H + hh) * W + ww) * C) + c4);
       reinterpret_cast<float4*>(swd)[i] = v;
     }
-    for (int i = threadIdx.x; i < CF::TR * NC_TW * 4; i += 256) {
+    for (int i = threadIdx.x; i < CF::TR * NC_TW * 4; i += CF::THREADS) {
       int a = i & 3, px = (i >> 2) % NC_TW, py = i / (4 * NC_TW);
       int hh = h0 + py, ww = w0 + px;
       snr[i] = (a < A && hh < H && ww < W) ? nar[(((long long)n * H + hh) * W + ww) * A + a] : 0.f;
     }
     __syncthreads();
-    for (int py = 0; py < CF::TR; ++py)
+    for (int py = 0; py < CF::TR; ++py) {
+      const float* wrow = swd + ((py + r) * CF::HTW) * C + c;       // wide[h0+py+r-pad][w0-pad ...][c]
+      float win[KS];
+#pragma unroll
+      for (int s = 0; s < KS - 1; ++s) win[s + 1] = wrow[s * C];    // preload: after the first shift win[0..KS-2] hold cols 0..KS-2
+#pragma unroll 4
       for (int px = 0; px < NC_TW; ++px) {
+#pragma unroll
+        for (int s = 0; s < KS - 1; ++s) win[s] = win[s + 1];
+        win[KS - 1] = wrow[(px + KS - 1) * C];
         const float4 nv = *reinterpret_cast<const float4*>(snr + (py * NC_TW + px) * 4);   // broadcast
 #pragma unroll
-        for (int i = 0; i < CF::TPG; ++i) {
-          const int t = t_begin + i;
-          if (t < CF::TAPS) {
-            const int r = t / KS, s = t - r * KS;
-            const float wv = swd[((py + r) * CF::HTW + px + s) * C + c];
-            acc[i][0] = fmaf(nv.x, wv, acc[i][0]);
-            acc[i][1] = fmaf(nv.y, wv, acc[i][1]);
-            acc[i][2] = fmaf(nv.z, wv, acc[i][2]);
-            acc[i][3] = fmaf(nv.w, wv, acc[i][3]);
-          }
+        for (int s = 0; s < KS; ++s) {
+          acc[s][0] = fmaf(nv.x, win[s], acc[s][0]);
+          acc[s][1] = fmaf(nv.y, win[s], acc[s][1]);
+          acc[s][2] = fmaf(nv.z, win[s], acc[s][2]);
+          acc[s][3] = fmaf(nv.w, win[s], acc[s][3]);
         }
       }
+    }
   }
   // part[block][tap][a(4)][C]
   float* dst = part + (long long)blockIdx.x * CF::TAPS * 4 * C;
 #pragma unroll
-  for (int i = 0; i < CF::TPG; ++i) {
-    const int t = t_begin + i;
-    if (t < CF::TAPS) {
+  for (int s = 0; s < KS; ++s)
 #pragma unroll
-      for (int a = 0; a < 4; ++a) dst[(t * 4 + a) * C + c] = acc[i][a];
-    }
-  }
+    for (int a = 0; a < 4; ++a) dst[((r * KS + s) * 4 + a) * C + c] = acc[s][a];
 }
 // mode 0 (predict wgrad): dw[a][tap][c]   = G[tap][a][c]             (nar = dy (A = Cout), wide = x)
 // mode 1 (stem wgrad):    dw[c][tap][a]   = G[mirror(tap)][a][c]     (nar = x  (A = Cin),  wide = dy)
@@ -197,7 +207,7 @@ __global__ void k_narrow_corr_reduce(const float* __restrict__ part, float* __re
   dw[o] = accumulate ? (float)((double)dw[o] + s) : (float)s;
 }
 
-static int narrow_corr_blocks() { return 148 * 2; }
+static int narrow_corr_blocks() { return 148; }      // 1 persistent block per SM (110-147 KB of shared memory each)
 bool conv_narrow_corr_supported(int wideC, int narrowA, int k) {
   return (wideC == 32 || wideC == 64 || wideC == 128) && narrowA >= 1 && narrowA <= 4 && k == 5;
 }
@@ -208,7 +218,7 @@ static void launch_corr_t(const float* nar, const float* wide, float* part, int 
   using CF = NarrowCorrCfg<C, 5>;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_narrow_corr<C, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM); attr = true; }
-  k_narrow_corr<C, 5><<<nblk, 256, CF::SMEM, st>>>(nar, wide, part, N, H, W, A);
+  k_narrow_corr<C, 5><<<nblk, CF::THREADS, CF::SMEM, st>>>(nar, wide, part, N, H, W, A);
 }
 void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int N, int H, int W, int A, int C, int k, int mode,
                              bool accumulate, void* scratch, size_t scratch_bytes, cudaStream_t st) {

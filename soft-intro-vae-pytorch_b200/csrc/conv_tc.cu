@@ -535,6 +535,239 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const Fwd
   k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, p, n_tiles, total);
   return (int)cudaGetLastError();
 }
+// ---------------------------------------------------------------------------------------------------------------
+// forward / dgrad kernel v3 (3x3 only): HALO REUSE.  The v1/v2 kernels fetch one A tile per filter tap, i.e. every input
+// pixel crosses L2->SM nine times; ncu shows them pinned at the ~10 TB/s L2 read ceiling (profiles/r01a_prof_fwd.md).
+// Here one TMA box {32c, 16w, 16T+2 rows} = the pixel tile PLUS its halo is loaded once per 32-channel chunk and
+// all nine taps are fed from it: for tap (r,s) the A operand of the UMMA is the same shared-memory tile addressed from
+// row (r*16 + s): output pixel (h, w<8) -> smem row (h+r)*16 + (w+s), i.e. 8-row groups 2048 B apart (SBO) whose
+// start is shifted by s rows.  (The swizzle is a function of absolute smem address bits, so no base_offset is needed
+// as long as the tile itself is 1024B-aligned -- verified on hardware, see halo_mode().)
+// T = 2 vertically stacked 16x8 pixel tiles share every B (filter) tile, halving filter traffic as well.
+// Two rings: A (halo, consumed for a whole chunk = 9 taps) and B (one filter tap x 32 channels).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+  return d;
+}
+struct HaloParams {
+  int N, H, W, Cin, Cout;
+  int tiles_w, tiles_h;        // W/8, H/(16*T)
+  int n_tiles, total;          // Cout tiles, total work items
+  int base_offset_mode;        // 1: descriptor base_offset = s (documented semantics); 0: always 0 (experiment)
+  const float* bias;
+  const float* addend;
+  float* y;
+};
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+struct HaloSmem {
+  static constexpr int ROWS = 16 * T + 2;
+  static constexpr int A_BYTES = ROWS * 16 * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_OFF = A_STAGES * A_BYTES;
+  static constexpr int BAR_OFF = B_OFF + B_STAGES * B_BYTES;
+  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
+};
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+__global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__ CUtensorMap map_x,
+                                                         const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* a_empty = a_full + A_STAGES;
+  uint64_t* b_full = a_empty + A_STAGES;
+  uint64_t* b_empty = b_full + B_STAGES;
+  uint64_t* tmem_full = b_empty + B_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cchunks = p.Cin >> 5;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int ai = 0, bi = 0;
+      for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
+        const int nt = item % p.n_tiles, mt = item / p.n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * 8, h0 = th * 16 * T, col0 = nt * BLOCK_N;
+        for (int ch = 0; ch < cchunks; ++ch) {
+          {
+            const int st = ai % A_STAGES;
+            mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&a_full[st], SM::A_BYTES);
+            tma_load_4d(smem + st * SM::A_BYTES, &map_x, &a_full[st], ch << 5, w0 - 1, h0 - 1, n);
+            ++ai;
+          }
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const int st = bi % B_STAGES;
+            mbar_wait(&b_empty[st], ((bi / B_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&b_full[st], SM::B_BYTES);
+            tma_load_2d(smem + SM::B_OFF + st * SM::B_BYTES, &map_w, &b_full[st], tap * p.Cin + (ch << 5), col0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+    int ai = 0, bi = 0, lt = 0;
+    for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T * BLOCK_N);
+      for (int ch = 0; ch < cchunks; ++ch, ++ai) {
+        const int ast = ai % A_STAGES;
+        mbar_wait(&a_full[ast], (ai / A_STAGES) & 1);
+        const uint32_t sa = smem_u32(smem + ast * SM::A_BYTES);
+        for (int tap = 0; tap < 9; ++tap, ++bi) {
+          const int bst = bi % B_STAGES;
+          mbar_wait(&b_full[bst], (bi / B_STAGES) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const uint32_t arow = sa + (uint32_t)(((16 * t + r) * 16 + s) * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t ad = make_smem_desc_bo(arow + k * 32, 2048, bo);
+                uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+                umma_tf32(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&b_empty[bst]);
+            if (tap == 8) {
+              umma_commit(&a_empty[ast]);
+              if (ch == cchunks - 1) umma_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dh = row >> 3, dw = row & 7;
+    int lt = 0;
+    for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
+      const int acc = lt & 1;
+      const int nt = item % p.n_tiles, mt = item / p.n_tiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 8, h0 = th * 16 * T, col0 = nt * BLOCK_N;
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const long long pix = ((long long)n * p.H + (h0 + 16 * t + dh)) * p.W + (w0 + dw);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          if (col0 + c >= p.Cout) break;
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          float* dst = p.y + pix * p.Cout + col0 + c;
+          const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + c + j < p.Cout) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (p.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (add) {
+                float4 a = *reinterpret_cast<const float4*>(add + j);
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<SM::TMEM_COLS>(tmem_base);
+}
+// 0 = off (v2 kernel), 2 = on with descriptor base_offset = 0 (default), 1 = on with base_offset = s.
+// Measured on B200 (tests/tc_probe.py, profiles/r01b_halo_probe.txt): the tensor core swizzles on ABSOLUTE shared-memory
+// address bits, so a start address shifted by s rows inside a 1024B-aligned tile needs base_offset = 0; base_offset = s
+// (the documented formula for a matrix whose own base is unaligned) gives wrong results here.
+static int halo_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_HALO");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+static bool halo_supported(const ConvShape& s) {
+  return s.k == 3 && s.Cin % 32 == 0 && s.Cout % 4 == 0 && s.Cout >= 32 && s.W % 8 == 0 && s.H % 16 == 0;
+}
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                         cudaStream_t st) {
+  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv3x3_halo<BLOCK_N, T, A_STAGES, B_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  HaloParams p;
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout;
+  p.tiles_w = s.W / 8; p.tiles_h = s.H / (16 * T);
+  p.n_tiles = (s.Cout + BLOCK_N - 1) / BLOCK_N;
+  p.total = p.tiles_w * p.tiles_h * s.N * p.n_tiles;
+  p.base_offset_mode = halo_mode() == 1 ? 1 : 0;
+  p.bias = bias; p.addend = addend; p.y = y;
+  CUtensorMap mx, mw;
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, SM::ROWS, 1);
+  if (r) return r;
+  r = make_map_2d(&mw, w, s.Cout, 9LL * s.Cin, BLOCK_N);
+  if (r) return r;
+  const int grid = p.total < num_sms() ? p.total : num_sms();
+  g_launches += 1;
+  k_conv3x3_halo<BLOCK_N, T, A_STAGES, B_STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, p);
+  return (int)cudaGetLastError();
+}
+static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                       cudaStream_t st) {
+  const bool two = (s.H % 32 == 0);
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4>(x, w, bias, addend, y, s, st) : launch_halo_t<128, 1, 3, 5>(x, w, bias, addend, y, s, st);
+  return two ? launch_halo_t<64, 2, 2, 6>(x, w, bias, addend, y, s, st) : launch_halo_t<64, 1, 3, 8>(x, w, bias, addend, y, s, st);
+}
+
 static int fwd_kernel_version() {
   static int v = -1;
   if (v < 0) {
@@ -553,6 +786,7 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   p.bias = bias; p.addend = addend; p.y = y;
   const int tiles_n = (s.N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_supported(s)) return launch_halo(x, w, bias, addend, y, s, st);
   CUtensorMap mx, mw;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
   if (r) return r;

@@ -309,7 +309,7 @@ static size_t carve(sivae_engine* e, char* base) {
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
 enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_COUNT = 4 };
-struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; ConvShape shape; };
 struct Prof {
   bool on = false;
   std::vector<ProfRec> recs;
@@ -327,6 +327,7 @@ struct ProfScope {
     r = &g_prof.recs[g_prof.used++];
     r->cls = cls;
     r->flops = 2.0 * (double)s.pixels() * (double)s.Cout * (double)s.ktot();
+    r->shape = s;
     cudaEventRecord(r->a, st);
   }
   ~ProfScope() { if (r) cudaEventRecord(r->b, st); }
@@ -852,6 +853,33 @@ extern "C" int sivae_profile_enable(int on) {
 }
 // out[class][3] = {milliseconds, flops, launches} for class 0 = tcgen05 conv fwd/dgrad, 1 = tcgen05 wgrad,
 // 2 = SIMT conv fwd/dgrad, 3 = SIMT wgrad.  Synchronises the device.
+// per-(class, shape) table of the recorded launches as text lines "cls N H W Cin Cout k launches ms gflop"; call BEFORE
+// sivae_profile_read (which resets the recorder).  Returns the number of bytes written (truncated to len-1).
+extern "C" int sivae_profile_dump(char* buf, int len) {
+  if (!buf || len < 2) return fail(-1, "bad buffer");
+  cudaDeviceSynchronize();
+  struct Agg { int cls; ConvShape s; int n; double ms, fl; };
+  std::vector<Agg> aggs;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    const ProfRec& r = g_prof.recs[i];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    bool found = false;
+    for (Agg& a : aggs)
+      if (a.cls == r.cls && a.s.N == r.shape.N && a.s.H == r.shape.H && a.s.W == r.shape.W && a.s.Cin == r.shape.Cin &&
+          a.s.Cout == r.shape.Cout && a.s.k == r.shape.k) { a.n++; a.ms += ms; a.fl += r.flops; found = true; break; }
+    if (!found) aggs.push_back(Agg{r.cls, r.shape, 1, ms, r.flops});
+  }
+  int off = 0;
+  for (const Agg& a : aggs) {
+    int w = snprintf(buf + off, len - off, "%d %d %d %d %d %d %d %d %.4f %.3f\n", a.cls, a.s.N, a.s.H, a.s.W, a.s.Cin, a.s.Cout,
+                     a.s.k, a.n, a.ms, a.fl * 1e-9);
+    if (w < 0 || w >= len - off) break;
+    off += w;
+  }
+  buf[off] = 0;
+  return off;
+}
 extern "C" int sivae_profile_read(double* out) {
   if (!out) return fail(-1, "null argument");
   cudaDeviceSynchronize();

@@ -57,6 +57,7 @@ _SIGS = {
     "sivae_launch_count": (C.c_ulonglong, []),
     "sivae_profile_enable": (C.c_int, [C.c_int]),
     "sivae_profile_read": (C.c_int, [C.POINTER(C.c_double)]),
+    "sivae_profile_dump": (C.c_int, [C.c_char_p, C.c_int]),
     "sivae_last_image": (C.c_int, [_P, C.c_int, _P, _P]),
     "sivae_last_batch": (C.c_int, [_P]),
     "sivae_conv2d_fwd": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 7 + [_P]),

@@ -97,11 +97,18 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def compare(eng, ora, tol, label="", lr=2e-4, verbose=True, tensor_tol=None):
+def compare(eng, ora, tol, label="", lr=2e-4, verbose=True, tensor_tol=None, noise=None):
     """tol: relative tolerance for scalars; tensors (gradients, BN statistics) get 10*tol as relative-L2 / max-rel.
     All deviations are measured first (and appended to gpurun_out/parity_report.jsonl), then asserted."""
     import json
     ttol = 10 * tol if tensor_tol is None else tensor_tol
+    # `noise`: the same oracle run in fp32.  Some seeds are ill-conditioned (the fp32 reference itself is 2e-3 away from
+    # fp64 on the CIFAR-shaped case); a gradient tensor may deviate from the fp64 truth by 3x the reference's own fp32
+    # round-off before it counts as a failure.
+    def floor(name, k):
+        if noise is None or k not in noise.get(name, {}):
+            return 0.0
+        return 3.0 * rel_l2(noise[name][k], ora[name][k])
     dev, fails = {}, []
     es, os_ = eng["scalars"], ora["scalars"]
     if es.get("nan", 0.0) != 0.0:
@@ -121,8 +128,8 @@ def compare(eng, ora, tol, label="", lr=2e-4, verbose=True, tensor_tol=None):
         for k in ora[name]:
             r = rel_l2(eng[name][k], ora[name][k])
             dev[name + ":" + k] = r
-            if not r < ttol:
-                fails.append("%s[%s] rel-L2 %.3g > %.3g" % (name, k, r, ttol))
+            if not r < max(ttol, floor(name, k)):
+                fails.append("%s[%s] rel-L2 %.3g > %.3g" % (name, k, r, max(ttol, floor(name, k))))
     for k, v in ora["post"].items():
         e = eng["post"][k]
         if k.endswith("num_batches_tracked"):

@@ -67,6 +67,7 @@ if __name__ == "__main__":
     say("device:", torch.cuda.get_device_name(0))
     for shp in [(1, 16, 16, 32, 32, 1), (1, 16, 16, 32, 64, 3), (2, 8, 8, 64, 64, 3), (8, 4, 4, 64, 128, 3),
                 (3, 16, 16, 32, 64, 3), (5, 8, 8, 32, 64, 1), (2, 32, 32, 64, 64, 3), (2, 16, 16, 128, 256, 3),
-                (4, 32, 32, 64, 3 * 0 + 64, 5), (32, 4, 4, 512, 512, 3)]:
+                (4, 32, 32, 64, 3 * 0 + 64, 5), (32, 4, 4, 512, 512, 3), (2, 32, 32, 64, 128, 3), (1, 64, 64, 64, 64, 3),
+                (3, 32, 16, 32, 96, 3), (2, 64, 32, 128, 512, 3)]:
         case(*shp, what=what)
     say("probe done")
