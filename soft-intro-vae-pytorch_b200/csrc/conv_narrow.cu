@@ -15,17 +15,20 @@ namespace sivae {
 static inline unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// narrow-in forward.  Block = 16 rows x 32 cols of output pixels, 256 threads, thread = pixels (ty, tx) and (ty, tx+16)
+// narrow-in forward.  Block = 8 rows x 32 cols of output pixels, one warp per row.  Lane = (channel quad cq = lane & 15,
+// pixel parity ph = lane >> 4): a lane accumulates 4 output channels for 8 pixels at a time, so the filter quad is one
+// conflict-free LDS.128 reused over 8 pixels (96 FMA per 11 LDS) and the 16 lanes of a pixel write 256 contiguous bytes
+// (the first version stored 16 B per lane at a 256 B stride: store-bound at ~0.5 TB/s, profiles/r01d_layers_H_tmastore.md)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int NI_TH = 16, NI_TW = 32;
+constexpr int NI_TH = 8, NI_TW = 32;
 template <int KS>
 __global__ void __launch_bounds__(256) k_narrow_in_fwd(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* addend, float* y, int N,
                                                        int H, int W, int A, int Cout) {
   extern __shared__ float sm[];
   constexpr int HTH = NI_TH + KS - 1, HTW = NI_TW + KS - 1;
-  float* sx = sm;                                   // [HTH][HTW][A]
-  float* sw = sm + ((HTH * HTW * 4 + 3) & ~3);      // [tap][a][Cout]: 4 consecutive co = one LDS.128
+  float* sx = sm;                                   // [HTH][HTW][4]  (channels padded to 4: one LDS.128 per pixel)
+  float* sw = sm + HTH * HTW * 4;                   // [tap][a][Cout]
   const int tiles_w = (W + NI_TW - 1) / NI_TW, tiles_h = (H + NI_TH - 1) / NI_TH;
   const int tile = blockIdx.x;
   const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
@@ -35,60 +38,57 @@ __global__ void __launch_bounds__(256) k_narrow_in_fwd(const float* __restrict__
     int a = i % A, t = (i / A) % taps, co = i / (A * taps);
     sw[(t * A + a) * Cout + co] = w[i];
   }
-  for (int i = threadIdx.x; i < HTH * HTW * A; i += 256) {
-    int a = i % A, cx = (i / A) % HTW, cy = i / (A * HTW);
+  for (int i = threadIdx.x; i < HTH * HTW * 4; i += 256) {
+    int a = i & 3, cx = (i >> 2) % HTW, cy = i / (4 * HTW);
     int hh = h0 + cy - pad, ww = w0 + cx - pad;
-    sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)n * H + hh) * W + ww) * A + a] : 0.f;
+    sx[i] = (a < A && hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)n * H + hh) * W + ww) * A + a] : 0.f;
   }
   __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int ho = h0 + ty;
-  const int wo[2] = {w0 + tx, w0 + tx + 16};
-  for (int c0 = 0; c0 < Cout; c0 += 32) {
-    const int cn = min(32, Cout - c0);          // multiple of 4
-    float acc[2][32];
+  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
+  const int cq = lane & 15, ph = lane >> 4;
+  const int ho = h0 + row;
+  for (int c0 = 0; c0 < Cout; c0 += 64) {
+    const int co = c0 + 4 * cq;
+    const bool cvalid = co < Cout;
+    const int cos = cvalid ? co : 0;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      float acc[8][4];
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[p][j] = 0.f;
-    for (int r = 0; r < KS; ++r)
-      for (int s = 0; s < KS; ++s) {
-        const float* xp0 = sx + ((ty + r) * HTW + tx + s) * A;
-        const float* xp1 = xp0 + 16 * A;
-        const float* wp = sw + (r * KS + s) * A * Cout + c0;
-        for (int a = 0; a < A; ++a) {
-          const float x0 = xp0[a], x1 = xp1[a];
-          const float4* w4 = reinterpret_cast<const float4*>(wp + a * Cout);
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int r = 0; r < KS; ++r)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (4 * j < cn) {
-              const float4 q = w4[j];
-              acc[0][4 * j] = fmaf(x0, q.x, acc[0][4 * j]);         acc[1][4 * j] = fmaf(x1, q.x, acc[1][4 * j]);
-              acc[0][4 * j + 1] = fmaf(x0, q.y, acc[0][4 * j + 1]); acc[1][4 * j + 1] = fmaf(x1, q.y, acc[1][4 * j + 1]);
-              acc[0][4 * j + 2] = fmaf(x0, q.z, acc[0][4 * j + 2]); acc[1][4 * j + 2] = fmaf(x1, q.z, acc[1][4 * j + 2]);
-              acc[0][4 * j + 3] = fmaf(x0, q.w, acc[0][4 * j + 3]); acc[1][4 * j + 3] = fmaf(x1, q.w, acc[1][4 * j + 3]);
-            }
+        for (int s = 0; s < KS; ++s) {
+          const float* wp = sw + (r * KS + s) * A * Cout + cos;
+          float4 wq[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) wq[a] = a < A ? *reinterpret_cast<const float4*>(wp + a * Cout) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* xp = sx + ((row + r) * HTW + ph + 16 * g + s) * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(xp + 8 * i);      // pixel ph + 2*(8g + i), tap column s
+            acc[i][0] = fmaf(xv.x, wq[0].x, fmaf(xv.y, wq[1].x, fmaf(xv.z, wq[2].x, fmaf(xv.w, wq[3].x, acc[i][0]))));
+            acc[i][1] = fmaf(xv.x, wq[0].y, fmaf(xv.y, wq[1].y, fmaf(xv.z, wq[2].y, fmaf(xv.w, wq[3].y, acc[i][1]))));
+            acc[i][2] = fmaf(xv.x, wq[0].z, fmaf(xv.y, wq[1].z, fmaf(xv.z, wq[2].z, fmaf(xv.w, wq[3].z, acc[i][2]))));
+            acc[i][3] = fmaf(xv.x, wq[0].w, fmaf(xv.y, wq[1].w, fmaf(xv.z, wq[2].w, fmaf(xv.w, wq[3].w, acc[i][3]))));
           }
         }
-      }
+      if (cvalid && ho < H) {
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) bq = *reinterpret_cast<const float4*>(bias + co);
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      if (ho < H && wo[p] < W) {
-        const long long pix = ((long long)n * H + ho) * W + wo[p];
-        float* dst = y + pix * Cout + c0;
-        const float* add = addend ? addend + pix * Cout + c0 : nullptr;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (4 * j < cn) {
-            float4 o = make_float4(acc[p][4 * j], acc[p][4 * j + 1], acc[p][4 * j + 2], acc[p][4 * j + 3]);
-            if (bias) {
-              o.x += bias[c0 + 4 * j]; o.y += bias[c0 + 4 * j + 1]; o.z += bias[c0 + 4 * j + 2]; o.w += bias[c0 + 4 * j + 3];
-            }
-            if (add) {
-              float4 q = *reinterpret_cast<const float4*>(add + 4 * j);
+        for (int i = 0; i < 8; ++i) {
+          const int wo = w0 + ph + 2 * (8 * g + i);
+          if (wo < W) {
+            const long long pix = ((long long)n * H + ho) * W + wo;
+            float4 o = make_float4(acc[i][0] + bq.x, acc[i][1] + bq.y, acc[i][2] + bq.z, acc[i][3] + bq.w);
+            if (addend) {
+              float4 q = *reinterpret_cast<const float4*>(addend + pix * Cout + co);
               o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
             }
-            *reinterpret_cast<float4*>(dst + 4 * j) = o;
+            *reinterpret_cast<float4*>(y + pix * Cout + co) = o;
           }
         }
       }
@@ -103,7 +103,7 @@ void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias
                                const ConvShape& s, cudaStream_t st) {
   g_launches += 1;
   const int HTH = NI_TH + s.k - 1, HTW = NI_TW + s.k - 1;
-  size_t shmem = ((size_t)((HTH * HTW * 4 + 3) & ~3) + (size_t)s.Cout * s.k * s.k * s.Cin) * sizeof(float);
+  size_t shmem = ((size_t)HTH * HTW * 4 + (size_t)s.Cout * s.k * s.k * s.Cin) * sizeof(float);
   unsigned grid = (unsigned)(cdivu(s.W, NI_TW) * cdivu(s.H, NI_TH) * s.N);
   if (s.k == 5) {
     static bool attr = false;

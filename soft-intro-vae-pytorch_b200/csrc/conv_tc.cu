@@ -54,6 +54,9 @@ static int make_map_nhwc(CUtensorMap* m, const float* base, int N, int H, int W,
                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -102;
 }
+static int make_store_map(CUtensorMap* m, float* base, int N, int H, int W, int C, int sw, int sh, int sn) {
+  return make_map_nhwc(m, base, N, H, W, C, sw, sh, sn);
+}
 // row-major fp32 matrix [rows][cols] -> 2-D map, box {32, box_rows}
 static int make_map_2d(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows) {
   EncodeTiledFn f = encode_fn();
@@ -157,6 +160,81 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue of one 32-row x 32-column accumulator chunk held by a warp (lane = row): + bias + addend, then either
+//  (a) staged through a 4 KB shared tile (128B-swizzled, conflict-free 16-byte stores) and written by ONE TMA store of the
+//      box {32 ch, bw, bh, bn} -- full-line coalesced writes, batch tail clipped by the tensor map; or
+//  (b) direct per-thread stores (narrow outputs whose channel count is not a multiple of 4, e.g. the 3-channel image).
+// Path (a) exists because direct stores (32 rows x 16 B per instruction, each its own L2 transaction) capped every
+// output-heavy layer at ~1.1 TB/s (profiles/r01c_layers_H_halo.md: 1x1 convs 35-126 TFLOP/s, 64-channel 3x3 at 0.45 ms).
+struct EpiOut { const float* bias; const float* addend; float* y; int Cout; };
+__device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
+                                          uint8_t* stage, const CUtensorMap* map_y, int cw, int ch, int cn, int lane) {
+  if (tma) {
+    const float* add = (o.addend && valid) ? o.addend + pix * o.Cout + col : nullptr;
+    if (lane == 0) bulk_wait_read0();            // the previous TMA store has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 q = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      if (col + 4 * j < o.Cout) {
+        if (o.bias) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(o.bias + col + 4 * j));
+          q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+        }
+        if (add) {
+          float4 a = *reinterpret_cast<const float4*>(add + 4 * j);
+          q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+        }
+      }
+      *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = q;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(map_y, stage, col, cw, ch, cn);
+      bulk_commit();
+    }
+    return;
+  }
+  if (!valid) return;
+  float* dst = o.y + pix * o.Cout + col;
+  const float* add = o.addend ? o.addend + pix * o.Cout + col : nullptr;
+  if ((o.Cout & 3) != 0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col + j < o.Cout) {
+        float x = __uint_as_float(v[j]);
+        if (o.bias) x += __ldg(o.bias + col + j);
+        if (add) x += add[j];
+        dst[j] = x;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col + j < o.Cout) {
+        float4 q = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        if (o.bias) {
+          float4 b = __ldg(reinterpret_cast<const float4*>(o.bias + col + j));
+          q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+        }
+        if (add) {
+          float4 a = *reinterpret_cast<const float4*>(add + j);
+          q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+        }
+        *reinterpret_cast<float4*>(dst + j) = q;
+      }
+    }
+  }
+}
 // shared-memory matrix descriptor (sm_100 UMMA): start address, leading / stride byte offsets (>>4), version 1,
 // layout type 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only layout the
 // tensor core accepts for MN-major 32-bit operands)
@@ -182,6 +260,8 @@ struct FwdParams {
   int N, H, W, Cin, Cout, ks;
   int bw, bh, bn;            // pixel tile = bn x bh x bw = 128
   int tiles_w, tiles_h;      // W/bw, H/bh
+  int sbh, sbn;              // TMA-store box of one warp's 32 rows: {32 ch, bw, sbh, sbn}
+  int tma_store;             // 1: epilogue through shared memory + TMA store; 0: direct stores
   const float* bias;
   const float* addend;
   float* y;
@@ -363,13 +443,15 @@ template <int BLOCK_N, int STAGES>
 struct Fwd2Smem {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAGE_OFF = STAGES * STAGE_BYTES;          // 4 x 4 KB epilogue staging tiles
+  static constexpr int BAR_OFF = STAGE_OFF + 4 * 4096;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__ CUtensorMap map_x,
-                                                         const __grid_constant__ CUtensorMap map_w, const FwdParams p,
+                                                         const __grid_constant__ CUtensorMap map_w,
+                                                         const __grid_constant__ CUtensorMap map_y, const FwdParams p,
                                                          const int n_tiles, const int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   using SM = Fwd2Smem<BLOCK_N, STAGES>;
@@ -450,6 +532,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int dw = row % p.bw, dh = (row / p.bw) % p.bh, dn = row / (p.bw * p.bh);
+    const int r0 = q * 32;                                  // first row of this warp: TMA-store box origin
+    const int sdh = (r0 / p.bw) % p.bh, sdn = r0 / (p.bw * p.bh);
+    uint8_t* stage = smem + SM::STAGE_OFF + q * 4096;
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout};
+    const bool tma = p.tma_store != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -467,43 +554,14 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
         if (col0 + c >= p.Cout) break;                     // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        if (valid && (p.Cout & 3) != 0) {
-          float* dst = p.y + pix * p.Cout + col0 + c;
-          const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + c + j < p.Cout) {
-              float o = __uint_as_float(v[j]);
-              if (p.bias) o += __ldg(p.bias + col0 + c + j);
-              if (add) o += add[j];
-              dst[j] = o;
-            }
-          }
-        } else if (valid) {
-          float* dst = p.y + pix * p.Cout + col0 + c;
-          const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + c + j < p.Cout) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              if (p.bias) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (add) {
-                float4 a = *reinterpret_cast<const float4*>(add + j);
-                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-              }
-              *reinterpret_cast<float4*>(dst + j) = o;
-            }
-          }
-        }
+        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, &map_y, w0, h0 + sdh, n0 + sdn, lane);
       }
       // this warp is done reading the accumulator: release it to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (tma && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -520,7 +578,8 @@ static int num_sms() {
   return n;
 }
 template <int BLOCK_N, int STAGES>
-static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const FwdParams& p, int m_tiles, cudaStream_t st) {
+static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const FwdParams& p, int m_tiles,
+                         cudaStream_t st) {
   using SM = Fwd2Smem<BLOCK_N, STAGES>;
   static bool attr = false;
   if (!attr) {
@@ -532,7 +591,7 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const Fwd
   const int total = m_tiles * n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   g_launches += 1;
-  k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, p, n_tiles, total);
+  k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p, n_tiles, total);
   return (int)cudaGetLastError();
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -546,6 +605,14 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const Fwd
 // T = 2 vertically stacked 16x8 pixel tiles share every B (filter) tile, halving filter traffic as well.
 // Two rings: A (halo, consumed for a whole chunk = 9 taps) and B (one filter tap x 32 channels).
 // ---------------------------------------------------------------------------------------------------------------
+static bool tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_TMASTORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 __device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -557,6 +624,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t s
 }
 struct HaloParams {
   int N, H, W, Cin, Cout;
+  int tma_store;
   int tiles_w, tiles_h;        // W/8, H/(16*T)
   int n_tiles, total;          // Cout tiles, total work items
   int base_offset_mode;        // 1: descriptor base_offset = s (documented semantics); 0: always 0 (experiment)
@@ -564,22 +632,25 @@ struct HaloParams {
   const float* addend;
   float* y;
 };
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
 struct HaloSmem {
-  static constexpr int ROWS = 16 * T + 2;
+  static constexpr int ROWS = 16 * T + KS - 1;
   static constexpr int A_BYTES = ROWS * 16 * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
-  static constexpr int BAR_OFF = B_OFF + B_STAGES * B_BYTES;
+  static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;     // 4 x 4 KB epilogue staging tiles
+  static constexpr int BAR_OFF = STAGE_OFF + 4 * 4096;
   static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
-__global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__ CUtensorMap map_x,
-                                                         const __grid_constant__ CUtensorMap map_w, const HaloParams p) {
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
+__global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CUtensorMap map_x,
+                                                      const __grid_constant__ CUtensorMap map_w,
+                                                      const __grid_constant__ CUtensorMap map_y, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES>;
+  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KS>;
+  constexpr int TAPS = KS * KS, PAD = KS / 2;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* a_empty = a_full + A_STAGES;
@@ -618,10 +689,10 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__
             const int st = ai % A_STAGES;
             mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
             mbar_expect_tx(&a_full[st], SM::A_BYTES);
-            tma_load_4d(smem + st * SM::A_BYTES, &map_x, &a_full[st], ch << 5, w0 - 1, h0 - 1, n);
+            tma_load_4d(smem + st * SM::A_BYTES, &map_x, &a_full[st], ch << 5, w0 - PAD, h0 - PAD, n);
             ++ai;
           }
-          for (int tap = 0; tap < 9; ++tap, ++bi) {
+          for (int tap = 0; tap < TAPS; ++tap, ++bi) {
             const int st = bi % B_STAGES;
             mbar_wait(&b_empty[st], ((bi / B_STAGES) & 1) ^ 1);
             mbar_expect_tx(&b_full[st], SM::B_BYTES);
@@ -642,13 +713,13 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__
         const int ast = ai % A_STAGES;
         mbar_wait(&a_full[ast], (ai / A_STAGES) & 1);
         const uint32_t sa = smem_u32(smem + ast * SM::A_BYTES);
-        for (int tap = 0; tap < 9; ++tap, ++bi) {
+        for (int tap = 0; tap < TAPS; ++tap, ++bi) {
           const int bst = bi % B_STAGES;
           mbar_wait(&b_full[bst], (bi / B_STAGES) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
-            const int r = tap / 3, s = tap - 3 * r;
+            const int r = tap / KS, s = tap - KS * r;
             const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -661,7 +732,7 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__
               }
             }
             umma_commit(&b_empty[bst]);
-            if (tap == 8) {
+            if (tap == TAPS - 1) {
               umma_commit(&a_empty[ast]);
               if (ch == cchunks - 1) umma_commit(&tmem_full[acc]);
             }
@@ -674,6 +745,9 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int dh = row >> 3, dw = row & 7;
+    uint8_t* stage = smem + SM::STAGE_OFF + q * 4096;
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout};
+    const bool tma = p.tma_store != 0;
     int lt = 0;
     for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -691,29 +765,15 @@ __global__ void __launch_bounds__(192, 1) k_conv3x3_halo(const __grid_constant__
           if (col0 + c >= p.Cout) break;
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
-          float* dst = p.y + pix * p.Cout + col0 + c;
-          const float* add = p.addend ? p.addend + pix * p.Cout + col0 + c : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + c + j < p.Cout) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              if (p.bias) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c + j));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (add) {
-                float4 a = *reinterpret_cast<const float4*>(add + j);
-                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-              }
-              *reinterpret_cast<float4*>(dst + j) = o;
-            }
-          }
+          // this warp's 32 rows = image rows h0+16t+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
+          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, &map_y, w0, h0 + 16 * t + 4 * q, n, lane);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (tma && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -732,15 +792,16 @@ static int halo_mode() {
   return v;
 }
 static bool halo_supported(const ConvShape& s) {
-  return s.k == 3 && s.Cin % 32 == 0 && s.Cout % 4 == 0 && s.Cout >= 32 && s.W % 8 == 0 && s.H % 16 == 0;
+  return (s.k == 3 || s.k == 5) && s.Cin % 32 == 0 && s.Cout >= 1 && s.W % 8 == 0 && s.H % 16 == 0;
 }
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
 static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                          cudaStream_t st) {
-  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES>;
+  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KS>;
+  static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv3x3_halo<BLOCK_N, T, A_STAGES, B_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -751,21 +812,35 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   p.total = p.tiles_w * p.tiles_h * s.N * p.n_tiles;
   p.base_offset_mode = halo_mode() == 1 ? 1 : 0;
   p.bias = bias; p.addend = addend; p.y = y;
-  CUtensorMap mx, mw;
+  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
+  CUtensorMap mx, mw, my;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, SM::ROWS, 1);
   if (r) return r;
-  r = make_map_2d(&mw, w, s.Cout, 9LL * s.Cin, BLOCK_N);
+  r = make_map_2d(&mw, w, s.Cout, (long long)KS * KS * s.Cin, BLOCK_N);
   if (r) return r;
+  my = mx;
+  if (p.tma_store) {
+    r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
+    if (r) return r;
+  }
   const int grid = p.total < num_sms() ? p.total : num_sms();
   g_launches += 1;
-  k_conv3x3_halo<BLOCK_N, T, A_STAGES, B_STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, p);
+  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KS><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p);
   return (int)cudaGetLastError();
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        cudaStream_t st) {
   const bool two = (s.H % 32 == 0);
-  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4>(x, w, bias, addend, y, s, st) : launch_halo_t<128, 1, 3, 5>(x, w, bias, addend, y, s, st);
-  return two ? launch_halo_t<64, 2, 2, 6>(x, w, bias, addend, y, s, st) : launch_halo_t<64, 1, 3, 8>(x, w, bias, addend, y, s, st);
+  if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
+    return two ? launch_halo_t<32, 2, 2, 8, 5>(x, w, bias, addend, y, s, st) : launch_halo_t<32, 1, 3, 8, 5>(x, w, bias, addend, y, s, st);
+  }
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4, 3>(x, w, bias, addend, y, s, st) : launch_halo_t<128, 1, 3, 5, 3>(x, w, bias, addend, y, s, st);
+  return two ? launch_halo_t<64, 2, 2, 6, 3>(x, w, bias, addend, y, s, st) : launch_halo_t<64, 1, 3, 8, 3>(x, w, bias, addend, y, s, st);
+}
+static bool halo_eligible(const ConvShape& s) {
+  if (!halo_supported(s)) return false;
+  if (s.k == 5) return s.Cout <= 32;          // wide 5x5 outputs do not occur in this model
+  return s.Cout >= 32;
 }
 
 static int fwd_kernel_version() {
@@ -784,9 +859,10 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   pick_tile(s.H, s.W, &p.bw, &p.bh, &p.bn);
   p.tiles_w = s.W / p.bw; p.tiles_h = s.H / p.bh;
   p.bias = bias; p.addend = addend; p.y = y;
+  p.sbh = p.sbn = 1; p.tma_store = 0;
   const int tiles_n = (s.N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_supported(s)) return launch_halo(x, w, bias, addend, y, s, st);
+  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_eligible(s)) return launch_halo(x, w, bias, addend, y, s, st);
   CUtensorMap mx, mw;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
   if (r) return r;
@@ -803,10 +879,19 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   while (block_n > 64 && (long long)m_tiles * ((s.Cout + block_n - 1) / block_n) < num_sms()) block_n >>= 1;
   r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
   if (r) return r;
-  if (block_n == 256) return launch_fwd2_t<256, 4>(mx, mw, p, m_tiles, st);
-  if (block_n == 128) return launch_fwd2_t<128, 6>(mx, mw, p, m_tiles, st);
-  if (block_n == 64) return launch_fwd2_t<64, 8>(mx, mw, p, m_tiles, st);
-  return launch_fwd2_t<32, 8>(mx, mw, p, m_tiles, st);
+  // epilogue store path: TMA store of each warp's 32-row slab (needs 16-byte aligned channel rows)
+  CUtensorMap my = mx;
+  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
+  if (p.tma_store) {
+    p.sbh = (32 / p.bw) < p.bh ? (32 / p.bw) : p.bh;
+    p.sbn = 32 / (p.bw * p.sbh);
+    r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
+    if (r) return r;
+  }
+  if (block_n == 256) return launch_fwd2_t<256, 4>(mx, mw, my, p, m_tiles, st);
+  if (block_n == 128) return launch_fwd2_t<128, 5>(mx, mw, my, p, m_tiles, st);
+  if (block_n == 64) return launch_fwd2_t<64, 8>(mx, mw, my, p, m_tiles, st);
+  return launch_fwd2_t<32, 8>(mx, mw, my, p, m_tiles, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -989,7 +1074,11 @@ bool conv_tc_supported_wgrad(const ConvShape& s) {
   if (pn > 256) return false;
   return true;
 }
+struct Wg2Plan;
+static bool wgrad_halo_supported(const ConvShape& s);
+static size_t wg2_scratch_bytes(const ConvShape& s);
 size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s) {
+  if (wgrad_halo_supported(s)) return wg2_scratch_bytes(s);
   int splits; long long kbt, per;
   wg_plan(s, &splits, &kbt, &per);
   return (size_t)splits * s.Cout * s.ktot() * sizeof(float);
@@ -1008,8 +1097,225 @@ static int launch_wg_t(const CUtensorMap& mx, const CUtensorMap& mdy, const WgPa
   k_conv_wgrad_tc<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
   return (int)cudaGetLastError();
 }
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad kernel v2 (3x3, H % 16 == 0, W % 8 == 0): HALO REUSE in the MN-major formulation.
+// Work item = one 16x8 pixel tile (K = 128 pixels).  Per item the CTA loads, for each of its G 32-channel input chunks,
+// ONE halo box of x {32c, 16w, 18h} (36 KB) and the dy tile {32c, 8w, 16h} per 32 output channels.  For filter row r
+// and image row h one UMMA (M = 128, N = N_TILE, K = 8 pixels) is issued whose A operand is the x halo addressed at row
+// (h + r) * 16 with FOUR MN chunks 128 B (= one pixel = one filter column s) apart:
+//        D[(s, ci)][co] += sum_w x[h + r - 1][w + s - 1][ci] * dy[h][w][co]           s = 0..3 (s = 3 is a phantom tap)
+// so the three real taps of a filter row come out of one instruction and x is read from L2 once instead of 9 times
+// (v1 sat at 75-100 TFLOP/s: L2 + TMA-issue bound, profiles/r01c_layers_H_halo.md).  Accumulators for all
+// (chunk, r) pairs stay in TMEM (G * 3 * N_TILE <= 512 columns) across the CTA's whole pixel range; split over pixel
+// tiles, partials reduced in fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+struct Wg2Params {
+  int N, H, W, Cin, Cout, Ktot;
+  int tiles_w, tiles_h;
+  long long items_total, items_per_split;
+  float* part;                 // [splits][Cout][Ktot]
+};
+constexpr int WG2_X_BYTES = 18 * 16 * 128;     // x halo box
+constexpr int WG2_DY_BYTES = 16 * 8 * 128;     // dy box (32 channels)
+template <int N_TILE, int G, int STAGES>
+struct Wg2Smem {
+  static constexpr int A_BYTES = G * WG2_X_BYTES;
+  static constexpr int B_BYTES = (N_TILE / 32) * WG2_DY_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = (G * 3 * N_TILE) <= 128 ? 128 : ((G * 3 * N_TILE) <= 256 ? 256 : 512);
+};
+template <int N_TILE, int G, int STAGES>
+__global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constant__ CUtensorMap map_x,
+                                                            const __grid_constant__ CUtensorMap map_dy, const Wg2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = Wg2Smem<N_TILE, G, STAGES>;
+  static_assert(G * 3 * N_TILE <= 512, "TMEM budget");
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = blockIdx.x;                  // group of G input-channel chunks
+  const int col0 = blockIdx.y * N_TILE;       // first output channel
+  const long long it_begin = (long long)blockIdx.z * p.items_per_split;
+  long long it_end = it_begin + p.items_per_split;
+  if (it_end > p.items_total) it_end = p.items_total;
+  const int num_items = (int)(it_end > it_begin ? it_end - it_begin : 0);
+  int b_chunks = (p.Cout - col0 + 31) / 32;
+  if (b_chunks > N_TILE / 32) b_chunks = N_TILE / 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < num_items; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(&empty[st], ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)(G * WG2_X_BYTES + b_chunks * WG2_DY_BYTES));
+        const long long item = it_begin + i;
+        const int tw = (int)(item % p.tiles_w), th = (int)((item / p.tiles_w) % p.tiles_h);
+        const int n = (int)(item / ((long long)p.tiles_w * p.tiles_h));
+        const int w0 = tw * 8, h0 = th * 16;
+        uint8_t* sa = smem + st * SM::STAGE_BYTES;
+        for (int g = 0; g < G; ++g)
+          tma_load_4d(sa + g * WG2_X_BYTES, &map_x, &full[st], (cg * G + g) * 32, w0 - 1, h0 - 1, n);
+        uint8_t* sb = sa + SM::A_BYTES;
+        for (int j = 0; j < b_chunks; ++j)
+          tma_load_4d(sb + j * WG2_DY_BYTES, &map_dy, &full[st], col0 + 32 * j, w0, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, N_TILE, 1, 1);
+    for (int i = 0; i < num_items; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(&full[st], (i / STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
+        const uint32_t sb = sa + SM::A_BYTES;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)((g * 3 + r) * N_TILE);
+#pragma unroll 4
+            for (int h = 0; h < 16; ++h) {
+              // A: x halo rows (h + r) * 16 + w; MN chunks = filter columns s, 128 B (one pixel) apart; K atoms 512 B
+              uint64_t ad = make_smem_desc(sa + g * WG2_X_BYTES + (uint32_t)((h + r) * 16 * 128), 128, 512, 1);
+              // B: dy rows h * 8 + w; MN chunks = 32-channel boxes
+              uint64_t bd = make_smem_desc(sb + (uint32_t)(h * 8 * 128), WG2_DY_BYTES, 512, 1);
+              umma_tf32(tmem_d, ad, bd, idesc, (i > 0 || h > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty[st]);
+        if (i == num_items - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;          // = filter column s of this warp's 32 accumulator rows; s == 3 is the phantom tap
+    if (num_items > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    if (q < 3) {
+      float* dst = p.part + (long long)blockIdx.z * p.Cout * p.Ktot;
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const int ci = (cg * G + g) * 32 + lane;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+          const int kidx = (r * 3 + q) * p.Cin + ci;
+#pragma unroll 1
+          for (int c = 0; c < N_TILE; c += 32) {
+            if (col0 + c >= p.Cout) break;
+            uint32_t v[32];
+            if (num_items > 0) {
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 3 + r) * N_TILE + c), v);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int co = col0 + c + j;
+              if (co < p.Cout) dst[(long long)co * p.Ktot + kidx] = __uint_as_float(v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<SM::TMEM_COLS>(tmem_base);
+}
+static int wgrad_halo_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_WGHALO");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static bool wgrad_halo_supported(const ConvShape& s) {
+  return wgrad_halo_mode() != 0 && s.k == 3 && s.H % 16 == 0 && s.W % 8 == 0 && s.Cin % 32 == 0 && s.Cout % 32 == 0;
+}
+struct Wg2Plan { int n_tile, g, cgroups, ntiles, splits; long long items, per; };
+static Wg2Plan wg2_plan(const ConvShape& s) {
+  Wg2Plan pl;
+  pl.n_tile = s.Cout >= 128 ? 128 : 64;
+  pl.g = (pl.n_tile == 64 && s.Cin % 64 == 0) ? 2 : 1;
+  pl.cgroups = s.Cin / (32 * pl.g);
+  pl.ntiles = (s.Cout + pl.n_tile - 1) / pl.n_tile;
+  pl.items = (long long)s.N * (s.H / 16) * (s.W / 8);
+  long long pairs = (long long)pl.cgroups * pl.ntiles;
+  long long want = (num_sms() + pairs - 1) / pairs;       // ~one wave of 1-CTA-per-SM blocks
+  if (want > pl.items) want = pl.items;
+  if (want < 1) want = 1;
+  pl.per = (pl.items + want - 1) / want;
+  pl.splits = (int)((pl.items + pl.per - 1) / pl.per);
+  return pl;
+}
+static size_t wg2_scratch_bytes(const ConvShape& s) { return (size_t)wg2_plan(s).splits * s.Cout * s.ktot() * sizeof(float); }
+template <int N_TILE, int G, int STAGES>
+static int launch_wg2_t(const float* x, const float* dy, const ConvShape& s, const Wg2Plan& pl, float* part, cudaStream_t st) {
+  using SM = Wg2Smem<N_TILE, G, STAGES>;
+  static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_halo<N_TILE, G, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  Wg2Params p;
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.Ktot = (int)s.ktot();
+  p.tiles_w = s.W / 8; p.tiles_h = s.H / 16;
+  p.items_total = pl.items; p.items_per_split = pl.per;
+  p.part = part;
+  CUtensorMap mx, mdy;
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, 18, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (r) return r;
+  r = make_map_nhwc(&mdy, dy, s.N, s.H, s.W, s.Cout, 8, 16, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (r) return r;
+  dim3 grid(pl.cgroups, pl.ntiles, pl.splits);
+  g_launches += 2;
+  k_conv_wgrad_halo<N_TILE, G, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
+  return (int)cudaGetLastError();
+}
+
 int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate, void* scratch,
                          size_t scratch_bytes, cudaStream_t st) {
+  if (wgrad_halo_supported(s)) {
+    Wg2Plan pl = wg2_plan(s);
+    if (scratch_bytes < (size_t)pl.splits * s.Cout * s.ktot() * sizeof(float)) return -103;
+    int r2;
+    if (pl.n_tile == 128) r2 = launch_wg2_t<128, 1, 2>(x, dy, s, pl, (float*)scratch, st);
+    else if (pl.g == 2) r2 = launch_wg2_t<64, 2, 2>(x, dy, s, pl, (float*)scratch, st);
+    else r2 = launch_wg2_t<64, 1, 3>(x, dy, s, pl, (float*)scratch, st);
+    if (r2) return r2;
+    long long n2 = (long long)s.Cout * s.ktot();
+    unsigned blocks2 = (unsigned)((n2 + 255) / 256);
+    if (blocks2 > 148u * 8) blocks2 = 148u * 8;
+    k_wg_reduce<<<blocks2, 256, 0, st>>>((const float*)scratch, dw, n2, pl.splits, accumulate ? 1 : 0);
+    return (int)cudaGetLastError();
+  }
   WgParams p;
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
   pick_pixel_block(s.H, s.W, &p.pw, &p.ph, &p.pn);

@@ -159,3 +159,37 @@ def test_tiny_bootstrap_step_vs_reference_golden(backend):
         assert out["scalars"][k] == pytest.approx(v, rel=TOL[backend]), k
     ref = dict(scalars=ora["scalars"], grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
     compare(out, ref, TOL[backend], label="tiny bootstrap golden backend %d" % backend, tensor_tol=TTOL[backend])
+
+
+def test_train_driver_end_to_end(tmp_path):
+    """train_soft_intro_vae() itself on the GPU (synthetic data): one VAE warm-up epoch + one introspective epoch, then the
+    reference's side effects: checkpoint in the reference schema, statistics pickle, sample grids."""
+    import importlib
+    import pickle
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        M.train_soft_intro_vae(dataset="synthetic32:48", z_dim=32, batch_size=16, num_workers=0, num_epochs=2, num_vae=1,
+                               beta_kl=1.0, beta_neg=256, beta_rec=1.0, device=torch.device("cuda:0"), save_interval=1,
+                               start_epoch=0, lr_e=2e-4, lr_d=2e-4, pretrained=None, seed=3, test_iter=2, with_fid=False)
+        saves = sorted(os.listdir("saves"))
+        assert any(s.endswith("model_epoch_1_iter_6.pth") for s in saves), saves
+        ck = torch.load(os.path.join("saves", [s for s in saves if s.endswith("iter_6.pth")][0]), map_location="cpu")
+        assert set(ck) == {"epoch", "model"} and ck["epoch"] == 1
+        sd = ck["model"]
+        assert sd["encoder.main.0.weight"].shape == (64, 3, 5, 5) and sd["encoder.main.0.weight"].is_contiguous()
+        assert sd["decoder.main.predict.bias"].shape == (3,)
+        assert int(sd["encoder.main.1.num_batches_tracked"]) > 1
+        assert all(torch.isfinite(v).all() for v in sd.values() if v.is_floating_point())
+        with open("soft_intro_train_graphs_data.pickle", "rb") as fp:
+            g = pickle.load(fp)
+        assert set(g) == {"kl_real", "kl_fake", "kl_rec", "rec_err"} and len(g["kl_real"]) == 1
+        assert len([f for f in os.listdir("figures_synthetic32_48") if f.endswith(".jpg")]) >= 2
+        # the checkpoint loads back through the reference-style helper
+        model = M.SoftIntroVAE(cdim=3, zdim=32, channels=[64, 128, 256], image_size=32).to("cuda:0")
+        M.load_model(model, os.path.join("saves", [s for s in saves if s.endswith("iter_6.pth")][0]), torch.device("cuda:0"))
+        assert torch.equal(model.state_dict()["decoder.fc.0.weight"].cpu(), sd["decoder.fc.0.weight"])
+    finally:
+        os.chdir(cwd)
