@@ -174,9 +174,12 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 //  (b) direct per-thread stores (narrow outputs whose channel count is not a multiple of 4, e.g. the 3-channel image).
 // Path (a) exists because direct stores (32 rows x 16 B per instruction, each its own L2 transaction) capped every
 // output-heavy layer at ~1.1 TB/s (profiles/r01c_layers_H_halo.md: 1x1 convs 35-126 TFLOP/s, 64-channel 3x3 at 0.45 ms).
-struct EpiOut { const float* bias; const float* addend; float* y; int Cout; };
+struct EpiOut { const float* bias; const float* addend; float* y; int Cout; float* stats; };   // stats: BN partials base or null
+// srow >= 0 (TMA path only): also emit the per-channel sum / sum of squares of this warp's 32 rows (train-mode BatchNorm
+// statistics, fused so that the conv output is not re-read): stats[srow][0][c] = sum, stats[srow][1][c] = sum of squares
 __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
-                                          uint8_t* stage, const CUtensorMap* map_y, int cw, int ch, int cn, int lane) {
+                                          uint8_t* stage, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
+                                          long long srow = -1) {
   if (tma) {
     const float* add = (o.addend && valid) ? o.addend + pix * o.Cout + col : nullptr;
     if (lane == 0) bulk_wait_read0();            // the previous TMA store has finished reading the staging tile
@@ -201,6 +204,22 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, lo
     if (lane == 0) {
       tma_store_4d(map_y, stage, col, cw, ch, cn);
       bulk_commit();
+    }
+    if (o.stats && srow >= 0) {
+      // lane = column: walk the 32 staged rows (swizzled 16-byte chunks -> conflict-free)
+      float sm = 0.f, sq = 0.f;
+      const int cj = lane >> 2, ce = (lane & 3) << 2;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        const float x = *reinterpret_cast<const float*>(stage + r * 128 + ((cj ^ (r & 7)) << 4) + ce);
+        sm += x;
+        sq = fmaf(x, x, sq);
+      }
+      if (col + lane < o.Cout) {
+        float* d = o.stats + srow * 2 * o.Cout + col + lane;
+        d[0] = sm;
+        d[o.Cout] = sq;
+      }
     }
     return;
   }
@@ -265,6 +284,7 @@ struct FwdParams {
   const float* bias;
   const float* addend;
   float* y;
+  float* stats;              // BN partial sums [m_tiles*4][2][Cout] or null
 };
 constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 32 fp32
 
@@ -535,7 +555,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     const int r0 = q * 32;                                  // first row of this warp: TMA-store box origin
     const int sdh = (r0 / p.bw) % p.bh, sdn = r0 / (p.bw * p.bh);
     uint8_t* stage = smem + SM::STAGE_OFF + q * 4096;
-    const EpiOut eo{p.bias, p.addend, p.y, p.Cout};
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats};
     const bool tma = p.tma_store != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
@@ -554,7 +574,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
         if (col0 + c >= p.Cout) break;                     // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, &map_y, w0, h0 + sdh, n0 + sdn, lane);
+        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q);
       }
       // this warp is done reading the accumulator: release it to the MMA warp
       tc_fence_before();
@@ -631,6 +651,7 @@ struct HaloParams {
   const float* bias;
   const float* addend;
   float* y;
+  float* stats;                // BN partial sums [m_items*T*4][2][Cout] or null
 };
 template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
 struct HaloSmem {
@@ -746,7 +767,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
     const int row = q * 32 + lane;
     const int dh = row >> 3, dw = row & 7;
     uint8_t* stage = smem + SM::STAGE_OFF + q * 4096;
-    const EpiOut eo{p.bias, p.addend, p.y, p.Cout};
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats};
     const bool tma = p.tma_store != 0;
     int lt = 0;
     for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
@@ -766,7 +787,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           // this warp's 32 rows = image rows h0+16t+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
-          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, &map_y, w0, h0 + 16 * t + 4 * q, n, lane);
+          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, &map_y, w0, h0 + 16 * t + 4 * q, n, lane, ((long long)mt * T + t) * 4 + q);
         }
       }
       tc_fence_before();
@@ -796,7 +817,7 @@ static bool halo_supported(const ConvShape& s) {
 }
 template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
 static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                         cudaStream_t st) {
+                         float* stats, cudaStream_t st) {
   using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KS>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr = false;
@@ -813,6 +834,7 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   p.base_offset_mode = halo_mode() == 1 ? 1 : 0;
   p.bias = bias; p.addend = addend; p.y = y;
   p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
+  p.stats = p.tma_store ? stats : nullptr;
   CUtensorMap mx, mw, my;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, SM::ROWS, 1);
   if (r) return r;
@@ -829,13 +851,13 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   return (int)cudaGetLastError();
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                       cudaStream_t st) {
+                       float* stats, cudaStream_t st) {
   const bool two = (s.H % 32 == 0);
   if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
-    return two ? launch_halo_t<32, 2, 2, 8, 5>(x, w, bias, addend, y, s, st) : launch_halo_t<32, 1, 3, 8, 5>(x, w, bias, addend, y, s, st);
+    return two ? launch_halo_t<32, 2, 2, 8, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5>(x, w, bias, addend, y, s, stats, st);
   }
-  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4, 3>(x, w, bias, addend, y, s, st) : launch_halo_t<128, 1, 3, 5, 3>(x, w, bias, addend, y, s, st);
-  return two ? launch_halo_t<64, 2, 2, 6, 3>(x, w, bias, addend, y, s, st) : launch_halo_t<64, 1, 3, 8, 3>(x, w, bias, addend, y, s, st);
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 5, 3>(x, w, bias, addend, y, s, stats, st);
+  return two ? launch_halo_t<64, 2, 2, 6, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3>(x, w, bias, addend, y, s, stats, st);
 }
 static bool halo_eligible(const ConvShape& s) {
   if (!halo_supported(s)) return false;
@@ -852,17 +874,25 @@ static int fwd_kernel_version() {
   return v;
 }
 
+// number of BN partial rows the fused-statistics epilogue produces for this shape (0: not available, use launch_bn_stats)
+int conv_tc_stats_parts(const ConvShape& s) {
+  if (!conv_tc_supported_fwd(s) || (s.Cout & 3) != 0 || !tma_store_enabled() || fwd_kernel_version() == 1) return 0;
+  if (halo_mode() != 0 && halo_eligible(s)) return s.N * (s.H / 16) * (s.W / 8) * 4;      // items * T * 4 warps (T cancels)
+  int bw, bh, bn;
+  pick_tile(s.H, s.W, &bw, &bh, &bn);
+  return (s.W / bw) * (s.H / bh) * ((s.N + bn - 1) / bn) * 4;
+}
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* stats) {
   FwdParams p;
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
   pick_tile(s.H, s.W, &p.bw, &p.bh, &p.bn);
   p.tiles_w = s.W / p.bw; p.tiles_h = s.H / p.bh;
   p.bias = bias; p.addend = addend; p.y = y;
-  p.sbh = p.sbn = 1; p.tma_store = 0;
+  p.sbh = p.sbn = 1; p.tma_store = 0; p.stats = nullptr;
   const int tiles_n = (s.N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_eligible(s)) return launch_halo(x, w, bias, addend, y, s, st);
+  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_eligible(s)) return launch_halo(x, w, bias, addend, y, s, stats, st);
   CUtensorMap mx, mw;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
   if (r) return r;
@@ -882,6 +912,7 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   // epilogue store path: TMA store of each warp's 32-row slab (needs 16-byte aligned channel rows)
   CUtensorMap my = mx;
   p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
+  p.stats = p.tma_store ? stats : nullptr;
   if (p.tma_store) {
     p.sbh = (32 / p.bw) < p.bh ? (32 / p.bw) : p.bh;
     p.sbn = 32 / (p.bw * p.sbh);

@@ -26,6 +26,8 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess) return fail((int)_e, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
   } while (0)
 
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
 namespace {
 
 struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1; };
@@ -220,6 +222,7 @@ static size_t reduce_scratch_bytes(const sivae_engine* e) {
     size_t a = conv_wgrad_simt_scratch_bytes(s);
     if (a > m) m = a;
     if (conv_tc_supported_wgrad(s)) { size_t t = conv_wgrad_tc_scratch_bytes(s); if (t > m) m = t; }
+    { int parts = conv_tc_stats_parts(s); if (parts > 0) { size_t t = bn_parts_scratch_bytes(parts, cv.cout); if (t > m) m = t; } }
     if (cv.cin <= 4 && conv_narrow_corr_supported(cv.cout, cv.cin, cv.k)) { size_t t = conv_narrow_corr_scratch_bytes(cv.cout, cv.k); if (t > m) m = t; }
     if (cv.cout <= 4 && conv_narrow_corr_supported(cv.cin, cv.cout, cv.k)) { size_t t = conv_narrow_corr_scratch_bytes(cv.cin, cv.k); if (t > m) m = t; }
   };
@@ -355,13 +358,13 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
 }
 // y = conv(x, filt) (+bias) (+addend).  w_master: fp32 filter [Cout][k][k][Cin]; w_tc: its tf32-rounded copy
 static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const float* w_master, const float* w_tc,
-                    const float* bias, const float* addend, float* y, cudaStream_t st) {
+                    const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr) {
   if (fwd_on_narrow(e, s)) {
     ProfScope ps(PC_SIMT_FWD, s, st);
     launch_conv_narrow_in_fwd(x, w_master, bias, addend, y, s, st);
   } else if (fwd_on_tc(e, s)) {
     ProfScope ps(PC_TC_FWD, s, st);
-    int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st);
+    int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats);
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else {
     ProfScope ps(PC_SIMT_FWD, s, st);
@@ -373,6 +376,24 @@ static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, floa
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
   return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st);
+}
+// t = conv(x, W) followed by the BatchNorm batch statistics of t (train) or the running statistics (eval).  On the tensor
+// core path the statistics come out of the conv epilogue (no second pass over t).
+static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, const float* x, float* t, float* mi, int B, int size,
+                         bool train, cudaStream_t st) {
+  ConvShape s{B, size, size, c.cin, c.cout, c.k};
+  const long long rows = (long long)B * size * size;
+  int parts = (train && e->tc && !fwd_on_narrow(e, s) && fwd_on_tc(e, s)) ? conv_tc_stats_parts(s) : 0;
+  if (parts > 0 && bn_parts_scratch_bytes(parts, c.cout) > e->red_bytes) parts = 0;
+  float* sp = parts > 0 ? (float*)e->red : nullptr;
+  TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp));
+  if (parts > 0)
+    launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st);
+  else if (train)
+    launch_bn_stats(t, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, e->red, e->red_bytes, st);
+  else
+    launch_bn_eval_stats(n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, bn.c, mi, st);
+  return 0;
 }
 // dx = conv_transpose(dy, W) (+addend): a forward conv over dy with the packed dgrad filters
 static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
@@ -402,7 +423,6 @@ static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, co
 // -------------------------------------------------------------------------------------------------------------
 // forward passes
 // -------------------------------------------------------------------------------------------------------------
-#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
 
 static int bn_forward_stats(sivae_engine* e, Net& n, const Bn& bn, const float* t, long long rows, float* mi, bool train, cudaStream_t st) {
   if (train)
@@ -419,11 +439,9 @@ static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, c
   const long long rows = (long long)B * s * s;
   const float* idn = x;
   if (b.expand) { TRY(conv_fwd(e, n, b.ce, x, a.id, nullptr, B, s, st)); idn = a.id; }
-  TRY(conv_fwd(e, n, b.c1, x, a.t1, nullptr, B, s, st));
-  bn_forward_stats(e, n, b.bn1, a.t1, rows, a.mi1, train, st);
+  TRY(conv_bn_stats(e, n, b.c1, b.bn1, x, a.t1, a.mi1, B, s, train, st));
   launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->tc, st);
-  TRY(conv_fwd(e, n, b.c2, a.a1, a.t2, nullptr, B, s, st));
-  bn_forward_stats(e, n, b.bn2, a.t2, rows, a.mi2, train, st);
+  TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st));
   launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->tc, st);
   return 0;
 }
@@ -433,8 +451,7 @@ static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, in
   const sivae_config& c = e->cfg;
   const int S = c.image_size;
   p.img = img;
-  TRY(conv_fwd(e, n, n.stem, img, p.t0, nullptr, B, S, st));
-  bn_forward_stats(e, n, n.stem_bn, p.t0, (long long)B * S * S, p.mi0, train, st);
+  TRY(conv_bn_stats(e, n, n.stem, n.stem_bn, img, p.t0, p.mi0, B, S, train, st));
   launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->tc, st);
   const float* x = p.a0;
   for (size_t i = 0; i < n.blocks.size(); ++i) {

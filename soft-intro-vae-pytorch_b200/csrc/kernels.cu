@@ -470,6 +470,35 @@ void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, 
   k_bn_stats_partial<<<nblk, 256, shmem, st>>>(t, rows, C, part, bn_rows_per_block(rows));
   k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, mean_invstd, running_mean, running_var, nbt);
 }
+// coalesced pre-reduction of many partial rows: out[b][i] = sum_{r in slab b} part[r][i], i over 2*C
+__global__ void __launch_bounds__(256) k_parts_reduce(const float* __restrict__ part, float* __restrict__ out, int nparts, int twoC, int slab) {
+  const int r0 = blockIdx.x * slab, r1 = min(nparts, r0 + slab);
+  for (int i = threadIdx.x; i < twoC; i += 256) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += part[(size_t)r * twoC + i];
+    out[(size_t)blockIdx.x * twoC + i] = s;
+  }
+}
+size_t bn_parts_scratch_bytes(int nparts, int C) {
+  return ((size_t)nparts + (size_t)(nparts + 63) / 64) * 2 * C * sizeof(float);
+}
+// part: [nparts][2][C] written by the conv epilogue; the pre-reduced rows are stored right behind it (same scratch)
+void launch_bn_stats_from_parts(float* part, int nparts, long long rows, int C, float* mean_invstd, float* running_mean,
+                                float* running_var, long long* nbt, cudaStream_t st) {
+  const float* src = part;
+  int n = nparts;
+  if (nparts > 512) {
+    const int slab = 64;
+    const int nb = (nparts + slab - 1) / slab;
+    float* out = part + (size_t)nparts * 2 * C;
+    g_launches += 1;
+    k_parts_reduce<<<nb, 256, 0, st>>>(part, out, nparts, 2 * C, slab);
+    src = out;
+    n = nb;
+  }
+  g_launches += 1;
+  k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(src, n, rows, C, mean_invstd, running_mean, running_var, nbt);
+}
 __global__ void k_bn_eval_stats(const float* rm, const float* rv, int C, float* mi) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) { mi[c] = rm[c]; mi[C + c] = rsqrtf(rv[c] + kBnEps); }

@@ -55,7 +55,10 @@ void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int
 bool conv_tc_supported_fwd(const ConvShape& s);
 // returns cudaError / driver error code (0 ok)
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y,
-                       const ConvShape& s, cudaStream_t st);
+                       const ConvShape& s, cudaStream_t st, float* stats = nullptr);
+// fused train-mode BN statistics: if > 0, passing `stats` ([parts][2][Cout] floats) to launch_conv_fwd_tc makes the
+// epilogue emit per-warp column sums / sums of squares; finish with launch_bn_stats_from_parts
+int conv_tc_stats_parts(const ConvShape& s);
 bool conv_tc_supported_wgrad(const ConvShape& s);
 size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s);
 int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
@@ -66,6 +69,9 @@ size_t bn_scratch_bytes(long long rows, int C);
 // batch statistics of t[rows][C] -> mean_invstd[0..C) = mean, [C..2C) = invstd; running-stat EMA + nbt++
 void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, float* running_mean,
                      float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t bn_parts_scratch_bytes(int nparts, int C);
+void launch_bn_stats_from_parts(float* part, int nparts, long long rows, int C, float* mean_invstd, float* running_mean,
+                                float* running_var, long long* nbt, cudaStream_t st);
 // eval-mode: mean_invstd from running stats
 void launch_bn_eval_stats(const float* running_mean, const float* running_var, int C, float* mean_invstd, cudaStream_t st);
 // out = resample(lrelu(bn(t) + identity)); identity may be null. (N,H,W) are the dims of t.
