@@ -179,7 +179,7 @@ def run_ours(args):
     if args.layers and rank == 0:
         buf = C.create_string_buffer(1 << 16)
         lib.sivae_profile_dump(buf, len(buf))
-        names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad"}
+        names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, GB/s)"}
         rows = [l.split() for l in buf.value.decode().splitlines()]
         rows.sort(key=lambda r: -float(r[8]))
         with open(args.layers, "w") as f:
@@ -188,7 +188,7 @@ def run_ours(args):
                 n, ms, gf = int(r[7]), float(r[8]), float(r[9])
                 f.write("| %s | %s | %s | %s | %s | %s | %s | %.1f | %.3f | %.4f | %.1f |\n" % (
                     names[int(r[0])], r[1], r[2], r[3], r[4], r[5], r[6], n / args.steps, ms / args.steps, ms / n, gf / ms if ms > 0 else 0))
-    prof = (C.c_double * 12)()
+    prof = (C.c_double * 15)()
     lib.sivae_profile_read(prof)
     lib.sivae_profile_enable(0)
     launches = lib.sivae_launch_count() - launches0
@@ -218,6 +218,11 @@ def run_ours(args):
                     wgrad=dict(achieved=round(wg_flops / (wg_ms * 1e-3) / 1e12, 2) if wg_ms > 0 else None,
                                ms_per_step=round(wg_ms / args.steps, 3), launches_per_step=wg_n / args.steps),
                     simt_conv_ms_per_step=round(simt_ms / args.steps, 3))
+        if prof[14] > 0 and prof[12] > 0:
+            gbs = prof[13] / (prof[12] * 1e-3) / 1e9
+            roof["loss_pass"] = dict(bound="hbm", kernel="k_mse3_partial (fused 3x per-sample MSE over five images)",
+                                     achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4),
+                                     ms_per_launch=round(prof[12] / prof[14], 4), bytes_per_launch=int(prof[13] / prof[14]))
     line = dict(metric="images/sec per introspective E+D step", value=round(value, 2), unit="images/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_step, 3), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="tf32 operands (fp32 storage, fp32 accumulate, fp32 BN/loss/Adam)", data="synthetic",

@@ -115,7 +115,8 @@ int sivae_last_batch(const sivae_engine* e);
 /* instrumentation for bench.py: number of kernels this library has enqueued so far; optional CUDA-event timing of
    every convolution launch on its stream, summed per kernel class by sivae_profile_read (which synchronises):
    out[class*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches}; class 0 = tcgen05 conv fwd/dgrad,
-   1 = tcgen05 wgrad, 2 = SIMT conv fwd/dgrad, 3 = SIMT wgrad */
+   1 = tcgen05 wgrad, 2 = CUDA-core conv fwd/dgrad, 3 = CUDA-core wgrad, 4 = fused loss pass (the FLOP slot holds
+   its algorithmic BYTES: five images read once); out must hold 15 doubles */
 unsigned long long sivae_launch_count(void);
 int sivae_profile_enable(int on);
 int sivae_profile_read(double* out);

@@ -34,10 +34,11 @@ __global__ void __launch_bounds__(256) k_narrow_in_fwd(const float* __restrict__
   const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, n = tile / (tiles_w * tiles_h);
   const int w0 = tw * NI_TW, h0 = th * NI_TH, pad = KS / 2;
   constexpr int taps = KS * KS;
-  for (int i = threadIdx.x; i < Cout * taps * A; i += 256) {
-    int a = i % A, t = (i / A) % taps, co = i / (A * taps);
-    sw[(t * A + a) * Cout + co] = w[i];
-  }
+  // w is PRE-TRANSPOSED to [tap][a][Cout] (launch_narrow_transpose): straight 128-bit copy.  (Transposing here cost a
+  // 32-way bank-conflicted store + three integer divisions per element in every one of the 8192 blocks: 70 % of the
+  // kernel, profiles/r01g_prof_narrow.md.)
+  for (int i = threadIdx.x; i < (Cout * taps * A) >> 2; i += 256)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
   for (int i = threadIdx.x; i < HTH * HTW * 4; i += 256) {
     int a = i & 3, cx = (i >> 2) % HTW, cy = i / (4 * HTW);
     int hh = h0 + cy - pad, ww = w0 + cx - pad;
@@ -96,11 +97,25 @@ __global__ void __launch_bounds__(256) k_narrow_in_fwd(const float* __restrict__
   }
 }
 
+// wt[tap][a][co] = w[co][tap][a]
+__global__ void k_narrow_transpose(const float* __restrict__ w, float* __restrict__ wt, int Cout, int taps, int A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * taps * A) return;
+  int a = i % A, t = (i / A) % taps, co = i / (A * taps);
+  wt[(t * A + a) * Cout + co] = w[i];
+}
+void launch_narrow_transpose(const float* w, float* wt, int Cout, int k, int A, cudaStream_t st) {
+  g_launches += 1;
+  int n = Cout * k * k * A;
+  k_narrow_transpose<<<cdivu(n, 256), 256, 0, st>>>(w, wt, Cout, k * k, A);
+}
 bool conv_narrow_in_supported(const ConvShape& s) {
   return s.Cin >= 1 && s.Cin <= 4 && s.Cout % 4 == 0 && s.Cout <= 256 && (s.k == 5 || s.k == 3) && s.N * (long long)s.H * s.W > 0;
 }
-void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,
+// wt: the filter transposed to [tap][Cin][Cout] by launch_narrow_transpose
+void launch_conv_narrow_in_fwd(const float* x, const float* wt, const float* bias, const float* addend, float* y,
                                const ConvShape& s, cudaStream_t st) {
+  const float* w = wt;
   g_launches += 1;
   const int HTH = NI_TH + s.k - 1, HTW = NI_TW + s.k - 1;
   size_t shmem = ((size_t)HTH * HTW * 4 + (size_t)s.Cout * s.k * s.k * s.Cin) * sizeof(float);
@@ -133,7 +148,7 @@ struct NarrowCorrCfg {
   static constexpr int HTH = TR + KS - 1, HTW = NC_TW + KS - 1;
   static constexpr size_t SMEM = ((size_t)HTH * HTW * C + (size_t)TR * NC_TW * 4) * sizeof(float);
 };
-template <int C, int KS>
+template <int C, int KS, bool A4>
 __global__ void __launch_bounds__(C* KS) k_narrow_corr(const float* __restrict__ nar, const float* __restrict__ wide,
                                                        float* __restrict__ part, int N, int H, int W, int A) {
   using CF = NarrowCorrCfg<C, KS>;
@@ -171,8 +186,8 @@ __global__ void __launch_bounds__(C* KS) k_narrow_corr(const float* __restrict__
       float win[KS];
 #pragma unroll
       for (int s = 0; s < KS - 1; ++s) win[s + 1] = wrow[s * C];    // preload: after the first shift win[0..KS-2] hold cols 0..KS-2
-#pragma unroll 4
-      for (int px = 0; px < NC_TW; ++px) {
+#pragma unroll
+      for (int px = 0; px < NC_TW; ++px) {          // fully unrolled: the window shift becomes register renaming
 #pragma unroll
         for (int s = 0; s < KS - 1; ++s) win[s] = win[s + 1];
         win[KS - 1] = wrow[(px + KS - 1) * C];
@@ -182,7 +197,7 @@ __global__ void __launch_bounds__(C* KS) k_narrow_corr(const float* __restrict__
           acc[s][0] = fmaf(nv.x, win[s], acc[s][0]);
           acc[s][1] = fmaf(nv.y, win[s], acc[s][1]);
           acc[s][2] = fmaf(nv.z, win[s], acc[s][2]);
-          acc[s][3] = fmaf(nv.w, win[s], acc[s][3]);
+          if (A4) acc[s][3] = fmaf(nv.w, win[s], acc[s][3]);
         }
       }
     }
@@ -217,8 +232,13 @@ template <int C>
 static void launch_corr_t(const float* nar, const float* wide, float* part, int N, int H, int W, int A, int nblk, cudaStream_t st) {
   using CF = NarrowCorrCfg<C, 5>;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_narrow_corr<C, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM); attr = true; }
-  k_narrow_corr<C, 5><<<nblk, CF::THREADS, CF::SMEM, st>>>(nar, wide, part, N, H, W, A);
+  if (!attr) {
+    cudaFuncSetAttribute(k_narrow_corr<C, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM);
+    cudaFuncSetAttribute(k_narrow_corr<C, 5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM);
+    attr = true;
+  }
+  if (A == 4) k_narrow_corr<C, 5, true><<<nblk, CF::THREADS, CF::SMEM, st>>>(nar, wide, part, N, H, W, A);
+  else k_narrow_corr<C, 5, false><<<nblk, CF::THREADS, CF::SMEM, st>>>(nar, wide, part, N, H, W, A);
 }
 void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int N, int H, int W, int A, int C, int k, int mode,
                              bool accumulate, void* scratch, size_t scratch_bytes, cudaStream_t st) {

@@ -30,7 +30,7 @@ static int fail(int code, const std::string& msg) {
 
 namespace {
 
-struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1; };
+struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1, wn_off = -1; };
 struct Bn { int c = 0; long long g_off = -1, b_off = -1, rm_off = -1; int idx = -1; };
 struct Lin { int fin = 0, fout = 0; long long w_off = -1, b_off = -1; };
 struct Block { int inc = 0, outc = 0, size = 0, mode = RS_NONE; bool expand = false; Conv ce, c1, c2; Bn bn1, bn2; };
@@ -122,6 +122,7 @@ static void add_conv(Net& n, const std::string& name, Conv& c, int cin, int cout
   if (bias) add_tensor(n, name + ".bias", SIVAE_T_BIAS, cout, {cout}, &c.b_off);
   c.wd_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
   c.wr_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
+  c.wn_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;     // [tap][narrow][wide] copy for the CUDA-core kernels
 }
 static void add_bn(Net& n, const std::string& name, Bn& b, int c) {
   b.c = c;
@@ -311,7 +312,7 @@ static size_t carve(sivae_engine* e, char* base) {
 // -------------------------------------------------------------------------------------------------------------
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
-enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_COUNT = 4 };
+enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_COUNT = 5 };
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; ConvShape shape; };
 struct Prof {
   bool on = false;
@@ -335,6 +336,13 @@ struct ProfScope {
   }
   ~ProfScope() { if (r) cudaEventRecord(r->b, st); }
 };
+// fused loss pass: `flops` carries the algorithmic BYTES (5 images read once)
+struct ProfLoss {
+  ProfScope ps;
+  ProfLoss(int B, long long per, cudaStream_t st) : ps(PC_LOSS, ConvShape{B, 1, 1, 1, 1, 1}, st) {
+    if (ps.r) ps.r->flops = 5.0 * (double)B * (double)per * 4.0;
+  }
+};
 // which implementation serves a convolution (exact = SIMT-only engine; narrow = cdim-facing CUDA-core kernels)
 static bool fwd_on_tc(const sivae_engine* e, const ConvShape& s) { return e->tc && conv_tc_supported_fwd(s); }
 static bool fwd_on_narrow(const sivae_engine* e, const ConvShape& s) { return e->fast && conv_narrow_in_supported(s); }
@@ -349,6 +357,9 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
     ConvShape sf{1, 8, 8, c.cin, c.cout, c.k};
     if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf))
       launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, (long long)c.cout * c.cin * c.k * c.k, st);
+    // narrow (cdim-facing) kernels read the filter transposed to [tap][narrow][wide]
+    if (fwd_on_narrow(e, sf)) launch_narrow_transpose(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.k, c.cin, st);
+    else if (fwd_on_narrow(e, sd)) launch_narrow_transpose(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.k, c.cout, st);
   };
   if (n.enc) one(n.stem); else one(n.predict);
   for (const Block& b : n.blocks) { one(b.ce); one(b.c1); one(b.c2); }
@@ -358,10 +369,11 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
 }
 // y = conv(x, filt) (+bias) (+addend).  w_master: fp32 filter [Cout][k][k][Cin]; w_tc: its tf32-rounded copy
 static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const float* w_master, const float* w_tc,
-                    const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr) {
-  if (fwd_on_narrow(e, s)) {
+                    const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr,
+                    const float* w_narrow = nullptr) {
+  if (fwd_on_narrow(e, s) && w_narrow) {
     ProfScope ps(PC_SIMT_FWD, s, st);
-    launch_conv_narrow_in_fwd(x, w_master, bias, addend, y, s, st);
+    launch_conv_narrow_in_fwd(x, w_narrow, bias, addend, y, s, st);
   } else if (fwd_on_tc(e, s)) {
     ProfScope ps(PC_TC_FWD, s, st);
     int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats);
@@ -375,7 +387,7 @@ static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const f
 static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, float* y, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
-  return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st);
+  return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st, nullptr, n.derived + c.wn_off);
 }
 // t = conv(x, W) followed by the BatchNorm batch statistics of t (train) or the running statistics (eval).  On the tensor
 // core path the statistics come out of the conv epilogue (no second pass over t).
@@ -386,7 +398,7 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
   int parts = (train && e->tc && !fwd_on_narrow(e, s) && fwd_on_tc(e, s)) ? conv_tc_stats_parts(s) : 0;
   if (parts > 0 && bn_parts_scratch_bytes(parts, c.cout) > e->red_bytes) parts = 0;
   float* sp = parts > 0 ? (float*)e->red : nullptr;
-  TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp));
+  TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp, n.derived + c.wn_off));
   if (parts > 0)
     launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st);
   else if (train)
@@ -398,7 +410,7 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
 // dx = conv_transpose(dy, W) (+addend): a forward conv over dy with the packed dgrad filters
 static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cout, c.cin, c.k};
-  return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st);
+  return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st, nullptr, n.derived + c.wn_off);
 }
 static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
@@ -691,7 +703,7 @@ extern "C" int sivae_e_step(sivae_engine* e, const float* real_nchw, const float
   launch_kl_reparam(E3.ml, eps3, E3.z, E3.kl, B, z, st);
   TRY(dec_forward(e, tn, D4, E3.z, B, true, st));                     // rec_fake
   // losses :563-586
-  launch_mse3(e->real, D2.y, D3.y, D1.y, D4.y, e->mse, B, per, e->red, e->red_bytes, st);
+  { ProfLoss pl(B, per, st); launch_mse3(e->real, D2.y, D3.y, D1.y, D4.y, e->mse, B, per, e->red, e->red_bytes, st); }
   launch_e_loss_finalize(e->mse, E1.kl, E2.kl, E3.kl, B, hp->beta_kl, hp->beta_rec, hp->beta_neg, hp->scale, stats,
                          e->coef, e->ckl_a, e->ckl_b, st);
   const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
@@ -741,7 +753,7 @@ extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper
   launch_kl_reparam(E5.ml, eps5, E5.z, E5.kl, B, z, st);
   TRY(dec_forward(e, tn, D7, E4.z, B, true, st));                     // rec_rec :607
   TRY(dec_forward(e, tn, D8, E5.z, B, true, st));                     // rec_fake :608
-  launch_mse3(e->real, D6.y, D7.y, D5.y, D8.y, e->mse, B, per, e->red, e->red_bytes, st);
+  { ProfLoss pl(B, per, st); launch_mse3(e->real, D6.y, D7.y, D5.y, D8.y, e->mse, B, per, e->red, e->red_bytes, st); }
   launch_d_loss_finalize(e->mse, E4.kl, E5.kl, B, hp->beta_kl, hp->beta_rec, hp->gamma_r, hp->scale, stats, st);
   const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
   const float a_t = hp->scale * hp->gamma_r * hp->beta_rec / (float)B;     // 2 * (scale * gamma_r/2 * beta_rec / B)
@@ -922,6 +934,18 @@ extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void
 }
 
 // ---- single-kernel entry points ------------------------------------------------------------------------------
+// library-owned scratch for the transposed narrow filter of the single-kernel test entry points (the engine keeps its
+// own copy in the workspace)
+static float* narrow_scratch(size_t floats) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    if (buf) cudaFree(buf);
+    if (cudaMalloc(&buf, floats * sizeof(float)) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
+    cap = floats;
+  }
+  return buf;
+}
 // backend: SIVAE_CONV_SIMT = generic exact fp32 kernel; SIVAE_CONV_TCGEN05 = tensor-core kernel or error -7;
 // SIVAE_CONV_AUTO = what the engine would pick for this shape (narrow CUDA-core kernel, tensor core, generic)
 extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y, int N, int H,
@@ -934,7 +958,14 @@ extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bia
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (backend == SIVAE_CONV_AUTO) {
     sivae_engine tmp; tmp.tc = tmp.fast = true;
-    TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st));
+    const float* wn = nullptr;
+    if (fwd_on_narrow(&tmp, s)) {
+      float* buf = narrow_scratch((size_t)Cout * Cin * k * k);
+      if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
+      launch_narrow_transpose(w, buf, Cout, k, Cin, st);
+      wn = buf;
+    }
+    TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st, nullptr, wn));
   } else {
     launch_conv_fwd_simt(x, w, bias, addend, y, s, st);
   }
@@ -956,7 +987,14 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
     int r = launch_conv_fwd_tc(dy, wd, nullptr, addend, dx, s, st);
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (backend == SIVAE_CONV_AUTO) {
-    TRY(conv_any(&tmp, s, dy, wd, wd, nullptr, addend, dx, st));
+    const float* wn = nullptr;
+    if (fwd_on_narrow(&tmp, s)) {
+      float* buf = narrow_scratch((size_t)Cout * Cin * k * k);
+      if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
+      launch_narrow_transpose(wd, buf, Cin, k, Cout, st);
+      wn = buf;
+    }
+    TRY(conv_any(&tmp, s, dy, wd, wd, nullptr, addend, dx, st, nullptr, wn));
   } else {
     launch_conv_fwd_simt(dy, wd, nullptr, addend, dx, s, st);
   }

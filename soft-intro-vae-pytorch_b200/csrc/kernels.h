@@ -43,7 +43,9 @@ void launch_colsum(const float* in, float* out, long long rows, int C, bool accu
 
 // ---------------- cdim-facing 5x5 convolutions on CUDA cores (conv_narrow.cu) ----------------
 bool conv_narrow_in_supported(const ConvShape& s);            // Cin <= 4: stem forward, predict dgrad
-void launch_conv_narrow_in_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y,
+// wt = filter transposed to [tap][Cin][Cout] (launch_narrow_transpose of the [Cout][tap][Cin] filter)
+void launch_narrow_transpose(const float* w, float* wt, int Cout, int k, int A, cudaStream_t st);
+void launch_conv_narrow_in_fwd(const float* x, const float* wt, const float* bias, const float* addend, float* y,
                                const ConvShape& s, cudaStream_t st);
 bool conv_narrow_corr_supported(int wideC, int narrowA, int k);
 size_t conv_narrow_corr_scratch_bytes(int wideC, int k);
