@@ -625,6 +625,8 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUt
 // T = 2 vertically stacked 16x8 pixel tiles share every B (filter) tile, halving filter traffic as well.
 // Two rings: A (halo, consumed for a whole chunk = 9 taps) and B (one filter tap x 32 channels).
 // ---------------------------------------------------------------------------------------------------------------
+static int fwd_kernel_version();
+static bool fwd_kernel_version_is2() { return fwd_kernel_version() != 1; }
 static bool tma_store_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -653,10 +655,11 @@ struct HaloParams {
   float* y;
   float* stats;                // BN partial sums [m_items*T*4][2][Cout] or null
 };
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 struct HaloSmem {
-  static constexpr int ROWS = 16 * T + KS - 1;
-  static constexpr int A_BYTES = ROWS * 16 * 128;
+  static constexpr int ROWS = 16 * T + KH - 1;
+  static constexpr int BW = (KW == 1) ? 8 : 16;      // box width in pixels (8 output columns + column halo)
+  static constexpr int A_BYTES = ROWS * BW * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
   static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;     // 4 x 4 KB epilogue staging tiles
@@ -665,13 +668,13 @@ struct HaloSmem {
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CUtensorMap map_x,
                                                       const __grid_constant__ CUtensorMap map_w,
                                                       const __grid_constant__ CUtensorMap map_y, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KS>;
-  constexpr int TAPS = KS * KS, PAD = KS / 2;
+  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW>;
+  constexpr int TAPS = KH * KW, PADH = KH / 2, PADW = KW / 2, BW = SM::BW;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* a_empty = a_full + A_STAGES;
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
             const int st = ai % A_STAGES;
             mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
             mbar_expect_tx(&a_full[st], SM::A_BYTES);
-            tma_load_4d(smem + st * SM::A_BYTES, &map_x, &a_full[st], ch << 5, w0 - PAD, h0 - PAD, n);
+            tma_load_4d(smem + st * SM::A_BYTES, &map_x, &a_full[st], ch << 5, w0 - PADW, h0 - PADH, n);
             ++ai;
           }
           for (int tap = 0; tap < TAPS; ++tap, ++bi) {
@@ -740,14 +743,14 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
-            const int r = tap / KS, s = tap - KS * r;
+            const int r = tap / KW, s = tap - KW * r;
             const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const uint32_t arow = sa + (uint32_t)(((16 * t + r) * 16 + s) * 128);
+              const uint32_t arow = sa + (uint32_t)(((16 * t + r) * BW + s) * 128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                uint64_t ad = make_smem_desc_bo(arow + k * 32, 2048, bo);
+                uint64_t ad = make_smem_desc_bo(arow + k * 32, BW * 128, bo);
                 uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
                 umma_tf32(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
               }
@@ -815,14 +818,14 @@ static int halo_mode() {
 static bool halo_supported(const ConvShape& s) {
   return (s.k == 3 || s.k == 5) && s.Cin % 32 == 0 && s.Cout >= 1 && s.W % 8 == 0 && s.H % 16 == 0;
 }
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KS>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                          float* stats, cudaStream_t st) {
-  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KS>;
+  using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -836,9 +839,9 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
   p.stats = p.tma_store ? stats : nullptr;
   CUtensorMap mx, mw, my;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, SM::ROWS, 1);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
   if (r) return r;
-  r = make_map_2d(&mw, w, s.Cout, (long long)KS * KS * s.Cin, BLOCK_N);
+  r = make_map_2d(&mw, w, s.Cout, (long long)KH * KW * s.Cin, BLOCK_N);
   if (r) return r;
   my = mx;
   if (p.tma_store) {
@@ -847,18 +850,164 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   }
   const int grid = p.total < num_sms() ? p.total : num_sms();
   g_launches += 1;
-  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KS><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p);
+  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p);
   return (int)cudaGetLastError();
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        float* stats, cudaStream_t st) {
   const bool two = (s.H % 32 == 0);
   if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
-    return two ? launch_halo_t<32, 2, 2, 8, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5>(x, w, bias, addend, y, s, stats, st);
+    return two ? launch_halo_t<32, 2, 2, 8, 5, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5, 5>(x, w, bias, addend, y, s, stats, st);
   }
-  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 5, 3>(x, w, bias, addend, y, s, stats, st);
-  return two ? launch_halo_t<64, 2, 2, 6, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 5, 3, 3>(x, w, bias, addend, y, s, stats, st);
+  return two ? launch_halo_t<64, 2, 2, 6, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3, 3>(x, w, bias, addend, y, s, stats, st);
 }
+// ---------------------------------------------------------------------------------------------------------------
+// Row-separable form of the two image-facing 5x5 convolutions (c = cdim <= 3 channels on one side).
+// A 5x5 conv with a c-channel side wastes the tensor core (K or N of 3) and, as a direct CUDA-core kernel, sits at
+// ~28 TFLOP/s (profiles/r01f_layers_H.md: 0.72-1.05 ms per launch at 256x256).  Both directions become a 5x1 (rows only)
+// implicit GEMM for the halo kernel above plus one cheap streaming pass:
+//   narrow INPUT  (stem forward, predict dgrad):  xe[n,h,w,j] = x[n,h,w-2+j/c, j%c]  (j < 5c, zero-padded to 32 channels:
+//       in NHWC the 5-pixel window of a c-channel row is 5c CONTIGUOUS floats), then  y = conv5x1(xe, We),
+//       We[co][r][j] = F[co][r][j/c][j%c]  -- again 5c contiguous floats of the original filter.
+//   narrow OUTPUT (predict forward, stem dgrad):  P = conv5x1(x, Wg) with 16 output columns (s, co),
+//       Wg[s*c+co][r][ci] = F[co][r][s][ci],  then  y[n,h,w,co] = bias + addend + sum_s P[n,h,w+s-2, s*c+co].
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rs_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+// rev = 1: mirrored column shift, xe[n,h,w,s*c+ch] = x[n,h,w+2-s,ch] (the dP/dy expansion used by the predict wgrad)
+__global__ void k_rowsep_expand_rev(const float* __restrict__ x, float* __restrict__ xe, long long rows, int W, int c) {
+  const long long total = rows * W * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int w = (int)(pix % W);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;
+      const int s = j / c, ch = j - s * c;
+      const int ws = w + 2 - s;
+      v[e] = (j < 5 * c && ws >= 0 && ws < W) ? rs_tf32(__ldg(x + (pix + 2 - s) * c + ch)) : 0.f;
+    }
+    *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+__global__ void k_rowsep_expand(const float* __restrict__ x, float* __restrict__ xe, long long rows, int W, int c) {
+  // one thread per (pixel, channel quad): 8 threads cover the 32 expanded channels of a pixel
+  const long long total = rows * W * 8;
+  const int rowlen = W * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int w = (int)(pix % W);
+    const long long row = pix / W;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q * 4 < 5 * c) {
+      const float* src = x + row * rowlen;
+      const int j0 = (w - 2) * c + q * 4;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + e;
+        v[e] = (q * 4 + e < 5 * c && j >= 0 && j < rowlen) ? rs_tf32(__ldg(src + j)) : 0.f;
+      }
+      o = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = o;
+  }
+}
+__global__ void k_rowsep_gather(const float* __restrict__ P, const float* __restrict__ bias, const float* __restrict__ addend,
+                                float* __restrict__ y, long long rows, int W, int c) {
+  const long long total = rows * W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(pix % W);
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const int ws = w + s - 2;
+      if (ws < 0 || ws >= W) continue;
+      const float* src = P + (pix + s - 2) * 16 + s * c;
+      for (int co = 0; co < c; ++co) acc[co] += __ldg(src + co);
+    }
+    for (int co = 0; co < c; ++co) {
+      float v = acc[co];
+      if (bias) v += __ldg(bias + co);
+      if (addend) v += addend[pix * c + co];
+      y[pix * c + co] = v;
+    }
+  }
+}
+// F[Co][5][5][c] -> We[Co][5][32] (tf32-rounded, zero padded)
+__global__ void k_rowsep_filter_expand(const float* __restrict__ f, float* __restrict__ out, int Co, int c) {
+  const int total = Co * 5 * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i & 31, cr = i >> 5;
+    out[i] = j < 5 * c ? rs_tf32(f[(long long)cr * 5 * c + j]) : 0.f;
+  }
+}
+// F[c][5][5][Ci] -> Wg[16][5][Ci]: row s*c+co, (tf32-rounded, unused rows zero)
+__global__ void k_rowsep_filter_gather(const float* __restrict__ f, float* __restrict__ out, int c, int Ci) {
+  const int total = 16 * 5 * Ci;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Ci, r = (i / Ci) % 5, row = i / (5 * Ci);
+    float v = 0.f;
+    if (row < 5 * c) {
+      const int s = row / c, co = row - s * c;
+      v = rs_tf32(f[(((long long)co * 5 + r) * 5 + s) * Ci + ci]);
+    }
+    out[i] = v;
+  }
+}
+static bool rowsep_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_ROWSEP");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0 && halo_mode() != 0 && tma_store_enabled() && fwd_kernel_version_is2();
+}
+bool conv_rowsep_in_supported(const ConvShape& s) {
+  return rowsep_enabled() && s.k == 5 && s.Cin >= 1 && s.Cin <= 3 && s.Cout >= 32 && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0;
+}
+bool conv_rowsep_out_supported(const ConvShape& s) {
+  return rowsep_enabled() && s.k == 5 && s.Cout >= 1 && s.Cout <= 3 && s.Cin % 32 == 0 && s.W % 8 == 0 && s.H % 16 == 0;
+}
+long long conv_rowsep_scratch_floats(const ConvShape& s) { return (long long)s.N * s.H * s.W * 32; }
+long long conv_rowsep_filter_floats(const ConvShape& s) { return s.Cin <= 3 ? (long long)s.Cout * 160 : (long long)80 * s.Cin; }
+void launch_rowsep_filter_expand(const float* f, float* out, int Co, int c, cudaStream_t st) {
+  g_launches += 1;
+  k_rowsep_filter_expand<<<(Co * 160 + 255) / 256, 256, 0, st>>>(f, out, Co, c);
+}
+void launch_rowsep_filter_gather(const float* f, float* out, int c, int Ci, cudaStream_t st) {
+  g_launches += 1;
+  k_rowsep_filter_gather<<<(80 * Ci + 255) / 256, 256, 0, st>>>(f, out, c, Ci);
+}
+// y[N,H,W,Cout] = conv5x5(x[N,H,W,c], F) (+bias)(+addend); we = expanded filter; scratch >= N*H*W*32 floats
+int launch_conv_rowsep_in(const float* x, const float* we, const float* bias, const float* addend, float* y, const ConvShape& s,
+                          float* scratch, float* stats, cudaStream_t st) {
+  const long long rows = (long long)s.N * s.H;
+  g_launches += 1;
+  k_rowsep_expand<<<num_sms() * 8, 256, 0, st>>>(x, scratch, rows, s.W, s.Cin);
+  ConvShape e{s.N, s.H, s.W, 32, s.Cout, 5};
+  if (s.H % 32 == 0) return launch_halo_t<64, 2, 2, 6, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
+  return launch_halo_t<64, 1, 3, 8, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
+}
+// y[N,H,W,c] = conv5x5(x[N,H,W,Cin], F) (+bias)(+addend); wg = gather-form filter; scratch >= N*H*W*16 floats
+int launch_conv_rowsep_out(const float* x, const float* wg, const float* bias, const float* addend, float* y, const ConvShape& s,
+                           float* scratch, cudaStream_t st) {
+  ConvShape e{s.N, s.H, s.W, s.Cin, 16, 5};
+  int r = (s.H % 32 == 0) ? launch_halo_t<32, 2, 2, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st)
+                          : launch_halo_t<32, 1, 3, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st);
+  if (r) return r;
+  g_launches += 1;
+  k_rowsep_gather<<<num_sms() * 8, 256, 0, st>>>(scratch, bias, addend, y, (long long)s.N * s.H, s.W, s.Cout);
+  return (int)cudaGetLastError();
+}
+
 static bool halo_eligible(const ConvShape& s) {
   if (!halo_supported(s)) return false;
   if (s.k == 5) return s.Cout <= 32;          // wide 5x5 outputs do not occur in this model
@@ -876,6 +1025,7 @@ static int fwd_kernel_version() {
 
 // number of BN partial rows the fused-statistics epilogue produces for this shape (0: not available, use launch_bn_stats)
 int conv_tc_stats_parts(const ConvShape& s) {
+  if (conv_rowsep_in_supported(s)) return s.N * (s.H / 16) * (s.W / 8) * 4;
   if (!conv_tc_supported_fwd(s) || (s.Cout & 3) != 0 || !tma_store_enabled() || fwd_kernel_version() == 1) return 0;
   if (halo_mode() != 0 && halo_eligible(s)) return s.N * (s.H / 16) * (s.W / 8) * 4;      // items * T * 4 warps (T cancels)
   int bw, bh, bn;
@@ -1146,23 +1296,27 @@ struct Wg2Params {
   long long items_total, items_per_split;
   float* part;                 // [splits][Cout][Ktot]
 };
-constexpr int WG2_X_BYTES = 18 * 16 * 128;     // x halo box
 constexpr int WG2_DY_BYTES = 16 * 8 * 128;     // dy box (32 channels)
-template <int N_TILE, int G, int STAGES>
+// KH x KW taps: 3x3 for the residual blocks; 5x1 for the row-separable image-facing convs (x = row-expanded 32-channel
+// image, only MN chunk 0 is a real tap there -- chunks 1..3 are phantoms that cost tensor time but no extra traffic)
+template <int N_TILE, int G, int STAGES, int KH, int KW>
 struct Wg2Smem {
-  static constexpr int A_BYTES = G * WG2_X_BYTES;
+  static constexpr int BW = (KW == 1) ? 8 : 16;
+  static constexpr int X_BYTES = (16 + KH - 1) * BW * 128;     // x halo box
+  static constexpr int A_BYTES = G * X_BYTES;
   static constexpr int B_BYTES = (N_TILE / 32) * WG2_DY_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
-  static constexpr int TMEM_COLS = (G * 3 * N_TILE) <= 128 ? 128 : ((G * 3 * N_TILE) <= 256 ? 256 : 512);
+  static constexpr int TMEM_COLS = (G * KH * N_TILE) <= 128 ? 128 : ((G * KH * N_TILE) <= 256 ? 256 : 512);
 };
-template <int N_TILE, int G, int STAGES>
+template <int N_TILE, int G, int STAGES, int KH, int KW>
 __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constant__ CUtensorMap map_x,
                                                             const __grid_constant__ CUtensorMap map_dy, const Wg2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  using SM = Wg2Smem<N_TILE, G, STAGES>;
-  static_assert(G * 3 * N_TILE <= 512, "TMEM budget");
+  using SM = Wg2Smem<N_TILE, G, STAGES, KH, KW>;
+  static_assert(G * KH * N_TILE <= 512, "TMEM budget");
+  constexpr int WG2_X_BYTES = SM::X_BYTES, BW = SM::BW;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* empty = full + STAGES;
@@ -1204,7 +1358,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
         const int w0 = tw * 8, h0 = th * 16;
         uint8_t* sa = smem + st * SM::STAGE_BYTES;
         for (int g = 0; g < G; ++g)
-          tma_load_4d(sa + g * WG2_X_BYTES, &map_x, &full[st], (cg * G + g) * 32, w0 - 1, h0 - 1, n);
+          tma_load_4d(sa + g * WG2_X_BYTES, &map_x, &full[st], (cg * G + g) * 32, w0 - KW / 2, h0 - KH / 2, n);
         uint8_t* sb = sa + SM::A_BYTES;
         for (int j = 0; j < b_chunks; ++j)
           tma_load_4d(sb + j * WG2_DY_BYTES, &map_dy, &full[st], col0 + 32 * j, w0, h0, n);
@@ -1222,12 +1376,12 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
 #pragma unroll
         for (int g = 0; g < G; ++g) {
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const uint32_t tmem_d = tmem_base + (uint32_t)((g * 3 + r) * N_TILE);
+          for (int r = 0; r < KH; ++r) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)((g * KH + r) * N_TILE);
 #pragma unroll 4
             for (int h = 0; h < 16; ++h) {
               // A: x halo rows (h + r) * 16 + w; MN chunks = filter columns s, 128 B (one pixel) apart; K atoms 512 B
-              uint64_t ad = make_smem_desc(sa + g * WG2_X_BYTES + (uint32_t)((h + r) * 16 * 128), 128, 512, 1);
+              uint64_t ad = make_smem_desc(sa + g * WG2_X_BYTES + (uint32_t)((h + r) * BW * 128), 128, 512, 1);
               // B: dy rows h * 8 + w; MN chunks = 32-channel boxes
               uint64_t bd = make_smem_desc(sb + (uint32_t)(h * 8 * 128), WG2_DY_BYTES, 512, 1);
               umma_tf32(tmem_d, ad, bd, idesc, (i > 0 || h > 0) ? 1u : 0u);
@@ -1245,20 +1399,20 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
       mbar_wait(tmem_full, 0);
       tc_fence_after();
     }
-    if (q < 3) {
+    if (q < KW) {
       float* dst = p.part + (long long)blockIdx.z * p.Cout * p.Ktot;
 #pragma unroll 1
       for (int g = 0; g < G; ++g) {
         const int ci = (cg * G + g) * 32 + lane;
 #pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-          const int kidx = (r * 3 + q) * p.Cin + ci;
+        for (int r = 0; r < KH; ++r) {
+          const int kidx = (r * KW + q) * p.Cin + ci;
 #pragma unroll 1
           for (int c = 0; c < N_TILE; c += 32) {
             if (col0 + c >= p.Cout) break;
             uint32_t v[32];
             if (num_items > 0) {
-              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * 3 + r) * N_TILE + c), v);
+              tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g * KH + r) * N_TILE + c), v);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = 0u;
@@ -1305,29 +1459,29 @@ static Wg2Plan wg2_plan(const ConvShape& s) {
   return pl;
 }
 static size_t wg2_scratch_bytes(const ConvShape& s) { return (size_t)wg2_plan(s).splits * s.Cout * s.ktot() * sizeof(float); }
-template <int N_TILE, int G, int STAGES>
+template <int N_TILE, int G, int STAGES, int KH = 3, int KW = 3>
 static int launch_wg2_t(const float* x, const float* dy, const ConvShape& s, const Wg2Plan& pl, float* part, cudaStream_t st) {
-  using SM = Wg2Smem<N_TILE, G, STAGES>;
+  using SM = Wg2Smem<N_TILE, G, STAGES, KH, KW>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_halo<N_TILE, G, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_halo<N_TILE, G, STAGES, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
   Wg2Params p;
-  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.Ktot = (int)s.ktot();
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.Ktot = KH * KW * s.Cin;
   p.tiles_w = s.W / 8; p.tiles_h = s.H / 16;
   p.items_total = pl.items; p.items_per_split = pl.per;
   p.part = part;
   CUtensorMap mx, mdy;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, 18, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, 16 + KH - 1, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (r) return r;
   r = make_map_nhwc(&mdy, dy, s.N, s.H, s.W, s.Cout, 8, 16, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (r) return r;
   dim3 grid(pl.cgroups, pl.ntiles, pl.splits);
   g_launches += 2;
-  k_conv_wgrad_halo<N_TILE, G, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
+  k_conv_wgrad_halo<N_TILE, G, STAGES, KH, KW><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
   return (int)cudaGetLastError();
 }
 
@@ -1370,6 +1524,64 @@ int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvS
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (blocks > 148u * 8) blocks = 148u * 8;
   k_wg_reduce<<<blocks, 256, 0, st>>>(p.part, dw, n, splits, accumulate ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad of the row-separable image-facing convs: the 5x1 halo kernel over (A side = row-expanded narrow tensor with its
+// 4-row halo, B side = the wide tensor), then one reduce that folds the split partials T[wide][5][32] into dW[Cout][5][5][Cin]:
+//   mode 1 (stem,    narrow = x, wide = dy):   dW[co][r][s][ci] += T[co][r][s*c+ci]
+//   mode 0 (predict, narrow = dy, wide = x):   dW[co][r][s][ci] += T[ci][4-r][s*c+co]     (mirrored expansion, see above)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_rowsep_wg_reduce(const float* __restrict__ part, float* __restrict__ dw, int splits, int c, int wide, int mode,
+                                   int accumulate) {
+  const int total = c * 25 * wide;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    long long t;
+    if (mode == 1) {            // dw index: ((co*5 + r)*5 + s)*c + ci  = co*25c + r*5c + j
+      const int j = i % (5 * c), r = (i / (5 * c)) % 5, co = i / (25 * c);
+      t = ((long long)co * 5 + r) * 32 + j;
+    } else {                    // dw index: ((co*5 + r)*5 + s)*wide + ci
+      const int ci = i % wide, s = (i / wide) % 5, r = (i / (5 * wide)) % 5, co = i / (25 * wide);
+      t = ((long long)ci * 5 + (4 - r)) * 32 + s * c + co;
+    }
+    const long long stride = (long long)wide * 160;
+    float acc = 0.f;
+    for (int k = 0; k < splits; ++k) acc += part[k * stride + t];
+    dw[i] = accumulate ? dw[i] + acc : acc;
+  }
+}
+static Wg2Plan rowsep_wg_plan(int N, int H, int W, int wide) {
+  Wg2Plan pl;
+  pl.n_tile = 64; pl.g = 1; pl.cgroups = 1;
+  pl.ntiles = (wide + 63) / 64;
+  pl.items = (long long)N * (H / 16) * (W / 8);
+  long long want = (num_sms() + pl.ntiles - 1) / pl.ntiles;
+  if (want > pl.items) want = pl.items;
+  if (want < 1) want = 1;
+  pl.per = (pl.items + want - 1) / want;
+  pl.splits = (int)((pl.items + pl.per - 1) / pl.per);
+  return pl;
+}
+bool conv_rowsep_wgrad_supported(int H, int W, int c, int wide, int k) {
+  return rowsep_enabled() && wgrad_halo_mode() != 0 && k == 5 && c >= 1 && c <= 3 && wide % 32 == 0 && W % 8 == 0 && H % 16 == 0;
+}
+size_t conv_rowsep_wgrad_scratch_bytes(int N, int H, int W, int wide) {
+  return (size_t)rowsep_wg_plan(N, H, W, wide).splits * wide * 160 * sizeof(float);
+}
+int launch_conv_rowsep_wgrad(const float* narrow_t, const float* wide_t, float* dw, int N, int H, int W, int c, int wide, int mode,
+                             bool accumulate, float* expand_scratch, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+  Wg2Plan pl = rowsep_wg_plan(N, H, W, wide);
+  if (scratch_bytes < (size_t)pl.splits * wide * 160 * sizeof(float)) return -103;
+  const long long rows = (long long)N * H;
+  g_launches += 2;
+  if (mode == 1) k_rowsep_expand<<<num_sms() * 8, 256, 0, st>>>(narrow_t, expand_scratch, rows, W, c);
+  else k_rowsep_expand_rev<<<num_sms() * 8, 256, 0, st>>>(narrow_t, expand_scratch, rows, W, c);
+  ConvShape e{N, H, W, 32, wide, 5};
+  int r = launch_wg2_t<64, 1, 4, 5, 1>(expand_scratch, wide_t, e, pl, (float*)scratch, st);
+  if (r) return r;
+  const int total = c * 25 * wide;
+  k_rowsep_wg_reduce<<<(total + 255) / 256, 256, 0, st>>>((const float*)scratch, dw, pl.splits, c, wide, mode, accumulate ? 1 : 0);
   return (int)cudaGetLastError();
 }
 

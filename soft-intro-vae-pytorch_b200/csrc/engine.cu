@@ -30,7 +30,7 @@ static int fail(int code, const std::string& msg) {
 
 namespace {
 
-struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1, wn_off = -1; };
+struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1, wn_off = -1, wg_off = -1; };
 struct Bn { int c = 0; long long g_off = -1, b_off = -1, rm_off = -1; int idx = -1; };
 struct Lin { int fin = 0, fout = 0; long long w_off = -1, b_off = -1; };
 struct Block { int inc = 0, outc = 0, size = 0, mode = RS_NONE; bool expand = false; Conv ce, c1, c2; Bn bn1, bn2; };
@@ -93,6 +93,7 @@ struct sivae_engine {
   float *d_rec = nullptr, *d_rec_rec = nullptr, *d_rec_fake = nullptr, *d_fake = nullptr;
   float *dml = nullptr, *dz = nullptr, *dfeat = nullptr, *dfeat2 = nullptr, *coef = nullptr, *ckl_a = nullptr, *ckl_b = nullptr, *mse = nullptr;
   float *out_tmp = nullptr;
+  float *rs = nullptr;             // scratch of the row-separable image-facing convs (B*S*S*32 floats)
   void* red = nullptr; size_t red_bytes = 0;
   int cur_batch = 0;
   bool have_e_state = false;
@@ -122,7 +123,12 @@ static void add_conv(Net& n, const std::string& name, Conv& c, int cin, int cout
   if (bias) add_tensor(n, name + ".bias", SIVAE_T_BIAS, cout, {cout}, &c.b_off);
   c.wd_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
   c.wr_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
-  c.wn_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;     // [tap][narrow][wide] copy for the CUDA-core kernels
+  // narrow-side filter forms: wn = [tap][narrow][wide] (CUDA-core kernels) or the row-expanded [wide][5][32] form;
+  // wg = the 16-row gather form [16][5][wide] of the row-separable tensor-core path (conv_tc.cu)
+  const bool narrow = (cin <= 4 || cout <= 4) && k == 5;
+  const long long wide = cin > cout ? cin : cout;
+  c.wn_off = n.derived_floats; n.derived_floats += narrow ? wide * 160 : (long long)cout * cin * k * k;
+  if (narrow) { c.wg_off = n.derived_floats; n.derived_floats += wide * 80; }
 }
 static void add_bn(Net& n, const std::string& name, Bn& b, int c) {
   b.c = c;
@@ -224,6 +230,10 @@ static size_t reduce_scratch_bytes(const sivae_engine* e) {
     if (a > m) m = a;
     if (conv_tc_supported_wgrad(s)) { size_t t = conv_wgrad_tc_scratch_bytes(s); if (t > m) m = t; }
     { int parts = conv_tc_stats_parts(s); if (parts > 0) { size_t t = bn_parts_scratch_bytes(parts, cv.cout); if (t > m) m = t; } }
+    if ((cv.cin <= 3 || cv.cout <= 3) && cv.k == 5) {
+      const int wide = cv.cin > cv.cout ? cv.cin : cv.cout, c = cv.cin > cv.cout ? cv.cout : cv.cin;
+      if (conv_rowsep_wgrad_supported(size, size, c, wide, cv.k)) { size_t t = conv_rowsep_wgrad_scratch_bytes((int)B, size, size, wide); if (t > m) m = t; }
+    }
     if (cv.cin <= 4 && conv_narrow_corr_supported(cv.cout, cv.cin, cv.k)) { size_t t = conv_narrow_corr_scratch_bytes(cv.cout, cv.k); if (t > m) m = t; }
     if (cv.cout <= 4 && conv_narrow_corr_supported(cv.cin, cv.cout, cv.k)) { size_t t = conv_narrow_corr_scratch_bytes(cv.cin, cv.k); if (t > m) m = t; }
   };
@@ -299,6 +309,7 @@ static size_t carve(sivae_engine* e, char* base) {
   long long img = B * S * S * c.cdim;
   e->d_rec = bp.take<float>(img); e->d_rec_rec = bp.take<float>(img); e->d_rec_fake = bp.take<float>(img); e->d_fake = bp.take<float>(img);
   e->out_tmp = bp.take<float>(img);
+  e->rs = bp.take<float>(B * S * S * 32);        // row-expanded image / 16-column partial image of the row-separable convs
   e->dml = bp.take<float>(B * 2 * z); e->dz = bp.take<float>(B * z);
   e->dfeat = bp.take<float>(B * e->feat); e->dfeat2 = bp.take<float>(B * e->feat);
   e->coef = bp.take<float>(4 * B); e->ckl_a = bp.take<float>(B); e->ckl_b = bp.take<float>(B); e->mse = bp.take<float>(3 * B);
@@ -345,23 +356,32 @@ struct ProfLoss {
 };
 // which implementation serves a convolution (exact = SIMT-only engine; narrow = cdim-facing CUDA-core kernels)
 static bool fwd_on_tc(const sivae_engine* e, const ConvShape& s) { return e->tc && conv_tc_supported_fwd(s); }
-static bool fwd_on_narrow(const sivae_engine* e, const ConvShape& s) { return e->fast && conv_narrow_in_supported(s); }
+static bool fwd_on_rowsep_in(const sivae_engine* e, const ConvShape& s) { return e->tc && e->fast && e->rs && conv_rowsep_in_supported(s); }
+static bool fwd_on_rowsep_out(const sivae_engine* e, const ConvShape& s) { return e->tc && e->fast && e->rs && conv_rowsep_out_supported(s); }
+static bool fwd_on_narrow(const sivae_engine* e, const ConvShape& s) { return e->fast && !fwd_on_rowsep_in(e, s) && conv_narrow_in_supported(s); }
 
 static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
   if (!n.dirty) return 0;
-  auto one = [&](const Conv& c) {
+  auto one = [&](const Conv& c, int size = 8) {
     if (c.k == 0) return;
     // dgrad filters (a dgrad is a forward conv over dy): rounded to tf32 only when the tensor core consumes them
-    ConvShape sd{1, 8, 8, c.cout, c.cin, c.k};
+    ConvShape sd{1, size, size, c.cout, c.cin, c.k};
     launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, fwd_on_tc(e, sd) && !fwd_on_narrow(e, sd), st);
-    ConvShape sf{1, 8, 8, c.cin, c.cout, c.k};
+    ConvShape sf{1, size, size, c.cin, c.cout, c.k};
     if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf))
       launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, (long long)c.cout * c.cin * c.k * c.k, st);
     // narrow (cdim-facing) kernels read the filter transposed to [tap][narrow][wide]
     if (fwd_on_narrow(e, sf)) launch_narrow_transpose(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.k, c.cin, st);
     else if (fwd_on_narrow(e, sd)) launch_narrow_transpose(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.k, c.cout, st);
+    // row-separable tensor-core forms of the image-facing 5x5 convs
+    if (fwd_on_rowsep_in(e, sf)) launch_rowsep_filter_expand(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.cin, st);
+    else if (fwd_on_rowsep_in(e, sd)) launch_rowsep_filter_expand(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.cout, st);
+    if (c.wg_off >= 0) {
+      if (fwd_on_rowsep_out(e, sf)) launch_rowsep_filter_gather(n.params + c.w_off, n.derived + c.wg_off, c.cout, c.cin, st);
+      else if (fwd_on_rowsep_out(e, sd)) launch_rowsep_filter_gather(n.derived + c.wd_off, n.derived + c.wg_off, c.cin, c.cout, st);
+    }
   };
-  if (n.enc) one(n.stem); else one(n.predict);
+  if (n.enc) one(n.stem, e->cfg.image_size); else one(n.predict, e->cfg.image_size);
   for (const Block& b : n.blocks) { one(b.ce); one(b.c1); one(b.c2); }
   n.dirty = false;
   CHECK_CUDA_RET();
@@ -370,8 +390,16 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
 // y = conv(x, filt) (+bias) (+addend).  w_master: fp32 filter [Cout][k][k][Cin]; w_tc: its tf32-rounded copy
 static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const float* w_master, const float* w_tc,
                     const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr,
-                    const float* w_narrow = nullptr) {
-  if (fwd_on_narrow(e, s) && w_narrow) {
+                    const float* w_narrow = nullptr, const float* w_gather = nullptr) {
+  if (fwd_on_rowsep_in(e, s) && w_narrow) {
+    ProfScope ps(PC_TC_FWD, s, st);
+    int r = launch_conv_rowsep_in(x, w_narrow, bias, addend, y, s, e->rs, stats, st);
+    if (r) return fail(r, "row-separable tcgen05 conv launch failed");
+  } else if (fwd_on_rowsep_out(e, s) && w_gather) {
+    ProfScope ps(PC_TC_FWD, s, st);
+    int r = launch_conv_rowsep_out(x, w_gather, bias, addend, y, s, e->rs, st);
+    if (r) return fail(r, "row-separable tcgen05 conv launch failed");
+  } else if (fwd_on_narrow(e, s) && w_narrow) {
     ProfScope ps(PC_SIMT_FWD, s, st);
     launch_conv_narrow_in_fwd(x, w_narrow, bias, addend, y, s, st);
   } else if (fwd_on_tc(e, s)) {
@@ -387,7 +415,8 @@ static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const f
 static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, float* y, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
-  return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st, nullptr, n.derived + c.wn_off);
+  return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st, nullptr, n.derived + c.wn_off,
+                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr);
 }
 // t = conv(x, W) followed by the BatchNorm batch statistics of t (train) or the running statistics (eval).  On the tensor
 // core path the statistics come out of the conv epilogue (no second pass over t).
@@ -395,10 +424,11 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
                          bool train, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const long long rows = (long long)B * size * size;
-  int parts = (train && e->tc && !fwd_on_narrow(e, s) && fwd_on_tc(e, s)) ? conv_tc_stats_parts(s) : 0;
+  int parts = (train && e->tc && (fwd_on_rowsep_in(e, s) || (!fwd_on_narrow(e, s) && fwd_on_tc(e, s)))) ? conv_tc_stats_parts(s) : 0;
   if (parts > 0 && bn_parts_scratch_bytes(parts, c.cout) > e->red_bytes) parts = 0;
   float* sp = parts > 0 ? (float*)e->red : nullptr;
-  TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp, n.derived + c.wn_off));
+  TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp, n.derived + c.wn_off,
+               c.wg_off >= 0 ? n.derived + c.wg_off : nullptr));
   if (parts > 0)
     launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st);
   else if (train)
@@ -410,12 +440,21 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
 // dx = conv_transpose(dy, W) (+addend): a forward conv over dy with the packed dgrad filters
 static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cout, c.cin, c.k};
-  return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st, nullptr, n.derived + c.wn_off);
+  return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st, nullptr, n.derived + c.wn_off,
+                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr);
 }
 static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   float* dw = n.grads + c.w_off;
-  if (e->fast && c.cin <= 4 && conv_narrow_corr_supported(c.cout, c.cin, c.k)) {            // stem
+  if (e->tc && e->fast && e->rs && c.cin <= 3 && conv_rowsep_wgrad_supported(size, size, c.cin, c.cout, c.k)) {          // stem
+    ProfScope ps(PC_TC_WGRAD, s, st);
+    int r = launch_conv_rowsep_wgrad(x, dy, dw, B, size, size, c.cin, c.cout, 1, true, e->rs, e->red, e->red_bytes, st);
+    if (r) return fail(r, "row-separable tcgen05 wgrad launch failed");
+  } else if (e->tc && e->fast && e->rs && c.cout <= 3 && conv_rowsep_wgrad_supported(size, size, c.cout, c.cin, c.k)) {  // predict
+    ProfScope ps(PC_TC_WGRAD, s, st);
+    int r = launch_conv_rowsep_wgrad(dy, x, dw, B, size, size, c.cout, c.cin, 0, true, e->rs, e->red, e->red_bytes, st);
+    if (r) return fail(r, "row-separable tcgen05 wgrad launch failed");
+  } else if (e->fast && c.cin <= 4 && conv_narrow_corr_supported(c.cout, c.cin, c.k)) {            // stem
     ProfScope ps(PC_SIMT_WGRAD, s, st);
     launch_conv_narrow_corr(x, dy, dw, B, size, size, c.cin, c.cout, c.k, 1, true, e->red, e->red_bytes, st);
   } else if (e->fast && c.cout <= 4 && conv_narrow_corr_supported(c.cin, c.cout, c.k)) {     // predict
@@ -936,15 +975,39 @@ extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void
 // ---- single-kernel entry points ------------------------------------------------------------------------------
 // library-owned scratch for the transposed narrow filter of the single-kernel test entry points (the engine keeps its
 // own copy in the workspace)
-static float* narrow_scratch(size_t floats) {
-  static float* buf = nullptr;
-  static size_t cap = 0;
-  if (floats > cap) {
-    if (buf) cudaFree(buf);
-    if (cudaMalloc(&buf, floats * sizeof(float)) != cudaSuccess) { buf = nullptr; cap = 0; return nullptr; }
-    cap = floats;
+static float* lib_scratch(int slot, size_t floats) {
+  static float* buf[2] = {nullptr, nullptr};
+  static size_t cap[2] = {0, 0};
+  if (floats > cap[slot]) {
+    if (buf[slot]) cudaFree(buf[slot]);
+    if (cudaMalloc(&buf[slot], floats * sizeof(float)) != cudaSuccess) { buf[slot] = nullptr; cap[slot] = 0; return nullptr; }
+    cap[slot] = floats;
   }
-  return buf;
+  return buf[slot];
+}
+static float* narrow_scratch(size_t floats) { return lib_scratch(0, floats); }
+// AUTO backend of the single-kernel entry points: prepare whatever derived filter / scratch the engine's choice needs
+static int auto_prepare(sivae_engine* tmp, const ConvShape& s, const float* filt, const float** wn, const float** wg, cudaStream_t st) {
+  *wn = *wg = nullptr;
+  tmp->rs = lib_scratch(1, (size_t)conv_rowsep_scratch_floats(s));
+  const int wide = s.Cin > s.Cout ? s.Cin : s.Cout;
+  if (fwd_on_rowsep_in(tmp, s)) {
+    float* buf = narrow_scratch((size_t)wide * 160);
+    if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
+    launch_rowsep_filter_expand(filt, buf, s.Cout, s.Cin, st);
+    *wn = buf;
+  } else if (fwd_on_rowsep_out(tmp, s)) {
+    float* buf = narrow_scratch((size_t)wide * 160);
+    if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
+    launch_rowsep_filter_gather(filt, buf, s.Cout, s.Cin, st);
+    *wg = buf;
+  } else if (fwd_on_narrow(tmp, s)) {
+    float* buf = narrow_scratch((size_t)s.Cout * s.Cin * s.k * s.k);
+    if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
+    launch_narrow_transpose(filt, buf, s.Cout, s.k, s.Cin, st);
+    *wn = buf;
+  }
+  return 0;
 }
 // backend: SIVAE_CONV_SIMT = generic exact fp32 kernel; SIVAE_CONV_TCGEN05 = tensor-core kernel or error -7;
 // SIVAE_CONV_AUTO = what the engine would pick for this shape (narrow CUDA-core kernel, tensor core, generic)
@@ -958,14 +1021,9 @@ extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bia
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (backend == SIVAE_CONV_AUTO) {
     sivae_engine tmp; tmp.tc = tmp.fast = true;
-    const float* wn = nullptr;
-    if (fwd_on_narrow(&tmp, s)) {
-      float* buf = narrow_scratch((size_t)Cout * Cin * k * k);
-      if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
-      launch_narrow_transpose(w, buf, Cout, k, Cin, st);
-      wn = buf;
-    }
-    TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st, nullptr, wn));
+    const float *wn, *wg;
+    TRY(auto_prepare(&tmp, s, w, &wn, &wg, st));
+    TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st, nullptr, wn, wg));
   } else {
     launch_conv_fwd_simt(x, w, bias, addend, y, s, st);
   }
@@ -987,14 +1045,9 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
     int r = launch_conv_fwd_tc(dy, wd, nullptr, addend, dx, s, st);
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (backend == SIVAE_CONV_AUTO) {
-    const float* wn = nullptr;
-    if (fwd_on_narrow(&tmp, s)) {
-      float* buf = narrow_scratch((size_t)Cout * Cin * k * k);
-      if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
-      launch_narrow_transpose(wd, buf, Cin, k, Cout, st);
-      wn = buf;
-    }
-    TRY(conv_any(&tmp, s, dy, wd, wd, nullptr, addend, dx, st, nullptr, wn));
+    const float *wn, *wg;
+    TRY(auto_prepare(&tmp, s, wd, &wn, &wg, st));
+    TRY(conv_any(&tmp, s, dy, wd, wd, nullptr, addend, dx, st, nullptr, wn, wg));
   } else {
     launch_conv_fwd_simt(dy, wd, nullptr, addend, dx, s, st);
   }
@@ -1006,7 +1059,17 @@ extern "C" int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, in
   ConvShape s{N, H, W, Cin, Cout, k};
   cudaStream_t st = (cudaStream_t)stream;
   const bool acc = accumulate != 0;
-  if (backend == SIVAE_CONV_AUTO && Cin <= 4 && conv_narrow_corr_supported(Cout, Cin, k)) {
+  const bool rs_stem = backend == SIVAE_CONV_AUTO && Cin <= 3 && conv_rowsep_wgrad_supported(H, W, Cin, Cout, k);
+  const bool rs_pred = backend == SIVAE_CONV_AUTO && Cout <= 3 && conv_rowsep_wgrad_supported(H, W, Cout, Cin, k);
+  if (rs_stem || rs_pred) {
+    const int wide = rs_stem ? Cout : Cin, c = rs_stem ? Cin : Cout;
+    if ((size_t)ws_bytes < conv_rowsep_wgrad_scratch_bytes(N, H, W, wide)) return fail(-3, "workspace too small");
+    float* xe = lib_scratch(1, (size_t)conv_rowsep_scratch_floats(s));
+    if (!xe) return fail(-3, "cudaMalloc of the row-expansion scratch failed");
+    int r = launch_conv_rowsep_wgrad(rs_stem ? x : dy, rs_stem ? dy : x, dw, N, H, W, c, wide, rs_stem ? 1 : 0, acc, xe, workspace,
+                                     (size_t)ws_bytes, st);
+    if (r) return fail(r, "row-separable tcgen05 wgrad launch failed");
+  } else if (backend == SIVAE_CONV_AUTO && Cin <= 4 && conv_narrow_corr_supported(Cout, Cin, k)) {
     if ((size_t)ws_bytes < conv_narrow_corr_scratch_bytes(Cout, k)) return fail(-3, "workspace too small");
     launch_conv_narrow_corr(x, dy, dw, N, H, W, Cin, Cout, k, 1, acc, workspace, (size_t)ws_bytes, st);
   } else if (backend == SIVAE_CONV_AUTO && Cout <= 4 && conv_narrow_corr_supported(Cin, Cout, k)) {

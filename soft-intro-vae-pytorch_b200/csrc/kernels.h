@@ -42,6 +42,21 @@ size_t colsum_scratch_bytes(int C);
 void launch_colsum(const float* in, float* out, long long rows, int C, bool accumulate, void* scratch, cudaStream_t st);
 
 // ---------------- cdim-facing 5x5 convolutions on CUDA cores (conv_narrow.cu) ----------------
+// row-separable tensor-core form of the image-facing 5x5 convs (conv_tc.cu): c <= 3 channels on the input or output side
+bool conv_rowsep_in_supported(const ConvShape& s);
+bool conv_rowsep_out_supported(const ConvShape& s);
+long long conv_rowsep_scratch_floats(const ConvShape& s);
+void launch_rowsep_filter_expand(const float* f, float* out, int Co, int c, cudaStream_t st);     // [Co][5][5][c] -> [Co][5][32]
+void launch_rowsep_filter_gather(const float* f, float* out, int c, int Ci, cudaStream_t st);     // [c][5][5][Ci] -> [16][5][Ci]
+int launch_conv_rowsep_in(const float* x, const float* we, const float* bias, const float* addend, float* y, const ConvShape& s,
+                          float* scratch, float* stats, cudaStream_t st);
+bool conv_rowsep_wgrad_supported(int H, int W, int c, int wide, int k);
+size_t conv_rowsep_wgrad_scratch_bytes(int N, int H, int W, int wide);
+// mode 1: stem (narrow = x [N,H,W,c], wide = dy [N,H,W,wide]); mode 0: predict (narrow = dy, wide = x); dw [Cout][5][5][Cin]
+int launch_conv_rowsep_wgrad(const float* narrow_t, const float* wide_t, float* dw, int N, int H, int W, int c, int wide, int mode,
+                             bool accumulate, float* expand_scratch, void* scratch, size_t scratch_bytes, cudaStream_t st);
+int launch_conv_rowsep_out(const float* x, const float* wg, const float* bias, const float* addend, float* y, const ConvShape& s,
+                           float* scratch, cudaStream_t st);
 bool conv_narrow_in_supported(const ConvShape& s);            // Cin <= 4: stem forward, predict dgrad
 // wt = filter transposed to [tap][Cin][Cout] (launch_narrow_transpose of the [Cout][tap][Cin] filter)
 void launch_narrow_transpose(const float* w, float* wt, int Cout, int k, int A, cudaStream_t st);

@@ -47,6 +47,13 @@ CONV_SHAPES = [
     (3, 20, 12, 3, 64, 5),     # stem-like, partial 16x16 tiles
     (2, 16, 16, 64, 3, 5),     # predict-like at the narrow-correlation kernel's channel count
     (1, 8, 8, 1, 32, 5),       # cdim = 1 (mnist-like)
+    (2, 32, 16, 3, 64, 5),     # row-separable tensor-core stem (two stacked 16-row tiles)
+    (3, 16, 24, 3, 32, 5),     # row-separable stem, single tile row, 32 output channels
+    (1, 16, 16, 3, 128, 5),    # row-separable stem with two output-channel tiles
+    (2, 32, 16, 64, 3, 5),     # row-separable predict conv
+    (1, 16, 8, 32, 3, 5),      # row-separable predict conv, one input chunk
+    (2, 16, 16, 1, 32, 5),     # row-separable, cdim = 1
+    (2, 16, 16, 32, 1, 5),
 ]
 
 
