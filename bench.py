@@ -179,7 +179,8 @@ def run_ours(args):
     if args.layers and rank == 0:
         buf = C.create_string_buffer(1 << 16)
         lib.sivae_profile_dump(buf, len(buf))
-        names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, GB/s)"}
+        names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, TB/s)",
+                 5: "bn+act fwd (k=4+mode: residual; TB/s)", 6: "bn+act bwd (k=4+mode: residual; TB/s)"}
         rows = [l.split() for l in buf.value.decode().splitlines()]
         rows.sort(key=lambda r: -float(r[8]))
         with open(args.layers, "w") as f:

@@ -323,7 +323,8 @@ static size_t carve(sivae_engine* e, char* base) {
 // -------------------------------------------------------------------------------------------------------------
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
-enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_COUNT = 5 };
+enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_COUNT = 5,
+       PC_BN_FWD = 5, PC_BN_BWD = 6 };      // classes >= PC_COUNT appear in sivae_profile_dump only (bytes in the flops slot)
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; ConvShape shape; };
 struct Prof {
   bool on = false;
@@ -354,6 +355,15 @@ struct ProfLoss {
     if (ps.r) ps.r->flops = 5.0 * (double)B * (double)per * 4.0;
   }
 };
+// BatchNorm + activation (+ residual, + resample) passes: `flops` carries the algorithmic bytes.
+// passes = tensors of B*s*s*C floats touched (a pooled tensor counts 1/4, an upsampled one 4)
+struct ProfElem {
+  ProfScope ps;
+  ProfElem(int cls, int B, int s, int C, int mode, double passes, cudaStream_t st) : ps(cls, ConvShape{B, s, s, C, C, mode}, st) {
+    if (ps.r) ps.r->flops = passes * (double)B * s * s * C * 4.0;
+  }
+};
+static double resampled(int mode) { return mode == RS_POOL ? 0.25 : (mode == RS_UP ? 4.0 : 1.0); }
 // which implementation serves a convolution (exact = SIMT-only engine; narrow = cdim-facing CUDA-core kernels)
 static bool fwd_on_tc(const sivae_engine* e, const ConvShape& s) { return e->tc && conv_tc_supported_fwd(s); }
 static bool fwd_on_rowsep_in(const sivae_engine* e, const ConvShape& s) { return e->tc && e->fast && e->rs && conv_rowsep_in_supported(s); }
@@ -491,9 +501,11 @@ static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, c
   const float* idn = x;
   if (b.expand) { TRY(conv_fwd(e, n, b.ce, x, a.id, nullptr, B, s, st)); idn = a.id; }
   TRY(conv_bn_stats(e, n, b.c1, b.bn1, x, a.t1, a.mi1, B, s, train, st));
-  launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->tc, st);
+  { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0, st);
+    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->tc, st); }
   TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st));
-  launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->tc, st);
+  { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode), st);
+    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->tc, st); }
   return 0;
 }
 
@@ -503,7 +515,8 @@ static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, in
   const int S = c.image_size;
   p.img = img;
   TRY(conv_bn_stats(e, n, n.stem, n.stem_bn, img, p.t0, p.mi0, B, S, train, st));
-  launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->tc, st);
+  { ProfElem pe(PC_BN_FWD, B, S, n.stem.cout, RS_POOL, 1.25, st);
+    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->tc, st); }
   const float* x = p.a0;
   for (size_t i = 0; i < n.blocks.size(); ++i) {
     TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
@@ -544,14 +557,17 @@ static int block_backward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, 
   float* DA1 = e->sb[4];
   const float* idn = b.expand ? a.id : a.x;
   float* g = n.grads;
-  launch_bn_act_bwd(dout, a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, DT, G2,
-                    wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->tc,
-                    e->red, e->red_bytes, st);
+  { // reduce pass reads dout, t2, identity; apply pass reads them again and writes dt and the identity-path gradient
+    ProfElem pe(PC_BN_BWD, B, s, b.outc, 4 + b.mode, 2.0 * (resampled(b.mode) + 2.0) + 2.0, st);
+    launch_bn_act_bwd(dout, a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, DT, G2,
+                      wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->tc,
+                      e->red, e->red_bytes, st); }
   if (wgrad) TRY(conv_wgrad(e, n, b.c2, a.a1, DT, B, s, st));
   TRY(conv_dgrad(e, n, b.c2, DT, DA1, nullptr, B, s, st));
-  launch_bn_act_bwd(DA1, a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, DT, nullptr,
-                    wgrad ? g + b.bn1.g_off : nullptr, wgrad ? g + b.bn1.b_off : nullptr, true, B, s, s, b.outc, RS_NONE, e->tc,
-                    e->red, e->red_bytes, st);
+  { ProfElem pe(PC_BN_BWD, B, s, b.outc, RS_NONE, 5.0, st);
+    launch_bn_act_bwd(DA1, a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, DT, nullptr,
+                      wgrad ? g + b.bn1.g_off : nullptr, wgrad ? g + b.bn1.b_off : nullptr, true, B, s, s, b.outc, RS_NONE, e->tc,
+                      e->red, e->red_bytes, st); }
   if (wgrad) {
     TRY(conv_wgrad(e, n, b.c1, a.x, DT, B, s, st));
     if (b.expand) TRY(conv_wgrad(e, n, b.ce, a.x, G2, B, s, st));
@@ -581,9 +597,10 @@ static int enc_backward(sivae_engine* e, Net& n, EncPass& p, const float* dml, b
   }
   // stem: conv5x5 + BN + LeakyReLU + AvgPool (:89-92)
   float* DT = e->sb[2];
-  launch_bn_act_bwd(cur, p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, DT, nullptr,
-                    wgrad ? n.grads + n.stem_bn.g_off : nullptr, wgrad ? n.grads + n.stem_bn.b_off : nullptr, true, B, S, S,
-                    n.stem.cout, RS_POOL, e->tc, e->red, e->red_bytes, st);
+  { ProfElem pe(PC_BN_BWD, B, S, n.stem.cout, RS_POOL, 2.0 * 1.25 + 1.0, st);
+    launch_bn_act_bwd(cur, p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, DT, nullptr,
+                      wgrad ? n.grads + n.stem_bn.g_off : nullptr, wgrad ? n.grads + n.stem_bn.b_off : nullptr, true, B, S, S,
+                      n.stem.cout, RS_POOL, e->tc, e->red, e->red_bytes, st); }
   if (wgrad) TRY(conv_wgrad(e, n, n.stem, p.img, DT, B, S, st));
   if (d_img) TRY(conv_dgrad(e, n, n.stem, DT, d_img, d_img_addend, B, S, st));
   CHECK_CUDA_RET();
@@ -955,6 +972,7 @@ extern "C" int sivae_profile_read(double* out) {
   for (size_t i = 0; i < g_prof.used; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, g_prof.recs[i].a, g_prof.recs[i].b) != cudaSuccess) continue;
+    if (g_prof.recs[i].cls >= PC_COUNT) continue;
     out[g_prof.recs[i].cls * 3 + 0] += ms;
     out[g_prof.recs[i].cls * 3 + 1] += g_prof.recs[i].flops;
     out[g_prof.recs[i].cls * 3 + 2] += 1.0;
