@@ -1,13 +1,15 @@
 // fp32 CUDA-core kernels for the two image-facing 5x5 convolutions whose narrow side (cdim = 1..4 channels) does not
 // fill a tensor-core tile: the encoder stem (cdim -> c0, reference :89) and the decoder's `predict` (c0 -> cdim, :159).
-//   k_narrow_in_fwd   y[p][co] = sum_{tap,a} x[p+tap][a] * w[co][tap][a]          stem forward, predict dgrad
+//   k_narrow_in_fwd   y[p][co] = sum_{tap,a} x[p+tap][a] * w[tap][a][co]          stem forward, predict dgrad
 //   k_narrow_corr     G[tap][a][c] = sum_p nar[p][a] * wide[p+tap][c]             stem wgrad, predict wgrad
-// (the wide->narrow direction, predict forward / stem dgrad, runs on the tcgen05 kernel with a masked epilogue.)
+// Since the row-separable tensor-core form exists (conv_tc.cu: launch_conv_rowsep_in/_out/_wgrad, 0.29 / 0.29 / 0.4 ms
+// against 0.72 / 0.92 / 0.94 ms here at 32x256x256) these kernels are the FALLBACK for shapes it does not take: image
+// sizes that are not multiples of 16 x 8, cdim = 4, or a tensor-core-less build of the engine's "fast" mode.
 // Both are FMA-bound direct convolutions with the halo tile staged in shared memory; exact fp32 (no tf32 rounding).
-// The inner loops are arranged for a high FMA : shared-load ratio (the first versions were LSU-bound at 19-30 % of the
-// fp32 peak, profiles/r01a_launches_H.md): forward = 2 pixels x 32 output channels per thread and 128-bit broadcast
-// filter loads (64 FMA per 10 LDS); correlation = one filter row per thread with a 5-wide sliding register window
-// (15 FMA per 2 LDS).
+//   forward: block = 8 x 32 output pixels, lane = (output-channel quad, pixel parity), filter pre-transposed to
+//            [tap][a][Cout] so a quad is one conflict-free LDS.128 reused over 8 pixels (96 FMA per 11 LDS);
+//   correlation: thread = (wide channel, filter row) with a KS-wide sliding register window over the pixel row, fully
+//            unrolled (15 FMA per 2 LDS), persistent blocks, partials folded by k_narrow_corr_reduce in fixed order.
 #include "kernels.h"
 
 namespace sivae {

@@ -166,6 +166,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// Staging tiles per epilogue warp.  With ONE tile every chunk waited for the previous TMA store to finish reading it:
+// ~3.3k clk per 32x32 chunk, which made the epilogue (not the MMA loop) the bottleneck of every output-heavy layer
+// (profiles/r01h_layers_H_rowsep_wgrad.md: 1x1 convs at 1.4 TB/s of output, 64->64 3x3 at 15k clk per 256-pixel item).
+constexpr int EPI_NBUF = 2;
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Epilogue of one 32-row x 32-column accumulator chunk held by a warp (lane = row): + bias + addend, then either
@@ -175,14 +181,17 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // Path (a) exists because direct stores (32 rows x 16 B per instruction, each its own L2 transaction) capped every
 // output-heavy layer at ~1.1 TB/s (profiles/r01c_layers_H_halo.md: 1x1 convs 35-126 TFLOP/s, 64-channel 3x3 at 0.45 ms).
 struct EpiOut { const float* bias; const float* addend; float* y; int Cout; float* stats; };   // stats: BN partials base or null
+struct EpiState { uint32_t n = 0; };     // per-warp count of staged chunks (selects the staging tile)
 // srow >= 0 (TMA path only): also emit the per-channel sum / sum of squares of this warp's 32 rows (train-mode BatchNorm
 // statistics, fused so that the conv output is not re-read): stats[srow][0][c] = sum, stats[srow][1][c] = sum of squares
 __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
-                                          uint8_t* stage, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
+                                          uint8_t* stage0, EpiState& es, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
                                           long long srow = -1) {
   if (tma) {
     const float* add = (o.addend && valid) ? o.addend + pix * o.Cout + col : nullptr;
-    if (lane == 0) bulk_wait_read0();            // the previous TMA store has finished reading the staging tile
+    uint8_t* stage = stage0 + (es.n % EPI_NBUF) * 4096;
+    ++es.n;
+    if (lane == 0) bulk_wait_read<EPI_NBUF - 1>();   // the store issued EPI_NBUF chunks ago has finished reading this tile
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -285,6 +294,7 @@ struct FwdParams {
   const float* addend;
   float* y;
   float* stats;              // BN partial sums [m_tiles*4][2][Cout] or null
+  int ksplit, kb_per, npad;  // split-K (v2 kernel): k-blocks per split; partial tensor batch stride (tiles_n * bn)
 };
 constexpr int TC_A_BYTES = 128 * 128;       // 128 rows x 32 fp32
 
@@ -463,8 +473,8 @@ template <int BLOCK_N, int STAGES>
 struct Fwd2Smem {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGE_OFF = STAGES * STAGE_BYTES;          // 4 x 4 KB epilogue staging tiles
-  static constexpr int BAR_OFF = STAGE_OFF + 4 * 4096;
+  static constexpr int STAGE_OFF = STAGES * STAGE_BYTES;          // 4 warps x EPI_NBUF x 4 KB epilogue staging tiles
+  static constexpr int BAR_OFF = STAGE_OFF + 4 * EPI_NBUF * 4096;
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
@@ -504,10 +514,12 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     if (elect_one()) {
       int it = 0;                                          // global k-block counter of this CTA (ring position)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int nt = tile % n_tiles, rest = tile / n_tiles;
+        const int z = rest % p.ksplit, mt = rest / p.ksplit;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, col0 = nt * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb0 = z * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[st], ph ^ 1);
@@ -528,7 +540,9 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
       mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);    // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      const int z = (tile / n_tiles) % p.ksplit;
+      const int kb0 = z * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int st = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[st], ph);
@@ -540,10 +554,10 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
             uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-            umma_tf32(tmem_d, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[st]);
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
         __syncwarp();
       }
@@ -554,15 +568,17 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     const int dw = row % p.bw, dh = (row / p.bw) % p.bh, dn = row / (p.bw * p.bh);
     const int r0 = q * 32;                                  // first row of this warp: TMA-store box origin
     const int sdh = (r0 / p.bw) % p.bh, sdn = r0 / (p.bw * p.bh);
-    uint8_t* stage = smem + SM::STAGE_OFF + q * 4096;
+    uint8_t* stage = smem + SM::STAGE_OFF + q * (EPI_NBUF * 4096);
+    EpiState es;
     const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats};
     const bool tma = p.tma_store != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
-      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      const int nt = tile % n_tiles, rest = tile / n_tiles;
+      const int z = rest % p.ksplit, mt = rest / p.ksplit;
       const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn, col0 = nt * BLOCK_N;
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn + z * p.npad, col0 = nt * BLOCK_N;   // split z -> its own batch slab
       const int n = n0 + dn;
       const bool valid = n < p.N;
       const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
@@ -574,7 +590,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
         if (col0 + c >= p.Cout) break;                     // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q);
+        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q);
       }
       // this warp is done reading the accumulator: release it to the MMA warp
       tc_fence_before();
@@ -608,7 +624,7 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUt
     attr = true;
   }
   const int n_tiles = (p.Cout + BLOCK_N - 1) / BLOCK_N;
-  const int total = m_tiles * n_tiles;
+  const int total = m_tiles * n_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   g_launches += 1;
   k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p, n_tiles, total);
@@ -647,7 +663,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t s
 struct HaloParams {
   int N, H, W, Cin, Cout;
   int tma_store;
-  int tiles_w, tiles_h;        // W/8, H/(16*T)
+  int tiles_w, tiles_h;        // W/8, H/16
   int n_tiles, total;          // Cout tiles, total work items
   int base_offset_mode;        // 1: descriptor base_offset = s (documented semantics); 0: always 0 (experiment)
   const float* bias;
@@ -657,13 +673,14 @@ struct HaloParams {
 };
 template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 struct HaloSmem {
-  static constexpr int ROWS = 16 * T + KH - 1;
+  static constexpr int ROWS = 16 + KH - 1;           // one halo box per 16x8 pixel tile
   static constexpr int BW = (KW == 1) ? 8 : 16;      // box width in pixels (8 output columns + column halo)
-  static constexpr int A_BYTES = ROWS * BW * 128;
+  static constexpr int BOX_BYTES = ROWS * BW * 128;
+  static constexpr int A_BYTES = T * BOX_BYTES;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
-  static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;     // 4 x 4 KB epilogue staging tiles
-  static constexpr int BAR_OFF = STAGE_OFF + 4 * 4096;
+  static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;     // 4 warps x EPI_NBUF x 4 KB epilogue staging tiles
+  static constexpr int BAR_OFF = STAGE_OFF + 4 * EPI_NBUF * 4096;
   static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
@@ -706,14 +723,18 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
       int ai = 0, bi = 0;
       for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
         const int nt = item % p.n_tiles, mt = item / p.n_tiles;
-        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * 8, h0 = th * 16 * T, col0 = nt * BLOCK_N;
+        const int col0 = nt * BLOCK_N;
         for (int ch = 0; ch < cchunks; ++ch) {
           {
             const int st = ai % A_STAGES;
             mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
             mbar_expect_tx(&a_full[st], SM::A_BYTES);
-            tma_load_4d(smem + st * SM::A_BYTES, &map_x, &a_full[st], ch << 5, w0 - PADW, h0 - PADH, n);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {        // the T pixel tiles of an item are consecutive in (n, tile row, tile column) order
+              const int lin = mt * T + t;
+              const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
+              tma_load_4d(smem + st * SM::A_BYTES + t * SM::BOX_BYTES, &map_x, &a_full[st], ch << 5, tw * 8 - PADW, th * 16 - PADH, n);
+            }
             ++ai;
           }
           for (int tap = 0; tap < TAPS; ++tap, ++bi) {
@@ -747,7 +768,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
             const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-              const uint32_t arow = sa + (uint32_t)(((16 * t + r) * BW + s) * 128);
+              const uint32_t arow = sa + (uint32_t)(t * SM::BOX_BYTES + (r * BW + s) * 128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 uint64_t ad = make_smem_desc_bo(arow + k * 32, BW * 128, bo);
@@ -769,20 +790,23 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int dh = row >> 3, dw = row & 7;
-    uint8_t* stage = smem + SM::STAGE_OFF + q * 4096;
+    uint8_t* stage = smem + SM::STAGE_OFF + q * (EPI_NBUF * 4096);
+    EpiState es;
     const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats};
     const bool tma = p.tma_store != 0;
     int lt = 0;
     for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
       const int acc = lt & 1;
       const int nt = item % p.n_tiles, mt = item / p.n_tiles;
-      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * 8, h0 = th * 16 * T, col0 = nt * BLOCK_N;
+      const int col0 = nt * BLOCK_N;
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        const long long pix = ((long long)n * p.H + (h0 + 16 * t + dh)) * p.W + (w0 + dw);
+        const int lin = mt * T + t;
+        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * 8, h0 = th * 16;
+        const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
@@ -790,7 +814,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           // this warp's 32 rows = image rows h0+16t+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
-          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, &map_y, w0, h0 + 16 * t + 4 * q, n, lane, ((long long)mt * T + t) * 4 + q);
+          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, (long long)lin * 4 + q);
         }
       }
       tc_fence_before();
@@ -831,9 +855,9 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   }
   HaloParams p;
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout;
-  p.tiles_w = s.W / 8; p.tiles_h = s.H / (16 * T);
+  p.tiles_w = s.W / 8; p.tiles_h = s.H / 16;
   p.n_tiles = (s.Cout + BLOCK_N - 1) / BLOCK_N;
-  p.total = p.tiles_w * p.tiles_h * s.N * p.n_tiles;
+  p.total = (p.tiles_w * p.tiles_h * s.N / T) * p.n_tiles;      // callers pick T = 2 only when the tile count is even
   p.base_offset_mode = halo_mode() == 1 ? 1 : 0;
   p.bias = bias; p.addend = addend; p.y = y;
   p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
@@ -855,11 +879,11 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        float* stats, cudaStream_t st) {
-  const bool two = (s.H % 32 == 0);
+  const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
   if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
     return two ? launch_halo_t<32, 2, 2, 8, 5, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5, 5>(x, w, bias, addend, y, s, stats, st);
   }
-  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 4, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 5, 3, 3>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 3, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 5, 3, 3>(x, w, bias, addend, y, s, stats, st);
   return two ? launch_halo_t<64, 2, 2, 6, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3, 3>(x, w, bias, addend, y, s, stats, st);
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -993,14 +1017,16 @@ int launch_conv_rowsep_in(const float* x, const float* we, const float* bias, co
   g_launches += 1;
   k_rowsep_expand<<<num_sms() * 8, 256, 0, st>>>(x, scratch, rows, s.W, s.Cin);
   ConvShape e{s.N, s.H, s.W, 32, s.Cout, 5};
-  if (s.H % 32 == 0) return launch_halo_t<64, 2, 2, 6, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
+  const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
+  if (two) return launch_halo_t<64, 2, 2, 6, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
   return launch_halo_t<64, 1, 3, 8, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
 }
 // y[N,H,W,c] = conv5x5(x[N,H,W,Cin], F) (+bias)(+addend); wg = gather-form filter; scratch >= N*H*W*16 floats
 int launch_conv_rowsep_out(const float* x, const float* wg, const float* bias, const float* addend, float* y, const ConvShape& s,
                            float* scratch, cudaStream_t st) {
   ConvShape e{s.N, s.H, s.W, s.Cin, 16, 5};
-  int r = (s.H % 32 == 0) ? launch_halo_t<32, 2, 2, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st)
+  const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
+  int r = two ? launch_halo_t<32, 2, 2, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st)
                           : launch_halo_t<32, 1, 3, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st);
   if (r) return r;
   g_launches += 1;
@@ -1023,18 +1049,83 @@ static int fwd_kernel_version() {
   return v;
 }
 
+static int splitk_count(const ConvShape& s);
 // number of BN partial rows the fused-statistics epilogue produces for this shape (0: not available, use launch_bn_stats)
 int conv_tc_stats_parts(const ConvShape& s) {
   if (conv_rowsep_in_supported(s)) return s.N * (s.H / 16) * (s.W / 8) * 4;
   if (!conv_tc_supported_fwd(s) || (s.Cout & 3) != 0 || !tma_store_enabled() || fwd_kernel_version() == 1) return 0;
   if (halo_mode() != 0 && halo_eligible(s)) return s.N * (s.H / 16) * (s.W / 8) * 4;      // items * T * 4 warps (T cancels)
+  if (splitk_count(s) > 1) return 0;                // split-K layers: statistics from the reduced output (launch_bn_stats)
   int bw, bh, bn;
   pick_tile(s.H, s.W, &bw, &bh, &bn);
   return (s.W / bw) * (s.H / bh) * ((s.N + bn - 1) / bn) * 4;
 }
+// ---- split-K for few-tile layers (4x4 / 8x8 feature maps): tiles x splits CTAs each accumulate a slice of the
+// (tap, channel-chunk) loop into their own slab of a partial tensor; one pass sums the slabs in fixed order (+bias, +addend).
+__global__ void k_splitk_reduce(const float4* __restrict__ part, const float* __restrict__ bias, const float4* __restrict__ addend,
+                                float4* __restrict__ y, long long n4, long long slab4, int splits, int cvec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = part[i];
+    for (int z = 1; z < splits; ++z) {
+      const float4 b = part[z * slab4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % cvec));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (addend) {
+      const float4 b = addend[i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    y[i] = a;
+  }
+}
+struct SplitKPlan { int block_n, ksplit, kb_per, npad; };
+static bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_SPLITK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+static SplitKPlan splitk_plan(const ConvShape& s) {
+  SplitKPlan pl{0, 1, 0, 0};
+  int bw, bh, bn;
+  pick_tile(s.H, s.W, &bw, &bh, &bn);
+  const int tiles_n = (s.N + bn - 1) / bn;
+  const int m_tiles = (s.W / bw) * (s.H / bh) * tiles_n;
+  // few-tile layers: keep the WIDEST N tile (a narrow tile re-streams the A tiles Cout/block_n times and pins the kernel
+  // at the L2->SM ceiling: 8x8x512->512 with 64-wide tiles moved 442 MB per launch) and fill the SMs by splitting K instead
+  int block_n = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32));
+  const int num_kb = s.k * s.k * (s.Cin / 32);
+  pl.kb_per = num_kb;
+  pl.npad = tiles_n * bn;
+  const long long wide_tiles = (long long)m_tiles * ((s.Cout + block_n - 1) / block_n);
+  if (splitk_enabled() && tma_store_enabled() && (s.Cout & 3) == 0 && wide_tiles * 2 <= num_sms() && num_kb >= 16) {
+    int ks = (int)(num_sms() / wide_tiles);
+    if (ks > num_kb / 8) ks = num_kb / 8;
+    if (ks > 1) {
+      pl.kb_per = (num_kb + ks - 1) / ks;
+      pl.ksplit = (num_kb + pl.kb_per - 1) / pl.kb_per;     // every split owns at least one k-block
+    }
+  }
+  if (pl.ksplit == 1)
+    while (block_n > 64 && (long long)m_tiles * ((s.Cout + block_n - 1) / block_n) < num_sms()) block_n >>= 1;
+  pl.block_n = block_n;
+  return pl;
+}
+static int splitk_count(const ConvShape& s) { return splitk_plan(s).ksplit; }
+size_t conv_tc_splitk_scratch_bytes(const ConvShape& s) {
+  if (!conv_tc_supported_fwd(s) || (halo_mode() != 0 && halo_eligible(s)) || fwd_kernel_version() == 1) return 0;
+  SplitKPlan pl = splitk_plan(s);
+  return pl.ksplit > 1 ? (size_t)pl.ksplit * pl.npad * s.H * s.W * s.Cout * sizeof(float) : 0;
+}
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                       cudaStream_t st, float* stats) {
+                       cudaStream_t st, float* stats, void* scratch, size_t scratch_bytes) {
   FwdParams p;
+  p.ksplit = 1; p.kb_per = s.k * s.k * (s.Cin / 32); p.npad = 0;
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
   pick_tile(s.H, s.W, &p.bw, &p.bh, &p.bn);
   p.tiles_w = s.W / p.bw; p.tiles_h = s.H / p.bh;
@@ -1054,9 +1145,10 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
     if (block_n == 64) return launch_fwd_t<64, 4>(mx, mw, p, m_tiles, st);
     return launch_fwd_t<32, 4>(mx, mw, p, m_tiles, st);
   }
-  // v2: widest N tile that the layer fills; few-tile problems prefer narrower tiles (more CTAs busy)
-  int block_n = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32));
-  while (block_n > 64 && (long long)m_tiles * ((s.Cout + block_n - 1) / block_n) < num_sms()) block_n >>= 1;
+  // v2: widest N tile that the layer fills; few-tile problems prefer narrower tiles (more CTAs busy) and split K
+  SplitKPlan pl = splitk_plan(s);
+  const int block_n = pl.block_n;
+  if (pl.ksplit > 1 && (!scratch || scratch_bytes < (size_t)pl.ksplit * pl.npad * s.H * s.W * s.Cout * sizeof(float))) pl.ksplit = 1;
   r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
   if (r) return r;
   // epilogue store path: TMA store of each warp's 32-row slab (needs 16-byte aligned channel rows)
@@ -1066,13 +1158,28 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   if (p.tma_store) {
     p.sbh = (32 / p.bw) < p.bh ? (32 / p.bw) : p.bh;
     p.sbn = 32 / (p.bw * p.sbh);
-    r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
+    if (pl.ksplit > 1) {        // raw partial sums into the scratch tensor [ksplit * npad][H][W][Cout]
+      p.ksplit = pl.ksplit; p.kb_per = pl.kb_per; p.npad = pl.npad;
+      p.bias = nullptr; p.addend = nullptr; p.stats = nullptr; p.y = (float*)scratch;
+      p.N = pl.ksplit * pl.npad;       // every slab row is "valid" for the epilogue
+      r = make_store_map(&my, (float*)scratch, pl.ksplit * pl.npad, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
+    } else {
+      r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
+    }
     if (r) return r;
   }
-  if (block_n == 256) return launch_fwd2_t<256, 4>(mx, mw, my, p, m_tiles, st);
-  if (block_n == 128) return launch_fwd2_t<128, 5>(mx, mw, my, p, m_tiles, st);
-  if (block_n == 64) return launch_fwd2_t<64, 8>(mx, mw, my, p, m_tiles, st);
-  return launch_fwd2_t<32, 8>(mx, mw, my, p, m_tiles, st);
+  if (block_n == 256) r = launch_fwd2_t<256, 4>(mx, mw, my, p, m_tiles, st);
+  else if (block_n == 128) r = launch_fwd2_t<128, 5>(mx, mw, my, p, m_tiles, st);
+  else if (block_n == 64) r = launch_fwd2_t<64, 7>(mx, mw, my, p, m_tiles, st);
+  else r = launch_fwd2_t<32, 8>(mx, mw, my, p, m_tiles, st);
+  if (r || pl.ksplit <= 1) return r;
+  const long long n4 = (long long)s.N * s.H * s.W * s.Cout / 4, slab4 = (long long)pl.npad * s.H * s.W * s.Cout / 4;
+  unsigned blocks = (unsigned)((n4 + 255) / 256);
+  if (blocks > 148u * 8) blocks = 148u * 8;
+  g_launches += 1;
+  k_splitk_reduce<<<blocks, 256, 0, st>>>((const float4*)scratch, bias, (const float4*)addend, (float4*)y, n4, slab4, pl.ksplit,
+                                          s.Cout / 4);
+  return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

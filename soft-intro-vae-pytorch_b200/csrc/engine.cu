@@ -93,6 +93,7 @@ struct sivae_engine {
   float *d_rec = nullptr, *d_rec_rec = nullptr, *d_rec_fake = nullptr, *d_fake = nullptr;
   float *dml = nullptr, *dz = nullptr, *dfeat = nullptr, *dfeat2 = nullptr, *coef = nullptr, *ckl_a = nullptr, *ckl_b = nullptr, *mse = nullptr;
   float *out_tmp = nullptr;
+  void* sk = nullptr; size_t sk_bytes = 0;   // split-K partial tensor of the few-tile tensor-core convs
   float *rs = nullptr;             // scratch of the row-separable image-facing convs (B*S*S*32 floats)
   void* red = nullptr; size_t red_bytes = 0;
   int cur_batch = 0;
@@ -313,6 +314,20 @@ static size_t carve(sivae_engine* e, char* base) {
   e->dml = bp.take<float>(B * 2 * z); e->dz = bp.take<float>(B * z);
   e->dfeat = bp.take<float>(B * e->feat); e->dfeat2 = bp.take<float>(B * e->feat);
   e->coef = bp.take<float>(4 * B); e->ckl_a = bp.take<float>(B); e->ckl_b = bp.take<float>(B); e->mse = bp.take<float>(3 * B);
+  {
+    size_t m = 0;
+    auto upd = [&](const Conv& cv, int size) {
+      if (cv.k == 0 || !e->tc) return;
+      size_t a = conv_tc_splitk_scratch_bytes(ConvShape{(int)B, size, size, cv.cin, cv.cout, cv.k});
+      size_t b2 = conv_tc_splitk_scratch_bytes(ConvShape{(int)B, size, size, cv.cout, cv.cin, cv.k});
+      if (a > m) m = a;
+      if (b2 > m) m = b2;
+    };
+    for (int ni = 0; ni < 2; ++ni)
+      for (const Block& b : e->nets[ni].blocks) { upd(b.ce, b.size); upd(b.c1, b.size); upd(b.c2, b.size); }
+    e->sk_bytes = m;
+    e->sk = m ? bp.take<char>(m) : nullptr;
+  }
   e->red_bytes = reduce_scratch_bytes(e);
   e->red = bp.take<char>(e->red_bytes);
   return bp.off + 256;
@@ -414,7 +429,7 @@ static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const f
     launch_conv_narrow_in_fwd(x, w_narrow, bias, addend, y, s, st);
   } else if (fwd_on_tc(e, s)) {
     ProfScope ps(PC_TC_FWD, s, st);
-    int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats);
+    int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats, e->sk, e->sk_bytes);
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else {
     ProfScope ps(PC_SIMT_FWD, s, st);
@@ -994,8 +1009,8 @@ extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void
 // library-owned scratch for the transposed narrow filter of the single-kernel test entry points (the engine keeps its
 // own copy in the workspace)
 static float* lib_scratch(int slot, size_t floats) {
-  static float* buf[2] = {nullptr, nullptr};
-  static size_t cap[2] = {0, 0};
+  static float* buf[3] = {nullptr, nullptr, nullptr};
+  static size_t cap[3] = {0, 0, 0};
   if (floats > cap[slot]) {
     if (buf[slot]) cudaFree(buf[slot]);
     if (cudaMalloc(&buf[slot], floats * sizeof(float)) != cudaSuccess) { buf[slot] = nullptr; cap[slot] = 0; return nullptr; }
@@ -1008,6 +1023,9 @@ static float* narrow_scratch(size_t floats) { return lib_scratch(0, floats); }
 static int auto_prepare(sivae_engine* tmp, const ConvShape& s, const float* filt, const float** wn, const float** wg, cudaStream_t st) {
   *wn = *wg = nullptr;
   tmp->rs = lib_scratch(1, (size_t)conv_rowsep_scratch_floats(s));
+  tmp->sk_bytes = conv_tc_supported_fwd(s) ? conv_tc_splitk_scratch_bytes(s) : 0;
+  tmp->sk = tmp->sk_bytes ? (void*)lib_scratch(2, (tmp->sk_bytes + 3) / 4) : nullptr;
+  if (!tmp->sk) tmp->sk_bytes = 0;
   const int wide = s.Cin > s.Cout ? s.Cin : s.Cout;
   if (fwd_on_rowsep_in(tmp, s)) {
     float* buf = narrow_scratch((size_t)wide * 160);
@@ -1035,7 +1053,9 @@ extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   if (backend == SIVAE_CONV_TCGEN05) {
     if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
-    int r = launch_conv_fwd_tc(x, w, bias, addend, y, s, st);
+    size_t skb = conv_tc_splitk_scratch_bytes(s);
+    void* sk = skb ? (void*)lib_scratch(2, (skb + 3) / 4) : nullptr;
+    int r = launch_conv_fwd_tc(x, w, bias, addend, y, s, st, nullptr, sk, sk ? skb : 0);
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (backend == SIVAE_CONV_AUTO) {
     sivae_engine tmp; tmp.tc = tmp.fast = true;
@@ -1060,7 +1080,9 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
   launch_pack_dgrad_filter(w, wd, Cout, Cin, k, on_tc, st);
   if (backend == SIVAE_CONV_TCGEN05) {
     if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
-    int r = launch_conv_fwd_tc(dy, wd, nullptr, addend, dx, s, st);
+    size_t skb = conv_tc_splitk_scratch_bytes(s);
+    void* sk = skb ? (void*)lib_scratch(2, (skb + 3) / 4) : nullptr;
+    int r = launch_conv_fwd_tc(dy, wd, nullptr, addend, dx, s, st, nullptr, sk, sk ? skb : 0);
     if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (backend == SIVAE_CONV_AUTO) {
     const float *wn, *wg;

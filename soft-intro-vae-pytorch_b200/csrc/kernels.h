@@ -72,7 +72,10 @@ void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int
 bool conv_tc_supported_fwd(const ConvShape& s);
 // returns cudaError / driver error code (0 ok)
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y,
-                       const ConvShape& s, cudaStream_t st, float* stats = nullptr);
+                       const ConvShape& s, cudaStream_t st, float* stats = nullptr, void* scratch = nullptr,
+                       size_t scratch_bytes = 0);
+// split-K partial tensor the v2 kernel wants for few-tile layers (0: no split for this shape)
+size_t conv_tc_splitk_scratch_bytes(const ConvShape& s);
 // fused train-mode BN statistics: if > 0, passing `stats` ([parts][2][Cout] floats) to launch_conv_fwd_tc makes the
 // epilogue emit per-warp column sums / sums of squares; finish with launch_bn_stats_from_parts
 int conv_tc_stats_parts(const ConvShape& s);
