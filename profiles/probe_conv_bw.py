@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 L = importlib.import_module("soft-intro-vae-pytorch_b200.lib")
 DEV = "cuda:0"
 
-CASES = [
+CASES_ALL = [
     # N, H, W, Cin, Cout, k
     (32, 128, 128, 64, 128, 1),
     (32, 128, 128, 128, 64, 1),
@@ -24,6 +24,9 @@ CASES = [
     (32, 4, 4, 512, 512, 3),
     (32, 16, 16, 512, 512, 3),
 ]
+
+
+CASES = CASES_ALL[:4] if os.environ.get("PROBE_SHORT") else CASES_ALL
 
 
 def timed(fn, n):
@@ -49,9 +52,10 @@ def main():
         ys = [torch.empty(N, H, W, Cout, device=DEV) for _ in range(sets)]
         w = torch.randn(Cout, k, k, Cin, device=DEV) * 0.05
 
-        def run(i, rot):
+        def run(i, rot, add=0):
             j = (i % sets) if rot else 0
-            rc = lib.sivae_conv2d_fwd(L.ptr(xs[j]), L.ptr(w), None, None, L.ptr(ys[j]), N, H, W, Cin, Cout, k, L.CONV_TCGEN05, st)
+            a = None if add == 0 else (L.ptr(ys[j]) if add == 1 else L.ptr(ys[(j + 1) % sets]))
+            rc = lib.sivae_conv2d_fwd(L.ptr(xs[j]), L.ptr(w), None, a, L.ptr(ys[j]), N, H, W, Cin, Cout, k, L.CONV_TCGEN05, st)
             assert rc == 0, rc
 
         for _ in range(3):
@@ -60,10 +64,16 @@ def main():
         for i in range(sets):
             run(i, True)
         cold = timed(lambda i: run(i, True), 2 * sets)
+        for y in ys:
+            y.zero_()
+        addt = timed(lambda i: run(i, True, 1), 2 * sets)          # in-place addend (dx += conv), as the block backward does
+        for y in ys:
+            y.zero_()
+        adds = timed(lambda i: run(i, True, 2), 2 * sets)          # addend from a different buffer
         gb = (in_b + out_b) / 1e9
         fl = 2.0 * N * H * W * Cin * Cout * k * k / 1e12
-        print("N%d %dx%d %d->%d k%d  sets=%d  hot %.4f ms (%.2f TB/s, %.0f TF)   cold %.4f ms (%.2f TB/s, %.0f TF)" % (
-            N, H, W, Cin, Cout, k, sets, hot, gb / hot, fl / hot * 1e3, cold, gb / cold, fl / cold * 1e3), flush=True)
+        print("N%d %dx%d %d->%d k%d  sets=%d  hot %.4f ms (%.2f TB/s, %.0f TF)   cold %.4f ms (%.2f TB/s, %.0f TF)   +addend in-place %.4f ms, separate %.4f ms" % (
+            N, H, W, Cin, Cout, k, sets, hot, gb / hot, fl / hot * 1e3, cold, gb / cold, fl / cold * 1e3, addt, adds), flush=True)
         del xs, ys
 
 

@@ -180,33 +180,64 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 //  (b) direct per-thread stores (narrow outputs whose channel count is not a multiple of 4, e.g. the 3-channel image).
 // Path (a) exists because direct stores (32 rows x 16 B per instruction, each its own L2 transaction) capped every
 // output-heavy layer at ~1.1 TB/s (profiles/r01c_layers_H_halo.md: 1x1 convs 35-126 TFLOP/s, 64-channel 3x3 at 0.45 ms).
-struct EpiOut { const float* bias; const float* addend; float* y; int Cout; float* stats; };   // stats: BN partials base or null
+struct EpiOut { const float* bias; const float* addend; float* y; int Cout; float* stats; int amode; };   // stats: BN partials base or null
 struct EpiState { uint32_t n = 0; };     // per-warp count of staged chunks (selects the staging tile)
 // srow >= 0 (TMA path only): also emit the per-channel sum / sum of squares of this warp's 32 rows (train-mode BatchNorm
 // statistics, fused so that the conv output is not re-read): stats[srow][0][c] = sum, stats[srow][1][c] = sum of squares
+// addend (residual / accumulated gradient; may alias the output) of one 32x32 chunk: COALESCED loads -- instruction j covers
+// rows 4j..4j+3 of this warp's 32 rows (lane -> row 4j + lane/8, 16-byte piece lane%8 = four full 128 B lines per
+// instruction); epi_chunk passes them through the staging tile.  The earlier lane-per-row loads (32 lines x 16 B per
+// instruction) made every dgrad-with-addend launch ~2.5x slower than the same conv without it, and loading inside epi_chunk
+// still exposed one global-load latency per chunk (profiles/r01i_probe_conv_bw.txt): callers prefetch chunk i+1 here
+// before they process chunk i.
+__device__ __forceinline__ void epi_load_addend(const EpiOut& o, long long pix, bool valid, int col, int lane, float4 (&a)[8]) {
+  if (!o.addend) return;
+  const long long mypix = valid ? pix : -1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long prow = __shfl_sync(0xffffffffu, mypix, 4 * j + (lane >> 3));
+    const int cc = col + ((lane & 7) << 2);
+    a[j] = (prow >= 0 && cc < o.Cout) ? *reinterpret_cast<const float4*>(o.addend + prow * o.Cout + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
 __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
                                           uint8_t* stage0, EpiState& es, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
-                                          long long srow = -1) {
+                                          const float4 (&a)[8], long long srow = -1) {
   if (tma) {
-    const float* add = (o.addend && valid) ? o.addend + pix * o.Cout + col : nullptr;
     uint8_t* stage = stage0 + (es.n % EPI_NBUF) * 4096;
     ++es.n;
+    float4 al[8];
+    const bool staged_add = o.addend && o.amode != 0;
+    if (o.addend && o.amode == 1) epi_load_addend(o, pix, valid, col, lane, al);      // coalesced, not prefetched
     if (lane == 0) bulk_wait_read<EPI_NBUF - 1>();   // the store issued EPI_NBUF chunks ago has finished reading this tile
     __syncwarp();
+    if (staged_add) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = 4 * j + (lane >> 3);
+        *reinterpret_cast<float4*>(stage + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = (o.amode == 2) ? a[j] : al[j];
+      }
+      __syncwarp();
+    }
+    const float* add0 = (o.addend && o.amode == 0 && valid) ? o.addend + pix * o.Cout + col : nullptr;   // mode 0: lane-per-row loads
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 q = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      float4* slot = reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4));
       if (col + 4 * j < o.Cout) {
         if (o.bias) {
           float4 b = __ldg(reinterpret_cast<const float4*>(o.bias + col + 4 * j));
           q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
         }
-        if (add) {
-          float4 a = *reinterpret_cast<const float4*>(add + 4 * j);
-          q.x += a.x; q.y += a.y; q.z += a.z; q.w += a.w;
+        if (staged_add) {
+          const float4 d = *slot;
+          q.x += d.x; q.y += d.y; q.z += d.z; q.w += d.w;
+        } else if (add0) {
+          const float4 d = *reinterpret_cast<const float4*>(add0 + 4 * j);
+          q.x += d.x; q.y += d.y; q.z += d.z; q.w += d.w;
         }
       }
-      *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = q;
+      *slot = q;
     }
     fence_proxy_async();
     __syncwarp();
@@ -570,8 +601,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     const int sdh = (r0 / p.bw) % p.bh, sdn = r0 / (p.bw * p.bh);
     uint8_t* stage = smem + SM::STAGE_OFF + q * (EPI_NBUF * 4096);
     EpiState es;
-    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats};
-    const bool tma = p.tma_store != 0;
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats, p.tma_store >> 4};
+    const bool tma = (p.tma_store & 1) != 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -582,15 +613,23 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
       const int n = n0 + dn;
       const bool valid = n < p.N;
       const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+      float4 a[8], an[8];
+      if (tma && eo.amode == 2) epi_load_addend(eo, pix, valid, col0, lane, a);      // in flight while the mainloop of this tile finishes
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         if (col0 + c >= p.Cout) break;                     // warp-uniform
+        const bool more = tma && eo.amode == 2 && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout);
+        if (more) epi_load_addend(eo, pix, valid, col0 + c + 32, lane, an);
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q);
+        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, a, (long long)mt * 4 + q);
+        if (more) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = an[j];
+        }
       }
       // this warp is done reading the accumulator: release it to the MMA warp
       tc_fence_before();
@@ -643,6 +682,14 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUt
 // ---------------------------------------------------------------------------------------------------------------
 static int fwd_kernel_version();
 static bool fwd_kernel_version_is2() { return fwd_kernel_version() != 1; }
+static int addend_mode() {      // 0: lane-per-row loads, 1: coalesced through the staging tile, 2: coalesced + prefetched
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_ADDEND");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 static bool tma_store_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -792,29 +839,47 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
     const int dh = row >> 3, dw = row & 7;
     uint8_t* stage = smem + SM::STAGE_OFF + q * (EPI_NBUF * 4096);
     EpiState es;
-    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats};
-    const bool tma = p.tma_store != 0;
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats, p.tma_store >> 4};
+    const bool tma = (p.tma_store & 1) != 0;
     int lt = 0;
     for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
       const int acc = lt & 1;
       const int nt = item % p.n_tiles, mt = item / p.n_tiles;
       const int col0 = nt * BLOCK_N;
-      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
-      tc_fence_after();
-#pragma unroll 1
+      // chunk sequence of an item: (t, c) for t < T, c < BLOCK_N step 32; the addend of chunk i+1 is loaded before chunk i
+      // is processed (and that of chunk 0 before the accumulator is ready)
+      long long pixs[T]; int w0s[T], h0s[T], ns[T];
+#pragma unroll
       for (int t = 0; t < T; ++t) {
         const int lin = mt * T + t;
         const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * 8, h0 = th * 16;
-        const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+        w0s[t] = tw * 8; h0s[t] = th * 16; ns[t] = n;
+        pixs[t] = ((long long)n * p.H + (h0s[t] + dh)) * p.W + (w0s[t] + dw);
+      }
+      int ncol = (p.Cout - col0 + 31) / 32;
+      if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
+      float4 a[8], an[8];
+      if (tma && eo.amode == 2) epi_load_addend(eo, pixs[0], true, col0, lane, a);
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          if (col0 + c >= p.Cout) break;
+        for (int ci = 0; ci < ncol; ++ci) {
+          const int c = ci * 32;
+          const bool more_c = ci + 1 < ncol;
+          const bool more = tma && eo.amode == 2 && (more_c || t + 1 < T);
+          if (more) epi_load_addend(eo, more_c ? pixs[t] : pixs[(t + 1) % T], true, more_c ? col0 + c + 32 : col0, lane, an);
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
-          // this warp's 32 rows = image rows h0+16t+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
-          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, (long long)lin * 4 + q);
+          // this warp's 32 rows = image rows h0+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
+          epi_chunk(v, eo, pixs[t], true, col0 + c, tma, stage, es, &map_y, w0s[t], h0s[t] + 4 * q, ns[t], lane, a,
+                    (long long)(mt * T + t) * 4 + q);
+          if (more) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = an[j];
+          }
         }
       }
       tc_fence_before();
@@ -860,7 +925,7 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   p.total = (p.tiles_w * p.tiles_h * s.N / T) * p.n_tiles;      // callers pick T = 2 only when the tile count is even
   p.base_offset_mode = halo_mode() == 1 ? 1 : 0;
   p.bias = bias; p.addend = addend; p.y = y;
-  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
+  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4)) : 0;
   p.stats = p.tma_store ? stats : nullptr;
   CUtensorMap mx, mw, my;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
@@ -877,8 +942,272 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p);
   return (int)cudaGetLastError();
 }
+// ---------------------------------------------------------------------------------------------------------------
+// forward / dgrad kernel v4 (3x3, Cout >= 128): CTA PAIR, tcgen05.mma.cta_group::2, M = 256.
+// The single-CTA TF32 mainloop is shared-memory-bandwidth bound (a 128xNx8 tf32 UMMA reads 4 KB of A + 32 N bytes of B:
+// 64 clk at N = 128, exactly the MMA's own 64 clk, before any TMA write).  A CTA pair (cluster of 2 = one TPC) issues
+// ONE 256 x N x 8 instruction from the leader: each CTA supplies its own 128 pixel rows of A and only HALF of the B tile
+// (N/2 filter rows), so at N = 256 a CTA reads 8 KB per 128 clk of tensor work and loads half the filter bytes.
+// Each CTA: its own pixel tile (halo box, exactly as k_conv_halo with T = 1), rows [r*N/2, (r+1)*N/2) of every B tile,
+// its own 128 x N fp32 accumulator (double buffered) and epilogue.  Barriers: "full" barriers live in the leader and
+// collect the TMA bytes of BOTH CTAs (cp.async.bulk.tensor.cta_group::2 with the leader's barrier address); "empty" and
+// "accumulator ready" are multicast tcgen05.commit arrivals to the same barrier offset in both CTAs; "accumulator
+// drained" = 8 epilogue-warp arrivals (4 local, 4 remote via mapa) on the leader.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+struct Halo2Smem {
+  static constexpr int ROWS = 18;
+  static constexpr int A_BYTES = ROWS * 16 * 128;                 // one halo box
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 128;             // this CTA's half of a filter tile
+  static constexpr int B_OFF = A_STAGES * A_BYTES;
+  static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;
+  static constexpr int BAR_OFF = STAGE_OFF + 4 * EPI_NBUF * 4096;
+  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+};
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+    k_conv_halo2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_y, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = Halo2Smem<BLOCK_N, A_STAGES, B_STAGES>;
+  constexpr int TAPS = 9;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* a_empty = a_full + A_STAGES;
+  uint64_t* b_full = a_empty + A_STAGES;
+  uint64_t* b_empty = b_full + B_STAGES;
+  uint64_t* tmem_full = b_empty + B_STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]  (used in the leader only)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cchunks = p.Cin >> 5;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<SM::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs' barriers are initialised before any remote signal can arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int ai = 0, bi = 0;
+      for (int item = cluster_id; item < p.total; item += nclusters) {
+        const int nt = item % p.n_tiles, mp = item / p.n_tiles;
+        const int col0 = nt * BLOCK_N;
+        const int lin = mp * 2 + (int)rank;
+        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
+        for (int ch = 0; ch < cchunks; ++ch) {
+          {
+            const int st = ai % A_STAGES;
+            mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
+            if (leader) mbar_expect_tx(&a_full[st], 2 * SM::A_BYTES);           // bytes of both CTAs' boxes
+            tma_load_4d_2cta(smem + st * SM::A_BYTES, &map_x, mapa_rank(smem_u32(&a_full[st]), 0), ch << 5, tw * 8 - 1, th * 16 - 1, n);
+            ++ai;
+          }
+          for (int tap = 0; tap < TAPS; ++tap, ++bi) {
+            const int st = bi % B_STAGES;
+            mbar_wait(&b_empty[st], ((bi / B_STAGES) & 1) ^ 1);
+            if (leader) mbar_expect_tx(&b_full[st], 2 * SM::B_BYTES);
+            tma_load_2d_2cta(smem + SM::B_OFF + st * SM::B_BYTES, &map_w, mapa_rank(smem_u32(&b_full[st]), 0), tap * p.Cin + (ch << 5),
+                             col0 + (int)rank * (BLOCK_N / 2));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_tf32(256, BLOCK_N, 0, 0);
+      int ai = 0, bi = 0, lt = 0;
+      for (int item = cluster_id; item < p.total; item += nclusters, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ch = 0; ch < cchunks; ++ch, ++ai) {
+          const int ast = ai % A_STAGES;
+          mbar_wait(&a_full[ast], (ai / A_STAGES) & 1);
+          const uint32_t sa = smem_u32(smem + ast * SM::A_BYTES);
+          for (int tap = 0; tap < TAPS; ++tap, ++bi) {
+            const int bst = bi % B_STAGES;
+            mbar_wait(&b_full[bst], (bi / B_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
+              const int r = tap / 3, s = tap - 3 * r;
+              const uint32_t arow = sa + (uint32_t)((r * 16 + s) * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t ad = make_smem_desc_bo(arow + k * 32, 2048, 0);
+                uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+                umma_tf32_2cta(tmem_d, ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit_2cta(&b_empty[bst]);
+              if (tap == TAPS - 1) {
+                umma_commit_2cta(&a_empty[ast]);
+                if (ch == cchunks - 1) umma_commit_2cta(&tmem_full[acc]);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dh = row >> 3, dw = row & 7;
+    uint8_t* stage = smem + SM::STAGE_OFF + q * (EPI_NBUF * 4096);
+    EpiState es;
+    const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats, p.tma_store >> 4};
+    const bool tma = (p.tma_store & 1) != 0;
+    int lt = 0;
+    for (int item = cluster_id; item < p.total; item += nclusters, ++lt) {
+      const int acc = lt & 1;
+      const int nt = item % p.n_tiles, mp = item / p.n_tiles;
+      const int col0 = nt * BLOCK_N;
+      const int lin = mp * 2 + (int)rank;
+      const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 8, h0 = th * 16;
+      const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+      float4 a[8];
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        if (col0 + c >= p.Cout) break;
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, a, (long long)lin * 4 + q);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));      // accumulator drained -> leader's MMA warp
+    }
+    if (tma && lane == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // no CTA of the pair leaves (or frees TMEM) while the other may still signal it
+  if (warp == 1) tmem_dealloc_2cta<SM::TMEM_COLS>(tmem_base);
+}
+static int two_cta_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_2CTA");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static bool halo2_eligible(const ConvShape& s) {
+  return two_cta_mode() != 0 && s.k == 3 && s.Cin % 32 == 0 && s.Cout >= 128 && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0 &&
+         (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0) && tma_store_enabled();
+}
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+static int launch_halo2_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                          float* stats, cudaStream_t st) {
+  using SM = Halo2Smem<BLOCK_N, A_STAGES, B_STAGES>;
+  static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
+  static_assert(SM::TMEM_COLS <= 512, "TMEM budget exceeded");
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, A_STAGES, B_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  HaloParams p;
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout;
+  p.tiles_w = s.W / 8; p.tiles_h = s.H / 16;
+  p.n_tiles = (s.Cout + BLOCK_N - 1) / BLOCK_N;
+  p.total = (p.tiles_w * p.tiles_h * s.N / 2) * p.n_tiles;          // items = (pixel-tile pair, n-tile)
+  p.base_offset_mode = 0;
+  p.bias = bias; p.addend = addend; p.y = y;
+  p.tma_store = 1 | (addend_mode() << 4);
+  p.stats = stats;
+  CUtensorMap mx, mw, my;
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, SM::ROWS, 1);
+  if (r) return r;
+  r = make_map_2d(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
+  if (r) return r;
+  r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
+  if (r) return r;
+  int nclusters = num_sms() / 2;
+  if (p.total < nclusters) nclusters = p.total;
+  g_launches += 1;
+  k_conv_halo2<BLOCK_N, A_STAGES, B_STAGES><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, p);
+  return (int)cudaGetLastError();
+}
+static int launch_halo2(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                        float* stats, cudaStream_t st) {
+  if (s.Cout >= 256) return launch_halo2_t<256, 3, 4>(x, w, bias, addend, y, s, stats, st);
+  return launch_halo2_t<128, 3, 6>(x, w, bias, addend, y, s, stats, st);
+}
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        float* stats, cudaStream_t st) {
+  if (halo2_eligible(s)) return launch_halo2(x, w, bias, addend, y, s, stats, st);
   const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
   if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
     return two ? launch_halo_t<32, 2, 2, 8, 5, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5, 5>(x, w, bias, addend, y, s, stats, st);
@@ -1153,7 +1482,7 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   if (r) return r;
   // epilogue store path: TMA store of each warp's 32-row slab (needs 16-byte aligned channel rows)
   CUtensorMap my = mx;
-  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? 1 : 0;
+  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4)) : 0;
   p.stats = p.tma_store ? stats : nullptr;
   if (p.tma_store) {
     p.sbh = (32 / p.bw) < p.bh ? (32 / p.bw) : p.bh;
@@ -1557,10 +1886,16 @@ static Wg2Plan wg2_plan(const ConvShape& s) {
   pl.cgroups = s.Cin / (32 * pl.g);
   pl.ntiles = (s.Cout + pl.n_tile - 1) / pl.n_tile;
   pl.items = (long long)s.N * (s.H / 16) * (s.W / 8);
-  long long pairs = (long long)pl.cgroups * pl.ntiles;
-  long long want = (num_sms() + pairs - 1) / pairs;       // ~one wave of 1-CTA-per-SM blocks
-  if (want > pl.items) want = pl.items;
-  if (want < 1) want = 1;
+  // splits: minimise (waves of 1-CTA-per-SM blocks) x (pixel tiles per CTA + fixed per-CTA cost).  Rounding the split count UP to cover all
+  // SMs (the first version) put e.g. 256->256 at 64x64 on 160 CTAs = two waves of 103 items instead of one wave of 114.
+  const long long pairs = (long long)pl.cgroups * pl.ntiles;
+  long long want = 1, best = -1;
+  for (long long w = 1; w <= pl.items && w <= 2 * num_sms(); ++w) {
+    const long long per = (pl.items + w - 1) / w;
+    const long long waves = (pairs * ((pl.items + per - 1) / per) + num_sms() - 1) / num_sms();
+    const long long cost = waves * (per + 16);        // + fixed cost per CTA (accumulator write-out, reduce) in item units
+    if (best < 0 || cost < best) { best = cost; want = w; }
+  }
   pl.per = (pl.items + want - 1) / want;
   pl.splits = (int)((pl.items + pl.per - 1) / pl.per);
   return pl;

@@ -80,6 +80,8 @@ class Engine:
                 self.mem[L.NET_TARGET] = NetMemory(self.handle, L.NET_TARGET, self.device, trainable=False)
             self.stats = torch.zeros(16, dtype=torch.float32, device=self.device)
             self._bind()
+        self._graphs = {}          # key -> (CUDAGraph, static input tensors); see graphed()
+        self._graph_seen = set()
 
     def _bind(self):
         lib = L.load()
@@ -97,8 +99,40 @@ class Engine:
     def max_batch(self):
         return self.cfg.max_batch
 
+    def drop_graphs(self):
+        """Forget every captured step graph (pointers or derived-filter state they baked in are no longer valid)."""
+        self._graphs = {}
+        self._graph_seen = set()
+
+    def graphed(self, key, inputs, fn):
+        """Run fn(*static_inputs) -- a sequence of engine calls on the current stream -- from a CUDA graph.
+        `inputs` are copied into per-key static tensors first.  The first call with a given key runs eagerly (it also
+        performs the one-time cudaFuncSetAttribute calls), the second captures, later ones replay.  Everything that
+        changes between iterations lives on the device (parameters, Adam moments and step counters, BN statistics),
+        so a replay is one more training step.  Scalars baked into the graph (learning rates, betas) are part of `key`."""
+        if key not in self._graph_seen:
+            self._graph_seen.add(key)
+            return fn(*inputs)
+        ent = self._graphs.get(key)
+        if ent is None:
+            statics = [torch.empty_like(t) for t in inputs]
+            for s_, t in zip(statics, inputs):
+                s_.copy_(t, non_blocking=True)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn(*statics)
+            ent = (g, statics)
+            self._graphs[key] = ent
+        g, statics = ent
+        for s_, t in zip(statics, inputs):
+            s_.copy_(t, non_blocking=True)
+        g.replay()
+        return None
+
     def grow(self, max_batch):
         """Re-create the native handle with a larger workspace; parameter / optimiser memory is kept."""
+        self.drop_graphs()
         lib = L.load()
         steps = {net: lib.sivae_adam_get_step(self.handle, net) for net in self.mem}
         lib.sivae_destroy(self.handle)
@@ -124,6 +158,7 @@ class Engine:
 
     # ---- steps --------------------------------------------------------------------------------------------
     def params_changed(self, net=None):
+        self.drop_graphs()
         lib = L.load()
         for n in (self.mem if net is None else [net]):
             L.check(lib.sivae_params_changed(self.handle, n), "sivae_params_changed")

@@ -462,20 +462,42 @@ def _dist():
     return None
 
 
-def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d):
+def _graph_mode():
+    """SIVAE_CUDA_GRAPH: 0 = never, 1 (default) = single-process runs replay the step from a CUDA graph, 2 = also under
+    torch.distributed (the two NCCL all-reduces are captured with the step)"""
+    try:
+        return int(os.environ.get("SIVAE_CUDA_GRAPH", "1"))
+    except ValueError:
+        return 1
+
+
+def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d, use_graph=None):
     """One E-step + D-step through the engine (reference :551-624).  real: [B,C,S,S] on the model's device; noise:
-    [B,z]; eps: [5,B,z].  Returns the 16-float device statistics tensor (see include/sivae.h)."""
+    [B,z]; eps: [5,B,z].  Returns the 16-float device statistics tensor (see include/sivae.h).
+    The ~1900 kernel launches of a step are replayed from a CUDA graph after the first two calls with the same batch
+    size and hyper-parameters (Engine.graphed); use_graph=False (or SIVAE_CUDA_GRAPH=0) keeps every call eager."""
     eng = model._ensure_engine(real.size(0))
     dist = _dist()
     inv_world = 1.0 / dist.get_world_size() if dist else 1.0
-    eng.e_step(real, noise, eps[:3], hp)
-    if dist:
-        dist.all_reduce(eng.mem[_L.NET_ENCODER].grads)
-    eng.adam(_L.NET_ENCODER, lr_e, inv_world)
-    eng.d_step(eps[3:], hp)
-    if dist:
-        dist.all_reduce(eng.mem[_L.NET_DECODER].grads)
-    eng.adam(_L.NET_DECODER, lr_d, inv_world)
+
+    def step(real_, noise_, eps_):
+        eng.e_step(real_, noise_, eps_[:3], hp)
+        if dist:
+            dist.all_reduce(eng.mem[_L.NET_ENCODER].grads)
+        eng.adam(_L.NET_ENCODER, lr_e, inv_world)
+        eng.d_step(eps_[3:], hp)
+        if dist:
+            dist.all_reduce(eng.mem[_L.NET_DECODER].grads)
+        eng.adam(_L.NET_DECODER, lr_d, inv_world)
+
+    mode = _graph_mode()
+    if use_graph is None:
+        use_graph = mode >= 2 or (mode == 1 and not dist)
+    if use_graph and real.is_cuda and not torch.cuda.is_current_stream_capturing():
+        key = ("introspective", tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world)
+        eng.graphed(key, [real.contiguous(), noise.contiguous(), eps.contiguous()], step)
+    else:
+        step(real, noise, eps)
     return eng.stats
 
 

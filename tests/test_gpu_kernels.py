@@ -54,6 +54,9 @@ CONV_SHAPES = [
     (1, 16, 8, 32, 3, 5),      # row-separable predict conv, one input chunk
     (2, 16, 16, 1, 32, 5),     # row-separable, cdim = 1
     (2, 16, 16, 32, 1, 5),
+    (2, 16, 16, 64, 128, 3),   # Cout >= 128: eligible for the CTA-pair (cta_group::2) kernel when SIVAE_TC_2CTA=1
+    (2, 32, 16, 32, 256, 3),
+    (2, 16, 16, 32, 320, 3),   # second 256-wide output tile only partly filled
 ]
 
 

@@ -193,3 +193,36 @@ def test_train_driver_end_to_end(tmp_path):
         assert torch.equal(model.state_dict()["decoder.fc.0.weight"].cpu(), sd["decoder.fc.0.weight"])
     finally:
         os.chdir(cwd)
+
+
+def test_graph_replay_is_bit_identical_to_eager():
+    """introspective_iteration() replays the step from a CUDA graph from its third call on (Engine.graphed): every
+    kernel is deterministic and all iteration state lives on the device, so five graphed iterations must leave exactly
+    the parameters, Adam/BN state and statistics that five eager iterations leave."""
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    g = torch.Generator().manual_seed(11)
+    reals = [torch.rand(8, 3, 32, 32, generator=g).cuda() for _ in range(5)]
+    noises = [torch.randn(8, 32, generator=g).cuda() for _ in range(5)]
+    epss = [torch.randn(5, 8, 32, generator=g).cuda() for _ in range(5)]
+    hp = E.make_hyper(1.0, 1.0, 256.0, 1e-8, 1.0 / (3 * 32 * 32))
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(4)
+        model = M.SoftIntroVAE(**cfg).to("cuda:0")
+        stats = []
+        for i in range(5):
+            st = M.introspective_iteration(model, reals[i], noises[i], epss[i], hp, 2e-4, 2e-4, use_graph=use_graph)
+            stats.append(st.clone())
+        torch.cuda.synchronize()
+        if use_graph:
+            assert len(model._engine._graphs) == 1, "the graph path did not capture"
+        outs.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, stats))
+    (sd_a, st_a), (sd_b, st_b) = outs
+    for a, b in zip(st_a, st_b):
+        assert torch.equal(a, b)
+    for k in sd_a:
+        assert torch.equal(sd_a[k], sd_b[k]), k
