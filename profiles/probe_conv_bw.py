@@ -23,6 +23,8 @@ CASES_ALL = [
     (32, 8, 8, 512, 512, 3),
     (32, 4, 4, 512, 512, 3),
     (32, 16, 16, 512, 512, 3),
+    (32, 64, 64, 256, 256, 3),
+    (32, 32, 32, 512, 512, 3),
 ]
 
 

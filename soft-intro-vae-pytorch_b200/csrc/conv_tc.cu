@@ -1157,13 +1157,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 static int two_cta_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SIVAE_TC_2CTA");
-    v = e ? atoi(e) : 0;
+    const char* e = getenv("SIVAE_TC_2CTA");      // 0: off, 1 (default): Cout >= 256, 2: Cout >= 128 as well
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
 static bool halo2_eligible(const ConvShape& s) {
-  return two_cta_mode() != 0 && s.k == 3 && s.Cin % 32 == 0 && s.Cout >= 128 && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0 &&
+  // measured (profiles/r01k_probe_2cta.txt): N = 256 pairs run the 256/512-channel layers at 660-800 TFLOP/s against
+  // 530-665 single-CTA; at N = 128 the pair (T = 1 per CTA) is no faster than the single-CTA T = 2 kernel (622 vs 648)
+  const int min_cout = two_cta_mode() >= 2 ? 128 : 256;
+  return two_cta_mode() != 0 && s.k == 3 && s.Cin % 32 == 0 && s.Cout >= min_cout && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0 &&
          (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0) && tma_store_enabled();
 }
 template <int BLOCK_N, int A_STAGES, int B_STAGES>
