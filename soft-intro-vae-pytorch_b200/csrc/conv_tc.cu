@@ -181,7 +181,23 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // Path (a) exists because direct stores (32 rows x 16 B per instruction, each its own L2 transaction) capped every
 // output-heavy layer at ~1.1 TB/s (profiles/r01c_layers_H_halo.md: 1x1 convs 35-126 TFLOP/s, 64-channel 3x3 at 0.45 ms).
 struct EpiOut { const float* bias; const float* addend; float* y; int Cout; float* stats; int amode; };   // stats: BN partials base or null
-struct EpiState { uint32_t n = 0; };     // per-warp count of staged chunks (selects the staging tile)
+struct EpiState { uint32_t n = 0; bool pref = false; };     // per-warp count of staged chunks (selects the staging tile);
+                                                             // pref: the addend of chunk n is already on its way (mode 3)
+// Addend mode 3: the addend tile of a chunk is fetched by TMA straight into the staging tile that chunk will use (same
+// box and swizzle as the output store), one chunk ahead -- no registers, no exposed global-load latency.  abar = this
+// warp's EPI_NBUF mbarriers.  Issued right after the previous chunk's store (or, for the first chunk of an item, before
+// the accumulator is ready).
+__device__ __forceinline__ void epi_prefetch(const float* addend, int amode, EpiState& es, uint8_t* stage0, uint64_t* abar,
+                                             const CUtensorMap* map_add, int col, int cw, int ch, int cn, int lane) {
+  if (!addend || (amode & 3) != 3 || es.pref) return;
+  const uint32_t b = es.n % EPI_NBUF;
+  if (lane == 0) {
+    bulk_wait_read<EPI_NBUF - 1>();       // the store that last used this tile has finished reading it
+    mbar_expect_tx(&abar[b], 4096);
+    tma_load_4d(stage0 + b * 4096, map_add, &abar[b], col, cw, ch, cn);
+  }
+  es.pref = true;
+}
 // srow >= 0 (TMA path only): also emit the per-channel sum / sum of squares of this warp's 32 rows (train-mode BatchNorm
 // statistics, fused so that the conv output is not re-read): stats[srow][0][c] = sum, stats[srow][1][c] = sum of squares
 // addend (residual / accumulated gradient; may alias the output) of one 32x32 chunk: COALESCED loads -- instruction j covers
@@ -202,24 +218,33 @@ __device__ __forceinline__ void epi_load_addend(const EpiOut& o, long long pix, 
 }
 __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
                                           uint8_t* stage0, EpiState& es, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
-                                          const float4 (&a)[8], long long srow = -1) {
+                                          const float4 (&a)[8], long long srow = -1, uint64_t* abar = nullptr,
+                                          const CUtensorMap* map_add = nullptr) {
   if (tma) {
-    uint8_t* stage = stage0 + (es.n % EPI_NBUF) * 4096;
+    const bool tma_add = o.addend && (o.amode & 3) == 3;
+    if (tma_add) epi_prefetch(o.addend, o.amode, es, stage0, abar, map_add, col, cw, ch, cn, lane);     // no-op if already requested
+    const uint32_t buf = es.n % EPI_NBUF, par = (es.n / EPI_NBUF) & 1;
+    uint8_t* stage = stage0 + buf * 4096;
     ++es.n;
+    es.pref = false;
     float4 al[8];
-    const bool staged_add = o.addend && o.amode != 0;
-    if (o.addend && o.amode == 1) epi_load_addend(o, pix, valid, col, lane, al);      // coalesced, not prefetched
-    if (lane == 0) bulk_wait_read<EPI_NBUF - 1>();   // the store issued EPI_NBUF chunks ago has finished reading this tile
-    __syncwarp();
-    if (staged_add) {
+    const bool staged_add = o.addend && (o.amode & 3) != 0;
+    if (o.addend && (o.amode & 3) == 1) epi_load_addend(o, pix, valid, col, lane, al);      // coalesced, not prefetched
+    if (tma_add) {
+      mbar_wait(&abar[buf], par);                    // the addend tile has landed in this staging tile
+    } else {
+      if (lane == 0) bulk_wait_read<EPI_NBUF - 1>();   // the store issued EPI_NBUF chunks ago has finished reading this tile
+      __syncwarp();
+    }
+    if (staged_add && !tma_add) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int row = 4 * j + (lane >> 3);
-        *reinterpret_cast<float4*>(stage + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = (o.amode == 2) ? a[j] : al[j];
+        *reinterpret_cast<float4*>(stage + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = ((o.amode & 3) == 2) ? a[j] : al[j];
       }
       __syncwarp();
     }
-    const float* add0 = (o.addend && o.amode == 0 && valid) ? o.addend + pix * o.Cout + col : nullptr;   // mode 0: lane-per-row loads
+    const float* add0 = (o.addend && (o.amode & 3) == 0 && valid) ? o.addend + pix * o.Cout + col : nullptr;   // mode 0: lane-per-row loads
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 q = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
@@ -239,7 +264,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, lo
       }
       *slot = q;
     }
-    fence_proxy_async();
+    if (!(o.amode & 8)) fence_proxy_async();      // bit 3 of amode: timing experiment only (SIVAE_TC_NOFENCE=1, results invalid)
     __syncwarp();
     if (lane == 0) {
       tma_store_4d(map_y, stage, col, cw, ch, cn);
@@ -456,7 +481,7 @@ __global__ void __launch_bounds__(192) k_conv_fwd_tc(const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+  if (warp == 1) { __syncwarp(); tmem_dealloc<BLOCK_N>(tmem_base); }
 }
 
 static void pick_tile(int H, int W, int* bw, int* bh, int* bn) {
@@ -506,13 +531,14 @@ struct Fwd2Smem {
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
   static constexpr int STAGE_OFF = STAGES * STAGE_BYTES;          // 4 warps x EPI_NBUF x 4 KB epilogue staging tiles
   static constexpr int BAR_OFF = STAGE_OFF + 4 * EPI_NBUF * 4096;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 4 * EPI_NBUF) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__ CUtensorMap map_x,
                                                          const __grid_constant__ CUtensorMap map_w,
-                                                         const __grid_constant__ CUtensorMap map_y, const FwdParams p,
+                                                         const __grid_constant__ CUtensorMap map_y,
+                                                         const __grid_constant__ CUtensorMap map_add, const FwdParams p,
                                                          const int n_tiles, const int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
   using SM = Fwd2Smem<BLOCK_N, STAGES>;
@@ -521,7 +547,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* abar = tmem_empty + 2;           // [4 warps][EPI_NBUF] addend-tile barriers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(abar + 4 * EPI_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin >> 5;
@@ -533,6 +560,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     tma_prefetch_desc(&map_w);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 4 * EPI_NBUF; ++i) mbar_init(&abar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_ptr);
@@ -564,21 +592,20 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
-    int it = 0, lt = 0;                                    // lt = local tile counter
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);    // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-      const int z = (tile / n_tiles) % p.ksplit;
-      const int kb0 = z * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int st = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[st], ph);
+    if (elect_one()) {               // one thread runs the whole issue loop (see k_conv_halo)
+      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+      int it = 0, lt = 0;                                    // lt = local tile counter
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);    // epilogue has drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const int z = (tile / n_tiles) % p.ksplit;
+        const int kb0 = z * p.kb_per, kb1 = min(num_kb, kb0 + p.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[st], ph);
           const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
           const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
@@ -590,7 +617,6 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
           umma_commit(&empty[st]);
           if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
-        __syncwarp();
       }
     }
   } else {
@@ -614,18 +640,22 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
       const bool valid = n < p.N;
       const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
       float4 a[8], an[8];
-      if (tma && eo.amode == 2) epi_load_addend(eo, pix, valid, col0, lane, a);      // in flight while the mainloop of this tile finishes
+      if (tma && (eo.amode & 3) == 2) epi_load_addend(eo, pix, valid, col0, lane, a);      // in flight while the mainloop of this tile finishes
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0, h0 + sdh, n0 + sdn, lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         if (col0 + c >= p.Cout) break;                     // warp-uniform
-        const bool more = tma && eo.amode == 2 && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout);
+        const bool more = tma && (eo.amode & 3) == 2 && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout);
         if (more) epi_load_addend(eo, pix, valid, col0 + c + 32, lane, an);
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, a, (long long)mt * 4 + q);
+        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, a, (long long)mt * 4 + q,
+                  abar + q * EPI_NBUF, &map_add);
+        if (tma && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout))
+          epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + sdh, n0 + sdn, lane);
         if (more) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) a[j] = an[j];
@@ -640,7 +670,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<SM::TMEM_COLS>(tmem_base);
+  if (warp == 1) { __syncwarp(); tmem_dealloc<SM::TMEM_COLS>(tmem_base); }
 }
 
 static int num_sms() {
@@ -653,8 +683,8 @@ static int num_sms() {
   return n;
 }
 template <int BLOCK_N, int STAGES>
-static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const FwdParams& p, int m_tiles,
-                         cudaStream_t st) {
+static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& madd,
+                         const FwdParams& p, int m_tiles, cudaStream_t st) {
   using SM = Fwd2Smem<BLOCK_N, STAGES>;
   static bool attr = false;
   if (!attr) {
@@ -666,7 +696,7 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUt
   const int total = m_tiles * n_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   g_launches += 1;
-  k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p, n_tiles, total);
+  k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p, n_tiles, total);
   return (int)cudaGetLastError();
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -687,6 +717,8 @@ static int addend_mode() {      // 0: lane-per-row loads, 1: coalesced through t
   if (v < 0) {
     const char* e = getenv("SIVAE_TC_ADDEND");
     v = e ? atoi(e) : 1;
+    const char* nf = getenv("SIVAE_TC_NOFENCE");
+    if (nf && nf[0] == '1') v |= 8;
   }
   return v;
 }
@@ -721,21 +753,26 @@ struct HaloParams {
 template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 struct HaloSmem {
   static constexpr int ROWS = 16 + KH - 1;           // one halo box per 16x8 pixel tile
-  static constexpr int BW = (KW == 1) ? 8 : 16;      // box width in pixels (8 output columns + column halo)
-  static constexpr int BOX_BYTES = ROWS * BW * 128;
+  // box width in pixels = 8 output columns + column halo.  The 8-pixel row groups of the A operand sit BW*128 bytes apart
+  // (SBO): any multiple of 16 B works because the swizzle is a function of absolute address bits, so the box is exactly
+  // as wide as the halo needs (10 for 3x3: 37 % less L2->SM traffic and shared memory than the first 16-wide boxes).
+  static constexpr int BW = 8 + KW - 1;
+  static constexpr int BOX_TX = ROWS * BW * 128;                       // bytes one TMA box delivers
+  static constexpr int BOX_BYTES = (BOX_TX + 1023) / 1024 * 1024;      // boxes stay 1024B-aligned
   static constexpr int A_BYTES = T * BOX_BYTES;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int B_OFF = A_STAGES * A_BYTES;
   static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;     // 4 warps x EPI_NBUF x 4 KB epilogue staging tiles
   static constexpr int BAR_OFF = STAGE_OFF + 4 * EPI_NBUF * 4096;
-  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4 + 4 * EPI_NBUF;
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
 template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CUtensorMap map_x,
                                                       const __grid_constant__ CUtensorMap map_w,
-                                                      const __grid_constant__ CUtensorMap map_y, const HaloParams p) {
+                                                      const __grid_constant__ CUtensorMap map_y,
+                                                      const __grid_constant__ CUtensorMap map_add, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW>;
   constexpr int TAPS = KH * KW, PADH = KH / 2, PADW = KW / 2, BW = SM::BW;
@@ -746,7 +783,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
   uint64_t* b_empty = b_full + B_STAGES;
   uint64_t* tmem_full = b_empty + B_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* abar = tmem_empty + 2;            // [4 warps][EPI_NBUF] addend-tile barriers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(abar + 4 * EPI_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cchunks = p.Cin >> 5;
@@ -757,6 +795,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 4 * EPI_NBUF; ++i) mbar_init(&abar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_ptr);
@@ -775,7 +814,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
           {
             const int st = ai % A_STAGES;
             mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
-            mbar_expect_tx(&a_full[st], SM::A_BYTES);
+            mbar_expect_tx(&a_full[st], T * SM::BOX_TX);
 #pragma unroll
             for (int t = 0; t < T; ++t) {        // the T pixel tiles of an item are consecutive in (n, tile row, tile column) order
               const int lin = mt * T + t;
@@ -794,22 +833,24 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
-    int ai = 0, bi = 0, lt = 0;
-    for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
-      const int acc = lt & 1;
-      mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T * BLOCK_N);
-      for (int ch = 0; ch < cchunks; ++ch, ++ai) {
-        const int ast = ai % A_STAGES;
-        mbar_wait(&a_full[ast], (ai / A_STAGES) & 1);
-        const uint32_t sa = smem_u32(smem + ast * SM::A_BYTES);
-        for (int tap = 0; tap < TAPS; ++tap, ++bi) {
-          const int bst = bi % B_STAGES;
-          mbar_wait(&b_full[bst], (bi / B_STAGES) & 1);
-          tc_fence_after();
-          if (elect_one()) {
+    // ONE elected thread runs the whole issue loop (barrier waits included): no warp-wide election / re-convergence per
+    // filter tap between the MMAs
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+      int ai = 0, bi = 0, lt = 0;
+      for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T * BLOCK_N);
+        for (int ch = 0; ch < cchunks; ++ch, ++ai) {
+          const int ast = ai % A_STAGES;
+          mbar_wait(&a_full[ast], (ai / A_STAGES) & 1);
+          const uint32_t sa = smem_u32(smem + ast * SM::A_BYTES);
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap, ++bi) {
+            const int bst = bi % B_STAGES;
+            mbar_wait(&b_full[bst], (bi / B_STAGES) & 1);
             const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
             const int r = tap / KW, s = tap - KW * r;
             const uint32_t bo = p.base_offset_mode ? (uint32_t)s : 0u;
@@ -829,7 +870,6 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
               if (ch == cchunks - 1) umma_commit(&tmem_full[acc]);
             }
           }
-          __syncwarp();
         }
       }
     }
@@ -859,7 +899,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
       int ncol = (p.Cout - col0 + 31) / 32;
       if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
       float4 a[8], an[8];
-      if (tma && eo.amode == 2) epi_load_addend(eo, pixs[0], true, col0, lane, a);
+      if (tma && (eo.amode & 3) == 2) epi_load_addend(eo, pixs[0], true, col0, lane, a);
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0s[0], h0s[0] + 4 * q, ns[0], lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll
@@ -869,13 +910,18 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
         for (int ci = 0; ci < ncol; ++ci) {
           const int c = ci * 32;
           const bool more_c = ci + 1 < ncol;
-          const bool more = tma && eo.amode == 2 && (more_c || t + 1 < T);
+          const bool more = tma && (eo.amode & 3) == 2 && (more_c || t + 1 < T);
           if (more) epi_load_addend(eo, more_c ? pixs[t] : pixs[(t + 1) % T], true, more_c ? col0 + c + 32 : col0, lane, an);
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           // this warp's 32 rows = image rows h0+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
           epi_chunk(v, eo, pixs[t], true, col0 + c, tma, stage, es, &map_y, w0s[t], h0s[t] + 4 * q, ns[t], lane, a,
-                    (long long)(mt * T + t) * 4 + q);
+                    (long long)(mt * T + t) * 4 + q, abar + q * EPI_NBUF, &map_add);
+          if (tma && (more_c || t + 1 < T)) {
+            const int tn = more_c ? t : (t + 1) % T;
+            epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, more_c ? col0 + c + 32 : col0, w0s[tn],
+                         h0s[tn] + 4 * q, ns[tn], lane);
+          }
           if (more) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = an[j];
@@ -890,7 +936,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<SM::TMEM_COLS>(tmem_base);
+  if (warp == 1) { __syncwarp(); tmem_dealloc<SM::TMEM_COLS>(tmem_base); }
 }
 // 0 = off (v2 kernel), 2 = on with descriptor base_offset = 0 (default), 1 = on with base_offset = s.
 // Measured on B200 (tests/tc_probe.py, profiles/r01b_halo_probe.txt): the tensor core swizzles on ABSOLUTE shared-memory
@@ -937,9 +983,14 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
     r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
     if (r) return r;
   }
+  CUtensorMap madd = my;
+  if (p.tma_store && addend && (addend_mode() & 3) == 3) {
+    r = make_store_map(&madd, (float*)addend, s.N, s.H, s.W, s.Cout, 8, 4, 1);
+    if (r) return r;
+  }
   const int grid = p.total < num_sms() ? p.total : num_sms();
   g_launches += 1;
-  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, p);
+  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
   return (int)cudaGetLastError();
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -960,6 +1011,7 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();      // .aligned: the warp must be converged (single-thread role loops diverge it)
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
@@ -1002,24 +1054,26 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
 }
-template <int BLOCK_N, int A_STAGES, int B_STAGES>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
 struct Halo2Smem {
-  static constexpr int ROWS = 18;
-  static constexpr int A_BYTES = ROWS * 16 * 128;                 // one halo box
+  static constexpr int ROWS = 18, BW = 10;
+  static constexpr int BOX_TX = ROWS * BW * 128;                  // bytes of one halo box
+  static constexpr int BOX_BYTES = (BOX_TX + 1023) / 1024 * 1024;
+  static constexpr int A_BYTES = T * BOX_BYTES;                   // T pixel tiles per CTA share every filter half-tile
   static constexpr int B_BYTES = (BLOCK_N / 2) * 128;             // this CTA's half of a filter tile
   static constexpr int B_OFF = A_STAGES * A_BYTES;
   static constexpr int STAGE_OFF = B_OFF + B_STAGES * B_BYTES;
   static constexpr int BAR_OFF = STAGE_OFF + 4 * EPI_NBUF * 4096;
-  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4;
+  static constexpr int NBAR = 2 * A_STAGES + 2 * B_STAGES + 4 + 4 * EPI_NBUF;
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
-template <int BLOCK_N, int A_STAGES, int B_STAGES>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     k_conv_halo2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_y, const HaloParams p) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_add, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  using SM = Halo2Smem<BLOCK_N, A_STAGES, B_STAGES>;
+  using SM = Halo2Smem<BLOCK_N, T, A_STAGES, B_STAGES>;
   constexpr int TAPS = 9;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
@@ -1028,7 +1082,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   uint64_t* b_empty = b_full + B_STAGES;
   uint64_t* tmem_full = b_empty + B_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]  (used in the leader only)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* abar = tmem_empty + 2;            // [4 warps][EPI_NBUF] addend-tile barriers (CTA-local)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(abar + 4 * EPI_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1042,6 +1097,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    for (int i = 0; i < 4 * EPI_NBUF; ++i) mbar_init(&abar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta<SM::TMEM_COLS>(tmem_ptr);
@@ -1057,14 +1113,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       for (int item = cluster_id; item < p.total; item += nclusters) {
         const int nt = item % p.n_tiles, mp = item / p.n_tiles;
         const int col0 = nt * BLOCK_N;
-        const int lin = mp * 2 + (int)rank;
-        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
         for (int ch = 0; ch < cchunks; ++ch) {
           {
             const int st = ai % A_STAGES;
             mbar_wait(&a_empty[st], ((ai / A_STAGES) & 1) ^ 1);
-            if (leader) mbar_expect_tx(&a_full[st], 2 * SM::A_BYTES);           // bytes of both CTAs' boxes
-            tma_load_4d_2cta(smem + st * SM::A_BYTES, &map_x, mapa_rank(smem_u32(&a_full[st]), 0), ch << 5, tw * 8 - 1, th * 16 - 1, n);
+            if (leader) mbar_expect_tx(&a_full[st], 2 * T * SM::BOX_TX);        // bytes of both CTAs' boxes
+            const uint32_t bar = mapa_rank(smem_u32(&a_full[st]), 0);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const int lin = (mp * 2 + (int)rank) * T + t;
+              const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
+              tma_load_4d_2cta(smem + st * SM::A_BYTES + t * SM::BOX_BYTES, &map_x, bar, ch << 5, tw * 8 - 1, th * 16 - 1, n);
+            }
             ++ai;
           }
           for (int tap = 0; tap < TAPS; ++tap, ++bi) {
@@ -1078,39 +1138,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       }
     }
   } else if (warp == 1) {
-    if (leader) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32(256, BLOCK_N, 0, 0);
       int ai = 0, bi = 0, lt = 0;
       for (int item = cluster_id; item < p.total; item += nclusters, ++lt) {
         const int acc = lt & 1;
         mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T * BLOCK_N);
         for (int ch = 0; ch < cchunks; ++ch, ++ai) {
           const int ast = ai % A_STAGES;
           mbar_wait(&a_full[ast], (ai / A_STAGES) & 1);
           const uint32_t sa = smem_u32(smem + ast * SM::A_BYTES);
+#pragma unroll
           for (int tap = 0; tap < TAPS; ++tap, ++bi) {
             const int bst = bi % B_STAGES;
             mbar_wait(&b_full[bst], (bi / B_STAGES) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
-              const int r = tap / 3, s = tap - 3 * r;
-              const uint32_t arow = sa + (uint32_t)((r * 16 + s) * 128);
+            const uint32_t sb = smem_u32(smem + SM::B_OFF + bst * SM::B_BYTES);
+            const int r = tap / 3, s = tap - 3 * r;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              const uint32_t arow = sa + (uint32_t)(t * SM::BOX_BYTES + (r * SM::BW + s) * 128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                uint64_t ad = make_smem_desc_bo(arow + k * 32, 2048, 0);
+                uint64_t ad = make_smem_desc_bo(arow + k * 32, SM::BW * 128, 0);
                 uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-                umma_tf32_2cta(tmem_d, ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              }
-              umma_commit_2cta(&b_empty[bst]);
-              if (tap == TAPS - 1) {
-                umma_commit_2cta(&a_empty[ast]);
-                if (ch == cchunks - 1) umma_commit_2cta(&tmem_full[acc]);
+                umma_tf32_2cta(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
               }
             }
-            __syncwarp();
+            umma_commit_2cta(&b_empty[bst]);
+            if (tap == TAPS - 1) {
+              umma_commit_2cta(&a_empty[ast]);
+              if (ch == cchunks - 1) umma_commit_2cta(&tmem_full[acc]);
+            }
           }
         }
       }
@@ -1128,20 +1188,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       const int acc = lt & 1;
       const int nt = item % p.n_tiles, mp = item / p.n_tiles;
       const int col0 = nt * BLOCK_N;
-      const int lin = mp * 2 + (int)rank;
-      const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * 8, h0 = th * 16;
-      const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
       float4 a[8];
+      int w0s[T], h0s[T], ns[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int lin = (mp * 2 + (int)rank) * T + t;
+        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h;
+        ns[t] = lin / (p.tiles_w * p.tiles_h); w0s[t] = tw * 8; h0s[t] = th * 16;
+      }
+      int ncol = (p.Cout - col0 + 31) / 32;
+      if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0s[0], h0s[0] + 4 * q, ns[0], lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int lin = (mp * 2 + (int)rank) * T + t;
+        const long long pix = ((long long)ns[t] * p.H + (h0s[t] + dh)) * p.W + (w0s[t] + dw);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        if (col0 + c >= p.Cout) break;
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, a, (long long)lin * 4 + q);
+        for (int ci = 0; ci < ncol; ++ci) {
+          const int c = ci * 32;
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0s[t], h0s[t] + 4 * q, ns[t], lane, a, (long long)lin * 4 + q,
+                    abar + q * EPI_NBUF, &map_add);
+          const bool more_c = ci + 1 < ncol;
+          if (tma && (more_c || t + 1 < T)) {
+            const int tn = more_c ? t : (t + 1) % T;
+            epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, more_c ? col0 + c + 32 : col0, w0s[tn],
+                         h0s[tn] + 4 * q, ns[tn], lane);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1152,32 +1230,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                 // no CTA of the pair leaves (or frees TMEM) while the other may still signal it
-  if (warp == 1) tmem_dealloc_2cta<SM::TMEM_COLS>(tmem_base);
+  if (warp == 1) { __syncwarp(); tmem_dealloc_2cta<SM::TMEM_COLS>(tmem_base); }
 }
 static int two_cta_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SIVAE_TC_2CTA");      // 0: off, 1 (default): Cout >= 256, 2: Cout >= 128 as well
-    v = e ? atoi(e) : 1;
+    const char* e = getenv("SIVAE_TC_2CTA");      // 0: off, 1: Cout >= 256 only, 2 (default): every 3x3 layer with Cout > 32
+    v = e ? atoi(e) : 2;
   }
   return v;
 }
 static bool halo2_eligible(const ConvShape& s) {
   // measured (profiles/r01k_probe_2cta.txt): N = 256 pairs run the 256/512-channel layers at 660-800 TFLOP/s against
   // 530-665 single-CTA; at N = 128 the pair (T = 1 per CTA) is no faster than the single-CTA T = 2 kernel (622 vs 648)
-  const int min_cout = two_cta_mode() >= 2 ? 128 : 256;
+  // mode 2 adds T = 2 pairs for the 128- and 64-channel layers (half the filter bytes and 6 resp. 5 KB instead of 8 / 6 KB
+  // of operand reads per MMA and CTA)
+  const int min_cout = two_cta_mode() >= 2 ? 33 : 256;
+  const long long tiles = (long long)s.N * (s.H / 16) * (s.W / 8);
   return two_cta_mode() != 0 && s.k == 3 && s.Cin % 32 == 0 && s.Cout >= min_cout && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0 &&
-         (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0) && tma_store_enabled();
+         tiles % (s.Cout >= 256 ? 2 : 4) == 0 && tma_store_enabled();
 }
-template <int BLOCK_N, int A_STAGES, int B_STAGES>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
 static int launch_halo2_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                           float* stats, cudaStream_t st) {
-  using SM = Halo2Smem<BLOCK_N, A_STAGES, B_STAGES>;
+  using SM = Halo2Smem<BLOCK_N, T, A_STAGES, B_STAGES>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static_assert(SM::TMEM_COLS <= 512, "TMEM budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, A_STAGES, B_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -1185,28 +1266,34 @@ static int launch_halo2_t(const float* x, const float* w, const float* bias, con
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout;
   p.tiles_w = s.W / 8; p.tiles_h = s.H / 16;
   p.n_tiles = (s.Cout + BLOCK_N - 1) / BLOCK_N;
-  p.total = (p.tiles_w * p.tiles_h * s.N / 2) * p.n_tiles;          // items = (pixel-tile pair, n-tile)
+  p.total = (p.tiles_w * p.tiles_h * s.N / (2 * T)) * p.n_tiles;    // items = (2T consecutive pixel tiles, n-tile)
   p.base_offset_mode = 0;
   p.bias = bias; p.addend = addend; p.y = y;
   p.tma_store = 1 | (addend_mode() << 4);
   p.stats = stats;
   CUtensorMap mx, mw, my;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, 16, SM::ROWS, 1);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
   if (r) return r;
   r = make_map_2d(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
   if (r) return r;
   r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
   if (r) return r;
+  CUtensorMap madd = my;
+  if (addend && (addend_mode() & 3) == 3) {
+    r = make_store_map(&madd, (float*)addend, s.N, s.H, s.W, s.Cout, 8, 4, 1);
+    if (r) return r;
+  }
   int nclusters = num_sms() / 2;
   if (p.total < nclusters) nclusters = p.total;
   g_launches += 1;
-  k_conv_halo2<BLOCK_N, A_STAGES, B_STAGES><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, p);
+  k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
   return (int)cudaGetLastError();
 }
 static int launch_halo2(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                         float* stats, cudaStream_t st) {
-  if (s.Cout >= 256) return launch_halo2_t<256, 3, 4>(x, w, bias, addend, y, s, stats, st);
-  return launch_halo2_t<128, 3, 6>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout >= 256) return launch_halo2_t<256, 1, 3, 6>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout > 64) return launch_halo2_t<128, 2, 2, 8>(x, w, bias, addend, y, s, stats, st);
+  return launch_halo2_t<64, 2, 3, 8>(x, w, bias, addend, y, s, stats, st);
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        float* stats, cudaStream_t st) {
@@ -1215,8 +1302,8 @@ static int launch_halo(const float* x, const float* w, const float* bias, const 
   if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
     return two ? launch_halo_t<32, 2, 2, 8, 5, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5, 5>(x, w, bias, addend, y, s, stats, st);
   }
-  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 3, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 5, 3, 3>(x, w, bias, addend, y, s, stats, st);
-  return two ? launch_halo_t<64, 2, 2, 6, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3, 3>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 5, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 7, 3, 3>(x, w, bias, addend, y, s, stats, st);
+  return two ? launch_halo_t<64, 2, 3, 6, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3, 3>(x, w, bias, addend, y, s, stats, st);
 }
 // ---------------------------------------------------------------------------------------------------------------
 // Row-separable form of the two image-facing 5x5 convolutions (c = cdim <= 3 channels on one side).
@@ -1500,10 +1587,15 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
     }
     if (r) return r;
   }
-  if (block_n == 256) r = launch_fwd2_t<256, 4>(mx, mw, my, p, m_tiles, st);
-  else if (block_n == 128) r = launch_fwd2_t<128, 5>(mx, mw, my, p, m_tiles, st);
-  else if (block_n == 64) r = launch_fwd2_t<64, 7>(mx, mw, my, p, m_tiles, st);
-  else r = launch_fwd2_t<32, 8>(mx, mw, my, p, m_tiles, st);
+  CUtensorMap madd = my;
+  if (p.tma_store && p.addend && (addend_mode() & 3) == 3) {
+    r = make_store_map(&madd, (float*)p.addend, s.N, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
+    if (r) return r;
+  }
+  if (block_n == 256) r = launch_fwd2_t<256, 4>(mx, mw, my, madd, p, m_tiles, st);
+  else if (block_n == 128) r = launch_fwd2_t<128, 5>(mx, mw, my, madd, p, m_tiles, st);
+  else if (block_n == 64) r = launch_fwd2_t<64, 7>(mx, mw, my, madd, p, m_tiles, st);
+  else r = launch_fwd2_t<32, 8>(mx, mw, my, madd, p, m_tiles, st);
   if (r || pl.ksplit <= 1) return r;
   const long long n4 = (long long)s.N * s.H * s.W * s.Cout / 4, slab4 = (long long)pl.npad * s.H * s.W * s.Cout / 4;
   unsigned blocks = (unsigned)((n4 + 255) / 256);
@@ -1601,12 +1693,12 @@ __global__ void __launch_bounds__(192) k_conv_wgrad_tc(const __grid_constant__ C
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
+    if (elect_one())                   // one thread runs the whole issue loop (see k_conv_halo)
     for (int i = 0; i < num_kb; ++i) {
       const int st = i % STAGES;
       const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(&full[st], ph);
-      tc_fence_after();
-      if (elect_one()) {
+      {
         const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
         const uint32_t sb = sa + SM::A_BYTES;
 #pragma unroll
@@ -1621,7 +1713,6 @@ __global__ void __launch_bounds__(192) k_conv_wgrad_tc(const __grid_constant__ C
         umma_commit(&empty[st]);
         if (i == num_kb - 1) umma_commit(tmem_full);
       }
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;
@@ -1652,7 +1743,7 @@ __global__ void __launch_bounds__(192) k_conv_wgrad_tc(const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_base);
+  if (warp == 1) { __syncwarp(); tmem_dealloc<BLOCK_N>(tmem_base); }
 }
 
 __global__ void k_wg_reduce(const float* __restrict__ part, float* __restrict__ out, long long n, int splits, int accumulate) {
@@ -1740,8 +1831,9 @@ constexpr int WG2_DY_BYTES = 16 * 8 * 128;     // dy box (32 channels)
 // image, only MN chunk 0 is a real tap there -- chunks 1..3 are phantoms that cost tensor time but no extra traffic)
 template <int N_TILE, int G, int STAGES, int KH, int KW>
 struct Wg2Smem {
-  static constexpr int BW = (KW == 1) ? 8 : 16;
-  static constexpr int X_BYTES = (16 + KH - 1) * BW * 128;     // x halo box
+  static constexpr int BW = 8 + KW - 1;                          // box exactly as wide as the column halo needs
+  static constexpr int X_TX = (16 + KH - 1) * BW * 128;          // bytes of one x halo box
+  static constexpr int X_BYTES = (X_TX + 1023) / 1024 * 1024;
   static constexpr int A_BYTES = G * X_BYTES;
   static constexpr int B_BYTES = (N_TILE / 32) * WG2_DY_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -1790,7 +1882,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
       for (int i = 0; i < num_items; ++i) {
         const int st = i % STAGES;
         mbar_wait(&empty[st], ((i / STAGES) & 1) ^ 1);
-        mbar_expect_tx(&full[st], (uint32_t)(G * WG2_X_BYTES + b_chunks * WG2_DY_BYTES));
+        mbar_expect_tx(&full[st], (uint32_t)(G * SM::X_TX + b_chunks * WG2_DY_BYTES));
         const long long item = it_begin + i;
         const int tw = (int)(item % p.tiles_w), th = (int)((item / p.tiles_w) % p.tiles_h);
         const int n = (int)(item / ((long long)p.tiles_w * p.tiles_h));
@@ -1805,11 +1897,11 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_tf32(128, N_TILE, 1, 1);
+    if (elect_one())                   // one thread runs the whole issue loop (see k_conv_halo)
     for (int i = 0; i < num_items; ++i) {
       const int st = i % STAGES;
       mbar_wait(&full[st], (i / STAGES) & 1);
-      tc_fence_after();
-      if (elect_one()) {
+      {
         const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
         const uint32_t sb = sa + SM::A_BYTES;
 #pragma unroll
@@ -1830,7 +1922,6 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
         umma_commit(&empty[st]);
         if (i == num_items - 1) umma_commit(tmem_full);
       }
-      __syncwarp();
     }
   } else {
     const int q = warp & 3;          // = filter column s of this warp's 32 accumulator rows; s == 3 is the phantom tap
@@ -1868,7 +1959,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<SM::TMEM_COLS>(tmem_base);
+  if (warp == 1) { __syncwarp(); tmem_dealloc<SM::TMEM_COLS>(tmem_base); }
 }
 static int wgrad_halo_mode() {
   static int v = -1;
