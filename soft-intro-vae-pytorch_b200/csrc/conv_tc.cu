@@ -180,6 +180,22 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 //  (b) direct per-thread stores (narrow outputs whose channel count is not a multiple of 4, e.g. the 3-channel image).
 // Path (a) exists because direct stores (32 rows x 16 B per instruction, each its own L2 transaction) capped every
 // output-heavy layer at ~1.1 TB/s (profiles/r01c_layers_H_halo.md: 1x1 convs 35-126 TFLOP/s, 64-channel 3x3 at 0.45 ms).
+// explicit shared-space accesses for the staging tiles: their addresses are derived from a 1024B-aligned (integer
+// round-up) base, so the compiler no longer knows the state space and would emit GENERIC ld/st (ST.E.128 / LD.E in the
+// SASS of the first versions) for every staging access
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
 struct EpiOut { const float* bias; const float* addend; float* y; int Cout; float* stats; int amode; };   // stats: BN partials base or null
 struct EpiState { uint32_t n = 0; bool pref = false; };     // per-warp count of staged chunks (selects the staging tile);
                                                              // pref: the addend of chunk n is already on its way (mode 3)
@@ -218,13 +234,13 @@ __device__ __forceinline__ void epi_load_addend(const EpiOut& o, long long pix, 
 }
 __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
                                           uint8_t* stage0, EpiState& es, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
-                                          const float4 (&a)[8], long long srow = -1, uint64_t* abar = nullptr,
-                                          const CUtensorMap* map_add = nullptr) {
+                                          long long srow = -1, uint64_t* abar = nullptr, const CUtensorMap* map_add = nullptr) {
   if (tma) {
     const bool tma_add = o.addend && (o.amode & 3) == 3;
     if (tma_add) epi_prefetch(o.addend, o.amode, es, stage0, abar, map_add, col, cw, ch, cn, lane);     // no-op if already requested
     const uint32_t buf = es.n % EPI_NBUF, par = (es.n / EPI_NBUF) & 1;
     uint8_t* stage = stage0 + buf * 4096;
+    const uint32_t stage_s = smem_u32(stage);
     ++es.n;
     es.pref = false;
     float4 al[8];
@@ -240,7 +256,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, lo
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int row = 4 * j + (lane >> 3);
-        *reinterpret_cast<float4*>(stage + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = ((o.amode & 3) == 2) ? a[j] : al[j];
+        sts128(stage_s + row * 128 + (((lane & 7) ^ (row & 7)) << 4), al[j]);
       }
       __syncwarp();
     }
@@ -248,21 +264,21 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, lo
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 q = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-      float4* slot = reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4));
+      const uint32_t slot = stage_s + lane * 128 + ((j ^ (lane & 7)) << 4);
       if (col + 4 * j < o.Cout) {
         if (o.bias) {
           float4 b = __ldg(reinterpret_cast<const float4*>(o.bias + col + 4 * j));
           q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
         }
         if (staged_add) {
-          const float4 d = *slot;
+          const float4 d = lds128(slot);
           q.x += d.x; q.y += d.y; q.z += d.z; q.w += d.w;
         } else if (add0) {
           const float4 d = *reinterpret_cast<const float4*>(add0 + 4 * j);
           q.x += d.x; q.y += d.y; q.z += d.z; q.w += d.w;
         }
       }
-      *slot = q;
+      sts128(slot, q);
     }
     if (!(o.amode & 8)) fence_proxy_async();      // bit 3 of amode: timing experiment only (SIVAE_TC_NOFENCE=1, results invalid)
     __syncwarp();
@@ -276,7 +292,7 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, lo
       const int cj = lane >> 2, ce = (lane & 3) << 2;
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        const float x = *reinterpret_cast<const float*>(stage + r * 128 + ((cj ^ (r & 7)) << 4) + ce);
+        const float x = lds32(stage_s + r * 128 + ((cj ^ (r & 7)) << 4) + ce);
         sm += x;
         sq = fmaf(x, x, sq);
       }
@@ -639,8 +655,6 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
       const int n = n0 + dn;
       const bool valid = n < p.N;
       const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
-      float4 a[8], an[8];
-      if (tma && (eo.amode & 3) == 2) epi_load_addend(eo, pix, valid, col0, lane, a);      // in flight while the mainloop of this tile finishes
       if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0, h0 + sdh, n0 + sdn, lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
@@ -648,18 +662,12 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         if (col0 + c >= p.Cout) break;                     // warp-uniform
-        const bool more = tma && (eo.amode & 3) == 2 && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout);
-        if (more) epi_load_addend(eo, pix, valid, col0 + c + 32, lane, an);
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, a, (long long)mt * 4 + q,
+        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q,
                   abar + q * EPI_NBUF, &map_add);
-        if (tma && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout))
+        if (tma && eo.addend && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout))
           epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + sdh, n0 + sdn, lane);
-        if (more) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = an[j];
-        }
       }
       // this warp is done reading the accumulator: release it to the MMA warp
       tc_fence_before();
@@ -712,11 +720,16 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUt
 // ---------------------------------------------------------------------------------------------------------------
 static int fwd_kernel_version();
 static bool fwd_kernel_version_is2() { return fwd_kernel_version() != 1; }
-static int addend_mode() {      // 0: lane-per-row loads, 1: coalesced through the staging tile, 2: coalesced + prefetched
+// how the epilogue fetches an addend tile.  0: lane-per-row loads (first version), 1: coalesced loads through the staging
+// tile, (2: register-prefetched variant, removed: slower, profiles/r01i_probe_conv_bw.txt), 3 (default): TMA load
+// straight into the staging tile, one chunk ahead.  Measured extra time of the in-place addend, 32x256x256 64->64 3x3:
+// +0.21 / +0.095..0.23 / +0.41 / +0.084 ms; 1x1 64->128 at 128x128: +0.19 / +0.137 / +0.36 / +0.063 ms.
+static int addend_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SIVAE_TC_ADDEND");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 3;
+    if (v == 2 || v < 0 || v > 3) v = 1;
     const char* nf = getenv("SIVAE_TC_NOFENCE");
     if (nf && nf[0] == '1') v |= 8;
   }
@@ -886,45 +899,41 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
       const int acc = lt & 1;
       const int nt = item % p.n_tiles, mt = item / p.n_tiles;
       const int col0 = nt * BLOCK_N;
-      // chunk sequence of an item: (t, c) for t < T, c < BLOCK_N step 32; the addend of chunk i+1 is loaded before chunk i
-      // is processed (and that of chunk 0 before the accumulator is ready)
-      long long pixs[T]; int w0s[T], h0s[T], ns[T];
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
+      // chunk sequence of an item: (t, c) for t < T, c < BLOCK_N step 32; the addend tile of chunk i+1 is requested right
+      // after chunk i's store (that of chunk 0 before the accumulator is ready)
+      auto tile_coords = [&](int t, int& w0, int& h0, int& n) {
         const int lin = mt * T + t;
-        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
-        w0s[t] = tw * 8; h0s[t] = th * 16; ns[t] = n;
-        pixs[t] = ((long long)n * p.H + (h0s[t] + dh)) * p.W + (w0s[t] + dw);
-      }
+        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h;
+        n = lin / (p.tiles_w * p.tiles_h); w0 = tw * 8; h0 = th * 16;
+      };
       int ncol = (p.Cout - col0 + 31) / 32;
       if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
-      float4 a[8], an[8];
-      if (tma && (eo.amode & 3) == 2) epi_load_addend(eo, pixs[0], true, col0, lane, a);
-      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0s[0], h0s[0] + 4 * q, ns[0], lane);
+      int w0, h0, n;
+      tile_coords(0, w0, h0, n);
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0, h0 + 4 * q, n, lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < T; ++t) {
+        tile_coords(t, w0, h0, n);
+        const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
         for (int ci = 0; ci < ncol; ++ci) {
           const int c = ci * 32;
-          const bool more_c = ci + 1 < ncol;
-          const bool more = tma && (eo.amode & 3) == 2 && (more_c || t + 1 < T);
-          if (more) epi_load_addend(eo, more_c ? pixs[t] : pixs[(t + 1) % T], true, more_c ? col0 + c + 32 : col0, lane, an);
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           // this warp's 32 rows = image rows h0+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
-          epi_chunk(v, eo, pixs[t], true, col0 + c, tma, stage, es, &map_y, w0s[t], h0s[t] + 4 * q, ns[t], lane, a,
-                    (long long)(mt * T + t) * 4 + q, abar + q * EPI_NBUF, &map_add);
-          if (tma && (more_c || t + 1 < T)) {
-            const int tn = more_c ? t : (t + 1) % T;
-            epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, more_c ? col0 + c + 32 : col0, w0s[tn],
-                         h0s[tn] + 4 * q, ns[tn], lane);
-          }
-          if (more) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = an[j];
+          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, (long long)(mt * T + t) * 4 + q,
+                    abar + q * EPI_NBUF, &map_add);
+          if (tma && eo.addend) {
+            if (ci + 1 < ncol) {
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + 4 * q, n, lane);
+            } else if (t + 1 < T) {
+              int w1, h1, n1;
+              tile_coords(t + 1, w1, h1, n1);
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w1, h1 + 4 * q, n1, lane);
+            }
           }
         }
       }
@@ -1188,36 +1197,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       const int acc = lt & 1;
       const int nt = item % p.n_tiles, mp = item / p.n_tiles;
       const int col0 = nt * BLOCK_N;
-      float4 a[8];
-      int w0s[T], h0s[T], ns[T];
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
+      auto tile_coords = [&](int t, int& w0, int& h0, int& n) {
         const int lin = (mp * 2 + (int)rank) * T + t;
         const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h;
-        ns[t] = lin / (p.tiles_w * p.tiles_h); w0s[t] = tw * 8; h0s[t] = th * 16;
-      }
+        n = lin / (p.tiles_w * p.tiles_h); w0 = tw * 8; h0 = th * 16;
+      };
       int ncol = (p.Cout - col0 + 31) / 32;
       if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
-      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0s[0], h0s[0] + 4 * q, ns[0], lane);
+      int w0, h0, n;
+      tile_coords(0, w0, h0, n);
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0, h0 + 4 * q, n, lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int t = 0; t < T; ++t) {
+        tile_coords(t, w0, h0, n);
         const int lin = (mp * 2 + (int)rank) * T + t;
-        const long long pix = ((long long)ns[t] * p.H + (h0s[t] + dh)) * p.W + (w0s[t] + dw);
+        const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
         for (int ci = 0; ci < ncol; ++ci) {
           const int c = ci * 32;
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
-          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0s[t], h0s[t] + 4 * q, ns[t], lane, a, (long long)lin * 4 + q,
+          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, (long long)lin * 4 + q,
                     abar + q * EPI_NBUF, &map_add);
-          const bool more_c = ci + 1 < ncol;
-          if (tma && (more_c || t + 1 < T)) {
-            const int tn = more_c ? t : (t + 1) % T;
-            epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, more_c ? col0 + c + 32 : col0, w0s[tn],
-                         h0s[tn] + 4 * q, ns[tn], lane);
+          if (tma && eo.addend) {
+            if (ci + 1 < ncol) {
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + 4 * q, n, lane);
+            } else if (t + 1 < T) {
+              int w1, h1, n1;
+              tile_coords(t + 1, w1, h1, n1);
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w1, h1 + 4 * q, n1, lane);
+            }
           }
         }
       }

@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsivae_b200.so")
+# SIVAE_LIB_PATH: load another build of the same library (A/B timing of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("SIVAE_LIB_PATH") or os.path.join(_HERE, "libsivae_b200.so")
 
 NET_ENCODER, NET_DECODER, NET_TARGET = 0, 1, 2
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
