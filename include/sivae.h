@@ -28,7 +28,11 @@ extern "C" {
 typedef struct sivae_engine sivae_engine;
 
 enum { SIVAE_NET_ENCODER = 0, SIVAE_NET_DECODER = 1, SIVAE_NET_TARGET = 2 };
-enum { SIVAE_CONV_AUTO = 0, SIVAE_CONV_SIMT = 1, SIVAE_CONV_TCGEN05 = 2 };
+/* conv_backend: AUTO = tcgen05 kind::tf32 where the shape allows (default); SIMT = exact fp32 CUDA-core path with fp64-chunked
+   accumulation (on-device reference); TCGEN05 = single-kernel entry points only: tensor core or error;
+   TC3X = compensated tensor-core mode: every operand split into two tf32 parts (hi + lo), three MMAs per product
+   (hi*hi + hi*lo + lo*hi), fp32-class accuracy (ELBO/KL within 1e-4 of the reference) at ~3x the conv time */
+enum { SIVAE_CONV_AUTO = 0, SIVAE_CONV_SIMT = 1, SIVAE_CONV_TCGEN05 = 2, SIVAE_CONV_TC3X = 3 };
 enum { SIVAE_T_CONV = 0, SIVAE_T_BN_WEIGHT = 1, SIVAE_T_BN_BIAS = 2, SIVAE_T_LINEAR = 3, SIVAE_T_BIAS = 4 };
 
 /* SoftIntroVAE(cdim, zdim, channels, image_size) -- ctor :173-184; Encoder :79-109; Decoder :126-159 */

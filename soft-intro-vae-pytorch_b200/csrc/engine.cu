@@ -30,7 +30,8 @@ static int fail(int code, const std::string& msg) {
 
 namespace {
 
-struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1, wn_off = -1, wg_off = -1; };
+struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1, wn_off = -1, wg_off = -1,
+              wl_off = -1, wdl_off = -1;   /* 3xTF32 mode: low parts of the forward / dgrad-packed filter */ };
 struct Bn { int c = 0; long long g_off = -1, b_off = -1, rm_off = -1; int idx = -1; };
 struct Lin { int fin = 0, fout = 0; long long w_off = -1, b_off = -1; };
 struct Block { int inc = 0, outc = 0, size = 0, mode = RS_NONE; bool expand = false; Conv ce, c1, c2; Bn bn1, bn2; };
@@ -48,6 +49,7 @@ struct Net {
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *bn = nullptr, *derived = nullptr;
   long long* nbt = nullptr;
   bool dirty = true;
+  bool comp = false;               // 3xTF32 mode: keep the low parts of the filters in `derived`
   long long* step_dev = nullptr;   // device-side Adam step counter + 2 floats of bias-correction scratch (workspace)
   float* coef_dev = nullptr;
   long long step_pending = 0;      // value to load into step_dev at the next workspace bind
@@ -85,6 +87,9 @@ struct sivae_engine {
   long long feat = 0;              // C_last*hw_last^2
   bool tc = false;                 // tcgen05 backend in use (activations pre-rounded to tf32)
   bool fast = false;               // cdim-facing narrow CUDA-core kernels in use (false: generic exact SIMT everywhere)
+  bool comp = false;               // compensated tensor-core mode (SIVAE_CONV_TC3X): 3 tf32 MMAs per product on split operands
+  bool rnd = false;                // producers round stored activations / gradients to tf32 (plain tensor-core mode only)
+  float* split[4] = {nullptr, nullptr, nullptr, nullptr};   // comp: hi / lo parts of the two conv operands, max activation size each
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0, ws_need = 0;
   EncPass ep[3]; DecPass dp[4];
@@ -130,6 +135,10 @@ static void add_conv(Net& n, const std::string& name, Conv& c, int cin, int cout
   const long long wide = cin > cout ? cin : cout;
   c.wn_off = n.derived_floats; n.derived_floats += narrow ? wide * 160 : (long long)cout * cin * k * k;
   if (narrow) { c.wg_off = n.derived_floats; n.derived_floats += wide * 80; }
+  if (n.comp) {
+    c.wl_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
+    c.wdl_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
+  }
 }
 static void add_bn(Net& n, const std::string& name, Bn& b, int c) {
   b.c = c;
@@ -307,6 +316,7 @@ static size_t carve(sivae_engine* e, char* base) {
   }
   long long ma = max_act_elems(e);
   for (int i = 0; i < 5; ++i) e->sb[i] = bp.take<float>(ma);
+  if (e->comp) for (int i = 0; i < 4; ++i) e->split[i] = bp.take<float>(ma);
   long long img = B * S * S * c.cdim;
   e->d_rec = bp.take<float>(img); e->d_rec_rec = bp.take<float>(img); e->d_rec_fake = bp.take<float>(img); e->d_fake = bp.take<float>(img);
   e->out_tmp = bp.take<float>(img);
@@ -381,8 +391,8 @@ struct ProfElem {
 static double resampled(int mode) { return mode == RS_POOL ? 0.25 : (mode == RS_UP ? 4.0 : 1.0); }
 // which implementation serves a convolution (exact = SIMT-only engine; narrow = cdim-facing CUDA-core kernels)
 static bool fwd_on_tc(const sivae_engine* e, const ConvShape& s) { return e->tc && conv_tc_supported_fwd(s); }
-static bool fwd_on_rowsep_in(const sivae_engine* e, const ConvShape& s) { return e->tc && e->fast && e->rs && conv_rowsep_in_supported(s); }
-static bool fwd_on_rowsep_out(const sivae_engine* e, const ConvShape& s) { return e->tc && e->fast && e->rs && conv_rowsep_out_supported(s); }
+static bool fwd_on_rowsep_in(const sivae_engine* e, const ConvShape& s) { return e->tc && !e->comp && e->fast && e->rs && conv_rowsep_in_supported(s); }
+static bool fwd_on_rowsep_out(const sivae_engine* e, const ConvShape& s) { return e->tc && !e->comp && e->fast && e->rs && conv_rowsep_out_supported(s); }
 static bool fwd_on_narrow(const sivae_engine* e, const ConvShape& s) { return e->fast && !fwd_on_rowsep_in(e, s) && conv_narrow_in_supported(s); }
 
 static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
@@ -391,10 +401,15 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
     if (c.k == 0) return;
     // dgrad filters (a dgrad is a forward conv over dy): rounded to tf32 only when the tensor core consumes them
     ConvShape sd{1, size, size, c.cout, c.cin, c.k};
-    launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, fwd_on_tc(e, sd) && !fwd_on_narrow(e, sd), st);
+    const long long wn = (long long)c.cout * c.cin * c.k * c.k;
+    const bool d_tc = fwd_on_tc(e, sd) && !fwd_on_narrow(e, sd);
+    launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, d_tc && !e->comp, st);
+    if (d_tc && e->comp) launch_split_tf32(n.derived + c.wd_off, n.derived + c.wd_off, n.derived + c.wdl_off, wn, st);
     ConvShape sf{1, size, size, c.cin, c.cout, c.k};
-    if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf))
-      launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, (long long)c.cout * c.cin * c.k * c.k, st);
+    if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf)) {
+      if (e->comp) launch_split_tf32(n.params + c.w_off, n.derived + c.wr_off, n.derived + c.wl_off, wn, st);
+      else launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, wn, st);
+    }
     // narrow (cdim-facing) kernels read the filter transposed to [tap][narrow][wide]
     if (fwd_on_narrow(e, sf)) launch_narrow_transpose(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.k, c.cin, st);
     else if (fwd_on_narrow(e, sd)) launch_narrow_transpose(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.k, c.cout, st);
@@ -415,7 +430,7 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
 // y = conv(x, filt) (+bias) (+addend).  w_master: fp32 filter [Cout][k][k][Cin]; w_tc: its tf32-rounded copy
 static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const float* w_master, const float* w_tc,
                     const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr,
-                    const float* w_narrow = nullptr, const float* w_gather = nullptr) {
+                    const float* w_narrow = nullptr, const float* w_gather = nullptr, const float* w_lo = nullptr) {
   if (fwd_on_rowsep_in(e, s) && w_narrow) {
     ProfScope ps(PC_TC_FWD, s, st);
     int r = launch_conv_rowsep_in(x, w_narrow, bias, addend, y, s, e->rs, stats, st);
@@ -427,6 +442,17 @@ static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const f
   } else if (fwd_on_narrow(e, s) && w_narrow) {
     ProfScope ps(PC_SIMT_FWD, s, st);
     launch_conv_narrow_in_fwd(x, w_narrow, bias, addend, y, s, st);
+  } else if (fwd_on_tc(e, s) && e->comp) {
+    // 3xTF32: x = xh + xl, w = wh + wl (every part an exact tf32 operand); y = xl*wh + xh*wl + xh*wh (+bias +addend), the
+    // three tensor-core convs chained through the in-place addend path, small terms first.  Dropped: xl*wl (2^-22).
+    if (!w_lo || !e->split[0]) return fail(-4, "compensated conv needs the split filter and the split scratch");
+    ProfScope ps(PC_TC_FWD, s, st);
+    float *xh = e->split[0], *xl = e->split[1];
+    launch_split_tf32(x, xh, xl, s.pixels() * s.Cin, st);
+    int r = launch_conv_fwd_tc(xl, w_tc, bias, addend, y, s, st, nullptr, e->sk, e->sk_bytes);
+    if (!r) r = launch_conv_fwd_tc(xh, w_lo, nullptr, y, y, s, st, nullptr, e->sk, e->sk_bytes);
+    if (!r) r = launch_conv_fwd_tc(xh, w_tc, nullptr, y, y, s, st, nullptr, e->sk, e->sk_bytes);
+    if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (fwd_on_tc(e, s)) {
     ProfScope ps(PC_TC_FWD, s, st);
     int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats, e->sk, e->sk_bytes);
@@ -441,7 +467,7 @@ static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, floa
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
   return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st, nullptr, n.derived + c.wn_off,
-                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr);
+                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr);
 }
 // t = conv(x, W) followed by the BatchNorm batch statistics of t (train) or the running statistics (eval).  On the tensor
 // core path the statistics come out of the conv epilogue (no second pass over t).
@@ -449,11 +475,11 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
                          bool train, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const long long rows = (long long)B * size * size;
-  int parts = (train && e->tc && (fwd_on_rowsep_in(e, s) || (!fwd_on_narrow(e, s) && fwd_on_tc(e, s)))) ? conv_tc_stats_parts(s) : 0;
+  int parts = (train && e->tc && !e->comp && (fwd_on_rowsep_in(e, s) || (!fwd_on_narrow(e, s) && fwd_on_tc(e, s)))) ? conv_tc_stats_parts(s) : 0;
   if (parts > 0 && bn_parts_scratch_bytes(parts, c.cout) > e->red_bytes) parts = 0;
   float* sp = parts > 0 ? (float*)e->red : nullptr;
   TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp, n.derived + c.wn_off,
-               c.wg_off >= 0 ? n.derived + c.wg_off : nullptr));
+               c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr));
   if (parts > 0)
     launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st);
   else if (train)
@@ -466,16 +492,16 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
 static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cout, c.cin, c.k};
   return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st, nullptr, n.derived + c.wn_off,
-                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr);
+                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wdl_off >= 0 ? n.derived + c.wdl_off : nullptr);
 }
 static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   float* dw = n.grads + c.w_off;
-  if (e->tc && e->fast && e->rs && c.cin <= 3 && conv_rowsep_wgrad_supported(size, size, c.cin, c.cout, c.k)) {          // stem
+  if (e->tc && !e->comp && e->fast && e->rs && c.cin <= 3 && conv_rowsep_wgrad_supported(size, size, c.cin, c.cout, c.k)) {          // stem
     ProfScope ps(PC_TC_WGRAD, s, st);
     int r = launch_conv_rowsep_wgrad(x, dy, dw, B, size, size, c.cin, c.cout, 1, true, e->rs, e->red, e->red_bytes, st);
     if (r) return fail(r, "row-separable tcgen05 wgrad launch failed");
-  } else if (e->tc && e->fast && e->rs && c.cout <= 3 && conv_rowsep_wgrad_supported(size, size, c.cout, c.cin, c.k)) {  // predict
+  } else if (e->tc && !e->comp && e->fast && e->rs && c.cout <= 3 && conv_rowsep_wgrad_supported(size, size, c.cout, c.cin, c.k)) {  // predict
     ProfScope ps(PC_TC_WGRAD, s, st);
     int r = launch_conv_rowsep_wgrad(dy, x, dw, B, size, size, c.cout, c.cin, 0, true, e->rs, e->red, e->red_bytes, st);
     if (r) return fail(r, "row-separable tcgen05 wgrad launch failed");
@@ -485,6 +511,17 @@ static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, co
   } else if (e->fast && c.cout <= 4 && conv_narrow_corr_supported(c.cin, c.cout, c.k)) {     // predict
     ProfScope ps(PC_SIMT_WGRAD, s, st);
     launch_conv_narrow_corr(dy, x, dw, B, size, size, c.cout, c.cin, c.k, 0, true, e->red, e->red_bytes, st);
+  } else if (e->tc && e->comp && conv_tc_supported_wgrad(s)) {
+    // 3xTF32: dw += xl (x) dyh + xh (x) dyl + xh (x) dyh
+    if (!e->split[0]) return fail(-4, "compensated wgrad needs the split scratch");
+    ProfScope ps(PC_TC_WGRAD, s, st);
+    float *xh = e->split[0], *xl = e->split[1], *dh = e->split[2], *dl = e->split[3];
+    launch_split_tf32(x, xh, xl, s.pixels() * s.Cin, st);
+    launch_split_tf32(dy, dh, dl, s.pixels() * s.Cout, st);
+    int r = launch_conv_wgrad_tc(xl, dh, dw, s, true, e->red, e->red_bytes, st);
+    if (!r) r = launch_conv_wgrad_tc(xh, dl, dw, s, true, e->red, e->red_bytes, st);
+    if (!r) r = launch_conv_wgrad_tc(xh, dh, dw, s, true, e->red, e->red_bytes, st);
+    if (r) return fail(r, "tcgen05 conv wgrad launch failed");
   } else if (e->tc && conv_tc_supported_wgrad(s)) {
     ProfScope ps(PC_TC_WGRAD, s, st);
     int r = launch_conv_wgrad_tc(x, dy, dw, s, true, e->red, e->red_bytes, st);
@@ -517,10 +554,10 @@ static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, c
   if (b.expand) { TRY(conv_fwd(e, n, b.ce, x, a.id, nullptr, B, s, st)); idn = a.id; }
   TRY(conv_bn_stats(e, n, b.c1, b.bn1, x, a.t1, a.mi1, B, s, train, st));
   { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0, st);
-    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->tc, st); }
+    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->rnd, st); }
   TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st));
   { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode), st);
-    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->tc, st); }
+    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->rnd, st); }
   return 0;
 }
 
@@ -531,7 +568,7 @@ static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, in
   p.img = img;
   TRY(conv_bn_stats(e, n, n.stem, n.stem_bn, img, p.t0, p.mi0, B, S, train, st));
   { ProfElem pe(PC_BN_FWD, B, S, n.stem.cout, RS_POOL, 1.25, st);
-    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->tc, st); }
+    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->rnd, st); }
   const float* x = p.a0;
   for (size_t i = 0; i < n.blocks.size(); ++i) {
     TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
@@ -550,7 +587,7 @@ static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int 
   p.zin = z;
   launch_linear_fwd(z, n.params + n.fc.w_off, n.params + n.fc.b_off, p.h, B, n.fc.fin, n.fc.fout, true, st);
   launch_nchw_to_nhwc(p.h, p.x0, B, e->C_last, e->hw_last, e->hw_last, st);
-  if (e->tc) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
+  if (e->rnd) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
   const float* x = p.x0;
   for (size_t i = 0; i < n.blocks.size(); ++i) {
     TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
@@ -575,13 +612,13 @@ static int block_backward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, 
   { // reduce pass reads dout, t2, identity; apply pass reads them again and writes dt and the identity-path gradient
     ProfElem pe(PC_BN_BWD, B, s, b.outc, 4 + b.mode, 2.0 * (resampled(b.mode) + 2.0) + 2.0, st);
     launch_bn_act_bwd(dout, a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, DT, G2,
-                      wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->tc,
+                      wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->rnd,
                       e->red, e->red_bytes, st); }
   if (wgrad) TRY(conv_wgrad(e, n, b.c2, a.a1, DT, B, s, st));
   TRY(conv_dgrad(e, n, b.c2, DT, DA1, nullptr, B, s, st));
   { ProfElem pe(PC_BN_BWD, B, s, b.outc, RS_NONE, 5.0, st);
     launch_bn_act_bwd(DA1, a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, DT, nullptr,
-                      wgrad ? g + b.bn1.g_off : nullptr, wgrad ? g + b.bn1.b_off : nullptr, true, B, s, s, b.outc, RS_NONE, e->tc,
+                      wgrad ? g + b.bn1.g_off : nullptr, wgrad ? g + b.bn1.b_off : nullptr, true, B, s, s, b.outc, RS_NONE, e->rnd,
                       e->red, e->red_bytes, st); }
   if (wgrad) {
     TRY(conv_wgrad(e, n, b.c1, a.x, DT, B, s, st));
@@ -615,7 +652,7 @@ static int enc_backward(sivae_engine* e, Net& n, EncPass& p, const float* dml, b
   { ProfElem pe(PC_BN_BWD, B, S, n.stem.cout, RS_POOL, 2.0 * 1.25 + 1.0, st);
     launch_bn_act_bwd(cur, p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, DT, nullptr,
                       wgrad ? n.grads + n.stem_bn.g_off : nullptr, wgrad ? n.grads + n.stem_bn.b_off : nullptr, true, B, S, S,
-                      n.stem.cout, RS_POOL, e->tc, e->red, e->red_bytes, st); }
+                      n.stem.cout, RS_POOL, e->rnd, e->red, e->red_bytes, st); }
   if (wgrad) TRY(conv_wgrad(e, n, n.stem, p.img, DT, B, S, st));
   if (d_img) TRY(conv_dgrad(e, n, n.stem, DT, d_img, d_img_addend, B, S, st));
   CHECK_CUDA_RET();
@@ -659,14 +696,17 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   for (int i = 0; i < cfg->n_channels; ++i)
     if (cfg->channels[i] < 4 || cfg->channels[i] % 4 != 0 || cfg->channels[i] > 1024) return fail(-2, "channels must be multiples of 4 in [4,1024]");
   if ((cfg->cdim * S * S) % 4 != 0) return fail(-2, "cdim*image_size^2 must be a multiple of 4");
+  if (cfg->conv_backend < SIVAE_CONV_AUTO || cfg->conv_backend > SIVAE_CONV_TC3X) return fail(-2, "bad conv_backend");
   sivae_engine* e = new sivae_engine();
   e->cfg = *cfg;
-  for (int i = 0; i < 3; ++i) e->nets[i].id = i;
+  e->comp = cfg->conv_backend == SIVAE_CONV_TC3X;
+  for (int i = 0; i < 3; ++i) { e->nets[i].id = i; e->nets[i].comp = e->comp; }
   build_encoder(e, e->nets[0]);
   build_decoder(e, e->nets[1]);
   if (cfg->variant == 1) build_decoder(e, e->nets[2]);
   e->tc = cfg->conv_backend != SIVAE_CONV_SIMT;
   e->fast = cfg->conv_backend != SIVAE_CONV_SIMT;
+  e->rnd = e->tc && !e->comp;
   e->ws_need = carve(e, nullptr);
   *out = e;
   return 0;
@@ -1009,8 +1049,8 @@ extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void
 // library-owned scratch for the transposed narrow filter of the single-kernel test entry points (the engine keeps its
 // own copy in the workspace)
 static float* lib_scratch(int slot, size_t floats) {
-  static float* buf[3] = {nullptr, nullptr, nullptr};
-  static size_t cap[3] = {0, 0, 0};
+  static float* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  static size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (floats > cap[slot]) {
     if (buf[slot]) cudaFree(buf[slot]);
     if (cudaMalloc(&buf[slot], floats * sizeof(float)) != cudaSuccess) { buf[slot] = nullptr; cap[slot] = 0; return nullptr; }
@@ -1045,7 +1085,24 @@ static int auto_prepare(sivae_engine* tmp, const ConvShape& s, const float* filt
   }
   return 0;
 }
+// compensated (3xTF32) conv of the single-kernel entry points: unrounded fp32 x and filter, library-owned split scratch
+static int conv3x_entry(const ConvShape& s, const float* x, const float* filt, const float* bias, const float* addend, float* y,
+                        cudaStream_t st) {
+  if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
+  sivae_engine tmp; tmp.tc = tmp.comp = true; tmp.fast = false;
+  const long long wn = (long long)s.Cout * s.ktot();
+  float* wh = lib_scratch(3, (size_t)wn);
+  float* wl = lib_scratch(4, (size_t)wn);
+  tmp.split[0] = lib_scratch(5, (size_t)(s.pixels() * s.Cin));
+  tmp.split[1] = lib_scratch(6, (size_t)(s.pixels() * s.Cin));
+  tmp.sk_bytes = conv_tc_splitk_scratch_bytes(s);
+  tmp.sk = tmp.sk_bytes ? (void*)lib_scratch(2, (tmp.sk_bytes + 3) / 4) : nullptr;
+  if (!wh || !wl || !tmp.split[0] || !tmp.split[1] || (tmp.sk_bytes && !tmp.sk)) return fail(-3, "cudaMalloc of the split scratch failed");
+  launch_split_tf32(filt, wh, wl, wn, st);
+  return conv_any(&tmp, s, x, filt, wh, bias, addend, y, st, nullptr, nullptr, nullptr, wl);
+}
 // backend: SIVAE_CONV_SIMT = generic exact fp32 kernel; SIVAE_CONV_TCGEN05 = tensor-core kernel or error -7;
+// SIVAE_CONV_TC3X = compensated tensor-core conv (3 tf32 MMAs per product on split operands, fp32-class accuracy);
 // SIVAE_CONV_AUTO = what the engine would pick for this shape (narrow CUDA-core kernel, tensor core, generic)
 extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bias, const float* addend, float* y, int N, int H,
                                 int W, int Cin, int Cout, int k, int backend, void* stream) {
@@ -1062,6 +1119,8 @@ extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bia
     const float *wn, *wg;
     TRY(auto_prepare(&tmp, s, w, &wn, &wg, st));
     TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st, nullptr, wn, wg));
+  } else if (backend == SIVAE_CONV_TC3X) {
+    TRY(conv3x_entry(s, x, w, bias, addend, y, st));
   } else {
     launch_conv_fwd_simt(x, w, bias, addend, y, s, st);
   }
@@ -1078,7 +1137,9 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
   sivae_engine tmp; tmp.tc = tmp.fast = (backend == SIVAE_CONV_AUTO);
   const bool on_tc = backend == SIVAE_CONV_TCGEN05 || (backend == SIVAE_CONV_AUTO && !fwd_on_narrow(&tmp, s) && fwd_on_tc(&tmp, s));
   launch_pack_dgrad_filter(w, wd, Cout, Cin, k, on_tc, st);
-  if (backend == SIVAE_CONV_TCGEN05) {
+  if (backend == SIVAE_CONV_TC3X) {
+    TRY(conv3x_entry(s, dy, wd, nullptr, addend, dx, st));
+  } else if (backend == SIVAE_CONV_TCGEN05) {
     if (!conv_tc_supported_fwd(s)) return fail(-7, "shape not supported by the tcgen05 conv kernel");
     size_t skb = conv_tc_splitk_scratch_bytes(s);
     void* sk = skb ? (void*)lib_scratch(2, (skb + 3) / 4) : nullptr;
@@ -1115,6 +1176,21 @@ extern "C" int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, in
   } else if (backend == SIVAE_CONV_AUTO && Cout <= 4 && conv_narrow_corr_supported(Cin, Cout, k)) {
     if ((size_t)ws_bytes < conv_narrow_corr_scratch_bytes(Cin, k)) return fail(-3, "workspace too small");
     launch_conv_narrow_corr(dy, x, dw, N, H, W, Cout, Cin, k, 0, acc, workspace, (size_t)ws_bytes, st);
+  } else if (backend == SIVAE_CONV_TC3X) {
+    if (!conv_tc_supported_wgrad(s)) return fail(-7, "shape not supported by the tcgen05 wgrad kernel");
+    if ((size_t)ws_bytes < conv_wgrad_tc_scratch_bytes(s)) return fail(-3, "workspace too small");
+    float* sp[4];
+    for (int i = 0; i < 4; ++i) {
+      sp[i] = lib_scratch(4 + i, (size_t)(s.pixels() * (i < 2 ? s.Cin : s.Cout)));
+      if (!sp[i]) return fail(-3, "cudaMalloc of the split scratch failed");
+    }
+    launch_split_tf32(x, sp[0], sp[1], s.pixels() * s.Cin, st);
+    launch_split_tf32(dy, sp[2], sp[3], s.pixels() * s.Cout, st);
+    if (!acc) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)s.Cout * s.ktot(), st);
+    int r = launch_conv_wgrad_tc(sp[1], sp[2], dw, s, true, workspace, (size_t)ws_bytes, st);
+    if (!r) r = launch_conv_wgrad_tc(sp[0], sp[3], dw, s, true, workspace, (size_t)ws_bytes, st);
+    if (!r) r = launch_conv_wgrad_tc(sp[0], sp[2], dw, s, true, workspace, (size_t)ws_bytes, st);
+    if (r) return fail(r, "tcgen05 wgrad launch failed");
   } else if (backend == SIVAE_CONV_TCGEN05 || (backend == SIVAE_CONV_AUTO && conv_tc_supported_wgrad(s))) {
     if (!conv_tc_supported_wgrad(s)) return fail(-7, "shape not supported by the tcgen05 wgrad kernel");
     if ((size_t)ws_bytes < conv_wgrad_tc_scratch_bytes(s)) return fail(-3, "workspace too small");

@@ -76,6 +76,30 @@ void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st
   if (n <= 0) return;
   k_round_tf32<<<min(cdiv(n, 256), 148u * 8), 256, 0, st>>>(in, out, n);
 }
+// 3xTF32 operand split (compensated tensor-core mode): hi = rna_tf32(x), lo = rna_tf32(x - hi).  x - hi is exact in fp32
+// (13 significant bits), so hi + lo carries 21-22 bits of x and both parts are exactly representable tf32 operands.
+__global__ void k_split_tf32(const float* in, float* hi, float* __restrict__ lo, long long n) {   // hi may alias in
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    float4 h, l;
+    h.x = round_tf32_dev(v.x); h.y = round_tf32_dev(v.y); h.z = round_tf32_dev(v.z); h.w = round_tf32_dev(v.w);
+    l.x = round_tf32_dev(v.x - h.x); l.y = round_tf32_dev(v.y - h.y); l.z = round_tf32_dev(v.z - h.z); l.w = round_tf32_dev(v.w - h.w);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    const float v = in[i], h = round_tf32_dev(v);
+    hi[i] = h;
+    lo[i] = round_tf32_dev(v - h);
+  }
+}
+void launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaStream_t st) {
+  g_launches += 1;
+  if (n <= 0) return;
+  k_split_tf32<<<min(cdiv((n >> 2) + 1, 256), 148u * 16), 256, 0, st>>>(in, hi, lo, n);
+}
 __global__ void k_pack_dgrad(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int k, int rnd) {
   long long total = (long long)Cout * Cin * k * k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

@@ -26,6 +26,8 @@ void launch_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W
 void launch_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, cudaStream_t st);
 void launch_fill(float* p, float v, long long n, cudaStream_t st);
 void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st);
+// compensated (3xTF32) operand split: hi = tf32(x), lo = tf32(x - hi); hi may alias in (16-byte aligned pointers)
+void launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaStream_t st);
 // wd[ci][k-1-r][k-1-s][co] = w[co][r][s][ci]  (filters for dgrad as a forward conv); optional tf32 rounding
 void launch_pack_dgrad_filter(const float* w, float* wd, int Cout, int Cin, int k, bool round_tf32, cudaStream_t st);
 

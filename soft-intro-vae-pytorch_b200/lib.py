@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIVAE_LIB_PATH") or os.path.join(_HERE, "libsivae_b200.so")
 
 NET_ENCODER, NET_DECODER, NET_TARGET = 0, 1, 2
-CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
+CONV_AUTO, CONV_SIMT, CONV_TCGEN05, CONV_TC3X = 0, 1, 2, 3
 T_CONV, T_BN_WEIGHT, T_BN_BIAS, T_LINEAR, T_BIAS = 0, 1, 2, 3, 4
 
 

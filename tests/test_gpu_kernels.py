@@ -111,6 +111,45 @@ def test_conv_fwd_dgrad_wgrad(shape, backend):
         assert _rel(dw.cpu() - 0.5, _krsc(wd.grad)) < tol
 
 
+@pytest.mark.parametrize("shape", [sh for sh in CONV_SHAPES if sh[3] % 32 == 0] + [(2, 32, 32, 64, 64, 3), (2, 8, 8, 128, 128, 3)])
+def test_conv_tc3x_unrounded_operands(shape):
+    """compensated tensor-core conv (SIVAE_CONV_TC3X): full-precision fp32 operands, three tf32 MMAs per product on the
+    hi/lo split -- fp32-class agreement with fp64 (plain tf32 on the same operands is ~5e-4)"""
+    lib = L.load()
+    N, H, W, Cin, Cout, k = shape
+    x, w, dy = _conv_case(*shape, seed=3)
+    xd, wd, dyd = x.double().requires_grad_(True), w.double().requires_grad_(True), dy.double()
+    bias = torch.randn(Cout)
+    addend = torch.randn(N, Cout, H, W)
+    y_ref = F.conv2d(xd, wd, bias.double(), 1, k // 2) + addend.double()
+    y_ref.backward(dyd)
+    tol = 2e-5
+    xg, wg, dyg = _nhwc(x).to(DEV), _krsc(w).to(DEV), _nhwc(dy).to(DEV)
+    bg, ag = bias.to(DEV), _nhwc(addend).to(DEV)
+    y = torch.empty(N, H, W, Cout, device=DEV)
+    rc = lib.sivae_conv2d_fwd(L.ptr(xg), L.ptr(wg), L.ptr(bg), L.ptr(ag), L.ptr(y), N, H, W, Cin, Cout, k, L.CONV_TC3X, _s())
+    if rc == -7:
+        pytest.skip("shape not eligible for the tcgen05 kernel")
+    L.check(rc, "conv fwd 3x")
+    torch.cuda.synchronize()
+    assert _rel(y.cpu(), _nhwc(y_ref.detach())) < tol
+    ws = torch.empty(max(1 << 25, Cout * Cin * k * k * 4 * 64), dtype=torch.uint8, device=DEV)
+    if Cout % 32 == 0:          # the dgrad is a forward conv with Cout input channels
+        dx = torch.empty(N, H, W, Cin, device=DEV)
+        L.check(lib.sivae_conv2d_dgrad(L.ptr(dyg), L.ptr(wg), None, L.ptr(dx), N, H, W, Cin, Cout, k, L.CONV_TC3X, L.ptr(ws),
+                                       ws.numel(), _s()), "conv dgrad 3x")
+        torch.cuda.synchronize()
+        assert _rel(dx.cpu(), _nhwc(xd.grad)) < tol
+    for acc in (1, 0):
+        dw = torch.full((Cout, k, k, Cin), 0.5, device=DEV)
+        rc = lib.sivae_conv2d_wgrad(L.ptr(xg), L.ptr(dyg), L.ptr(dw), N, H, W, Cin, Cout, k, acc, L.CONV_TC3X, L.ptr(ws), ws.numel(), _s())
+        if rc == -7:
+            break
+        L.check(rc, "conv wgrad 3x")
+        torch.cuda.synchronize()
+        assert _rel(dw.cpu() - 0.5 * acc, _krsc(wd.grad)) < tol
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("with_id", [False, True])
 def test_bn_act_fwd_bwd(mode, with_id):

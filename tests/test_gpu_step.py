@@ -3,6 +3,8 @@
 
 Tolerances (relative; tensors: relative L2) -- measured deviations are logged to gpurun_out/parity_report.jsonl:
   exact path (fp32 SIMT, fp64-chunked accumulation)   scalars 2e-5, gradients / BN statistics 2e-4  (measured ~4e-7 / ~2e-5)
+  compensated tcgen05 path (3xTF32: operands split hi+lo, 3 MMAs per product; conv_backend = 3)
+                                                      scalars 1e-4 (the north-star ELBO/KL bound), gradients 2e-3
   tcgen05 path (TF32 operands, fp32 accumulate)       scalars 2e-3, gradients / BN statistics 1e-1
       TF32 rounds every conv operand to 11 significant bits (2^-11 = 4.9e-4 per operand).  Forward scalars land at
       1e-4..7e-4 (exp-ELBO amplifies by 2*scale*beta_neg*KL); gradients see the same rounding through the
@@ -19,8 +21,8 @@ from tests.step_harness import compare, run_engine_iteration, run_oracle_iterati
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = {1: 2e-5, 0: 2e-3}    # backend id -> scalar tolerance
-TTOL = {1: 2e-4, 0: 1e-1}   # backend id -> tensor (relative L2) tolerance
+TOL = {1: 2e-5, 0: 2e-3, 3: 1e-4}    # backend id -> scalar tolerance (3 = compensated 3xTF32 tensor-core mode)
+TTOL = {1: 2e-4, 0: 1e-1, 3: 2e-3}   # backend id -> tensor (relative L2) tolerance
 
 
 def _golden_as_oracle(g, bootstrap=False):
@@ -30,7 +32,7 @@ def _golden_as_oracle(g, bootstrap=False):
     return scal
 
 
-@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("backend", [1, 0, 3])
 def test_tiny_step_vs_reference_golden(backend):
     """engine vs the unmodified reference (tests/golden/tiny_std.pt: init, inputs, grads, post-step state)"""
     g = torch.load(os.path.join(GOLD, "tiny_std.pt"), weights_only=False)
@@ -48,7 +50,7 @@ def test_tiny_step_vs_reference_golden(backend):
     compare(out, ref, TOL[backend], label="tiny golden backend %d" % backend, tensor_tol=TTOL[backend])
 
 
-@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("backend", [1, 0, 3])
 @pytest.mark.parametrize("cfg,batch", [
     (dict(cdim=3, zdim=128, channels=[64, 128, 256], image_size=32), 8),          # BASELINE config C (CIFAR shape)
     (dict(cdim=3, zdim=32, channels=[32, 64, 64], image_size=32), 5),             # odd batch, identity + expand blocks
@@ -70,6 +72,23 @@ def test_free_running_step_vs_oracle(backend):
     ora32 = run_oracle_iteration(cfg, 8, seed=5, dtype=torch.float32)
     out = run_engine_iteration(cfg, 8, seed=5, backend=backend)
     compare(out, ora, {1: 1e-4, 0: 4e-3}[backend], label="free-running backend %d" % backend, tensor_tol={1: 5e-3, 0: 2e-1}[backend], noise=ora32)
+
+
+def test_full_size_architecture_tensor_core_vs_exact_path():
+    """BASELINE config H's architecture (256x256, z512, [64,128,256,512,512,512]: every kernel variant, tile plan and split the
+    benchmark uses) at batch 4.  The CPU oracle needs minutes per image at this size, so the on-device exact path
+    (conv_backend 1, itself pinned to the unmodified reference at 4e-7 / 1e-6 by the golden tests) is the checker:
+    compensated 3xTF32 mode within the north-star 1e-4 on every scalar, plain TF32 within its stated bound."""
+    cfg = dict(cdim=3, zdim=512, channels=[64, 128, 256, 512, 512, 512], image_size=256)
+    hp = dict(beta_neg=1024.0)
+    exact = run_engine_iteration(cfg, 4, seed=7, backend=1, hp=hp)
+    del exact["model"]
+    torch.cuda.empty_cache()
+    for backend, tol, ttol in ((3, 1e-4, 2e-2), (0, 5e-3, 2.5e-1)):
+        out = run_engine_iteration(cfg, 4, seed=7, backend=backend, hp=hp, teacher_enc=exact["post"])
+        del out["model"]
+        torch.cuda.empty_cache()
+        compare(out, exact, tol, label="config-H architecture, backend %d vs exact path" % backend, tensor_tol=ttol)
 
 
 def test_init_matches_golden_fingerprint():
@@ -146,7 +165,7 @@ def test_inference_api_train_and_eval():
         assert y.shape == (4, 3, 16, 16)
 
 
-@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("backend", [1, 0, 3])
 def test_tiny_bootstrap_step_vs_reference_golden(backend):
     """bootstrap variant (target decoder, nothing detached in the D half) vs the unmodified reference bootstrap trainer"""
     g = torch.load(os.path.join(GOLD, "tiny_bootstrap.pt"), weights_only=False)
