@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace sivae {
 
@@ -335,6 +336,96 @@ __device__ __forceinline__ void epi_chunk(uint32_t (&v)[32], const EpiOut& o, lo
     }
   }
 }
+// Straight-line epilogue of a FULL 32x32 chunk on the TMA-store path: no bias, all 32 columns valid, addend either absent
+// or TMA-prefetched into the staging tile (mode 3).  The generic epi_chunk above spends ~2.9k clk per chunk on the
+// 64-channel layers (336 SASS instructions, a runtime branch and a constant-bank reload per 16-byte piece, instruction
+// fetch stalls from jumping over the unused modes) and is the critical path there: the epilogue warps never wait for an
+// accumulator while the tensor pipe idles at 43 % (profiles/r01o_prof_halo2.md).  Same arithmetic, same staging layout.
+// Statistics: lane (g = lane/8, p = lane%8) sums the 16-byte piece p of rows 8g..8g+7 (conflict-free under the swizzle),
+// two xor-shuffles fold the four row groups, lanes 0..7 write one float4 of sums and one of squares.
+template <bool ADD, bool STATS>
+__device__ __forceinline__ void epi_chunk_fast(uint32_t (&v)[32], const EpiOut& o, int col, uint8_t* stage0, EpiState& es,
+                                               const CUtensorMap* map_y, int cw, int ch, int cn, int lane, long long srow,
+                                               uint64_t* abar, const CUtensorMap* map_add) {
+  if (ADD) epi_prefetch(o.addend, 3, es, stage0, abar, map_add, col, cw, ch, cn, lane);     // no-op if already requested
+  const uint32_t buf = es.n % EPI_NBUF, par = (es.n / EPI_NBUF) & 1;
+  uint8_t* stage = stage0 + buf * 4096;
+  const uint32_t stage_s = smem_u32(stage);
+  ++es.n;
+  es.pref = false;
+  if (ADD) {
+    mbar_wait(&abar[buf], par);                      // the addend tile has landed in this staging tile
+  } else {
+    bulk_wait_read<EPI_NBUF - 1>();                  // per-thread groups: a no-op for the lanes that never issue a store
+    __syncwarp();
+  }
+  const uint32_t mine = stage_s + lane * 128;
+  const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 q = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    const uint32_t slot = mine + ((j ^ sw) << 4);
+    if (ADD) {
+      const float4 d = lds128(slot);
+      q.x += d.x; q.y += d.y; q.z += d.z; q.w += d.w;
+    }
+    sts128(slot, q);
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(map_y, stage, col, cw, ch, cn);
+    bulk_commit();
+  }
+  if (STATS) {
+    const uint32_t g = (uint32_t)lane >> 3, pc = (uint32_t)lane & 7;
+    const uint32_t rbase = stage_s + g * 1024;       // rows 8g .. 8g+7
+    float4 sm = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 x = lds128(rbase + i * 128 + ((pc ^ (uint32_t)i) << 4));
+      sm.x += x.x; sm.y += x.y; sm.z += x.z; sm.w += x.w;
+      sq.x = fmaf(x.x, x.x, sq.x); sq.y = fmaf(x.y, x.y, sq.y); sq.z = fmaf(x.z, x.z, sq.z); sq.w = fmaf(x.w, x.w, sq.w);
+    }
+#pragma unroll
+    for (int o2 = 8; o2 <= 16; o2 <<= 1) {
+      sm.x += __shfl_xor_sync(0xffffffffu, sm.x, o2); sm.y += __shfl_xor_sync(0xffffffffu, sm.y, o2);
+      sm.z += __shfl_xor_sync(0xffffffffu, sm.z, o2); sm.w += __shfl_xor_sync(0xffffffffu, sm.w, o2);
+      sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o2); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o2);
+      sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o2); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o2);
+    }
+    if (g == 0) {
+      float* d = o.stats + srow * 2 * o.Cout + col + 4 * (int)pc;
+      *reinterpret_cast<float4*>(d) = sm;
+      *reinterpret_cast<float4*>(d + o.Cout) = sq;
+    }
+  }
+}
+// epilogue variant of a launch (warp-uniform, fixed for the whole kernel): 0 = generic epi_chunk; otherwise
+// 1 | ADD << 1 | STATS << 2 selects epi_chunk_fast<ADD, STATS>.  SIVAE_TC_FASTEPI=0 (host side) forces 0.
+__device__ __forceinline__ int epi_variant(const EpiOut& o, bool tma, int fast_ok) {
+  if (!fast_ok || !tma || o.bias || (o.Cout & 31) != 0) return 0;
+  if (o.addend && (o.amode & 3) != 3) return 0;
+  return 1 | (o.addend ? 2 : 0) | (o.stats ? 4 : 0);
+}
+template <int EM>
+__device__ __forceinline__ void epi_do(uint32_t (&v)[32], const EpiOut& o, long long pix, bool valid, int col, bool tma,
+                                       uint8_t* stage0, EpiState& es, const CUtensorMap* map_y, int cw, int ch, int cn, int lane,
+                                       long long srow, uint64_t* abar, const CUtensorMap* map_add) {
+  if (EM == 0) epi_chunk(v, o, pix, valid, col, tma, stage0, es, map_y, cw, ch, cn, lane, srow, abar, map_add);
+  else epi_chunk_fast<(EM & 2) != 0, (EM & 4) != 0>(v, o, col, stage0, es, map_y, cw, ch, cn, lane, srow, abar, map_add);
+}
+// run `body(std::integral_constant<int, EM>)` for the launch's epilogue variant
+template <class F>
+__device__ __forceinline__ void epi_dispatch(int em, F&& body) {
+  switch (em) {
+    case 1: body(std::integral_constant<int, 1>{}); break;
+    case 3: body(std::integral_constant<int, 3>{}); break;
+    case 5: body(std::integral_constant<int, 5>{}); break;
+    case 7: body(std::integral_constant<int, 7>{}); break;
+    default: body(std::integral_constant<int, 0>{}); break;
+  }
+}
 // shared-memory matrix descriptor (sm_100 UMMA): start address, leading / stride byte offsets (>>4), version 1,
 // layout type 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only layout the
 // tensor core accepts for MN-major 32-bit operands)
@@ -645,6 +736,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     EpiState es;
     const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats, p.tma_store >> 4};
     const bool tma = (p.tma_store & 1) != 0;
+    epi_dispatch(epi_variant(eo, tma, (p.tma_store >> 12) & 1), [&](auto emc) {
+    constexpr int EM = decltype(emc)::value;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -664,8 +757,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
         if (col0 + c >= p.Cout) break;                     // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
-        epi_chunk(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q,
-                  abar + q * EPI_NBUF, &map_add);
+        epi_do<EM>(v, eo, pix, valid, col0 + c, tma, stage, es, &map_y, w0, h0 + sdh, n0 + sdn, lane, (long long)mt * 4 + q,
+                   abar + q * EPI_NBUF, &map_add);
         if (tma && eo.addend && (c + 32 < BLOCK_N) && (col0 + c + 32 < p.Cout))
           epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + sdh, n0 + sdn, lane);
       }
@@ -674,6 +767,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    });
     if (tma && lane == 0) bulk_wait0();
   }
   tc_fence_before();
@@ -732,6 +826,15 @@ static int addend_mode() {
     if (v == 2 || v < 0 || v > 3) v = 1;
     const char* nf = getenv("SIVAE_TC_NOFENCE");
     if (nf && nf[0] == '1') v |= 8;
+  }
+  return v;
+}
+// SIVAE_TC_FASTEPI (default 1): straight-line epilogue variants (epi_chunk_fast) where the launch qualifies
+static int fast_epi() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SIVAE_TC_FASTEPI");
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v;
 }
@@ -894,6 +997,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
     EpiState es;
     const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats, p.tma_store >> 4};
     const bool tma = (p.tma_store & 1) != 0;
+    epi_dispatch(epi_variant(eo, tma, (p.tma_store >> 12) & 1), [&](auto emc) {
+    constexpr int EM = decltype(emc)::value;
     int lt = 0;
     for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
       const int acc = lt & 1;
@@ -901,22 +1006,21 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
       const int col0 = nt * BLOCK_N;
       // chunk sequence of an item: (t, c) for t < T, c < BLOCK_N step 32; the addend tile of chunk i+1 is requested right
       // after chunk i's store (that of chunk 0 before the accumulator is ready)
-      auto tile_coords = [&](int t, int& w0, int& h0, int& n) {
-        const int lin = mt * T + t;
-        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h;
-        n = lin / (p.tiles_w * p.tiles_h); w0 = tw * 8; h0 = th * 16;
-      };
       int ncol = (p.Cout - col0 + 31) / 32;
       if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
-      int w0, h0, n;
-      tile_coords(0, w0, h0, n);
-      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0, h0 + 4 * q, n, lane);
+      // tile t of the item is linear pixel tile mt*T + t: one division per item, then carry increments (the divisions by
+      // runtime tile counts cost more instructions than the chunk epilogue itself)
+      const int lin0 = mt * T;
+      int tw = lin0 % p.tiles_w, th, n;
+      { const int r = lin0 / p.tiles_w; th = r % p.tiles_h; n = r / p.tiles_h; }
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, tw * 8, th * 16 + 4 * q, n, lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        tile_coords(t, w0, h0, n);
-        const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+        const int w0 = tw * 8, h0 = th * 16, n_cur = n;
+        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }       // (tw, th, n) = next tile
+        const long long pix = ((long long)n_cur * p.H + (h0 + dh)) * p.W + (w0 + dw);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
         for (int ci = 0; ci < ncol; ++ci) {
@@ -924,15 +1028,13 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           // this warp's 32 rows = image rows h0+4q .. +3, columns w0 .. w0+7  -> store box {32 ch, 8, 4, 1}
-          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, (long long)(mt * T + t) * 4 + q,
-                    abar + q * EPI_NBUF, &map_add);
-          if (tma && eo.addend) {
+          epi_do<EM>(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n_cur, lane, (long long)(lin0 + t) * 4 + q,
+                     abar + q * EPI_NBUF, &map_add);
+          if ((EM == 0 && tma && eo.addend) || (EM & 2)) {
             if (ci + 1 < ncol) {
-              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + 4 * q, n, lane);
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + 4 * q, n_cur, lane);
             } else if (t + 1 < T) {
-              int w1, h1, n1;
-              tile_coords(t + 1, w1, h1, n1);
-              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w1, h1 + 4 * q, n1, lane);
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, tw * 8, th * 16 + 4 * q, n, lane);
             }
           }
         }
@@ -941,6 +1043,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    });
     if (tma && lane == 0) bulk_wait0();
   }
   tc_fence_before();
@@ -980,7 +1083,7 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   p.total = (p.tiles_w * p.tiles_h * s.N / T) * p.n_tiles;      // callers pick T = 2 only when the tile count is even
   p.base_offset_mode = halo_mode() == 1 ? 1 : 0;
   p.bias = bias; p.addend = addend; p.y = y;
-  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4)) : 0;
+  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4) | (fast_epi() << 12)) : 0;
   p.stats = p.tma_store ? stats : nullptr;
   CUtensorMap mx, mw, my;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
@@ -1028,8 +1131,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Remote arrive on the leader's "accumulator drained" barrier.  What it orders is TMEM traffic only (the warp's tcgen05.ld
+// have completed: wait::ld + tcgen05.fence::before_thread_sync), so no memory release at cluster scope is needed; the
+// `.release.cluster` form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive -- 10 % of the epilogue
+// warps' time in the ncu capture of the 64-channel layers (profiles/r01o_prof_halo2.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -1192,43 +1299,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     EpiState es;
     const EpiOut eo{p.bias, p.addend, p.y, p.Cout, p.stats, p.tma_store >> 4};
     const bool tma = (p.tma_store & 1) != 0;
+    epi_dispatch(epi_variant(eo, tma, (p.tma_store >> 12) & 1), [&](auto emc) {
+    constexpr int EM = decltype(emc)::value;
     int lt = 0;
     for (int item = cluster_id; item < p.total; item += nclusters, ++lt) {
       const int acc = lt & 1;
       const int nt = item % p.n_tiles, mp = item / p.n_tiles;
       const int col0 = nt * BLOCK_N;
-      auto tile_coords = [&](int t, int& w0, int& h0, int& n) {
-        const int lin = (mp * 2 + (int)rank) * T + t;
-        const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h;
-        n = lin / (p.tiles_w * p.tiles_h); w0 = tw * 8; h0 = th * 16;
-      };
       int ncol = (p.Cout - col0 + 31) / 32;
       if (ncol > BLOCK_N / 32) ncol = BLOCK_N / 32;
-      int w0, h0, n;
-      tile_coords(0, w0, h0, n);
-      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w0, h0 + 4 * q, n, lane);
+      // this CTA's tile t of the item is linear pixel tile (2 mp + rank) T + t: one division per item, then carry increments
+      const int lin0 = (mp * 2 + (int)rank) * T;
+      int tw = lin0 % p.tiles_w, th, n;
+      { const int r = lin0 / p.tiles_w; th = r % p.tiles_h; n = r / p.tiles_h; }
+      if (tma) epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, tw * 8, th * 16 + 4 * q, n, lane);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        tile_coords(t, w0, h0, n);
-        const int lin = (mp * 2 + (int)rank) * T + t;
-        const long long pix = ((long long)n * p.H + (h0 + dh)) * p.W + (w0 + dw);
+        const int w0 = tw * 8, h0 = th * 16, n_cur = n;
+        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++n; } }       // (tw, th, n) = next tile
+        const long long pix = ((long long)n_cur * p.H + (h0 + dh)) * p.W + (w0 + dw);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * T + t) * BLOCK_N);
 #pragma unroll 1
         for (int ci = 0; ci < ncol; ++ci) {
           const int c = ci * 32;
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
-          epi_chunk(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n, lane, (long long)lin * 4 + q,
-                    abar + q * EPI_NBUF, &map_add);
-          if (tma && eo.addend) {
+          epi_do<EM>(v, eo, pix, true, col0 + c, tma, stage, es, &map_y, w0, h0 + 4 * q, n_cur, lane, (long long)(lin0 + t) * 4 + q,
+                     abar + q * EPI_NBUF, &map_add);
+          if ((EM == 0 && tma && eo.addend) || (EM & 2)) {
             if (ci + 1 < ncol) {
-              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + 4 * q, n, lane);
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0 + c + 32, w0, h0 + 4 * q, n_cur, lane);
             } else if (t + 1 < T) {
-              int w1, h1, n1;
-              tile_coords(t + 1, w1, h1, n1);
-              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, w1, h1 + 4 * q, n1, lane);
+              epi_prefetch(eo.addend, eo.amode, es, stage, abar + q * EPI_NBUF, &map_add, col0, tw * 8, th * 16 + 4 * q, n, lane);
             }
           }
         }
@@ -1237,6 +1341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));      // accumulator drained -> leader's MMA warp
     }
+    });
     if (tma && lane == 0) bulk_wait0();
   }
   tc_fence_before();
@@ -1281,7 +1386,7 @@ static int launch_halo2_t(const float* x, const float* w, const float* bias, con
   p.total = (p.tiles_w * p.tiles_h * s.N / (2 * T)) * p.n_tiles;    // items = (2T consecutive pixel tiles, n-tile)
   p.base_offset_mode = 0;
   p.bias = bias; p.addend = addend; p.y = y;
-  p.tma_store = 1 | (addend_mode() << 4);
+  p.tma_store = 1 | (addend_mode() << 4) | (fast_epi() << 12);
   p.stats = stats;
   CUtensorMap mx, mw, my;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
@@ -1584,7 +1689,7 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   if (r) return r;
   // epilogue store path: TMA store of each warp's 32-row slab (needs 16-byte aligned channel rows)
   CUtensorMap my = mx;
-  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4)) : 0;
+  p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4) | (fast_epi() << 12)) : 0;
   p.stats = p.tma_store ? stats : nullptr;
   if (p.tma_store) {
     p.sbh = (32 / p.bw) < p.bh ? (32 / p.bw) : p.bh;
