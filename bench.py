@@ -223,7 +223,7 @@ def run_ours(args):
                               "frac<=0.5 by construction" % peaks["source"],
                     launches_per_step=tc_n / args.steps, ms_per_step=round(tc_ms / args.steps, 3),
                     share_of_step=round(tc_ms / ms_prof, 4), ms_per_step_with_events=round(ms_prof / args.steps, 3),
-                    traffic=_traffic("fwd"),
+                    traffic=_traffic("fwd"), traffic_detail=_traffic("fwd_detail"),
                     wgrad=dict(achieved=round(wg_flops / (wg_ms * 1e-3) / 1e12, 2) if wg_ms > 0 else None,
                                ms_per_step=round(wg_ms / args.steps, 3), launches_per_step=wg_n / args.steps),
                     simt_conv_ms_per_step=round(simt_ms / args.steps, 3))
@@ -243,7 +243,7 @@ def run_ours(args):
                 e2e=dict(value=round(e2e_value, 2), unit="images/s", ms_per_step=round(ms_e2e / args.steps, 3),
                          h2d_bytes_per_step=batch * 3 * size * size * 4 + batch * zdim * 4, d2h_bytes_per_step=64),
                 gpu_launches=int(launches),
-                launch_mode=("cuda graph replay" if importlib.import_module(PKG + ".train_soft_intro_vae")._graph_mode() >= (2 if world > 1 else 1) else "eager") +
+                launch_mode=(("cuda graph replay" if world == 1 else "replay of 3 cuda graph segments, NCCL all-reduces eager between them") if importlib.import_module(PKG + ".train_soft_intro_vae")._graph_mode() >= 1 else "eager") +
                             " of %d kernels per step (counted on an eager step)" % launches_per_step,
                 roofline=roof, clocks=sampler.summary() if rank == 0 else None,
                 last_stats=dict(loss_rec=float(st[5]), kl_real=float(st[1]), lossE=float(st[4]), lossD=float(st[10])))

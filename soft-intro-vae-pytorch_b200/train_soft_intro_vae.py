@@ -463,39 +463,64 @@ def _dist():
 
 
 def _graph_mode():
-    """SIVAE_CUDA_GRAPH: 0 = never, 1 (default) = single-process runs replay the step from a CUDA graph, 2 = also under
-    torch.distributed (the two NCCL all-reduces are captured with the step)"""
+    """SIVAE_CUDA_GRAPH: 0 = never; 1 (default) = replay the step from CUDA graphs -- one graph for the whole iteration in a
+    single-process run, three graph segments with the two NCCL all-reduces launched eagerly between them under
+    torch.distributed; 2 = experimental: also capture the all-reduces inside one graph (hung on this pool's torch 2.11 /
+    NCCL 2.28.9 build, profiles/r01q_dist.md)"""
     try:
         return int(os.environ.get("SIVAE_CUDA_GRAPH", "1"))
     except ValueError:
         return 1
 
 
+def _segmented_step(eng, dist, real, noise, eps, hp, lr_e, lr_d, inv_world, key):
+    """data-parallel iteration as three replayed graph segments cut at the two all-reduces (which run eagerly on the
+    current stream, ordered with the replays): [E half] AR(enc grads) [Adam(E) + D half] AR(dec grads) [Adam(D)]"""
+    enc, dec = _L.NET_ENCODER, _L.NET_DECODER
+    eng.graphed(("introspective/E",) + key, [real.contiguous(), noise.contiguous(), eps[:3].contiguous()],
+                lambda r_, n_, e_: eng.e_step(r_, n_, e_, hp))
+    dist.all_reduce(eng.mem[enc].grads)
+
+    def d_half(e_):
+        eng.adam(enc, lr_e, inv_world)
+        eng.d_step(e_, hp)
+    eng.graphed(("introspective/D",) + key, [eps[3:].contiguous()], d_half)
+    dist.all_reduce(eng.mem[dec].grads)
+    eng.graphed(("introspective/A",) + key, [], lambda: eng.adam(dec, lr_d, inv_world))
+
+
 def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d, use_graph=None):
     """One E-step + D-step through the engine (reference :551-624).  real: [B,C,S,S] on the model's device; noise:
     [B,z]; eps: [5,B,z].  Returns the 16-float device statistics tensor (see include/sivae.h).
-    The ~1900 kernel launches of a step are replayed from a CUDA graph after the first two calls with the same batch
-    size and hyper-parameters (Engine.graphed); use_graph=False (or SIVAE_CUDA_GRAPH=0) keeps every call eager."""
+    The ~2000 kernel launches of a step are replayed from CUDA graphs after the first two calls with the same batch
+    size and hyper-parameters (Engine.graphed); use_graph=False (or SIVAE_CUDA_GRAPH=0) keeps every call eager.
+    Data parallel (torch.distributed initialised): the flat encoder / decoder gradient buffers are
+    sum-all-reduced once each, 1/world folded into the Adam kernel.  The graph is then cut at the two collectives --
+    [E half] all-reduce [Adam(E) + D half] all-reduce [Adam(D)] -- so NCCL is never captured."""
     eng = model._ensure_engine(real.size(0))
     dist = _dist()
     inv_world = 1.0 / dist.get_world_size() if dist else 1.0
+    enc, dec = _L.NET_ENCODER, _L.NET_DECODER
 
     def step(real_, noise_, eps_):
         eng.e_step(real_, noise_, eps_[:3], hp)
         if dist:
-            dist.all_reduce(eng.mem[_L.NET_ENCODER].grads)
-        eng.adam(_L.NET_ENCODER, lr_e, inv_world)
+            dist.all_reduce(eng.mem[enc].grads)
+        eng.adam(enc, lr_e, inv_world)
         eng.d_step(eps_[3:], hp)
         if dist:
-            dist.all_reduce(eng.mem[_L.NET_DECODER].grads)
-        eng.adam(_L.NET_DECODER, lr_d, inv_world)
+            dist.all_reduce(eng.mem[dec].grads)
+        eng.adam(dec, lr_d, inv_world)
 
     mode = _graph_mode()
     if use_graph is None:
-        use_graph = mode >= 2 or (mode == 1 and not dist)
+        use_graph = mode >= 1
     if use_graph and real.is_cuda and not torch.cuda.is_current_stream_capturing():
-        key = ("introspective", tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world)
-        eng.graphed(key, [real.contiguous(), noise.contiguous(), eps.contiguous()], step)
+        key = (tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world)
+        if dist and mode < 2:
+            _segmented_step(eng, dist, real, noise, eps, hp, lr_e, lr_d, inv_world, key)
+        else:
+            eng.graphed(("introspective",) + key, [real.contiguous(), noise.contiguous(), eps.contiguous()], step)
     else:
         step(real, noise, eps)
     return eng.stats

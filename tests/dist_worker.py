@@ -6,8 +6,8 @@ Checks, on every rank:
      model with the same init and inputs are reproduced bit for bit and all-gathered for the comparison);
   2. parameters, Adam moments and statistics are bit-identical on all ranks after the step (one all-reduce result feeds the
      same Adam kernel everywhere) while BatchNorm running statistics stay rank-local (SURVEY 8e);
-  3. the CUDA-graph replay of the step with the two NCCL all-reduces captured inside (SIVAE_CUDA_GRAPH=2) leaves the same
-     state as eager execution over several iterations.
+  3. the CUDA-graph replay of the step (three graph segments, the two NCCL all-reduces launched eagerly between them)
+     leaves the same state as eager execution over several iterations.
 Prints "DIST_OK" from rank 0 on success."""
 import importlib
 import os
@@ -81,7 +81,7 @@ def main():
     if rank != 0:
         assert not torch.equal(bn, ref), "BatchNorm running statistics should be rank-local (different shards)"
 
-    # ---- 3. graph replay with the all-reduces captured == eager ----------------------------------------------
+    # ---- 3. segmented graph replay == eager --------------------------------------------------------------------
     outs = []
     for use_graph in (False, True):
         m = fresh()
@@ -91,7 +91,7 @@ def main():
             stats.append(st.clone())
         torch.cuda.synchronize()
         if use_graph:
-            assert len(m._engine._graphs) == 1, "the graph path did not capture"
+            assert len(m._engine._graphs) == 3, "the graph path did not capture its three segments"
         outs.append(({k: v.detach().clone() for k, v in m.state_dict().items()}, stats))
         dist.barrier()
     (sd_a, st_a), (sd_b, st_b) = outs

@@ -44,6 +44,11 @@ class _StubEngine:
     def adam(self, net, lr, grad_scale=1.0):
         self.calls.append(("adam", net, lr, grad_scale, self.mem[net].grads.clone()))
 
+    def graphed(self, key, inputs, fn):
+        """Engine.graphed without a GPU: run the segment, remember its key"""
+        self.calls.append(("segment", key[0]))
+        return fn(*inputs)
+
 
 class _StubModel:
     def __init__(self, rank):
@@ -70,6 +75,14 @@ def _worker(rank, world, port, out):
         # sum over ranks of arange*(rank+1) = arange*3 ; mean (after grad_scale) = arange*1.5
         assert torch.allclose(g_e, torch.arange(7.0) * 3) and torch.allclose(g_e * gs_e, torch.arange(7.0) * 1.5)
         assert torch.allclose(g_d, 2 * torch.arange(5.0) + 10.0)
+        # the graph-segmented form used on the GPU under torch.distributed: same order, all-reduces between the segments
+        model3 = _StubModel(rank)
+        M._segmented_step(model3.eng, dist, real, torch.zeros(2, 4), torch.zeros(5, 2, 4), None, 1e-3, 2e-3, 1.0 / world, ("k",))
+        names = [c if isinstance(c, str) else (c[1] if c[0] == "segment" else c[0]) for c in model3.eng.calls]
+        assert names == ["introspective/E", "e_step", "introspective/D", "adam", "d_step", "introspective/A", "adam"], names
+        seg_adams = [c for c in model3.eng.calls if not isinstance(c, str) and c[0] == "adam"]
+        assert torch.allclose(seg_adams[0][4], torch.arange(7.0) * 3) and seg_adams[0][3] == 0.5
+        assert torch.allclose(seg_adams[1][4], 2 * torch.arange(5.0) + 10.0) and seg_adams[1][1] == 1
         model2 = _StubModel(rank)
         M.vae_iteration(model2, real, torch.zeros(2, 4), None, 1e-3, 1e-3)
         adams = [c for c in model2.eng.calls if not isinstance(c, str)]
