@@ -147,6 +147,17 @@ int sivae_bn_act_fwd(const float* t, const float* identity, const float* gamma, 
 int sivae_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* gamma, const float* beta,
                      const float* mean_invstd, float* dt, float* g, float* dgamma, float* dbeta, int accumulate,
                      int N, int H, int W, int C, int mode, void* workspace, long long ws_bytes, void* stream);
+/* the same pair with the forward's SIGN BYTES: sign_mask (N*H*W*C/4 bytes, one per float4 of t; bit j = pre-activation of
+   component j was positive) is written by the forward; given to the backward, neither of its passes reads `identity`
+   (6.1 instead of 8 full-tensor passes for a residual block's second BatchNorm).  NULL = the plain functions above. */
+int sivae_bn_act_fwd_m(const float* t, const float* identity, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, long long* nbt, float* mean_invstd, float* out,
+                       int N, int H, int W, int C, int mode, int train, void* workspace, long long ws_bytes,
+                       unsigned char* sign_mask, void* stream);
+int sivae_bn_act_bwd_m(const float* dout, const float* t, const float* identity, const float* gamma, const float* beta,
+                       const float* mean_invstd, float* dt, float* g, float* dgamma, float* dbeta, int accumulate,
+                       int N, int H, int W, int C, int mode, void* workspace, long long ws_bytes,
+                       const unsigned char* sign_mask, void* stream);
 /* fused loss pass (:563-586 / :599-620): per-sample squared-error sums of (rec-real), (rec_rec-rec),
    (rec_fake-fake) in one read of the five images; out: [B,3] */
 int sivae_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,

@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,7 +57,8 @@ struct Net {
   bool present = false;
 };
 
-struct BlockAct { float *id = nullptr, *t1 = nullptr, *a1 = nullptr, *t2 = nullptr, *out = nullptr, *mi1 = nullptr, *mi2 = nullptr; const float* x = nullptr; };
+struct BlockAct { float *id = nullptr, *t1 = nullptr, *a1 = nullptr, *t2 = nullptr, *out = nullptr, *mi1 = nullptr, *mi2 = nullptr; const float* x = nullptr;
+                  unsigned char* m2 = nullptr;   /* sign bytes of the block's final pre-activation (one per float4 of t2) */ };
 struct EncPass {
   const float* img = nullptr;
   float *t0 = nullptr, *mi0 = nullptr, *a0 = nullptr, *feat = nullptr, *ml = nullptr, *z = nullptr, *kl = nullptr;
@@ -89,6 +91,7 @@ struct sivae_engine {
   bool fast = false;               // cdim-facing narrow CUDA-core kernels in use (false: generic exact SIMT everywhere)
   bool comp = false;               // compensated tensor-core mode (SIVAE_CONV_TC3X): 3 tf32 MMAs per product on split operands
   bool rnd = false;                // producers round stored activations / gradients to tf32 (plain tensor-core mode only)
+  bool bn_mask = true;             // residual BN+LeakyReLU forward stores sign bytes so its backward skips the identity re-read (SIVAE_BN_MASK=0: off)
   float* split[4] = {nullptr, nullptr, nullptr, nullptr};   // comp: hi / lo parts of the two conv operands, max activation size each
   // workspace
   void* ws = nullptr; size_t ws_bytes = 0, ws_need = 0;
@@ -291,6 +294,7 @@ static size_t carve(sivae_engine* e, char* base) {
       a.t1 = bp.take<float>(full); a.a1 = bp.take<float>(full); a.t2 = bp.take<float>(full);
       a.out = bp.take<float>(B * os * os * b.outc);
       a.mi1 = bp.take<float>(2 * b.outc); a.mi2 = bp.take<float>(2 * b.outc);
+      a.m2 = e->bn_mask ? bp.take<unsigned char>(full / 4) : nullptr;
     }
     p.feat = bp.take<float>(B * e->feat);
     p.ml = bp.take<float>(B * 2 * z);
@@ -311,6 +315,7 @@ static size_t carve(sivae_engine* e, char* base) {
       a.t1 = bp.take<float>(full); a.a1 = bp.take<float>(full); a.t2 = bp.take<float>(full);
       a.out = bp.take<float>(B * os * os * b.outc);
       a.mi1 = bp.take<float>(2 * b.outc); a.mi2 = bp.take<float>(2 * b.outc);
+      a.m2 = e->bn_mask ? bp.take<unsigned char>(full / 4) : nullptr;
     }
     p.y = bp.take<float>(B * S * S * c.cdim);
   }
@@ -557,7 +562,7 @@ static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, c
     launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->rnd, st); }
   TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st));
   { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode), st);
-    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->rnd, st); }
+    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->rnd, st, a.m2); }
   return 0;
 }
 
@@ -609,11 +614,12 @@ static int block_backward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, 
   float* DA1 = e->sb[4];
   const float* idn = b.expand ? a.id : a.x;
   float* g = n.grads;
-  { // reduce pass reads dout, t2, identity; apply pass reads them again and writes dt and the identity-path gradient
-    ProfElem pe(PC_BN_BWD, B, s, b.outc, 4 + b.mode, 2.0 * (resampled(b.mode) + 2.0) + 2.0, st);
+  { // reduce pass reads dout, t2 and the identity (or, with the forward's sign bytes, 1/16 of a pass instead of it); the apply
+    // pass reads them again and writes dt and the identity-path gradient
+    ProfElem pe(PC_BN_BWD, B, s, b.outc, 4 + b.mode, 2.0 * (resampled(b.mode) + (a.m2 ? 1.0625 : 2.0)) + 2.0, st);
     launch_bn_act_bwd(dout, a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, DT, G2,
                       wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->rnd,
-                      e->red, e->red_bytes, st); }
+                      e->red, e->red_bytes, st, a.m2); }
   if (wgrad) TRY(conv_wgrad(e, n, b.c2, a.a1, DT, B, s, st));
   TRY(conv_dgrad(e, n, b.c2, DT, DA1, nullptr, B, s, st));
   { ProfElem pe(PC_BN_BWD, B, s, b.outc, RS_NONE, 5.0, st);
@@ -700,6 +706,7 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   sivae_engine* e = new sivae_engine();
   e->cfg = *cfg;
   e->comp = cfg->conv_backend == SIVAE_CONV_TC3X;
+  { const char* v = getenv("SIVAE_BN_MASK"); e->bn_mask = !(v && v[0] == '0'); }
   for (int i = 0; i < 3; ++i) { e->nets[i].id = i; e->nets[i].comp = e->comp; }
   build_encoder(e, e->nets[0]);
   build_decoder(e, e->nets[1]);
@@ -1223,6 +1230,31 @@ extern "C" int sivae_bn_act_bwd(const float* dout, const float* t, const float* 
   if ((size_t)ws_bytes < bn_scratch_bytes((long long)N * H * W, C)) return fail(-3, "workspace too small");
   launch_bn_act_bwd(dout, t, identity, mean_invstd, gamma, beta, dt, g, dgamma, dbeta, accumulate != 0, N, H, W, C, mode, false,
                     workspace, (size_t)ws_bytes, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+// variants with the forward's sign bytes (N*H*W*C/4 bytes): the backward then never reads `identity`
+extern "C" int sivae_bn_act_fwd_m(const float* t, const float* identity, const float* gamma, const float* beta, float* running_mean,
+                                  float* running_var, long long* nbt, float* mean_invstd, float* out, int N, int H, int W, int C,
+                                  int mode, int train, void* workspace, long long ws_bytes, unsigned char* sign_mask, void* stream) {
+  if (C % 4 != 0) return fail(-2, "C must be a multiple of 4");
+  long long rows = (long long)N * H * W;
+  if ((size_t)ws_bytes < bn_scratch_bytes(rows, C)) return fail(-3, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (train) launch_bn_stats(t, rows, C, mean_invstd, running_mean, running_var, nbt, workspace, (size_t)ws_bytes, st);
+  else launch_bn_eval_stats(running_mean, running_var, C, mean_invstd, st);
+  launch_bn_act_fwd(t, identity, mean_invstd, gamma, beta, out, N, H, W, C, mode, false, st, sign_mask);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_bn_act_bwd_m(const float* dout, const float* t, const float* identity, const float* gamma, const float* beta,
+                                  const float* mean_invstd, float* dt, float* g, float* dgamma, float* dbeta, int accumulate, int N,
+                                  int H, int W, int C, int mode, void* workspace, long long ws_bytes, const unsigned char* sign_mask,
+                                  void* stream) {
+  if (C % 4 != 0) return fail(-2, "C must be a multiple of 4");
+  if ((size_t)ws_bytes < bn_scratch_bytes((long long)N * H * W, C)) return fail(-3, "workspace too small");
+  launch_bn_act_bwd(dout, t, identity, mean_invstd, gamma, beta, dt, g, dgamma, dbeta, accumulate != 0, N, H, W, C, mode, false,
+                    workspace, (size_t)ws_bytes, (cudaStream_t)stream, sign_mask);
   CHECK_CUDA_RET();
   return 0;
 }

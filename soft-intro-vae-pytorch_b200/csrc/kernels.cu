@@ -538,7 +538,7 @@ template <int MODE, bool ROUND>
 __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t, const float* __restrict__ idn,
                                                     const float* __restrict__ mi, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float* __restrict__ out, int N,
-                                                    int H, int W, int C) {
+                                                    int H, int W, int C, unsigned char* __restrict__ mask) {
   // 32-bit index arithmetic (tensor sizes are < 2^31 float4s; checked by the launcher): 64-bit div/mod per element
   // would make this HBM-bound kernel instruction-bound
   const unsigned cvec = (unsigned)C >> 2;
@@ -567,6 +567,10 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
         float4 d = __ldg(reinterpret_cast<const float4*>(idn + pix * C) + c4);
         y.x += d.x; y.y += d.y; y.z += d.z; y.w += d.w;
       }
+      // sign of the pre-activation, one byte per float4: the backward needs nothing else of y, so it can skip
+      // re-reading the identity tensor (two of its eight full-tensor passes)
+      if (mask)
+        mask[pix * cvec + c4] = (unsigned char)((y.x > 0.f ? 1 : 0) | (y.y > 0.f ? 2 : 0) | (y.z > 0.f ? 4 : 0) | (y.w > 0.f ? 8 : 0));
       return make_float4(lrelu(y.x), lrelu(y.y), lrelu(y.z), lrelu(y.w));
     };
     if (MODE == RS_NONE) {
@@ -595,13 +599,13 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
   }
 }
 void launch_bn_act_fwd(const float* t, const float* identity, const float* mi, const float* gamma, const float* beta,
-                       float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st) {
+                       float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st, unsigned char* mask) {
   g_launches += 1;
   int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
   long long total = (long long)N * Ho * Wo * (C / 4);
   if (total == 0) return;
   unsigned grid = min(cdiv(total, 256), 148u * 32);
-#define LAUNCH(M, R) k_bn_act_fwd<M, R><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C)
+#define LAUNCH(M, R) k_bn_act_fwd<M, R><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C, mask)
   if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
   else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
   else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }
@@ -627,12 +631,17 @@ __device__ __forceinline__ float4 upstream(const float* __restrict__ dout, long 
   }
 }
 __device__ __forceinline__ float lrelu_grad(float y, float d) { return y > 0.f ? d : kSlope * d; }
+// the same through the forward's sign byte (bit j = pre-activation of component j was positive)
+__device__ __forceinline__ float4 lrelu_grad_mask(unsigned m, const float4& d) {
+  return make_float4((m & 1u) ? d.x : kSlope * d.x, (m & 2u) ? d.y : kSlope * d.y, (m & 4u) ? d.z : kSlope * d.z, (m & 8u) ? d.w : kSlope * d.w);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__ dout, const float* __restrict__ t,
                                                        const float* __restrict__ idn, const float* __restrict__ mi,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       int N, int H, int W, int C, float* __restrict__ part, int rpb) {
+                                                       int N, int H, int W, int C, float* __restrict__ part, int rpb,
+                                                       const unsigned char* __restrict__ mask) {
   extern __shared__ float sh[];
   const int cvec = C >> 2;
   const int rl_n = 256 / cvec;
@@ -659,12 +668,17 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
       float4 d = upstream<MODE>(dout, r, n, h, w, H, W, C, cl);
       float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + cl);
       float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
-      float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
-      if (idn) {
-        float4 e = __ldg(reinterpret_cast<const float4*>(idn + r * C) + cl);
-        y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+      float4 g;
+      if (mask) {
+        g = lrelu_grad_mask(__ldg(mask + r * cvec + cl), d);
+      } else {
+        float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
+        if (idn) {
+          float4 e = __ldg(reinterpret_cast<const float4*>(idn + r * C) + cl);
+          y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+        }
+        g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
       }
-      float4 g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
       sg.x += g.x; sg.y += g.y; sg.z += g.z; sg.w += g.w;
       sx.x = fmaf(g.x, xh.x, sx.x); sx.y = fmaf(g.y, xh.y, sx.y); sx.z = fmaf(g.z, xh.z, sx.z); sx.w = fmaf(g.w, xh.w, sx.w);
     }
@@ -707,7 +721,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ idn, const float* __restrict__ mi,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ sums, float* __restrict__ dt,
-                                                      float* __restrict__ gout, int N, int H, int W, int C) {
+                                                      float* __restrict__ gout, int N, int H, int W, int C,
+                                                      const unsigned char* __restrict__ mask) {
   const unsigned cvec = (unsigned)C >> 2;
   const unsigned total = (unsigned)N * H * W * cvec;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -729,12 +744,17 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
     float4 d = upstream<MODE>(dout, (long long)r, n, h, w, H, W, C, c4);
     float4 v = __ldg(reinterpret_cast<const float4*>(t + r * C) + c4);
     float4 xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
-    float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
-    if (idn) {
-      float4 e = __ldg(reinterpret_cast<const float4*>(idn + r * C) + c4);
-      y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+    float4 g;
+    if (mask) {
+      g = lrelu_grad_mask(__ldg(mask + (size_t)r * cvec + c4), d);
+    } else {
+      float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
+      if (idn) {
+        float4 e = __ldg(reinterpret_cast<const float4*>(idn + r * C) + c4);
+        y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+      }
+      g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
     }
-    float4 g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
     float4 o;
     o.x = ga.x * istd.x * (g.x - mg.x - xh.x * mx.x);
     o.y = ga.y * istd.y * (g.y - mg.y - xh.y * mx.y);
@@ -752,7 +772,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
 }
 void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mi, const float* gamma,
                        const float* beta, float* dt, float* g, float* dgamma, float* dbeta, bool accumulate, int N,
-                       int H, int W, int C, int mode, bool rnd, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                       int H, int W, int C, int mode, bool rnd, void* scratch, size_t scratch_bytes, cudaStream_t st,
+                       const unsigned char* mask) {
   g_launches += 3;
   long long rows = (long long)N * H * W;
   if (rows == 0) return;
@@ -762,13 +783,13 @@ void launch_bn_act_bwd(const float* dout, const float* t, const float* identity,
   float* sums = part + (size_t)nblk * 2 * C;
   int cvec = C / 4, rl_n = 256 / cvec;
   size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
-  if (mode == RS_NONE) k_bn_bwd_reduce<RS_NONE><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb);
-  else if (mode == RS_POOL) k_bn_bwd_reduce<RS_POOL><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb);
-  else k_bn_bwd_reduce<RS_UP><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb);
+  if (mode == RS_NONE) k_bn_bwd_reduce<RS_NONE><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb, mask);
+  else if (mode == RS_POOL) k_bn_bwd_reduce<RS_POOL><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb, mask);
+  else k_bn_bwd_reduce<RS_UP><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb, mask);
   k_bn_bwd_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, sums, dgamma, dbeta, accumulate ? 1 : 0);
   long long total = rows * cvec;
   unsigned grid = min(cdiv(total, 256), 148u * 32);
-#define LAUNCH(M, R) k_bn_bwd_apply<M, R><<<grid, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, sums, dt, g, N, H, W, C)
+#define LAUNCH(M, R) k_bn_bwd_apply<M, R><<<grid, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, sums, dt, g, N, H, W, C, mask)
   if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
   else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
   else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }

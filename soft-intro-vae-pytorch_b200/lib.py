@@ -66,6 +66,8 @@ _SIGS = {
     "sivae_conv2d_wgrad": (C.c_int, [_P, _P, _P] + [C.c_int] * 8 + [_P, C.c_longlong, _P]),
     "sivae_bn_act_fwd": (C.c_int, [_P] * 9 + [C.c_int] * 6 + [_P, C.c_longlong, _P]),
     "sivae_bn_act_bwd": (C.c_int, [_P] * 10 + [C.c_int] * 6 + [_P, C.c_longlong, _P]),
+    "sivae_bn_act_fwd_m": (C.c_int, [_P] * 9 + [C.c_int] * 6 + [_P, C.c_longlong, _P, _P]),
+    "sivae_bn_act_bwd_m": (C.c_int, [_P] * 10 + [C.c_int] * 6 + [_P, C.c_longlong, _P, _P]),
     "sivae_mse3": (C.c_int, [_P] * 6 + [C.c_int, C.c_longlong, _P, C.c_longlong, _P]),
     "sivae_kl_reparam": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "sivae_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_longlong, _P]),

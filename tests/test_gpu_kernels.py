@@ -151,8 +151,8 @@ def test_conv_tc3x_unrounded_operands(shape):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("with_id", [False, True])
-def test_bn_act_fwd_bwd(mode, with_id):
+@pytest.mark.parametrize("with_id,use_mask", [(False, False), (True, False), (True, True)])
+def test_bn_act_fwd_bwd(mode, with_id, use_mask):
     lib = L.load()
     N, H, W, Cc = 3, 8, 8, 32
     g = torch.Generator().manual_seed(5)
@@ -181,8 +181,13 @@ def test_bn_act_fwd_bwd(mode, with_id):
     mi = torch.empty(2 * Cc, device=DEV)
     out = torch.empty(_nhwc(y.detach()).shape, device=DEV)
     ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
-    L.check(lib.sivae_bn_act_fwd(L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(rmg), L.ptr(rvg), L.ptr(nbt), L.ptr(mi),
-                                 L.ptr(out), N, H, W, Cc, mode, 1, L.ptr(ws), ws.numel(), _s()), "bn fwd")
+    mask = torch.full((N * H * W * Cc // 4,), 0xF0, dtype=torch.uint8, device=DEV) if use_mask else None
+    if use_mask:
+        L.check(lib.sivae_bn_act_fwd_m(L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(rmg), L.ptr(rvg), L.ptr(nbt), L.ptr(mi),
+                                       L.ptr(out), N, H, W, Cc, mode, 1, L.ptr(ws), ws.numel(), L.ptr(mask), _s()), "bn fwd (mask)")
+    else:
+        L.check(lib.sivae_bn_act_fwd(L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(rmg), L.ptr(rvg), L.ptr(nbt), L.ptr(mi),
+                                     L.ptr(out), N, H, W, Cc, mode, 1, L.ptr(ws), ws.numel(), _s()), "bn fwd")
     torch.cuda.synchronize()
     assert _rel(out.cpu(), _nhwc(y.detach())) < 1e-5
     assert torch.allclose(rmg.cpu().double(), rmd, rtol=1e-5, atol=1e-6)
@@ -192,8 +197,20 @@ def test_bn_act_fwd_bwd(mode, with_id):
     gi = torch.empty_like(tg)
     dgam, dbet = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     doutg = _nhwc(dout).to(DEV)
-    L.check(lib.sivae_bn_act_bwd(L.ptr(doutg), L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(mi), L.ptr(dt),
-                                 L.ptr(gi), L.ptr(dgam), L.ptr(dbet), 0, N, H, W, Cc, mode, L.ptr(ws), ws.numel(), _s()), "bn bwd")
+    if use_mask:
+        # sign bytes = the pre-activation's signs (bit j <-> channel 4*c4 + j), exactly (integer work)
+        yb = F.batch_norm(t.double(), None, None, gamma.double(), beta.double(), True, 0.1, 1e-5) + idn.double()
+        bits = (_nhwc(yb) > 0).reshape(N * H * W, Cc // 4, 4).to(torch.int64)
+        want = (bits * torch.tensor([1, 2, 4, 8])).sum(-1).reshape(-1)
+        near0 = (_nhwc(yb).abs() < 1e-5).reshape(N * H * W, Cc // 4, 4).any(-1).reshape(-1)      # fp32 vs fp64 sign flips at |y| ~ 0
+        assert torch.equal(mask.cpu().to(torch.int64)[~near0], want[~near0])
+        bogus = torch.full_like(ig, float("nan"))      # the masked backward must not read the identity tensor
+        L.check(lib.sivae_bn_act_bwd_m(L.ptr(doutg), L.ptr(tg), L.ptr(bogus), L.ptr(gg), L.ptr(bg), L.ptr(mi), L.ptr(dt),
+                                       L.ptr(gi), L.ptr(dgam), L.ptr(dbet), 0, N, H, W, Cc, mode, L.ptr(ws), ws.numel(), L.ptr(mask),
+                                       _s()), "bn bwd (mask)")
+    else:
+        L.check(lib.sivae_bn_act_bwd(L.ptr(doutg), L.ptr(tg), L.ptr(ig), L.ptr(gg), L.ptr(bg), L.ptr(mi), L.ptr(dt),
+                                     L.ptr(gi), L.ptr(dgam), L.ptr(dbet), 0, N, H, W, Cc, mode, L.ptr(ws), ws.numel(), _s()), "bn bwd")
     torch.cuda.synchronize()
     assert _rel(dt.cpu(), _nhwc(td.grad)) < 2e-5
     assert _rel(dgam.cpu(), gd.grad) < 2e-5 and _rel(dbet.cpu(), bd.grad) < 2e-5
