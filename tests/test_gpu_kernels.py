@@ -152,9 +152,10 @@ def test_conv_tc3x_unrounded_operands(shape):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("with_id,use_mask", [(False, False), (True, False), (True, True)])
-def test_bn_act_fwd_bwd(mode, with_id, use_mask):
+@pytest.mark.parametrize("dims", [(3, 8, 8, 32), (2, 6, 10, 24)])      # power-of-two fast index path / generic path
+def test_bn_act_fwd_bwd(mode, with_id, use_mask, dims):
     lib = L.load()
-    N, H, W, Cc = 3, 8, 8, 32
+    N, H, W, Cc = dims
     g = torch.Generator().manual_seed(5)
     t = torch.randn(N, Cc, H, W, generator=g) * 2 + 0.3
     idn = torch.randn(N, Cc, H, W, generator=g) if with_id else None
