@@ -96,6 +96,14 @@ int sivae_e_step(sivae_engine* e, const float* real_nchw, const float* noise, co
    eps: [2,B,z] (:602,:605).  stats[5]=loss_rec [6]=lossD_rec_kl [7]=lossD_fake_kl [8]=loss_rec_rec
    [9]=loss_fake_rec [10]=lossD [15]=nan flag (the isnan guard of :625). */
 int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper* hp, float* stats, void* stream);
+/* Opt-in (default off; env SIVAE_REUSE_DEC=1): the reference recomputes fake = decoder(noise) and rec = decoder(z) at
+   :597-598 although the decoder has not changed since :557,:561 (only optimizer_e stepped in between).  With on != 0
+   sivae_d_step takes both passes' activations from the preceding sivae_e_step and replays only their BatchNorm
+   running_mean / running_var / num_batches_tracked updates, in the reference's order, from the saved batch statistics:
+   losses, gradients, parameters and buffers stay bit-identical to the recomputing path.  Falls back to recomputing when
+   the decoder parameters were touched between the two halves. */
+int sivae_set_reuse_decoder_passes(sivae_engine* e, int on);
+int sivae_get_reuse_decoder_passes(const sivae_engine* e);
 /* vanilla VAE warm-up step (:512-536): grads of encoder AND decoder. eps: [B,z].
    stats[11]=loss_rec [12]=loss_kl [13]=loss */
 int sivae_vae_step(sivae_engine* e, const float* real_nchw, const float* eps, int batch, const sivae_hyper* hp,

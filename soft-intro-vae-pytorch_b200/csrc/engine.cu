@@ -67,6 +67,8 @@ struct EncPass {
 struct DecPass {
   const float* zin = nullptr;
   float *h = nullptr, *x0 = nullptr, *y = nullptr;
+  double* ema = nullptr;           // EMA inputs (batch mean | unbiased var) of every BN of the pass, in the net's BN buffer layout
+  const void* net = nullptr;       // the weight set the slot's activations were computed with (pass re-use check)
   std::vector<BlockAct> blk;
 };
 
@@ -106,6 +108,8 @@ struct sivae_engine {
   void* red = nullptr; size_t red_bytes = 0;
   int cur_batch = 0;
   bool have_e_state = false;
+  bool reuse_dec = false;          // D half re-uses the E half's fake / rec decoder passes (SIVAE_REUSE_DEC=1 or sivae_set_option)
+  bool e_dec_valid = false;        // dp[0] / dp[1] hold D(noise) / D(z) of the current decoder weights
 };
 
 // -------------------------------------------------------------------------------------------------------------
@@ -318,6 +322,7 @@ static size_t carve(sivae_engine* e, char* base) {
       a.m2 = e->bn_mask ? bp.take<unsigned char>(full / 4) : nullptr;
     }
     p.y = bp.take<float>(B * S * S * c.cdim);
+    p.ema = bp.take<double>(dn.bn_floats);
   }
   long long ma = max_act_elems(e);
   for (int i = 0; i < 5; ++i) e->sb[i] = bp.take<float>(ma);
@@ -477,7 +482,7 @@ static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, floa
 // t = conv(x, W) followed by the BatchNorm batch statistics of t (train) or the running statistics (eval).  On the tensor
 // core path the statistics come out of the conv epilogue (no second pass over t).
 static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, const float* x, float* t, float* mi, int B, int size,
-                         bool train, cudaStream_t st) {
+                         bool train, cudaStream_t st, double* ema = nullptr) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const long long rows = (long long)B * size * size;
   int parts = (train && e->tc && !e->comp && (fwd_on_rowsep_in(e, s) || (!fwd_on_narrow(e, s) && fwd_on_tc(e, s)))) ? conv_tc_stats_parts(s) : 0;
@@ -486,9 +491,11 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
   TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp, n.derived + c.wn_off,
                c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr));
   if (parts > 0)
-    launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st);
+    launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st,
+                               ema ? ema + bn.rm_off : nullptr);
   else if (train)
-    launch_bn_stats(t, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, e->red, e->red_bytes, st);
+    launch_bn_stats(t, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, e->red, e->red_bytes, st,
+                    ema ? ema + bn.rm_off : nullptr);
   else
     launch_bn_eval_stats(n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, bn.c, mi, st);
   return 0;
@@ -542,25 +549,17 @@ static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, co
 // forward passes
 // -------------------------------------------------------------------------------------------------------------
 
-static int bn_forward_stats(sivae_engine* e, Net& n, const Bn& bn, const float* t, long long rows, float* mi, bool train, cudaStream_t st) {
-  if (train)
-    launch_bn_stats(t, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, e->red, e->red_bytes, st);
-  else
-    launch_bn_eval_stats(n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, bn.c, mi, st);
-  return 0;
-}
-
 // ResidualBlock.forward (:65-75) + the AvgPool2d / Upsample that follows it in `main` (:98,155)
-static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* x, int B, bool train, cudaStream_t st) {
+static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* x, int B, bool train, cudaStream_t st,
+                         double* ema = nullptr) {
   a.x = x;
   const int s = b.size;
-  const long long rows = (long long)B * s * s;
   const float* idn = x;
   if (b.expand) { TRY(conv_fwd(e, n, b.ce, x, a.id, nullptr, B, s, st)); idn = a.id; }
-  TRY(conv_bn_stats(e, n, b.c1, b.bn1, x, a.t1, a.mi1, B, s, train, st));
+  TRY(conv_bn_stats(e, n, b.c1, b.bn1, x, a.t1, a.mi1, B, s, train, st, ema));
   { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0, st);
     launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->rnd, st); }
-  TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st));
+  TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st, ema));
   { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode), st);
     launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->rnd, st, a.m2); }
   return 0;
@@ -594,8 +593,9 @@ static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int 
   launch_nchw_to_nhwc(p.h, p.x0, B, e->C_last, e->hw_last, e->hw_last, st);
   if (e->rnd) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
   const float* x = p.x0;
+  p.net = train ? &n : nullptr;
   for (size_t i = 0; i < n.blocks.size(); ++i) {
-    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st, train ? p.ema : nullptr));
     x = p.blk[i].out;
   }
   TRY(conv_fwd(e, n, n.predict, x, p.y, nullptr, B, c.image_size, st));
@@ -707,6 +707,7 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   e->cfg = *cfg;
   e->comp = cfg->conv_backend == SIVAE_CONV_TC3X;
   { const char* v = getenv("SIVAE_BN_MASK"); e->bn_mask = !(v && v[0] == '0'); }
+  { const char* v = getenv("SIVAE_REUSE_DEC"); e->reuse_dec = v && v[0] == '1'; }
   for (int i = 0; i < 3; ++i) { e->nets[i].id = i; e->nets[i].comp = e->comp; }
   build_encoder(e, e->nets[0]);
   build_decoder(e, e->nets[1]);
@@ -772,6 +773,7 @@ extern "C" int sivae_bind_workspace(sivae_engine* e, void* ws, long long bytes) 
     if (e->nets[i].present) cudaMemcpy(e->nets[i].step_dev, &e->nets[i].step_pending, sizeof(long long), cudaMemcpyHostToDevice);
   }
   e->have_e_state = false;
+  e->e_dec_valid = false;
   return 0;
 }
 extern "C" int sivae_params_changed(sivae_engine* e, int net) {
@@ -841,6 +843,7 @@ extern "C" int sivae_e_step(sivae_engine* e, const float* real_nchw, const float
   CHECK_CUDA_RET();
   e->cur_batch = B;
   e->have_e_state = true;
+  e->e_dec_valid = true;
   return 0;
 }
 
@@ -858,13 +861,23 @@ extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper
   Net& dn = e->nets[1];
   Net& tn = boot ? e->nets[2] : e->nets[1];
   if (!dn.grads) return fail(-4, "decoder grads not bound");
+  // pass re-use (opt-in): the decoder weights have not moved since the E half (only Adam(encoder) ran), so fake = D(noise)
+  // and rec = D(z) (:597-598) are bit for bit the E half's passes (:557,:561), whose activations still sit in dp[0] / dp[1]
+  const bool reuse = e->reuse_dec && e->e_dec_valid && !dn.dirty && e->dp[0].net == &dn && e->dp[1].net == &dn;
+  e->e_dec_valid = false;
   TRY(refresh_derived(e, en, st)); TRY(refresh_derived(e, dn, st));
   if (boot) TRY(refresh_derived(e, tn, st));
   const float *eps4 = eps, *eps5 = eps + (long long)B * z;
   EncPass &E4 = e->ep[0], &E5 = e->ep[1];
   DecPass &D5 = e->dp[0], &D6 = e->dp[1], &D7 = e->dp[2], &D8 = e->dp[3];
-  TRY(dec_forward(e, dn, D5, e->noise, B, true, st));                 // fake :597
-  TRY(dec_forward(e, dn, D6, e->z_keep, B, true, st));                // rec  :598
+  if (reuse) {
+    // the only new effect of recomputing them: one more running-statistics update per pass, in this order
+    launch_bn_ema_replay(D5.ema, dn.bn, dn.bn_floats, dn.nbt, (int)dn.binfo.size(), st);
+    launch_bn_ema_replay(D6.ema, dn.bn, dn.bn_floats, dn.nbt, (int)dn.binfo.size(), st);
+  } else {
+    TRY(dec_forward(e, dn, D5, e->noise, B, true, st));               // fake :597
+    TRY(dec_forward(e, dn, D6, e->z_keep, B, true, st));              // rec  :598
+  }
   TRY(enc_forward(e, en, E4, D6.y, B, true, st));                     // :601
   launch_kl_reparam(E4.ml, eps4, E4.z, E4.kl, B, z, st);
   TRY(enc_forward(e, en, E5, D5.y, B, true, st));                     // :604
@@ -930,8 +943,16 @@ extern "C" int sivae_vae_step(sivae_engine* e, const float* real_nchw, const flo
   TRY(enc_backward(e, en, E1, e->dml, true, nullptr, nullptr, B, st));
   CHECK_CUDA_RET();
   e->have_e_state = false;
+  e->e_dec_valid = false;
   return 0;
 }
+
+extern "C" int sivae_set_reuse_decoder_passes(sivae_engine* e, int on) {
+  if (!e) return fail(-1, "null engine");
+  e->reuse_dec = on != 0;
+  return 0;
+}
+extern "C" int sivae_get_reuse_decoder_passes(const sivae_engine* e) { return e ? (e->reuse_dec ? 1 : 0) : -1; }
 
 extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_scale, void* stream) {
   Net* n = get_net(e, net);

@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) k_bn_stats_partial(const float* __restric
 // one warp per channel: lanes stride over the per-block partials (fp64), shuffle-reduce, lane 0 finalises
 __global__ void k_bn_stats_finalize(const float* __restrict__ part, int nblk, long long rows, int C,
                                     float* __restrict__ mean_invstd, float* running_mean, float* running_var,
-                                    long long* nbt) {
+                                    long long* nbt, double* __restrict__ ema_save) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c == 0 && lane == 0 && nbt) *nbt += 1;
@@ -481,10 +481,26 @@ __global__ void k_bn_stats_finalize(const float* __restrict__ part, int nblk, lo
     double unb = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
     running_mean[c] = (float)((1.0 - kBnMomentum) * (double)running_mean[c] + kBnMomentum * mean);
     running_var[c] = (float)((1.0 - kBnMomentum) * (double)running_var[c] + kBnMomentum * unb);
+    if (ema_save) { ema_save[c] = mean; ema_save[C + c] = unb; }     // the exact EMA inputs, for launch_bn_ema_replay
   }
 }
+// A second train-mode forward of the same net over the same input with unchanged weights (the D half's fake / rec,
+// :597-598, repeat the E half's :557,:561) sees the same batch statistics: its only new effect is one more EMA update of
+// every running buffer and num_batches_tracked.  `ema` mirrors the net's BN buffer layout ([mean C | unbiased var C] per
+// layer) and holds the doubles k_bn_stats_finalize used, so the replayed update is bit-identical to recomputing the pass.
+__global__ void k_bn_ema_replay(const double* __restrict__ ema, float* __restrict__ running, long long n,
+                                long long* __restrict__ nbt, int n_bn) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) running[i] = (float)((1.0 - kBnMomentum) * (double)running[i] + kBnMomentum * ema[i]);
+  if (i < n_bn) nbt[i] += 1;
+}
+void launch_bn_ema_replay(const double* ema, float* running, long long n, long long* nbt, int n_bn, cudaStream_t st) {
+  g_launches += 1;
+  long long m = n > n_bn ? n : n_bn;
+  k_bn_ema_replay<<<cdiv(m, 256), 256, 0, st>>>(ema, running, n, nbt, n_bn);
+}
 void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, float* running_mean,
-                     float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                     float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st, double* ema_save) {
   g_launches += 2;
   int nblk = bn_nblocks(rows);
   float* part = (float*)scratch;
@@ -492,7 +508,7 @@ void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, 
   int rl_n = 256 / cvec;
   size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
   k_bn_stats_partial<<<nblk, 256, shmem, st>>>(t, rows, C, part, bn_rows_per_block(rows));
-  k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, mean_invstd, running_mean, running_var, nbt);
+  k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, mean_invstd, running_mean, running_var, nbt, ema_save);
 }
 // coalesced pre-reduction of many partial rows: out[b][i] = sum_{r in slab b} part[r][i], i over 2*C
 __global__ void __launch_bounds__(256) k_parts_reduce(const float* __restrict__ part, float* __restrict__ out, int nparts, int twoC, int slab) {
@@ -508,7 +524,7 @@ size_t bn_parts_scratch_bytes(int nparts, int C) {
 }
 // part: [nparts][2][C] written by the conv epilogue; the pre-reduced rows are stored right behind it (same scratch)
 void launch_bn_stats_from_parts(float* part, int nparts, long long rows, int C, float* mean_invstd, float* running_mean,
-                                float* running_var, long long* nbt, cudaStream_t st) {
+                                float* running_var, long long* nbt, cudaStream_t st, double* ema_save) {
   const float* src = part;
   int n = nparts;
   if (nparts > 512) {
@@ -521,7 +537,7 @@ void launch_bn_stats_from_parts(float* part, int nparts, long long rows, int C, 
     n = nb;
   }
   g_launches += 1;
-  k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(src, n, rows, C, mean_invstd, running_mean, running_var, nbt);
+  k_bn_stats_finalize<<<cdiv(C, 8), 256, 0, st>>>(src, n, rows, C, mean_invstd, running_mean, running_var, nbt, ema_save);
 }
 __global__ void k_bn_eval_stats(const float* rm, const float* rv, int C, float* mi) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;

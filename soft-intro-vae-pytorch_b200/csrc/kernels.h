@@ -90,10 +90,15 @@ int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvS
 size_t bn_scratch_bytes(long long rows, int C);
 // batch statistics of t[rows][C] -> mean_invstd[0..C) = mean, [C..2C) = invstd; running-stat EMA + nbt++
 void launch_bn_stats(const float* t, long long rows, int C, float* mean_invstd, float* running_mean,
-                     float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st);
+                     float* running_var, long long* nbt, void* scratch, size_t scratch_bytes, cudaStream_t st,
+                     double* ema_save = nullptr);
 size_t bn_parts_scratch_bytes(int nparts, int C);
 void launch_bn_stats_from_parts(float* part, int nparts, long long rows, int C, float* mean_invstd, float* running_mean,
-                                float* running_var, long long* nbt, cudaStream_t st);
+                                float* running_var, long long* nbt, cudaStream_t st, double* ema_save = nullptr);
+// ema_save ([mean C | unbiased var C] doubles, nullable) receives the exact EMA inputs of the update; replaying them with
+// launch_bn_ema_replay over a whole net (`ema` / `running` in the net's BN buffer layout, n floats, n_bn layers) applies
+// the running-statistics side effect of one more identical train-mode forward without recomputing it
+void launch_bn_ema_replay(const double* ema, float* running, long long n, long long* nbt, int n_bn, cudaStream_t st);
 // eval-mode: mean_invstd from running stats
 void launch_bn_eval_stats(const float* running_mean, const float* running_var, int C, float* mean_invstd, cudaStream_t st);
 // out = resample(lrelu(bn(t) + identity)); identity may be null. (N,H,W) are the dims of t.

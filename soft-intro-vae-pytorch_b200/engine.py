@@ -99,6 +99,17 @@ class Engine:
     def max_batch(self):
         return self.cfg.max_batch
 
+    @property
+    def reuse_decoder_passes(self):
+        """D half takes fake = D(noise) and rec = D(z) (reference :597-598) from the E half's identical passes (:557,
+        :561) instead of recomputing them; the BatchNorm running-statistics updates of the skipped passes are replayed
+        from the saved batch statistics, so every result stays bit-identical.  Off unless SIVAE_REUSE_DEC=1 or set here."""
+        return bool(L.load().sivae_get_reuse_decoder_passes(self.handle))
+
+    @reuse_decoder_passes.setter
+    def reuse_decoder_passes(self, on):
+        L.check(L.load().sivae_set_reuse_decoder_passes(self.handle, 1 if on else 0), "sivae_set_reuse_decoder_passes")
+
     def drop_graphs(self):
         """Forget every captured step graph (pointers or derived-filter state they baked in are no longer valid)."""
         self._graphs = {}
@@ -135,6 +146,7 @@ class Engine:
         self.drop_graphs()
         lib = L.load()
         steps = {net: lib.sivae_adam_get_step(self.handle, net) for net in self.mem}
+        reuse = self.reuse_decoder_passes
         lib.sivae_destroy(self.handle)
         self.cfg.max_batch = int(max_batch)
         self.handle = C.c_void_p()
@@ -144,6 +156,7 @@ class Engine:
             self._bind()
         for net, s in steps.items():
             lib.sivae_adam_set_step(self.handle, net, s)
+        self.reuse_decoder_passes = reuse
 
     def close(self):
         if self.handle:

@@ -50,6 +50,8 @@ _SIGS = {
     "sivae_e_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(Hyper), _P, _P]),
     "sivae_d_step": (C.c_int, [_P, _P, C.POINTER(Hyper), _P, _P]),
     "sivae_vae_step": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Hyper), _P, _P]),
+    "sivae_set_reuse_decoder_passes": (C.c_int, [_P, C.c_int]),
+    "sivae_get_reuse_decoder_passes": (C.c_int, [_P]),
     "sivae_adam_step": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, _P]),
     "sivae_adam_set_step": (C.c_int, [_P, C.c_int, C.c_longlong]),
     "sivae_adam_get_step": (C.c_longlong, [_P, C.c_int]),

@@ -489,15 +489,19 @@ def _segmented_step(eng, dist, real, noise, eps, hp, lr_e, lr_d, inv_world, key)
     eng.graphed(("introspective/A",) + key, [], lambda: eng.adam(dec, lr_d, inv_world))
 
 
-def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d, use_graph=None):
+def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d, use_graph=None, reuse_decoder_passes=None):
     """One E-step + D-step through the engine (reference :551-624).  real: [B,C,S,S] on the model's device; noise:
     [B,z]; eps: [5,B,z].  Returns the 16-float device statistics tensor (see include/sivae.h).
     The ~2000 kernel launches of a step are replayed from CUDA graphs after the first two calls with the same batch
     size and hyper-parameters (Engine.graphed); use_graph=False (or SIVAE_CUDA_GRAPH=0) keeps every call eager.
     Data parallel (torch.distributed initialised): the flat encoder / decoder gradient buffers are
     sum-all-reduced once each, 1/world folded into the Adam kernel.  The graph is then cut at the two collectives --
-    [E half] all-reduce [Adam(E) + D half] all-reduce [Adam(D)] -- so NCCL is never captured."""
+    [E half] all-reduce [Adam(E) + D half] all-reduce [Adam(D)] -- so NCCL is never captured.
+    reuse_decoder_passes (None: keep the engine's setting, default off / SIVAE_REUSE_DEC): the D half re-uses the E half's
+    fake / rec decoder passes instead of recomputing them (bit-identical results, see Engine.reuse_decoder_passes)."""
     eng = model._ensure_engine(real.size(0))
+    if reuse_decoder_passes is not None and bool(reuse_decoder_passes) != eng.reuse_decoder_passes:
+        eng.reuse_decoder_passes = reuse_decoder_passes
     dist = _dist()
     inv_world = 1.0 / dist.get_world_size() if dist else 1.0
     enc, dec = _L.NET_ENCODER, _L.NET_DECODER
@@ -516,7 +520,7 @@ def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d, use_graph=N
     if use_graph is None:
         use_graph = mode >= 1
     if use_graph and real.is_cuda and not torch.cuda.is_current_stream_capturing():
-        key = (tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world)
+        key = (tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world, eng.reuse_decoder_passes)
         if dist and mode < 2:
             _segmented_step(eng, dist, real, noise, eps, hp, lr_e, lr_d, inv_world, key)
         else:

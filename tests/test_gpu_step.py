@@ -246,3 +246,71 @@ def test_graph_replay_is_bit_identical_to_eager():
         assert torch.equal(a, b)
     for k in sd_a:
         assert torch.equal(sd_a[k], sd_b[k]), k
+
+
+@pytest.mark.parametrize("bootstrap", [False, True])
+def test_decoder_pass_reuse_is_bit_identical(bootstrap):
+    """sivae_set_reuse_decoder_passes: the D half takes fake = D(noise) and rec = D(z) (reference :597-598) from the E
+    half's passes (:557,:561) -- the decoder did not move in between -- and replays only their BatchNorm running-stat /
+    num_batches_tracked updates.  Parameters, Adam state, BN buffers and the logged statistics must be bit for bit those
+    of the recomputing path, eager and graphed, over several iterations; and fewer kernels must have launched."""
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + (".train_soft_intro_vae_bootstrap" if bootstrap else ".train_soft_intro_vae"))
+    E = importlib.import_module(PKG + ".engine")
+    L = importlib.import_module(PKG + ".lib")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    g = torch.Generator().manual_seed(12)
+    reals = [torch.rand(8, 3, 32, 32, generator=g).cuda() for _ in range(4)]
+    noises = [torch.randn(8, 32, generator=g).cuda() for _ in range(4)]
+    epss = [torch.randn(5, 8, 32, generator=g).cuda() for _ in range(4)]
+    hp = E.make_hyper(1.0, 1.0, 256.0, 1.0 if bootstrap else 1e-8, 1.0 / (3 * 32 * 32))
+    outs, launches = [], []
+    for reuse, use_graph in ((False, False), (True, False), (True, True)):
+        torch.manual_seed(4)
+        model = M.SoftIntroVAE(**cfg).to("cuda:0")
+        stats = []
+        n0 = L.load().sivae_launch_count()
+        for i in range(4):
+            st = M.introspective_iteration(model, reals[i], noises[i], epss[i], hp, 2e-4, 2e-4, use_graph=use_graph,
+                                           reuse_decoder_passes=reuse)
+            stats.append(st.clone())
+        torch.cuda.synchronize()
+        launches.append(L.load().sivae_launch_count() - n0)
+        assert model._engine.reuse_decoder_passes == reuse
+        outs.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, stats))
+    assert launches[1] < launches[0], "the re-use path launched as many kernels as the recomputing path"
+    for sd_b, st_b in outs[1:]:
+        for a, b in zip(outs[0][1], st_b):
+            assert torch.equal(a, b)
+        for k in outs[0][0]:
+            assert torch.equal(outs[0][0][k], sd_b[k]), k
+
+
+def test_decoder_pass_reuse_falls_back_when_decoder_touched():
+    """parameters edited between the two halves (sivae_params_changed on the decoder): the D half must recompute"""
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    L = importlib.import_module(PKG + ".lib")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    g = torch.Generator().manual_seed(13)
+    real, noise, eps = torch.rand(8, 3, 32, 32, generator=g).cuda(), torch.randn(8, 32, generator=g).cuda(), torch.randn(5, 8, 32, generator=g).cuda()
+    hp = E.make_hyper(1.0, 1.0, 256.0, 1e-8, 1.0 / (3 * 32 * 32))
+    res = []
+    for reuse in (False, True):
+        torch.manual_seed(4)
+        model = M.SoftIntroVAE(**cfg).to("cuda:0")
+        eng = model._ensure_engine(8)
+        eng.reuse_decoder_passes = reuse
+        eng.e_step(real, noise, eps[:3], hp)
+        eng.adam(L.NET_ENCODER, 2e-4)
+        with torch.no_grad():
+            model.decoder.fc[0].weight.mul_(1.5)            # an edit the E half's cached passes know nothing about
+        eng.params_changed(L.NET_DECODER)
+        eng.d_step(eps[3:], hp)
+        torch.cuda.synchronize()
+        res.append((eng.stats.clone(), eng.mem[L.NET_DECODER].grads.clone(), eng.mem[L.NET_DECODER].bn.clone()))
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
