@@ -265,12 +265,72 @@ def run_ours(args):
                                                "fake/rec decoder passes, BN running-stat updates replayed; bit-identical results")
     if graph_ms is not None:
         line["cuda_graph"] = dict(ms_per_step=round(graph_ms, 3), value=round(world * batch / (graph_ms / 1e3), 2))
+    if rank == 0 and world == 1 and not args.no_loader_leg and size >= 128:
+        try:
+            line["image_loader"] = image_loader_leg(device, size, batch)
+        except Exception as ex:                       # a secondary leg must never take the headline down with it
+            line["image_loader"] = dict(error=repr(ex)[:300])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, budget_s=args.cpu_budget)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def image_loader_leg(device, out_size, batch, steps=20, warmup=3, src_size=1024):
+    """Secondary kernel: batch assembly of decoded 8-bit images -- mirror + Pillow-exact bicubic resize
+    + ToTensor -- for the workload's loader geometry (CelebA-HQ / FFHQ sources are 1024x1024).  HBM-bound byte work:
+    algorithmic bytes = source pixels once + float output once."""
+    import numpy as np
+    import torch
+    G = importlib.import_module(PKG + ".gpu_dataset")
+    peaks = measured_peaks()
+    n_host = 4                                   # 4 x 100 MB distinct source batches: every launch reads cold data
+    g = torch.Generator().manual_seed(99)
+    host = [torch.randint(0, 256, (batch, src_size, src_size, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(n_host)]
+    dev = [h.to(device) for h in host]
+    flags = (torch.arange(batch) % 2).to(torch.uint8)
+    flags_d = flags.to(device)
+    bt = G.ImageBatcher(out_size, out_size, device)
+    out = torch.empty(batch, 3, out_size, out_size, dtype=torch.float32, device=device)
+
+    def timed(fn):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+    ms = timed(lambda i: bt(dev[i % n_host], flags_d, out=out))
+    ms_e2e = timed(lambda i: bt(host[i % n_host], flags, out=out))          # pinned host pixels -> device inside the region
+    nbytes = batch * src_size * src_size * 3 + batch * 3 * out_size * out_size * 4
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    # the reference's own implementation of the same work on one host core (main.py:47 passes num_workers=0): Pillow + ToTensor
+    from PIL import Image
+    a = host[0][0].numpy()
+    t0, n_cpu = time.time(), 0
+    while time.time() - t0 < 3.0:
+        im = Image.fromarray(a, "RGB")
+        if n_cpu % 2:
+            im = im.transpose(Image.FLIP_LEFT_RIGHT)
+        r = np.asarray(im.resize((out_size, out_size), Image.BICUBIC))
+        torch.from_numpy(r.copy()).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+        n_cpu += 1
+    cpu_ips = n_cpu / (time.time() - t0)
+    return dict(kernel="k_image_batch<3> (mirror + Pillow-exact bicubic %dx%d -> %dx%d + ToTensor, batch %d)" % (src_size, src_size, out_size, out_size, batch),
+                value=round(batch / (ms * 1e-3), 1), unit="images/s", ms_per_batch=round(ms, 4),
+                e2e=dict(value=round(batch / (ms_e2e * 1e-3), 1), unit="images/s", ms_per_batch=round(ms_e2e, 4),
+                         h2d_bytes_per_step=batch * src_size * src_size * 3 + batch, d2h_bytes_per_step=0),
+                roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4),
+                              bytes_per_launch=nbytes, traffic=None),
+                cpu_baseline=dict(value=round(cpu_ips, 1), unit="images/s", cores=1, kind="reference",
+                                  sample="Pillow %s resize + ToTensor of one %dx%d image repeated for 3 s on one core "
+                                         "(the reference's loader runs in the training process, num_workers=0)" % (__import__("PIL").__version__, src_size, src_size)))
 
 
 def _traffic(kind):
@@ -356,6 +416,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-loader-leg", action="store_true", help="skip the image batch-assembly kernel timing")
     ap.add_argument("--no-reuse-leg", action="store_true", help="skip the secondary timing with decoder-pass re-use")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     ap.add_argument("--layers", default="", help="write the per-conv-shape timing table (CUDA events) to this file")

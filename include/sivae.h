@@ -175,6 +175,23 @@ int sivae_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* 
 int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
                     long long step, void* stream);
 
+
+/* ---- image batch assembly: the loader that feeds the step -------------------------------------
+   soft_intro_vae/dataset.py:12-47 load_image as the image configs call it (train_soft_intro_vae.py:388-392, 400-404,
+   415-417: input_height=None, crop_height=None, output_height=S, is_mirror=True) + transforms.ToTensor (:66-68, 75):
+   ImageOps.mirror -> Image.resize((S,S), Image.BICUBIC) -> uint8/255.  Bit-exact with Pillow's fixed-point resampler
+   (Resample.c); JPEG/PNG decoding stays with the caller.
+   sivae_resample_coeffs: Pillow's precompute_coeffs + normalize_coeffs_8bpc for one axis (host only, no GPU needed):
+   bounds [out_size][2] = (first source index, tap count), kk [out_size][*ksize] 22-bit fixed-point taps.
+   A "plan" is the pair of coefficient tables of one (in_h,in_w)->(out_h,out_w) geometry in caller-owned device memory
+   (sivae_image_plan_bytes / _init once per geometry).  sivae_image_batch_u8: src_hwc [B,in_h,in_w,C] decoded 8-bit
+   pixels (C = 1 or 3, 4-byte aligned base), mirror [B] bytes (NULL = none), out_nchw [B,C,out_h,out_w] float32. */
+int sivae_resample_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk, long long kk_capacity);
+long long sivae_image_plan_bytes(int in_h, int in_w, int out_h, int out_w);
+int sivae_image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, long long plan_bytes, void* stream);
+int sivae_image_batch_u8(const unsigned char* src_hwc, const unsigned char* mirror, int batch, int in_h, int in_w,
+                         int channels, int out_h, int out_w, const void* plan_dev, float* out_nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

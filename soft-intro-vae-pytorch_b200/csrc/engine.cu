@@ -1303,3 +1303,35 @@ extern "C" int sivae_adam_flat(float* p, const float* g, float* m, float* v, lon
   CHECK_CUDA_RET();
   return 0;
 }
+
+// ---- image batch assembly (image.cu) -----------------------------------------------------------------------------
+extern "C" int sivae_resample_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk, long long kk_capacity) {
+  if (in_size < 1 || out_size < 1 || !ksize || !bounds || !kk) return fail(-1, "bad argument");
+  std::vector<int> b, k;
+  const int ks = resample_coeffs(in_size, out_size, b, k);
+  *ksize = ks;
+  if ((long long)k.size() > kk_capacity) return fail(-3, "coefficient buffer too small");
+  memcpy(bounds, b.data(), sizeof(int) * b.size());
+  memcpy(kk, k.data(), sizeof(int) * k.size());
+  return 0;
+}
+extern "C" long long sivae_image_plan_bytes(int in_h, int in_w, int out_h, int out_w) {
+  if (in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1) return -1;
+  return (long long)image_plan_bytes(in_h, in_w, out_h, out_w);
+}
+extern "C" int sivae_image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, long long plan_bytes, void* stream) {
+  if (in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1 || !plan_dev) return fail(-1, "bad argument");
+  if ((size_t)plan_bytes < image_plan_bytes(in_h, in_w, out_h, out_w)) return fail(-3, "plan buffer too small");
+  int r = image_plan_init(in_h, in_w, out_h, out_w, plan_dev, (cudaStream_t)stream);
+  if (r) return fail(r, "coefficient upload failed");
+  return 0;
+}
+extern "C" int sivae_image_batch_u8(const unsigned char* src_hwc, const unsigned char* mirror, int batch, int in_h, int in_w,
+                                    int channels, int out_h, int out_w, const void* plan_dev, float* out_nchw, void* stream) {
+  if (!src_hwc || !plan_dev || !out_nchw) return fail(-1, "null argument");
+  int r = launch_image_batch(src_hwc, mirror, batch, in_h, in_w, channels, out_h, out_w, plan_dev, out_nchw, (cudaStream_t)stream);
+  if (r == -2) return fail(-2, "bad image batch arguments (channels must be 1 or 3, batch <= 65535, source 4-byte aligned)");
+  if (r == -7) return fail(-7, "down-scaling factor too large for the shared-memory staging of the resize kernel");
+  if (r) return fail(r, cudaGetErrorString((cudaError_t)r));
+  return 0;
+}

@@ -1,0 +1,297 @@
+// image.cu -- batch assembly of decoded 8-bit images on the GPU (the loader that feeds the step):
+//   ImageOps.mirror  ->  Image.resize((S, S), Image.BICUBIC)  ->  transforms.ToTensor()
+// i.e. soft_intro_vae/dataset.py:26-27, :46 and :66-68,75 as the image configs call load_image
+// (train_soft_intro_vae.py:388-392, 400-404, 415-417: input_height=None, crop_height=None, output_height=S).
+// The arithmetic is Pillow's (src/libImaging/Resample.c; not part of the reference tree): fixed-point (22 fractional bits)
+// bicubic coefficients computed in doubles on the host, a horizontal pass that rounds and saturates to 8 bits, then a
+// vertical pass that does the same; ToTensor is uint8 / 255 in float32.  All of it integer / correctly-rounded, so the
+// result is bit-exact (tests/test_gpu_image.py against oracle/image_oracle.py, which is pinned to Pillow itself).
+//
+// One kernel per batch: a CTA owns a TW x TH tile of one output image, stages the source window it needs (coalesced
+// aligned 32-bit loads) in shared memory, runs the horizontal pass into a shared 8-bit intermediate (never written to
+// HBM) and the vertical pass straight into the NCHW float output.  HBM traffic = source bytes (x halo overlap, absorbed
+// by L2) + output floats.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace sivae {
+
+constexpr int IMG_PRECISION_BITS = 32 - 8 - 2;     // Resample.c PRECISION_BITS
+
+// Resample.c bicubic_filter (Keys, a = -0.5)
+static double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// Resample.c precompute_coeffs (box = the whole axis) + normalize_coeffs_8bpc.  bounds: [out][2] = (first source index,
+// tap count); kk: [out][ksize] fixed-point taps, unused tail zero.  Same operation order in IEEE doubles as Pillow.
+int resample_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk) {
+  const double scale = (double)in_size / out_size;
+  double filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  bounds.assign((size_t)out_size * 2, 0);
+  kk.assign((size_t)out_size * ksize, 0);
+  std::vector<double> w((size_t)ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = bicubic_filter((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      double k = w[x];
+      if (ww != 0.0) k /= ww;
+      kk[(size_t)xx * ksize + x] = k < 0 ? (int)(-0.5 + k * (1 << IMG_PRECISION_BITS)) : (int)(0.5 + k * (1 << IMG_PRECISION_BITS));
+    }
+    bounds[(size_t)xx * 2] = xmin;
+    bounds[(size_t)xx * 2 + 1] = xmax;
+  }
+  return ksize;
+}
+
+namespace {
+
+struct ImgArgs {
+  const unsigned char* src;      // [B][Hin][Win][CH] decoded pixels
+  const unsigned char* src_end;  // one past the last source byte
+  const unsigned char* mirror;   // [B] flags (nullable): 1 = ImageOps.mirror before the resize
+  float* dst;                    // [B][CH][Hout][Wout]
+  const int *bx, *kx, *by, *ky;  // device coefficient tables (plan)
+  int B, Hin, Win, Hout, Wout, ksx, ksy, TW, TH, pitch_in, max_rows;
+};
+
+__device__ __forceinline__ int clip8(int acc) {     // Resample.c clip8: saturating lookup of acc >> PRECISION_BITS
+  int v = acc >> IMG_PRECISION_BITS;
+  return min(max(v, 0), 255);
+}
+
+constexpr int IMG_RG = 4;        // source rows one thread carries through the horizontal pass (taps loaded once for all)
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_image_batch(ImgArgs a) {
+  extern __shared__ __align__(16) unsigned char img_smem[];
+  int* kx_s = reinterpret_cast<int*>(img_smem);          // [TW][ksx]
+  int* ky_s = kx_s + a.TW * a.ksx;                        // [TH][ksy]
+  int* bx_s = ky_s + a.TH * a.ksy;                        // [TW][2]
+  int* by_s = bx_s + 2 * a.TW;                            // [TH][2]
+  unsigned char* in_s = reinterpret_cast<unsigned char*>(by_s + 2 * a.TH);     // [max_rows][pitch_in] source window
+  unsigned char* mid_s = in_s + (size_t)a.max_rows * a.pitch_in;                // [max_rows][TW*CH] after the horizontal pass
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx0 = blockIdx.x * a.TW, ty0 = blockIdx.y * a.TH, b = blockIdx.z;
+  const int tw = min(a.TW, a.Wout - tx0), th = min(a.TH, a.Hout - ty0);
+  for (int i = tid; i < tw * a.ksx; i += 256) kx_s[i] = __ldg(a.kx + (size_t)tx0 * a.ksx + i);
+  for (int i = tid; i < th * a.ksy; i += 256) ky_s[i] = __ldg(a.ky + (size_t)ty0 * a.ksy + i);
+  for (int i = tid; i < 2 * tw; i += 256) bx_s[i] = __ldg(a.bx + 2 * tx0 + i);
+  for (int i = tid; i < 2 * th; i += 256) by_s[i] = __ldg(a.by + 2 * ty0 + i);
+  __syncthreads();
+  // source window of the tile (first index and first+count are both non-decreasing in the output coordinate)
+  const int x0 = bx_s[0], x1 = bx_s[2 * (tw - 1)] + bx_s[2 * (tw - 1) + 1];
+  const int y0 = by_s[0], y1 = by_s[2 * (th - 1)] + by_s[2 * (th - 1) + 1];
+  const int span = x1 - x0, R = y1 - y0;
+  const bool mir = a.mirror != nullptr && a.mirror[b] != 0;
+  const int sx0 = mir ? a.Win - x1 : x0;                  // mirrored window [x0,x1) = source [Win-x1, Win-x0) reversed
+  const unsigned char* img = a.src + (size_t)b * a.Hin * a.Win * CH;
+  const int nbytes = span * CH;
+
+  // ---- stage: one warp per source row, aligned 32-bit words (the row start is rounded down to a word) -------------
+  for (int r = warp; r < R; r += 8) {
+    const unsigned char* rp = img + ((size_t)(y0 + r) * a.Win + sx0) * CH;
+    const int g = (int)(reinterpret_cast<uintptr_t>(rp) & 3);
+    const unsigned char* ap = rp - g;
+    const int nwords = (g + nbytes + 3) >> 2;
+    unsigned* drow = reinterpret_cast<unsigned*>(in_s + (size_t)r * a.pitch_in);
+    for (int w = lane; w < nwords; w += 32) {
+      const unsigned char* wp = ap + 4 * w;
+      unsigned v;
+      if (wp + 4 <= a.src_end) {
+        v = __ldg(reinterpret_cast<const unsigned*>(wp));
+      } else {                                            // last word of the last image: never read past the tensor
+        v = 0;
+        for (int j = 0; j < 4; ++j)
+          if (wp + j < a.src_end) v |= (unsigned)wp[j] << (8 * j);
+      }
+      drow[w] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- horizontal pass (ImagingResampleHorizontal_8bpc): thread = (output column, group of IMG_RG source rows) -----
+  const int ngroups = (R + IMG_RG - 1) / IMG_RG;
+  const int mid_pitch = a.TW * CH;
+  for (int item = tid; item < tw * ngroups; item += 256) {
+    const int x = item % tw, rg = item / tw;
+    const int xmin = bx_s[2 * x], cnt = bx_s[2 * x + 1];
+    const int* kp = kx_s + x * a.ksx;
+    int acc[IMG_RG][CH];
+    const unsigned char* rowp[IMG_RG];
+#pragma unroll
+    for (int r = 0; r < IMG_RG; ++r) {
+      const int row = min(rg * IMG_RG + r, R - 1);        // rows past the window repeat the last one, result discarded
+      const unsigned char* rp = img + ((size_t)(y0 + row) * a.Win + sx0) * CH;
+      rowp[r] = in_s + (size_t)row * a.pitch_in + (int)(reinterpret_cast<uintptr_t>(rp) & 3);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[r][c] = 1 << (IMG_PRECISION_BITS - 1);
+    }
+    const int p = xmin - x0;                              // first tap, in window coordinates of the (mirrored) image
+    int off = (mir ? span - 1 - p : p) * CH;
+    const int step = mir ? -CH : CH;
+    for (int k = 0; k < cnt; ++k) {
+      const int coef = kp[k];
+#pragma unroll
+      for (int r = 0; r < IMG_RG; ++r)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[r][c] += (int)rowp[r][off + c] * coef;
+      off += step;
+    }
+#pragma unroll
+    for (int r = 0; r < IMG_RG; ++r) {
+      const int row = rg * IMG_RG + r;
+      if (row < R) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) mid_s[(size_t)row * mid_pitch + x * CH + c] = (unsigned char)clip8(acc[r][c]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- vertical pass (ImagingResampleVertical_8bpc) + ToTensor: thread = (row, channel, column), columns fastest ---
+  for (int item = tid; item < th * CH * tw; item += 256) {
+    const int x = item % tw;
+    const int t = item / tw;
+    const int c = t % CH, yy = t / CH;
+    const int ymin = by_s[2 * yy] - y0, cnt = by_s[2 * yy + 1];
+    const int* kp = ky_s + yy * a.ksy;
+    const unsigned char* mp = mid_s + (size_t)ymin * mid_pitch + x * CH + c;
+    int acc = 1 << (IMG_PRECISION_BITS - 1);
+    for (int k = 0; k < cnt; ++k) acc += (int)mp[(size_t)k * mid_pitch] * kp[k];
+    const int v = clip8(acc);
+    a.dst[(((size_t)b * CH + c) * a.Hout + ty0 + yy) * a.Wout + tx0 + x] = __fdiv_rn((float)v, 255.f);   // ToTensor: .div(255)
+  }
+}
+
+struct ImgPlan {
+  int ksx = 0, ksy = 0;
+  std::vector<int> bx, kx, by, ky;
+};
+struct TileCfg { int TW = 0, TH = 0, pitch_in = 0, max_rows = 0; size_t smem = 0; };
+
+std::mutex g_plan_mu;
+std::map<std::tuple<int, int, int, int>, ImgPlan> g_plans;
+
+const ImgPlan& get_plan(int in_h, int in_w, int out_h, int out_w) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  auto key = std::make_tuple(in_h, in_w, out_h, out_w);
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) return it->second;
+  ImgPlan p;
+  p.ksx = resample_coeffs(in_w, out_w, p.bx, p.kx);
+  p.ksy = resample_coeffs(in_h, out_h, p.by, p.ky);
+  return g_plans.emplace(key, std::move(p)).first->second;
+}
+
+// largest tile whose staging fits the shared-memory budget (two CTAs per SM)
+bool pick_tile(const ImgPlan& p, int out_h, int out_w, int ch, TileCfg* out) {
+  static const int cand[][2] = {{32, 16}, {32, 8}, {16, 8}, {16, 4}, {8, 4}, {8, 2}, {4, 2}, {4, 1}};
+  const size_t budget = 100 * 1024;
+  for (auto& c : cand) {
+    const int TW = c[0], TH = c[1];
+    int max_span = 0, max_rows = 0;
+    for (int x0 = 0; x0 < out_w; x0 += TW) {
+      const int xl = (x0 + TW < out_w ? x0 + TW : out_w) - 1;
+      const int s = p.bx[2 * xl] + p.bx[2 * xl + 1] - p.bx[2 * x0];
+      if (s > max_span) max_span = s;
+    }
+    for (int y0 = 0; y0 < out_h; y0 += TH) {
+      const int yl = (y0 + TH < out_h ? y0 + TH : out_h) - 1;
+      const int r = p.by[2 * yl] + p.by[2 * yl + 1] - p.by[2 * y0];
+      if (r > max_rows) max_rows = r;
+    }
+    const int pitch = ((max_span * ch + 3 + 3) / 4) * 4;
+    const size_t smem = sizeof(int) * ((size_t)TW * p.ksx + (size_t)TH * p.ksy + 2 * TW + 2 * TH) +
+                        (size_t)max_rows * pitch + (size_t)max_rows * TW * ch;
+    if (smem <= budget) {
+      out->TW = TW; out->TH = TH; out->pitch_in = pitch; out->max_rows = max_rows; out->smem = smem;
+      return true;
+    }
+  }
+  return false;
+}
+
+}  // namespace
+
+size_t image_plan_bytes(int in_h, int in_w, int out_h, int out_w) {
+  const ImgPlan& p = get_plan(in_h, in_w, out_h, out_w);
+  return sizeof(int) * (p.bx.size() + p.kx.size() + p.by.size() + p.ky.size());
+}
+
+int image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, cudaStream_t st) {
+  const ImgPlan& p = get_plan(in_h, in_w, out_h, out_w);          // lives in the process-wide cache: stable source for the async copies
+  int* d = static_cast<int*>(plan_dev);
+  cudaMemcpyAsync(d, p.bx.data(), sizeof(int) * p.bx.size(), cudaMemcpyHostToDevice, st); d += p.bx.size();
+  cudaMemcpyAsync(d, p.kx.data(), sizeof(int) * p.kx.size(), cudaMemcpyHostToDevice, st); d += p.kx.size();
+  cudaMemcpyAsync(d, p.by.data(), sizeof(int) * p.by.size(), cudaMemcpyHostToDevice, st); d += p.by.size();
+  cudaMemcpyAsync(d, p.ky.data(), sizeof(int) * p.ky.size(), cudaMemcpyHostToDevice, st);
+  return (int)cudaGetLastError();
+}
+
+// returns 0, a cudaError_t (> 0), -2 (bad argument) or -7 (down-scaling factor too large for the shared-memory staging)
+int launch_image_batch(const unsigned char* src, const unsigned char* mirror, int B, int in_h, int in_w, int ch, int out_h,
+                       int out_w, const void* plan_dev, float* dst, cudaStream_t st) {
+  if (B < 1 || in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1 || (ch != 1 && ch != 3)) return -2;
+  if (B > 65535 || (reinterpret_cast<uintptr_t>(src) & 3) != 0) return -2;
+  const ImgPlan& p = get_plan(in_h, in_w, out_h, out_w);
+  TileCfg t;
+  if (!pick_tile(p, out_h, out_w, ch, &t)) return -7;
+  ImgArgs a;
+  a.src = src; a.src_end = src + (size_t)B * in_h * in_w * ch; a.mirror = mirror; a.dst = dst;
+  const int* d = static_cast<const int*>(plan_dev);
+  a.bx = d; d += p.bx.size();
+  a.kx = d; d += p.kx.size();
+  a.by = d; d += p.by.size();
+  a.ky = d;
+  a.B = B; a.Hin = in_h; a.Win = in_w; a.Hout = out_h; a.Wout = out_w; a.ksx = p.ksx; a.ksy = p.ksy;
+  a.TW = t.TW; a.TH = t.TH; a.pitch_in = t.pitch_in; a.max_rows = t.max_rows;
+  dim3 grid((out_w + t.TW - 1) / t.TW, (out_h + t.TH - 1) / t.TH, B);
+  g_launches += 1;
+  if (ch == 3) {
+    static size_t attr3 = 0;
+    if (t.smem > 48 * 1024 && t.smem > attr3) {
+      cudaFuncSetAttribute(k_image_batch<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+      attr3 = t.smem;
+    }
+    k_image_batch<3><<<grid, 256, t.smem, st>>>(a);
+  } else {
+    static size_t attr1 = 0;
+    if (t.smem > 48 * 1024 && t.smem > attr1) {
+      cudaFuncSetAttribute(k_image_batch<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem);
+      attr1 = t.smem;
+    }
+    k_image_batch<1><<<grid, 256, t.smem, st>>>(a);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace sivae

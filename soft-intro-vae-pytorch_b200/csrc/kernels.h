@@ -162,4 +162,14 @@ void launch_loss_seed(const float* real, const float* rec, const float* rec_rec,
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
                  float b1, float b2, float eps, long long* step_dev, float* coef_dev, cudaStream_t st);
 
+// ---------------- image batch assembly (image.cu): mirror + Pillow-exact bicubic resize + ToTensor ----------------
+}  // namespace sivae
+#include <vector>
+namespace sivae {
+int resample_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk);   // returns ksize
+size_t image_plan_bytes(int in_h, int in_w, int out_h, int out_w);
+int image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, cudaStream_t st);
+int launch_image_batch(const unsigned char* src, const unsigned char* mirror, int B, int in_h, int in_w, int ch, int out_h,
+                       int out_w, const void* plan_dev, float* dst, cudaStream_t st);
+
 }  // namespace sivae

@@ -422,8 +422,11 @@ def _build_dataset(dataset):
         size, channels, root, n_train = files[dataset]
         names = [f for f in os.listdir(root) if is_image_file(f)][:n_train]
         assert len(names) > 0
-        ds = _reference_dataset_module().ImageDatasetFromFile(names, root, input_height=None, crop_height=None,
-                                                              output_height=size, is_mirror=True)
+        # decode on the host, mirror + bicubic resize + ToTensor per batch on the GPU (gpu_dataset.py; bit-exact with the
+        # reference's loader).  SIVAE_GPU_LOADER=0: the reference's own dataset.py (PIL on the DataLoader workers).
+        mod = _reference_dataset_module() if os.environ.get("SIVAE_GPU_LOADER", "1") == "0" else \
+            importlib.import_module(_PKG + ".gpu_dataset")
+        ds = mod.ImageDatasetFromFile(names, root, input_height=None, crop_height=None, output_height=size, is_mirror=True)
         return ds, size, channels, 3, False
     if dataset == "monsters128":
         ds = _reference_dataset_module().DigitalMonstersDataset(root_path='./monsters_ds/', output_height=128)
@@ -601,8 +604,13 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
     sampler = None
     if dist:
         sampler = torch.utils.data.distributed.DistributedSampler(train_set, shuffle=True)
+    gpu_ds = importlib.import_module(_PKG + ".gpu_dataset")
+    on_gpu = isinstance(train_set, gpu_ds.ImageDatasetFromFile)
     loader = torch.utils.data.DataLoader(train_set, batch_size=batch_size, shuffle=sampler is None, sampler=sampler,
-                                         num_workers=num_workers, pin_memory=True)
+                                         num_workers=num_workers, pin_memory=True,
+                                         collate_fn=gpu_ds.collate_decoded if on_gpu else None)
+    if on_gpu:
+        loader = gpu_ds.GpuImageLoader(loader, device)      # yields the float32 [B,C,S,S] batches the reference's loader yields
     from tqdm import tqdm
     start_time = time.time()
     cur_iter = 0

@@ -1,0 +1,110 @@
+"""-m gpu: the image batch-assembly kernel (csrc/image.cu) through the C ABI against the oracle (oracle/image_oracle.py,
+pinned to Pillow and to the reference's dataset.py in tests/test_image_oracle.py).  Integer / correctly-rounded work:
+the bar is bit-exact."""
+import importlib
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import image_oracle as IO
+
+pytestmark = pytest.mark.gpu
+PKG = "soft-intro-vae-pytorch_b200"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "image_pipeline.npz")
+
+
+def _mod():
+    return importlib.import_module(PKG + ".gpu_dataset")
+
+
+def test_golden_vectors_of_the_reference_loader():
+    z = np.load(GOLD)
+    for name in sorted({k.split("/")[0] for k in z.files}):
+        src, mirror, out_u8, size = z[name + "/src"], z[name + "/mirror"], z[name + "/out_u8"], int(z[name + "/size"][0])
+        got = _mod().ImageBatcher(size, size, "cuda:0")(torch.from_numpy(src), torch.from_numpy(mirror)).cpu().numpy()
+        assert np.array_equal(got, out_u8.astype(np.float32) / np.float32(255.0)), name
+
+
+@pytest.mark.parametrize("shape", [((218, 178), (128, 128)), ((64, 64), (32, 32)), ((100, 37), (13, 91)), ((33, 47), (47, 33)),
+                                   ((40, 40), (40, 17)), ((17, 29), (64, 128)), ((300, 200), (9, 7)), ((5, 5), (64, 64)),
+                                   ((1, 7), (4, 4)), ((31, 31), (31, 31)), ((257, 131), (96, 200))])
+@pytest.mark.parametrize("ch", [3, 1])
+def test_matches_oracle(shape, ch):
+    """up- and down-scaling, identity axes, ragged tiles, rows whose byte length is not a multiple of 4 (unaligned row
+    starts in the word staging), mixed mirror flags, saturating content"""
+    (h, w), (oh, ow) = shape
+    B = 5
+    rng = np.random.default_rng(h * 131 + w * 7 + ch)
+    src = rng.integers(0, 256, (B, h, w, ch), dtype=np.uint8)
+    src[:, : h // 2, : w // 2] = 255
+    src[:, h // 2:, w // 2:] = 0
+    mirror = np.array([0, 1, 1, 0, 1], dtype=np.uint8)
+    got = _mod().ImageBatcher(oh, ow, "cuda:0")(torch.from_numpy(src), torch.from_numpy(mirror)).cpu().numpy()
+    want = IO.batch(src, mirror, oh, ow)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # no mirror array at all == all zeros
+    got0 = _mod().ImageBatcher(oh, ow, "cuda:0")(torch.from_numpy(src), None).cpu().numpy()
+    assert np.array_equal(got0, IO.batch(src, np.zeros(B, np.uint8), oh, ow))
+
+
+def test_full_size_properties():
+    """BASELINE sizes (1024x1024 -> 256x256, batch 32): two images against the oracle, the rest through size-independent
+    properties: mirror flag == mirrored source, constant images stay constant, identity geometry == source / 255."""
+    rng = np.random.default_rng(3)
+    B, S, T = 32, 1024, 256
+    src = rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8)
+    src[5] = 255
+    src[6] = 0
+    src[7] = 77
+    mirror = (np.arange(B) % 2).astype(np.uint8)
+    bt = _mod().ImageBatcher(T, T, "cuda:0")
+    got = bt(torch.from_numpy(src), torch.from_numpy(mirror)).cpu().numpy()
+    for i in (0, 1):
+        assert np.array_equal(got[i], IO.load_image_tensor(src[i], T, T, bool(mirror[i])))
+    flipped = np.ascontiguousarray(src[:, :, ::-1])
+    got_f = bt(torch.from_numpy(flipped), torch.from_numpy(1 - mirror)).cpu().numpy()
+    assert np.array_equal(got, got_f)
+    assert (got[5] == 1.0).all() and (got[6] == 0.0).all() and (got[7] == np.float32(77) / np.float32(255)).all()
+    ident = _mod().ImageBatcher(S, S, "cuda:0")(torch.from_numpy(src[:2]), None).cpu().numpy()
+    assert np.array_equal(ident, (src[:2].astype(np.float32) / np.float32(255)).transpose(0, 3, 1, 2))
+
+
+def test_downscale_beyond_staging_capacity_fails_loudly():
+    src = torch.zeros(1, 4096, 8, 3, dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="down-scaling factor too large"):
+        _mod().ImageBatcher(2, 8, "cuda:0")(src, None)
+    with pytest.raises(RuntimeError):
+        _mod().ImageBatcher(8, 8, "cuda:0")(torch.zeros(1, 8, 8, 2, dtype=torch.uint8), None)      # 2 channels
+
+
+def test_loader_end_to_end(tmp_path):
+    """files -> ImageDatasetFromFile (decode + the reference's mirror coin) -> DataLoader -> GpuImageLoader == the tensors
+    the reference's dataset returns for the same seed (golden), including a batch with two source geometries"""
+    from PIL import Image
+    M = _mod()
+    z = np.load(GOLD)
+    src, mirror, out_u8 = z["celeba_like/src"], z["celeba_like/mirror"], z["celeba_like/out_u8"]
+    size = int(z["celeba_like/size"][0])
+    names = []
+    for i, a in enumerate(src):
+        names.append("img_%d.png" % i)
+        Image.fromarray(a, "RGB").save(tmp_path / names[-1])
+    ds = M.ImageDatasetFromFile(names, str(tmp_path), input_height=None, crop_height=None, output_height=size, is_mirror=True)
+    loader = M.GpuImageLoader(torch.utils.data.DataLoader(ds, batch_size=len(names), shuffle=False, num_workers=0,
+                                                          collate_fn=M.collate_decoded), "cuda:0")
+    random.seed(1234)                                   # the seed the golden was recorded with (oracle/make_image_golden.py)
+    batches = list(loader)
+    assert len(batches) == 1 and batches[0].is_cuda
+    assert np.array_equal(batches[0].cpu().numpy(), out_u8.astype(np.float32) / np.float32(255.0))
+    # mixed geometries in one batch
+    odd = np.ascontiguousarray(src[0][:50, :41])
+    Image.fromarray(odd, "RGB").save(tmp_path / "odd.png")
+    ds2 = M.ImageDatasetFromFile(["img_0.png", "odd.png", "img_1.png"], str(tmp_path), input_height=None, crop_height=None,
+                                 output_height=size, is_mirror=False)
+    (b2,) = list(M.GpuImageLoader(torch.utils.data.DataLoader(ds2, batch_size=3, collate_fn=M.collate_decoded), "cuda:0"))
+    want = np.stack([IO.load_image_tensor(a, size, size, False) for a in (src[0], odd, src[1])])
+    assert np.array_equal(b2.cpu().numpy(), want)
