@@ -174,6 +174,13 @@ int sivae_mse3(const float* real, const float* rec, const float* rec_rec, const 
 int sivae_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int batch, int zdim, void* stream);
 int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
                     long long step, void* stream);
+/* nn.Linear (encoder fc :109,:121; decoder fc + ReLU :145-148,:166-167): y[B,O] = x[B,F] . w[O,F]^T + b (relu != 0: then
+   ReLU), and its input gradient dx[B,F] = dy[B,O] . w[O,F] (workspace: sivae_linear_dgrad_workspace_bytes) */
+int sivae_linear_fwd(const float* x, const float* w, const float* b, float* y, int batch, int in_features, int out_features,
+                     int relu, void* stream);
+int sivae_linear_dgrad(const float* dy, const float* w, float* dx, int batch, int in_features, int out_features,
+                       void* workspace, long long ws_bytes, void* stream);
+long long sivae_linear_dgrad_workspace_bytes(int batch, int in_features, int out_features);
 
 
 /* ---- image batch assembly: the loader that feeds the step -------------------------------------

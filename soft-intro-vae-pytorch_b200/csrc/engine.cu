@@ -1304,6 +1304,23 @@ extern "C" int sivae_adam_flat(float* p, const float* g, float* m, float* v, lon
   return 0;
 }
 
+// nn.Linear forward / input gradient as stand-alone calls (unit parity of the fc kernels)
+extern "C" int sivae_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, int relu, void* stream) {
+  if (!x || !w || !y || B < 1 || F < 1 || O < 1) return fail(-1, "bad argument");
+  launch_linear_fwd(x, w, b, y, B, F, O, relu != 0, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" int sivae_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, void* workspace, long long ws_bytes,
+                                  void* stream) {
+  if (!dy || !w || !dx || !workspace || B < 1 || F < 1 || O < 1) return fail(-1, "bad argument");
+  if ((size_t)ws_bytes < linear_dgrad_scratch_bytes(B, F, O)) return fail(-3, "workspace too small");
+  launch_linear_dgrad(dy, w, dx, B, F, O, workspace, (cudaStream_t)stream);
+  CHECK_CUDA_RET();
+  return 0;
+}
+extern "C" long long sivae_linear_dgrad_workspace_bytes(int B, int F, int O) { return (long long)linear_dgrad_scratch_bytes(B, F, O); }
+
 // ---- image batch assembly (image.cu) -----------------------------------------------------------------------------
 extern "C" int sivae_resample_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk, long long kk_capacity) {
   if (in_size < 1 || out_size < 1 || !ksize || !bounds || !kk) return fail(-1, "bad argument");

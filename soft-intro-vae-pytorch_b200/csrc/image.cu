@@ -89,21 +89,29 @@ __device__ __forceinline__ int clip8(int acc) {     // Resample.c clip8: saturat
 
 constexpr int IMG_RG = 4;        // source rows one thread carries through the horizontal pass (taps loaded once for all)
 
-template <int CH>
-__global__ void __launch_bounds__(256) k_image_batch(ImgArgs a) {
-  extern __shared__ __align__(16) unsigned char img_smem[];
-  int* kx_s = reinterpret_cast<int*>(img_smem);          // [TW][ksx]
-  int* ky_s = kx_s + a.TW * a.ksx;                        // [TH][ksy]
-  int* bx_s = ky_s + a.TH * a.ksy;                        // [TW][2]
+// MIR: the tile's image is mirrored (block-uniform; ImageOps.mirror folded into the horizontal pass' tap direction)
+template <int CH, bool MIR>
+__device__ __forceinline__ void image_tile(const ImgArgs& a, unsigned char* img_smem) {
+  // tables: taps padded to a multiple of 4 per output (zero-filled) so the tap loops run in unrolled groups of 4
+  const int ksx4 = (a.ksx + 3) & ~3, ksy4 = (a.ksy + 3) & ~3;
+  int* kx_s = reinterpret_cast<int*>(img_smem);          // [TW][ksx4]
+  int* ky_s = kx_s + a.TW * ksx4;                         // [TH][ksy4]
+  int* bx_s = ky_s + a.TH * ksy4;                         // [TW][2]
   int* by_s = bx_s + 2 * a.TW;                            // [TH][2]
-  unsigned char* in_s = reinterpret_cast<unsigned char*>(by_s + 2 * a.TH);     // [max_rows][pitch_in] source window
-  unsigned char* mid_s = in_s + (size_t)a.max_rows * a.pitch_in;                // [max_rows][TW*CH] after the horizontal pass
-
+  unsigned char* in_s = reinterpret_cast<unsigned char*>(by_s + 2 * a.TH) + 16;   // [max_rows][pitch_in] source window (+16 B slack either side:
+  unsigned char* mid_s = in_s + (size_t)a.max_rows * a.pitch_in + 16;              //  zero-weight padded taps may read just outside a row)
+                                                                                   // [max_rows + 3][TW*CH] after the horizontal pass
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = blockIdx.x * a.TW, ty0 = blockIdx.y * a.TH, b = blockIdx.z;
   const int tw = min(a.TW, a.Wout - tx0), th = min(a.TH, a.Hout - ty0);
-  for (int i = tid; i < tw * a.ksx; i += 256) kx_s[i] = __ldg(a.kx + (size_t)tx0 * a.ksx + i);
-  for (int i = tid; i < th * a.ksy; i += 256) ky_s[i] = __ldg(a.ky + (size_t)ty0 * a.ksy + i);
+  for (int i = tid; i < tw * ksx4; i += 256) {
+    const int x = i / ksx4, k = i - x * ksx4;
+    kx_s[i] = k < a.ksx ? __ldg(a.kx + (size_t)(tx0 + x) * a.ksx + k) : 0;
+  }
+  for (int i = tid; i < th * ksy4; i += 256) {
+    const int y = i / ksy4, k = i - y * ksy4;
+    ky_s[i] = k < a.ksy ? __ldg(a.ky + (size_t)(ty0 + y) * a.ksy + k) : 0;
+  }
   for (int i = tid; i < 2 * tw; i += 256) bx_s[i] = __ldg(a.bx + 2 * tx0 + i);
   for (int i = tid; i < 2 * th; i += 256) by_s[i] = __ldg(a.by + 2 * ty0 + i);
   __syncthreads();
@@ -111,85 +119,108 @@ __global__ void __launch_bounds__(256) k_image_batch(ImgArgs a) {
   const int x0 = bx_s[0], x1 = bx_s[2 * (tw - 1)] + bx_s[2 * (tw - 1) + 1];
   const int y0 = by_s[0], y1 = by_s[2 * (th - 1)] + by_s[2 * (th - 1) + 1];
   const int span = x1 - x0, R = y1 - y0;
-  const bool mir = a.mirror != nullptr && a.mirror[b] != 0;
-  const int sx0 = mir ? a.Win - x1 : x0;                  // mirrored window [x0,x1) = source [Win-x1, Win-x0) reversed
+  const int sx0 = MIR ? a.Win - x1 : x0;                  // mirrored window [x0,x1) = source [Win-x1, Win-x0) reversed
   const unsigned char* img = a.src + (size_t)b * a.Hin * a.Win * CH;
   const int nbytes = span * CH;
+  const unsigned char* win = img + ((size_t)y0 * a.Win + sx0) * CH;               // first byte of the window's first row
+  const int g0 = (int)(reinterpret_cast<uintptr_t>(win) & 3);                      // its misalignment; row r: (g0 + r*rowb) & 3
+  const int rowb = a.Win * CH;
 
-  // ---- stage: one warp per source row, aligned 32-bit words (the row start is rounded down to a word) -------------
+  // ---- stage: one warp per source row, aligned 32-bit words (the row start is rounded down to a word), asynchronous
+  //      global->shared copies (LDGSTS): every row of the window is in flight at once, no register round trip --------------
   for (int r = warp; r < R; r += 8) {
-    const unsigned char* rp = img + ((size_t)(y0 + r) * a.Win + sx0) * CH;
-    const int g = (int)(reinterpret_cast<uintptr_t>(rp) & 3);
-    const unsigned char* ap = rp - g;
+    const int g = (g0 + r * (rowb & 3)) & 3;
+    const unsigned char* ap = win + (size_t)r * rowb - g;
     const int nwords = (g + nbytes + 3) >> 2;
-    unsigned* drow = reinterpret_cast<unsigned*>(in_s + (size_t)r * a.pitch_in);
-    for (int w = lane; w < nwords; w += 32) {
-      const unsigned char* wp = ap + 4 * w;
-      unsigned v;
-      if (wp + 4 <= a.src_end) {
-        v = __ldg(reinterpret_cast<const unsigned*>(wp));
-      } else {                                            // last word of the last image: never read past the tensor
-        v = 0;
+    unsigned char* drow = in_s + (size_t)r * a.pitch_in;
+    if (ap + 4 * (size_t)nwords <= a.src_end) {
+      const unsigned dsh = (unsigned)__cvta_generic_to_shared(drow);
+      for (int w = lane; w < nwords; w += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsh + 4u * (unsigned)w), "l"(ap + 4 * (size_t)w) : "memory");
+    } else {                                              // last row of the last image: never read past the tensor
+      for (int w = lane; w < nwords; w += 32) {
+        unsigned v = 0;
         for (int j = 0; j < 4; ++j)
-          if (wp + j < a.src_end) v |= (unsigned)wp[j] << (8 * j);
+          if (ap + 4 * w + j < a.src_end) v |= (unsigned)ap[4 * w + j] << (8 * j);
+        reinterpret_cast<unsigned*>(drow)[w] = v;
       }
-      drow[w] = v;
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  // ---- horizontal pass (ImagingResampleHorizontal_8bpc): thread = (output column, group of IMG_RG source rows) -----
+  // ---- horizontal pass (ImagingResampleHorizontal_8bpc): lane = output column, warp = groups of IMG_RG source rows ----
   const int ngroups = (R + IMG_RG - 1) / IMG_RG;
   const int mid_pitch = a.TW * CH;
-  for (int item = tid; item < tw * ngroups; item += 256) {
-    const int x = item % tw, rg = item / tw;
-    const int xmin = bx_s[2 * x], cnt = bx_s[2 * x + 1];
-    const int* kp = kx_s + x * a.ksx;
-    int acc[IMG_RG][CH];
-    const unsigned char* rowp[IMG_RG];
-#pragma unroll
-    for (int r = 0; r < IMG_RG; ++r) {
-      const int row = min(rg * IMG_RG + r, R - 1);        // rows past the window repeat the last one, result discarded
-      const unsigned char* rp = img + ((size_t)(y0 + row) * a.Win + sx0) * CH;
-      rowp[r] = in_s + (size_t)row * a.pitch_in + (int)(reinterpret_cast<uintptr_t>(rp) & 3);
-#pragma unroll
-      for (int c = 0; c < CH; ++c) acc[r][c] = 1 << (IMG_PRECISION_BITS - 1);
-    }
+  for (int x = lane; x < tw; x += 32) {
+    const int xmin = bx_s[2 * x], ngrp4 = (bx_s[2 * x + 1] + 3) >> 2;
+    const int* kp = kx_s + x * ksx4;
     const int p = xmin - x0;                              // first tap, in window coordinates of the (mirrored) image
-    int off = (mir ? span - 1 - p : p) * CH;
-    const int step = mir ? -CH : CH;
-    for (int k = 0; k < cnt; ++k) {
-      const int coef = kp[k];
+    const int off0 = (MIR ? span - 1 - p : p) * CH;
+    for (int rg = warp; rg < ngroups; rg += 8) {
+      int acc[IMG_RG][CH];
+      const unsigned char* rowp[IMG_RG];
 #pragma unroll
-      for (int r = 0; r < IMG_RG; ++r)
+      for (int r = 0; r < IMG_RG; ++r) {
+        const int row = min(rg * IMG_RG + r, R - 1);      // rows past the window repeat the last one, result discarded
+        rowp[r] = in_s + row * a.pitch_in + ((g0 + row * (rowb & 3)) & 3) + off0;
 #pragma unroll
-        for (int c = 0; c < CH; ++c) acc[r][c] += (int)rowp[r][off + c] * coef;
-      off += step;
-    }
+        for (int c = 0; c < CH; ++c) acc[r][c] = 1 << (IMG_PRECISION_BITS - 1);
+      }
+      for (int k4 = 0; k4 < ngrp4; ++k4) {
+        const int4 cf = *reinterpret_cast<const int4*>(kp + 4 * k4);
+        const int coef[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
-    for (int r = 0; r < IMG_RG; ++r) {
-      const int row = rg * IMG_RG + r;
-      if (row < R) {
+        for (int r = 0; r < IMG_RG; ++r) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) mid_s[(size_t)row * mid_pitch + x * CH + c] = (unsigned char)clip8(acc[r][c]);
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[r][c] += (int)rowp[r][(MIR ? -k : k) * CH + c] * coef[k];
+          rowp[r] += MIR ? -4 * CH : 4 * CH;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < IMG_RG; ++r) {
+        const int row = rg * IMG_RG + r;
+        if (row < R) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) mid_s[row * mid_pitch + x * CH + c] = (unsigned char)clip8(acc[r][c]);
+        }
       }
     }
   }
   __syncthreads();
 
-  // ---- vertical pass (ImagingResampleVertical_8bpc) + ToTensor: thread = (row, channel, column), columns fastest ---
-  for (int item = tid; item < th * CH * tw; item += 256) {
-    const int x = item % tw;
-    const int t = item / tw;
-    const int c = t % CH, yy = t / CH;
-    const int ymin = by_s[2 * yy] - y0, cnt = by_s[2 * yy + 1];
-    const int* kp = ky_s + yy * a.ksy;
-    const unsigned char* mp = mid_s + (size_t)ymin * mid_pitch + x * CH + c;
-    int acc = 1 << (IMG_PRECISION_BITS - 1);
-    for (int k = 0; k < cnt; ++k) acc += (int)mp[(size_t)k * mid_pitch] * kp[k];
-    const int v = clip8(acc);
-    a.dst[(((size_t)b * CH + c) * a.Hout + ty0 + yy) * a.Wout + tx0 + x] = __fdiv_rn((float)v, 255.f);   // ToTensor: .div(255)
+  // ---- vertical pass (ImagingResampleVertical_8bpc) + ToTensor: lane = output column, warp = output rows ----------
+  for (int x = lane; x < tw; x += 32) {
+    for (int yy = warp; yy < th; yy += 8) {
+      const int ymin = by_s[2 * yy] - y0, ngrp4 = (by_s[2 * yy + 1] + 3) >> 2;
+      const int* kp = ky_s + yy * ksy4;
+      const unsigned char* mp = mid_s + ymin * mid_pitch + x * CH;
+      int acc[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 1 << (IMG_PRECISION_BITS - 1);
+      for (int k4 = 0; k4 < ngrp4; ++k4) {
+        const int4 cf = *reinterpret_cast<const int4*>(kp + 4 * k4);
+        const int coef[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int c = 0; c < CH; ++c) acc[c] += (int)mp[k * mid_pitch + c] * coef[k];
+        mp += 4 * mid_pitch;
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        a.dst[(((size_t)b * CH + c) * a.Hout + ty0 + yy) * a.Wout + tx0 + x] = __fdiv_rn((float)clip8(acc[c]), 255.f);   // ToTensor: .div(255)
+    }
   }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_image_batch(ImgArgs a) {
+  extern __shared__ __align__(16) unsigned char img_smem[];
+  if (a.mirror != nullptr && a.mirror[blockIdx.z] != 0) image_tile<CH, true>(a, img_smem);
+  else image_tile<CH, false>(a, img_smem);
 }
 
 struct ImgPlan {
@@ -230,8 +261,9 @@ bool pick_tile(const ImgPlan& p, int out_h, int out_w, int ch, TileCfg* out) {
       if (r > max_rows) max_rows = r;
     }
     const int pitch = ((max_span * ch + 3 + 3) / 4) * 4;
-    const size_t smem = sizeof(int) * ((size_t)TW * p.ksx + (size_t)TH * p.ksy + 2 * TW + 2 * TH) +
-                        (size_t)max_rows * pitch + (size_t)max_rows * TW * ch;
+    const int ksx4 = (p.ksx + 3) & ~3, ksy4 = (p.ksy + 3) & ~3;
+    const size_t smem = sizeof(int) * ((size_t)TW * ksx4 + (size_t)TH * ksy4 + 2 * TW + 2 * TH) + 16 +
+                        (size_t)max_rows * pitch + 16 + (size_t)(max_rows + 3) * TW * ch;
     if (smem <= budget) {
       out->TW = TW; out->TH = TH; out->pitch_in = pitch; out->max_rows = max_rows; out->smem = smem;
       return true;

@@ -3,6 +3,7 @@
 // convolution used for the 3-channel stem / predict layers and as the on-device cross-check of the tcgen05 path.
 // Reference semantics: soft_intro_vae/train_soft_intro_vae.py (lines cited per kernel).
 #include "kernels.h"
+#include <cstdint>
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -860,23 +861,118 @@ __global__ void __launch_bounds__(256) k_linear_fwd(const float* __restrict__ x,
     }
   }
 }
+// y[b][o] = x[b][:] . w[o][:] for 8 outputs x 32 batch rows per block: warp w owns batch rows 4w..4w+3 against all 8 weight
+// rows (the 8 warps read the same weight lines: one trip to L2, the rest L1 hits), lanes stride the reduction dimension
+// with 128-bit loads.  The 32 per-lane partials are reduced with a transposing butterfly (31 shuffles instead of 160;
+// lane l ends up owning sum l), fixed order -> deterministic.
+constexpr int LF2_OT = 8, LF2_BT = 32;
+__global__ void __launch_bounds__(256) k_linear_fwd_v2(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ y, int B, int F,
+                                                       int O, int relu) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int o0 = blockIdx.x * LF2_OT, b0 = blockIdx.y * LF2_BT + wid * 4;
+  float acc[LF2_OT * 4];
+#pragma unroll
+  for (int i = 0; i < LF2_OT * 4; ++i) acc[i] = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int f = lane * 4; f < F; f += 128) {
+    float4 xv[4], wv[LF2_OT];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xv[j] = (b0 + j < B) ? __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + j) * F + f)) : z4;
+#pragma unroll
+    for (int i = 0; i < LF2_OT; ++i) wv[i] = (o0 + i < O) ? __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + i) * F + f)) : z4;
+#pragma unroll
+    for (int i = 0; i < LF2_OT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[i * 4 + j];
+        a = fmaf(wv[i].x, xv[j].x, a); a = fmaf(wv[i].y, xv[j].y, a);
+        a = fmaf(wv[i].z, xv[j].z, a); a = fmaf(wv[i].w, xv[j].w, a);
+        acc[i * 4 + j] = a;
+      }
+  }
+  // transposing butterfly: after the step with mask m, a lane with bit m set carries the upper half of the index range
+#pragma unroll
+  for (int m = 16, n = 32; m > 0; m >>= 1, n >>= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = up ? acc[i + n / 2] : acc[i];
+      const float send = up ? acc[i] : acc[i + n / 2];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  const int i = lane >> 2, j = lane & 3;           // lane l owns (output l/4, batch row l%4)
+  if (o0 + i < O && b0 + j < B) {
+    float v = acc[0];
+    if (b) v += b[o0 + i];
+    if (relu) v = fmaxf(v, 0.f);
+    y[(long long)(b0 + j) * O + o0 + i] = v;
+  }
+}
 void launch_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, bool relu, cudaStream_t st) {
   g_launches += 1;
+  // long reductions (encoder fc, F = 8192) stay on the many-small-blocks kernel: with 8 weight rows per block the v2 kernel
+  // has only 4 KB of unique weight bytes in flight per SM per iteration and is latency-bound there (85 vs 68 us, cold L2);
+  // short ones (decoder fc, F = z) are reduction-overhead-bound on the old kernel (31 us on v2)
+  if (F <= 2048 && (F & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    dim3 grid(cdiv(O, LF2_OT), cdiv(B, LF2_BT));
+    k_linear_fwd_v2<<<grid, 256, 0, st>>>(x, w, b, y, B, F, O, relu ? 1 : 0);
+    return;
+  }
   dim3 grid(cdiv(O, LF_OT), cdiv(B, LF_BT));
   k_linear_fwd<<<grid, 256, 0, st>>>(x, w, b, y, B, F, O, relu ? 1 : 0);
 }
-constexpr int LD_BT = 8, LD_OC = 512;
-// dx[B][F] = dy[B][O] . w[O][F]; O is split over blockIdx.z in chunks of LD_OC (partials in scratch, reduced in fixed order)
+constexpr int LD_BT = 16, LD_OC = 128;
+// dx[B][F] = dy[B][O] . w[O][F]; a thread owns 4 consecutive columns f (128-bit, coalesced weight loads) for 16 batch rows;
+// O is split over blockIdx.z in chunks of LD_OC (partials in scratch, reduced in fixed order -> deterministic)
 __global__ void __launch_bounds__(256) k_linear_dgrad(const float* __restrict__ dy, const float* __restrict__ w,
                                                       float* __restrict__ part, int B, int F, int O) {
-  __shared__ float sdy[LD_BT][LD_OC];
+  __shared__ __align__(16) float sdy[LD_OC][LD_BT];   // [o][b]: the 16 batch values of one o are 4 x 128-bit broadcast reads
+  const int b0 = blockIdx.y * LD_BT;
+  const int f = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int o0 = blockIdx.z * LD_OC;
+  const int oc = min(LD_OC, O - o0);
+  for (int i = threadIdx.x; i < LD_BT * oc; i += 256) {
+    int j = i / oc, o = i - j * oc;
+    sdy[o][j] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o0 + o] : 0.f;
+  }
+  __syncthreads();
+  if (f >= F) return;
+  float4 acc[LD_BT];
+#pragma unroll
+  for (int j = 0; j < LD_BT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* wp = w + (long long)o0 * F + f;
+#pragma unroll 2
+  for (int o = 0; o < oc; ++o) {
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(wp + (long long)o * F));
+#pragma unroll
+    for (int j4 = 0; j4 < LD_BT / 4; ++j4) {
+      const float4 d = *reinterpret_cast<const float4*>(&sdy[o][j4 * 4]);
+      const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4& a = acc[j4 * 4 + q];
+        a.x = fmaf(dv[q], wv.x, a.x); a.y = fmaf(dv[q], wv.y, a.y); a.z = fmaf(dv[q], wv.z, a.z); a.w = fmaf(dv[q], wv.w, a.w);
+      }
+    }
+  }
+  float* dst = part + (long long)blockIdx.z * B * F;
+#pragma unroll
+  for (int j = 0; j < LD_BT; ++j)
+    if (b0 + j < B) *reinterpret_cast<float4*>(dst + (long long)(b0 + j) * F + f) = acc[j];
+}
+// generic fallback (F not a multiple of 4): one column per thread
+__global__ void __launch_bounds__(256) k_linear_dgrad_scalar(const float* __restrict__ dy, const float* __restrict__ w,
+                                                             float* __restrict__ part, int B, int F, int O) {
+  __shared__ float sdy[LD_OC][LD_BT];
   const int b0 = blockIdx.y * LD_BT;
   const int f = blockIdx.x * 256 + threadIdx.x;
   const int o0 = blockIdx.z * LD_OC;
   const int oc = min(LD_OC, O - o0);
   for (int i = threadIdx.x; i < LD_BT * oc; i += 256) {
     int j = i / oc, o = i - j * oc;
-    sdy[j][o] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o0 + o] : 0.f;
+    sdy[o][j] = (b0 + j < B) ? dy[(long long)(b0 + j) * O + o0 + o] : 0.f;
   }
   __syncthreads();
   if (f >= F) return;
@@ -886,7 +982,7 @@ __global__ void __launch_bounds__(256) k_linear_dgrad(const float* __restrict__ 
   for (int o = 0; o < oc; ++o) {
     float wv = __ldg(w + (long long)(o0 + o) * F + f);
 #pragma unroll
-    for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[j][o], wv, acc[j]);
+    for (int j = 0; j < LD_BT; ++j) acc[j] = fmaf(sdy[o][j], wv, acc[j]);
   }
   float* dst = part + (long long)blockIdx.z * B * F;
 #pragma unroll
@@ -904,8 +1000,13 @@ size_t linear_dgrad_scratch_bytes(int B, int F, int O) { return (size_t)cdiv(O, 
 void launch_linear_dgrad(const float* dy, const float* w, float* dx, int B, int F, int O, void* scratch, cudaStream_t st) {
   g_launches += 2;
   const int splits = (int)cdiv(O, LD_OC);
-  dim3 grid(cdiv(F, 256), cdiv(B, LD_BT), splits);
-  k_linear_dgrad<<<grid, 256, 0, st>>>(dy, w, (float*)scratch, B, F, O);
+  if ((F & 3) == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0) {
+    dim3 grid(cdiv(F, 1024), cdiv(B, LD_BT), splits);
+    k_linear_dgrad<<<grid, 256, 0, st>>>(dy, w, (float*)scratch, B, F, O);
+  } else {
+    dim3 grid(cdiv(F, 256), cdiv(B, LD_BT), splits);
+    k_linear_dgrad_scalar<<<grid, 256, 0, st>>>(dy, w, (float*)scratch, B, F, O);
+  }
   long long n = (long long)B * F;
   k_linear_dgrad_reduce<<<min(cdiv(n, 256), 148u * 4), 256, 0, st>>>((const float*)scratch, dx, n, splits);
 }

@@ -287,3 +287,29 @@ def test_adam_matches_torch_optim():
         torch.cuda.synchronize()
     torch.cuda.synchronize()
     assert torch.allclose(p.cpu(), p_ref.detach(), rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("dims", [(32, 8192, 1024), (32, 512, 8192), (128, 4096, 256), (128, 128, 4096), (5, 36, 10), (3, 7, 9),
+                                  (33, 260, 17)])
+def test_linear_fwd_dgrad(dims):
+    """fc kernels (vectorised paths for F % 4 == 0 at the config shapes, scalar fallbacks otherwise) against fp64 matmul"""
+    lib = L.load()
+    B, F, O = dims
+    g = torch.Generator().manual_seed(B + F + O)
+    x, w, b, dy = torch.randn(B, F, generator=g), torch.randn(O, F, generator=g) / F ** 0.5, torch.randn(O, generator=g), torch.randn(B, O, generator=g)
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    for relu in (0, 1):
+        y = torch.empty(B, O, device="cuda")
+        L.check(lib.sivae_linear_fwd(L.ptr(xd), L.ptr(wd), L.ptr(bd), L.ptr(y), B, F, O, relu, None), "sivae_linear_fwd")
+        ref = x.double() @ w.double().t() + b.double()
+        ref = ref.clamp_min(0) if relu else ref
+        assert (y.cpu().double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    nws = lib.sivae_linear_dgrad_workspace_bytes(B, F, O)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    dx = torch.empty(B, F, device="cuda")
+    L.check(lib.sivae_linear_dgrad(L.ptr(dyd), L.ptr(wd), L.ptr(dx), B, F, O, L.ptr(ws), nws, None), "sivae_linear_dgrad")
+    ref = dy.double() @ w.double()
+    assert (dx.cpu().double() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    dx2 = torch.empty_like(dx)
+    L.check(lib.sivae_linear_dgrad(L.ptr(dyd), L.ptr(wd), L.ptr(dx2), B, F, O, L.ptr(ws), nws, None), "sivae_linear_dgrad")
+    assert torch.equal(dx, dx2)                     # deterministic (fixed-order split reduction)

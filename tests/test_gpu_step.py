@@ -48,7 +48,12 @@ def test_tiny_step_vs_reference_golden(backend):
         assert out["scalars"][k] == pytest.approx(v, rel=TOL[backend]), k
     # gradients / BN buffers / num_batches_tracked against the reference's own tensors
     ref = dict(scalars=ora["scalars"], grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
-    compare(out, ref, TOL[backend], label="tiny golden backend %d" % backend, tensor_tol=TTOL[backend])
+    # noise floor = 3x the reference's OWN fp32 round-off (its tensors vs the fp64 oracle from the same state).  This seed has
+    # a knife-edge unit: the LeakyReLU after encoder res_in_8.bn1 sees a pre-activation within fp32 round-off of zero, so the
+    # fp32 reference and the fp64 truth take different slopes for it and five small gradient tensors (stem conv / BN,
+    # res_in_8.conv1 / bn1) of the reference are 5e-4..1.3e-3 away from fp64 (measured on CPU, oracle fp32 == golden bit for
+    # bit).  The engine's exact path lands on one side or the other depending on the summation order of its fc kernels.
+    compare(out, ref, TOL[backend], label="tiny golden backend %d" % backend, tensor_tol=TTOL[backend], noise=ora)
 
 
 @pytest.mark.parametrize("backend", [1, 0, 3])
@@ -178,7 +183,7 @@ def test_tiny_bootstrap_step_vs_reference_golden(backend):
     for k, v in _golden_as_oracle(g).items():
         assert out["scalars"][k] == pytest.approx(v, rel=TOL[backend]), k
     ref = dict(scalars=ora["scalars"], grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
-    compare(out, ref, TOL[backend], label="tiny bootstrap golden backend %d" % backend, tensor_tol=TTOL[backend])
+    compare(out, ref, TOL[backend], label="tiny bootstrap golden backend %d" % backend, tensor_tol=TTOL[backend], noise=ora)
 
 
 def test_train_driver_end_to_end(tmp_path):
