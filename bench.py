@@ -327,7 +327,9 @@ def image_loader_leg(device, out_size, batch, steps=20, warmup=3, src_size=1024)
                 e2e=dict(value=round(batch / (ms_e2e * 1e-3), 1), unit="images/s", ms_per_batch=round(ms_e2e, 4),
                          h2d_bytes_per_step=batch * src_size * src_size * 3 + batch, d2h_bytes_per_step=0),
                 roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4),
-                              bytes_per_launch=nbytes, traffic=None),
+                              bytes_per_launch=nbytes, traffic=_traffic("image"), traffic_detail=_traffic("image_detail"),
+                              note="instruction-bound, not HBM-bound: 20 M warp-level integer MACs per batch (17-tap bicubic at 4x "
+                                   "down-scaling) each need a byte load and an IMAD; see DESIGN.md section 5"),
                 cpu_baseline=dict(value=round(cpu_ips, 1), unit="images/s", cores=1, kind="reference",
                                   sample="Pillow %s resize + ToTensor of one %dx%d image repeated for 3 s on one core "
                                          "(the reference's loader runs in the training process, num_workers=0)" % (__import__("PIL").__version__, src_size, src_size)))
