@@ -11,7 +11,7 @@ tensor-core path from its exact path.
   fp16-noscale  the same without the gradient scale (shows why the scale is needed)
   bf16        7-bit mantissa
 
-Test infrastructure (imports oracle/); usage:  python profiles/study_operand_formats.py > profiles/r01v_operand_formats.md
+Test infrastructure (imports oracle/, hence under tests/; not collected by pytest); usage:  python tests/study_operand_formats.py > profiles/r01v_operand_formats.md
 """
 import os
 import sys
