@@ -184,12 +184,18 @@ def run_ours(args):
     # ~3 % of the step, so they stay out of the headline region); roofline numbers come from this pass
     lib.sivae_profile_enable(1)
     ms_prof = timed(lambda i: step_resident(i + args.steps, use_graph=False), args.steps)
+    buf = C.create_string_buffer(1 << 16)
+    lib.sivae_profile_dump(buf, len(buf))
+    rows = [l.split() for l in buf.value.decode().splitlines()]
+    # BatchNorm+activation passes (classes 5 / 6 of the dump; their "gflop" column carries algorithmic GB): HBM-bound
+    bn_cls = {}
+    for r in rows:
+        if int(r[0]) in (5, 6):
+            a = bn_cls.setdefault(int(r[0]), [0.0, 0.0, 0])
+            a[0] += float(r[8]); a[1] += float(r[9]); a[2] += int(r[7])
     if args.layers and rank == 0:
-        buf = C.create_string_buffer(1 << 16)
-        lib.sivae_profile_dump(buf, len(buf))
         names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, TB/s)",
                  5: "bn+act fwd (k=4+mode: residual; TB/s)", 6: "bn+act bwd (k=4+mode: residual; TB/s)"}
-        rows = [l.split() for l in buf.value.decode().splitlines()]
         rows.sort(key=lambda r: -float(r[8]))
         with open(args.layers, "w") as f:
             f.write("| class | N | H | W | Cin | Cout | k | launches/step | ms/step | ms/launch | TFLOP/s |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
@@ -238,6 +244,15 @@ def run_ours(args):
                     wgrad=dict(achieved=round(wg_flops / (wg_ms * 1e-3) / 1e12, 2) if wg_ms > 0 else None,
                                ms_per_step=round(wg_ms / args.steps, 3), launches_per_step=wg_n / args.steps),
                     simt_conv_ms_per_step=round(simt_ms / args.steps, 3))
+        for cls, key, kern in ((5, "bn_fwd", "k_bn_act_fwd (BN apply + residual + LeakyReLU + pool / upsample)"),
+                               (6, "bn_bwd", "k_bn_bwd_reduce + k_bn_bwd_apply (train-mode BN + LeakyReLU backward)")):
+            if cls in bn_cls and bn_cls[cls][0] > 0:
+                ms_c, gb_c, n_c = bn_cls[cls]
+                gbs = gb_c / (ms_c * 1e-3)
+                roof[key] = dict(bound="hbm", kernel=kern, achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                                 frac=round(gbs / peaks["hbm_gbs"], 4), ms_per_step=round(ms_c / args.steps, 3),
+                                 launches_per_step=n_c / args.steps, share_of_step=round(ms_c / ms_prof, 4),
+                                 note="algorithmic bytes = full-tensor passes each launch must make (DESIGN.md section 5)")
         if prof[14] > 0 and prof[12] > 0:
             gbs = prof[13] / (prof[12] * 1e-3) / 1e9
             roof["loss_pass"] = dict(bound="hbm", kernel="k_mse3_partial (fused 3x per-sample MSE over five images)",
