@@ -547,6 +547,54 @@ def vae_iteration(model, real, eps, hp, lr_e, lr_d):
     return eng.stats
 
 
+class DevicePrefetcher:
+    """Iterates `loader` one batch ahead: while the step on batch i runs, batch i+1 is fetched and moved to `device` on a side
+    stream (for a GpuImageLoader that includes its resize kernel), so the copy engine works under the step instead of in
+    front of it.  Yields what the loader yields, with every tensor on `device`; values and order are unchanged
+    (the reference does `batch.to(device)` synchronously at :549)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.dataset = getattr(loader, "dataset", None)
+        self.batch_size = getattr(loader, "batch_size", None)
+        self._stream = None
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _move(self, b, main):
+        if torch.is_tensor(b):
+            t = b.to(self.device, non_blocking=True)
+            t.record_stream(main)                 # allocated on the side stream, consumed on the main one
+            return t
+        if isinstance(b, (list, tuple)):
+            return type(b)(self._move(x, main) for x in b)
+        return b
+
+    def __iter__(self):
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(self.device)
+        side, it = self._stream, iter(self.loader)
+
+        def fetch():
+            main = torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(side):
+                try:
+                    b = next(it)
+                except StopIteration:
+                    return None
+                b = self._move(b, main)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return b, ev
+        nxt = fetch()
+        while nxt is not None:
+            cur, ev = nxt
+            nxt = fetch()                         # enqueue batch i+1 before the consumer launches (and waits on) step i
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            yield cur
+
+
 def _milestone_lr(lr, epoch_steps, milestones=(350,), gamma=0.1):
     """MultiStepLR(milestones=(350,), gamma=0.1) stepped once per epoch (:453-454, :649-650)"""
     return lr * (gamma ** sum(1 for m in milestones if epoch_steps >= m))
@@ -611,6 +659,9 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                                          collate_fn=gpu_ds.collate_decoded if on_gpu else None)
     if on_gpu:
         loader = gpu_ds.GpuImageLoader(loader, device)      # yields the float32 [B,C,S,S] batches the reference's loader yields
+    fid_loader = loader
+    if os.environ.get("SIVAE_PREFETCH", "1") != "0":
+        loader = DevicePrefetcher(loader, device)           # host->device copy of batch i+1 under step i
     from tqdm import tqdm
     start_time = time.time()
     cur_iter = 0
@@ -619,12 +670,13 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
     eps = torch.empty(5, batch_size, z_dim, device=device)
     prefix = "{}_soft_intro_betas_{}_{}_{}_".format(dataset, beta_kl, beta_neg, beta_rec)
     real_batch = None
+    noise_host = None
     for epoch in range(start_epoch, num_epochs):
         if with_fid and ((epoch == 0) or (epoch >= 100 and epoch % 20 == 0) or epoch == num_epochs - 1):
             from metrics.fid_score import calculate_fid_given_dataset     # the reference's evaluation package
             with torch.no_grad():
                 print("calculating fid...")
-                fid = calculate_fid_given_dataset(loader, model, batch_size, cuda=True, dims=2048, device=device,
+                fid = calculate_fid_given_dataset(fid_loader, model, batch_size, cuda=True, dims=2048, device=device,
                                                   num_images=50000)
                 print("fid:", fid)
                 if best_fid is None:
@@ -660,7 +712,10 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                     _, _, _, rec = model(real_batch)
                     _save_grid([real_batch, rec], '{}/image_{}.jpg'.format(fig_dir, cur_iter), num_row)
             else:
-                noise_batch = torch.randn(size=(b_size, z_dim)).to(device)          # CPU generator, like the reference
+                if noise_host is None or noise_host.size(0) != b_size:
+                    noise_host = torch.empty(b_size, z_dim).pin_memory()            # persistent pinned staging buffer
+                torch.randn((b_size, z_dim), out=noise_host)                        # CPU generator, like the reference (:547)
+                noise_batch = noise_host.to(device, non_blocking=True)              # (consumed before the per-step sync below)
                 real_batch = batch.to(device, non_blocking=True)
                 e5 = eps if b_size == batch_size else torch.empty(5, b_size, z_dim, device=device)
                 for i in range(5):                                                  # device generator, draw order of

@@ -26,6 +26,7 @@ calc_kl, reparameterize, calc_reconstruction_loss = _B.calc_kl, _B.reparameteriz
 str_to_list, is_image_file, record_scalar, record_image = _B.str_to_list, _B.is_image_file, _B.record_scalar, _B.record_image
 load_model, save_checkpoint = _B.load_model, _B.save_checkpoint
 introspective_iteration, vae_iteration = _B.introspective_iteration, _B.vae_iteration
+DevicePrefetcher = _B.DevicePrefetcher
 
 
 class SoftIntroVAE(_B.SoftIntroVAE):

@@ -108,3 +108,34 @@ def test_loader_end_to_end(tmp_path):
     (b2,) = list(M.GpuImageLoader(torch.utils.data.DataLoader(ds2, batch_size=3, collate_fn=M.collate_decoded), "cuda:0"))
     want = np.stack([IO.load_image_tensor(a, size, size, False) for a in (src[0], odd, src[1])])
     assert np.array_equal(b2.cpu().numpy(), want)
+
+
+def test_device_prefetcher_keeps_values_and_order(tmp_path):
+    """DevicePrefetcher (batch i+1 moves / is assembled on a side stream under step i): same batches, same order, on the
+    device -- for a plain float loader, a labelled one, and the GPU image loader"""
+    from PIL import Image
+    T = importlib.import_module(PKG + ".train_soft_intro_vae")
+    g = torch.Generator().manual_seed(2)
+    data = torch.rand(37, 3, 8, 8, generator=g)
+    plain = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(data), batch_size=8, shuffle=False, pin_memory=True)
+    got = [b[0] for b in T.DevicePrefetcher(plain, "cuda:0")]
+    assert all(t.is_cuda for t in got) and len(got) == 5
+    # consume with work on the main stream in between, as the trainer does
+    acc = torch.zeros(3, 8, 8, device="cuda:0")
+    for b in T.DevicePrefetcher(plain, "cuda:0"):
+        acc += b[0].sum(0) * 1.0
+        torch.cuda.current_stream().synchronize()
+    assert torch.equal(torch.cat(got).cpu(), data)
+    assert torch.allclose(acc.cpu(), data.sum(0), rtol=1e-5, atol=1e-5)
+    M = _mod()
+    z = np.load(GOLD)
+    src, out_u8, size = z["celeba_like/src"], z["celeba_like/out_u8"], int(z["celeba_like/size"][0])
+    names = []
+    for i, a in enumerate(src):
+        names.append("p_%d.png" % i)
+        Image.fromarray(a, "RGB").save(tmp_path / names[-1])
+    ds = M.ImageDatasetFromFile(names, str(tmp_path), input_height=None, crop_height=None, output_height=size, is_mirror=False)
+    loader = M.GpuImageLoader(torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, collate_fn=M.collate_decoded), "cuda:0")
+    want = np.stack([IO.load_image_tensor(a, size, size, False) for a in src])
+    got = torch.cat(list(T.DevicePrefetcher(loader, "cuda:0"))).cpu().numpy()
+    assert np.array_equal(got, want)
