@@ -319,3 +319,34 @@ def test_decoder_pass_reuse_falls_back_when_decoder_touched():
         res.append((eng.stats.clone(), eng.mem[L.NET_DECODER].grads.clone(), eng.mem[L.NET_DECODER].bn.clone()))
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
+
+
+def test_nan_loss_raises_system_error(tmp_path):
+    """reference :625-626: `if torch.isnan(lossD) or torch.isnan(lossE): raise SystemError` -- the engine sets stats[15] on the
+    device and the drop-in trainer raises; also at the iteration level (a NaN pixel poisons lossE / lossD)"""
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    torch.manual_seed(1)
+    model = M.SoftIntroVAE(**cfg).to("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    real = torch.rand(8, 3, 32, 32, generator=g).cuda()
+    noise, eps = torch.randn(8, 32, generator=g).cuda(), torch.randn(5, 8, 32, generator=g).cuda()
+    hp = E.make_hyper(1.0, 1.0, 256.0, 1e-8, 1.0 / (3 * 32 * 32))
+    st = M.introspective_iteration(model, real, noise, eps, hp, 2e-4, 2e-4, use_graph=False)
+    assert float(st[15]) == 0.0
+    real[3, 1, 5, 7] = float("nan")
+    st = M.introspective_iteration(model, real, noise, eps, hp, 2e-4, 2e-4, use_graph=False)
+    assert float(st[15]) != 0.0
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with pytest.raises(SystemError):
+            M.train_soft_intro_vae(dataset="synthetic32:32", z_dim=32, batch_size=16, num_workers=0, num_epochs=1, num_vae=0,
+                                   beta_kl=float("nan"), beta_neg=256, beta_rec=1.0, device=torch.device("cuda:0"),
+                                   save_interval=50, start_epoch=0, lr_e=2e-4, lr_d=2e-4, pretrained=None, seed=3,
+                                   test_iter=1000, with_fid=False)
+    finally:
+        os.chdir(cwd)
