@@ -125,7 +125,8 @@ def run_ours(args):
     noise_d = torch.randn(batch, zdim, device=device)
     eps_d = torch.randn(5, batch, zdim, device=device)
     stats_host = torch.empty(16).pin_memory()
-    noise_host = torch.empty(batch, zdim).pin_memory()
+    noise_host = [torch.empty(batch, zdim).pin_memory() for _ in range(2)]
+    stats_host2 = [torch.empty(16).pin_memory() for _ in range(2)]
 
     def step_resident(i, use_graph=None):
         mod.introspective_iteration(model, dev_real[i % n_host], noise_d, eps_d, hp, 2e-4, 2e-4, use_graph=use_graph)
@@ -144,16 +145,26 @@ def run_ours(args):
 
     def run_e2e(steps):
         """what the drop-in trainer does per iteration (train_soft_intro_vae.py _run_training): batch i+1 moves host->device on
-        a side stream while step i runs (DevicePrefetcher), noise from the CPU generator (:547), the five eps draws on the
-        device, the step, and the logged statistics read back (:628) -- every step, inside the timed region"""
-        for real in mod.DevicePrefetcher(_HostBatches(steps), device):
-            torch.randn((batch, zdim), out=noise_host)                  # CPU generator (:547) into a persistent pinned buffer
-            noise = noise_host.to(device, non_blocking=True)
+        a side stream while step i runs (DevicePrefetcher), noise from the CPU generator (:547) through a pinned buffer, the
+        five eps draws on the device, the step, and the logged statistics copied back every step (:628) -- read, like the
+        trainer reads them, once the next step has been queued (the last one before the region ends)"""
+        pend = None
+        for i, real in enumerate(mod.DevicePrefetcher(_HostBatches(steps), device)):
+            nh = noise_host[i % 2]
+            torch.randn((batch, zdim), out=nh)
+            noise = nh.to(device, non_blocking=True)
             for k in range(5):
                 torch.randn((batch, zdim), out=eps_d[k])
             st = mod.introspective_iteration(model, real, noise, eps_d, hp, 2e-4, 2e-4)
-            stats_host.copy_(st, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            stats_host2[i % 2].copy_(st, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if pend is not None:
+                pend[1].synchronize()
+                assert float(pend[0][15]) == 0.0, "NaN flag"
+            pend = (stats_host2[i % 2], ev)
+        pend[1].synchronize()
+        stats_host.copy_(pend[0])
         return stats_host
 
     def barrier():

@@ -4,6 +4,7 @@
 // Reference semantics: soft_intro_vae/train_soft_intro_vae.py (lines cited per kernel).
 #include "kernels.h"
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -787,18 +788,123 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
     }
   }
 }
+// Small maps (rows <= BN_SMALL_ROWS: the 4x4 / 8x8 layers, 50+ launches per step each): the three launches above are pure
+// latency there.  BatchNorm backward is channel-local, so one block per float4 channel group does everything: pass 1 over
+// all rows (256 row lanes) for sum(g), sum(g*xhat); block reduction (shuffles, then fp64 over the 8 warps, fixed order);
+// parameter gradients; pass 2 re-reads the rows (L1 / L2 hits) and writes dt (and the identity-branch gradient).
+constexpr long long BN_SMALL_ROWS = 4096;
+template <int MODE, bool ROUND>
+__global__ void __launch_bounds__(256) k_bn_bwd_small(const float* __restrict__ dout, const float* __restrict__ t,
+                                                      const float* __restrict__ idn, const float* __restrict__ mi,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ dt, float* __restrict__ gout, float* dgamma,
+                                                      float* dbeta, int accumulate, int N, int H, int W, int C,
+                                                      const unsigned char* __restrict__ mask) {
+  const int c4 = blockIdx.x;
+  const unsigned cvec = (unsigned)C >> 2;
+  const unsigned rows = (unsigned)N * H * W;
+  const float4 mean = __ldg(reinterpret_cast<const float4*>(mi) + c4);
+  const float4 istd = __ldg(reinterpret_cast<const float4*>(mi + C) + c4);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+  auto elem = [&](unsigned r, float4& g, float4& xh) {
+    int w = 0, h = 0, n = 0;
+    if (MODE != RS_NONE) {
+      w = (int)(r % (unsigned)W);
+      const unsigned q = r / (unsigned)W;
+      h = (int)(q % (unsigned)H);
+      n = (int)(q / (unsigned)H);
+    }
+    const float4 d = upstream<MODE>(dout, (long long)r, n, h, w, H, W, C, c4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(t + (size_t)r * C) + c4);
+    xh = make_float4((v.x - mean.x) * istd.x, (v.y - mean.y) * istd.y, (v.z - mean.z) * istd.z, (v.w - mean.w) * istd.w);
+    if (mask) {
+      g = lrelu_grad_mask(__ldg(mask + (size_t)r * cvec + c4), d);
+    } else {
+      float4 y = make_float4(fmaf(xh.x, ga.x, be.x), fmaf(xh.y, ga.y, be.y), fmaf(xh.z, ga.z, be.z), fmaf(xh.w, ga.w, be.w));
+      if (idn) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(idn + (size_t)r * C) + c4);
+        y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+      }
+      g = make_float4(lrelu_grad(y.x, d.x), lrelu_grad(y.y, d.y), lrelu_grad(y.z, d.z), lrelu_grad(y.w, d.w));
+    }
+  };
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // sum g (4), sum g*xhat (4)
+  for (unsigned r = threadIdx.x; r < rows; r += 256) {
+    float4 g, xh;
+    elem(r, g, xh);
+    acc[0] += g.x; acc[1] += g.y; acc[2] += g.z; acc[3] += g.w;
+    acc[4] = fmaf(g.x, xh.x, acc[4]); acc[5] = fmaf(g.y, xh.y, acc[5]); acc[6] = fmaf(g.z, xh.z, acc[6]); acc[7] = fmaf(g.w, xh.w, acc[7]);
+  }
+  __shared__ double red[8][8];
+  __shared__ float fin[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = (double)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][k];
+    fin[k] = (float)(s / (double)rows);                            // mean of g / of g*xhat
+    const int c = c4 * 4 + (k & 3);
+    if (dgamma) {
+      if (k < 4) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+      else dgamma[c] = accumulate ? dgamma[c] + (float)s : (float)s;
+    }
+  }
+  __syncthreads();
+  const float4 mg = make_float4(fin[0], fin[1], fin[2], fin[3]), mx = make_float4(fin[4], fin[5], fin[6], fin[7]);
+  for (unsigned r = threadIdx.x; r < rows; r += 256) {
+    float4 g, xh;
+    elem(r, g, xh);
+    float4 o;
+    o.x = ga.x * istd.x * (g.x - mg.x - xh.x * mx.x);
+    o.y = ga.y * istd.y * (g.y - mg.y - xh.y * mx.y);
+    o.z = ga.z * istd.z * (g.z - mg.z - xh.z * mx.z);
+    o.w = ga.w * istd.w * (g.w - mg.w - xh.w * mx.w);
+    if (ROUND) {
+      o.x = round_tf32_dev(o.x); o.y = round_tf32_dev(o.y); o.z = round_tf32_dev(o.z); o.w = round_tf32_dev(o.w);
+    }
+    reinterpret_cast<float4*>(dt + (size_t)r * C)[c4] = o;
+    if (gout) {
+      if (ROUND) { g.x = round_tf32_dev(g.x); g.y = round_tf32_dev(g.y); g.z = round_tf32_dev(g.z); g.w = round_tf32_dev(g.w); }
+      reinterpret_cast<float4*>(gout + (size_t)r * C)[c4] = g;
+    }
+  }
+}
+static bool bn_small_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SIVAE_BN_SMALL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mi, const float* gamma,
                        const float* beta, float* dt, float* g, float* dgamma, float* dbeta, bool accumulate, int N,
                        int H, int W, int C, int mode, bool rnd, void* scratch, size_t scratch_bytes, cudaStream_t st,
                        const unsigned char* mask) {
-  g_launches += 3;
   long long rows = (long long)N * H * W;
   if (rows == 0) return;
+  int cvec = C / 4;
+  if (rows <= BN_SMALL_ROWS && bn_small_enabled()) {
+    g_launches += 1;
+#define LAUNCH(M, R) k_bn_bwd_small<M, R><<<cvec, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, dt, g, dgamma, dbeta, accumulate ? 1 : 0, N, H, W, C, mask)
+    if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
+    else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
+    else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }
+#undef LAUNCH
+    return;
+  }
+  g_launches += 3;
   int nblk = bn_nblocks(rows);
   const int rpb = bn_rows_per_block(rows);
   float* part = (float*)scratch;
   float* sums = part + (size_t)nblk * 2 * C;
-  int cvec = C / 4, rl_n = 256 / cvec;
+  int rl_n = 256 / cvec;
   size_t shmem = (size_t)rl_n * 2 * C * sizeof(float);
   if (mode == RS_NONE) k_bn_bwd_reduce<RS_NONE><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb, mask);
   else if (mode == RS_POOL) k_bn_bwd_reduce<RS_POOL><<<nblk, 256, shmem, st>>>(dout, t, identity, mi, gamma, beta, N, H, W, C, part, rpb, mask);

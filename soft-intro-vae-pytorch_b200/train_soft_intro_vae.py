@@ -671,6 +671,22 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
     prefix = "{}_soft_intro_betas_{}_{}_{}_".format(dataset, beta_kl, beta_neg, beta_rec)
     real_batch = None
     noise_host = None
+    stats_host = [torch.empty(16).pin_memory() for _ in range(2)]
+    async_stats = os.environ.get("SIVAE_ASYNC_STATS", "1") != "0"
+    pending = None
+
+    def consume_stats(p):
+        sh_, ev_, epoch_, pbar_ = p
+        ev_.synchronize()
+        st = sh_.clone()
+        if bool(st[15] != 0):                                               # isnan(lossD) or isnan(lossE) (:625-626)
+            raise SystemError
+        kl_real, kl_fake, kl_rec, rec_err = st[1].item(), st[7].item(), st[6].item(), st[5].item()
+        pbar_.set_description_str('epoch #{}'.format(epoch_))
+        pbar_.set_postfix(r_loss=rec_err, kl=kl_real, diff_kl=kl_fake - kl_real, expelbo_f=st[3].item())
+        track.add(diff_kl=kl_fake - kl_real, kl_real=kl_real, kl_fake=kl_fake, kl_rec=kl_rec, rec_err=rec_err,
+                  exp_elbo_f=st[3].item(), exp_elbo_r=st[2].item())
+
     for epoch in range(start_epoch, num_epochs):
         if with_fid and ((epoch == 0) or (epoch >= 100 and epoch % 20 == 0) or epoch == num_epochs - 1):
             from metrics.fid_score import calculate_fid_given_dataset     # the reference's evaluation package
@@ -712,28 +728,39 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                     _, _, _, rec = model(real_batch)
                     _save_grid([real_batch, rec], '{}/image_{}.jpg'.format(fig_dir, cur_iter), num_row)
             else:
-                if noise_host is None or noise_host.size(0) != b_size:
-                    noise_host = torch.empty(b_size, z_dim).pin_memory()            # persistent pinned staging buffer
-                torch.randn((b_size, z_dim), out=noise_host)                        # CPU generator, like the reference (:547)
-                noise_batch = noise_host.to(device, non_blocking=True)              # (consumed before the per-step sync below)
+                if noise_host is None or noise_host[0].size(0) != b_size:
+                    noise_host = [torch.empty(b_size, z_dim).pin_memory() for _ in range(2)]   # persistent pinned staging
+                nh = noise_host[cur_iter % 2]            # last used two steps ago: that step's statistics have been read
+                torch.randn((b_size, z_dim), out=nh)                                # CPU generator, like the reference (:547)
+                noise_batch = nh.to(device, non_blocking=True)
                 real_batch = batch.to(device, non_blocking=True)
                 e5 = eps if b_size == batch_size else torch.empty(5, b_size, z_dim, device=device)
                 for i in range(5):                                                  # device generator, draw order of
                     torch.randn((b_size, z_dim), out=e5[i])                         # :560,567,568,602,605
-                st = introspective_iteration(model, real_batch, noise_batch, e5, hp, cur_lr_e, cur_lr_d).cpu()
-                if bool(st[15] != 0):                                               # isnan(lossD) or isnan(lossE)
-                    raise SystemError
-                kl_real, kl_fake, kl_rec, rec_err = st[1].item(), st[7].item(), st[6].item(), st[5].item()
-                pbar.set_description_str('epoch #{}'.format(epoch))
-                pbar.set_postfix(r_loss=rec_err, kl=kl_real, diff_kl=kl_fake - kl_real, expelbo_f=st[3].item())
-                track.add(diff_kl=kl_fake - kl_real, kl_real=kl_real, kl_fake=kl_fake, kl_rec=kl_rec, rec_err=rec_err,
-                          exp_elbo_f=st[3].item(), exp_elbo_r=st[2].item())
+                st_dev = introspective_iteration(model, real_batch, noise_batch, e5, hp, cur_lr_e, cur_lr_d)
+                sh = stats_host[cur_iter % 2]
+                sh.copy_(st_dev, non_blocking=True)                                 # the logged scalars (:628-639) + NaN flag
+                ev = torch.cuda.Event()
+                ev.record()
+                # The statistics of step i are read while step i+1 is already queued (SIVAE_ASYNC_STATS=0: right away, like
+                # the reference's .item() calls): the ~2000-node graph launch of the next step is then never exposed behind a
+                # device->host sync.  The NaN guard (:625-626) and the tqdm postfix therefore lag by one iteration; epoch
+                # statistics are complete (the last pending read is flushed at the end of the epoch).
+                if pending is not None:
+                    consume_stats(pending)
+                pending = (sh, ev, epoch, pbar)
+                if not async_stats:
+                    consume_stats(pending)
+                    pending = None
                 if cur_iter % test_iter == 0:
                     _, _, _, rec_det = model(real_batch, deterministic=True)
                     fake = model._engine.last_image(0)            # `fake` of the D half (:597), not a new forward
                     k = min(b_size, 16)
                     _save_grid([real_batch[:k], rec_det[:k], fake[:k]], '{}/image_{}.jpg'.format(fig_dir, cur_iter), num_row)
             cur_iter += 1
+        if pending is not None:
+            consume_stats(pending)
+            pending = None
         pbar.close()
         if copy_to_target_freq is not None and epoch % copy_to_target_freq == 0:
             # bootstrap: the frozen target decoder follows the decoder, lagging by up to copy_to_target_freq epochs

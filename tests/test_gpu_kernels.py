@@ -152,7 +152,7 @@ def test_conv_tc3x_unrounded_operands(shape):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("with_id,use_mask", [(False, False), (True, False), (True, True)])
-@pytest.mark.parametrize("dims", [(3, 8, 8, 32), (2, 6, 10, 24)])      # power-of-two fast index path / generic path
+@pytest.mark.parametrize("dims", [(3, 8, 8, 32), (2, 6, 10, 24), (5, 32, 32, 8)])      # small maps: fused one-block-per-channel-group backward; last: rows > 4096 -> reduce / finalize / apply
 def test_bn_act_fwd_bwd(mode, with_id, use_mask, dims):
     lib = L.load()
     N, H, W, Cc = dims
