@@ -143,13 +143,21 @@ def run_ours(args):
             for i in range(self.n):
                 yield host_real[i % n_host]
 
-    def run_e2e(steps):
-        """what the drop-in trainer does per iteration (train_soft_intro_vae.py _run_training): batch i+1 moves host->device on
-        a side stream while step i runs (DevicePrefetcher), noise from the CPU generator (:547) through a pinned buffer, the
-        five eps draws on the device, the step, and the logged statistics copied back every step (:628) -- read, like the
-        trainer reads them, once the next step has been queued (the last one before the region ends)"""
+    e2e_prefetch = os.environ.get("SIVAE_PREFETCH", "1") != "0"          # the trainer's defaults
+    e2e_async = os.environ.get("SIVAE_ASYNC_STATS", "0") == "1"
+
+    def run_e2e(steps, prefetch=None, defer=None):
+        """what the drop-in trainer does per iteration (train_soft_intro_vae.py _run_training): the batch moves host->device
+        (prefetch: batch i+1 on a side stream while step i runs, DevicePrefetcher), noise from the CPU generator (:547)
+        through a pinned buffer, the five eps draws on the device, the step, and the logged statistics copied back every
+        step (:628) -- read right away, or (defer) like the trainer once the next step has been queued"""
+        prefetch = e2e_prefetch if prefetch is None else prefetch
+        defer = e2e_async if defer is None else defer
+        src = mod.DevicePrefetcher(_HostBatches(steps), device) if prefetch else _HostBatches(steps)
         pend = None
-        for i, real in enumerate(mod.DevicePrefetcher(_HostBatches(steps), device)):
+        for i, real in enumerate(src):
+            if not prefetch:
+                real = real.to(device, non_blocking=True)
             nh = noise_host[i % 2]
             torch.randn((batch, zdim), out=nh)
             noise = nh.to(device, non_blocking=True)
@@ -163,9 +171,26 @@ def run_ours(args):
                 pend[1].synchronize()
                 assert float(pend[0][15]) == 0.0, "NaN flag"
             pend = (stats_host2[i % 2], ev)
-        pend[1].synchronize()
-        stats_host.copy_(pend[0])
+            if not defer:
+                ev.synchronize()
+                pend = None
+        if pend is not None:
+            pend[1].synchronize()
+        stats_host.copy_(stats_host2[(steps - 1) % 2])
         return stats_host
+
+    def time_e2e(steps, **kw):
+        run_e2e(5, **kw)                       # warm-up: side-stream allocator pool, pinned staging, graph replay path
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        run_e2e(steps, **kw)
+        eb.record()
+        barrier()
+        t = torch.tensor([ea.elapsed_time(eb)], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
     def barrier():
         if world > 1:
@@ -234,17 +259,11 @@ def run_ours(args):
     prof = (C.c_double * 15)()
     lib.sivae_profile_read(prof)
     lib.sivae_profile_enable(0)
-    run_e2e(3)
-    barrier()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea.record()
-    run_e2e(args.steps)
-    eb.record()
-    barrier()
-    ms_e2e_t = torch.tensor([ea.elapsed_time(eb)], device=device)
-    if world > 1:
-        dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms_e2e_t)
+    ms_e2e = time_e2e(args.steps)
+    e2e_sweep = None
+    if args.e2e_sweep:
+        e2e_sweep = {"prefetch=%d,defer=%d" % (p_, d_): round(time_e2e(args.steps, prefetch=bool(p_), defer=bool(d_)) / args.steps, 3)
+                     for p_ in (0, 1) for d_ in (0, 1)}
     # secondary number, NOT the headline: the opt-in pass re-use (the D half takes fake / rec from the E half's identical
     # decoder passes instead of recomputing them; bit-identical results, tests/test_gpu_step.py).  Headline and e2e above
     # execute all 13 forward passes of the reference step.
@@ -309,6 +328,9 @@ def run_ours(args):
                             " of %d kernels per step (counted on an eager step)" % launches_per_step,
                 roofline=roof, clocks=sampler.summary() if rank == 0 else None,
                 last_stats=dict(loss_rec=float(st[5]), kl_real=float(st[1]), lossE=float(st[4]), lossD=float(st[10])))
+    line["e2e"]["mode"] = "prefetch=%d,defer_stats=%d" % (int(e2e_prefetch), int(e2e_async))
+    if e2e_sweep is not None:
+        line["e2e"]["sweep_ms_per_step"] = e2e_sweep
     if reuse_ms is not None:
         line["decoder_pass_reuse"] = dict(in_headline=False, ms_per_step=round(reuse_ms, 3),
                                           value=round(world * batch / (reuse_ms / 1e3), 2), unit="images/s",
@@ -469,6 +491,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-sweep", action="store_true", help="also time the e2e leg with / without batch prefetch and deferred statistics reads")
     ap.add_argument("--no-loader-leg", action="store_true", help="skip the image batch-assembly kernel timing")
     ap.add_argument("--no-reuse-leg", action="store_true", help="skip the secondary timing with decoder-pass re-use")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")

@@ -553,11 +553,13 @@ class DevicePrefetcher:
     front of it.  Yields what the loader yields, with every tensor on `device`; values and order are unchanged
     (the reference does `batch.to(device)` synchronously at :549)."""
 
+    _streams = {}           # one side stream per device, shared by all prefetchers of the process
+
     def __init__(self, loader, device):
         self.loader, self.device = loader, torch.device(device)
         self.dataset = getattr(loader, "dataset", None)
         self.batch_size = getattr(loader, "batch_size", None)
-        self._stream = None
+        self._stream = DevicePrefetcher._streams.get(self.device)
 
     def __len__(self):
         return len(self.loader)
@@ -573,7 +575,7 @@ class DevicePrefetcher:
 
     def __iter__(self):
         if self._stream is None:
-            self._stream = torch.cuda.Stream(self.device)
+            self._stream = DevicePrefetcher._streams.setdefault(self.device, torch.cuda.Stream(self.device))
         side, it = self._stream, iter(self.loader)
 
         def fetch():
@@ -672,7 +674,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
     real_batch = None
     noise_host = None
     stats_host = [torch.empty(16).pin_memory() for _ in range(2)]
-    async_stats = os.environ.get("SIVAE_ASYNC_STATS", "1") != "0"
+    async_stats = os.environ.get("SIVAE_ASYNC_STATS", "0") == "1"
     pending = None
 
     def consume_stats(p):
@@ -742,10 +744,11 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                 sh.copy_(st_dev, non_blocking=True)                                 # the logged scalars (:628-639) + NaN flag
                 ev = torch.cuda.Event()
                 ev.record()
-                # The statistics of step i are read while step i+1 is already queued (SIVAE_ASYNC_STATS=0: right away, like
-                # the reference's .item() calls): the ~2000-node graph launch of the next step is then never exposed behind a
-                # device->host sync.  The NaN guard (:625-626) and the tqdm postfix therefore lag by one iteration; epoch
-                # statistics are complete (the last pending read is flushed at the end of the epoch).
+                # Default: the statistics are read right after the step, like the reference's .item() calls (:625-639).
+                # SIVAE_ASYNC_STATS=1 reads those of step i once step i+1 is queued, so a slow host never exposes the next
+                # launch behind the device->host sync; the NaN guard and the tqdm postfix then lag by one iteration, epoch
+                # statistics stay complete (flushed at the end of the epoch).  Measured equal on this pool's hosts
+                # (profiles/r01y_e2e_sweep.json), hence off.
                 if pending is not None:
                     consume_stats(pending)
                 pending = (sh, ev, epoch, pbar)
