@@ -174,6 +174,11 @@ int sivae_mse3(const float* real, const float* rec, const float* rec_rec, const 
 int sivae_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int batch, int zdim, void* stream);
 int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
                     long long step, void* stream);
+/* EXPERIMENTAL (round-2 groundwork, not used by any step entry point): the 3x3 conv forward with fp16 operands on the
+   CTA-pair tcgen05 kernel -- x: NHWC half [N,H,W,Cin], w: half [Cout,3,3,Cin], addend (nullable) / y: NHWC fp32.
+   Returns -8 unless k == 3, Cin % 64 == 0 and the shape tiles onto CTA pairs. */
+int sivae_conv2d_fwd_f16(const void* x_half_nhwc, const void* w_half_packed, const float* addend, float* y_nhwc, int N,
+                         int H, int W, int Cin, int Cout, int k, void* stream);
 /* nn.Linear (encoder fc :109,:121; decoder fc + ReLU :145-148,:166-167): y[B,O] = x[B,F] . w[O,F]^T + b (relu != 0: then
    ReLU), and its input gradient dx[B,F] = dy[B,O] . w[O,F] (workspace: sivae_linear_dgrad_workspace_bytes) */
 int sivae_linear_fwd(const float* x, const float* w, const float* b, float* y, int batch, int in_features, int out_features,

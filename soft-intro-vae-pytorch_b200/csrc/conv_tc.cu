@@ -55,6 +55,30 @@ static int make_map_nhwc(CUtensorMap* m, const float* base, int N, int H, int W,
                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -102;
 }
+// fp16 operand tensors (round-2 groundwork): NHWC half [N][H][W][C] -> box {64, bw, bh, bn}; a
+// 128-byte swizzle row then holds 64 channels instead of 32, every byte offset inside the staged tiles stays what it is
+static int make_map_nhwc_f16(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return -101;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -102;
+}
+static int make_map_2d_f16(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return -101;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -102;
+}
 static int make_store_map(CUtensorMap* m, float* base, int N, int H, int W, int C, int sw, int sh, int sn) {
   return make_map_nhwc(m, base, N, H, W, C, sw, sh, sn);
 }
@@ -442,6 +466,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// the same with fp16 A/B operands (format code 0): K = 16 halfs = the same 32 bytes per MMA as 8 tf32 values
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1157,6 +1186,13 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -1184,7 +1220,9 @@ struct Halo2Smem {
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+// F16 (round-2 groundwork, not dispatched by the engine yet): A / B operands are fp16 tensors -- 64 channels per 128-byte chunk,
+// tcgen05.mma.kind::f16 -- everything else (staging bytes, descriptors, fp32 accumulators and epilogue) is unchanged
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     k_conv_halo2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_add, const HaloParams p) {
@@ -1204,7 +1242,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int cchunks = p.Cin >> 5;
+  constexpr int CSH = F16 ? 6 : 5;          // log2(channels per 128-byte chunk)
+  const int cchunks = p.Cin >> CSH;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
@@ -1239,7 +1278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
             for (int t = 0; t < T; ++t) {
               const int lin = (mp * 2 + (int)rank) * T + t;
               const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
-              tma_load_4d_2cta(smem + st * SM::A_BYTES + t * SM::BOX_BYTES, &map_x, bar, ch << 5, tw * 8 - 1, th * 16 - 1, n);
+              tma_load_4d_2cta(smem + st * SM::A_BYTES + t * SM::BOX_BYTES, &map_x, bar, ch << CSH, tw * 8 - 1, th * 16 - 1, n);
             }
             ++ai;
           }
@@ -1247,7 +1286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
             const int st = bi % B_STAGES;
             mbar_wait(&b_empty[st], ((bi / B_STAGES) & 1) ^ 1);
             if (leader) mbar_expect_tx(&b_full[st], 2 * SM::B_BYTES);
-            tma_load_2d_2cta(smem + SM::B_OFF + st * SM::B_BYTES, &map_w, mapa_rank(smem_u32(&b_full[st]), 0), tap * p.Cin + (ch << 5),
+            tma_load_2d_2cta(smem + SM::B_OFF + st * SM::B_BYTES, &map_w, mapa_rank(smem_u32(&b_full[st]), 0), tap * p.Cin + (ch << CSH),
                              col0 + (int)rank * (BLOCK_N / 2));
           }
         }
@@ -1255,7 +1294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tf32(256, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(256, BLOCK_N, 0, 0) : make_idesc_tf32(256, BLOCK_N, 0, 0);
       int ai = 0, bi = 0, lt = 0;
       for (int item = cluster_id; item < p.total; item += nclusters, ++lt) {
         const int acc = lt & 1;
@@ -1279,7 +1318,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
               for (int k = 0; k < 4; ++k) {
                 uint64_t ad = make_smem_desc_bo(arow + k * 32, SM::BW * 128, 0);
                 uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-                umma_tf32_2cta(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                if constexpr (F16) umma_f16_2cta(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                else umma_tf32_2cta(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit_2cta(&b_empty[bst]);
@@ -1367,15 +1407,15 @@ static bool halo2_eligible(const ConvShape& s) {
   return two_cta_mode() != 0 && s.k == 3 && s.Cin % 32 == 0 && s.Cout >= min_cout && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0 &&
          tiles % (s.Cout >= 256 ? 2 : 4) == 0 && tma_store_enabled();
 }
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
-static int launch_halo2_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, bool F16 = false>
+static int launch_halo2_t(const void* x, const void* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                           float* stats, cudaStream_t st) {
   using SM = Halo2Smem<BLOCK_N, T, A_STAGES, B_STAGES>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static_assert(SM::TMEM_COLS <= 512, "TMEM budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -1389,9 +1429,11 @@ static int launch_halo2_t(const float* x, const float* w, const float* bias, con
   p.tma_store = 1 | (addend_mode() << 4) | (fast_epi() << 12);
   p.stats = stats;
   CUtensorMap mx, mw, my;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
+  int r = F16 ? make_map_nhwc_f16(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1)
+              : make_map_nhwc(&mx, static_cast<const float*>(x), s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
   if (r) return r;
-  r = make_map_2d(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
+  r = F16 ? make_map_2d_f16(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2)
+          : make_map_2d(&mw, static_cast<const float*>(w), s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
   if (r) return r;
   r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
   if (r) return r;
@@ -1403,7 +1445,7 @@ static int launch_halo2_t(const float* x, const float* w, const float* bias, con
   int nclusters = num_sms() / 2;
   if (p.total < nclusters) nclusters = p.total;
   g_launches += 1;
-  k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
+  k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES, F16><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
   return (int)cudaGetLastError();
 }
 static int launch_halo2(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
@@ -1411,6 +1453,16 @@ static int launch_halo2(const float* x, const float* w, const float* bias, const
   if (s.Cout >= 256) return launch_halo2_t<256, 1, 3, 6>(x, w, bias, addend, y, s, stats, st);
   if (s.Cout > 64) return launch_halo2_t<128, 2, 2, 8>(x, w, bias, addend, y, s, stats, st);
   return launch_halo2_t<64, 2, 3, 8>(x, w, bias, addend, y, s, stats, st);
+}
+// fp16-operand 3x3 conv on the CTA-pair kernel (x: NHWC half, w: [Cout][3][3][Cin] half, y / addend / statistics fp32).
+// Round-2 groundwork: reachable only through sivae_conv2d_fwd_f16; returns -8 for shapes the pair kernel does not take.
+bool conv_f16_supported(const ConvShape& s) { return halo2_eligible(s) && s.Cin % 64 == 0; }
+int launch_conv_fwd_f16(const void* x, const void* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                        float* stats, cudaStream_t st) {
+  if (!conv_f16_supported(s)) return -8;
+  if (s.Cout >= 256) return launch_halo2_t<256, 1, 3, 6, true>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout > 64) return launch_halo2_t<128, 2, 2, 8, true>(x, w, bias, addend, y, s, stats, st);
+  return launch_halo2_t<64, 2, 3, 8, true>(x, w, bias, addend, y, s, stats, st);
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        float* stats, cudaStream_t st) {

@@ -1304,6 +1304,18 @@ extern "C" int sivae_adam_flat(float* p, const float* g, float* m, float* v, lon
   return 0;
 }
 
+// fp16-operand 3x3 conv forward (round-2 groundwork): NOT on any engine path yet
+extern "C" int sivae_conv2d_fwd_f16(const void* x_half_nhwc, const void* w_half_packed, const float* addend, float* y_nhwc, int N,
+                                    int H, int W, int Cin, int Cout, int k, void* stream) {
+  if (!x_half_nhwc || !w_half_packed || !y_nhwc) return fail(-1, "null argument");
+  ConvShape s{N, H, W, Cin, Cout, k};
+  if (!conv_f16_supported(s)) return fail(-8, "fp16-operand conv: shape not supported (3x3, Cin % 64 == 0, CTA-pair tiling)");
+  int r = launch_conv_fwd_f16(x_half_nhwc, w_half_packed, nullptr, addend, y_nhwc, s, nullptr, (cudaStream_t)stream);
+  if (r) return fail(r, "fp16-operand conv launch failed");
+  CHECK_CUDA_RET();
+  return 0;
+}
+
 // nn.Linear forward / input gradient as stand-alone calls (unit parity of the fc kernels)
 extern "C" int sivae_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int F, int O, int relu, void* stream) {
   if (!x || !w || !y || B < 1 || F < 1 || O < 1) return fail(-1, "bad argument");

@@ -81,6 +81,11 @@ size_t conv_tc_splitk_scratch_bytes(const ConvShape& s);
 // fused train-mode BN statistics: if > 0, passing `stats` ([parts][2][Cout] floats) to launch_conv_fwd_tc makes the
 // epilogue emit per-warp column sums / sums of squares; finish with launch_bn_stats_from_parts
 int conv_tc_stats_parts(const ConvShape& s);
+// fp16-operand variant of the CTA-pair 3x3 kernel (round-2 groundwork; not dispatched by the engine): x NHWC half, w packed
+// [Cout][3][3][Cin] half, fp32 output / addend / statistics.  -8: shape not taken by the pair kernel or Cin % 64 != 0
+bool conv_f16_supported(const ConvShape& s);
+int launch_conv_fwd_f16(const void* x, const void* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                        float* stats, cudaStream_t st);
 bool conv_tc_supported_wgrad(const ConvShape& s);
 size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s);
 int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,

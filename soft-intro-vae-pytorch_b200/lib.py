@@ -73,6 +73,7 @@ _SIGS = {
     "sivae_mse3": (C.c_int, [_P] * 6 + [C.c_int, C.c_longlong, _P, C.c_longlong, _P]),
     "sivae_kl_reparam": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "sivae_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_longlong, _P]),
+    "sivae_conv2d_fwd_f16": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 6 + [_P]),
     "sivae_linear_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "sivae_linear_dgrad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_longlong, _P]),
     "sivae_linear_dgrad_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int]),

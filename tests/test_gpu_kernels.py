@@ -1,5 +1,6 @@
 """-m gpu: single-kernel parity through the C ABI against plain torch fp32/fp64 references of the same op."""
 import ctypes as C
+import os
 import importlib
 
 import pytest
@@ -313,3 +314,27 @@ def test_linear_fwd_dgrad(dims):
     dx2 = torch.empty_like(dx)
     L.check(lib.sivae_linear_dgrad(L.ptr(dyd), L.ptr(wd), L.ptr(dx2), B, F, O, L.ptr(ws), nws, None), "sivae_linear_dgrad")
     assert torch.equal(dx, dx2)                     # deterministic (fixed-order split reduction)
+
+
+@pytest.mark.skipif(os.environ.get("SIVAE_TEST_F16", "0") != "1",
+                    reason="round-2 groundwork: the fp16-operand conv variant has not been run on a GPU yet (SIVAE_TEST_F16=1)")
+@pytest.mark.parametrize("shape", [(4, 32, 32, 64, 64), (2, 64, 64, 128, 128), (2, 32, 32, 256, 256), (4, 16, 16, 128, 512)])
+def test_conv_fwd_f16_operands(shape):
+    """k_conv_halo2<..., F16>: fp16 operands are exact inputs of the tensor core, fp32 accumulation -> 1e-6 from the fp64 conv
+    of the same (fp16-rounded) operands, with and without an addend"""
+    lib = L.load()
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(N + H + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g).half()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).half()
+    add = torch.randn(N, Cout, H, W, generator=g)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wd = w.permute(0, 2, 3, 1).contiguous().cuda()
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), None, 1, 1)
+    for addend in (None, add):
+        y = torch.empty(N, H, W, Cout, device="cuda")
+        ad = addend.permute(0, 2, 3, 1).contiguous().cuda() if addend is not None else None
+        L.check(lib.sivae_conv2d_fwd_f16(L.ptr(xd), L.ptr(wd), L.ptr(ad), L.ptr(y), N, H, W, Cin, Cout, 3, None), "sivae_conv2d_fwd_f16")
+        want = ref + (addend.double() if addend is not None else 0)
+        got = y.cpu().permute(0, 3, 1, 2).double()
+        assert ((got - want).norm() / want.norm()).item() < 2e-6
