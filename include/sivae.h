@@ -28,11 +28,19 @@ extern "C" {
 typedef struct sivae_engine sivae_engine;
 
 enum { SIVAE_NET_ENCODER = 0, SIVAE_NET_DECODER = 1, SIVAE_NET_TARGET = 2 };
-/* conv_backend: AUTO = tcgen05 kind::tf32 where the shape allows (default); SIMT = exact fp32 CUDA-core path with fp64-chunked
-   accumulation (on-device reference); TCGEN05 = single-kernel entry points only: tensor core or error;
-   TC3X = compensated tensor-core mode: every operand split into two tf32 parts (hi + lo), three MMAs per product
-   (hi*hi + hi*lo + lo*hi), fp32-class accuracy (ELBO/KL within 1e-4 of the reference) at ~3x the conv time */
-enum { SIVAE_CONV_AUTO = 0, SIVAE_CONV_SIMT = 1, SIVAE_CONV_TCGEN05 = 2, SIVAE_CONV_TC3X = 3 };
+/* conv_backend:
+   AUTO (default) = tcgen05 with compensated 16-bit FORWARD operands: activations and filters are stored as bf16 hi + lo
+     pairs ("split32": 16 significand bits, fp32 exponent range) and every product of a forward conv is three kind::f16 MMAs
+     (lo*hi + hi*lo + hi*hi, fp32 accumulate) = 1.5x the tf32 tensor time; every logged scalar (ELBO / KL / exp-ELBO) stays
+     within 1e-4 of the reference.  dgrad / wgrad run kind::tf32 (their rounding moves the gradients by ~1e-3, below the
+     fp32 reference's own round-off on the same tensors).  Needs every channel count % 32 == 0 and image_size % 16 == 0;
+     otherwise AUTO degrades to TF32 below;
+   SIMT = exact fp32 CUDA-core path with fp64-chunked accumulation (on-device reference);
+   TCGEN05 = single-kernel entry points only: plain kind::tf32 tensor-core kernel or error;
+   TC3X = every operand split into two tf32 parts, three tf32 convs per product (round-1 compensated mode, ~3x conv time);
+   TF32 = round-1 default: kind::tf32 forward and backward (scalars 1e-4..2e-3 from the reference), SIMT where the shape
+     is not tensor-core eligible */
+enum { SIVAE_CONV_AUTO = 0, SIVAE_CONV_SIMT = 1, SIVAE_CONV_TCGEN05 = 2, SIVAE_CONV_TC3X = 3, SIVAE_CONV_TF32 = 4 };
 enum { SIVAE_T_CONV = 0, SIVAE_T_BN_WEIGHT = 1, SIVAE_T_BN_BIAS = 2, SIVAE_T_LINEAR = 3, SIVAE_T_BIAS = 4 };
 
 /* SoftIntroVAE(cdim, zdim, channels, image_size) -- ctor :173-184; Encoder :79-109; Decoder :126-159 */
@@ -174,11 +182,6 @@ int sivae_mse3(const float* real, const float* rec, const float* rec_rec, const 
 int sivae_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int batch, int zdim, void* stream);
 int sivae_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,
                     long long step, void* stream);
-/* EXPERIMENTAL (round-2 groundwork, not used by any step entry point): the 3x3 conv forward with fp16 operands on the
-   CTA-pair tcgen05 kernel -- x: NHWC half [N,H,W,Cin], w: half [Cout,3,3,Cin], addend (nullable) / y: NHWC fp32.
-   Returns -8 unless k == 3, Cin % 64 == 0 and the shape tiles onto CTA pairs. */
-int sivae_conv2d_fwd_f16(const void* x_half_nhwc, const void* w_half_packed, const float* addend, float* y_nhwc, int N,
-                         int H, int W, int Cin, int Cout, int k, void* stream);
 /* nn.Linear (encoder fc :109,:121; decoder fc + ReLU :145-148,:166-167): y[B,O] = x[B,F] . w[O,F]^T + b (relu != 0: then
    ReLU), and its input gradient dx[B,F] = dy[B,O] . w[O,F] (workspace: sivae_linear_dgrad_workspace_bytes) */
 int sivae_linear_fwd(const float* x, const float* w, const float* b, float* y, int batch, int in_features, int out_features,

@@ -16,6 +16,7 @@
 // mbarriers; tcgen05.commit releases slots and signals the epilogue.
 // Operands are expected to be pre-rounded to TF32 by their producers (the tensor core truncates fp32 -> tf32).
 #include "kernels.h"
+#include "split32.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -53,30 +54,6 @@ static int make_map_nhwc(CUtensorMap* m, const float* base, int N, int H, int W,
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -102;
-}
-// fp16 operand tensors (round-2 groundwork): NHWC half [N][H][W][C] -> box {64, bw, bh, bn}; a
-// 128-byte swizzle row then holds 64 channels instead of 32, every byte offset inside the staged tiles stays what it is
-static int make_map_nhwc_f16(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
-  EncodeTiledFn f = encode_fn();
-  if (!f) return -101;
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -102;
-}
-static int make_map_2d_f16(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
-  EncodeTiledFn f = encode_fn();
-  if (!f) return -101;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -102;
 }
 static int make_store_map(CUtensorMap* m, float* base, int N, int H, int W, int C, int sw, int sh, int sn) {
@@ -468,9 +445,59 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// the same with fp16 A/B operands (format code 0): K = 16 halfs = the same 32 bytes per MMA as 8 tf32 values
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 with bf16 A/B operands (format code 1): K = 16 elements = the same 32 bytes per MMA as 8 tf32 values
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate);
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operand formats of the forward / dgrad kernels (template parameter FMT).  Both formats occupy the SAME bytes: one
+// 128-byte swizzle row = one pixel (or filter row) x 32 channels.
+//   FMT_TF32  : 32 fp32 values, pre-rounded to tf32; 4 MMAs (K = 8) of kind::tf32 per row.
+//   FMT_SPLIT : "split32" = [32 x bf16 hi | 32 x bf16 lo] with hi = bf16(x), lo = bf16(x - hi) (16 significand bits, fp32
+//               exponent range).  Per 16-channel K step three kind::f16 MMAs: lo*hi + hi*lo + hi*hi (the lo*lo term, 2^-18
+//               relative, is dropped): 6 MMAs per row at twice the tf32 issue rate = 1.5x the tf32 tensor time for
+//               fp32-class products.  TMA maps, staging bytes, descriptors' row geometry and epilogues are identical.
+// a_addr / b_addr: shared-memory byte address of the first row of the operand tile (row start, K offset 0).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FMT_TF32 = 0, FMT_SPLIT = 1;
+template <int FMT> __host__ __device__ constexpr uint32_t make_idesc_fmt(int M, int N) {
+  return FMT == FMT_SPLIT ? make_idesc_bf16(M, N, 0, 0) : make_idesc_tf32(M, N, 0, 0);
+}
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset);
+template <int FMT, bool PAIR>
+__device__ __forceinline__ void umma_row(uint32_t tmem_d, uint32_t a_addr, uint32_t a_sbo, uint32_t a_bo, uint32_t b_addr,
+                                         uint32_t idesc, bool fresh) {
+  auto mma = [&](uint32_t ao, uint32_t bo, uint32_t acc) {
+    const uint64_t ad = make_smem_desc_bo(a_addr + ao, a_sbo, a_bo);
+    const uint64_t bd = make_smem_desc_bo(b_addr + bo, 1024, 0);
+    if constexpr (FMT == FMT_SPLIT) {
+      if constexpr (PAIR) umma_f16_2cta(tmem_d, ad, bd, idesc, acc); else umma_f16(tmem_d, ad, bd, idesc, acc);
+    } else {
+      if constexpr (PAIR) umma_tf32_2cta(tmem_d, ad, bd, idesc, acc); else umma_tf32(tmem_d, ad, bd, idesc, acc);
+    }
+  };
+  if constexpr (FMT == FMT_SPLIT) {
+#pragma unroll
+    for (uint32_t kk = 0; kk < 2; ++kk) {
+      mma(64 + kk * 32, kk * 32, (fresh && kk == 0) ? 0u : 1u);      // a_lo * b_hi
+      mma(kk * 32, 64 + kk * 32, 1u);                               // a_hi * b_lo
+      mma(kk * 32, kk * 32, 1u);                                    // a_hi * b_hi
+    }
+  } else {
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) mma(k * 32, k * 32, (fresh && k == 0) ? 0u : 1u);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -670,7 +697,7 @@ struct Fwd2Smem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4 + 4 * EPI_NBUF) * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int FMT>
 __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__ CUtensorMap map_x,
                                                          const __grid_constant__ CUtensorMap map_w,
                                                          const __grid_constant__ CUtensorMap map_y,
@@ -729,7 +756,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
     }
   } else if (warp == 1) {
     if (elect_one()) {               // one thread runs the whole issue loop (see k_conv_halo)
-      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = make_idesc_fmt<FMT>(128, BLOCK_N);
       int it = 0, lt = 0;                                    // lt = local tile counter
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const int acc = lt & 1;
@@ -744,12 +771,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
           mbar_wait(&full[st], ph);
           const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
           const uint32_t sb = sa + TC_A_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
-            uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-            umma_tf32(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          umma_row<FMT, false>(tmem_d, sa, 1024, 0, sb, idesc, kb == kb0);
           umma_commit(&empty[st]);
           if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
         }
@@ -813,13 +835,13 @@ static int num_sms() {
   }
   return n;
 }
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int FMT>
 static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& madd,
                          const FwdParams& p, int m_tiles, cudaStream_t st) {
   using SM = Fwd2Smem<BLOCK_N, STAGES>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_fwd_tc2<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_fwd_tc2<BLOCK_N, STAGES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -827,7 +849,7 @@ static int launch_fwd2_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUt
   const int total = m_tiles * n_tiles * p.ksplit;
   const int grid = total < num_sms() ? total : num_sms();
   g_launches += 1;
-  k_conv_fwd_tc2<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p, n_tiles, total);
+  k_conv_fwd_tc2<BLOCK_N, STAGES, FMT><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p, n_tiles, total);
   return (int)cudaGetLastError();
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -913,7 +935,7 @@ struct HaloSmem {
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW, int FMT>
 __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CUtensorMap map_x,
                                                       const __grid_constant__ CUtensorMap map_w,
                                                       const __grid_constant__ CUtensorMap map_y,
@@ -981,7 +1003,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
     // ONE elected thread runs the whole issue loop (barrier waits included): no warp-wide election / re-convergence per
     // filter tap between the MMAs
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = make_idesc_fmt<FMT>(128, BLOCK_N);
       int ai = 0, bi = 0, lt = 0;
       for (int item = blockIdx.x; item < p.total; item += gridDim.x, ++lt) {
         const int acc = lt & 1;
@@ -1002,12 +1024,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
 #pragma unroll
             for (int t = 0; t < T; ++t) {
               const uint32_t arow = sa + (uint32_t)(t * SM::BOX_BYTES + (r * BW + s) * 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint64_t ad = make_smem_desc_bo(arow + k * 32, BW * 128, bo);
-                uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-                umma_tf32(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              }
+              umma_row<FMT, false>(tmem_d + (uint32_t)(t * BLOCK_N), arow, BW * 128, bo, sb, idesc, ch == 0 && tap == 0);
             }
             umma_commit(&b_empty[bst]);
             if (tap == TAPS - 1) {
@@ -1094,14 +1111,14 @@ static int halo_mode() {
 static bool halo_supported(const ConvShape& s) {
   return (s.k == 3 || s.k == 5) && s.Cin % 32 == 0 && s.Cout >= 1 && s.W % 8 == 0 && s.H % 16 == 0;
 }
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
-static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW, int FMT>
+static int launch_halo_f(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                          float* stats, cudaStream_t st) {
   using SM = HaloSmem<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -1131,8 +1148,15 @@ static int launch_halo_t(const float* x, const float* w, const float* bias, cons
   }
   const int grid = p.total < num_sms() ? p.total : num_sms();
   g_launches += 1;
-  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
+  k_conv_halo<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT><<<grid, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
   return (int)cudaGetLastError();
+}
+// fmt: FMT_TF32 (x, w fp32 pre-rounded to tf32) or FMT_SPLIT (x, w in the split32 format, same bytes)
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
+static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                         float* stats, cudaStream_t st, int fmt) {
+  if (fmt == FMT_SPLIT) return launch_halo_f<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT_SPLIT>(x, w, bias, addend, y, s, stats, st);
+  return launch_halo_f<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT_TF32>(x, w, bias, addend, y, s, stats, st);
 }
 // ---------------------------------------------------------------------------------------------------------------
 // forward / dgrad kernel v4 (3x3, Cout >= 128): CTA PAIR, tcgen05.mma.cta_group::2, M = 256.
@@ -1220,9 +1244,7 @@ struct Halo2Smem {
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * T * BLOCK_N;
 };
-// F16 (round-2 groundwork, not dispatched by the engine yet): A / B operands are fp16 tensors -- 64 channels per 128-byte chunk,
-// tcgen05.mma.kind::f16 -- everything else (staging bytes, descriptors, fp32 accumulators and epilogue) is unchanged
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, bool F16 = false>
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     k_conv_halo2(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_add, const HaloParams p) {
@@ -1242,7 +1264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  constexpr int CSH = F16 ? 6 : 5;          // log2(channels per 128-byte chunk)
+  constexpr int CSH = 5;                    // log2(channels per 128-byte chunk), both operand formats
   const int cchunks = p.Cin >> CSH;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
@@ -1294,7 +1316,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     }
   } else if (warp == 1) {
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = F16 ? make_idesc_f16(256, BLOCK_N, 0, 0) : make_idesc_tf32(256, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc = make_idesc_fmt<FMT>(256, BLOCK_N);
       int ai = 0, bi = 0, lt = 0;
       for (int item = cluster_id; item < p.total; item += nclusters, ++lt) {
         const int acc = lt & 1;
@@ -1314,13 +1336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 #pragma unroll
             for (int t = 0; t < T; ++t) {
               const uint32_t arow = sa + (uint32_t)(t * SM::BOX_BYTES + (r * SM::BW + s) * 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                uint64_t ad = make_smem_desc_bo(arow + k * 32, SM::BW * 128, 0);
-                uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-                if constexpr (F16) umma_f16_2cta(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                else umma_tf32_2cta(tmem_d + (uint32_t)(t * BLOCK_N), ad, bd, idesc, (ch > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              }
+              umma_row<FMT, true>(tmem_d + (uint32_t)(t * BLOCK_N), arow, SM::BW * 128, 0, sb, idesc, ch == 0 && tap == 0);
             }
             umma_commit_2cta(&b_empty[bst]);
             if (tap == TAPS - 1) {
@@ -1407,15 +1423,15 @@ static bool halo2_eligible(const ConvShape& s) {
   return two_cta_mode() != 0 && s.k == 3 && s.Cin % 32 == 0 && s.Cout >= min_cout && (s.Cout & 3) == 0 && s.W % 8 == 0 && s.H % 16 == 0 &&
          tiles % (s.Cout >= 256 ? 2 : 4) == 0 && tma_store_enabled();
 }
-template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, bool F16 = false>
-static int launch_halo2_t(const void* x, const void* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int FMT>
+static int launch_halo2_f(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                           float* stats, cudaStream_t st) {
   using SM = Halo2Smem<BLOCK_N, T, A_STAGES, B_STAGES>;
   static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
   static_assert(SM::TMEM_COLS <= 512, "TMEM budget exceeded");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
@@ -1429,11 +1445,9 @@ static int launch_halo2_t(const void* x, const void* w, const float* bias, const
   p.tma_store = 1 | (addend_mode() << 4) | (fast_epi() << 12);
   p.stats = stats;
   CUtensorMap mx, mw, my;
-  int r = F16 ? make_map_nhwc_f16(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1)
-              : make_map_nhwc(&mx, static_cast<const float*>(x), s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
   if (r) return r;
-  r = F16 ? make_map_2d_f16(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2)
-          : make_map_2d(&mw, static_cast<const float*>(w), s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
+  r = make_map_2d(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
   if (r) return r;
   r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
   if (r) return r;
@@ -1445,34 +1459,30 @@ static int launch_halo2_t(const void* x, const void* w, const float* bias, const
   int nclusters = num_sms() / 2;
   if (p.total < nclusters) nclusters = p.total;
   g_launches += 1;
-  k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES, F16><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
+  k_conv_halo2<BLOCK_N, T, A_STAGES, B_STAGES, FMT><<<2 * nclusters, 192, SM::TOTAL, st>>>(mx, mw, my, madd, p);
   return (int)cudaGetLastError();
 }
-static int launch_halo2(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                        float* stats, cudaStream_t st) {
-  if (s.Cout >= 256) return launch_halo2_t<256, 1, 3, 6>(x, w, bias, addend, y, s, stats, st);
-  if (s.Cout > 64) return launch_halo2_t<128, 2, 2, 8>(x, w, bias, addend, y, s, stats, st);
-  return launch_halo2_t<64, 2, 3, 8>(x, w, bias, addend, y, s, stats, st);
+template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
+static int launch_halo2_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                          float* stats, cudaStream_t st, int fmt) {
+  if (fmt == FMT_SPLIT) return launch_halo2_f<BLOCK_N, T, A_STAGES, B_STAGES, FMT_SPLIT>(x, w, bias, addend, y, s, stats, st);
+  return launch_halo2_f<BLOCK_N, T, A_STAGES, B_STAGES, FMT_TF32>(x, w, bias, addend, y, s, stats, st);
 }
-// fp16-operand 3x3 conv on the CTA-pair kernel (x: NHWC half, w: [Cout][3][3][Cin] half, y / addend / statistics fp32).
-// Round-2 groundwork: reachable only through sivae_conv2d_fwd_f16; returns -8 for shapes the pair kernel does not take.
-bool conv_f16_supported(const ConvShape& s) { return halo2_eligible(s) && s.Cin % 64 == 0; }
-int launch_conv_fwd_f16(const void* x, const void* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                        float* stats, cudaStream_t st) {
-  if (!conv_f16_supported(s)) return -8;
-  if (s.Cout >= 256) return launch_halo2_t<256, 1, 3, 6, true>(x, w, bias, addend, y, s, stats, st);
-  if (s.Cout > 64) return launch_halo2_t<128, 2, 2, 8, true>(x, w, bias, addend, y, s, stats, st);
-  return launch_halo2_t<64, 2, 3, 8, true>(x, w, bias, addend, y, s, stats, st);
+static int launch_halo2(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
+                        float* stats, cudaStream_t st, int fmt) {
+  if (s.Cout >= 256) return launch_halo2_t<256, 1, 3, 6>(x, w, bias, addend, y, s, stats, st, fmt);
+  if (s.Cout > 64) return launch_halo2_t<128, 2, 2, 8>(x, w, bias, addend, y, s, stats, st, fmt);
+  return launch_halo2_t<64, 2, 3, 8>(x, w, bias, addend, y, s, stats, st, fmt);
 }
 static int launch_halo(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                       float* stats, cudaStream_t st) {
-  if (halo2_eligible(s)) return launch_halo2(x, w, bias, addend, y, s, stats, st);
+                       float* stats, cudaStream_t st, int fmt) {
+  if (halo2_eligible(s)) return launch_halo2(x, w, bias, addend, y, s, stats, st, fmt);
   const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
   if (s.k == 5) {     // image-facing 5x5 with a narrow output (predict forward, stem dgrad): N tile of 32
-    return two ? launch_halo_t<32, 2, 2, 8, 5, 5>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<32, 1, 3, 8, 5, 5>(x, w, bias, addend, y, s, stats, st);
+    return two ? launch_halo_t<32, 2, 2, 8, 5, 5>(x, w, bias, addend, y, s, stats, st, fmt) : launch_halo_t<32, 1, 3, 8, 5, 5>(x, w, bias, addend, y, s, stats, st, fmt);
   }
-  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 5, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<128, 1, 3, 7, 3, 3>(x, w, bias, addend, y, s, stats, st);
-  return two ? launch_halo_t<64, 2, 3, 6, 3, 3>(x, w, bias, addend, y, s, stats, st) : launch_halo_t<64, 1, 3, 8, 3, 3>(x, w, bias, addend, y, s, stats, st);
+  if (s.Cout > 64) return two ? launch_halo_t<128, 2, 2, 5, 3, 3>(x, w, bias, addend, y, s, stats, st, fmt) : launch_halo_t<128, 1, 3, 7, 3, 3>(x, w, bias, addend, y, s, stats, st, fmt);
+  return two ? launch_halo_t<64, 2, 3, 6, 3, 3>(x, w, bias, addend, y, s, stats, st, fmt) : launch_halo_t<64, 1, 3, 8, 3, 3>(x, w, bias, addend, y, s, stats, st, fmt);
 }
 // ---------------------------------------------------------------------------------------------------------------
 // Row-separable form of the two image-facing 5x5 convolutions (c = cdim <= 3 channels on one side).
@@ -1508,6 +1518,7 @@ __global__ void k_rowsep_expand_rev(const float* __restrict__ x, float* __restri
     *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
+template <bool SPLIT>      // SPLIT: xe in the split32 format (forward operand), unrounded source values
 __global__ void k_rowsep_expand(const float* __restrict__ x, float* __restrict__ xe, long long rows, int W, int c) {
   // one thread per (pixel, channel quad): 8 threads cover the 32 expanded channels of a pixel
   const long long total = rows * W * 8;
@@ -1525,11 +1536,12 @@ __global__ void k_rowsep_expand(const float* __restrict__ x, float* __restrict__
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = j0 + e;
-        v[e] = (q * 4 + e < 5 * c && j >= 0 && j < rowlen) ? rs_tf32(__ldg(src + j)) : 0.f;
+        v[e] = (q * 4 + e < 5 * c && j >= 0 && j < rowlen) ? (SPLIT ? __ldg(src + j) : rs_tf32(__ldg(src + j))) : 0.f;
       }
       o = make_float4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = o;
+    if (SPLIT) split32_store4(xe + pix * 32, (uint32_t)q, o);
+    else *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = o;
   }
 }
 __global__ void k_rowsep_gather(const float* __restrict__ P, const float* __restrict__ bias, const float* __restrict__ addend,
@@ -1554,22 +1566,24 @@ __global__ void k_rowsep_gather(const float* __restrict__ P, const float* __rest
   }
 }
 // F[Co][5][5][c] -> We[Co][5][32] (tf32-rounded, zero padded)
-__global__ void k_rowsep_filter_expand(const float* __restrict__ f, float* __restrict__ out, int Co, int c) {
+__global__ void k_rowsep_filter_expand(const float* __restrict__ f, float* __restrict__ out, int Co, int c, int rnd) {
   const int total = Co * 5 * 32;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int j = i & 31, cr = i >> 5;
-    out[i] = j < 5 * c ? rs_tf32(f[(long long)cr * 5 * c + j]) : 0.f;
+    const float v = j < 5 * c ? f[(long long)cr * 5 * c + j] : 0.f;
+    out[i] = rnd ? rs_tf32(v) : v;
   }
 }
 // F[c][5][5][Ci] -> Wg[16][5][Ci]: row s*c+co, (tf32-rounded, unused rows zero)
-__global__ void k_rowsep_filter_gather(const float* __restrict__ f, float* __restrict__ out, int c, int Ci) {
+__global__ void k_rowsep_filter_gather(const float* __restrict__ f, float* __restrict__ out, int c, int Ci, int rnd) {
   const int total = 16 * 5 * Ci;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ci = i % Ci, r = (i / Ci) % 5, row = i / (5 * Ci);
     float v = 0.f;
     if (row < 5 * c) {
       const int s = row / c, co = row - s * c;
-      v = rs_tf32(f[(((long long)co * 5 + r) * 5 + s) * Ci + ci]);
+      v = f[(((long long)co * 5 + r) * 5 + s) * Ci + ci];
+      if (rnd) v = rs_tf32(v);
     }
     out[i] = v;
   }
@@ -1590,32 +1604,33 @@ bool conv_rowsep_out_supported(const ConvShape& s) {
 }
 long long conv_rowsep_scratch_floats(const ConvShape& s) { return (long long)s.N * s.H * s.W * 32; }
 long long conv_rowsep_filter_floats(const ConvShape& s) { return s.Cin <= 3 ? (long long)s.Cout * 160 : (long long)80 * s.Cin; }
-void launch_rowsep_filter_expand(const float* f, float* out, int Co, int c, cudaStream_t st) {
+void launch_rowsep_filter_expand(const float* f, float* out, int Co, int c, cudaStream_t st, bool round_tf32) {
   g_launches += 1;
-  k_rowsep_filter_expand<<<(Co * 160 + 255) / 256, 256, 0, st>>>(f, out, Co, c);
+  k_rowsep_filter_expand<<<(Co * 160 + 255) / 256, 256, 0, st>>>(f, out, Co, c, round_tf32 ? 1 : 0);
 }
-void launch_rowsep_filter_gather(const float* f, float* out, int c, int Ci, cudaStream_t st) {
+void launch_rowsep_filter_gather(const float* f, float* out, int c, int Ci, cudaStream_t st, bool round_tf32) {
   g_launches += 1;
-  k_rowsep_filter_gather<<<(80 * Ci + 255) / 256, 256, 0, st>>>(f, out, c, Ci);
+  k_rowsep_filter_gather<<<(80 * Ci + 255) / 256, 256, 0, st>>>(f, out, c, Ci, round_tf32 ? 1 : 0);
 }
 // y[N,H,W,Cout] = conv5x5(x[N,H,W,c], F) (+bias)(+addend); we = expanded filter; scratch >= N*H*W*32 floats
 int launch_conv_rowsep_in(const float* x, const float* we, const float* bias, const float* addend, float* y, const ConvShape& s,
-                          float* scratch, float* stats, cudaStream_t st) {
+                          float* scratch, float* stats, cudaStream_t st, int fmt) {
   const long long rows = (long long)s.N * s.H;
   g_launches += 1;
-  k_rowsep_expand<<<num_sms() * 8, 256, 0, st>>>(x, scratch, rows, s.W, s.Cin);
+  if (fmt == FMT_SPLIT) k_rowsep_expand<true><<<num_sms() * 8, 256, 0, st>>>(x, scratch, rows, s.W, s.Cin);
+  else k_rowsep_expand<false><<<num_sms() * 8, 256, 0, st>>>(x, scratch, rows, s.W, s.Cin);
   ConvShape e{s.N, s.H, s.W, 32, s.Cout, 5};
   const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
-  if (two) return launch_halo_t<64, 2, 2, 6, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
-  return launch_halo_t<64, 1, 3, 8, 5, 1>(scratch, we, bias, addend, y, e, stats, st);
+  if (two) return launch_halo_t<64, 2, 2, 6, 5, 1>(scratch, we, bias, addend, y, e, stats, st, fmt);
+  return launch_halo_t<64, 1, 3, 8, 5, 1>(scratch, we, bias, addend, y, e, stats, st, fmt);
 }
 // y[N,H,W,c] = conv5x5(x[N,H,W,Cin], F) (+bias)(+addend); wg = gather-form filter; scratch >= N*H*W*16 floats
 int launch_conv_rowsep_out(const float* x, const float* wg, const float* bias, const float* addend, float* y, const ConvShape& s,
-                           float* scratch, cudaStream_t st) {
+                           float* scratch, cudaStream_t st, int fmt) {
   ConvShape e{s.N, s.H, s.W, s.Cin, 16, 5};
   const bool two = (((long long)s.N * (s.H / 16) * (s.W / 8)) % 2 == 0);
-  int r = two ? launch_halo_t<32, 2, 2, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st)
-                          : launch_halo_t<32, 1, 3, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st);
+  int r = two ? launch_halo_t<32, 2, 2, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st, fmt)
+                          : launch_halo_t<32, 1, 3, 8, 5, 1>(x, wg, nullptr, nullptr, scratch, e, nullptr, st, fmt);
   if (r) return r;
   g_launches += 1;
   k_rowsep_gather<<<num_sms() * 8, 256, 0, st>>>(scratch, bias, addend, y, (long long)s.N * s.H, s.W, s.Cout);
@@ -1711,7 +1726,7 @@ size_t conv_tc_splitk_scratch_bytes(const ConvShape& s) {
   return pl.ksplit > 1 ? (size_t)pl.ksplit * pl.npad * s.H * s.W * s.Cout * sizeof(float) : 0;
 }
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                       cudaStream_t st, float* stats, void* scratch, size_t scratch_bytes) {
+                       cudaStream_t st, float* stats, void* scratch, size_t scratch_bytes, int fmt) {
   FwdParams p;
   p.ksplit = 1; p.kb_per = s.k * s.k * (s.Cin / 32); p.npad = 0;
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
@@ -1721,11 +1736,12 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   p.sbh = p.sbn = 1; p.tma_store = 0; p.stats = nullptr;
   const int tiles_n = (s.N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
-  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_eligible(s)) return launch_halo(x, w, bias, addend, y, s, stats, st);
+  if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_eligible(s)) return launch_halo(x, w, bias, addend, y, s, stats, st, fmt);
   CUtensorMap mx, mw;
   int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
   if (r) return r;
   if (fwd_kernel_version() == 1) {
+    if (fmt != FMT_TF32) return -9;             // the first-generation kernel (SIVAE_TC_FWD=1, experiments only) is tf32-only
     const int block_n = s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32);
     r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
     if (r) return r;
@@ -1761,10 +1777,17 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
     r = make_store_map(&madd, (float*)p.addend, s.N, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
     if (r) return r;
   }
-  if (block_n == 256) r = launch_fwd2_t<256, 4>(mx, mw, my, madd, p, m_tiles, st);
-  else if (block_n == 128) r = launch_fwd2_t<128, 5>(mx, mw, my, madd, p, m_tiles, st);
-  else if (block_n == 64) r = launch_fwd2_t<64, 7>(mx, mw, my, madd, p, m_tiles, st);
-  else r = launch_fwd2_t<32, 8>(mx, mw, my, madd, p, m_tiles, st);
+  if (fmt == FMT_SPLIT) {
+    if (block_n == 256) r = launch_fwd2_t<256, 4, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
+    else if (block_n == 128) r = launch_fwd2_t<128, 5, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
+    else if (block_n == 64) r = launch_fwd2_t<64, 7, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
+    else r = launch_fwd2_t<32, 8, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
+  } else {
+    if (block_n == 256) r = launch_fwd2_t<256, 4, FMT_TF32>(mx, mw, my, madd, p, m_tiles, st);
+    else if (block_n == 128) r = launch_fwd2_t<128, 5, FMT_TF32>(mx, mw, my, madd, p, m_tiles, st);
+    else if (block_n == 64) r = launch_fwd2_t<64, 7, FMT_TF32>(mx, mw, my, madd, p, m_tiles, st);
+    else r = launch_fwd2_t<32, 8, FMT_TF32>(mx, mw, my, madd, p, m_tiles, st);
+  }
   if (r || pl.ksplit <= 1) return r;
   const long long n4 = (long long)s.N * s.H * s.W * s.Cout / 4, slab4 = (long long)pl.npad * s.H * s.W * s.Cout / 4;
   unsigned blocks = (unsigned)((n4 + 255) / 256);
@@ -2280,7 +2303,7 @@ int launch_conv_rowsep_wgrad(const float* narrow_t, const float* wide_t, float* 
   if (scratch_bytes < (size_t)pl.splits * wide * 160 * sizeof(float)) return -103;
   const long long rows = (long long)N * H;
   g_launches += 2;
-  if (mode == 1) k_rowsep_expand<<<num_sms() * 8, 256, 0, st>>>(narrow_t, expand_scratch, rows, W, c);
+  if (mode == 1) k_rowsep_expand<false><<<num_sms() * 8, 256, 0, st>>>(narrow_t, expand_scratch, rows, W, c);
   else k_rowsep_expand_rev<<<num_sms() * 8, 256, 0, st>>>(narrow_t, expand_scratch, rows, W, c);
   ConvShape e{N, H, W, 32, wide, 5};
   int r = launch_wg2_t<64, 1, 4, 5, 1>(expand_scratch, wide_t, e, pl, (float*)scratch, st);

@@ -57,16 +57,20 @@ struct Net {
   bool present = false;
 };
 
+// a1s / outs / xs (split-forward mode): the split32 copies (split32.cuh) of a1 / out / the block input that the FORWARD convs
+// consume; the fp32 tensors of the same name are the tf32-rounded wgrad operands, written only in passes whose net gets
+// parameter gradients
 struct BlockAct { float *id = nullptr, *t1 = nullptr, *a1 = nullptr, *t2 = nullptr, *out = nullptr, *mi1 = nullptr, *mi2 = nullptr; const float* x = nullptr;
+                  float *a1s = nullptr, *outs = nullptr; const float* xs = nullptr;
                   unsigned char* m2 = nullptr;   /* sign bytes of the block's final pre-activation (one per float4 of t2) */ };
 struct EncPass {
   const float* img = nullptr;
-  float *t0 = nullptr, *mi0 = nullptr, *a0 = nullptr, *feat = nullptr, *ml = nullptr, *z = nullptr, *kl = nullptr;
+  float *t0 = nullptr, *mi0 = nullptr, *a0 = nullptr, *a0s = nullptr, *feat = nullptr, *ml = nullptr, *z = nullptr, *kl = nullptr;
   std::vector<BlockAct> blk;
 };
 struct DecPass {
   const float* zin = nullptr;
-  float *h = nullptr, *x0 = nullptr, *y = nullptr;
+  float *h = nullptr, *x0 = nullptr, *x0s = nullptr, *y = nullptr;
   double* ema = nullptr;           // EMA inputs (batch mean | unbiased var) of every BN of the pass, in the net's BN buffer layout
   const void* net = nullptr;       // the weight set the slot's activations were computed with (pass re-use check)
   std::vector<BlockAct> blk;
@@ -93,6 +97,9 @@ struct sivae_engine {
   bool fast = false;               // cdim-facing narrow CUDA-core kernels in use (false: generic exact SIMT everywhere)
   bool comp = false;               // compensated tensor-core mode (SIVAE_CONV_TC3X): 3 tf32 MMAs per product on split operands
   bool rnd = false;                // producers round stored activations / gradients to tf32 (plain tensor-core mode only)
+  bool fsplit = false;             // default tensor-core mode: FORWARD convs consume split32 operands (bf16 hi + lo, three
+                                   // kind::f16 MMAs per product: fp32-class products, ELBO / KL within 1e-4 of the reference);
+                                   // dgrad / wgrad stay kind::tf32 on the tf32-rounded fp32 tensors
   bool bn_mask = true;             // residual BN+LeakyReLU forward stores sign bytes so its backward skips the identity re-read (SIVAE_BN_MASK=0: off)
   float* split[4] = {nullptr, nullptr, nullptr, nullptr};   // comp: hi / lo parts of the two conv operands, max activation size each
   // workspace
@@ -288,6 +295,7 @@ static size_t carve(sivae_engine* e, char* base) {
     p.t0 = bp.take<float>(B * S * S * c.channels[0]);
     p.mi0 = bp.take<float>(2 * c.channels[0]);
     p.a0 = bp.take<float>(B * (S / 2) * (S / 2) * c.channels[0]);
+    p.a0s = e->fsplit ? bp.take<float>(B * (S / 2) * (S / 2) * c.channels[0]) : nullptr;
     p.blk.assign(en.blocks.size(), BlockAct());
     for (size_t i = 0; i < en.blocks.size(); ++i) {
       const Block& b = en.blocks[i];
@@ -297,6 +305,7 @@ static size_t carve(sivae_engine* e, char* base) {
       if (b.expand) a.id = bp.take<float>(full);
       a.t1 = bp.take<float>(full); a.a1 = bp.take<float>(full); a.t2 = bp.take<float>(full);
       a.out = bp.take<float>(B * os * os * b.outc);
+      if (e->fsplit) { a.a1s = bp.take<float>(full); a.outs = (i + 1 < en.blocks.size()) ? bp.take<float>(B * os * os * b.outc) : nullptr; }
       a.mi1 = bp.take<float>(2 * b.outc); a.mi2 = bp.take<float>(2 * b.outc);
       a.m2 = e->bn_mask ? bp.take<unsigned char>(full / 4) : nullptr;
     }
@@ -309,6 +318,7 @@ static size_t carve(sivae_engine* e, char* base) {
     DecPass& p = e->dp[s];
     p.h = bp.take<float>(B * e->feat);
     p.x0 = bp.take<float>(B * e->feat);
+    p.x0s = e->fsplit ? bp.take<float>(B * e->feat) : nullptr;
     p.blk.assign(dn.blocks.size(), BlockAct());
     for (size_t i = 0; i < dn.blocks.size(); ++i) {
       const Block& b = dn.blocks[i];
@@ -318,6 +328,7 @@ static size_t carve(sivae_engine* e, char* base) {
       if (b.expand) a.id = bp.take<float>(full);
       a.t1 = bp.take<float>(full); a.a1 = bp.take<float>(full); a.t2 = bp.take<float>(full);
       a.out = bp.take<float>(B * os * os * b.outc);
+      if (e->fsplit) { a.a1s = bp.take<float>(full); a.outs = bp.take<float>(B * os * os * b.outc); }
       a.mi1 = bp.take<float>(2 * b.outc); a.mi2 = bp.take<float>(2 * b.outc);
       a.m2 = e->bn_mask ? bp.take<unsigned char>(full / 4) : nullptr;
     }
@@ -358,8 +369,9 @@ static size_t carve(sivae_engine* e, char* base) {
 // -------------------------------------------------------------------------------------------------------------
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
-enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_COUNT = 5,
-       PC_BN_FWD = 5, PC_BN_BWD = 6 };      // classes >= PC_COUNT appear in sivae_profile_dump only (bytes in the flops slot)
+// PC_TC_FWD3 = forward convs on split32 operands (three kind::f16 MMAs per product); PC_TC_FWD = kind::tf32 forward / dgrad
+enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_TC_FWD3 = 5, PC_COUNT = 6,
+       PC_BN_FWD = 6, PC_BN_BWD = 7 };      // classes >= PC_COUNT appear in sivae_profile_dump only (bytes in the flops slot)
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; ConvShape shape; };
 struct Prof {
   bool on = false;
@@ -418,17 +430,23 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
     ConvShape sf{1, size, size, c.cin, c.cout, c.k};
     if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf)) {
       if (e->comp) launch_split_tf32(n.params + c.w_off, n.derived + c.wr_off, n.derived + c.wl_off, wn, st);
+      else if (e->fsplit) launch_split32(n.params + c.w_off, n.derived + c.wr_off, wn, st);     // forward filters: split32
       else launch_round_tf32(n.params + c.w_off, n.derived + c.wr_off, wn, st);
     }
     // narrow (cdim-facing) kernels read the filter transposed to [tap][narrow][wide]
     if (fwd_on_narrow(e, sf)) launch_narrow_transpose(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.k, c.cin, st);
     else if (fwd_on_narrow(e, sd)) launch_narrow_transpose(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.k, c.cout, st);
     // row-separable tensor-core forms of the image-facing 5x5 convs
-    if (fwd_on_rowsep_in(e, sf)) launch_rowsep_filter_expand(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.cin, st);
-    else if (fwd_on_rowsep_in(e, sd)) launch_rowsep_filter_expand(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.cout, st);
+    // (split-forward mode: the forms a FORWARD conv reads are converted to split32 in place; dgrad forms stay tf32)
+    if (fwd_on_rowsep_in(e, sf)) {
+      launch_rowsep_filter_expand(n.params + c.w_off, n.derived + c.wn_off, c.cout, c.cin, st, !e->fsplit);
+      if (e->fsplit) launch_split32(n.derived + c.wn_off, n.derived + c.wn_off, (long long)c.cout * 160, st);
+    } else if (fwd_on_rowsep_in(e, sd)) launch_rowsep_filter_expand(n.derived + c.wd_off, n.derived + c.wn_off, c.cin, c.cout, st);
     if (c.wg_off >= 0) {
-      if (fwd_on_rowsep_out(e, sf)) launch_rowsep_filter_gather(n.params + c.w_off, n.derived + c.wg_off, c.cout, c.cin, st);
-      else if (fwd_on_rowsep_out(e, sd)) launch_rowsep_filter_gather(n.derived + c.wd_off, n.derived + c.wg_off, c.cin, c.cout, st);
+      if (fwd_on_rowsep_out(e, sf)) {
+        launch_rowsep_filter_gather(n.params + c.w_off, n.derived + c.wg_off, c.cout, c.cin, st, !e->fsplit);
+        if (e->fsplit) launch_split32(n.derived + c.wg_off, n.derived + c.wg_off, (long long)80 * c.cin, st);
+      } else if (fwd_on_rowsep_out(e, sd)) launch_rowsep_filter_gather(n.derived + c.wd_off, n.derived + c.wg_off, c.cin, c.cout, st);
     }
   };
   if (n.enc) one(n.stem, e->cfg.image_size); else one(n.predict, e->cfg.image_size);
@@ -438,17 +456,26 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
   return 0;
 }
 // y = conv(x, filt) (+bias) (+addend).  w_master: fp32 filter [Cout][k][k][Cin]; w_tc: its tf32-rounded copy
+// fmt = FMT_SPLIT_ (split-forward mode, forward convs only): x (except the fp32 image of a narrow-input conv), w_tc, w_narrow
+// and w_gather are split32 tensors; only tensor-core kernels can serve such a call
 static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const float* w_master, const float* w_tc,
                     const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr,
-                    const float* w_narrow = nullptr, const float* w_gather = nullptr, const float* w_lo = nullptr) {
+                    const float* w_narrow = nullptr, const float* w_gather = nullptr, const float* w_lo = nullptr,
+                    int fmt = FMT_TF32_) {
+  const int pc_fwd = fmt == FMT_SPLIT_ ? PC_TC_FWD3 : PC_TC_FWD;
   if (fwd_on_rowsep_in(e, s) && w_narrow) {
-    ProfScope ps(PC_TC_FWD, s, st);
-    int r = launch_conv_rowsep_in(x, w_narrow, bias, addend, y, s, e->rs, stats, st);
+    ProfScope ps(pc_fwd, s, st);
+    int r = launch_conv_rowsep_in(x, w_narrow, bias, addend, y, s, e->rs, stats, st, fmt);
     if (r) return fail(r, "row-separable tcgen05 conv launch failed");
   } else if (fwd_on_rowsep_out(e, s) && w_gather) {
-    ProfScope ps(PC_TC_FWD, s, st);
-    int r = launch_conv_rowsep_out(x, w_gather, bias, addend, y, s, e->rs, st);
+    ProfScope ps(pc_fwd, s, st);
+    int r = launch_conv_rowsep_out(x, w_gather, bias, addend, y, s, e->rs, st, fmt);
     if (r) return fail(r, "row-separable tcgen05 conv launch failed");
+  } else if (fmt == FMT_SPLIT_) {
+    if (!fwd_on_tc(e, s)) return fail(-7, "split32 forward conv: shape not served by a tensor-core kernel");
+    ProfScope ps(pc_fwd, s, st);
+    int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats, e->sk, e->sk_bytes, fmt);
+    if (r) return fail(r, "tcgen05 conv launch failed");
   } else if (fwd_on_narrow(e, s) && w_narrow) {
     ProfScope ps(PC_SIMT_FWD, s, st);
     launch_conv_narrow_in_fwd(x, w_narrow, bias, addend, y, s, st);
@@ -477,7 +504,8 @@ static int conv_fwd(sivae_engine* e, Net& n, const Conv& c, const float* x, floa
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   const float* bias = c.b_off >= 0 ? n.params + c.b_off : nullptr;
   return conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, bias, addend, y, st, nullptr, n.derived + c.wn_off,
-                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr);
+                  c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr,
+                  e->fsplit ? FMT_SPLIT_ : FMT_TF32_);
 }
 // t = conv(x, W) followed by the BatchNorm batch statistics of t (train) or the running statistics (eval).  On the tensor
 // core path the statistics come out of the conv epilogue (no second pass over t).
@@ -489,7 +517,8 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
   if (parts > 0 && bn_parts_scratch_bytes(parts, c.cout) > e->red_bytes) parts = 0;
   float* sp = parts > 0 ? (float*)e->red : nullptr;
   TRY(conv_any(e, s, x, n.params + c.w_off, n.derived + c.wr_off, nullptr, nullptr, t, st, sp, n.derived + c.wn_off,
-               c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr));
+               c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wl_off >= 0 ? n.derived + c.wl_off : nullptr,
+               e->fsplit ? FMT_SPLIT_ : FMT_TF32_));
   if (parts > 0)
     launch_bn_stats_from_parts(sp, parts, rows, bn.c, mi, n.bn + bn.rm_off, n.bn + bn.rm_off + bn.c, n.nbt + bn.idx, st,
                                ema ? ema + bn.rm_off : nullptr);
@@ -550,33 +579,45 @@ static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, co
 // -------------------------------------------------------------------------------------------------------------
 
 // ResidualBlock.forward (:65-75) + the AvgPool2d / Upsample that follows it in `main` (:98,155)
-static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* x, int B, bool train, cudaStream_t st,
-                         double* ema = nullptr) {
-  a.x = x;
+// x: the fp32 block input (wgrad operand; unused by the forward in split-forward mode), xs: its split32 copy (split-forward
+// mode).  keep: this pass will run wgrad, so the fp32 tf32-rounded copies of a1 / out are written next to the split32 ones.
+static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* x, const float* xs, int B, bool train,
+                         bool keep, cudaStream_t st, double* ema = nullptr) {
+  a.x = x; a.xs = xs;
   const int s = b.size;
-  const float* idn = x;
-  if (b.expand) { TRY(conv_fwd(e, n, b.ce, x, a.id, nullptr, B, s, st)); idn = a.id; }
-  TRY(conv_bn_stats(e, n, b.c1, b.bn1, x, a.t1, a.mi1, B, s, train, st, ema));
-  { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0, st);
-    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, a.a1, B, s, s, b.outc, RS_NONE, e->rnd, st); }
-  TRY(conv_bn_stats(e, n, b.c2, b.bn2, a.a1, a.t2, a.mi2, B, s, train, st, ema));
-  { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode), st);
-    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, a.out, B, s, s, b.outc, b.mode, e->rnd, st, a.m2); }
+  const bool sp = e->fsplit;
+  const float* xin = sp ? xs : x;            // what the forward convs read
+  const float* idn = xin;
+  if (b.expand) { TRY(conv_fwd(e, n, b.ce, xin, a.id, nullptr, B, s, st)); idn = a.id; }
+  TRY(conv_bn_stats(e, n, b.c1, b.bn1, xin, a.t1, a.mi1, B, s, train, st, ema));
+  { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0 + ((sp && keep) ? 1.0 : 0.0), st);
+    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, (sp && !keep) ? nullptr : a.a1, B, s, s,
+                      b.outc, RS_NONE, e->rnd, st, nullptr, sp ? a.a1s : nullptr); }
+  TRY(conv_bn_stats(e, n, b.c2, b.bn2, sp ? a.a1s : a.a1, a.t2, a.mi2, B, s, train, st, ema));
+  // the fp32 `out` is needed by the next conv's wgrad (keep) or, without a split32 twin (last encoder block), by the fc layer
+  const bool f32_out = !sp || keep || !a.outs;
+  { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode) * ((sp && a.outs && f32_out) ? 2.0 : 1.0), st);
+    launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, f32_out ? a.out : nullptr, B, s, s, b.outc,
+                      b.mode, (sp && !a.outs) ? false : e->rnd, st, a.m2, sp ? a.outs : nullptr, sp && !b.expand); }
   return 0;
 }
 
 // Encoder.forward (:116-122): img is NHWC [B,S,S,cdim]; result p.ml = [B,2z] (mu | logvar)
-static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, int B, bool train, cudaStream_t st) {
+// keep: the pass will be followed by a backward WITH parameter gradients (see block_forward)
+static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, int B, bool train, bool keep, cudaStream_t st) {
   const sivae_config& c = e->cfg;
   const int S = c.image_size;
+  const bool sp = e->fsplit;
   p.img = img;
   TRY(conv_bn_stats(e, n, n.stem, n.stem_bn, img, p.t0, p.mi0, B, S, train, st));
-  { ProfElem pe(PC_BN_FWD, B, S, n.stem.cout, RS_POOL, 1.25, st);
-    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, p.a0, B, S, S, n.stem.cout, RS_POOL, e->rnd, st); }
+  { ProfElem pe(PC_BN_FWD, B, S, n.stem.cout, RS_POOL, 1.25 + ((sp && keep) ? 0.25 : 0.0), st);
+    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, (sp && !keep) ? nullptr : p.a0, B, S, S,
+                      n.stem.cout, RS_POOL, e->rnd, st, nullptr, sp ? p.a0s : nullptr); }
   const float* x = p.a0;
+  const float* xs = p.a0s;
   for (size_t i = 0; i < n.blocks.size(); ++i) {
-    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st));
-    x = p.blk[i].out;
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, xs, B, train, keep, st));
+    x = p.blk[i].out; xs = p.blk[i].outs;
   }
   // .view(B, -1) of the NCHW tensor (:117)
   launch_nhwc_to_nchw(x, p.feat, B, e->C_last, e->hw_last, e->hw_last, st);
@@ -586,19 +627,21 @@ static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, in
 }
 
 // Decoder.forward (:161-169): z [B,zdim] -> p.y NHWC [B,S,S,cdim]
-static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int B, bool train, cudaStream_t st) {
+static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int B, bool train, bool keep, cudaStream_t st) {
   const sivae_config& c = e->cfg;
   p.zin = z;
   launch_linear_fwd(z, n.params + n.fc.w_off, n.params + n.fc.b_off, p.h, B, n.fc.fin, n.fc.fout, true, st);
   launch_nchw_to_nhwc(p.h, p.x0, B, e->C_last, e->hw_last, e->hw_last, st);
+  if (e->fsplit) launch_split32(p.x0, p.x0s, (long long)B * e->feat, st);       // from the unrounded values
   if (e->rnd) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
   const float* x = p.x0;
-  p.net = train ? &n : nullptr;
+  const float* xs = p.x0s;
+  p.net = (train && (keep || !e->fsplit)) ? &n : nullptr;       // pass re-use needs the wgrad operands of this pass
   for (size_t i = 0; i < n.blocks.size(); ++i) {
-    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, B, train, st, train ? p.ema : nullptr));
-    x = p.blk[i].out;
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, xs, B, train, keep, st, train ? p.ema : nullptr));
+    x = p.blk[i].out; xs = p.blk[i].outs;
   }
-  TRY(conv_fwd(e, n, n.predict, x, p.y, nullptr, B, c.image_size, st));
+  TRY(conv_fwd(e, n, n.predict, e->fsplit ? xs : x, p.y, nullptr, B, c.image_size, st));
   CHECK_CUDA_RET();
   return 0;
 }
@@ -702,7 +745,7 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   for (int i = 0; i < cfg->n_channels; ++i)
     if (cfg->channels[i] < 4 || cfg->channels[i] % 4 != 0 || cfg->channels[i] > 1024) return fail(-2, "channels must be multiples of 4 in [4,1024]");
   if ((cfg->cdim * S * S) % 4 != 0) return fail(-2, "cdim*image_size^2 must be a multiple of 4");
-  if (cfg->conv_backend < SIVAE_CONV_AUTO || cfg->conv_backend > SIVAE_CONV_TC3X) return fail(-2, "bad conv_backend");
+  if (cfg->conv_backend < SIVAE_CONV_AUTO || cfg->conv_backend > SIVAE_CONV_TF32) return fail(-2, "bad conv_backend");
   sivae_engine* e = new sivae_engine();
   e->cfg = *cfg;
   e->comp = cfg->conv_backend == SIVAE_CONV_TC3X;
@@ -715,6 +758,23 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   e->tc = cfg->conv_backend != SIVAE_CONV_SIMT;
   e->fast = cfg->conv_backend != SIVAE_CONV_SIMT;
   e->rnd = e->tc && !e->comp;
+  // split-forward mode (the default): every forward conv must be served by a tensor-core kernel -- stem / predict by the
+  // row-separable form, the blocks by the implicit-GEMM kernels -- and every activation must have whole 32-channel groups
+  e->fsplit = cfg->conv_backend == SIVAE_CONV_AUTO;
+  { const char* v = getenv("SIVAE_FWD_SPLIT"); if (v && v[0] == '0') e->fsplit = false; }
+  if (e->fsplit) {
+    e->rs = (float*)1;                       // fwd_on_rowsep_* test for "scratch present"; carve() sets the real pointer
+    bool ok = fwd_on_rowsep_in(e, ConvShape{1, S, S, cfg->cdim, cfg->channels[0], 5}) &&
+              fwd_on_rowsep_out(e, ConvShape{1, S, S, cfg->channels[0], cfg->cdim, 5});
+    for (int ni = 0; ni < 2 && ok; ++ni)
+      for (const Block& b : e->nets[ni].blocks) {
+        ok = ok && b.inc % 32 == 0 && b.outc % 32 == 0 && fwd_on_tc(e, ConvShape{1, b.size, b.size, b.inc, b.outc, 3}) &&
+             fwd_on_tc(e, ConvShape{1, b.size, b.size, b.outc, b.outc, 3});
+      }
+    e->rs = nullptr;
+    e->fsplit = ok;
+  }
+  if (e->fsplit) e->bn_mask = true;          // the backward must not need the fp32 identity tensor (absent in dgrad-only passes)
   e->ws_need = carve(e, nullptr);
   *out = e;
   return 0;
@@ -812,16 +872,19 @@ extern "C" int sivae_e_step(sivae_engine* e, const float* real_nchw, const float
   EncPass &E1 = e->ep[0], &E2 = e->ep[1], &E3 = e->ep[2];
   DecPass &D1 = e->dp[0], &D2 = e->dp[1], &D3 = e->dp[2], &D4 = e->dp[3];
   // forwards in the reference's per-net order (BN running stats are order dependent): :557-568
-  TRY(dec_forward(e, dn, D1, e->noise, B, true, st));                 // fake
-  TRY(enc_forward(e, en, E1, e->real, B, true, st));
+  // (keep flags: the encoder passes get parameter gradients in this half; the decoder passes are dgrad-only -- unless the D
+  // half is going to re-use D1 / D2, whose wgrad operands must then exist)
+  const bool kd = e->reuse_dec;
+  TRY(dec_forward(e, dn, D1, e->noise, B, true, kd, st));             // fake
+  TRY(enc_forward(e, en, E1, e->real, B, true, true, st));
   launch_kl_reparam(E1.ml, eps1, e->z_keep, E1.kl, B, z, st);          // z (kept for the D half, :598)
-  TRY(dec_forward(e, dn, D2, e->z_keep, B, true, st));                // rec
-  TRY(enc_forward(e, en, E2, D2.y, B, true, st));                     // model(rec.detach())
+  TRY(dec_forward(e, dn, D2, e->z_keep, B, true, kd, st));            // rec
+  TRY(enc_forward(e, en, E2, D2.y, B, true, true, st));               // model(rec.detach())
   launch_kl_reparam(E2.ml, eps2, E2.z, E2.kl, B, z, st);
-  TRY(dec_forward(e, tn, D3, E2.z, B, true, st));                     // rec_rec
-  TRY(enc_forward(e, en, E3, D1.y, B, true, st));                     // model(fake.detach())
+  TRY(dec_forward(e, tn, D3, E2.z, B, true, false, st));              // rec_rec
+  TRY(enc_forward(e, en, E3, D1.y, B, true, true, st));               // model(fake.detach())
   launch_kl_reparam(E3.ml, eps3, E3.z, E3.kl, B, z, st);
-  TRY(dec_forward(e, tn, D4, E3.z, B, true, st));                     // rec_fake
+  TRY(dec_forward(e, tn, D4, E3.z, B, true, false, st));              // rec_fake
   // losses :563-586
   { ProfLoss pl(B, per, st); launch_mse3(e->real, D2.y, D3.y, D1.y, D4.y, e->mse, B, per, e->red, e->red_bytes, st); }
   launch_e_loss_finalize(e->mse, E1.kl, E2.kl, E3.kl, B, hp->beta_kl, hp->beta_rec, hp->beta_neg, hp->scale, stats,
@@ -875,15 +938,15 @@ extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper
     launch_bn_ema_replay(D5.ema, dn.bn, dn.bn_floats, dn.nbt, (int)dn.binfo.size(), st);
     launch_bn_ema_replay(D6.ema, dn.bn, dn.bn_floats, dn.nbt, (int)dn.binfo.size(), st);
   } else {
-    TRY(dec_forward(e, dn, D5, e->noise, B, true, st));               // fake :597
-    TRY(dec_forward(e, dn, D6, e->z_keep, B, true, st));              // rec  :598
+    TRY(dec_forward(e, dn, D5, e->noise, B, true, true, st));         // fake :597
+    TRY(dec_forward(e, dn, D6, e->z_keep, B, true, true, st));        // rec  :598
   }
-  TRY(enc_forward(e, en, E4, D6.y, B, true, st));                     // :601
+  TRY(enc_forward(e, en, E4, D6.y, B, true, false, st));              // :601  (encoder: dgrad-only in this half)
   launch_kl_reparam(E4.ml, eps4, E4.z, E4.kl, B, z, st);
-  TRY(enc_forward(e, en, E5, D5.y, B, true, st));                     // :604
+  TRY(enc_forward(e, en, E5, D5.y, B, true, false, st));              // :604
   launch_kl_reparam(E5.ml, eps5, E5.z, E5.kl, B, z, st);
-  TRY(dec_forward(e, tn, D7, E4.z, B, true, st));                     // rec_rec :607
-  TRY(dec_forward(e, tn, D8, E5.z, B, true, st));                     // rec_fake :608
+  TRY(dec_forward(e, tn, D7, E4.z, B, true, !boot, st));              // rec_rec :607 (bootstrap: frozen target decoder)
+  TRY(dec_forward(e, tn, D8, E5.z, B, true, !boot, st));              // rec_fake :608
   { ProfLoss pl(B, per, st); launch_mse3(e->real, D6.y, D7.y, D5.y, D8.y, e->mse, B, per, e->red, e->red_bytes, st); }
   launch_d_loss_finalize(e->mse, E4.kl, E5.kl, B, hp->beta_kl, hp->beta_rec, hp->gamma_r, hp->scale, stats, st);
   const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
@@ -929,9 +992,9 @@ extern "C" int sivae_vae_step(sivae_engine* e, const float* real_nchw, const flo
   launch_nchw_to_nhwc(real_nchw, e->real, B, c.cdim, S, S, st);
   EncPass& E1 = e->ep[0];
   DecPass& D1 = e->dp[0];
-  TRY(enc_forward(e, en, E1, e->real, B, true, st));                  // model(real_batch) :518
+  TRY(enc_forward(e, en, E1, e->real, B, true, true, st));            // model(real_batch) :518
   launch_kl_reparam(E1.ml, eps, E1.z, E1.kl, B, z, st);
-  TRY(dec_forward(e, dn, D1, E1.z, B, true, st));
+  TRY(dec_forward(e, dn, D1, E1.z, B, true, true, st));
   launch_mse3(e->real, D1.y, nullptr, nullptr, nullptr, e->mse, B, per, e->red, e->red_bytes, st);
   launch_vae_loss_finalize(e->mse, E1.kl, B, hp->beta_kl, hp->beta_rec, stats, st);
   launch_loss_seed(e->real, D1.y, nullptr, nullptr, nullptr, 2.f * hp->beta_rec / (float)B, nullptr, 0.f, nullptr, 0.f, false,
@@ -992,7 +1055,7 @@ extern "C" int sivae_encode(sivae_engine* e, const float* x_nchw, int B, float* 
   TRY(refresh_derived(e, en, st));
   launch_nchw_to_nhwc(x_nchw, e->out_tmp, B, c.cdim, c.image_size, c.image_size, st);
   EncPass& p = e->ep[2];
-  TRY(enc_forward(e, en, p, e->out_tmp, B, train != 0, st));
+  TRY(enc_forward(e, en, p, e->out_tmp, B, train != 0, false, st));
   cudaMemcpy2DAsync(mu, sizeof(float) * c.zdim, p.ml, sizeof(float) * 2 * c.zdim, sizeof(float) * c.zdim, B, cudaMemcpyDeviceToDevice, st);
   cudaMemcpy2DAsync(logvar, sizeof(float) * c.zdim, p.ml + c.zdim, sizeof(float) * 2 * c.zdim, sizeof(float) * c.zdim, B, cudaMemcpyDeviceToDevice, st);
   CHECK_CUDA_RET();
@@ -1007,7 +1070,7 @@ extern "C" int sivae_decode(sivae_engine* e, int net, const float* z, int B, flo
   const sivae_config& c = e->cfg;
   TRY(refresh_derived(e, *n, st));
   DecPass& p = e->dp[3];
-  TRY(dec_forward(e, *n, p, z, B, train != 0, st));
+  TRY(dec_forward(e, *n, p, z, B, train != 0, false, st));
   launch_nhwc_to_nchw(p.y, out_nchw, B, c.cdim, c.image_size, c.image_size, st);
   CHECK_CUDA_RET();
   return 0;
@@ -1088,23 +1151,41 @@ static float* lib_scratch(int slot, size_t floats) {
 }
 static float* narrow_scratch(size_t floats) { return lib_scratch(0, floats); }
 // AUTO backend of the single-kernel entry points: prepare whatever derived filter / scratch the engine's choice needs
-static int auto_prepare(sivae_engine* tmp, const ConvShape& s, const float* filt, const float** wn, const float** wg, cudaStream_t st) {
+// split (forward entry point only): where a tensor-core kernel serves the shape, hand it split32 operands like the engine's
+// default mode does -- *x / *w_tc are redirected to library-owned split32 copies and *fmt is set to FMT_SPLIT_
+static int auto_prepare(sivae_engine* tmp, const ConvShape& s, const float* filt, const float** wn, const float** wg, cudaStream_t st,
+                        bool split = false, const float** x = nullptr, const float** w_tc = nullptr, int* fmt = nullptr) {
   *wn = *wg = nullptr;
   tmp->rs = lib_scratch(1, (size_t)conv_rowsep_scratch_floats(s));
   tmp->sk_bytes = conv_tc_supported_fwd(s) ? conv_tc_splitk_scratch_bytes(s) : 0;
   tmp->sk = tmp->sk_bytes ? (void*)lib_scratch(2, (tmp->sk_bytes + 3) / 4) : nullptr;
   if (!tmp->sk) tmp->sk_bytes = 0;
   const int wide = s.Cin > s.Cout ? s.Cin : s.Cout;
+  auto split_x = [&]() -> int {
+    float* xs = lib_scratch(5, (size_t)(s.pixels() * s.Cin));
+    if (!xs) return fail(-3, "cudaMalloc of the split32 scratch failed");
+    launch_split32(*x, xs, s.pixels() * s.Cin, st);
+    *x = xs; *fmt = FMT_SPLIT_;
+    return 0;
+  };
   if (fwd_on_rowsep_in(tmp, s)) {
     float* buf = narrow_scratch((size_t)wide * 160);
     if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
-    launch_rowsep_filter_expand(filt, buf, s.Cout, s.Cin, st);
+    launch_rowsep_filter_expand(filt, buf, s.Cout, s.Cin, st, !split);
+    if (split) { launch_split32(buf, buf, (long long)s.Cout * 160, st); *fmt = FMT_SPLIT_; }     // x stays the fp32 image
     *wn = buf;
   } else if (fwd_on_rowsep_out(tmp, s)) {
     float* buf = narrow_scratch((size_t)wide * 160);
     if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
-    launch_rowsep_filter_gather(filt, buf, s.Cout, s.Cin, st);
+    launch_rowsep_filter_gather(filt, buf, s.Cout, s.Cin, st, !split);
+    if (split) { launch_split32(buf, buf, (long long)80 * s.Cin, st); TRY(split_x()); }
     *wg = buf;
+  } else if (split && !fwd_on_narrow(tmp, s) && fwd_on_tc(tmp, s)) {
+    float* ws = lib_scratch(3, (size_t)(s.Cout * s.ktot()));
+    if (!ws) return fail(-3, "cudaMalloc of the split32 scratch failed");
+    launch_split32(filt, ws, (long long)s.Cout * s.ktot(), st);
+    *w_tc = ws;
+    TRY(split_x());
   } else if (fwd_on_narrow(tmp, s)) {
     float* buf = narrow_scratch((size_t)s.Cout * s.Cin * s.k * s.k);
     if (!buf) return fail(-3, "cudaMalloc of the narrow-filter scratch failed");
@@ -1142,11 +1223,14 @@ extern "C" int sivae_conv2d_fwd(const float* x, const float* w, const float* bia
     void* sk = skb ? (void*)lib_scratch(2, (skb + 3) / 4) : nullptr;
     int r = launch_conv_fwd_tc(x, w, bias, addend, y, s, st, nullptr, sk, sk ? skb : 0);
     if (r) return fail(r, "tcgen05 conv launch failed");
-  } else if (backend == SIVAE_CONV_AUTO) {
+  } else if (backend == SIVAE_CONV_AUTO || backend == SIVAE_CONV_TF32) {
+    // AUTO: what the engine's default mode runs for a FORWARD conv of this shape (split32 operands on the tensor core);
+    // TF32: the round-1 choice (kind::tf32 on the caller's values)
     sivae_engine tmp; tmp.tc = tmp.fast = true;
-    const float *wn, *wg;
-    TRY(auto_prepare(&tmp, s, w, &wn, &wg, st));
-    TRY(conv_any(&tmp, s, x, w, w, bias, addend, y, st, nullptr, wn, wg));
+    const float *wn, *wg, *xin = x, *wtc = w;
+    int fmt = FMT_TF32_;
+    TRY(auto_prepare(&tmp, s, w, &wn, &wg, st, backend == SIVAE_CONV_AUTO, &xin, &wtc, &fmt));
+    TRY(conv_any(&tmp, s, xin, w, wtc, bias, addend, y, st, nullptr, wn, wg, nullptr, fmt));
   } else if (backend == SIVAE_CONV_TC3X) {
     TRY(conv3x_entry(s, x, w, bias, addend, y, st));
   } else {
@@ -1162,6 +1246,7 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   float* wd = (float*)workspace;
   ConvShape s{N, H, W, Cout, Cin, k};
+  if (backend == SIVAE_CONV_TF32) backend = SIVAE_CONV_AUTO;      // the backward is kind::tf32 in both tensor-core modes
   sivae_engine tmp; tmp.tc = tmp.fast = (backend == SIVAE_CONV_AUTO);
   const bool on_tc = backend == SIVAE_CONV_TCGEN05 || (backend == SIVAE_CONV_AUTO && !fwd_on_narrow(&tmp, s) && fwd_on_tc(&tmp, s));
   launch_pack_dgrad_filter(w, wd, Cout, Cin, k, on_tc, st);
@@ -1188,6 +1273,7 @@ extern "C" int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, in
   ConvShape s{N, H, W, Cin, Cout, k};
   cudaStream_t st = (cudaStream_t)stream;
   const bool acc = accumulate != 0;
+  if (backend == SIVAE_CONV_TF32) backend = SIVAE_CONV_AUTO;      // the backward is kind::tf32 in both tensor-core modes
   const bool rs_stem = backend == SIVAE_CONV_AUTO && Cin <= 3 && conv_rowsep_wgrad_supported(H, W, Cin, Cout, k);
   const bool rs_pred = backend == SIVAE_CONV_AUTO && Cout <= 3 && conv_rowsep_wgrad_supported(H, W, Cout, Cin, k);
   if (rs_stem || rs_pred) {
@@ -1300,18 +1386,6 @@ extern "C" int sivae_adam_flat(float* p, const float* g, float* m, float* v, lon
   cudaMemcpyAsync(sdev, &prev, sizeof(long long), cudaMemcpyHostToDevice, (cudaStream_t)stream);
   cudaStreamSynchronize((cudaStream_t)stream);
   launch_adam(p, g, m, v, n, lr, grad_scale, 0.9f, 0.999f, 1e-8f, sdev, cdev, (cudaStream_t)stream);
-  CHECK_CUDA_RET();
-  return 0;
-}
-
-// fp16-operand 3x3 conv forward (round-2 groundwork): NOT on any engine path yet
-extern "C" int sivae_conv2d_fwd_f16(const void* x_half_nhwc, const void* w_half_packed, const float* addend, float* y_nhwc, int N,
-                                    int H, int W, int Cin, int Cout, int k, void* stream) {
-  if (!x_half_nhwc || !w_half_packed || !y_nhwc) return fail(-1, "null argument");
-  ConvShape s{N, H, W, Cin, Cout, k};
-  if (!conv_f16_supported(s)) return fail(-8, "fp16-operand conv: shape not supported (3x3, Cin % 64 == 0, CTA-pair tiling)");
-  int r = launch_conv_fwd_f16(x_half_nhwc, w_half_packed, nullptr, addend, y_nhwc, s, nullptr, (cudaStream_t)stream);
-  if (r) return fail(r, "fp16-operand conv launch failed");
   CHECK_CUDA_RET();
   return 0;
 }

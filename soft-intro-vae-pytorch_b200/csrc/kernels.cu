@@ -3,6 +3,7 @@
 // convolution used for the 3-channel stem / predict layers and as the on-device cross-check of the tcgen05 path.
 // Reference semantics: soft_intro_vae/train_soft_intro_vae.py (lines cited per kernel).
 #include "kernels.h"
+#include "split32.cuh"
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -101,6 +102,23 @@ void launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaS
   g_launches += 1;
   if (n <= 0) return;
   k_split_tf32<<<min(cdiv((n >> 2) + 1, 256), 148u * 16), 256, 0, st>>>(in, hi, lo, n);
+}
+// fp32 -> split32 (split32.cuh).  In-place safe: the 8 lanes that own one 128-byte group have all read their float4 before
+// any of them writes (warps stay converged: the loop bound is rounded up to a whole warp).
+__global__ void k_split32(const float* in, float* out, long long n4) {
+  const long long n4r = (n4 + 31) / 32 * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4r; i += (long long)gridDim.x * blockDim.x) {
+    const bool ok = i < n4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) v = reinterpret_cast<const float4*>(in)[i];
+    __syncwarp();
+    if (ok) split32_store4(out + (i >> 3) * 32, (uint32_t)(i & 7), v);
+  }
+}
+void launch_split32(const float* in, float* out, long long n, cudaStream_t st) {
+  g_launches += 1;
+  if (n <= 0) return;
+  k_split32<<<min(cdiv(n >> 2, 256), 148u * 16), 256, 0, st>>>(in, out, n >> 2);
 }
 __global__ void k_pack_dgrad(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int k, int rnd) {
   long long total = (long long)Cout * Cin * k * k;
@@ -552,11 +570,15 @@ void launch_bn_eval_stats(const float* rm, const float* rv, int C, float* mi, cu
 
 // out = resample(lrelu(bn(t) + identity)).  One thread per float4 of the OUTPUT for NONE/POOL, per float4 of the
 // INPUT for UP.  (:65-75 ResidualBlock.forward, :90-92 stem, :98 AvgPool2d(2), :155 Upsample nearest x2)
-template <int MODE, bool ROUND>
+// SPLIT: the output is (also) written in the split32 operand format of the forward convolutions to `outs`, from the
+// UNROUNDED value; `out` (fp32, tf32-rounded if ROUND: the wgrad operand) is skipped when null; a split32 identity tensor
+// (the block input when the block has no conv_expand) is read with idn_split != 0.
+template <int MODE, bool ROUND, bool SPLIT>
 __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t, const float* __restrict__ idn,
                                                     const float* __restrict__ mi, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float* __restrict__ out, int N,
-                                                    int H, int W, int C, unsigned char* __restrict__ mask) {
+                                                    int H, int W, int C, unsigned char* __restrict__ mask,
+                                                    float* __restrict__ outs, int idn_split) {
   // 32-bit index arithmetic (tensor sizes are < 2^31 float4s; checked by the launcher): 64-bit div/mod per element
   // would make this HBM-bound kernel instruction-bound
   const unsigned cvec = (unsigned)C >> 2;
@@ -582,7 +604,7 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
       float4 v = __ldg(reinterpret_cast<const float4*>(t + pix * C) + c4);
       float4 y = make_float4(fmaf(v.x, sc.x, sf.x), fmaf(v.y, sc.y, sf.y), fmaf(v.z, sc.z, sf.z), fmaf(v.w, sc.w, sf.w));
       if (idn) {
-        float4 d = __ldg(reinterpret_cast<const float4*>(idn + pix * C) + c4);
+        float4 d = idn_split ? split32_load4(idn + pix * C, c4) : __ldg(reinterpret_cast<const float4*>(idn + pix * C) + c4);
         y.x += d.x; y.y += d.y; y.z += d.z; y.w += d.w;
       }
       // sign of the pre-activation, one byte per float4: the backward needs nothing else of y, so it can skip
@@ -591,42 +613,66 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
         mask[pix * cvec + c4] = (unsigned char)((y.x > 0.f ? 1 : 0) | (y.y > 0.f ? 2 : 0) | (y.z > 0.f ? 4 : 0) | (y.w > 0.f ? 8 : 0));
       return make_float4(lrelu(y.x), lrelu(y.y), lrelu(y.z), lrelu(y.w));
     };
+    auto rnd4 = [](float4 y) {
+      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
+      return y;
+    };
     if (MODE == RS_NONE) {
       long long pix = p;
-      float4 y = eval(pix);
-      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
-      reinterpret_cast<float4*>(out + pix * C)[c4] = y;
+      const float4 y = eval(pix);
+      if (SPLIT) split32_store4(outs + pix * C, c4, y);
+      if (!SPLIT || out) reinterpret_cast<float4*>(out + pix * C)[c4] = rnd4(y);
     } else if (MODE == RS_POOL) {
       long long p00 = ((long long)n * H + 2 * h) * W + 2 * w;
       float4 a = eval(p00), b2 = eval(p00 + 1), c2 = eval(p00 + W), d2 = eval(p00 + W + 1);
-      float4 y = make_float4((a.x + b2.x + c2.x + d2.x) * 0.25f, (a.y + b2.y + c2.y + d2.y) * 0.25f,
-                             (a.z + b2.z + c2.z + d2.z) * 0.25f, (a.w + b2.w + c2.w + d2.w) * 0.25f);
-      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
+      const float4 y = make_float4((a.x + b2.x + c2.x + d2.x) * 0.25f, (a.y + b2.y + c2.y + d2.y) * 0.25f,
+                                   (a.z + b2.z + c2.z + d2.z) * 0.25f, (a.w + b2.w + c2.w + d2.w) * 0.25f);
       long long po = ((long long)n * Ho + h) * Wo + w;
-      reinterpret_cast<float4*>(out + po * C)[c4] = y;
+      if (SPLIT) split32_store4(outs + po * C, c4, y);
+      if (!SPLIT || out) reinterpret_cast<float4*>(out + po * C)[c4] = rnd4(y);
     } else {
       long long pix = ((long long)n * H + h) * W + w;
-      float4 y = eval(pix);
-      if (ROUND) { y.x = round_tf32_dev(y.x); y.y = round_tf32_dev(y.y); y.z = round_tf32_dev(y.z); y.w = round_tf32_dev(y.w); }
+      const float4 y = eval(pix);
       long long po = ((long long)n * (2 * H) + 2 * h) * (2 * W) + 2 * w;
-      reinterpret_cast<float4*>(out + po * C)[c4] = y;
-      reinterpret_cast<float4*>(out + (po + 1) * C)[c4] = y;
-      reinterpret_cast<float4*>(out + (po + 2 * W) * C)[c4] = y;
-      reinterpret_cast<float4*>(out + (po + 2 * W + 1) * C)[c4] = y;
+      if (SPLIT) {
+        uint2 hi, lo;
+        split32_pack4(y, hi, lo);
+        const uint32_t off = split32_off4(c4);
+        const long long pp[4] = {po, po + 1, po + 2 * W, po + 2 * W + 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          char* d = reinterpret_cast<char*>(outs + pp[k] * C) + off;
+          *reinterpret_cast<uint2*>(d) = hi;
+          *reinterpret_cast<uint2*>(d + 64) = lo;
+        }
+      }
+      if (!SPLIT || out) {
+        const float4 yr = rnd4(y);
+        reinterpret_cast<float4*>(out + po * C)[c4] = yr;
+        reinterpret_cast<float4*>(out + (po + 1) * C)[c4] = yr;
+        reinterpret_cast<float4*>(out + (po + 2 * W) * C)[c4] = yr;
+        reinterpret_cast<float4*>(out + (po + 2 * W + 1) * C)[c4] = yr;
+      }
     }
   }
 }
 void launch_bn_act_fwd(const float* t, const float* identity, const float* mi, const float* gamma, const float* beta,
-                       float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st, unsigned char* mask) {
+                       float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st, unsigned char* mask,
+                       float* outs, bool idn_split) {
   g_launches += 1;
   int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
   long long total = (long long)N * Ho * Wo * (C / 4);
   if (total == 0) return;
   unsigned grid = min(cdiv(total, 256), 148u * 32);
-#define LAUNCH(M, R) k_bn_act_fwd<M, R><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C, mask)
-  if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
-  else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
-  else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }
+  const int is = idn_split ? 1 : 0;
+#define LAUNCH(M, R, S) k_bn_act_fwd<M, R, S><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C, mask, outs, is)
+  if (outs) {           // split32 output (C % 32 == 0), always together with tf32 rounding of the optional fp32 copy
+    if (mode == RS_NONE) LAUNCH(RS_NONE, true, true);
+    else if (mode == RS_POOL) LAUNCH(RS_POOL, true, true);
+    else LAUNCH(RS_UP, true, true);
+  } else if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true, false); else LAUNCH(RS_NONE, false, false); }
+  else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true, false); else LAUNCH(RS_POOL, false, false); }
+  else { if (rnd) LAUNCH(RS_UP, true, false); else LAUNCH(RS_UP, false, false); }
 #undef LAUNCH
 }
 

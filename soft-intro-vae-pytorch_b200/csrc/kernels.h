@@ -28,6 +28,9 @@ void launch_fill(float* p, float v, long long n, cudaStream_t st);
 void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st);
 // compensated (3xTF32) operand split: hi = tf32(x), lo = tf32(x - hi); hi may alias in (16-byte aligned pointers)
 void launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaStream_t st);
+// fp32 -> split32 (split32.cuh); n floats, n % 32 == 0, groups of 32 aligned with the tensor's channel groups.  out may alias in.
+void launch_split32(const float* in, float* out, long long n, cudaStream_t st);
+constexpr int FMT_TF32_ = 0, FMT_SPLIT_ = 1;   // operand formats of the tensor-core forward kernels (mirrors conv_tc.cu)
 // wd[ci][k-1-r][k-1-s][co] = w[co][r][s][ci]  (filters for dgrad as a forward conv); optional tf32 rounding
 void launch_pack_dgrad_filter(const float* w, float* wd, int Cout, int Cin, int k, bool round_tf32, cudaStream_t st);
 
@@ -48,17 +51,19 @@ void launch_colsum(const float* in, float* out, long long rows, int C, bool accu
 bool conv_rowsep_in_supported(const ConvShape& s);
 bool conv_rowsep_out_supported(const ConvShape& s);
 long long conv_rowsep_scratch_floats(const ConvShape& s);
-void launch_rowsep_filter_expand(const float* f, float* out, int Co, int c, cudaStream_t st);     // [Co][5][5][c] -> [Co][5][32]
-void launch_rowsep_filter_gather(const float* f, float* out, int c, int Ci, cudaStream_t st);     // [c][5][5][Ci] -> [16][5][Ci]
+// round_tf32 = false: unrounded values (to be converted to split32 by launch_split32)
+void launch_rowsep_filter_expand(const float* f, float* out, int Co, int c, cudaStream_t st, bool round_tf32 = true);     // [Co][5][5][c] -> [Co][5][32]
+void launch_rowsep_filter_gather(const float* f, float* out, int c, int Ci, cudaStream_t st, bool round_tf32 = true);     // [c][5][5][Ci] -> [16][5][Ci]
+// fmt (conv_tc.cu): FMT_TF32 = 0 (x, filter fp32 pre-rounded to tf32) or FMT_SPLIT = 1 (x, filter in the split32 format)
 int launch_conv_rowsep_in(const float* x, const float* we, const float* bias, const float* addend, float* y, const ConvShape& s,
-                          float* scratch, float* stats, cudaStream_t st);
+                          float* scratch, float* stats, cudaStream_t st, int fmt = 0);
 bool conv_rowsep_wgrad_supported(int H, int W, int c, int wide, int k);
 size_t conv_rowsep_wgrad_scratch_bytes(int N, int H, int W, int wide);
 // mode 1: stem (narrow = x [N,H,W,c], wide = dy [N,H,W,wide]); mode 0: predict (narrow = dy, wide = x); dw [Cout][5][5][Cin]
 int launch_conv_rowsep_wgrad(const float* narrow_t, const float* wide_t, float* dw, int N, int H, int W, int c, int wide, int mode,
                              bool accumulate, float* expand_scratch, void* scratch, size_t scratch_bytes, cudaStream_t st);
 int launch_conv_rowsep_out(const float* x, const float* wg, const float* bias, const float* addend, float* y, const ConvShape& s,
-                           float* scratch, cudaStream_t st);
+                           float* scratch, cudaStream_t st, int fmt = 0);
 bool conv_narrow_in_supported(const ConvShape& s);            // Cin <= 4: stem forward, predict dgrad
 // wt = filter transposed to [tap][Cin][Cout] (launch_narrow_transpose of the [Cout][tap][Cin] filter)
 void launch_narrow_transpose(const float* w, float* wt, int Cout, int k, int A, cudaStream_t st);
@@ -73,19 +78,16 @@ void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int
 // ---------------- tcgen05 TF32 implicit-GEMM convolution (conv_tc.cu) ----------------
 bool conv_tc_supported_fwd(const ConvShape& s);
 // returns cudaError / driver error code (0 ok)
+// fmt = FMT_SPLIT: x and w are split32 tensors ([32 bf16 hi | 32 bf16 lo] per 32-channel group, split32.cuh) and every
+// product is computed as lo*hi + hi*lo + hi*hi with three kind::f16 MMAs -- fp32-class accuracy at 1.5x the tf32 tensor time
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y,
                        const ConvShape& s, cudaStream_t st, float* stats = nullptr, void* scratch = nullptr,
-                       size_t scratch_bytes = 0);
+                       size_t scratch_bytes = 0, int fmt = 0);
 // split-K partial tensor the v2 kernel wants for few-tile layers (0: no split for this shape)
 size_t conv_tc_splitk_scratch_bytes(const ConvShape& s);
 // fused train-mode BN statistics: if > 0, passing `stats` ([parts][2][Cout] floats) to launch_conv_fwd_tc makes the
 // epilogue emit per-warp column sums / sums of squares; finish with launch_bn_stats_from_parts
 int conv_tc_stats_parts(const ConvShape& s);
-// fp16-operand variant of the CTA-pair 3x3 kernel (round-2 groundwork; not dispatched by the engine): x NHWC half, w packed
-// [Cout][3][3][Cin] half, fp32 output / addend / statistics.  -8: shape not taken by the pair kernel or Cin % 64 != 0
-bool conv_f16_supported(const ConvShape& s);
-int launch_conv_fwd_f16(const void* x, const void* w, const float* bias, const float* addend, float* y, const ConvShape& s,
-                        float* stats, cudaStream_t st);
 bool conv_tc_supported_wgrad(const ConvShape& s);
 size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s);
 int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
@@ -108,9 +110,11 @@ void launch_bn_ema_replay(const double* ema, float* running, long long n, long l
 void launch_bn_eval_stats(const float* running_mean, const float* running_var, int C, float* mean_invstd, cudaStream_t st);
 // out = resample(lrelu(bn(t) + identity)); identity may be null. (N,H,W) are the dims of t.
 // sign_mask (nullable): receives one byte per float4 of t with the signs of the pre-activation (bit j = component j > 0)
+// outs (nullable; needs C % 32 == 0): the output in the split32 operand format (from the unrounded value); with outs the
+// fp32 copy `out` is optional (null = not written) and tf32-rounded.  idn_split: `identity` is a split32 tensor.
 void launch_bn_act_fwd(const float* t, const float* identity, const float* mean_invstd, const float* gamma,
                        const float* beta, float* out, int N, int H, int W, int C, int mode, bool round_tf32,
-                       cudaStream_t st, unsigned char* sign_mask = nullptr);
+                       cudaStream_t st, unsigned char* sign_mask = nullptr, float* outs = nullptr, bool idn_split = false);
 // backward. dout has the shape of the resampled output.  sums: 2*C floats scratch inside `scratch`.
 void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mean_invstd,
                        const float* gamma, const float* beta, float* dt, float* g, float* dgamma, float* dbeta,

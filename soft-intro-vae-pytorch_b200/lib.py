@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SIVAE_LIB_PATH") or os.path.join(_HERE, "libsivae_b200.so")
 
 NET_ENCODER, NET_DECODER, NET_TARGET = 0, 1, 2
-CONV_AUTO, CONV_SIMT, CONV_TCGEN05, CONV_TC3X = 0, 1, 2, 3
+CONV_AUTO, CONV_SIMT, CONV_TCGEN05, CONV_TC3X, CONV_TF32 = 0, 1, 2, 3, 4
 T_CONV, T_BN_WEIGHT, T_BN_BIAS, T_LINEAR, T_BIAS = 0, 1, 2, 3, 4
 
 
@@ -73,7 +73,6 @@ _SIGS = {
     "sivae_mse3": (C.c_int, [_P] * 6 + [C.c_int, C.c_longlong, _P, C.c_longlong, _P]),
     "sivae_kl_reparam": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "sivae_adam_flat": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_longlong, _P]),
-    "sivae_conv2d_fwd_f16": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 6 + [_P]),
     "sivae_linear_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "sivae_linear_dgrad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_longlong, _P]),
     "sivae_linear_dgrad_workspace_bytes": (C.c_longlong, [C.c_int, C.c_int, C.c_int]),

@@ -54,7 +54,7 @@ def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=N
     imgs_e = {k: eng.last_image(i).cpu() for i, k in enumerate(["fake", "rec", "rec_rec", "rec_fake"])}
     eng.adam(L.NET_ENCODER, hp["lr_e"])
     torch.cuda.synchronize()
-    enc_after_e = {k: v.detach().clone().cpu().contiguous() for k, v in model.encoder.state_dict().items()}
+    enc_after_e = {"encoder." + k: v.detach().clone().cpu().contiguous() for k, v in model.encoder.state_dict().items()}
     if teacher_enc is not None:
         # teacher forcing of the D half: Adam's first step moves every weight by ~lr*sign(g), which turns round-off
         # in tiny gradients into O(lr) weight differences; loading the comparison run's post-E-step encoder weights
@@ -141,14 +141,30 @@ def compare(eng, ora, tol, label="", lr=2e-4, verbose=True, tensor_tol=None, noi
             if not r < ttol:
                 fails.append("%s max-rel %.3g" % (k, r))
         else:
-            # one Adam step from zero moments moves each weight by ~lr*sign(g): bounded check here, the Adam kernel
-            # itself is unit-tested against torch.optim.Adam with identical gradients
+            # against the ORACLE only a bound holds: one Adam step from zero moments moves each weight by ~lr*sign(g), so
+            # round-off in a tiny gradient flips whole steps
             d = float((e.double() - v.double()).abs().max())
             if not d <= 2.05 * lr + 1e-7:
                 fails.append("post-step %s differs by %.3g" % (k, d))
+    # the optimiser step itself, teacher-forced with the ENGINE's own gradient: after the first Adam step (m = (1-b1) g,
+    # v = (1-b2) g^2, both bias-corrected back to g and g^2) every parameter must sit at p0 - lr * g / (|g| + eps)
+    if "init" in eng:
+        for name, after in (("grads_e", eng.get("enc_after_e")), ("grads_d", eng["post"])):
+            if after is None:
+                continue
+            for k, g in eng[name].items():
+                g64 = g.double()
+                want = eng["init"][k].double() - lr * g64 / (g64.abs() + 1e-8)
+                d = float((after[k].double() - want).abs().max())
+                dev["adam:" + k] = d / lr
+                if not d <= 2e-7 + 1e-3 * lr:
+                    fails.append("Adam step of %s: |p - (p0 - lr g/(|g|+eps))| = %.3g" % (k, d))
     top = sorted(dev.items(), key=lambda kv: -kv[1])
     if verbose:
-        print("[%s] worst deviations: %s" % (label, ", ".join("%s=%.2e" % kv for kv in top[:6])))
+        sc = [kv for kv in top if kv[0].startswith("scalar:")]
+        te = [kv for kv in top if not kv[0].startswith(("scalar:", "adam:"))]
+        print("[%s] worst scalars: %s | worst tensors: %s" % (label, ", ".join("%s=%.2e" % (k[7:], v) for k, v in sc[:3]),
+                                                               ", ".join("%s=%.2e" % kv for kv in te[:4])))
     try:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"), "a") as f:
