@@ -102,6 +102,13 @@ def build_model(cfg_name, device, batch):
     return mod, model
 
 
+DTYPE_NAMES = {
+    0: "bf16x2-compensated forward convs (operands = bf16 hi+lo pairs, 3 kind::f16 MMAs per product, fp32 accumulate; scalars within "
+       "1e-4 of the fp64 oracle) + tf32 dgrad/wgrad; fp32 BN/loss/Adam/master weights",
+    4: "tf32 operands (fp32 storage, fp32 accumulate, fp32 BN/loss/Adam)",
+    3: "3xTF32 compensated (three tf32 convs per product)", 1: "fp32 CUDA cores (exact path)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -240,15 +247,15 @@ def run_ours(args):
     buf = C.create_string_buffer(1 << 16)
     lib.sivae_profile_dump(buf, len(buf))
     rows = [l.split() for l in buf.value.decode().splitlines()]
-    # BatchNorm+activation passes (classes 5 / 6 of the dump; their "gflop" column carries algorithmic GB): HBM-bound
+    # BatchNorm+activation passes (classes 6 / 7 of the dump; their "gflop" column carries algorithmic GB): HBM-bound
     bn_cls = {}
     for r in rows:
-        if int(r[0]) in (5, 6):
+        if int(r[0]) in (6, 7):
             a = bn_cls.setdefault(int(r[0]), [0.0, 0.0, 0])
             a[0] += float(r[8]); a[1] += float(r[9]); a[2] += int(r[7])
     if args.layers and rank == 0:
-        names = {0: "tc_fwd/dgrad", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, TB/s)",
-                 5: "bn+act fwd (k=4+mode: residual; TB/s)", 6: "bn+act bwd (k=4+mode: residual; TB/s)"}
+        names = {0: "tc tf32 (dgrad)", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, TB/s)",
+                 5: "tc split32 fwd (3 MMAs/product)", 6: "bn+act fwd (k=4+mode: residual; TB/s)", 7: "bn+act bwd (k=4+mode: residual; TB/s)"}
         rows.sort(key=lambda r: -float(r[8]))
         with open(args.layers, "w") as f:
             f.write("| class | N | H | W | Cin | Cout | k | launches/step | ms/step | ms/launch | TFLOP/s |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
@@ -256,7 +263,7 @@ def run_ours(args):
                 n, ms, gf = int(r[7]), float(r[8]), float(r[9])
                 f.write("| %s | %s | %s | %s | %s | %s | %s | %.1f | %.3f | %.4f | %.1f |\n" % (
                     names[int(r[0])], r[1], r[2], r[3], r[4], r[5], r[6], n / args.steps, ms / args.steps, ms / n, gf / ms if ms > 0 else 0))
-    prof = (C.c_double * 15)()
+    prof = (C.c_double * 18)()
     lib.sivae_profile_read(prof)
     lib.sivae_profile_enable(0)
     ms_e2e = time_e2e(args.steps)
@@ -281,26 +288,46 @@ def run_ours(args):
     value = world * batch / (ms_step / 1e3)
     e2e_value = world * batch / (ms_e2e / args.steps / 1e3)
     peaks = measured_peaks()
-    # dominant kernel class: tcgen05 implicit-GEMM conv (fwd + dgrad launches); TF32 runs at half the bf16 rate
+    # kernel classes (CUDA events per launch): 0 = tcgen05 kind::tf32 conv (dgrad; also the forward of the TF32 backend),
+    # 1 = tcgen05 wgrad, 5 = tcgen05 forward conv on split32 operands (three kind::f16 MMAs per product).  The dominant class
+    # is the one with the most time in the step.
     tc_ms, tc_flops, tc_n = prof[0], prof[1], prof[2]
     wg_ms, wg_flops, wg_n = prof[3], prof[4], prof[5]
+    f3_ms, f3_flops, f3_n = prof[15], prof[16], prof[17]
     simt_ms = prof[6] + prof[9]
     roof = None
-    if tc_n > 0 and tc_ms > 0:
-        achieved = tc_flops / (tc_ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="k_conv_fwd_tc (tcgen05 kind::tf32 implicit-GEMM conv, fwd+dgrad)",
-                    achieved=round(achieved, 2), peak=peaks["bf16_sustained"], unit="TFLOP/s",
-                    frac=round(achieved / peaks["bf16_sustained"], 4),
-                    peak_note="MEASURED_PEAKS bf16_tflops_sustained (%s); kind::tf32 issues at half the bf16 rate, so "
-                              "frac<=0.5 by construction" % peaks["source"],
-                    launches_per_step=tc_n / args.steps, ms_per_step=round(tc_ms / args.steps, 3),
-                    share_of_step=round(tc_ms / ms_prof, 4), ms_per_step_with_events=round(ms_prof / args.steps, 3),
+
+    def tcls(ms, fl, n, mma_per_product=1):
+        if not (n > 0 and ms > 0):
+            return None
+        a = fl / (ms * 1e-3) / 1e12
+        return dict(achieved=round(a, 2), frac=round(a / peaks["bf16_sustained"], 4), ms_per_step=round(ms / args.steps, 3),
+                    launches_per_step=n / args.steps, share_of_step=round(ms / ms_prof, 4),
+                    tensor_pipe_issued_tflops=round(a * mma_per_product, 2),
+                    tensor_pipe_issued_frac=round(a * mma_per_product / peaks["bf16_sustained"], 4))
+    if (tc_n > 0 and tc_ms > 0) or (f3_n > 0 and f3_ms > 0):
+        split_mode = f3_n > 0 and f3_ms >= tc_ms
+        dom = tcls(f3_ms, f3_flops, f3_n, 3) if split_mode else tcls(tc_ms, tc_flops, tc_n)
+        roof = dict(bound="tensor",
+                    kernel=("k_conv_halo2<.., FMT_SPLIT> family (tcgen05 kind::f16 implicit-GEMM FORWARD conv on bf16 hi+lo operands, "
+                            "3 MMAs per product)" if split_mode else "k_conv_halo2 family (tcgen05 kind::tf32 implicit-GEMM conv, fwd+dgrad)"),
+                    achieved=dom["achieved"], peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=dom["frac"],
+                    peak_note="MEASURED_PEAKS bf16_tflops_sustained (%s).  achieved = ALGORITHMIC conv FLOPs / time; the compensated "
+                              "forward issues 3 bf16 MMAs per product (frac <= 0.333 by construction, tensor_pipe_issued_* = 3x), "
+                              "kind::tf32 classes issue at half the bf16 rate (frac <= 0.5)" % peaks["source"],
+                    launches_per_step=dom["launches_per_step"], ms_per_step=dom["ms_per_step"], share_of_step=dom["share_of_step"],
+                    tensor_pipe_issued_tflops=dom["tensor_pipe_issued_tflops"], tensor_pipe_issued_frac=dom["tensor_pipe_issued_frac"],
+                    ms_per_step_with_events=round(ms_prof / args.steps, 3),
                     traffic=_traffic("fwd"), traffic_detail=_traffic("fwd_detail"),
+                    fwd_split32=tcls(f3_ms, f3_flops, f3_n, 3), tf32_dgrad=tcls(tc_ms, tc_flops, tc_n),
                     wgrad=dict(achieved=round(wg_flops / (wg_ms * 1e-3) / 1e12, 2) if wg_ms > 0 else None,
+                               frac=round(wg_flops / (wg_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], 4) if wg_ms > 0 else None,
                                ms_per_step=round(wg_ms / args.steps, 3), launches_per_step=wg_n / args.steps),
+                    conv_stack=dict(achieved=round((tc_flops + wg_flops + f3_flops) / ((tc_ms + wg_ms + f3_ms) * 1e-3) / 1e12, 2),
+                                    ms_per_step=round((tc_ms + wg_ms + f3_ms) / args.steps, 3)),
                     simt_conv_ms_per_step=round(simt_ms / args.steps, 3))
-        for cls, key, kern in ((5, "bn_fwd", "k_bn_act_fwd (BN apply + residual + LeakyReLU + pool / upsample)"),
-                               (6, "bn_bwd", "k_bn_bwd_reduce + k_bn_bwd_apply (train-mode BN + LeakyReLU backward)")):
+        for cls, key, kern in ((6, "bn_fwd", "k_bn_act_fwd (BN apply + residual + LeakyReLU + pool / upsample)"),
+                               (7, "bn_bwd", "k_bn_bwd_reduce + k_bn_bwd_apply (train-mode BN + LeakyReLU backward)")):
             if cls in bn_cls and bn_cls[cls][0] > 0:
                 ms_c, gb_c, n_c = bn_cls[cls]
                 gbs = gb_c / (ms_c * 1e-3)
@@ -315,7 +342,7 @@ def run_ours(args):
                                      ms_per_launch=round(prof[12] / prof[14], 4), bytes_per_launch=int(prof[13] / prof[14]))
     line = dict(metric="images/sec per introspective E+D step", value=round(value, 2), unit="images/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(ms_step, 3), higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="tf32 operands (fp32 storage, fp32 accumulate, fp32 BN/loss/Adam)", data="synthetic",
+                vs_baseline=None, dtype=DTYPE_NAMES.get(int(model._conv_backend), "?"), data="synthetic",
                 config=dict(workload=WORKLOAD_NAMES[args.config], image_size=size, z_dim=zdim, channels=channels,
                             batch_per_gpu=batch, global_batch=batch * world, parallelism="dp%d" % world,
                             l2_policy="inputs cycle over %d distinct batches; activations per step (>20 GB) far exceed the 126 MB L2" % n_host,

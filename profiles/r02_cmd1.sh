@@ -1,0 +1,7 @@
+set -x
+cd $GRAFT_REPO_ROOT
+rm -f gpurun_out/parity_report.jsonl
+timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -k "conv" 2>&1 | tail -15 > gpurun_out/r02_1_kernels.log
+timeout 1500 python -m pytest tests/test_gpu_step.py -q -x -s 2>&1 | tail -60 > gpurun_out/r02_1_step.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-loader-leg --layers gpurun_out/r02_1_layers.md > gpurun_out/r02_1_bench.json 2> gpurun_out/r02_1_bench.err
+tail -5 gpurun_out/r02_1_kernels.log; tail -30 gpurun_out/r02_1_step.log; cat gpurun_out/r02_1_bench.json | head -c 3000; tail -5 gpurun_out/r02_1_bench.err
