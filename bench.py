@@ -103,8 +103,9 @@ def build_model(cfg_name, device, batch):
 
 
 DTYPE_NAMES = {
-    0: "bf16x2-compensated forward convs (operands = bf16 hi+lo pairs, 3 kind::f16 MMAs per product, fp32 accumulate; scalars within "
-       "1e-4 of the fp64 oracle) + tf32 dgrad/wgrad; fp32 BN/loss/Adam/master weights",
+    0: "bf16x2-compensated forward convs (operands = bf16 hi+lo pairs, 3 kind::f16 MMAs per product, fp32 accumulate; every logged "
+       "scalar within 1e-4 of the fp64 oracle) + bf16 dgrad/wgrad of the residual blocks (tf32 for the image-facing convs); "
+       "fp32 conv outputs / BN / loss / Adam / master weights",
     4: "tf32 operands (fp32 storage, fp32 accumulate, fp32 BN/loss/Adam)",
     3: "3xTF32 compensated (three tf32 convs per product)", 1: "fp32 CUDA cores (exact path)"}
 
@@ -247,15 +248,16 @@ def run_ours(args):
     buf = C.create_string_buffer(1 << 16)
     lib.sivae_profile_dump(buf, len(buf))
     rows = [l.split() for l in buf.value.decode().splitlines()]
-    # BatchNorm+activation passes (classes 6 / 7 of the dump; their "gflop" column carries algorithmic GB): HBM-bound
+    # BatchNorm+activation passes (classes 8 / 9 of the dump; their "gflop" column carries algorithmic GB): HBM-bound
     bn_cls = {}
     for r in rows:
-        if int(r[0]) in (6, 7):
+        if int(r[0]) in (8, 9):
             a = bn_cls.setdefault(int(r[0]), [0.0, 0.0, 0])
             a[0] += float(r[8]); a[1] += float(r[9]); a[2] += int(r[7])
     if args.layers and rank == 0:
         names = {0: "tc tf32 (dgrad)", 1: "tc_wgrad", 2: "cuda-core fwd/dgrad", 3: "cuda-core wgrad", 4: "fused loss pass (GB, TB/s)",
-                 5: "tc split32 fwd (3 MMAs/product)", 6: "bn+act fwd (k=4+mode: residual; TB/s)", 7: "bn+act bwd (k=4+mode: residual; TB/s)"}
+                 5: "tc split32 fwd (3 MMAs/product)", 6: "tc bf16 dgrad", 7: "tc bf16 wgrad",
+                 8: "bn+act fwd (k=4+mode: residual; TB/s)", 9: "bn+act bwd (k=4+mode: residual; TB/s)"}
         rows.sort(key=lambda r: -float(r[8]))
         with open(args.layers, "w") as f:
             f.write("| class | N | H | W | Cin | Cout | k | launches/step | ms/step | ms/launch | TFLOP/s |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
@@ -263,7 +265,7 @@ def run_ours(args):
                 n, ms, gf = int(r[7]), float(r[8]), float(r[9])
                 f.write("| %s | %s | %s | %s | %s | %s | %s | %.1f | %.3f | %.4f | %.1f |\n" % (
                     names[int(r[0])], r[1], r[2], r[3], r[4], r[5], r[6], n / args.steps, ms / args.steps, ms / n, gf / ms if ms > 0 else 0))
-    prof = (C.c_double * 18)()
+    prof = (C.c_double * 24)()
     lib.sivae_profile_read(prof)
     lib.sivae_profile_enable(0)
     ms_e2e = time_e2e(args.steps)
@@ -294,6 +296,8 @@ def run_ours(args):
     tc_ms, tc_flops, tc_n = prof[0], prof[1], prof[2]
     wg_ms, wg_flops, wg_n = prof[3], prof[4], prof[5]
     f3_ms, f3_flops, f3_n = prof[15], prof[16], prof[17]
+    d16_ms, d16_flops, d16_n = prof[18], prof[19], prof[20]
+    w16_ms, w16_flops, w16_n = prof[21], prof[22], prof[23]
     simt_ms = prof[6] + prof[9]
     roof = None
 
@@ -319,15 +323,15 @@ def run_ours(args):
                     tensor_pipe_issued_tflops=dom["tensor_pipe_issued_tflops"], tensor_pipe_issued_frac=dom["tensor_pipe_issued_frac"],
                     ms_per_step_with_events=round(ms_prof / args.steps, 3),
                     traffic=_traffic("fwd"), traffic_detail=_traffic("fwd_detail"),
-                    fwd_split32=tcls(f3_ms, f3_flops, f3_n, 3), tf32_dgrad=tcls(tc_ms, tc_flops, tc_n),
-                    wgrad=dict(achieved=round(wg_flops / (wg_ms * 1e-3) / 1e12, 2) if wg_ms > 0 else None,
-                               frac=round(wg_flops / (wg_ms * 1e-3) / 1e12 / peaks["bf16_sustained"], 4) if wg_ms > 0 else None,
-                               ms_per_step=round(wg_ms / args.steps, 3), launches_per_step=wg_n / args.steps),
-                    conv_stack=dict(achieved=round((tc_flops + wg_flops + f3_flops) / ((tc_ms + wg_ms + f3_ms) * 1e-3) / 1e12, 2),
-                                    ms_per_step=round((tc_ms + wg_ms + f3_ms) / args.steps, 3)),
+                    fwd_split32=tcls(f3_ms, f3_flops, f3_n, 3), tf32_conv=tcls(tc_ms, tc_flops, tc_n),
+                    dgrad_bf16=tcls(d16_ms, d16_flops, d16_n), wgrad_bf16=tcls(w16_ms, w16_flops, w16_n),
+                    wgrad_tf32=tcls(wg_ms, wg_flops, wg_n),
+                    conv_stack=dict(achieved=round((tc_flops + wg_flops + f3_flops + d16_flops + w16_flops) /
+                                                   ((tc_ms + wg_ms + f3_ms + d16_ms + w16_ms) * 1e-3) / 1e12, 2),
+                                    ms_per_step=round((tc_ms + wg_ms + f3_ms + d16_ms + w16_ms) / args.steps, 3)),
                     simt_conv_ms_per_step=round(simt_ms / args.steps, 3))
-        for cls, key, kern in ((6, "bn_fwd", "k_bn_act_fwd (BN apply + residual + LeakyReLU + pool / upsample)"),
-                               (7, "bn_bwd", "k_bn_bwd_reduce + k_bn_bwd_apply (train-mode BN + LeakyReLU backward)")):
+        for cls, key, kern in ((8, "bn_fwd", "k_bn_act_fwd (BN apply + residual + LeakyReLU + pool / upsample)"),
+                               (9, "bn_bwd", "k_bn_bwd_reduce + k_bn_bwd_apply (train-mode BN + LeakyReLU backward)")):
             if cls in bn_cls and bn_cls[cls][0] > 0:
                 ms_c, gb_c, n_c = bn_cls[cls]
                 gbs = gb_c / (ms_c * 1e-3)

@@ -43,32 +43,36 @@ static EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// NHWC fp32 tensor [N][H][W][C] -> 4-D map, box {32, bw, bh, bn}, 128B swizzle, OOB -> 0
-static int make_map_nhwc(CUtensorMap* m, const float* base, int N, int H, int W, int C, int bw, int bh, int bn,
-                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+// NHWC tensor [N][H][W][C] -> 4-D map, box {128 bytes of channels, bw, bh, bn}, 128B swizzle, OOB -> 0.
+// bf16 = false: fp32 elements (32 channels per box row; also the split32 format, which has the same byte geometry);
+// bf16 = true: plain bf16 elements (64 channels per box row)
+static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, bool bf16 = false) {
   EncodeTiledFn f = encode_fn();
   if (!f) return -101;
+  const cuuint64_t es_b = bf16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es_b, (cuuint64_t)W * C * es_b, (cuuint64_t)H * W * C * es_b};
+  cuuint32_t box[4] = {bf16 ? 64u : 32u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = f(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides,
+                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -102;
 }
 static int make_store_map(CUtensorMap* m, float* base, int N, int H, int W, int C, int sw, int sh, int sn) {
   return make_map_nhwc(m, base, N, H, W, C, sw, sh, sn);
 }
-// row-major fp32 matrix [rows][cols] -> 2-D map, box {32, box_rows}
-static int make_map_2d(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows) {
+// row-major matrix [rows][cols] (fp32 / split32, or plain bf16) -> 2-D map, box {128 bytes, box_rows}
+static int make_map_2d(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows, bool bf16 = false) {
   EncodeTiledFn f = encode_fn();
   if (!f) return -101;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {bf16 ? 64u : 32u, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = f(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides,
+                 box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -102;
 }
 
@@ -468,12 +472,16 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
 //               exponent range).  Per 16-channel K step three kind::f16 MMAs: lo*hi + hi*lo + hi*hi (the lo*lo term, 2^-18
 //               relative, is dropped): 6 MMAs per row at twice the tf32 issue rate = 1.5x the tf32 tensor time for
 //               fp32-class products.  TMA maps, staging bytes, descriptors' row geometry and epilogues are identical.
+//   FMT_BF16  : 64 plain bf16 values (one 128-byte row = 64 channels); 4 MMAs (K = 16) of kind::f16 per row = half the tf32
+//               tensor time per channel.  Used by the dgrad of the residual blocks: its operand rounding (8 significand
+//               bits) moves the gradients by less than the forward's own round-off does (profiles/r02a_split_formats.md).
 // a_addr / b_addr: shared-memory byte address of the first row of the operand tile (row start, K offset 0).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FMT_TF32 = 0, FMT_SPLIT = 1;
+constexpr int FMT_TF32 = 0, FMT_SPLIT = 1, FMT_BF16 = 2;
 template <int FMT> __host__ __device__ constexpr uint32_t make_idesc_fmt(int M, int N) {
-  return FMT == FMT_SPLIT ? make_idesc_bf16(M, N, 0, 0) : make_idesc_tf32(M, N, 0, 0);
+  return FMT == FMT_TF32 ? make_idesc_tf32(M, N, 0, 0) : make_idesc_bf16(M, N, 0, 0);
 }
+template <int FMT> __host__ __device__ constexpr int fmt_csh() { return FMT == FMT_BF16 ? 6 : 5; }   // log2(channels per 128-byte row)
 __device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset);
 template <int FMT, bool PAIR>
 __device__ __forceinline__ void umma_row(uint32_t tmem_d, uint32_t a_addr, uint32_t a_sbo, uint32_t a_bo, uint32_t b_addr,
@@ -481,7 +489,7 @@ __device__ __forceinline__ void umma_row(uint32_t tmem_d, uint32_t a_addr, uint3
   auto mma = [&](uint32_t ao, uint32_t bo, uint32_t acc) {
     const uint64_t ad = make_smem_desc_bo(a_addr + ao, a_sbo, a_bo);
     const uint64_t bd = make_smem_desc_bo(b_addr + bo, 1024, 0);
-    if constexpr (FMT == FMT_SPLIT) {
+    if constexpr (FMT != FMT_TF32) {
       if constexpr (PAIR) umma_f16_2cta(tmem_d, ad, bd, idesc, acc); else umma_f16(tmem_d, ad, bd, idesc, acc);
     } else {
       if constexpr (PAIR) umma_tf32_2cta(tmem_d, ad, bd, idesc, acc); else umma_tf32(tmem_d, ad, bd, idesc, acc);
@@ -655,9 +663,9 @@ static void pick_tile(int H, int W, int* bw, int* bh, int* bn) {
   *bw = w; *bh = h; *bn = 128 / (w * h);
 }
 
-bool conv_tc_supported_fwd(const ConvShape& s) {
+bool conv_tc_supported_fwd(const ConvShape& s, int fmt) {
   // Cout need not fill a UMMA tile: filter rows beyond Cout are TMA out-of-bounds zeros and the epilogue masks them
-  if (s.Cin % 32 != 0 || s.Cout < 1) return false;
+  if (s.Cin % (fmt == FMT_BF16 ? 64 : 32) != 0 || s.Cout < 1) return false;
   if (s.k != 1 && s.k != 3 && s.k != 5) return false;
   int bw, bh, bn;
   pick_tile(s.H, s.W, &bw, &bh, &bn);
@@ -714,7 +722,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(abar + 4 * EPI_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cchunks = p.Cin >> 5;
+  constexpr int CSH = fmt_csh<FMT>();
+  const int cchunks = p.Cin >> CSH;
   const int num_kb = p.ks * p.ks * cchunks;
   const int pad = p.ks >> 1;
 
@@ -746,7 +755,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_fwd_tc2(const __grid_constant__
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[st], ph ^ 1);
           mbar_expect_tx(&full[st], SM::STAGE_BYTES);
-          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) << 5;
+          const int tap = kb / cchunks, c0 = (kb - tap * cchunks) << CSH;
           const int r = tap / p.ks, s = tap - r * p.ks;
           uint8_t* sa = smem + st * SM::STAGE_BYTES;
           tma_load_4d(sa, &map_x, &full[st], c0, w0 + s - pad, h0 + r - pad, n0);
@@ -954,7 +963,8 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(abar + 4 * EPI_NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cchunks = p.Cin >> 5;
+  constexpr int CSH = fmt_csh<FMT>();
+  const int cchunks = p.Cin >> CSH;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -986,7 +996,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
             for (int t = 0; t < T; ++t) {        // the T pixel tiles of an item are consecutive in (n, tile row, tile column) order
               const int lin = mt * T + t;
               const int tw = lin % p.tiles_w, th = (lin / p.tiles_w) % p.tiles_h, n = lin / (p.tiles_w * p.tiles_h);
-              tma_load_4d(smem + st * SM::A_BYTES + t * SM::BOX_BYTES, &map_x, &a_full[st], ch << 5, tw * 8 - PADW, th * 16 - PADH, n);
+              tma_load_4d(smem + st * SM::A_BYTES + t * SM::BOX_BYTES, &map_x, &a_full[st], ch << CSH, tw * 8 - PADW, th * 16 - PADH, n);
             }
             ++ai;
           }
@@ -994,7 +1004,7 @@ __global__ void __launch_bounds__(192, 1) k_conv_halo(const __grid_constant__ CU
             const int st = bi % B_STAGES;
             mbar_wait(&b_empty[st], ((bi / B_STAGES) & 1) ^ 1);
             mbar_expect_tx(&b_full[st], SM::B_BYTES);
-            tma_load_2d(smem + SM::B_OFF + st * SM::B_BYTES, &map_w, &b_full[st], tap * p.Cin + (ch << 5), col0);
+            tma_load_2d(smem + SM::B_OFF + st * SM::B_BYTES, &map_w, &b_full[st], tap * p.Cin + (ch << CSH), col0);
           }
         }
       }
@@ -1132,9 +1142,9 @@ static int launch_halo_f(const float* x, const float* w, const float* bias, cons
   p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4) | (fast_epi() << 12)) : 0;
   p.stats = p.tma_store ? stats : nullptr;
   CUtensorMap mx, mw, my;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B, FMT == FMT_BF16);
   if (r) return r;
-  r = make_map_2d(&mw, w, s.Cout, (long long)KH * KW * s.Cin, BLOCK_N);
+  r = make_map_2d(&mw, w, s.Cout, (long long)KH * KW * s.Cin, BLOCK_N, FMT == FMT_BF16);
   if (r) return r;
   my = mx;
   if (p.tma_store) {
@@ -1156,6 +1166,10 @@ template <int BLOCK_N, int T, int A_STAGES, int B_STAGES, int KH, int KW>
 static int launch_halo_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                          float* stats, cudaStream_t st, int fmt) {
   if (fmt == FMT_SPLIT) return launch_halo_f<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT_SPLIT>(x, w, bias, addend, y, s, stats, st);
+  if (fmt == FMT_BF16) {         // plain bf16 operands: the dgrad of the residual blocks (3x3 only)
+    if constexpr (KH == 3 && KW == 3) return launch_halo_f<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT_BF16>(x, w, bias, addend, y, s, stats, st);
+    else return -9;
+  }
   return launch_halo_f<BLOCK_N, T, A_STAGES, B_STAGES, KH, KW, FMT_TF32>(x, w, bias, addend, y, s, stats, st);
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -1264,7 +1278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  constexpr int CSH = 5;                    // log2(channels per 128-byte chunk), both operand formats
+  constexpr int CSH = fmt_csh<FMT>();       // log2(channels per 128-byte row)
   const int cchunks = p.Cin >> CSH;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
@@ -1445,9 +1459,9 @@ static int launch_halo2_f(const float* x, const float* w, const float* bias, con
   p.tma_store = 1 | (addend_mode() << 4) | (fast_epi() << 12);
   p.stats = stats;
   CUtensorMap mx, mw, my;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, SM::ROWS, 1, CU_TENSOR_MAP_SWIZZLE_128B, FMT == FMT_BF16);
   if (r) return r;
-  r = make_map_2d(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2);
+  r = make_map_2d(&mw, w, s.Cout, (long long)9 * s.Cin, BLOCK_N / 2, FMT == FMT_BF16);
   if (r) return r;
   r = make_store_map(&my, y, s.N, s.H, s.W, s.Cout, 8, 4, 1);
   if (r) return r;
@@ -1466,6 +1480,7 @@ template <int BLOCK_N, int T, int A_STAGES, int B_STAGES>
 static int launch_halo2_t(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                           float* stats, cudaStream_t st, int fmt) {
   if (fmt == FMT_SPLIT) return launch_halo2_f<BLOCK_N, T, A_STAGES, B_STAGES, FMT_SPLIT>(x, w, bias, addend, y, s, stats, st);
+  if (fmt == FMT_BF16) return launch_halo2_f<BLOCK_N, T, A_STAGES, B_STAGES, FMT_BF16>(x, w, bias, addend, y, s, stats, st);
   return launch_halo2_f<BLOCK_N, T, A_STAGES, B_STAGES, FMT_TF32>(x, w, bias, addend, y, s, stats, st);
 }
 static int launch_halo2(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
@@ -1693,7 +1708,7 @@ static bool splitk_enabled() {
   }
   return v != 0;
 }
-static SplitKPlan splitk_plan(const ConvShape& s) {
+static SplitKPlan splitk_plan(const ConvShape& s, int fmt = FMT_TF32) {
   SplitKPlan pl{0, 1, 0, 0};
   int bw, bh, bn;
   pick_tile(s.H, s.W, &bw, &bh, &bn);
@@ -1702,7 +1717,7 @@ static SplitKPlan splitk_plan(const ConvShape& s) {
   // few-tile layers: keep the WIDEST N tile (a narrow tile re-streams the A tiles Cout/block_n times and pins the kernel
   // at the L2->SM ceiling: 8x8x512->512 with 64-wide tiles moved 442 MB per launch) and fill the SMs by splitting K instead
   int block_n = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : (s.Cout > 32 ? 64 : 32));
-  const int num_kb = s.k * s.k * (s.Cin / 32);
+  const int num_kb = s.k * s.k * (s.Cin / (fmt == FMT_BF16 ? 64 : 32));      // k-blocks = (tap, 128-byte channel chunk)
   pl.kb_per = num_kb;
   pl.npad = tiles_n * bn;
   const long long wide_tiles = (long long)m_tiles * ((s.Cout + block_n - 1) / block_n);
@@ -1728,7 +1743,9 @@ size_t conv_tc_splitk_scratch_bytes(const ConvShape& s) {
 int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const float* addend, float* y, const ConvShape& s,
                        cudaStream_t st, float* stats, void* scratch, size_t scratch_bytes, int fmt) {
   FwdParams p;
-  p.ksplit = 1; p.kb_per = s.k * s.k * (s.Cin / 32); p.npad = 0;
+  const bool b16 = fmt == FMT_BF16;
+  if (b16 && s.Cin % 64 != 0) return -9;
+  p.ksplit = 1; p.kb_per = s.k * s.k * (s.Cin / (b16 ? 64 : 32)); p.npad = 0;
   p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
   pick_tile(s.H, s.W, &p.bw, &p.bh, &p.bn);
   p.tiles_w = s.W / p.bw; p.tiles_h = s.H / p.bh;
@@ -1737,8 +1754,9 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
   const int tiles_n = (s.N + p.bn - 1) / p.bn;
   const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   if (fwd_kernel_version() != 1 && halo_mode() != 0 && halo_eligible(s)) return launch_halo(x, w, bias, addend, y, s, stats, st, fmt);
+  if (b16 && fwd_kernel_version() == 1) return -9;
   CUtensorMap mx, mw;
-  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn);
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.bw, p.bh, p.bn, CU_TENSOR_MAP_SWIZZLE_128B, b16);
   if (r) return r;
   if (fwd_kernel_version() == 1) {
     if (fmt != FMT_TF32) return -9;             // the first-generation kernel (SIVAE_TC_FWD=1, experiments only) is tf32-only
@@ -1750,13 +1768,14 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
     return launch_fwd_t<32, 4>(mx, mw, p, m_tiles, st);
   }
   // v2: widest N tile that the layer fills; few-tile problems prefer narrower tiles (more CTAs busy) and split K
-  SplitKPlan pl = splitk_plan(s);
+  SplitKPlan pl = splitk_plan(s, fmt);
   const int block_n = pl.block_n;
-  if (pl.ksplit > 1 && (!scratch || scratch_bytes < (size_t)pl.ksplit * pl.npad * s.H * s.W * s.Cout * sizeof(float))) pl.ksplit = 1;
-  r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n);
+  if (pl.ksplit > 1 && (!scratch || scratch_bytes < (size_t)pl.ksplit * pl.npad * s.H * s.W * s.Cout * sizeof(float))) { pl.ksplit = 1; pl.kb_per = p.kb_per; }
+  r = make_map_2d(&mw, w, s.Cout, (long long)s.k * s.k * s.Cin, block_n, b16);
   if (r) return r;
   // epilogue store path: TMA store of each warp's 32-row slab (needs 16-byte aligned channel rows)
   CUtensorMap my = mx;
+  if (b16 && ((s.Cout & 3) != 0 || !tma_store_enabled())) return -9;      // (my = mx is only a placeholder for fp32 inputs)
   p.tma_store = ((s.Cout & 3) == 0 && tma_store_enabled()) ? (1 | (addend_mode() << 4) | (fast_epi() << 12)) : 0;
   p.stats = p.tma_store ? stats : nullptr;
   if (p.tma_store) {
@@ -1777,7 +1796,12 @@ int launch_conv_fwd_tc(const float* x, const float* w, const float* bias, const 
     r = make_store_map(&madd, (float*)p.addend, s.N, s.H, s.W, s.Cout, p.bw, p.sbh, p.sbn);
     if (r) return r;
   }
-  if (fmt == FMT_SPLIT) {
+  if (fmt == FMT_BF16) {
+    if (block_n == 256) r = launch_fwd2_t<256, 4, FMT_BF16>(mx, mw, my, madd, p, m_tiles, st);
+    else if (block_n == 128) r = launch_fwd2_t<128, 5, FMT_BF16>(mx, mw, my, madd, p, m_tiles, st);
+    else if (block_n == 64) r = launch_fwd2_t<64, 7, FMT_BF16>(mx, mw, my, madd, p, m_tiles, st);
+    else r = launch_fwd2_t<32, 8, FMT_BF16>(mx, mw, my, madd, p, m_tiles, st);
+  } else if (fmt == FMT_SPLIT) {
     if (block_n == 256) r = launch_fwd2_t<256, 4, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
     else if (block_n == 128) r = launch_fwd2_t<128, 5, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
     else if (block_n == 64) r = launch_fwd2_t<64, 7, FMT_SPLIT>(mx, mw, my, madd, p, m_tiles, st);
@@ -2251,6 +2275,379 @@ int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvS
   long long n = (long long)s.Cout * s.ktot();
   unsigned blocks = (unsigned)((n + 255) / 256);
   if (blocks > 148u * 8) blocks = 148u * 8;
+  k_wg_reduce<<<blocks, 256, 0, st>>>(p.part, dw, n, splits, accumulate ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 wgrad (residual blocks in the default mode): x = the bf16 copy of the forward activation, dy = the bf16 gradient that
+// the BatchNorm backward writes; plain NHWC bf16, 64 channels per 128-byte pixel row, both operands MN-major with the
+// ordinary 128B swizzle (16-bit MN-major needs no special atom), K = 16 pixels per kind::f16 MMA = half the tf32 tensor time.
+//
+// k_conv_wgrad_halo16 (3x3, H % 16 == 0, W % 8 == 0): one 16x8 pixel tile per item, ONE x halo box {64c, 10w, 18h} per item
+// and dy tile {64c, 8w, 16h}; for filter row r and the image-row PAIR (h, h+1) one MMA with
+//     A = x halo from pixel row (h + r) * 10 + 2p: two MN chunks 128 B (one pixel = one filter column) apart -> taps s = 2p, 2p+1
+//         of 64 input channels (M = 128), two K groups (the 8 pixels of image row h + r, resp. h + r + 1) 1280 B apart;
+//     B = dy tile from pixel row h * 8: 64 output channels, K groups 1024 B apart.
+// p = 0 gives taps 0,1; p = 1 gives tap 2 plus a phantom tap (its accumulator rows are never read).  Accumulators of all
+// (r, p) stay in TMEM (6 x 64 columns) over the CTA's pixel range; split over pixel tiles, partials reduced in fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WG16_DY_BYTES = 16 * 8 * 128;
+template <int STAGES>
+struct Wg16Smem {
+  static constexpr int BW = 10;
+  static constexpr int X_TX = 18 * BW * 128;
+  static constexpr int X_BYTES = (X_TX + 1023) / 1024 * 1024 + 1024;     // + slack: the phantom tap reads 1 pixel past the box
+  static constexpr int STAGE_BYTES = X_BYTES + WG16_DY_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static constexpr int TMEM_COLS = 512;      // 3 filter rows x 2 tap pairs x 64 columns = 384
+};
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1) k_conv_wgrad_halo16(const __grid_constant__ CUtensorMap map_x,
+                                                              const __grid_constant__ CUtensorMap map_dy, const Wg2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = Wg16Smem<STAGES>;
+  constexpr int BW = SM::BW, NT = 64;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = blockIdx.x;                  // 64-channel input chunk
+  const int col0 = blockIdx.y * NT;           // first output channel
+  const long long it_begin = (long long)blockIdx.z * p.items_per_split;
+  long long it_end = it_begin + p.items_per_split;
+  if (it_end > p.items_total) it_end = p.items_total;
+  const int num_items = (int)(it_end > it_begin ? it_end - it_begin : 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < num_items; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(&empty[st], ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)(SM::X_TX + WG16_DY_BYTES));
+        const long long item = it_begin + i;
+        const int tw = (int)(item % p.tiles_w), th = (int)((item / p.tiles_w) % p.tiles_h);
+        const int n = (int)(item / ((long long)p.tiles_w * p.tiles_h));
+        uint8_t* sa = smem + st * SM::STAGE_BYTES;
+        tma_load_4d(sa, &map_x, &full[st], cg * 64, tw * 8 - 1, th * 16 - 1, n);
+        tma_load_4d(sa + SM::X_BYTES, &map_dy, &full[st], col0, tw * 8, th * 16, n);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
+    if (elect_one())
+    for (int i = 0; i < num_items; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(&full[st], (i / STAGES) & 1);
+      const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
+      const uint32_t sb = sa + SM::X_BYTES;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)((r * 2 + pr) * NT);
+#pragma unroll
+          for (int hp = 0; hp < 8; ++hp) {
+            const int h = 2 * hp;
+            // MN-major, 128B swizzle: LBO = distance of the 64-wide MN chunks, SBO = distance of the 8-row K groups
+            const uint64_t ad = make_smem_desc(sa + (uint32_t)(((h + r) * BW + 2 * pr) * 128), 128, BW * 128, 2);
+            const uint64_t bd = make_smem_desc(sb + (uint32_t)(h * 8 * 128), WG16_DY_BYTES, 1024, 2);
+            umma_f16(tmem_d, ad, bd, idesc, (i > 0 || hp > 0) ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(&empty[st]);
+      if (i == num_items - 1) umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;          // accumulator rows 32q .. 32q+31: tap (2 pr + q / 2), input channel (q & 1) * 32 + lane
+    if (num_items > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    float* dst = p.part + (long long)blockIdx.z * p.Cout * p.Ktot;
+    const int ci = cg * 64 + (q & 1) * 32 + lane;
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+      for (int pr = 0; pr < 2; ++pr) {
+        const int s_tap = 2 * pr + (q >> 1);
+        if (s_tap > 2) continue;                    // phantom tap
+        const int kidx = (r * 3 + s_tap) * p.Cin + ci;
+#pragma unroll 1
+        for (int c = 0; c < NT; c += 32) {
+          if (col0 + c >= p.Cout) break;
+          uint32_t v[32];
+          if (num_items > 0) {
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((r * 2 + pr) * NT + c), v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = col0 + c + j;
+            if (co < p.Cout) dst[(long long)co * p.Ktot + kidx] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc<SM::TMEM_COLS>(tmem_base); }
+}
+// generic bf16 wgrad (1x1 convs, maps smaller than a 16x8 tile): K block = 32 pixels (two MMAs), A = two 64-row (tap, ci) chunks
+// (Cin % 64 == 0 keeps a chunk inside one tap), B = BLOCK_N / 64 chunks of dy
+template <int BLOCK_N, int STAGES>
+struct Wg16tSmem {
+  static constexpr int A_BYTES = 2 * WG_CHUNK_BYTES;
+  static constexpr int B_BYTES = (BLOCK_N / 64) * WG_CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192) k_conv_wgrad_tc16(const __grid_constant__ CUtensorMap map_x,
+                                                         const __grid_constant__ CUtensorMap map_dy, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using SM = Wg16tSmem<BLOCK_N, STAGES>;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;            // first (tap, ci) row of this tile
+  const int col0 = blockIdx.y * BLOCK_N;
+  const long long kb_begin = (long long)blockIdx.z * p.kb_per_split;
+  long long kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.kb_total) kb_end = p.kb_total;
+  const int num_kb = (int)(kb_end > kb_begin ? kb_end - kb_begin : 0);
+  const int pad = p.ks >> 1;
+  int a_chunks = (p.Ktot - m0 + 63) / 64;
+  if (a_chunks > 2) a_chunks = 2;
+  int b_chunks = (p.Cout - col0 + 63) / 64;
+  if (b_chunks > BLOCK_N / 64) b_chunks = BLOCK_N / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(&empty[st], ((i / STAGES) & 1) ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)(a_chunks + b_chunks) * WG_CHUNK_BYTES);
+        const long long kb = kb_begin + i;
+        const int tw = (int)(kb % p.tiles_w);
+        const int th = (int)((kb / p.tiles_w) % p.tiles_h);
+        const int tn = (int)(kb / ((long long)p.tiles_w * p.tiles_h));
+        const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.pn;
+        uint8_t* sa = smem + st * SM::STAGE_BYTES;
+        for (int j = 0; j < a_chunks; ++j) {
+          const int m = m0 + 64 * j;
+          const int tap = m / p.Cin, c0 = m - tap * p.Cin;
+          const int r = tap / p.ks, s = tap - r * p.ks;
+          tma_load_4d(sa + j * WG_CHUNK_BYTES, &map_x, &full[st], c0, w0 + s - pad, h0 + r - pad, n0);
+        }
+        uint8_t* sb = sa + SM::A_BYTES;
+        for (int j = 0; j < b_chunks; ++j)
+          tma_load_4d(sb + j * WG_CHUNK_BYTES, &map_dy, &full[st], col0 + 64 * j, w0, h0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+    if (elect_one())
+    for (int i = 0; i < num_kb; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(&full[st], (i / STAGES) & 1);
+      const uint32_t sa = smem_u32(smem + st * SM::STAGE_BYTES);
+      const uint32_t sb = sa + SM::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        // 16 pixels (K) per MMA = two 8-row groups 1024 B apart; MN chunks (64 rows / channels) one box (4096 B) apart
+        const uint64_t ad = make_smem_desc(sa + k * 2048, WG_CHUNK_BYTES, 1024, 2);
+        const uint64_t bd = make_smem_desc(sb + k * 2048, WG_CHUNK_BYTES, 1024, 2);
+        umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty[st]);
+      if (i == num_kb - 1) umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool valid = m < p.Ktot && num_kb > 0 && (q >> 1) < a_chunks;
+    float* dst = p.part + (long long)blockIdx.z * p.Cout * p.Ktot;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (m < p.Ktot) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = col0 + c + j;
+          if (co < p.Cout) dst[(long long)co * p.Ktot + m] = valid ? __uint_as_float(v[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc<BLOCK_N>(tmem_base); }
+}
+bool conv_tc_supported_wgrad16(const ConvShape& s) {
+  if (s.Cin % 64 != 0 || s.Cout % 64 != 0 || (s.k != 1 && s.k != 3)) return false;
+  int pw, ph, pn;
+  pick_pixel_block(s.H, s.W, &pw, &ph, &pn);
+  return pn <= 256;
+}
+static bool wgrad_halo16_supported(const ConvShape& s) {
+  return wgrad_halo_mode() != 0 && s.k == 3 && s.H % 16 == 0 && s.W % 8 == 0;
+}
+static Wg2Plan wg16_plan(const ConvShape& s) {
+  Wg2Plan pl;
+  pl.n_tile = 64; pl.g = 1;
+  pl.cgroups = s.Cin / 64;
+  pl.ntiles = s.Cout / 64;
+  pl.items = (long long)s.N * (s.H / 16) * (s.W / 8);
+  const long long pairs = (long long)pl.cgroups * pl.ntiles;
+  long long want = 1, best = -1;
+  for (long long w = 1; w <= pl.items && w <= 2 * num_sms(); ++w) {
+    const long long per = (pl.items + w - 1) / w;
+    const long long waves = (pairs * ((pl.items + per - 1) / per) + num_sms() - 1) / num_sms();
+    const long long cost = waves * (per + 16);
+    if (best < 0 || cost < best) { best = cost; want = w; }
+  }
+  pl.per = (pl.items + want - 1) / want;
+  pl.splits = (int)((pl.items + pl.per - 1) / pl.per);
+  return pl;
+}
+static void wg16t_plan(const ConvShape& s, int* bn, int* splits, long long* kb_total, long long* kb_per_split) {
+  int pw, ph, pn;
+  pick_pixel_block(s.H, s.W, &pw, &ph, &pn);
+  const long long kbt = (long long)(s.W / pw) * (s.H / ph) * ((s.N + pn - 1) / pn);
+  *bn = s.Cout > 128 ? 256 : (s.Cout > 64 ? 128 : 64);
+  const long long tiles = (long long)((s.ktot() + 127) / 128) * ((s.Cout + *bn - 1) / *bn);
+  long long want = (num_sms() * 2 + tiles - 1) / tiles;
+  const long long maxs = (kbt + 7) / 8;       // at least 8 pixel blocks per CTA
+  long long sp = want < maxs ? want : maxs;
+  if (sp < 1) sp = 1;
+  if (sp > 512) sp = 512;
+  const long long per = (kbt + sp - 1) / sp;
+  sp = (kbt + per - 1) / per;
+  *splits = (int)sp; *kb_total = kbt; *kb_per_split = per;
+}
+size_t conv_wgrad_tc16_scratch_bytes(const ConvShape& s) {
+  if (wgrad_halo16_supported(s)) return (size_t)wg16_plan(s).splits * s.Cout * s.ktot() * sizeof(float);
+  int bn, splits; long long kbt, per;
+  wg16t_plan(s, &bn, &splits, &kbt, &per);
+  return (size_t)splits * s.Cout * s.ktot() * sizeof(float);
+}
+template <int BLOCK_N, int STAGES>
+static int launch_wg16t(const CUtensorMap& mx, const CUtensorMap& mdy, const WgParams& p, int splits, cudaStream_t st) {
+  using SM = Wg16tSmem<BLOCK_N, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_tc16<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  dim3 grid((p.Ktot + 127) / 128, (p.Cout + BLOCK_N - 1) / BLOCK_N, splits);
+  g_launches += 2;
+  k_conv_wgrad_tc16<BLOCK_N, STAGES><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
+  return (int)cudaGetLastError();
+}
+// x: bf16 NHWC [N,H,W,Cin], dy: bf16 NHWC [N,H,W,Cout]; dw fp32 [Cout][k][k][Cin] (+= if accumulate)
+int launch_conv_wgrad_tc16(const void* x, const void* dy, float* dw, const ConvShape& s, bool accumulate, void* scratch,
+                           size_t scratch_bytes, cudaStream_t st) {
+  if (!conv_tc_supported_wgrad16(s)) return -9;
+  const long long n = (long long)s.Cout * s.ktot();
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (blocks > 148u * 8) blocks = 148u * 8;
+  CUtensorMap mx, mdy;
+  if (wgrad_halo16_supported(s)) {
+    using SM = Wg16Smem<4>;
+    static_assert(SM::TOTAL <= 232448, "shared memory budget exceeded");
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(k_conv_wgrad_halo16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+      if (e != cudaSuccess) return (int)e;
+      attr = true;
+    }
+    const Wg2Plan pl = wg16_plan(s);
+    if (scratch_bytes < (size_t)pl.splits * n * sizeof(float)) return -103;
+    Wg2Params p;
+    p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.Ktot = 9 * s.Cin;
+    p.tiles_w = s.W / 8; p.tiles_h = s.H / 16;
+    p.items_total = pl.items; p.items_per_split = pl.per;
+    p.part = (float*)scratch;
+    int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, SM::BW, 18, 1, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (r) return r;
+    r = make_map_nhwc(&mdy, dy, s.N, s.H, s.W, s.Cout, 8, 16, 1, CU_TENSOR_MAP_SWIZZLE_128B, true);
+    if (r) return r;
+    dim3 grid(pl.cgroups, pl.ntiles, pl.splits);
+    g_launches += 2;
+    k_conv_wgrad_halo16<4><<<grid, 192, SM::TOTAL, st>>>(mx, mdy, p);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return (int)ce;
+    k_wg_reduce<<<blocks, 256, 0, st>>>((const float*)scratch, dw, n, pl.splits, accumulate ? 1 : 0);
+    return (int)cudaGetLastError();
+  }
+  WgParams p;
+  p.N = s.N; p.H = s.H; p.W = s.W; p.Cin = s.Cin; p.Cout = s.Cout; p.ks = s.k;
+  pick_pixel_block(s.H, s.W, &p.pw, &p.ph, &p.pn);
+  p.tiles_w = s.W / p.pw; p.tiles_h = s.H / p.ph;
+  int bn, splits;
+  wg16t_plan(s, &bn, &splits, &p.kb_total, &p.kb_per_split);
+  p.Ktot = (int)s.ktot();
+  p.part = (float*)scratch;
+  if (scratch_bytes < (size_t)splits * n * sizeof(float)) return -103;
+  int r = make_map_nhwc(&mx, x, s.N, s.H, s.W, s.Cin, p.pw, p.ph, p.pn, CU_TENSOR_MAP_SWIZZLE_128B, true);
+  if (r) return r;
+  r = make_map_nhwc(&mdy, dy, s.N, s.H, s.W, s.Cout, p.pw, p.ph, p.pn, CU_TENSOR_MAP_SWIZZLE_128B, true);
+  if (r) return r;
+  if (bn == 256) r = launch_wg16t<256, 4>(mx, mdy, p, splits, st);
+  else if (bn == 128) r = launch_wg16t<128, 5>(mx, mdy, p, splits, st);
+  else r = launch_wg16t<64, 6>(mx, mdy, p, splits, st);
+  if (r) return r;
   k_wg_reduce<<<blocks, 256, 0, st>>>(p.part, dw, n, splits, accumulate ? 1 : 0);
   return (int)cudaGetLastError();
 }

@@ -32,7 +32,8 @@ static int fail(int code, const std::string& msg) {
 namespace {
 
 struct Conv { int cin = 0, cout = 0, k = 0; long long w_off = -1, b_off = -1, wd_off = -1, wr_off = -1, wn_off = -1, wg_off = -1,
-              wl_off = -1, wdl_off = -1;   /* 3xTF32 mode: low parts of the forward / dgrad-packed filter */ };
+              wl_off = -1, wdl_off = -1;   /* 3xTF32 mode: low parts of the forward / dgrad-packed filter */
+              long long wdh_off = -1;      /* plain bf16 form of the dgrad-packed filter (bf16 backward of the residual blocks) */ };
 struct Bn { int c = 0; long long g_off = -1, b_off = -1, rm_off = -1; int idx = -1; };
 struct Lin { int fin = 0, fout = 0; long long w_off = -1, b_off = -1; };
 struct Block { int inc = 0, outc = 0, size = 0, mode = RS_NONE; bool expand = false; Conv ce, c1, c2; Bn bn1, bn2; };
@@ -70,7 +71,7 @@ struct EncPass {
 };
 struct DecPass {
   const float* zin = nullptr;
-  float *h = nullptr, *x0 = nullptr, *x0s = nullptr, *y = nullptr;
+  float *h = nullptr, *x0 = nullptr, *x0s = nullptr, *x0h = nullptr, *y = nullptr;
   double* ema = nullptr;           // EMA inputs (batch mean | unbiased var) of every BN of the pass, in the net's BN buffer layout
   const void* net = nullptr;       // the weight set the slot's activations were computed with (pass re-use check)
   std::vector<BlockAct> blk;
@@ -99,7 +100,9 @@ struct sivae_engine {
   bool rnd = false;                // producers round stored activations / gradients to tf32 (plain tensor-core mode only)
   bool fsplit = false;             // default tensor-core mode: FORWARD convs consume split32 operands (bf16 hi + lo, three
                                    // kind::f16 MMAs per product: fp32-class products, ELBO / KL within 1e-4 of the reference);
-                                   // dgrad / wgrad stay kind::tf32 on the tf32-rounded fp32 tensors
+                                   // dgrad / wgrad stay kind::tf32 on the tf32-rounded fp32 tensors, unless:
+  bool bwd16 = false;              // (with fsplit) dgrad / wgrad of the residual blocks run kind::f16 on plain bf16 operands: the
+                                   // BatchNorm backward writes bf16 gradients, the forward keeps bf16 copies of its activations
   bool bn_mask = true;             // residual BN+LeakyReLU forward stores sign bytes so its backward skips the identity re-read (SIVAE_BN_MASK=0: off)
   float* split[4] = {nullptr, nullptr, nullptr, nullptr};   // comp: hi / lo parts of the two conv operands, max activation size each
   // workspace
@@ -149,6 +152,7 @@ static void add_conv(Net& n, const std::string& name, Conv& c, int cin, int cout
   const long long wide = cin > cout ? cin : cout;
   c.wn_off = n.derived_floats; n.derived_floats += narrow ? wide * 160 : (long long)cout * cin * k * k;
   if (narrow) { c.wg_off = n.derived_floats; n.derived_floats += wide * 80; }
+  c.wdh_off = n.derived_floats; n.derived_floats += ((long long)cout * cin * k * k + 7) / 8 * 4;
   if (n.comp) {
     c.wl_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
     c.wdl_off = n.derived_floats; n.derived_floats += (long long)cout * cin * k * k;
@@ -253,6 +257,7 @@ static size_t reduce_scratch_bytes(const sivae_engine* e) {
     size_t a = conv_wgrad_simt_scratch_bytes(s);
     if (a > m) m = a;
     if (conv_tc_supported_wgrad(s)) { size_t t = conv_wgrad_tc_scratch_bytes(s); if (t > m) m = t; }
+    if (conv_tc_supported_wgrad16(s)) { size_t t = conv_wgrad_tc16_scratch_bytes(s); if (t > m) m = t; }
     { int parts = conv_tc_stats_parts(s); if (parts > 0) { size_t t = bn_parts_scratch_bytes(parts, cv.cout); if (t > m) m = t; } }
     if ((cv.cin <= 3 || cv.cout <= 3) && cv.k == 5) {
       const int wide = cv.cin > cv.cout ? cv.cin : cv.cout, c = cv.cin > cv.cout ? cv.cout : cv.cin;
@@ -319,6 +324,7 @@ static size_t carve(sivae_engine* e, char* base) {
     p.h = bp.take<float>(B * e->feat);
     p.x0 = bp.take<float>(B * e->feat);
     p.x0s = e->fsplit ? bp.take<float>(B * e->feat) : nullptr;
+    p.x0h = e->bwd16 ? bp.take<float>((B * e->feat + 1) / 2) : nullptr;
     p.blk.assign(dn.blocks.size(), BlockAct());
     for (size_t i = 0; i < dn.blocks.size(); ++i) {
       const Block& b = dn.blocks[i];
@@ -370,8 +376,9 @@ static size_t carve(sivae_engine* e, char* base) {
 
 // ---- optional per-kernel-class timing (CUDA events on the launching stream), used by bench.py's roofline ---------
 // PC_TC_FWD3 = forward convs on split32 operands (three kind::f16 MMAs per product); PC_TC_FWD = kind::tf32 forward / dgrad
-enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_TC_FWD3 = 5, PC_COUNT = 6,
-       PC_BN_FWD = 6, PC_BN_BWD = 7 };      // classes >= PC_COUNT appear in sivae_profile_dump only (bytes in the flops slot)
+// PC_TC_DG16 / PC_TC_WG16 = dgrad / wgrad of the residual blocks on plain bf16 operands (kind::f16, one MMA per product)
+enum { PC_TC_FWD = 0, PC_TC_WGRAD = 1, PC_SIMT_FWD = 2, PC_SIMT_WGRAD = 3, PC_LOSS = 4, PC_TC_FWD3 = 5, PC_TC_DG16 = 6, PC_TC_WG16 = 7,
+       PC_COUNT = 8, PC_BN_FWD = 8, PC_BN_BWD = 9 };      // classes >= PC_COUNT appear in sivae_profile_dump only (bytes in the flops slot)
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; ConvShape shape; };
 struct Prof {
   bool on = false;
@@ -427,6 +434,7 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
     const bool d_tc = fwd_on_tc(e, sd) && !fwd_on_narrow(e, sd);
     launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, d_tc && !e->comp, st);
     if (d_tc && e->comp) launch_split_tf32(n.derived + c.wd_off, n.derived + c.wd_off, n.derived + c.wdl_off, wn, st);
+    if (e->bwd16 && c.k != 5) launch_pack_dgrad_filter_bf16(n.params + c.w_off, n.derived + c.wdh_off, c.cout, c.cin, c.k, st);
     ConvShape sf{1, size, size, c.cin, c.cout, c.k};
     if (fwd_on_tc(e, sf) && !fwd_on_narrow(e, sf)) {
       if (e->comp) launch_split_tf32(n.params + c.w_off, n.derived + c.wr_off, n.derived + c.wl_off, wn, st);
@@ -462,7 +470,7 @@ static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const f
                     const float* bias, const float* addend, float* y, cudaStream_t st, float* stats = nullptr,
                     const float* w_narrow = nullptr, const float* w_gather = nullptr, const float* w_lo = nullptr,
                     int fmt = FMT_TF32_) {
-  const int pc_fwd = fmt == FMT_SPLIT_ ? PC_TC_FWD3 : PC_TC_FWD;
+  const int pc_fwd = fmt == FMT_SPLIT_ ? PC_TC_FWD3 : (fmt == FMT_BF16_ ? PC_TC_DG16 : PC_TC_FWD);
   if (fwd_on_rowsep_in(e, s) && w_narrow) {
     ProfScope ps(pc_fwd, s, st);
     int r = launch_conv_rowsep_in(x, w_narrow, bias, addend, y, s, e->rs, stats, st, fmt);
@@ -471,8 +479,8 @@ static int conv_any(sivae_engine* e, const ConvShape& s, const float* x, const f
     ProfScope ps(pc_fwd, s, st);
     int r = launch_conv_rowsep_out(x, w_gather, bias, addend, y, s, e->rs, st, fmt);
     if (r) return fail(r, "row-separable tcgen05 conv launch failed");
-  } else if (fmt == FMT_SPLIT_) {
-    if (!fwd_on_tc(e, s)) return fail(-7, "split32 forward conv: shape not served by a tensor-core kernel");
+  } else if (fmt != FMT_TF32_) {
+    if (!e->tc || !conv_tc_supported_fwd(s, fmt)) return fail(-7, "split32 / bf16 conv: shape not served by a tensor-core kernel");
     ProfScope ps(pc_fwd, s, st);
     int r = launch_conv_fwd_tc(x, w_tc, bias, addend, y, s, st, stats, e->sk, e->sk_bytes, fmt);
     if (r) return fail(r, "tcgen05 conv launch failed");
@@ -530,14 +538,26 @@ static int conv_bn_stats(sivae_engine* e, Net& n, const Conv& c, const Bn& bn, c
   return 0;
 }
 // dx = conv_transpose(dy, W) (+addend): a forward conv over dy with the packed dgrad filters
-static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st) {
+// dy16: dy is a plain bf16 tensor (written by the BatchNorm backward with out16) -> kind::f16 dgrad with the bf16 filter
+static int conv_dgrad(sivae_engine* e, Net& n, const Conv& c, const float* dy, float* dx, const float* addend, int B, int size, cudaStream_t st,
+                      bool dy16 = false) {
   ConvShape s{B, size, size, c.cout, c.cin, c.k};
+  if (dy16)
+    return conv_any(e, s, dy, nullptr, n.derived + c.wdh_off, nullptr, addend, dx, st, nullptr, nullptr, nullptr, nullptr, FMT_BF16_);
   return conv_any(e, s, dy, n.derived + c.wd_off, n.derived + c.wd_off, nullptr, addend, dx, st, nullptr, n.derived + c.wn_off,
                   c.wg_off >= 0 ? n.derived + c.wg_off : nullptr, c.wdl_off >= 0 ? n.derived + c.wdl_off : nullptr);
 }
-static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st) {
+// op16: x and dy are plain bf16 tensors
+static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, const float* dy, int B, int size, cudaStream_t st,
+                      bool op16 = false) {
   ConvShape s{B, size, size, c.cin, c.cout, c.k};
   float* dw = n.grads + c.w_off;
+  if (op16) {
+    ProfScope ps(PC_TC_WG16, s, st);
+    int r = launch_conv_wgrad_tc16(x, dy, dw, s, true, e->red, e->red_bytes, st);
+    if (r) return fail(r, "tcgen05 bf16 conv wgrad launch failed");
+    return 0;
+  }
   if (e->tc && !e->comp && e->fast && e->rs && c.cin <= 3 && conv_rowsep_wgrad_supported(size, size, c.cin, c.cout, c.k)) {          // stem
     ProfScope ps(PC_TC_WGRAD, s, st);
     int r = launch_conv_rowsep_wgrad(x, dy, dw, B, size, size, c.cin, c.cout, 1, true, e->rs, e->red, e->red_bytes, st);
@@ -582,7 +602,7 @@ static int conv_wgrad(sivae_engine* e, Net& n, const Conv& c, const float* x, co
 // x: the fp32 block input (wgrad operand; unused by the forward in split-forward mode), xs: its split32 copy (split-forward
 // mode).  keep: this pass will run wgrad, so the fp32 tf32-rounded copies of a1 / out are written next to the split32 ones.
 static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, const float* x, const float* xs, int B, bool train,
-                         bool keep, cudaStream_t st, double* ema = nullptr) {
+                         bool keep, bool last, cudaStream_t st, double* ema = nullptr) {
   a.x = x; a.xs = xs;
   const int s = b.size;
   const bool sp = e->fsplit;
@@ -590,15 +610,20 @@ static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, c
   const float* idn = xin;
   if (b.expand) { TRY(conv_fwd(e, n, b.ce, xin, a.id, nullptr, B, s, st)); idn = a.id; }
   TRY(conv_bn_stats(e, n, b.c1, b.bn1, xin, a.t1, a.mi1, B, s, train, st, ema));
-  { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0 + ((sp && keep) ? 1.0 : 0.0), st);
-    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, (sp && !keep) ? nullptr : a.a1, B, s, s,
-                      b.outc, RS_NONE, e->rnd, st, nullptr, sp ? a.a1s : nullptr); }
+  // wgrad operand copy of a1 (keep): fp32 tf32-rounded, or plain bf16 in the same buffer (bwd16)
+  const bool h16 = e->bwd16;
+  { ProfElem pe(PC_BN_FWD, B, s, b.outc, RS_NONE, 2.0 + ((sp && keep) ? (h16 ? 0.5 : 1.0) : 0.0), st);
+    launch_bn_act_fwd(a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, (sp && (!keep || h16)) ? nullptr : a.a1, B, s, s,
+                      b.outc, RS_NONE, e->rnd, st, nullptr, sp ? a.a1s : nullptr, false, (sp && keep && h16) ? a.a1 : nullptr); }
   TRY(conv_bn_stats(e, n, b.c2, b.bn2, sp ? a.a1s : a.a1, a.t2, a.mi2, B, s, train, st, ema));
-  // the fp32 `out` is needed by the next conv's wgrad (keep) or, without a split32 twin (last encoder block), by the fc layer
-  const bool f32_out = !sp || keep || !a.outs;
-  { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode) * ((sp && a.outs && f32_out) ? 2.0 : 1.0), st);
+  // copies of `out` next to the split32 one: fp32 for the fc layer (last encoder block: no split32 twin) and for the
+  // row-separable tf32 wgrad of `predict` (last decoder block, keep); otherwise (keep) the next block's wgrad operand:
+  // fp32 tf32-rounded, or plain bf16 in the same buffer (bwd16)
+  const bool f32_out = !sp || !a.outs || (keep && (!h16 || last));
+  const bool h_out = sp && a.outs && keep && h16 && !last;
+  { ProfElem pe(PC_BN_FWD, B, s, b.outc, 4 + b.mode, 2.0 + resampled(b.mode) * ((sp && a.outs) ? (f32_out ? 2.0 : (h_out ? 1.5 : 1.0)) : 1.0), st);
     launch_bn_act_fwd(a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, f32_out ? a.out : nullptr, B, s, s, b.outc,
-                      b.mode, (sp && !a.outs) ? false : e->rnd, st, a.m2, sp ? a.outs : nullptr, sp && !b.expand); }
+                      b.mode, (sp && !a.outs) ? false : e->rnd, st, a.m2, sp ? a.outs : nullptr, sp && !b.expand, h_out ? a.out : nullptr); }
   return 0;
 }
 
@@ -610,13 +635,13 @@ static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, in
   const bool sp = e->fsplit;
   p.img = img;
   TRY(conv_bn_stats(e, n, n.stem, n.stem_bn, img, p.t0, p.mi0, B, S, train, st));
-  { ProfElem pe(PC_BN_FWD, B, S, n.stem.cout, RS_POOL, 1.25 + ((sp && keep) ? 0.25 : 0.0), st);
-    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, (sp && !keep) ? nullptr : p.a0, B, S, S,
-                      n.stem.cout, RS_POOL, e->rnd, st, nullptr, sp ? p.a0s : nullptr); }
+  { ProfElem pe(PC_BN_FWD, B, S, n.stem.cout, RS_POOL, 1.25 + ((sp && keep) ? (e->bwd16 ? 0.125 : 0.25) : 0.0), st);
+    launch_bn_act_fwd(p.t0, nullptr, p.mi0, n.params + n.stem_bn.g_off, n.params + n.stem_bn.b_off, (sp && (!keep || e->bwd16)) ? nullptr : p.a0,
+                      B, S, S, n.stem.cout, RS_POOL, e->rnd, st, nullptr, sp ? p.a0s : nullptr, false, (sp && keep && e->bwd16) ? p.a0 : nullptr); }
   const float* x = p.a0;
   const float* xs = p.a0s;
   for (size_t i = 0; i < n.blocks.size(); ++i) {
-    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, xs, B, train, keep, st));
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, xs, B, train, keep, i + 1 == n.blocks.size(), st));
     x = p.blk[i].out; xs = p.blk[i].outs;
   }
   // .view(B, -1) of the NCHW tensor (:117)
@@ -633,12 +658,13 @@ static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int 
   launch_linear_fwd(z, n.params + n.fc.w_off, n.params + n.fc.b_off, p.h, B, n.fc.fin, n.fc.fout, true, st);
   launch_nchw_to_nhwc(p.h, p.x0, B, e->C_last, e->hw_last, e->hw_last, st);
   if (e->fsplit) launch_split32(p.x0, p.x0s, (long long)B * e->feat, st);       // from the unrounded values
-  if (e->rnd) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
-  const float* x = p.x0;
+  if (e->bwd16) { if (keep) launch_to_bf16(p.x0, p.x0h, (long long)B * e->feat, st); }
+  else if (e->rnd) launch_round_tf32(p.x0, p.x0, (long long)B * e->feat, st);
+  const float* x = e->bwd16 ? p.x0h : p.x0;
   const float* xs = p.x0s;
   p.net = (train && (keep || !e->fsplit)) ? &n : nullptr;       // pass re-use needs the wgrad operands of this pass
   for (size_t i = 0; i < n.blocks.size(); ++i) {
-    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, xs, B, train, keep, st, train ? p.ema : nullptr));
+    TRY(block_forward(e, n, n.blocks[i], p.blk[i], x, xs, B, train, keep, i + 1 == n.blocks.size(), st, train ? p.ema : nullptr));
     x = p.blk[i].out; xs = p.blk[i].outs;
   }
   TRY(conv_fwd(e, n, n.predict, e->fsplit ? xs : x, p.y, nullptr, B, c.image_size, st));
@@ -657,27 +683,30 @@ static int block_backward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, 
   float* DA1 = e->sb[4];
   const float* idn = b.expand ? a.id : a.x;
   float* g = n.grads;
+  // bwd16: the conv operands among the gradients (dt of both BatchNorms; the identity-branch gradient when it feeds conv_expand)
+  // are written as plain bf16; the identity-branch gradient of a block without conv_expand stays the fp32 addend of dx
+  const bool h16 = e->bwd16;
   { // reduce pass reads dout, t2 and the identity (or, with the forward's sign bytes, 1/16 of a pass instead of it); the apply
     // pass reads them again and writes dt and the identity-path gradient
-    ProfElem pe(PC_BN_BWD, B, s, b.outc, 4 + b.mode, 2.0 * (resampled(b.mode) + (a.m2 ? 1.0625 : 2.0)) + 2.0, st);
+    ProfElem pe(PC_BN_BWD, B, s, b.outc, 4 + b.mode, 2.0 * (resampled(b.mode) + (a.m2 ? 1.0625 : 2.0)) + (h16 ? (b.expand ? 1.0 : 1.5) : 2.0), st);
     launch_bn_act_bwd(dout, a.t2, idn, a.mi2, n.params + b.bn2.g_off, n.params + b.bn2.b_off, DT, G2,
                       wgrad ? g + b.bn2.g_off : nullptr, wgrad ? g + b.bn2.b_off : nullptr, true, B, s, s, b.outc, b.mode, e->rnd,
-                      e->red, e->red_bytes, st, a.m2); }
-  if (wgrad) TRY(conv_wgrad(e, n, b.c2, a.a1, DT, B, s, st));
-  TRY(conv_dgrad(e, n, b.c2, DT, DA1, nullptr, B, s, st));
-  { ProfElem pe(PC_BN_BWD, B, s, b.outc, RS_NONE, 5.0, st);
+                      e->red, e->red_bytes, st, a.m2, h16 ? (1 | (b.expand ? 2 : 0)) : 0); }
+  if (wgrad) TRY(conv_wgrad(e, n, b.c2, a.a1, DT, B, s, st, h16));
+  TRY(conv_dgrad(e, n, b.c2, DT, DA1, nullptr, B, s, st, h16));
+  { ProfElem pe(PC_BN_BWD, B, s, b.outc, RS_NONE, h16 ? 4.5 : 5.0, st);
     launch_bn_act_bwd(DA1, a.t1, nullptr, a.mi1, n.params + b.bn1.g_off, n.params + b.bn1.b_off, DT, nullptr,
                       wgrad ? g + b.bn1.g_off : nullptr, wgrad ? g + b.bn1.b_off : nullptr, true, B, s, s, b.outc, RS_NONE, e->rnd,
-                      e->red, e->red_bytes, st); }
+                      e->red, e->red_bytes, st, nullptr, h16 ? 1 : 0); }
   if (wgrad) {
-    TRY(conv_wgrad(e, n, b.c1, a.x, DT, B, s, st));
-    if (b.expand) TRY(conv_wgrad(e, n, b.ce, a.x, G2, B, s, st));
+    TRY(conv_wgrad(e, n, b.c1, a.x, DT, B, s, st, h16));
+    if (b.expand) TRY(conv_wgrad(e, n, b.ce, a.x, G2, B, s, st, h16));
   }
   if (b.expand) {
-    TRY(conv_dgrad(e, n, b.c1, DT, dx, nullptr, B, s, st));
-    TRY(conv_dgrad(e, n, b.ce, G2, dx, dx, B, s, st));
+    TRY(conv_dgrad(e, n, b.c1, DT, dx, nullptr, B, s, st, h16));
+    TRY(conv_dgrad(e, n, b.ce, G2, dx, dx, B, s, st, h16));
   } else {
-    TRY(conv_dgrad(e, n, b.c1, DT, dx, G2, B, s, st));
+    TRY(conv_dgrad(e, n, b.c1, DT, dx, G2, B, s, st, h16));
   }
   return 0;
 }
@@ -773,6 +802,18 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
       }
     e->rs = nullptr;
     e->fsplit = ok;
+  }
+  if (e->fsplit) {
+    bool ok = true;
+    { const char* v = getenv("SIVAE_BWD16"); if (v && v[0] == '0') ok = false; }
+    for (int ni = 0; ni < 2 && ok; ++ni)
+      for (const Block& b : e->nets[ni].blocks) {
+        const ConvShape s1{1, b.size, b.size, b.inc, b.outc, 3}, s2{1, b.size, b.size, b.outc, b.outc, 3};
+        ok = ok && b.inc % 64 == 0 && b.outc % 64 == 0 && conv_tc_supported_wgrad16(s1) && conv_tc_supported_wgrad16(s2) &&
+             conv_tc_supported_fwd(ConvShape{1, b.size, b.size, b.outc, b.inc, 3}, FMT_BF16_) &&
+             conv_tc_supported_fwd(ConvShape{1, b.size, b.size, b.outc, b.outc, 3}, FMT_BF16_);
+      }
+    e->bwd16 = ok;
   }
   if (e->fsplit) e->bn_mask = true;          // the backward must not need the fp32 identity tensor (absent in dgrad-only passes)
   e->ws_need = carve(e, nullptr);
@@ -1246,7 +1287,22 @@ extern "C" int sivae_conv2d_dgrad(const float* dy, const float* w, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   float* wd = (float*)workspace;
   ConvShape s{N, H, W, Cout, Cin, k};
-  if (backend == SIVAE_CONV_TF32) backend = SIVAE_CONV_AUTO;      // the backward is kind::tf32 in both tensor-core modes
+  if (backend == SIVAE_CONV_AUTO && k != 5 && conv_tc_supported_fwd(s, FMT_BF16_) && (Cin & 3) == 0) {
+    // what the engine's default mode runs for the dgrad of a residual-block conv: plain bf16 dy and filter, kind::f16
+    void* dyh = lib_scratch(6, (size_t)(s.pixels() * s.Cin + 1) / 2);
+    void* wdh = lib_scratch(7, (size_t)((long long)Cout * Cin * k * k + 1) / 2);
+    if (!dyh || !wdh) return fail(-3, "cudaMalloc of the bf16 scratch failed");
+    launch_to_bf16(dy, dyh, s.pixels() * s.Cin, st);
+    launch_pack_dgrad_filter_bf16(w, wdh, Cout, Cin, k, st);
+    sivae_engine tmp16; tmp16.tc = tmp16.fast = true;
+    tmp16.sk_bytes = conv_tc_splitk_scratch_bytes(s);
+    tmp16.sk = tmp16.sk_bytes ? (void*)lib_scratch(2, (tmp16.sk_bytes + 3) / 4) : nullptr;
+    if (!tmp16.sk) tmp16.sk_bytes = 0;
+    TRY(conv_any(&tmp16, s, (const float*)dyh, nullptr, (const float*)wdh, nullptr, addend, dx, st, nullptr, nullptr, nullptr, nullptr, FMT_BF16_));
+    CHECK_CUDA_RET();
+    return 0;
+  }
+  if (backend == SIVAE_CONV_TF32) backend = SIVAE_CONV_AUTO;      // TF32: the round-1 choice (kind::tf32 backward)
   sivae_engine tmp; tmp.tc = tmp.fast = (backend == SIVAE_CONV_AUTO);
   const bool on_tc = backend == SIVAE_CONV_TCGEN05 || (backend == SIVAE_CONV_AUTO && !fwd_on_narrow(&tmp, s) && fwd_on_tc(&tmp, s));
   launch_pack_dgrad_filter(w, wd, Cout, Cin, k, on_tc, st);
@@ -1273,7 +1329,20 @@ extern "C" int sivae_conv2d_wgrad(const float* x, const float* dy, float* dw, in
   ConvShape s{N, H, W, Cin, Cout, k};
   cudaStream_t st = (cudaStream_t)stream;
   const bool acc = accumulate != 0;
-  if (backend == SIVAE_CONV_TF32) backend = SIVAE_CONV_AUTO;      // the backward is kind::tf32 in both tensor-core modes
+  if (backend == SIVAE_CONV_AUTO && k != 5 && conv_tc_supported_wgrad16(s)) {
+    // the default mode's wgrad of a residual-block conv: plain bf16 x and dy, kind::f16
+    if ((size_t)ws_bytes < conv_wgrad_tc16_scratch_bytes(s)) return fail(-3, "workspace too small");
+    void* xh = lib_scratch(6, (size_t)(s.pixels() * s.Cin + 1) / 2);
+    void* dyh = lib_scratch(7, (size_t)(s.pixels() * s.Cout + 1) / 2);
+    if (!xh || !dyh) return fail(-3, "cudaMalloc of the bf16 scratch failed");
+    launch_to_bf16(x, xh, s.pixels() * s.Cin, st);
+    launch_to_bf16(dy, dyh, s.pixels() * s.Cout, st);
+    int r = launch_conv_wgrad_tc16(xh, dyh, dw, s, acc, workspace, (size_t)ws_bytes, st);
+    if (r) return fail(r, "tcgen05 bf16 wgrad launch failed");
+    CHECK_CUDA_RET();
+    return 0;
+  }
+  if (backend == SIVAE_CONV_TF32) backend = SIVAE_CONV_AUTO;      // TF32: the round-1 choice (kind::tf32 backward)
   const bool rs_stem = backend == SIVAE_CONV_AUTO && Cin <= 3 && conv_rowsep_wgrad_supported(H, W, Cin, Cout, k);
   const bool rs_pred = backend == SIVAE_CONV_AUTO && Cout <= 3 && conv_rowsep_wgrad_supported(H, W, Cout, Cin, k);
   if (rs_stem || rs_pred) {

@@ -120,6 +120,39 @@ void launch_split32(const float* in, float* out, long long n, cudaStream_t st) {
   if (n <= 0) return;
   k_split32<<<min(cdiv(n >> 2, 256), 148u * 16), 256, 0, st>>>(in, out, n >> 2);
 }
+// four floats -> four bf16 (round to nearest even), 8 bytes
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
+  const uint32_t a = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.x)), b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.y));
+  const uint32_t c = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.z)), d = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v.w));
+  return make_uint2(a | (b << 16), c | (d << 16));
+}
+__global__ void k_to_bf16(const float* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    out[i] = pack_bf16x4(reinterpret_cast<const float4*>(in)[i]);
+}
+void launch_to_bf16(const float* in, void* out, long long n, cudaStream_t st) {
+  g_launches += 1;
+  if (n <= 0) return;
+  k_to_bf16<<<min(cdiv(n >> 2, 256), 148u * 16), 256, 0, st>>>(in, (uint2*)out, n >> 2);
+}
+// bf16 form of the dgrad-packed filter (the dgrad of the residual blocks in the default mode)
+__global__ void k_pack_dgrad_bf16(const float* __restrict__ w, __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int k) {
+  long long total = (long long)Cout * Cin * k * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    long long q = i / Cout;
+    int s2 = (int)(q % k);
+    q /= k;
+    int r2 = (int)(q % k);
+    int ci = (int)(q / k);
+    wd[i] = __float2bfloat16_rn(w[(((long long)co * k + (k - 1 - r2)) * k + (k - 1 - s2)) * Cin + ci]);
+  }
+}
+void launch_pack_dgrad_filter_bf16(const float* w, void* wd, int Cout, int Cin, int k, cudaStream_t st) {
+  g_launches += 1;
+  long long total = (long long)Cout * Cin * k * k;
+  k_pack_dgrad_bf16<<<min(cdiv(total, 256), 148u * 8), 256, 0, st>>>(w, (__nv_bfloat16*)wd, Cout, Cin, k);
+}
 __global__ void k_pack_dgrad(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int k, int rnd) {
   long long total = (long long)Cout * Cin * k * k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -578,7 +611,7 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
                                                     const float* __restrict__ mi, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, float* __restrict__ out, int N,
                                                     int H, int W, int C, unsigned char* __restrict__ mask,
-                                                    float* __restrict__ outs, int idn_split) {
+                                                    float* __restrict__ outs, int idn_split, uint2* __restrict__ outh) {
   // 32-bit index arithmetic (tensor sizes are < 2^31 float4s; checked by the launcher): 64-bit div/mod per element
   // would make this HBM-bound kernel instruction-bound
   const unsigned cvec = (unsigned)C >> 2;
@@ -621,6 +654,7 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
       long long pix = p;
       const float4 y = eval(pix);
       if (SPLIT) split32_store4(outs + pix * C, c4, y);
+      if (SPLIT && outh) outh[pix * cvec + c4] = pack_bf16x4(y);            // plain bf16 copy: the wgrad operand
       if (!SPLIT || out) reinterpret_cast<float4*>(out + pix * C)[c4] = rnd4(y);
     } else if (MODE == RS_POOL) {
       long long p00 = ((long long)n * H + 2 * h) * W + 2 * w;
@@ -629,6 +663,7 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
                                    (a.z + b2.z + c2.z + d2.z) * 0.25f, (a.w + b2.w + c2.w + d2.w) * 0.25f);
       long long po = ((long long)n * Ho + h) * Wo + w;
       if (SPLIT) split32_store4(outs + po * C, c4, y);
+      if (SPLIT && outh) outh[po * cvec + c4] = pack_bf16x4(y);
       if (!SPLIT || out) reinterpret_cast<float4*>(out + po * C)[c4] = rnd4(y);
     } else {
       long long pix = ((long long)n * H + h) * W + w;
@@ -645,6 +680,11 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
           *reinterpret_cast<uint2*>(d) = hi;
           *reinterpret_cast<uint2*>(d + 64) = lo;
         }
+        if (outh) {
+          const uint2 hb = pack_bf16x4(y);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) outh[pp[k] * cvec + c4] = hb;
+        }
       }
       if (!SPLIT || out) {
         const float4 yr = rnd4(y);
@@ -658,14 +698,14 @@ __global__ void __launch_bounds__(256) k_bn_act_fwd(const float* __restrict__ t,
 }
 void launch_bn_act_fwd(const float* t, const float* identity, const float* mi, const float* gamma, const float* beta,
                        float* out, int N, int H, int W, int C, int mode, bool rnd, cudaStream_t st, unsigned char* mask,
-                       float* outs, bool idn_split) {
+                       float* outs, bool idn_split, void* outh) {
   g_launches += 1;
   int Ho = mode == RS_POOL ? H / 2 : H, Wo = mode == RS_POOL ? W / 2 : W;
   long long total = (long long)N * Ho * Wo * (C / 4);
   if (total == 0) return;
   unsigned grid = min(cdiv(total, 256), 148u * 32);
   const int is = idn_split ? 1 : 0;
-#define LAUNCH(M, R, S) k_bn_act_fwd<M, R, S><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C, mask, outs, is)
+#define LAUNCH(M, R, S) k_bn_act_fwd<M, R, S><<<grid, 256, 0, st>>>(t, identity, mi, gamma, beta, out, N, H, W, C, mask, outs, is, (uint2*)outh)
   if (outs) {           // split32 output (C % 32 == 0), always together with tf32 rounding of the optional fp32 copy
     if (mode == RS_NONE) LAUNCH(RS_NONE, true, true);
     else if (mode == RS_POOL) LAUNCH(RS_POOL, true, true);
@@ -780,13 +820,14 @@ __global__ void k_bn_bwd_finalize(const float* __restrict__ part, int nblk, long
     dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
   }
 }
+// out16 bit 0: dt is written as plain bf16 (the operand of the bf16 dgrad / wgrad); bit 1: so is gout
 template <int MODE, bool ROUND>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ dout, const float* __restrict__ t,
                                                       const float* __restrict__ idn, const float* __restrict__ mi,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ sums, float* __restrict__ dt,
                                                       float* __restrict__ gout, int N, int H, int W, int C,
-                                                      const unsigned char* __restrict__ mask) {
+                                                      const unsigned char* __restrict__ mask, int out16) {
   const unsigned cvec = (unsigned)C >> 2;
   const unsigned total = (unsigned)N * H * W * cvec;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -824,13 +865,21 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
     o.y = ga.y * istd.y * (g.y - mg.y - xh.y * mx.y);
     o.z = ga.z * istd.z * (g.z - mg.z - xh.z * mx.z);
     o.w = ga.w * istd.w * (g.w - mg.w - xh.w * mx.w);
-    if (ROUND) {
-      o.x = round_tf32_dev(o.x); o.y = round_tf32_dev(o.y); o.z = round_tf32_dev(o.z); o.w = round_tf32_dev(o.w);
+    if (out16 & 1) {
+      reinterpret_cast<uint2*>(dt)[(size_t)r * cvec + c4] = pack_bf16x4(o);
+    } else {
+      if (ROUND) {
+        o.x = round_tf32_dev(o.x); o.y = round_tf32_dev(o.y); o.z = round_tf32_dev(o.z); o.w = round_tf32_dev(o.w);
+      }
+      reinterpret_cast<float4*>(dt + r * C)[c4] = o;
     }
-    reinterpret_cast<float4*>(dt + r * C)[c4] = o;
     if (gout) {
-      if (ROUND) { g.x = round_tf32_dev(g.x); g.y = round_tf32_dev(g.y); g.z = round_tf32_dev(g.z); g.w = round_tf32_dev(g.w); }
-      reinterpret_cast<float4*>(gout + r * C)[c4] = g;
+      if (out16 & 2) {
+        reinterpret_cast<uint2*>(gout)[(size_t)r * cvec + c4] = pack_bf16x4(g);
+      } else {
+        if (ROUND) { g.x = round_tf32_dev(g.x); g.y = round_tf32_dev(g.y); g.z = round_tf32_dev(g.z); g.w = round_tf32_dev(g.w); }
+        reinterpret_cast<float4*>(gout + r * C)[c4] = g;
+      }
     }
   }
 }
@@ -845,7 +894,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_small(const float* __restrict__ 
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float* __restrict__ dt, float* __restrict__ gout, float* dgamma,
                                                       float* dbeta, int accumulate, int N, int H, int W, int C,
-                                                      const unsigned char* __restrict__ mask) {
+                                                      const unsigned char* __restrict__ mask, int out16) {
   const int c4 = blockIdx.x;
   const unsigned cvec = (unsigned)C >> 2;
   const unsigned rows = (unsigned)N * H * W;
@@ -914,13 +963,21 @@ __global__ void __launch_bounds__(256) k_bn_bwd_small(const float* __restrict__ 
     o.y = ga.y * istd.y * (g.y - mg.y - xh.y * mx.y);
     o.z = ga.z * istd.z * (g.z - mg.z - xh.z * mx.z);
     o.w = ga.w * istd.w * (g.w - mg.w - xh.w * mx.w);
-    if (ROUND) {
-      o.x = round_tf32_dev(o.x); o.y = round_tf32_dev(o.y); o.z = round_tf32_dev(o.z); o.w = round_tf32_dev(o.w);
+    if (out16 & 1) {
+      reinterpret_cast<uint2*>(dt)[(size_t)r * cvec + c4] = pack_bf16x4(o);
+    } else {
+      if (ROUND) {
+        o.x = round_tf32_dev(o.x); o.y = round_tf32_dev(o.y); o.z = round_tf32_dev(o.z); o.w = round_tf32_dev(o.w);
+      }
+      reinterpret_cast<float4*>(dt + (size_t)r * C)[c4] = o;
     }
-    reinterpret_cast<float4*>(dt + (size_t)r * C)[c4] = o;
     if (gout) {
-      if (ROUND) { g.x = round_tf32_dev(g.x); g.y = round_tf32_dev(g.y); g.z = round_tf32_dev(g.z); g.w = round_tf32_dev(g.w); }
-      reinterpret_cast<float4*>(gout + (size_t)r * C)[c4] = g;
+      if (out16 & 2) {
+        reinterpret_cast<uint2*>(gout)[(size_t)r * cvec + c4] = pack_bf16x4(g);
+      } else {
+        if (ROUND) { g.x = round_tf32_dev(g.x); g.y = round_tf32_dev(g.y); g.z = round_tf32_dev(g.z); g.w = round_tf32_dev(g.w); }
+        reinterpret_cast<float4*>(gout + (size_t)r * C)[c4] = g;
+      }
     }
   }
 }
@@ -932,13 +989,13 @@ static bool bn_small_enabled() {
 void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mi, const float* gamma,
                        const float* beta, float* dt, float* g, float* dgamma, float* dbeta, bool accumulate, int N,
                        int H, int W, int C, int mode, bool rnd, void* scratch, size_t scratch_bytes, cudaStream_t st,
-                       const unsigned char* mask) {
+                       const unsigned char* mask, int out16) {
   long long rows = (long long)N * H * W;
   if (rows == 0) return;
   int cvec = C / 4;
   if (rows <= BN_SMALL_ROWS && bn_small_enabled()) {
     g_launches += 1;
-#define LAUNCH(M, R) k_bn_bwd_small<M, R><<<cvec, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, dt, g, dgamma, dbeta, accumulate ? 1 : 0, N, H, W, C, mask)
+#define LAUNCH(M, R) k_bn_bwd_small<M, R><<<cvec, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, dt, g, dgamma, dbeta, accumulate ? 1 : 0, N, H, W, C, mask, out16)
     if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
     else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
     else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }
@@ -958,7 +1015,7 @@ void launch_bn_act_bwd(const float* dout, const float* t, const float* identity,
   k_bn_bwd_finalize<<<cdiv(C, 8), 256, 0, st>>>(part, nblk, rows, C, sums, dgamma, dbeta, accumulate ? 1 : 0);
   long long total = rows * cvec;
   unsigned grid = min(cdiv(total, 256), 148u * 32);
-#define LAUNCH(M, R) k_bn_bwd_apply<M, R><<<grid, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, sums, dt, g, N, H, W, C, mask)
+#define LAUNCH(M, R) k_bn_bwd_apply<M, R><<<grid, 256, 0, st>>>(dout, t, identity, mi, gamma, beta, sums, dt, g, N, H, W, C, mask, out16)
   if (mode == RS_NONE) { if (rnd) LAUNCH(RS_NONE, true); else LAUNCH(RS_NONE, false); }
   else if (mode == RS_POOL) { if (rnd) LAUNCH(RS_POOL, true); else LAUNCH(RS_POOL, false); }
   else { if (rnd) LAUNCH(RS_UP, true); else LAUNCH(RS_UP, false); }

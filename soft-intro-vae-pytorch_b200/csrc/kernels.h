@@ -30,9 +30,12 @@ void launch_round_tf32(const float* in, float* out, long long n, cudaStream_t st
 void launch_split_tf32(const float* in, float* hi, float* lo, long long n, cudaStream_t st);
 // fp32 -> split32 (split32.cuh); n floats, n % 32 == 0, groups of 32 aligned with the tensor's channel groups.  out may alias in.
 void launch_split32(const float* in, float* out, long long n, cudaStream_t st);
-constexpr int FMT_TF32_ = 0, FMT_SPLIT_ = 1;   // operand formats of the tensor-core forward kernels (mirrors conv_tc.cu)
+constexpr int FMT_TF32_ = 0, FMT_SPLIT_ = 1, FMT_BF16_ = 2;   // operand formats of the tensor-core forward / dgrad kernels (mirrors conv_tc.cu)
 // wd[ci][k-1-r][k-1-s][co] = w[co][r][s][ci]  (filters for dgrad as a forward conv); optional tf32 rounding
 void launch_pack_dgrad_filter(const float* w, float* wd, int Cout, int Cin, int k, bool round_tf32, cudaStream_t st);
+void launch_pack_dgrad_filter_bf16(const float* w, void* wd_bf16, int Cout, int Cin, int k, cudaStream_t st);
+// fp32 -> plain bf16 (round to nearest even); n % 4 == 0
+void launch_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
 
 // ---------------- SIMT fp32 implicit-GEMM convolution (exact path; also stem / predict shapes) ----------
 // y[p][co] = sum_{tap,ci} x[p+tap][ci] * w[co][tap][ci] + bias[co] + addend[p][co]
@@ -76,7 +79,7 @@ void launch_conv_narrow_corr(const float* nar, const float* wide, float* dw, int
                              bool accumulate, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 // ---------------- tcgen05 TF32 implicit-GEMM convolution (conv_tc.cu) ----------------
-bool conv_tc_supported_fwd(const ConvShape& s);
+bool conv_tc_supported_fwd(const ConvShape& s, int fmt = 0);
 // returns cudaError / driver error code (0 ok)
 // fmt = FMT_SPLIT: x and w are split32 tensors ([32 bf16 hi | 32 bf16 lo] per 32-channel group, split32.cuh) and every
 // product is computed as lo*hi + hi*lo + hi*hi with three kind::f16 MMAs -- fp32-class accuracy at 1.5x the tf32 tensor time
@@ -92,6 +95,11 @@ bool conv_tc_supported_wgrad(const ConvShape& s);
 size_t conv_wgrad_tc_scratch_bytes(const ConvShape& s);
 int launch_conv_wgrad_tc(const float* x, const float* dy, float* dw, const ConvShape& s, bool accumulate,
                          void* scratch, size_t scratch_bytes, cudaStream_t st);
+// bf16 wgrad (k = 1 or 3, Cin % 64 == 0, Cout % 64 == 0): x, dy plain bf16 NHWC tensors, dw fp32
+bool conv_tc_supported_wgrad16(const ConvShape& s);
+size_t conv_wgrad_tc16_scratch_bytes(const ConvShape& s);
+int launch_conv_wgrad_tc16(const void* x, const void* dy, float* dw, const ConvShape& s, bool accumulate,
+                           void* scratch, size_t scratch_bytes, cudaStream_t st);
 
 // ---------------- train-mode BatchNorm (+LeakyReLU, +residual, +pool / upsample) ----------------
 size_t bn_scratch_bytes(long long rows, int C);
@@ -114,12 +122,14 @@ void launch_bn_eval_stats(const float* running_mean, const float* running_var, i
 // fp32 copy `out` is optional (null = not written) and tf32-rounded.  idn_split: `identity` is a split32 tensor.
 void launch_bn_act_fwd(const float* t, const float* identity, const float* mean_invstd, const float* gamma,
                        const float* beta, float* out, int N, int H, int W, int C, int mode, bool round_tf32,
-                       cudaStream_t st, unsigned char* sign_mask = nullptr, float* outs = nullptr, bool idn_split = false);
+                       cudaStream_t st, unsigned char* sign_mask = nullptr, float* outs = nullptr, bool idn_split = false,
+                       void* outh = nullptr);      // outh (with outs only): plain bf16 copy of the output = the bf16 wgrad operand
 // backward. dout has the shape of the resampled output.  sums: 2*C floats scratch inside `scratch`.
 void launch_bn_act_bwd(const float* dout, const float* t, const float* identity, const float* mean_invstd,
                        const float* gamma, const float* beta, float* dt, float* g, float* dgamma, float* dbeta,
                        bool accumulate, int N, int H, int W, int C, int mode, bool round_tf32, void* scratch,
-                       size_t scratch_bytes, cudaStream_t st, const unsigned char* sign_mask = nullptr);
+                       size_t scratch_bytes, cudaStream_t st, const unsigned char* sign_mask = nullptr, int out16 = 0);
+// out16: bit 0 = dt, bit 1 = g are written as plain bf16 tensors (operands of the bf16 dgrad / wgrad kernels)
 // with sign_mask (written by launch_bn_act_fwd) neither pass reads `identity`: 6.1 instead of 8 full-tensor passes
 
 // ---------------- linear ----------------

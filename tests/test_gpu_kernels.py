@@ -76,7 +76,10 @@ def test_conv_fwd_dgrad_wgrad(shape, backend):
     N, H, W, Cin, Cout, k = shape
     x, w, dy = _conv_case(*shape)
     tc = backend == L.CONV_TCGEN05
-    if backend != L.CONV_SIMT:
+    if backend == L.CONV_AUTO:
+        # the default mode mixes split32 forward, bf16 / tf32 backward kernels: bf16 values are exact operands of all of them
+        x, w, dy = x.bfloat16().float(), w.bfloat16().float(), dy.bfloat16().float()
+    elif backend != L.CONV_SIMT:
         x, w, dy = _round_tf32(x), _round_tf32(w), _round_tf32(dy)      # operands exactly representable in tf32
     xd, wd, dyd = x.double(), w.double(), dy.double()
     xd.requires_grad_(True)
@@ -342,3 +345,39 @@ def test_conv_fwd_split32_unrounded_operands(shape):
     want = _nhwc(F.conv2d(x.double(), w.double(), None, 1, k // 2))
     assert _rel(got, want) < 1e-5
     assert _rel(y.cpu(), _nhwc(ref)) < 1e-5
+
+
+BWD16_SHAPES = [(2, 16, 16, 64, 64, 3), (2, 32, 32, 64, 64, 3), (2, 64, 64, 128, 128, 3), (4, 16, 16, 128, 512, 3), (2, 32, 32, 256, 256, 3),
+                (3, 4, 4, 512, 512, 3), (2, 8, 8, 128, 128, 3), (2, 32, 32, 64, 128, 1), (32, 4, 4, 256, 256, 3), (5, 16, 24, 64, 192, 3),
+                (2, 128, 128, 64, 64, 3), (3, 8, 8, 128, 64, 1)]
+
+
+@pytest.mark.parametrize("shape", BWD16_SHAPES)
+def test_conv_bwd_bf16_operands(shape):
+    """dgrad / wgrad of the residual blocks in the default mode: plain bf16 operands (the BatchNorm backward writes bf16
+    gradients, the forward keeps bf16 copies of its activations), kind::f16 MMAs, fp32 accumulation.  With bf16-exact inputs the
+    kernels must agree with fp64 to fp32 round-off: CTA-pair / single-CTA halo and one-box-per-tap dgrad (with and without the
+    in-place addend), halo (3 taps per instruction pair) and generic MN-major wgrad, accumulate on / off, several splits."""
+    lib = L.load()
+    N, H, W, Cin, Cout, k = shape
+    x, w, dy = _conv_case(*shape, seed=9)
+    x, w, dy = x.bfloat16().float(), w.bfloat16().float(), dy.bfloat16().float()
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    F.conv2d(xd, wd, None, 1, k // 2).backward(dy.double())
+    xg, wg, dyg = _nhwc(x).to(DEV), _krsc(w).to(DEV), _nhwc(dy).to(DEV)
+    ws = torch.empty(max(1 << 26, Cout * Cin * k * k * 4 * 160), dtype=torch.uint8, device=DEV)
+    addend = torch.randn(N, Cin, H, W)
+    for add in (None, addend):
+        dx = torch.empty(N, H, W, Cin, device=DEV)
+        ag = _nhwc(add).to(DEV) if add is not None else None
+        L.check(lib.sivae_conv2d_dgrad(L.ptr(dyg), L.ptr(wg), L.ptr(ag), L.ptr(dx), N, H, W, Cin, Cout, k, L.CONV_AUTO, L.ptr(ws),
+                                       ws.numel(), _s()), "bf16 dgrad")
+        torch.cuda.synchronize()
+        got = dx.cpu().double() - (_nhwc(add).double() if add is not None else 0)
+        assert _rel(got, _nhwc(xd.grad)) < 1e-5
+    for acc in (1, 0):
+        dw = torch.full((Cout, k, k, Cin), 0.5, device=DEV)
+        L.check(lib.sivae_conv2d_wgrad(L.ptr(xg), L.ptr(dyg), L.ptr(dw), N, H, W, Cin, Cout, k, acc, L.CONV_AUTO, L.ptr(ws), ws.numel(),
+                                       _s()), "bf16 wgrad")
+        torch.cuda.synchronize()
+        assert _rel(dw.cpu() - 0.5 * acc, _krsc(wd.grad)) < 1e-5
