@@ -122,6 +122,24 @@ int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_scale, void* 
 int sivae_adam_set_step(sivae_engine* e, int net, long long step);
 long long sivae_adam_get_step(const sivae_engine* e, int net);
 
+/* Data parallel (the reference's only DP precedent is style_soft_intro_vae/launcher.py:26-33 + DistributedDataParallel,
+   train_style_soft_intro_vae.py:154-161): one process per GPU, rank-local batches and BatchNorm statistics, ONE sum-all-reduce of
+   the flat encoder gradient buffer after the E backward and ONE of the decoder buffer after the D backward.  The library owns the
+   collective: raw ncclAllReduce on the step's own stream (capturable in a CUDA graph together with the kernels around it).
+   NCCL is resolved at run time with dlopen("libnccl.so.2") -- inside a torch process that is torch's own copy.
+     sivae_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId, the caller ships it to the other ranks (any side channel);
+     sivae_comm_init:      every rank, with its CUDA device current: ncclCommInitRank -> the engine owns the communicator;
+     sivae_allreduce_attach: alternative -- borrow an existing ncclComm_t (not destroyed by the engine); NULL detaches;
+     sivae_allreduce_grads: in-place sum-all-reduce of the net's flat gradient buffer (no-op without a communicator);
+     sivae_iteration:      E half, all-reduce, Adam(encoder, grad_scale 1/world), D half, all-reduce, Adam(decoder) in one call. */
+int sivae_comm_unique_id(unsigned char* out128);
+int sivae_comm_init(sivae_engine* e, const unsigned char* id128, int world_size, int rank);
+int sivae_allreduce_attach(sivae_engine* e, void* nccl_comm);
+int sivae_comm_world(const sivae_engine* e);
+int sivae_allreduce_grads(sivae_engine* e, int net, void* stream);
+int sivae_iteration(sivae_engine* e, const float* real_nchw, const float* noise, const float* eps5, int batch,
+                    const sivae_hyper* hp, float lr_e, float lr_d, float* stats, void* stream);
+
 /* model.encode / model.decode / model.sample (:203-223): mu, logvar: [B,z]; out: [B,cdim,S,S] NCHW.
    train != 0 uses batch statistics and moves the running stats like the reference in model.train(). */
 int sivae_encode(sivae_engine* e, const float* x_nchw, int batch, float* mu, float* logvar, int train, void* stream);
@@ -131,12 +149,15 @@ int sivae_decode(sivae_engine* e, int net, const float* z, int batch, float* out
    (what the reference keeps in the Python variables of the same names, used for the sample grid :641-646) */
 int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void* stream);
 int sivae_last_batch(const sivae_engine* e);
+/* a CUDA-graph replay of a step does not run the library's host code: the caller records the replayed step's batch size */
+int sivae_set_last_batch(sivae_engine* e, int batch);
 
 /* instrumentation for bench.py: number of kernels this library has enqueued so far; optional CUDA-event timing of
    every convolution launch on its stream, summed per kernel class by sivae_profile_read (which synchronises):
-   out[class*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches}; class 0 = tcgen05 conv fwd/dgrad,
-   1 = tcgen05 wgrad, 2 = CUDA-core conv fwd/dgrad, 3 = CUDA-core wgrad, 4 = fused loss pass (the FLOP slot holds
-   its algorithmic BYTES: five images read once); out must hold 15 doubles */
+   out[class*3 + {0,1,2}] = {milliseconds, algorithmic FLOPs, launches}; class 0 = tcgen05 kind::tf32 conv fwd/dgrad,
+   1 = tcgen05 kind::tf32 wgrad, 2 = CUDA-core conv fwd/dgrad, 3 = CUDA-core wgrad, 4 = fused loss pass (the FLOP slot holds
+   its algorithmic BYTES: five images read once), 5 = tcgen05 forward conv on split32 operands (3 kind::f16 MMAs per product),
+   6 = tcgen05 bf16 dgrad, 7 = tcgen05 bf16 wgrad; out must hold 24 doubles */
 unsigned long long sivae_launch_count(void);
 int sivae_profile_enable(int on);
 int sivae_profile_read(double* out);

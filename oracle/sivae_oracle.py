@@ -282,20 +282,22 @@ def d_step(sd, arch: Arch, real: Tensor, noise: Tensor, z: Tensor, eps: Sequence
     return scal, grads, tens
 
 
-def vae_step(sd, arch: Arch, real: Tensor, eps: Tensor, hp: Hyper):
-    """Vanilla-VAE warm-up step, :512-540 (loss NOT multiplied by `scale`)."""
+def vae_step(sd, arch: Arch, real: Tensor, eps: Tensor, hp: Hyper, bootstrap: bool = False):
+    """Vanilla-VAE warm-up step, :512-540 (loss NOT multiplied by `scale`).  Bootstrap trainer (:540-564 there): the same
+    code, but `model(real_batch)` decodes with the frozen target decoder (forward(..., target=True) is the default,
+    bootstrap :196-217), so the trainable decoder gets no gradient (gd comes back empty) and optimizer_d.step() is a no-op."""
     ek, dk = param_keys(sd, "encoder."), param_keys(sd, "decoder.")
     _set_grad(sd, ek, True)
-    _set_grad(sd, dk, True)
+    _set_grad(sd, dk, not bootstrap)
     mu, logvar = encoder_forward(sd, arch, real)
     z = reparameterize(mu, logvar, eps)
-    rec = decoder_forward(sd, arch, z)
+    rec = decoder_forward(sd, arch, z, prefix="target_decoder" if bootstrap else "decoder")
     loss_rec = rec_loss(real, rec, "mean")
     loss_kl = calc_kl(logvar, mu, "mean")
     loss = hp.beta_rec * loss_rec + hp.beta_kl * loss_kl
     loss.backward()
     ge = {k: sd[k].grad.detach().clone() for k in ek}
-    gd = {k: sd[k].grad.detach().clone() for k in dk}
+    gd = {} if bootstrap else {k: sd[k].grad.detach().clone() for k in dk}
     _set_grad(sd, ek, False)
     _set_grad(sd, dk, False)
     return dict(loss_rec=loss_rec.item(), loss_kl=loss_kl.item(), loss=loss.item()), ge, gd

@@ -5,6 +5,8 @@
 #include "kernels.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types and enums only: the functions are resolved with dlsym (no link-time dependency on NCCL)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -118,6 +120,8 @@ struct sivae_engine {
   void* red = nullptr; size_t red_bytes = 0;
   int cur_batch = 0;
   bool have_e_state = false;
+  // data parallel: NCCL communicator the gradient all-reduces run on, enqueued on the step's own stream
+  ncclComm_t comm = nullptr; int world = 1; bool own_comm = false;
   bool reuse_dec = false;          // D half re-uses the E half's fake / rec decoder passes (SIVAE_REUSE_DEC=1 or sivae_set_option)
   bool e_dec_valid = false;        // dp[0] / dp[1] hold D(noise) / D(z) of the current decoder weights
 };
@@ -820,7 +824,99 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   *out = e;
   return 0;
 }
-extern "C" void sivae_destroy(sivae_engine* e) { delete e; }
+// ---- NCCL, resolved at run time from the libnccl the process already has (torch's bundled one) or the system's ----------
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  const char* names[] = {getenv("SIVAE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* nm : names) {
+    if (!nm || !nm[0]) continue;
+    h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return nullptr;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+  api.CommCount = (decltype(api.CommCount))dlsym(h, "ncclCommCount");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.CommCount && api.GetErrorString;
+  return api.ok ? &api : nullptr;
+}
+int nccl_fail(const NcclApi* a, ncclResult_t r, const char* what) {
+  return fail(-20 - (int)r, std::string(what) + ": " + (a && a->GetErrorString ? a->GetErrorString(r) : "NCCL error"));
+}
+}  // namespace
+
+extern "C" int sivae_comm_unique_id(unsigned char* out128) {
+  NcclApi* a = nccl_api();
+  if (!a) return fail(-10, "libnccl.so.2 not found (set SIVAE_NCCL_LIB)");
+  if (!out128) return fail(-1, "null argument");
+  ncclUniqueId id;
+  ncclResult_t r = a->GetUniqueId(&id);
+  if (r != ncclSuccess) return nccl_fail(a, r, "ncclGetUniqueId");
+  memcpy(out128, &id, sizeof(id));
+  return 0;
+}
+static void comm_release(sivae_engine* e) {
+  if (e->comm && e->own_comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy(e->comm); }
+  e->comm = nullptr; e->world = 1; e->own_comm = false;
+}
+extern "C" int sivae_comm_init(sivae_engine* e, const unsigned char* id128, int world, int rank) {
+  NcclApi* a = nccl_api();
+  if (!a) return fail(-10, "libnccl.so.2 not found (set SIVAE_NCCL_LIB)");
+  if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(-1, "bad argument");
+  comm_release(e);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t c = nullptr;
+  ncclResult_t r = a->CommInitRank(&c, world, id, rank);          // on the calling thread's current device
+  if (r != ncclSuccess) return nccl_fail(a, r, "ncclCommInitRank");
+  e->comm = c; e->world = world; e->own_comm = true;
+  return 0;
+}
+extern "C" int sivae_allreduce_attach(sivae_engine* e, void* nccl_comm) {
+  NcclApi* a = nccl_api();
+  if (!a) return fail(-10, "libnccl.so.2 not found (set SIVAE_NCCL_LIB)");
+  if (!e) return fail(-1, "null engine");
+  comm_release(e);
+  if (!nccl_comm) return 0;                                         // detach
+  int n = 0;
+  ncclResult_t r = a->CommCount((ncclComm_t)nccl_comm, &n);
+  if (r != ncclSuccess) return nccl_fail(a, r, "ncclCommCount");
+  e->comm = (ncclComm_t)nccl_comm; e->world = n; e->own_comm = false;
+  return 0;
+}
+extern "C" int sivae_comm_world(const sivae_engine* e) { return e ? e->world : -1; }
+extern "C" int sivae_allreduce_grads(sivae_engine* e, int net, void* stream) {
+  if (!e || net < 0 || net > 2 || !e->nets[net].present) return fail(-1, "bad net id");
+  Net& n = e->nets[net];
+  if (!n.grads) return fail(-4, "grads not bound");
+  if (!e->comm || e->world <= 1) return 0;
+  NcclApi* a = nccl_api();
+  ncclResult_t r = a->AllReduce(n.grads, n.grads, (size_t)n.n_params, ncclFloat32, ncclSum, e->comm, (cudaStream_t)stream);
+  if (r != ncclSuccess) return nccl_fail(a, r, "ncclAllReduce");
+  g_launches += 1;
+  return 0;
+}
+extern "C" void sivae_destroy(sivae_engine* e) {
+  if (e) comm_release(e);
+  delete e;
+}
 static Net* get_net(sivae_engine* e, int net) {
   if (!e || net < 0 || net > 2 || !e->nets[net].present) return nullptr;
   return &e->nets[net];
@@ -1026,23 +1122,26 @@ extern "C" int sivae_vae_step(sivae_engine* e, const float* real_nchw, const flo
   const sivae_config& c = e->cfg;
   const int S = c.image_size, z = c.zdim;
   const long long per = (long long)c.cdim * S * S;
+  // bootstrap variant: model(real_batch) decodes with the frozen TARGET decoder (bootstrap trainer :196-217, default
+  // target=True; warm-up call at :546), so only the encoder receives gradients -- the decoder pass is dgrad-only
+  const bool boot = c.variant == 1;
   Net& en = e->nets[0];
-  Net& dn = e->nets[1];
-  if (!en.grads || !dn.grads) return fail(-4, "grads not bound");
+  Net& dn = boot ? e->nets[2] : e->nets[1];
+  if (!en.grads || (!boot && !dn.grads)) return fail(-4, "grads not bound");
   TRY(refresh_derived(e, en, st)); TRY(refresh_derived(e, dn, st));
   launch_nchw_to_nhwc(real_nchw, e->real, B, c.cdim, S, S, st);
   EncPass& E1 = e->ep[0];
   DecPass& D1 = e->dp[0];
   TRY(enc_forward(e, en, E1, e->real, B, true, true, st));            // model(real_batch) :518
   launch_kl_reparam(E1.ml, eps, E1.z, E1.kl, B, z, st);
-  TRY(dec_forward(e, dn, D1, E1.z, B, true, true, st));
+  TRY(dec_forward(e, dn, D1, E1.z, B, true, !boot, st));
   launch_mse3(e->real, D1.y, nullptr, nullptr, nullptr, e->mse, B, per, e->red, e->red_bytes, st);
   launch_vae_loss_finalize(e->mse, E1.kl, B, hp->beta_kl, hp->beta_rec, stats, st);
   launch_loss_seed(e->real, D1.y, nullptr, nullptr, nullptr, 2.f * hp->beta_rec / (float)B, nullptr, 0.f, nullptr, 0.f, false,
                    e->d_rec, nullptr, nullptr, nullptr, B, per, st);
   cudaMemsetAsync(en.grads, 0, sizeof(float) * en.n_params, st);
-  cudaMemsetAsync(dn.grads, 0, sizeof(float) * dn.n_params, st);
-  TRY(dec_backward(e, dn, D1, e->d_rec, true, e->dz, B, st));
+  if (!boot) cudaMemsetAsync(dn.grads, 0, sizeof(float) * dn.n_params, st);
+  TRY(dec_backward(e, dn, D1, e->d_rec, !boot, e->dz, B, st));
   launch_latent_bwd(E1.ml, eps, e->dz, nullptr, hp->beta_kl / (float)B, e->dml, B, z, st);
   TRY(enc_backward(e, en, E1, e->dml, true, nullptr, nullptr, B, st));
   CHECK_CUDA_RET();
@@ -1067,6 +1166,22 @@ extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_sc
               (cudaStream_t)stream);
   n->dirty = true;
   CHECK_CUDA_RET();
+  return 0;
+}
+// One whole introspective iteration (:551-624) as a single enqueue: E half, [all-reduce of the encoder gradients],
+// Adam(encoder), D half, [all-reduce of the decoder gradients], Adam(decoder) -- the collectives are raw ncclAllReduce calls on
+// the same stream (sivae_comm_init / sivae_allreduce_attach), so the iteration is capturable as ONE CUDA graph under data
+// parallelism too.  eps: [5,B,z] in the draw order of :560,:567,:568,:602,:605.  Gradients are averaged (1 / world in Adam).
+extern "C" int sivae_iteration(sivae_engine* e, const float* real_nchw, const float* noise, const float* eps5, int B,
+                               const sivae_hyper* hp, float lr_e, float lr_d, float* stats, void* stream) {
+  if (!e || !eps5) return fail(-1, "null argument");
+  const float gs = 1.f / (float)(e->world > 0 ? e->world : 1);
+  TRY(sivae_e_step(e, real_nchw, noise, eps5, B, hp, stats, stream));
+  TRY(sivae_allreduce_grads(e, SIVAE_NET_ENCODER, stream));
+  TRY(sivae_adam_step(e, SIVAE_NET_ENCODER, lr_e, gs, stream));
+  TRY(sivae_d_step(e, eps5 + 3LL * B * e->cfg.zdim, hp, stats, stream));
+  TRY(sivae_allreduce_grads(e, SIVAE_NET_DECODER, stream));
+  TRY(sivae_adam_step(e, SIVAE_NET_DECODER, lr_d, gs, stream));
   return 0;
 }
 extern "C" int sivae_adam_set_step(sivae_engine* e, int net, long long step) {
@@ -1169,6 +1284,12 @@ extern "C" int sivae_profile_read(double* out) {
   return 0;
 }
 extern "C" int sivae_last_batch(const sivae_engine* e) { return e ? e->cur_batch : -1; }
+// CUDA-graph replays of a step do not run this library's host code: the caller records the batch size of the replayed step
+extern "C" int sivae_set_last_batch(sivae_engine* e, int batch) {
+  if (!e || batch < 1 || batch > e->cfg.max_batch) return fail(-5, "batch out of range");
+  e->cur_batch = batch;
+  return 0;
+}
 extern "C" int sivae_last_image(sivae_engine* e, int slot, float* out_nchw, void* stream) {
   if (!e || !e->ws || slot < 0 || slot > 3 || !out_nchw || e->cur_batch < 1) return fail(-1, "bad argument / no step run yet");
   const sivae_config& c = e->cfg;

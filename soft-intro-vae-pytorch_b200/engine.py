@@ -82,6 +82,8 @@ class Engine:
             self._bind()
         self._graphs = {}          # key -> (CUDAGraph, static input tensors); see graphed()
         self._graph_seen = set()
+        self._graph_failed = set() # keys whose capture failed once: they stay eager
+        self._comm_world = 1
 
     def _bind(self):
         lib = L.load()
@@ -114,6 +116,7 @@ class Engine:
         """Forget every captured step graph (pointers or derived-filter state they baked in are no longer valid)."""
         self._graphs = {}
         self._graph_seen = set()
+        self._graph_failed = set()
 
     def graphed(self, key, inputs, fn):
         """Run fn(*static_inputs) -- a sequence of engine calls on the current stream -- from a CUDA graph.
@@ -124,6 +127,8 @@ class Engine:
         if key not in self._graph_seen:
             self._graph_seen.add(key)
             return fn(*inputs)
+        if key in self._graph_failed:
+            return fn(*inputs)
         ent = self._graphs.get(key)
         if ent is None:
             statics = [torch.empty_like(t) for t in inputs]
@@ -131,8 +136,19 @@ class Engine:
                 s_.copy_(t, non_blocking=True)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                fn(*statics)
+            try:
+                # thread_local: a cudaHostAlloc / cudaMalloc from ANOTHER thread (the DataLoader's pin-memory thread is still
+                # warming up when the second iteration captures) must not invalidate this thread's capture
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    fn(*statics)
+            except RuntimeError as ex:
+                # a failed capture leaves no partial work behind (nothing executes during capture): run this step eagerly
+                # and keep the key eager from now on
+                import warnings
+                warnings.warn("CUDA graph capture of %r failed (%s); this step shape stays eager" % (key[0], str(ex)[:200]))
+                self._graph_failed.add(key)
+                torch.cuda.synchronize(self.device)
+                return fn(*inputs)
             ent = (g, statics)
             self._graphs[key] = ent
         g, statics = ent
@@ -157,6 +173,55 @@ class Engine:
         for net, s in steps.items():
             lib.sivae_adam_set_step(self.handle, net, s)
         self.reuse_decoder_passes = reuse
+
+    # ---- data parallel: the library-owned NCCL communicator ------------------------------------------------------
+    @property
+    def comm_world(self):
+        return self._comm_world
+
+    def comm_init(self, dist):
+        """Create the engine's own NCCL communicator over the ranks of the initialised torch.distributed default group:
+        rank 0 draws the ncclUniqueId, torch.distributed ships its 128 bytes (plumbing), every rank calls ncclCommInitRank
+        inside the library.  From then on the gradient all-reduces are raw ncclAllReduce calls on the step's stream."""
+        lib = L.load()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            L.check(lib.sivae_comm_unique_id(buf), "sivae_comm_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        on_dev = dist.get_backend() == "nccl"
+        t = uid.to(self.device) if on_dev else uid
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        with torch.cuda.device(self.device):
+            L.check(lib.sivae_comm_init(self.handle, (C.c_ubyte * 128).from_buffer_copy(raw), world, rank), "sivae_comm_init")
+        self._comm_world = world
+        self.drop_graphs()
+
+    def allreduce_grads(self, net):
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_allreduce_grads(self.handle, net, _stream()), "sivae_allreduce_grads")
+
+    def iteration(self, real, noise, eps5, hp, lr_e, lr_d):
+        """E half, all-reduce, Adam(encoder), D half, all-reduce, Adam(decoder) as one library call (sivae_iteration)"""
+        with torch.cuda.device(self.device):
+            L.check(L.load().sivae_iteration(self.handle, L.ptr(real), L.ptr(noise), L.ptr(eps5), real.shape[0], C.byref(hp),
+                                             float(lr_e), float(lr_d), L.ptr(self.stats), _stream()), "sivae_iteration")
+
+    def broadcast_state(self, dist, src=0):
+        """make every rank's replica identical to rank `src`: parameters, Adam moments and step counters, BatchNorm running
+        statistics and num_batches_tracked (the reference's DP precedent, DistributedDataParallel, does this at construction)"""
+        lib = L.load()
+        for net, m in self.mem.items():
+            for t in (m.params, m.m, m.v, m.bn, m.nbt):
+                if t is not None:
+                    dist.broadcast(t, src=src)
+            if m.m is not None:
+                st = torch.tensor([lib.sivae_adam_get_step(self.handle, net)], dtype=torch.int64, device=self.device)
+                dist.broadcast(st, src=src)
+                lib.sivae_adam_set_step(self.handle, net, int(st.item()))
+        self.params_changed()
 
     def close(self):
         if self.handle:
@@ -209,6 +274,10 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(L.load().sivae_decode(self.handle, net, L.ptr(z), B, L.ptr(out), 1 if train else 0, _stream()), "sivae_decode")
         return out
+
+    def note_batch(self, B):
+        """graph replays do not run the library's host code: tell it the batch size of the step just replayed (last_image)"""
+        L.load().sivae_set_last_batch(self.handle, int(B))
 
     def last_image(self, slot):
         """decoder output of the last half step as NCHW: 0 = fake, 1 = rec, 2 = rec_rec, 3 = rec_fake"""

@@ -55,6 +55,12 @@ _SIGS = {
     "sivae_adam_step": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, _P]),
     "sivae_adam_set_step": (C.c_int, [_P, C.c_int, C.c_longlong]),
     "sivae_adam_get_step": (C.c_longlong, [_P, C.c_int]),
+    "sivae_comm_unique_id": (C.c_int, [_P]),
+    "sivae_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "sivae_allreduce_attach": (C.c_int, [_P, _P]),
+    "sivae_comm_world": (C.c_int, [_P]),
+    "sivae_allreduce_grads": (C.c_int, [_P, C.c_int, _P]),
+    "sivae_iteration": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(Hyper), C.c_float, C.c_float, _P, _P]),
     "sivae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     "sivae_decode": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     "sivae_launch_count": (C.c_ulonglong, []),
@@ -63,6 +69,7 @@ _SIGS = {
     "sivae_profile_dump": (C.c_int, [C.c_char_p, C.c_int]),
     "sivae_last_image": (C.c_int, [_P, C.c_int, _P, _P]),
     "sivae_last_batch": (C.c_int, [_P]),
+    "sivae_set_last_batch": (C.c_int, [_P, C.c_int]),
     "sivae_conv2d_fwd": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 7 + [_P]),
     "sivae_conv2d_dgrad": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 7 + [_P, C.c_longlong, _P]),
     "sivae_conv2d_wgrad": (C.c_int, [_P, _P, _P] + [C.c_int] * 8 + [_P, C.c_longlong, _P]),

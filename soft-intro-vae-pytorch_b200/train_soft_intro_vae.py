@@ -19,6 +19,7 @@ What is different by construction
     bench.py; data-parallel when ``torch.distributed`` is initialised (one process per GPU, NCCL all-reduce of the
     flat encoder / decoder gradient buffers before each Adam step, BN statistics stay per rank).
 """
+import contextlib
 import importlib
 import os
 import pickle
@@ -466,14 +467,28 @@ def _dist():
 
 
 def _graph_mode():
-    """SIVAE_CUDA_GRAPH: 0 = never; 1 (default) = replay the step from CUDA graphs -- one graph for the whole iteration in a
-    single-process run, three graph segments with the two NCCL all-reduces launched eagerly between them under
-    torch.distributed; 2 = experimental: also capture the all-reduces inside one graph (hung on this pool's torch 2.11 /
-    NCCL 2.28.9 build, profiles/r01q_dist.md)"""
+    """SIVAE_CUDA_GRAPH: 0 = never; 1 (default) = replay the whole iteration from ONE CUDA graph -- under torch.distributed
+    too: the two gradient all-reduces are raw ncclAllReduce calls of the library's own communicator on the step's stream
+    (sivae_comm_init), captured with the kernels around them."""
     try:
         return int(os.environ.get("SIVAE_CUDA_GRAPH", "1"))
     except ValueError:
         return 1
+
+
+def _dp_mode():
+    """SIVAE_DP_COMM: 'lib' (default) = the library owns an NCCL communicator (one graph per iteration); 'torch' = round-1
+    path: torch.distributed all-reduces launched eagerly between three graph segments (also what a non-NCCL backend gets)"""
+    return os.environ.get("SIVAE_DP_COMM", "lib")
+
+
+def _lib_comm(eng, dist):
+    """the engine's own communicator, created on first use (None: keep using torch.distributed collectives)"""
+    if _dp_mode() != "lib" or dist.get_backend() != "nccl":
+        return False
+    if eng.comm_world != dist.get_world_size():
+        eng.comm_init(dist)
+    return True
 
 
 def _segmented_step(eng, dist, real, noise, eps, hp, lr_e, lr_d, inv_world, key):
@@ -508,28 +523,30 @@ def introspective_iteration(model, real, noise, eps, hp, lr_e, lr_d, use_graph=N
     dist = _dist()
     inv_world = 1.0 / dist.get_world_size() if dist else 1.0
     enc, dec = _L.NET_ENCODER, _L.NET_DECODER
+    own = bool(dist) and _lib_comm(eng, dist)          # collectives inside the library (raw NCCL on the step's stream)
 
     def step(real_, noise_, eps_):
+        if own or not dist:
+            return eng.iteration(real_, noise_, eps_, hp, lr_e, lr_d)       # one call: both halves, collectives, both Adam steps
         eng.e_step(real_, noise_, eps_[:3], hp)
-        if dist:
-            dist.all_reduce(eng.mem[enc].grads)
+        dist.all_reduce(eng.mem[enc].grads)
         eng.adam(enc, lr_e, inv_world)
         eng.d_step(eps_[3:], hp)
-        if dist:
-            dist.all_reduce(eng.mem[dec].grads)
+        dist.all_reduce(eng.mem[dec].grads)
         eng.adam(dec, lr_d, inv_world)
 
     mode = _graph_mode()
     if use_graph is None:
         use_graph = mode >= 1
     if use_graph and real.is_cuda and not torch.cuda.is_current_stream_capturing():
-        key = (tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world, eng.reuse_decoder_passes)
-        if dist and mode < 2:
+        key = (tuple(real.shape), bytes(hp), float(lr_e), float(lr_d), inv_world, eng.reuse_decoder_passes, own)
+        if dist and not own:
             _segmented_step(eng, dist, real, noise, eps, hp, lr_e, lr_d, inv_world, key)
         else:
             eng.graphed(("introspective",) + key, [real.contiguous(), noise.contiguous(), eps.contiguous()], step)
+        eng.note_batch(real.size(0))
     else:
-        step(real, noise, eps)
+        step(real.contiguous(), noise.contiguous(), eps.contiguous())
     return eng.stats
 
 
@@ -538,12 +555,20 @@ def vae_iteration(model, real, eps, hp, lr_e, lr_d):
     eng = model._ensure_engine(real.size(0))
     dist = _dist()
     inv_world = 1.0 / dist.get_world_size() if dist else 1.0
+    own = bool(dist) and _lib_comm(eng, dist)
+    # bootstrap variant: model(real_batch) reconstructs through the frozen TARGET decoder (bootstrap :196-217, target=True by
+    # default; warm-up at :546), so the trainable decoder receives no gradient and optimizer_d.step() moves nothing
+    boot = bool(getattr(model, "_bootstrap", False))
+    nets = (_L.NET_ENCODER,) if boot else (_L.NET_ENCODER, _L.NET_DECODER)
     eng.vae_step(real, eps, hp)
-    if dist:
-        dist.all_reduce(eng.mem[_L.NET_ENCODER].grads)
-        dist.all_reduce(eng.mem[_L.NET_DECODER].grads)
+    for net in nets:
+        if own:
+            eng.allreduce_grads(net)
+        elif dist:
+            dist.all_reduce(eng.mem[net].grads)
     eng.adam(_L.NET_ENCODER, lr_e, inv_world)
-    eng.adam(_L.NET_DECODER, lr_d, inv_world)
+    if not boot:
+        eng.adam(_L.NET_DECODER, lr_d, inv_world)
     return eng.stats
 
 
@@ -638,11 +663,23 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
         print("random seed: ", seed)
 
     train_set, image_size, channels, ch, labelled = _build_dataset(dataset)
-    model = model_cls(cdim=ch, zdim=z_dim, channels=channels, image_size=image_size).to(device)
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    main = rank == 0                 # under data parallelism only rank 0 prints, saves figures / checkpoints / the pickle
+    with contextlib.redirect_stdout(None) if not main else contextlib.nullcontext():
+        model = model_cls(cdim=ch, zdim=z_dim, channels=channels, image_size=image_size).to(device)
     if pretrained is not None:
         load_model(model, pretrained, device)
-    print(model)
+    if main:
+        print(model)
     model.reserve(batch_size)
+    if dist:
+        # every replica starts from rank 0's state (weights, BN buffers, Adam state): with the default seed = -1 each rank
+        # would otherwise build different random weights and only the gradients would ever be averaged
+        model._engine.broadcast_state(dist, src=0)
+        # ... and draws its OWN noise / eps / shuffling from here on, also when a fixed seed made the generators identical
+        torch.manual_seed(torch.initial_seed() + 7919 * rank)
+        torch.cuda.manual_seed(torch.initial_seed())
 
     fig_dir = './figures_' + dataset.replace(":", "_")
     os.makedirs(fig_dir, exist_ok=True)
@@ -650,10 +687,9 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
     hp = _E.make_hyper(beta_kl, beta_rec, beta_neg, gamma_r, scale)
     hp_vae = hp
 
-    dist = _dist()
     sampler = None
     if dist:
-        sampler = torch.utils.data.distributed.DistributedSampler(train_set, shuffle=True)
+        sampler = torch.utils.data.distributed.DistributedSampler(train_set, shuffle=True, seed=0 if seed == -1 else int(seed))
     gpu_ds = importlib.import_module(_PKG + ".gpu_dataset")
     on_gpu = isinstance(train_set, gpu_ds.ImageDatasetFromFile)
     loader = torch.utils.data.DataLoader(train_set, batch_size=batch_size, shuffle=sampler is None, sampler=sampler,
@@ -702,8 +738,9 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                 elif best_fid > fid:
                     print("best fid updated: {} -> {}".format(best_fid, fid))
                     best_fid = fid
-                    save_checkpoint(model, epoch, cur_iter, prefix + "fid_" + str(fid) + "_")
-        if epoch % save_interval == 0 and epoch > 0:
+                    if main:
+                        save_checkpoint(model, epoch, cur_iter, prefix + "fid_" + str(fid) + "_")
+        if epoch % save_interval == 0 and epoch > 0 and main:
             save_checkpoint(model, (epoch // save_interval) * save_interval, cur_iter, prefix)
         model.train()
         if sampler is not None:
@@ -711,7 +748,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
         track.reset()
         cur_lr_e = _milestone_lr(lr_e, epoch - start_epoch)
         cur_lr_d = _milestone_lr(lr_d, epoch - start_epoch)
-        pbar = tqdm(iterable=loader)
+        pbar = tqdm(iterable=loader, disable=not main)
         for batch in pbar:
             if labelled:
                 batch = batch[0]
@@ -726,7 +763,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                     raise SystemError
                 pbar.set_description_str('epoch #{}'.format(epoch))
                 pbar.set_postfix(r_loss=st[11].item(), kl=st[12].item())
-                if cur_iter % test_iter == 0:
+                if cur_iter % test_iter == 0 and main:
                     _, _, _, rec = model(real_batch)
                     _save_grid([real_batch, rec], '{}/image_{}.jpg'.format(fig_dir, cur_iter), num_row)
             else:
@@ -755,7 +792,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                 if not async_stats:
                     consume_stats(pending)
                     pending = None
-                if cur_iter % test_iter == 0:
+                if cur_iter % test_iter == 0 and main:
                     _, _, _, rec_det = model(real_batch, deterministic=True)
                     fake = model._engine.last_image(0)            # `fake` of the D half (:597), not a new forward
                     k = min(b_size, 16)
@@ -776,6 +813,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
             raise SystemError("Negative KL Difference")
         if epoch > num_vae - 1:
             track.close_epoch()
+        if epoch > num_vae - 1 and main:
             h = track.hist
             print('#' * 50)
             print(f'Epoch {epoch} Summary:')
@@ -784,7 +822,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
             print(f'diff_kl: {np.mean(diff_kls):.3f}, exp_elbo_f: {h["exp_elbo_f"][-1]:.4e}, exp_elbo_r: {h["exp_elbo_r"][-1]:.4e}')
             print(f'time: {time.time() - start_time}')
             print('#' * 50)
-        if epoch == num_epochs - 1 and real_batch is not None:
+        if epoch == num_epochs - 1 and real_batch is not None and main:
             with torch.no_grad():
                 _, _, _, rec_det = model(real_batch, deterministic=True)
                 noise_batch = torch.randn(size=(real_batch.size(0), z_dim)).to(device)

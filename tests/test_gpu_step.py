@@ -163,6 +163,46 @@ def test_vae_step_vs_oracle():
         assert r < 2e-4, n
 
 
+def test_bootstrap_vae_warmup_step_vs_oracle():
+    """bootstrap trainer with num_vae > 0 (bootstrap :540-564): model(real_batch) decodes with the frozen TARGET decoder, so the
+    encoder gets its gradient through the target decoder's dgrad and the trainable decoder gets none (optimizer_d.step() moves
+    nothing); vae_iteration() must leave the decoder's parameters and Adam state untouched."""
+    import importlib
+    from oracle import sivae_oracle as O
+    from tests.step_harness import PKG, make_inputs
+    L = importlib.import_module(PKG + ".lib")
+    M = importlib.import_module(PKG + ".train_soft_intro_vae_bootstrap")
+    T = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    torch.manual_seed(2)
+    model = M.SoftIntroVAE(**cfg)
+    model._conv_backend = 1
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to("cuda:0")
+    real, _, eps = make_inputs(cfg, 6, 2)
+    model.reserve(6)
+    hp = E.make_hyper(0.7, 1.3, 256.0, 1.0, 1.0 / (3 * 32 * 32))
+    st = T.vae_iteration(model, real.cuda(), eps[0].cuda().contiguous(), hp, 2e-4, 2e-4).cpu()
+    torch.cuda.synchronize()
+    sd = O.clone_sd(init, torch.float64)
+    scal, ge, gd = O.vae_step(sd, O.Arch(**cfg), real.double(), eps[0].double(), O.Hyper(beta_kl=0.7, beta_rec=1.3), bootstrap=True)
+    assert gd == {}
+    assert st[11].item() == pytest.approx(scal["loss_rec"], rel=2e-5)
+    assert st[12].item() == pytest.approx(scal["loss_kl"], rel=2e-5)
+    for n, p in model.encoder.named_parameters():
+        r = (p.grad.cpu().double() - ge["encoder." + n]).norm() / (ge["encoder." + n].norm() + 1e-30)
+        assert r < 2e-4, n
+    post = model.state_dict()
+    for k, v in init.items():
+        if k.startswith("decoder."):
+            assert torch.equal(post[k].cpu(), v), "the trainable decoder moved in the bootstrap warm-up step: " + k
+        if k.startswith("target_decoder.") and k.endswith("num_batches_tracked"):
+            assert int(post[k]) == int(v) + 1, k        # the target decoder ran one train-mode forward
+    assert L.load().sivae_adam_get_step(model._engine.handle, L.NET_DECODER) == 0
+    assert L.load().sivae_adam_get_step(model._engine.handle, L.NET_ENCODER) == 1
+
+
 def test_inference_api_train_and_eval():
     """model(x) / model.sample(z) through the engine in train and eval mode vs the oracle forward"""
     import importlib
