@@ -374,6 +374,13 @@ def run_ours(args):
             line["image_loader"] = image_loader_leg(device, size, batch)
         except Exception as ex:                       # a secondary leg must never take the headline down with it
             line["image_loader"] = dict(error=repr(ex)[:300])
+    if rank == 0 and world == 1 and not args.no_stock_leg:
+        try:
+            torch.cuda.empty_cache()
+            line["stock_pytorch_same_gpu"] = stock_torch_leg(args.config, device)
+            line["stock_pytorch_same_gpu"]["speedup_of_this_engine"] = round(line["stock_pytorch_same_gpu"]["ms_per_step"] / ms_step, 2)
+        except Exception as ex:                       # a secondary leg must never take the headline down with it
+            line["stock_pytorch_same_gpu"] = dict(error=repr(ex)[:300])
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, budget_s=args.cpu_budget)
     if rank == 0:
@@ -449,62 +456,104 @@ def _traffic(kind):
     return None
 
 
-def cpu_baseline(cfg_name, budget_s=25.0, steps=1, warmup=0):
-    """the oracle port of the reference step on the host cores, on a bounded sample (reduced batch) of the workload.
-    The batch is sized adaptively: a probe iteration at the smallest legal batch measures seconds per image on this
-    host, then `steps` iteration(s) run at the largest batch (<= the workload's) that fits the budget (~10-30 s)."""
+def cpu_baseline(cfg_name, budget_s=25.0, steps=1, warmup=1):
+    """The reference's CPU implementation of the step on the host cores, on a bounded sample (reduced batch) of the workload.
+    kind "reference": the UNMODIFIED reference trainer from oracle/_ref (oracle/build_ref.py; its own train_soft_intro_vae()
+    loop body timed between two batch requests, oracle/ref_arm.py); kind "port" (only when oracle/_ref is absent): the oracle's
+    functional restatement.  The batch is sized adaptively: a WARM probe (one untimed + one timed iteration at the smallest
+    legal batch, so a cold oneDNN / thread pool cannot shrink the sample) measures seconds per image on this host, then
+    `warmup` + `steps` iterations run at the largest batch (<= the workload's) whose iteration fits the budget (~10-30 s)."""
     import torch
-    from oracle import sivae_oracle as O
+    from oracle import ref_arm
     size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[cfg_name]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
-    sd = O.make_state_dict(arch, seed=0, bootstrap=boot)
-    hp = O.Hyper(beta_neg=beta_neg, gamma_r=1.0 if boot else 1e-8, scale=1.0 / (3 * size * size))
+    use_ref = ref_arm.reference_root() is not None and os.environ.get("SIVAE_CPU_BASELINE", "reference") != "port"
+    if use_ref:
+        def run(b, n_warm, n_it):
+            return ref_arm.time_reference_iterations(size, zdim, b, beta_neg, boot, warmup=n_warm, steps=n_it, threads=cores)[0]
+    else:
+        from oracle import sivae_oracle as O
+        arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
+        sd = O.make_state_dict(arch, seed=0, bootstrap=boot)
+        hp = O.Hyper(beta_neg=beta_neg, gamma_r=1.0 if boot else 1e-8, scale=1.0 / (3 * size * size))
 
-    def run(b, n_it):
-        g = torch.Generator().manual_seed(1234)
-        real = torch.rand(b, 3, size, size, generator=g)
-        noise = torch.randn(b, zdim, generator=g)
-        eps = list(torch.randn(5, b, zdim, generator=g))
-        se, sdd = O.AdamState(), O.AdamState()
-        t0 = time.time()
-        for _ in range(n_it):
-            O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
-        return (time.time() - t0) / n_it
+        def run(b, n_warm, n_it):
+            g = torch.Generator().manual_seed(1234)
+            real = torch.rand(b, 3, size, size, generator=g)
+            noise = torch.randn(b, zdim, generator=g)
+            eps = list(torch.randn(5, b, zdim, generator=g))
+            se, sdd = O.AdamState(), O.AdamState()
+            for _ in range(n_warm):
+                O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
+            t0 = time.time()
+            for _ in range(n_it):
+                O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
+            return (time.time() - t0) / n_it
 
     b0 = 1 if size > 64 else 2                      # train-mode BN at 4x4 needs more than one value per channel
-    per_iter = budget_s / max(steps + warmup, 1)
-    b, probe = b0, run(b0, 1)                       # also pages the thread pool / oneDNN primitives in
-    dt, probes = probe, 1
-    while probes < 3 and b < batch:                 # small batches under-use the cores: re-estimate at the grown batch
-        nb = int(max(b0, min(batch, per_iter / (dt / b))))
-        if nb < 1.5 * b:
-            break
-        b, dt, probes = nb, run(nb, 1), probes + 1
-    if warmup:
-        run(b, warmup)
-    if steps > 1 or warmup:
-        dt = run(b, steps)
-    return dict(value=round(b / dt, 4), unit="images/s", cores=cores, kind="port",
-                sample="%d full E+D iteration(s) of the oracle at batch %d (of %d) on torch CPU fp32, %d threads; %.1f s/iter "
-                       "(batch grown from a %.1f s probe at batch %d towards a %.0f s budget, %d probe(s))"
-                       % (steps, b, batch, cores, dt, probe, b0, budget_s, probes))
+    probe = run(b0, 1, 1)                           # warm probe: seconds per iteration at the smallest batch
+    b = int(max(b0, min(batch, budget_s / (probe / b0))))
+    if b > 4 * b0:                                  # small batches under-use the cores: re-estimate at a quarter of the target
+        bm = max(b0, b // 4)
+        b = int(max(b0, min(batch, budget_s / (run(bm, 0, 1) / bm))))
+    dt = run(b, warmup, steps)
+    return dict(value=round(b / dt, 4), unit="images/s", cores=cores, kind="reference" if use_ref else "port",
+                sample="%d timed (+%d warm-up) full E+D iteration(s) of %s at batch %d (of %d) on torch CPU fp32, %d threads; %.1f s/iter "
+                       "(batch grown from a warm %.1f s probe at batch %d towards a %.0f s budget)"
+                       % (steps, warmup, "the unmodified reference train_soft_intro_vae() (oracle/_ref)" if use_ref else "the oracle port",
+                          b, batch, cores, dt, probe, b0, budget_s))
+
+
+def stock_torch_leg(cfg_name, device, steps=3, warmup=2):
+    """The honest same-GPU comparator: the reference's arithmetic through STOCK PyTorch on this B200 -- cuDNN
+    convolutions / batch norm, cuBLAS, ATen elementwise, autograd -- at torch's default flags (cudnn.allow_tf32 = True, i.e. TF32
+    convolutions: what the unmodified reference does on this GPU under torch 2.11).  Runs the oracle's functional restatement
+    (test infrastructure, timed here only as the thing being compared AGAINST) with the workload's shapes on the device."""
+    import torch
+    from oracle import sivae_oracle as O
+    size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[cfg_name]
+    arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
+    sd = {k: v.to(device) for k, v in O.make_state_dict(arch, seed=0, bootstrap=boot).items()}
+    hp = O.Hyper(beta_neg=beta_neg, gamma_r=1.0 if boot else 1e-8, scale=1.0 / (3 * size * size))
+    g = torch.Generator().manual_seed(1234)
+    real = torch.rand(batch, 3, size, size, generator=g).to(device)
+    noise = torch.randn(batch, zdim, generator=g).to(device)
+    eps = [e.to(device) for e in torch.randn(5, batch, zdim, generator=g)]
+    se, sdd = O.AdamState(), O.AdamState()
+    for _ in range(warmup):
+        O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        O.full_iteration(sd, arch, real, noise, eps, hp, se, sdd, boot)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    del sd
+    torch.cuda.empty_cache()
+    return dict(what="the same introspective iteration through stock PyTorch %s / cuDNN %s on this GPU (autograd, NCHW fp32 tensors, "
+                     "torch.backends.cudnn.allow_tf32 = %s, matmul.allow_tf32 = %s: torch defaults = what the unmodified reference runs)"
+                     % (torch.__version__, torch.backends.cudnn.version(), torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32),
+                ms_per_step=round(ms, 2), value=round(batch / (ms * 1e-3), 2), unit="images/s", steps=steps, warmup=warmup)
 
 
 def run_reference(args):
-    """reference arm: the reference's CPU implementation of the path = the oracle port, all host threads"""
+    """reference arm: the reference's own CPU implementation of the path (the unmodified trainer from oracle/_ref), all host
+    threads, on a bounded sample of the workload; rank 0 only"""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", 1))
     t0 = time.time()
-    # bounded: every step is one iteration on a small batch; cap the number of steps to stay within minutes
-    steps = max(1, min(args.steps, 3)) if size <= 64 else 1
-    cb = cpu_baseline(args.config, budget_s=args.cpu_budget, steps=steps, warmup=1 if (args.warmup > 0 and size <= 64) else 0)
+    # bounded: every step is one iteration on the sample batch (~cpu_budget seconds each): cap the counts to stay within minutes
+    steps = max(1, min(args.steps, 3 if size <= 64 else 2))
+    warmup = 1 if args.warmup > 0 else 0
+    cb = cpu_baseline(args.config, budget_s=args.cpu_budget, steps=steps, warmup=warmup)
     line = dict(impl="reference", metric="images/sec per introspective E+D step", value=cb["value"], unit="images/s",
-                n_gpus=world, steps=steps, warmup=1 if (args.warmup > 0 and size <= 64) else 0, ms_per_step=None, higher_is_better=True,
+                n_gpus=world, steps=steps, warmup=warmup, ms_per_step=None, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="fp32", data="synthetic",
                 config=dict(workload=WORKLOAD_NAMES[args.config], image_size=size, z_dim=zdim, channels=channels,
                             batch_per_gpu=batch, note="CPU path: bounded sample, see cpu_baseline.sample"),
@@ -522,6 +571,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock-leg", action="store_true", help="skip the stock-PyTorch-on-the-same-GPU comparator")
     ap.add_argument("--e2e-sweep", action="store_true", help="also time the e2e leg with / without batch prefetch and deferred statistics reads")
     ap.add_argument("--no-loader-leg", action="store_true", help="skip the image batch-assembly kernel timing")
     ap.add_argument("--no-reuse-leg", action="store_true", help="skip the secondary timing with decoder-pass re-use")

@@ -39,6 +39,8 @@ if os.path.dirname(_HERE) not in sys.path:
 _PKG = os.path.basename(_HERE)
 _L = importlib.import_module(_PKG + ".lib")
 _E = importlib.import_module(_PKG + ".engine")
+if os.environ.get("SIVAE_ANNOUNCE") == "1":      # which file served `import train_soft_intro_vae` (tests/test_gpu_boundary.py)
+    print("SIVAE_DROPIN %s %s" % (__name__, os.path.abspath(__file__)), file=sys.stderr)
 
 __all__ = ["ResidualBlock", "Encoder", "Decoder", "SoftIntroVAE", "calc_kl", "reparameterize",
            "calc_reconstruction_loss", "str_to_list", "is_image_file", "record_scalar", "record_image", "load_model",

@@ -20,6 +20,8 @@ if os.path.dirname(_HERE) not in sys.path:
 _PKG = os.path.basename(_HERE)
 _B = importlib.import_module(_PKG + ".train_soft_intro_vae")
 _L = importlib.import_module(_PKG + ".lib")
+if os.environ.get("SIVAE_ANNOUNCE") == "1":      # which file served `import train_soft_intro_vae_bootstrap` (tests/test_gpu_boundary.py)
+    print("SIVAE_DROPIN %s %s" % (__name__, os.path.abspath(__file__)), file=sys.stderr)
 
 ResidualBlock, Encoder, Decoder = _B.ResidualBlock, _B.Encoder, _B.Decoder
 calc_kl, reparameterize, calc_reconstruction_loss = _B.calc_kl, _B.reparameterize, _B.calc_reconstruction_loss

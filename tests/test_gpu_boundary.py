@@ -1,0 +1,87 @@
+"""-m gpu: the drop-in boundary itself (reference soft_intro_vae/main.py:8,45-52).
+
+The reference's own `main.py` -- byte for byte the file of the reference (oracle/_ref, sha256 in its MANIFEST) -- is run as a
+script against this repository's modules, both ways INTEGRATION.md documents (the `sivae_b200.py` launcher and the
+PYTHONSAFEPATH recipe), for the standard and the bootstrap trainer.  Asserted: the module that served
+`from train_soft_intro_vae import train_soft_intro_vae` is the drop-in (not the reference's file next to main.py), a
+checkpoint in the reference's schema appears, and the REFERENCE's SoftIntroVAE loads it with strict=True and computes the
+same eval-mode forward on the CPU as the drop-in does on the GPU.  The only non-reference input is the dataset name
+(`synthetic32:48`, no files / network): an argparse string the reference passes through unchanged."""
+import hashlib
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import ref_arm
+from tests.step_harness import PKG, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("how", ["launcher", "safepath"])
+@pytest.mark.parametrize("bootstrap", [False, True])
+def test_reference_main_runs_unmodified_against_the_dropin(tmp_path, bootstrap, how):
+    ref_root = ref_arm.reference_root()
+    if ref_root is None:
+        pytest.skip("no reference scripts (oracle/_ref not built and /root/reference absent)")
+    subdir = "soft_intro_vae_bootstrap" if bootstrap else "soft_intro_vae"
+    modname = "train_soft_intro_vae_bootstrap" if bootstrap else "train_soft_intro_vae"
+    main_py = os.path.join(ref_root, subdir, "main.py")
+    man = os.path.join(ref_root, "MANIFEST.json")
+    if os.path.exists(man):        # the script under test is the reference's file, unmodified
+        want = json.load(open(man))["files"][subdir + "/main.py"]
+        assert hashlib.sha256(open(main_py, "rb").read()).hexdigest() == want
+    args = ["--dataset", "synthetic32:48", "--device", "0", "--num_epochs", "1", "--batch_size", "16", "--z_dim", "32",
+            "--beta_neg", "256", "--seed", "3"]
+    env = dict(os.environ)
+    env["SIVAE_ANNOUNCE"] = "1"          # the drop-in modules then report their own file on stderr when imported
+    env.pop("PYTHONPATH", None)
+    pkg_dir = os.path.join(ROOT, PKG)
+    if how == "launcher":
+        cmd = [sys.executable, os.path.join(ROOT, "sivae_b200.py"), main_py] + args
+    else:                                # INTEGRATION.md section 1, second recipe: plain `python main.py` with the safe-path switch
+        env["PYTHONSAFEPATH"] = "1"
+        env["PYTHONPATH"] = os.pathsep.join([pkg_dir, os.path.join(ref_root, subdir)])
+        cmd = [sys.executable, main_py] + args
+    r = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    served = [l.split()[2] for l in r.stderr.splitlines() if l.startswith("SIVAE_DROPIN " + modname + " ")]
+    assert served and os.path.samefile(served[0], os.path.join(pkg_dir, modname + ".py")), \
+        "the reference's import was not served by the drop-in module: %s" % served
+    assert "conv shape:" in r.stdout and "Epoch 0 Summary:" in r.stdout          # the reference's prints
+    saves = sorted(os.listdir(tmp_path / "saves"))
+    assert len(saves) == 1 and saves[0].endswith("model_epoch_0_iter_3.pth"), saves
+    ck = torch.load(tmp_path / "saves" / saves[0], map_location="cpu")
+    assert set(ck) == {"epoch", "model"}
+    # the REFERENCE's model class loads the drop-in's checkpoint strictly ...
+    ref = ref_arm.import_reference(bootstrap)
+    torch.manual_seed(0)
+    stdout, sys.stdout = sys.stdout, open(os.devnull, "w")
+    try:
+        rm = ref.SoftIntroVAE(cdim=3, zdim=32, channels=[64, 128, 256], image_size=32)
+    finally:
+        sys.stdout = stdout
+    missing = rm.load_state_dict(ck["model"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    # ... and computes what the drop-in computes from the same weights (eval mode, deterministic latent)
+    rm.eval()
+    x = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        mu_r, lv_r, _, y_r = rm(x, deterministic=True)        # (bootstrap: target=True by default on both sides)
+    M = importlib.import_module(PKG + "." + modname)
+    stdout, sys.stdout = sys.stdout, open(os.devnull, "w")
+    try:
+        dm = M.SoftIntroVAE(cdim=3, zdim=32, channels=[64, 128, 256], image_size=32)
+    finally:
+        sys.stdout = stdout
+    M.load_model(dm, str(tmp_path / "saves" / saves[0]), torch.device("cpu"))
+    dm = dm.to("cuda:0").eval()
+    mu_d, lv_d, _, y_d = dm(x.cuda(), deterministic=True)
+    assert torch.allclose(mu_d.cpu(), mu_r, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(lv_d.cpu(), lv_r, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(y_d.cpu(), y_r, rtol=1e-3, atol=1e-3)
