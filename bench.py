@@ -355,7 +355,9 @@ def run_ours(args):
                 e2e=dict(value=round(e2e_value, 2), unit="images/s", ms_per_step=round(ms_e2e / args.steps, 3),
                          h2d_bytes_per_step=batch * 3 * size * size * 4 + batch * zdim * 4, d2h_bytes_per_step=64),
                 gpu_launches=int(launches),
-                launch_mode=(("cuda graph replay" if world == 1 else "replay of 3 cuda graph segments, NCCL all-reduces eager between them") if importlib.import_module(PKG + ".train_soft_intro_vae")._graph_mode() >= 1 else "eager") +
+                launch_mode=(("cuda graph replay" if world == 1 else ("replay of ONE cuda graph per iteration, the two ncclAllReduce calls of the library-owned communicator captured inside"
+                                                                    if eng.comm_world == world else "replay of 3 cuda graph segments, torch.distributed all-reduces eager between them"))
+                             if importlib.import_module(PKG + ".train_soft_intro_vae")._graph_mode() >= 1 else "eager") +
                             " of %d kernels per step (counted on an eager step)" % launches_per_step,
                 roofline=roof, clocks=sampler.summary() if rank == 0 else None,
                 last_stats=dict(loss_rec=float(st[5]), kl_real=float(st[1]), lossE=float(st[4]), lossD=float(st[10])))
@@ -386,6 +388,9 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        barrier()
+        # the library's own communicator is deliberately NOT destroyed here: the process is about to exit and the OS reclaims it
+        # (an explicit teardown exists -- Engine.comm_finalize -- and is exercised by tests/dist_worker.py)
         dist.destroy_process_group()
 
 

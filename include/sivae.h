@@ -128,12 +128,17 @@ long long sivae_adam_get_step(const sivae_engine* e, int net);
    collective: raw ncclAllReduce on the step's own stream (capturable in a CUDA graph together with the kernels around it).
    NCCL is resolved at run time with dlopen("libnccl.so.2") -- inside a torch process that is torch's own copy.
      sivae_comm_unique_id: rank 0 creates the 128-byte ncclUniqueId, the caller ships it to the other ranks (any side channel);
-     sivae_comm_init:      every rank, with its CUDA device current: ncclCommInitRank -> the engine owns the communicator;
+     sivae_comm_init:      every rank, with its CUDA device current: ncclCommInitRank.  The communicator is process-global (one
+                           process = one GPU): later engines attach to it with id128 == NULL; it is destroyed only by
+     sivae_comm_finalize   (all ranks, after their last step; never implicitly -- an un-finalized process leaves it to the OS);
+     sivae_comm_global_world: world size of the process-global communicator, 0 if none;
      sivae_allreduce_attach: alternative -- borrow an existing ncclComm_t (not destroyed by the engine); NULL detaches;
      sivae_allreduce_grads: in-place sum-all-reduce of the net's flat gradient buffer (no-op without a communicator);
      sivae_iteration:      E half, all-reduce, Adam(encoder, grad_scale 1/world), D half, all-reduce, Adam(decoder) in one call. */
 int sivae_comm_unique_id(unsigned char* out128);
 int sivae_comm_init(sivae_engine* e, const unsigned char* id128, int world_size, int rank);
+int sivae_comm_global_world(void);
+int sivae_comm_finalize(void);
 int sivae_allreduce_attach(sivae_engine* e, void* nccl_comm);
 int sivae_comm_world(const sivae_engine* e);
 int sivae_allreduce_grads(sivae_engine* e, int net, void* stream);

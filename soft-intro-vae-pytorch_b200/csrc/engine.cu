@@ -872,21 +872,42 @@ extern "C" int sivae_comm_unique_id(unsigned char* out128) {
   memcpy(out128, &id, sizeof(id));
   return 0;
 }
-static void comm_release(sivae_engine* e) {
-  if (e->comm && e->own_comm) { NcclApi* a = nccl_api(); if (a) a->CommDestroy(e->comm); }
-  e->comm = nullptr; e->world = 1; e->own_comm = false;
-}
+// The library's communicator is PROCESS-GLOBAL (one process = one GPU = one rank): created once by the first
+// sivae_comm_init, shared by every engine of the process, and destroyed only by an explicit sivae_comm_finalize -- never from
+// an engine's destructor (ncclCommDestroy from garbage collection or interpreter shutdown runs at rank-dependent times and
+// after CUDA teardown: both hang).  A process that exits without finalizing simply leaves the cleanup to the OS.
+static ncclComm_t g_comm = nullptr;
+static int g_comm_world = 0, g_comm_rank = -1;
+static void comm_release(sivae_engine* e) { e->comm = nullptr; e->world = 1; e->own_comm = false; }
+extern "C" int sivae_comm_global_world(void) { return g_comm ? g_comm_world : 0; }
+// id128 == NULL: attach the process-global communicator that an earlier call created (same world / rank)
 extern "C" int sivae_comm_init(sivae_engine* e, const unsigned char* id128, int world, int rank) {
   NcclApi* a = nccl_api();
   if (!a) return fail(-10, "libnccl.so.2 not found (set SIVAE_NCCL_LIB)");
-  if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(-1, "bad argument");
+  if (!e || world < 1 || rank < 0 || rank >= world) return fail(-1, "bad argument");
   comm_release(e);
-  ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
-  ncclComm_t c = nullptr;
-  ncclResult_t r = a->CommInitRank(&c, world, id, rank);          // on the calling thread's current device
-  if (r != ncclSuccess) return nccl_fail(a, r, "ncclCommInitRank");
-  e->comm = c; e->world = world; e->own_comm = true;
+  if (g_comm) {
+    if (g_comm_world != world || g_comm_rank != rank) return fail(-11, "the process-global communicator has another world size / rank");
+  } else {
+    if (!id128) return fail(-11, "no process-global communicator yet: pass the ncclUniqueId");
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t c = nullptr;
+    ncclResult_t r = a->CommInitRank(&c, world, id, rank);          // on the calling thread's current device
+    if (r != ncclSuccess) return nccl_fail(a, r, "ncclCommInitRank");
+    g_comm = c; g_comm_world = world; g_comm_rank = rank;
+  }
+  e->comm = g_comm; e->world = world; e->own_comm = false;
+  return 0;
+}
+// explicit teardown (after the last step of every engine, all ranks): synchronises the device, then ncclCommDestroy
+extern "C" int sivae_comm_finalize(void) {
+  if (!g_comm) return 0;
+  NcclApi* a = nccl_api();
+  cudaDeviceSynchronize();
+  ncclResult_t r = a ? a->CommDestroy(g_comm) : ncclSuccess;
+  g_comm = nullptr; g_comm_world = 0; g_comm_rank = -1;
+  if (r != ncclSuccess) return nccl_fail(a, r, "ncclCommDestroy");
   return 0;
 }
 extern "C" int sivae_allreduce_attach(sivae_engine* e, void* nccl_comm) {

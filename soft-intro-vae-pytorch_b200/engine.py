@@ -185,19 +185,28 @@ class Engine:
         inside the library.  From then on the gradient all-reduces are raw ncclAllReduce calls on the step's stream."""
         lib = L.load()
         world, rank = dist.get_world_size(), dist.get_rank()
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_ubyte * 128)()
-            L.check(lib.sivae_comm_unique_id(buf), "sivae_comm_unique_id")
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        on_dev = dist.get_backend() == "nccl"
-        t = uid.to(self.device) if on_dev else uid
-        dist.broadcast(t, src=0)
-        raw = bytes(t.cpu().tolist())
-        with torch.cuda.device(self.device):
-            L.check(lib.sivae_comm_init(self.handle, (C.c_ubyte * 128).from_buffer_copy(raw), world, rank), "sivae_comm_init")
+        if lib.sivae_comm_global_world() == world:
+            # the communicator is process-global: a second engine of this process attaches to the existing one
+            L.check(lib.sivae_comm_init(self.handle, None, world, rank), "sivae_comm_init (attach)")
+        else:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_ubyte * 128)()
+                L.check(lib.sivae_comm_unique_id(buf), "sivae_comm_unique_id")
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            on_dev = dist.get_backend() == "nccl"
+            t = uid.to(self.device) if on_dev else uid
+            dist.broadcast(t, src=0)
+            raw = bytes(t.cpu().tolist())
+            with torch.cuda.device(self.device):
+                L.check(lib.sivae_comm_init(self.handle, (C.c_ubyte * 128).from_buffer_copy(raw), world, rank), "sivae_comm_init")
         self._comm_world = world
         self.drop_graphs()
+
+    @staticmethod
+    def comm_finalize():
+        """destroy the process-global communicator (all ranks, after the last step, before dist.destroy_process_group)"""
+        L.check(L.load().sivae_comm_finalize(), "sivae_comm_finalize")
 
     def allreduce_grads(self, net):
         with torch.cuda.device(self.device):

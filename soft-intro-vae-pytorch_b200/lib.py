@@ -57,6 +57,8 @@ _SIGS = {
     "sivae_adam_get_step": (C.c_longlong, [_P, C.c_int]),
     "sivae_comm_unique_id": (C.c_int, [_P]),
     "sivae_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "sivae_comm_global_world": (C.c_int, []),
+    "sivae_comm_finalize": (C.c_int, []),
     "sivae_allreduce_attach": (C.c_int, [_P, _P]),
     "sivae_comm_world": (C.c_int, [_P]),
     "sivae_allreduce_grads": (C.c_int, [_P, C.c_int, _P]),

@@ -191,6 +191,8 @@ def main():
             dist.broadcast(ref, 0)
             assert torch.equal(t, ref), "broadcast_state: %s of net %d differs from rank 0 on rank %d" % (name, net, rank)
     dist.barrier()
+    torch.cuda.synchronize()
+    E.Engine.comm_finalize()
     if rank == 0:
         print("DIST_OK world=%d graph_vs_eager[%s] allreduce_rel_err=%.3g dp_oracle_grad_rel_l2=(%.3g, %.3g)"
               % (world, " ".join(report), err, worst_ge, worst_gd))

@@ -21,5 +21,5 @@ def test_two_gpu_data_parallel_step():
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(HERE, "dist_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert r.returncode == 0 and "DIST_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
