@@ -122,6 +122,9 @@ struct sivae_engine {
   bool have_e_state = false;
   // data parallel: NCCL communicator the gradient all-reduces run on, enqueued on the step's own stream
   ncclComm_t comm = nullptr; int world = 1; bool own_comm = false;
+  // overlap of the encoder-gradient all-reduce + Adam(encoder) with the two decoder passes that open the D half (they do not
+  // depend on the encoder): a library-owned side stream forked from / joined back into the step's stream with events
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool dp_overlap = true;
   bool reuse_dec = false;          // D half re-uses the E half's fake / rec decoder passes (SIVAE_REUSE_DEC=1 or sivae_set_option)
   bool e_dec_valid = false;        // dp[0] / dp[1] hold D(noise) / D(z) of the current decoder weights
 };
@@ -784,6 +787,7 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
   e->comp = cfg->conv_backend == SIVAE_CONV_TC3X;
   { const char* v = getenv("SIVAE_BN_MASK"); e->bn_mask = !(v && v[0] == '0'); }
   { const char* v = getenv("SIVAE_REUSE_DEC"); e->reuse_dec = v && v[0] == '1'; }
+  { const char* v = getenv("SIVAE_DP_OVERLAP"); e->dp_overlap = !(v && v[0] == '0'); }
   for (int i = 0; i < 3; ++i) { e->nets[i].id = i; e->nets[i].comp = e->comp; }
   build_encoder(e, e->nets[0]);
   build_decoder(e, e->nets[1]);
@@ -935,7 +939,12 @@ extern "C" int sivae_allreduce_grads(sivae_engine* e, int net, void* stream) {
   return 0;
 }
 extern "C" void sivae_destroy(sivae_engine* e) {
-  if (e) comm_release(e);
+  if (e) {
+    comm_release(e);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->side) cudaStreamDestroy(e->side);
+  }
   delete e;
 }
 static Net* get_net(sivae_engine* e, int net) {
@@ -1068,7 +1077,13 @@ extern "C" int sivae_e_step(sivae_engine* e, const float* real_nchw, const float
   return 0;
 }
 
+// join (nullable): an event recorded on ANOTHER stream after the encoder's Adam step; the D half then starts with its two
+// encoder-independent decoder passes, waits for the event and only then touches the encoder's (refreshed) filters
+static int d_step_impl(sivae_engine* e, const float* eps, const sivae_hyper* hp, float* stats, void* stream, cudaEvent_t join);
 extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper* hp, float* stats, void* stream) {
+  return d_step_impl(e, eps, hp, stats, stream, nullptr);
+}
+static int d_step_impl(sivae_engine* e, const float* eps, const sivae_hyper* hp, float* stats, void* stream, cudaEvent_t join) {
   if (!e || !e->have_e_state) return fail(-6, "sivae_d_step requires a preceding sivae_e_step");
   const int B = e->cur_batch;
   TRY(check_ready(e, B));
@@ -1086,7 +1101,8 @@ extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper
   // and rec = D(z) (:597-598) are bit for bit the E half's passes (:557,:561), whose activations still sit in dp[0] / dp[1]
   const bool reuse = e->reuse_dec && e->e_dec_valid && !dn.dirty && e->dp[0].net == &dn && e->dp[1].net == &dn;
   e->e_dec_valid = false;
-  TRY(refresh_derived(e, en, st)); TRY(refresh_derived(e, dn, st));
+  if (!join) TRY(refresh_derived(e, en, st));
+  TRY(refresh_derived(e, dn, st));
   if (boot) TRY(refresh_derived(e, tn, st));
   const float *eps4 = eps, *eps5 = eps + (long long)B * z;
   EncPass &E4 = e->ep[0], &E5 = e->ep[1];
@@ -1098,6 +1114,10 @@ extern "C" int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper
   } else {
     TRY(dec_forward(e, dn, D5, e->noise, B, true, true, st));         // fake :597
     TRY(dec_forward(e, dn, D6, e->z_keep, B, true, true, st));        // rec  :598
+  }
+  if (join) {                         // the encoder's all-reduce + Adam step ran beside the two passes above
+    cudaStreamWaitEvent(st, join, 0);
+    TRY(refresh_derived(e, en, st));
   }
   TRY(enc_forward(e, en, E4, D6.y, B, true, false, st));              // :601  (encoder: dgrad-only in this half)
   launch_kl_reparam(E4.ml, eps4, E4.z, E4.kl, B, z, st);
@@ -1198,9 +1218,25 @@ extern "C" int sivae_iteration(sivae_engine* e, const float* real_nchw, const fl
   if (!e || !eps5) return fail(-1, "null argument");
   const float gs = 1.f / (float)(e->world > 0 ? e->world : 1);
   TRY(sivae_e_step(e, real_nchw, noise, eps5, B, hp, stats, stream));
-  TRY(sivae_allreduce_grads(e, SIVAE_NET_ENCODER, stream));
-  TRY(sivae_adam_step(e, SIVAE_NET_ENCODER, lr_e, gs, stream));
-  TRY(sivae_d_step(e, eps5 + 3LL * B * e->cfg.zdim, hp, stats, stream));
+  if (e->comm && e->world > 1 && e->dp_overlap && !e->reuse_dec) {
+    if (!e->side) {
+      if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return fail(-3, "could not create the side stream of the data-parallel overlap");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEventRecord(e->ev_fork, st);
+    cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+    TRY(sivae_allreduce_grads(e, SIVAE_NET_ENCODER, e->side));
+    TRY(sivae_adam_step(e, SIVAE_NET_ENCODER, lr_e, gs, e->side));
+    cudaEventRecord(e->ev_join, e->side);
+    TRY(d_step_impl(e, eps5 + 3LL * B * e->cfg.zdim, hp, stats, stream, e->ev_join));
+  } else {
+    TRY(sivae_allreduce_grads(e, SIVAE_NET_ENCODER, stream));
+    TRY(sivae_adam_step(e, SIVAE_NET_ENCODER, lr_e, gs, stream));
+    TRY(sivae_d_step(e, eps5 + 3LL * B * e->cfg.zdim, hp, stats, stream));
+  }
   TRY(sivae_allreduce_grads(e, SIVAE_NET_DECODER, stream));
   TRY(sivae_adam_step(e, SIVAE_NET_DECODER, lr_d, gs, stream));
   return 0;
