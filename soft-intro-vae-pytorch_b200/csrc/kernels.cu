@@ -466,8 +466,8 @@ void launch_colsum(const float* in, float* out, long long rows, int C, bool accu
 // =====================================================================================================
 // rows handled by one block of the per-channel reductions: sized so that the grid is ~4 waves of 148 SMs even for the
 // low-resolution layers (a fixed 1024 rows/block left the 4x4..16x16 layers on 1..8 SMs)
-constexpr int BN_MAX_BLOCKS = 148 * 8;      // 8 resident 256-thread blocks per SM: one full wave (ncu r02d: the reduce kernels
-                                            // ran at 57-73 % of the HBM rate the apply kernels reach with 4 blocks per SM)
+constexpr int BN_MAX_BLOCKS = 148 * 4;      // (148 * 8 blocks + a 4x unrolled row loop measured SLOWER: 21.9 vs 20.6 ms of BN backward
+                                            // per config-H step, profiles/r02e_bench_H_bnreduce_grid.json)
 static int bn_rows_per_block(long long rows) {
   long long r = (rows + BN_MAX_BLOCKS - 1) / BN_MAX_BLOCKS;
   if (r < 16) r = 16;
@@ -761,7 +761,6 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const float* __restrict__
     float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cl);
     long long r0 = (long long)blockIdx.x * rpb;
     long long r1 = min(rows, r0 + rpb);
-#pragma unroll 4
     for (long long r = r0 + rl; r < r1; r += rl_n) {
       int w = 0, h = 0, n = 0;
       if (MODE != RS_NONE) {
