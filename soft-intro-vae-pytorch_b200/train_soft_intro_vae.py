@@ -360,16 +360,97 @@ def record_image(writer, image_list, cur_iter, num_rows=8):
 
 
 def load_model(model, pretrained, device):
+    """reference :316-318.  A checkpoint written by this module also carries `sivae_train_state` (see save_checkpoint); it is
+    kept on the model and applied by the trainer once the engine exists, so that training RESUMES (optimiser moments and step
+    counters, RNG streams, iteration counter) instead of restarting Adam from zero like the reference does."""
     weights = torch.load(pretrained, map_location=device)
     model.load_state_dict(weights['model'], strict=False)
+    model._resume_state = weights.get("sivae_train_state")
+
+
+def _train_state(model, iteration):
+    """what the reference's checkpoints lack: Adam moments / step counters per parameter (reference key names
+    and logical shapes), the four RNG streams the trainer draws from, the iteration counter"""
+    eng = getattr(model, "_engine", None)
+    if eng is None:
+        return None
+    lib = _L.load()
+    adam = {}
+    for net_id, mod in model._nets().items():
+        mem = eng.mem[net_id]
+        if mem.m is None:
+            continue
+        pref = {_L.NET_ENCODER: "encoder.", _L.NET_DECODER: "decoder."}[net_id]
+        ent = {"step": int(lib.sivae_adam_get_step(eng.handle, net_id)), "m": {}, "v": {}}
+        for name, kind, off, numel, shape in mem.tensors:
+            ent["m"][pref + name] = _E.NetMemory.view(mem.m, kind, off, numel, shape).detach().cpu().contiguous()
+            ent["v"][pref + name] = _E.NetMemory.view(mem.v, kind, off, numel, shape).detach().cpu().contiguous()
+        adam[net_id] = ent
+    # plain tensors / ints / floats / strings only, so that torch.load(weights_only=True) -- the default the reference's own
+    # load_model runs into under current torch -- still accepts the file
+    pv, pstate, pgauss = random.getstate()
+    nname, nkey, npos, nhas, ncached = np.random.get_state()
+    rng = {"python": {"version": int(pv), "state": torch.tensor(list(pstate), dtype=torch.int64), "gauss": pgauss},
+           "numpy": {"name": str(nname), "key": torch.from_numpy(nkey.astype(np.int64)), "pos": int(npos), "has_gauss": int(nhas),
+                     "cached": float(ncached)},
+           "torch_cpu": torch.get_rng_state(), "torch_cuda": torch.cuda.get_rng_state(eng.device)}
+    return {"version": 1, "adam": adam, "rng": rng, "cur_iter": int(iteration)}
+
+
+def _restore_train_state(model, st, restore_rng=True):
+    eng = model._engine
+    lib = _L.load()
+    with torch.no_grad():
+        for net_id, ent in st["adam"].items():
+            mem = eng.mem[net_id]
+            pref = {_L.NET_ENCODER: "encoder.", _L.NET_DECODER: "decoder."}[net_id]
+            for name, kind, off, numel, shape in mem.tensors:
+                _E.NetMemory.view(mem.m, kind, off, numel, shape).copy_(ent["m"][pref + name])
+                _E.NetMemory.view(mem.v, kind, off, numel, shape).copy_(ent["v"][pref + name])
+            lib.sivae_adam_set_step(eng.handle, net_id, int(ent["step"]))
+    if restore_rng:
+        r = st["rng"]
+        random.setstate((r["python"]["version"], tuple(int(x) for x in r["python"]["state"].tolist()), r["python"]["gauss"]))
+        np.random.set_state((r["numpy"]["name"], r["numpy"]["key"].numpy().astype(np.uint32), r["numpy"]["pos"], r["numpy"]["has_gauss"],
+                             r["numpy"]["cached"]))
+        torch.set_rng_state(r["torch_cpu"].cpu())
+        torch.cuda.set_rng_state(r["torch_cuda"].cpu(), eng.device)
+    return int(st.get("cur_iter", 0))
+
+
+_save_thread = None
+
+
+def _join_async_save():
+    global _save_thread
+    if _save_thread is not None:
+        _save_thread.join()
+        _save_thread = None
 
 
 def save_checkpoint(model, epoch, iteration, prefix=""):
+    """reference :321-329: `{"epoch", "model": state_dict}` at ./saves/<prefix>model_epoch_{e}_iter_{i}.pth -- loadable by the
+    reference.  Extensions a reference loader ignores (it reads only ['model']): the key `sivae_train_state` (optimiser + RNG
+    state for an exact resume; SIVAE_CKPT_STATE=0 omits it) and SIVAE_ASYNC_SAVE=1 = the file is written by a background thread
+    from a host snapshot taken here (the pattern of style_soft_intro_vae/checkpointer.py:60-67); joined before the next save and
+    at the end of training."""
+    global _save_thread
     os.makedirs("./saves/", exist_ok=True)
     path = "./saves/" + prefix + "model_epoch_{}_iter_{}.pth".format(epoch, iteration)
-    # contiguous copies in the reference layout, so the file is loadable by the reference and small
-    state = {k: v.detach().clone().contiguous() for k, v in model.state_dict().items()}
-    torch.save({"epoch": epoch, "model": state}, path)
+    # contiguous host copies in the reference layout, so the file is loadable by the reference and small
+    state = {k: v.detach().cpu().clone().contiguous() for k, v in model.state_dict().items()}
+    payload = {"epoch": epoch, "model": state}
+    if os.environ.get("SIVAE_CKPT_STATE", "1") != "0":
+        ts = _train_state(model, iteration)
+        if ts is not None:
+            payload["sivae_train_state"] = ts
+    _join_async_save()
+    if os.environ.get("SIVAE_ASYNC_SAVE", "0") == "1":
+        import threading
+        _save_thread = threading.Thread(target=torch.save, args=(payload, path), daemon=False)
+        _save_thread.start()
+    else:
+        torch.save(payload, path)
     print("model checkpoint saved @ {}".format(path))
 
 
@@ -675,6 +756,11 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
     if main:
         print(model)
     model.reserve(batch_size)
+    resumed_iter = 0
+    if getattr(model, "_resume_state", None) is not None:
+        # checkpoint written by this module: continue Adam, the RNG streams and the iteration counter where they stopped
+        resumed_iter = _restore_train_state(model, model._resume_state, restore_rng=os.environ.get("SIVAE_RESUME_RNG", "1") != "0")
+        model._resume_state = None
     if dist:
         # every replica starts from rank 0's state (weights, BN buffers, Adam state): with the default seed = -1 each rank
         # would otherwise build different random weights and only the gradients would ever be averaged
@@ -704,7 +790,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
         loader = DevicePrefetcher(loader, device)           # host->device copy of batch i+1 under step i
     from tqdm import tqdm
     start_time = time.time()
-    cur_iter = 0
+    cur_iter = resumed_iter
     track = _Tracker()
     best_fid = None
     eps = torch.empty(5, batch_size, z_dim, device=device)
@@ -848,6 +934,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                 pickle.dump({"kl_real": h["kl_real"], "kl_fake": h["kl_fake"], "kl_rec": h["kl_rec"], "rec_err": h["rec_err"]}, fp)
             save_checkpoint(model, epoch, cur_iter, prefix)
             model.train()
+    _join_async_save()
 
 
 if __name__ == '__main__':

@@ -85,3 +85,61 @@ def test_reference_main_runs_unmodified_against_the_dropin(tmp_path, bootstrap, 
     assert torch.allclose(mu_d.cpu(), mu_r, rtol=1e-3, atol=1e-4)
     assert torch.allclose(lv_d.cpu(), lv_r, rtol=1e-3, atol=1e-4)
     assert torch.allclose(y_d.cpu(), y_r, rtol=1e-3, atol=1e-3)
+
+
+def test_fid_path_of_the_reference_runs_on_the_dropin_model():
+    """the reference's own FID code (metrics/fid_score.py:213-271, 274-325, 454-469, taken unmodified from
+    oracle/_ref) drives the drop-in model through `model_s.zdim` and `model_s.sample(noise)` (:246-247).  InceptionV3 needs
+    downloaded weights (no network here), so that ONE module global is substituted by a small fixed feature extractor; the
+    generator sampling, uint8 round trip, activation statistics and scipy Frechet distance are the reference's code."""
+    ref_root = ref_arm.reference_root()
+    if ref_root is None:
+        pytest.skip("no reference scripts (oracle/_ref not built and /root/reference absent)")
+    sub = os.path.join(ref_root, "soft_intro_vae")
+    for m in ("metrics", "metrics.fid_score", "metrics.inception"):
+        sys.modules.pop(m, None)
+    sys.path.insert(0, sub)
+    try:
+        fid = importlib.import_module("metrics.fid_score")
+    finally:
+        sys.path.pop(0)
+    dims = 12
+
+    class StubInception(torch.nn.Module):
+        BLOCK_INDEX_BY_DIM = {dims: 0}
+
+        def __init__(self, blocks):
+            super().__init__()
+            g = torch.Generator().manual_seed(0)
+            self.proj = torch.nn.Parameter(torch.randn(dims, 3, 4, 4, generator=g), requires_grad=False)
+
+        def forward(self, x):
+            # [B, dims, 1, 1] like pool_3 of the real network (the generator path, :254, does not pool itself)
+            return [torch.nn.functional.adaptive_avg_pool2d(torch.nn.functional.conv2d(x, self.proj, stride=4), (1, 1))]
+
+    fid.InceptionV3 = StubInception
+    # the reference pins scipy 1.5.3 (environment.yml:93) and calls linalg.sqrtm(..., disp=False) -> (sqrtm, errest) (:307); the
+    # image's scipy dropped that keyword, so the old calling convention is restored around the same routine
+    import types
+    import scipy.linalg as _sl
+    fid.linalg = types.SimpleNamespace(sqrtm=lambda a, disp=True: (_sl.sqrtm(a), 0.0) if not disp else _sl.sqrtm(a))
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    torch.manual_seed(5)
+    stdout, sys.stdout = sys.stdout, open(os.devnull, "w")
+    try:
+        model = M.SoftIntroVAE(cdim=3, zdim=32, channels=[64, 128, 256], image_size=32).to("cuda:0")
+    finally:
+        sys.stdout = stdout
+    model.eval()
+    g = torch.Generator().manual_seed(6)
+    loader = [torch.rand(8, 3, 32, 32, generator=g) for _ in range(4)]
+    dev = torch.device("cuda:0")
+    with torch.no_grad():
+        stdout, sys.stdout = sys.stdout, open(os.devnull, "w")
+        try:
+            val = fid.calculate_fid_given_dataset(loader, model, 8, cuda=True, dims=dims, device=dev, num_images=32)
+        finally:
+            sys.stdout = stdout
+    assert val == val and abs(val) < 1e6            # a finite Frechet distance came out of the reference's code
+    for m in ("metrics", "metrics.fid_score", "metrics.inception"):
+        sys.modules.pop(m, None)

@@ -279,6 +279,49 @@ def test_train_driver_end_to_end(tmp_path):
         os.chdir(cwd)
 
 
+def test_resume_from_checkpoint_is_bit_identical_to_uninterrupted_training(tmp_path):
+    """the reference's checkpoints hold only the weights, so its resumed runs restart Adam from zero moments.  The
+    drop-in's files carry, next to the reference-schema {"epoch", "model"}, the Adam moments / step counters, the four RNG
+    streams and the iteration counter (`sivae_train_state`): a run resumed from the periodic checkpoint written at the start of
+    epoch 1 must end with bit for bit the weights, BN buffers and epoch statistics of the uninterrupted run.  SIVAE_ASYNC_SAVE=1:
+    files written by a background thread must be complete when train_soft_intro_vae() returns."""
+    import importlib
+    import pickle
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    kw = dict(dataset="synthetic32:48", z_dim=32, batch_size=16, num_workers=0, num_vae=0, beta_kl=1.0, beta_neg=256,
+              beta_rec=1.0, device=torch.device("cuda:0"), save_interval=1, lr_e=2e-4, lr_d=2e-4, seed=5, test_iter=1000,
+              with_fid=False)
+    cwd = os.getcwd()
+    os.environ["SIVAE_ASYNC_SAVE"] = "1"
+    try:
+        a_dir, b_dir = tmp_path / "a", tmp_path / "b"
+        a_dir.mkdir(); b_dir.mkdir()
+        os.chdir(a_dir)
+        M.train_soft_intro_vae(num_epochs=2, start_epoch=0, pretrained=None, **kw)             # uninterrupted: epochs 0 and 1
+        saves = sorted(os.listdir("saves"))
+        mid = [f for f in saves if f.endswith("model_epoch_1_iter_3.pth")]
+        end_a = [f for f in saves if f.endswith("model_epoch_1_iter_6.pth")]
+        assert mid and end_a, saves
+        ck_mid = torch.load(os.path.join("saves", mid[0]), map_location="cpu")                # default weights_only=True must accept it
+        assert set(ck_mid) == {"epoch", "model", "sivae_train_state"} and ck_mid["sivae_train_state"]["cur_iter"] == 3
+        assert ck_mid["sivae_train_state"]["adam"][0]["step"] == 3
+        final_a = torch.load(os.path.join("saves", end_a[0]), map_location="cpu")["model"]
+        hist_a = pickle.load(open("soft_intro_train_graphs_data.pickle", "rb"))
+        os.chdir(b_dir)
+        M.train_soft_intro_vae(num_epochs=2, start_epoch=1, pretrained=str(a_dir / "saves" / mid[0]), **kw)   # resumed: epoch 1 only
+        end_b = [f for f in os.listdir("saves") if f.endswith("model_epoch_1_iter_6.pth")]
+        assert end_b, os.listdir("saves")
+        final_b = torch.load(os.path.join("saves", end_b[0]), map_location="cpu")["model"]
+        hist_b = pickle.load(open("soft_intro_train_graphs_data.pickle", "rb"))
+        for k in final_a:
+            assert torch.equal(final_a[k], final_b[k]), "resumed run differs from the uninterrupted one in " + k
+        assert hist_a["kl_real"][-1] == hist_b["kl_real"][-1] and hist_a["rec_err"][-1] == hist_b["rec_err"][-1]
+    finally:
+        os.environ.pop("SIVAE_ASYNC_SAVE", None)
+        os.chdir(cwd)
+
+
 def test_graph_replay_is_bit_identical_to_eager():
     """introspective_iteration() replays the step from a CUDA graph from its third call on (Engine.graphed): every
     kernel is deterministic and all iteration state lives on the device, so five graphed iterations must leave exactly
