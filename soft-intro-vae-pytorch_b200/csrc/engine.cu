@@ -1207,6 +1207,12 @@ extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_sc
               (cudaStream_t)stream);
   n->dirty = true;
   CHECK_CUDA_RET();
+  // The derived operand copies (split32 / bf16 / tf32 filters) are refreshed HERE, on the same stream, not lazily at their next
+  // use: the lazy form made the kernel sequence of a step depend on a host flag, and a CUDA graph captured right after an
+  // inference call (the trainer's iteration-0 sample grid: sivae_decode refreshes the decoder and clears its flag) then
+  // lacked the decoder refresh -- every replay ran the decoder on the filters of the capture iteration.  Found by
+  // tests/test_gpu_step.py::test_resume_from_checkpoint_is_bit_identical_to_uninterrupted_training.
+  if (e->ws) TRY(refresh_derived(e, *n, (cudaStream_t)stream));
   return 0;
 }
 // One whole introspective iteration (:551-624) as a single enqueue: E half, [all-reduce of the encoder gradients],

@@ -404,14 +404,14 @@ def _restore_train_state(model, st, restore_rng=True):
         for net_id, ent in st["adam"].items():
             mem = eng.mem[net_id]
             pref = {_L.NET_ENCODER: "encoder.", _L.NET_DECODER: "decoder."}[net_id]
-            for name, kind, off, numel, shape in mem.tensors:
-                _E.NetMemory.view(mem.m, kind, off, numel, shape).copy_(ent["m"][pref + name])
-                _E.NetMemory.view(mem.v, kind, off, numel, shape).copy_(ent["v"][pref + name])
+            for name, kind, off, numel, shape in mem.tensors:          # (map_location may have put the saved tensors anywhere)
+                _E.NetMemory.view(mem.m, kind, off, numel, shape).copy_(ent["m"][pref + name].to(mem.m.device))
+                _E.NetMemory.view(mem.v, kind, off, numel, shape).copy_(ent["v"][pref + name].to(mem.v.device))
             lib.sivae_adam_set_step(eng.handle, net_id, int(ent["step"]))
     if restore_rng:
         r = st["rng"]
         random.setstate((r["python"]["version"], tuple(int(x) for x in r["python"]["state"].tolist()), r["python"]["gauss"]))
-        np.random.set_state((r["numpy"]["name"], r["numpy"]["key"].numpy().astype(np.uint32), r["numpy"]["pos"], r["numpy"]["has_gauss"],
+        np.random.set_state((r["numpy"]["name"], r["numpy"]["key"].cpu().numpy().astype(np.uint32), r["numpy"]["pos"], r["numpy"]["has_gauss"],
                              r["numpy"]["cached"]))
         torch.set_rng_state(r["torch_cpu"].cpu())
         torch.cuda.set_rng_state(r["torch_cuda"].cpu(), eng.device)

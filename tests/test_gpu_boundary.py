@@ -57,7 +57,7 @@ def test_reference_main_runs_unmodified_against_the_dropin(tmp_path, bootstrap, 
     saves = sorted(os.listdir(tmp_path / "saves"))
     assert len(saves) == 1 and saves[0].endswith("model_epoch_0_iter_3.pth"), saves
     ck = torch.load(tmp_path / "saves" / saves[0], map_location="cpu")
-    assert set(ck) == {"epoch", "model"}
+    assert set(ck) == {"epoch", "model", "sivae_train_state"}          # reference schema + the resume state its loader ignores
     # the REFERENCE's model class loads the drop-in's checkpoint strictly ...
     ref = ref_arm.import_reference(bootstrap)
     torch.manual_seed(0)

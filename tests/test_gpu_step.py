@@ -261,7 +261,8 @@ def test_train_driver_end_to_end(tmp_path):
         saves = sorted(os.listdir("saves"))
         assert any(s.endswith("model_epoch_1_iter_6.pth") for s in saves), saves
         ck = torch.load(os.path.join("saves", [s for s in saves if s.endswith("iter_6.pth")][0]), map_location="cpu")
-        assert set(ck) == {"epoch", "model"} and ck["epoch"] == 1
+        # the reference's schema, plus the resume state its loader ignores
+        assert set(ck) == {"epoch", "model", "sivae_train_state"} and ck["epoch"] == 1
         sd = ck["model"]
         assert sd["encoder.main.0.weight"].shape == (64, 3, 5, 5) and sd["encoder.main.0.weight"].is_contiguous()
         assert sd["decoder.main.predict.bias"].shape == (3,)
@@ -351,6 +352,43 @@ def test_graph_replay_is_bit_identical_to_eager():
     (sd_a, st_a), (sd_b, st_b) = outs
     for a, b in zip(st_a, st_b):
         assert torch.equal(a, b)
+    for k in sd_a:
+        assert torch.equal(sd_a[k], sd_b[k]), k
+
+
+def test_inference_calls_between_iterations_do_not_stale_the_graph():
+    """Regression (round 2): the trainer draws a sample grid after iteration 0 (reference :641-646: model(real_batch),
+    model.sample) -- engine inference calls between the eager first iteration and the one that is CAPTURED.  With lazily refreshed
+    operand copies such a call cleared the decoder's host-side dirty flag, the captured graph lacked the decoder refresh and
+    every replay ran the decoder on stale filters.  Eager and graphed training with interleaved inference must stay bit-identical."""
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    cfg = dict(cdim=3, zdim=32, channels=[32, 64], image_size=32)
+    g = torch.Generator().manual_seed(21)
+    reals = [torch.rand(8, 3, 32, 32, generator=g).cuda() for _ in range(5)]
+    noises = [torch.randn(8, 32, generator=g).cuda() for _ in range(5)]
+    epss = [torch.randn(5, 8, 32, generator=g).cuda() for _ in range(5)]
+    hp = E.make_hyper(1.0, 1.0, 256.0, 1e-8, 1.0 / (3 * 32 * 32))
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(4)
+        model = M.SoftIntroVAE(**cfg).to("cuda:0")
+        stats, imgs = [], []
+        for i in range(5):
+            st = M.introspective_iteration(model, reals[i], noises[i], epss[i], hp, 2e-4, 2e-4, use_graph=use_graph)
+            stats.append(st.clone())
+            if i in (0, 2, 3):
+                _, _, _, rec = model(reals[i], deterministic=True)
+                imgs.append((rec.clone(), model.sample(noises[i]).clone()))
+        torch.cuda.synchronize()
+        outs.append(({k: v.detach().clone() for k, v in model.state_dict().items()}, stats, imgs))
+    (sd_a, st_a, im_a), (sd_b, st_b, im_b) = outs
+    for a, b in zip(st_a, st_b):
+        assert torch.equal(a, b)
+    for (ra, sa), (rb, sb) in zip(im_a, im_b):
+        assert torch.equal(ra, rb) and torch.equal(sa, sb)
     for k in sd_a:
         assert torch.equal(sd_a[k], sd_b[k]), k
 
