@@ -439,7 +439,9 @@ static int refresh_derived(sivae_engine* e, Net& n, cudaStream_t st) {
     ConvShape sd{1, size, size, c.cout, c.cin, c.k};
     const long long wn = (long long)c.cout * c.cin * c.k * c.k;
     const bool d_tc = fwd_on_tc(e, sd) && !fwd_on_narrow(e, sd);
-    launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, d_tc && !e->comp, st);
+    // (bf16 backward: the residual blocks' dgrads read only the bf16 form below; the tf32 form is needed by the image-facing convs)
+    if (!(e->bwd16 && c.k != 5))
+      launch_pack_dgrad_filter(n.params + c.w_off, n.derived + c.wd_off, c.cout, c.cin, c.k, d_tc && !e->comp, st);
     if (d_tc && e->comp) launch_split_tf32(n.derived + c.wd_off, n.derived + c.wd_off, n.derived + c.wdl_off, wn, st);
     if (e->bwd16 && c.k != 5) launch_pack_dgrad_filter_bf16(n.params + c.w_off, n.derived + c.wdh_off, c.cout, c.cin, c.k, st);
     ConvShape sf{1, size, size, c.cin, c.cout, c.k};
