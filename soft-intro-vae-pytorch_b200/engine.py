@@ -173,6 +173,7 @@ class Engine:
         for net, s in steps.items():
             lib.sivae_adam_set_step(self.handle, net, s)
         self.reuse_decoder_passes = reuse
+        self._comm_world = 1        # the new handle is not attached to the process-global communicator yet (re-attached on next use)
 
     # ---- data parallel: the library-owned NCCL communicator ------------------------------------------------------
     @property
