@@ -516,8 +516,19 @@ def stock_torch_leg(cfg_name, device, steps=3, warmup=2):
     convolutions: what the unmodified reference does on this GPU under torch 2.11).  Runs the oracle's functional restatement
     (test infrastructure, timed here only as the thing being compared AGAINST) with the workload's shapes on the device."""
     import torch
+    from oracle import ref_arm
     from oracle import sivae_oracle as O
     size, zdim, channels, batch, beta_neg, boot, gflop_img = CONFIGS[cfg_name]
+    flags = "torch.backends.cudnn.allow_tf32 = %s, matmul.allow_tf32 = %s: torch defaults = what the unmodified reference runs" % (
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    if ref_arm.reference_root() is not None:
+        # the UNMODIFIED reference trainer itself (oracle/_ref), device = this GPU
+        dt, _ = ref_arm.time_reference_iterations(size, zdim, batch, beta_neg, boot, warmup=warmup, steps=steps, device=str(device))
+        ms = dt * 1e3
+        return dict(what="the UNMODIFIED reference train_soft_intro_vae() (oracle/_ref) on this GPU through stock PyTorch %s / cuDNN %s "
+                         "(%s); full batch of %d, its own loop incl. the per-iteration .item() reads" % (
+                             torch.__version__, torch.backends.cudnn.version(), flags, batch),
+                    ms_per_step=round(ms, 2), value=round(batch / (ms * 1e-3), 2), unit="images/s", steps=steps, warmup=warmup)
     arch = O.Arch(cdim=3, zdim=zdim, channels=channels, image_size=size)
     sd = {k: v.to(device) for k, v in O.make_state_dict(arch, seed=0, bootstrap=boot).items()}
     hp = O.Hyper(beta_neg=beta_neg, gamma_r=1.0 if boot else 1e-8, scale=1.0 / (3 * size * size))

@@ -71,9 +71,12 @@ class _Synth(torch.utils.data.Dataset):
         return (self.x[i], 0) if self.labelled else self.x[i]
 
 
-def time_reference_iterations(size, zdim, batch, beta_neg, bootstrap=False, warmup=1, steps=1, threads=None, seed=0):
-    """run the reference's own train function for (warmup + steps) iterations of `batch` images on the CPU; returns
-    (seconds per timed iteration, list of all iteration times)"""
+def time_reference_iterations(size, zdim, batch, beta_neg, bootstrap=False, warmup=1, steps=1, threads=None, seed=-1, device="cpu"):
+    """run the reference's own train function for (warmup + steps) iterations of `batch` images on `device` ("cpu": the CPU arm;
+    "cuda:N": the unmodified reference through stock PyTorch / cuDNN on that GPU -- its loop reads ten scalars with .item() every
+    iteration (:628-639), so the host time between two batch requests is the device time of the iteration); returns
+    (seconds per timed iteration, list of all iteration times).  seed = -1 like the reference's default (a fixed seed would also
+    switch cudnn.deterministic on, :372)."""
     ref = import_reference(bootstrap)
     threads = threads or (os.cpu_count() or 1)
     torch.set_num_threads(threads)
@@ -124,7 +127,7 @@ def time_reference_iterations(size, zdim, batch, beta_neg, bootstrap=False, warm
     sys.stdout = open(os.devnull, "w")
     try:
         kw = dict(dataset=_DATASET[size], z_dim=zdim, batch_size=batch, num_workers=0, num_epochs=1, num_vae=0, beta_kl=1.0,
-                  beta_neg=beta_neg, beta_rec=1.0, device=torch.device("cpu"), seed=seed, test_iter=10 ** 9, save_interval=50,
+                  beta_neg=beta_neg, beta_rec=1.0, device=torch.device(device), seed=seed, test_iter=10 ** 9, save_interval=50,
                   start_epoch=0, lr_e=2e-4, lr_d=2e-4)
         if bootstrap:
             kw.update(gamma_r=1.0, copy_to_target_freq=1)
@@ -135,6 +138,9 @@ def time_reference_iterations(size, zdim, batch, beta_neg, bootstrap=False, warm
         os.chdir(cwd)
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(torch.device(device))
+        torch.cuda.empty_cache()
     its = [b - a for a, b in zip(stamps[:-1], stamps[1:])]
     assert len(its) == n_it, (len(its), n_it)
     timed = its[warmup:]
