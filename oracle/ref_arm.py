@@ -145,3 +145,62 @@ def time_reference_iterations(size, zdim, batch, beta_neg, bootstrap=False, warm
     assert len(its) == n_it, (len(its), n_it)
     timed = its[warmup:]
     return sum(timed) / len(timed), its
+
+
+def run_reference_training(n_images, batch, zdim, beta_neg, seed, device="cpu", size=32, bootstrap=False, threads=None):
+    """the UNMODIFIED reference `train_soft_intro_vae()` for one epoch over a synthetic data set (the tensor the drop-in's
+    `synthetic<size>:<n>` data set holds: torch.rand with generator seed 1234) with a fixed seed; returns the tqdm postfix
+    dictionaries of its iterations (:629-631: r_loss, kl, diff_kl, expelbo_f) -- the trainer-level trace the drop-in is held to"""
+    ref = import_reference(bootstrap)
+    if threads:
+        torch.set_num_threads(threads)
+    trace = []
+
+    class Bar:
+        def __init__(self, iterable=None, **k):
+            self.it = iterable
+
+        def __iter__(self):
+            return iter(self.it)
+
+        def set_description_str(self, *a, **k):
+            pass
+
+        def set_postfix(self, **k):
+            trace.append({n: float(v) for n, v in k.items()})
+
+        def close(self):
+            pass
+
+    ref.tqdm = Bar
+    ds = _Synth(n_images, size, labelled=size == 32)
+    if size == 32:
+        ref.CIFAR10 = lambda *a, **k: ds
+    else:
+        ref.ImageDatasetFromFile = lambda *a, **k: ds
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="sivae_reftrace_")
+    run_dir = os.path.join(tmp, "run")
+    os.makedirs(run_dir)
+    if size != 32:
+        d = os.path.join(tmp, "data", "celeb256", "img_align_celeba")
+        os.makedirs(d)
+        for i in range(4):
+            open(os.path.join(d, "%06d.jpg" % i), "w").close()
+    os.chdir(run_dir)
+    stdout = sys.stdout
+    sys.stdout = open(os.devnull, "w")
+    try:
+        kw = dict(dataset=_DATASET[size], z_dim=zdim, batch_size=batch, num_workers=0, num_epochs=1, num_vae=0, beta_kl=1.0,
+                  beta_neg=beta_neg, beta_rec=1.0, device=torch.device(device), seed=seed, test_iter=1000, save_interval=50,
+                  start_epoch=0, lr_e=2e-4, lr_d=2e-4)
+        if bootstrap:
+            kw.update(gamma_r=1.0, copy_to_target_freq=1)
+        getattr(ref, "train_soft_intro_vae")(**kw)
+    finally:
+        sys.stdout.close()
+        sys.stdout = stdout
+        os.chdir(cwd)
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return trace
