@@ -5,7 +5,7 @@ shapes and at the architectures of BASELINE.json's configs C, M, H and Bs.
 Tolerances (relative; tensors: relative L2) -- measured deviations are logged to gpurun_out/parity_report.jsonl:
   exact path (conv_backend 1: fp32 SIMT, fp64-chunked accumulation)   scalars 2e-5, gradients / BN statistics 2e-4
   DEFAULT tensor-core path (conv_backend 0 -- what bench.py times): forward convs on split32 operands (bf16 hi + lo, three
-      kind::f16 MMAs per product), kind::tf32 dgrad / wgrad           scalars 1e-4 (the north-star ELBO / KL bound), gradients 3e-2
+      kind::f16 MMAs per product), bf16 dgrad / wgrad of the blocks     scalars 1e-4 (the north-star ELBO / KL bound), gradients 4e-2
       (CPU study profiles/r02a_split_formats.md: operand rounding alone moves the scalars by 6e-6..1e-5 and the gradients by
       6e-4..6e-3 median / 1e-2 worst; some gradient tensors are ill-conditioned for ANY fp32 implementation, hence the floor of
       3x the fp32 reference's own round-off in compare())
@@ -22,7 +22,8 @@ from tests.step_harness import compare, run_engine_iteration, run_oracle_iterati
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = {1: 2e-5, 0: 1e-4, 3: 1e-4, 4: 2e-3}    # backend id -> scalar tolerance (0 = default: split32 forward, tf32 backward)
-TTOL = {1: 2e-4, 0: 3e-2, 3: 2e-2, 4: 1e-1}   # backend id -> tensor (relative L2) tolerance
+TTOL = {1: 2e-4, 0: 4e-2, 3: 2e-2, 4: 1e-1}   # backend id -> tensor (relative L2) tolerance (backend 0: measured median 4e-4..1e-2,
+                                              # worst 2.7e-2 -- BatchNorm bias gradients = sums over whole tensors -- at config M)
 
 
 def _golden_as_oracle(g, bootstrap=False):
