@@ -1516,21 +1516,31 @@ __device__ __forceinline__ float rs_tf32(float x) {
   return __uint_as_float(u);
 }
 // rev = 1: mirrored column shift, xe[n,h,w,s*c+ch] = x[n,h,w+2-s,ch] (the dP/dy expansion used by the predict wgrad)
+// (all three helpers: the channel quad q of a thread is loop-invariant -- the grid stride is a multiple of 8 -- so the per-channel
+// index arithmetic is hoisted, and pixel indices are 32-bit.  They run at 1.8-2.7 TB/s under ncu, profiles/r02d_prof_rowsep.md;
+// removing the 64-bit `pix % W` of the first version did not change that (r02_cmd20.sh): half of the 32 expanded channels are
+// zero padding and each thread moves 16 bytes per four scalar loads -- the next step is 16-channel rows)
 __global__ void k_rowsep_expand_rev(const float* __restrict__ x, float* __restrict__ xe, long long rows, int W, int c) {
   const long long total = rows * W * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int w = (int)(pix % W);
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int q = (int)(i0 & 7);
+  int so[4], cho[4];
+  bool ok[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = q * 4 + e;
+    so[e] = j / c; cho[e] = j - so[e] * c; ok[e] = j < 5 * c;
+  }
+  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned pix = (unsigned)(i >> 3);
+    const int w = (int)(pix % (unsigned)W);
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int j = q * 4 + e;
-      const int s = j / c, ch = j - s * c;
-      const int ws = w + 2 - s;
-      v[e] = (j < 5 * c && ws >= 0 && ws < W) ? rs_tf32(__ldg(x + (pix + 2 - s) * c + ch)) : 0.f;
+      const int ws = w + 2 - so[e];
+      v[e] = (ok[e] && ws >= 0 && ws < W) ? rs_tf32(__ldg(x + ((long long)pix + 2 - so[e]) * c + cho[e])) : 0.f;
     }
-    *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(xe + (long long)pix * 32 + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 template <bool SPLIT>      // SPLIT: xe in the split32 format (forward operand), unrounded source values
@@ -1538,14 +1548,16 @@ __global__ void k_rowsep_expand(const float* __restrict__ x, float* __restrict__
   // one thread per (pixel, channel quad): 8 threads cover the 32 expanded channels of a pixel
   const long long total = rows * W * 8;
   const int rowlen = W * c;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int w = (int)(pix % W);
-    const long long row = pix / W;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int q = (int)(i0 & 7);
+  const bool active = q * 4 < 5 * c;
+  for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned pix = (unsigned)(i >> 3);
+    const unsigned row = pix / (unsigned)W;
+    const int w = (int)(pix - row * (unsigned)W);
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q * 4 < 5 * c) {
-      const float* src = x + row * rowlen;
+    if (active) {
+      const float* src = x + (long long)row * rowlen;
       const int j0 = (w - 2) * c + q * 4;
       float v[4];
 #pragma unroll
@@ -1555,28 +1567,29 @@ __global__ void k_rowsep_expand(const float* __restrict__ x, float* __restrict__
       }
       o = make_float4(v[0], v[1], v[2], v[3]);
     }
-    if (SPLIT) split32_store4(xe + pix * 32, (uint32_t)q, o);
-    else *reinterpret_cast<float4*>(xe + pix * 32 + q * 4) = o;
+    if (SPLIT) split32_store4(xe + (long long)pix * 32, (uint32_t)q, o);
+    else *reinterpret_cast<float4*>(xe + (long long)pix * 32 + q * 4) = o;
   }
 }
 __global__ void k_rowsep_gather(const float* __restrict__ P, const float* __restrict__ bias, const float* __restrict__ addend,
                                 float* __restrict__ y, long long rows, int W, int c) {
   const long long total = rows * W;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(pix % W);
+  for (long long pl = blockIdx.x * (long long)blockDim.x + threadIdx.x; pl < total; pl += (long long)gridDim.x * blockDim.x) {
+    const unsigned pix = (unsigned)pl;
+    const int w = (int)(pix % (unsigned)W);
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
       const int ws = w + s - 2;
       if (ws < 0 || ws >= W) continue;
-      const float* src = P + (pix + s - 2) * 16 + s * c;
+      const float* src = P + ((long long)pix + s - 2) * 16 + s * c;
       for (int co = 0; co < c; ++co) acc[co] += __ldg(src + co);
     }
     for (int co = 0; co < c; ++co) {
       float v = acc[co];
       if (bias) v += __ldg(bias + co);
-      if (addend) v += addend[pix * c + co];
-      y[pix * c + co] = v;
+      if (addend) v += addend[(long long)pix * c + co];
+      y[(long long)pix * c + co] = v;
     }
   }
 }
