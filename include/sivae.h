@@ -32,8 +32,9 @@ enum { SIVAE_NET_ENCODER = 0, SIVAE_NET_DECODER = 1, SIVAE_NET_TARGET = 2 };
    AUTO (default) = tcgen05 with compensated 16-bit FORWARD operands: activations and filters are stored as bf16 hi + lo
      pairs ("split32": 16 significand bits, fp32 exponent range) and every product of a forward conv is three kind::f16 MMAs
      (lo*hi + hi*lo + hi*hi, fp32 accumulate) = 1.5x the tf32 tensor time; every logged scalar (ELBO / KL / exp-ELBO) stays
-     within 1e-4 of the reference.  dgrad / wgrad run kind::tf32 (their rounding moves the gradients by ~1e-3, below the
-     fp32 reference's own round-off on the same tensors).  Needs every channel count % 32 == 0 and image_size % 16 == 0;
+     within 1e-4 of the reference.  dgrad / wgrad of the residual blocks run kind::f16 on plain bf16 operands (gradients
+     within 4e-3..8e-3 median of the fp64 oracle; SIVAE_BWD16=0: kind::tf32), the image-facing convs (stem, predict) kind::tf32.
+     Needs every channel count % 32 == 0 and image_size % 16 == 0;
      otherwise AUTO degrades to TF32 below;
    SIMT = exact fp32 CUDA-core path with fp64-chunked accumulation (on-device reference);
    TCGEN05 = single-kernel entry points only: plain kind::tf32 tensor-core kernel or error;
@@ -97,7 +98,8 @@ int sivae_params_changed(sivae_engine* e, int net);
 /* Update-E half of the introspective iteration (:551-588): all forwards, the loss and the backward that
    fills the encoder's flat grad buffer.  real: [B,cdim,S,S] NCHW; noise: [B,z] (:547); eps: [3,B,z] the
    reparameterisation draws in the order of :560,:567,:568.  stats (device, 16 floats) receives
-   [0]=loss_rec [1]=lossE_real_kl [2]=expelbo_rec [3]=expelbo_fake [4]=lossE [15]=nan flag. */
+   [0]=loss_rec [1]=lossE_real_kl [2]=expelbo_rec [3]=expelbo_fake [4]=lossE [15]=nan flag
+   [14]=bce domain flag (a reconstruction outside [0, 1], see sivae_set_recon_loss). */
 int sivae_e_step(sivae_engine* e, const float* real_nchw, const float* noise, const float* eps, int batch,
                  const sivae_hyper* hp, float* stats, void* stream);
 /* Update-D half (:591-623); reuses real, noise and z of the preceding sivae_e_step (:597-598).
@@ -112,6 +114,14 @@ int sivae_d_step(sivae_engine* e, const float* eps, const sivae_hyper* hp, float
    the decoder parameters were touched between the two halves. */
 int sivae_set_reuse_decoder_passes(sivae_engine* e, int on);
 int sivae_get_reuse_decoder_passes(const sivae_engine* e);
+/* recon_loss_type kwarg of train_soft_intro_vae (:339) = loss_type of every calc_reconstruction_loss call of the step
+   (:268-294; :563,573,576,599,610,612; VAE warm-up :520).  MSE (default): per-sample sum of squared errors, 'mean' = mean over
+   the batch (:282-287).  L1 / BCE: F.l1_loss / F.binary_cross_entropy on the [B, D] views (:288-291): 'mean' divides by B*D,
+   the 'none' form is summed per sample by the caller (:574-578).  BCE needs reconstructions inside [0, 1] (the reference raises
+   inside F.binary_cross_entropy otherwise): the step then sets stats[14] = 1 and the Python boundary raises RuntimeError. */
+enum { SIVAE_LOSS_MSE = 0, SIVAE_LOSS_L1 = 1, SIVAE_LOSS_BCE = 2 };
+int sivae_set_recon_loss(sivae_engine* e, int loss_type);
+int sivae_get_recon_loss(const sivae_engine* e);
 /* vanilla VAE warm-up step (:512-536): grads of encoder AND decoder. eps: [B,z].
    stats[11]=loss_rec [12]=loss_kl [13]=loss */
 int sivae_vae_step(sivae_engine* e, const float* real_nchw, const float* eps, int batch, const sivae_hyper* hp,

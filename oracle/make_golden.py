@@ -49,7 +49,9 @@ def _import_reference(subdir: str, modname: str):
 
 
 def run_reference_iteration(subdir, modname, fn_name, *, tiny, batch, z_dim, seed, beta_neg, extra_kwargs=None,
-                            data_seed=1234, image_size=32):
+                            data_seed=1234, image_size=32, init_edit=None):
+    """init_edit(model): optional in-place edit of the freshly constructed reference model (recorded as part of `init`);
+    used for recon_loss_type='bce', whose F.binary_cross_entropy needs decoder outputs inside [0, 1] (:291)."""
     ref = _import_reference(subdir, modname)
     rec = {"eps": [], "noise": [], "grads": [], "postfix": None}
 
@@ -73,6 +75,9 @@ def run_reference_iteration(subdir, modname, fn_name, *, tiny, batch, z_dim, see
             channels, image_size = tiny["channels"], tiny["image_size"]
         orig_init(self, cdim=cdim, zdim=zdim, channels=channels, image_size=image_size, **kw)
         holder["model"] = self
+        if init_edit is not None:
+            with torch.no_grad():
+                init_edit(self)
         holder["init"] = {k: v.detach().clone() for k, v in self.state_dict().items()}
         holder["arch"] = dict(cdim=cdim, zdim=zdim, channels=list(channels), image_size=image_size)
 
@@ -155,7 +160,7 @@ def run_reference_iteration(subdir, modname, fn_name, *, tiny, batch, z_dim, see
     out = dict(
         arch=holder["arch"], batch=batch, seed=seed, data_seed=data_seed,
         hyper=dict(beta_kl=1.0, beta_rec=1.0, beta_neg=float(beta_neg), gamma_r=float(kwargs.get("gamma_r", 1e-8 if "bootstrap" not in modname else 1.0)),
-                   scale=1.0 / (3 * 32 ** 2), lr_e=2e-4, lr_d=2e-4),
+                   scale=1.0 / (3 * 32 ** 2), lr_e=2e-4, lr_d=2e-4, loss_type=kwargs.get("recon_loss_type", "mse")),
         real=rec["real"], noise=rec["noise"][0], eps=rec["eps"][:5],
         init=holder["init"], post=post, grads_e=grads_e, grads_d=grads_d,
         scalars=dict(r_loss=rec["postfix"]["r_loss"], kl=rec["postfix"]["kl"], diff_kl=rec["postfix"]["diff_kl"],
@@ -204,12 +209,32 @@ def main():
                                 tiny=None, batch=8, z_dim=128, seed=0, beta_neg=256, image_size=32)
     torch.save(summarise(g), os.path.join(OUT, "cifar_std_summary.pt"))
     print("cifar_std", g["scalars"])
+    extra_losses()
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:16])
 
 
-if __name__ == "__main__" and "--toy" not in sys.argv:
+def _unit_range_decoder(model):
+    """decoder outputs inside (0, 1): small `predict` filters around a bias of 0.5 (for the bce golden)"""
+    model.decoder.main.predict.weight.mul_(0.05)
+    model.decoder.main.predict.bias.fill_(0.5)
+
+
+def extra_losses():
+    """recon_loss_type = 'l1' / 'bce' (:288-291) at the tiny architecture, same seeds as tiny_std"""
+    tiny = dict(channels=[32, 64], image_size=16)
+    for lt, edit in (("l1", None), ("bce", _unit_range_decoder)):
+        g = run_reference_iteration("soft_intro_vae", "train_soft_intro_vae", "train_soft_intro_vae",
+                                    tiny=tiny, batch=8, z_dim=16, seed=0, beta_neg=256, image_size=16,
+                                    extra_kwargs=dict(recon_loss_type=lt), init_edit=edit)
+        torch.save(g, os.path.join(OUT, "tiny_%s.pt" % lt))
+        print("tiny_" + lt, g["scalars"])
+
+
+if __name__ == "__main__" and "--losses" in sys.argv:
+    extra_losses()
+elif __name__ == "__main__" and "--toy" not in sys.argv:
     main()
 
 

@@ -162,13 +162,28 @@ def reparameterize(mu: Tensor, logvar: Tensor, eps: Tensor) -> Tensor:
     return mu + eps * torch.exp(0.5 * logvar)
 
 
-def rec_loss(x: Tensor, recon_x: Tensor, reduction: str) -> Tensor:
-    """calc_reconstruction_loss(loss_type='mse'), :268-287.  Arg order is (x, recon_x)."""
-    err = (recon_x.reshape(recon_x.size(0), -1) - x.reshape(x.size(0), -1)).pow(2).sum(1)
-    if reduction == "sum":
-        err = err.sum()
-    elif reduction == "mean":
-        err = err.mean()
+def rec_loss(x: Tensor, recon_x: Tensor, reduction: str, loss_type: str = "mse") -> Tensor:
+    """calc_reconstruction_loss, :268-294.  Arg order is (x, recon_x).  'mse' sums the squared error per sample BEFORE the
+    batch reduction (:282-287); 'l1' / 'bce' hand `reduction` straight to F.l1_loss / F.binary_cross_entropy on the
+    [B, D] views (:288-291), so 'mean' divides by B*D and 'none' is element-wise -- the callers of the 'none' form then
+    sum the trailing dimensions away (`while len(shape) > 1: sum(-1)`, :574-578), which is folded in here."""
+    b = recon_x.size(0)
+    r, t = recon_x.reshape(b, -1), x.reshape(b, -1)
+    if loss_type == "mse":
+        err = (r - t).pow(2).sum(1)
+        if reduction == "sum":
+            err = err.sum()
+        elif reduction == "mean":
+            err = err.mean()
+        return err
+    if loss_type == "l1":
+        err = F.l1_loss(r, t, reduction=reduction)
+    elif loss_type == "bce":
+        err = F.binary_cross_entropy(r, t, reduction=reduction)
+    else:
+        raise NotImplementedError
+    while err.dim() > 1:
+        err = err.sum(-1)
     return err
 
 
@@ -187,6 +202,7 @@ class Hyper:
     adam_b1: float = 0.9
     adam_b2: float = 0.999
     adam_eps: float = 1e-8
+    loss_type: str = "mse"                  # recon_loss_type kwarg, :339
 
 
 def _set_grad(sd, keys, flag: bool):
@@ -211,7 +227,7 @@ def e_step(sd, arch: Arch, real: Tensor, noise: Tensor, eps: Sequence[Tensor], h
     real_mu, real_logvar = encoder_forward(sd, arch, real)                    # :559
     z = reparameterize(real_mu, real_logvar, eps[0])                          # :560
     rec = decoder_forward(sd, arch, z)                                        # :561
-    loss_rec = rec_loss(real, rec, "mean")                                    # :563
+    loss_rec = rec_loss(real, rec, "mean", hp.loss_type)                                    # :563
     lossE_real_kl = calc_kl(real_logvar, real_mu, "mean")                     # :565
     rec_mu, rec_logvar = encoder_forward(sd, arch, rec.detach())              # :567
     z_rec = reparameterize(rec_mu, rec_logvar, eps[1])
@@ -221,8 +237,8 @@ def e_step(sd, arch: Arch, real: Tensor, noise: Tensor, eps: Sequence[Tensor], h
     rec_fake = decoder_forward(sd, arch, z_fake, prefix=tgt)
     kl_rec = calc_kl(rec_logvar, rec_mu, "none")                              # :570
     kl_fake = calc_kl(fake_logvar, fake_mu, "none")                           # :571
-    l_rr = rec_loss(rec, rec_rec, "none")          # :573 -- `rec` NOT detached (graph fidelity)
-    l_rf = rec_loss(fake, rec_fake, "none")                                   # :576
+    l_rr = rec_loss(rec, rec_rec, "none", hp.loss_type)          # :573 -- `rec` NOT detached (graph fidelity)
+    l_rf = rec_loss(fake, rec_fake, "none", hp.loss_type)                                   # :576
     expelbo_rec = (-2 * hp.scale * (hp.beta_rec * l_rr + hp.beta_neg * kl_rec)).exp().mean()    # :580
     expelbo_fake = (-2 * hp.scale * (hp.beta_rec * l_rf + hp.beta_neg * kl_fake)).exp().mean()  # :581
     lossE_fake = 0.25 * (expelbo_rec + expelbo_fake)                          # :583
@@ -252,7 +268,7 @@ def d_step(sd, arch: Arch, real: Tensor, noise: Tensor, z: Tensor, eps: Sequence
 
     fake = decoder_forward(sd, arch, noise)                                   # :597
     rec = decoder_forward(sd, arch, z.detach())                               # :598
-    loss_rec = rec_loss(real, rec, "mean")                                    # :599
+    loss_rec = rec_loss(real, rec, "mean", hp.loss_type)                                    # :599
     rec_mu, rec_logvar = encoder_forward(sd, arch, rec)                       # :601
     z_rec = reparameterize(rec_mu, rec_logvar, eps[0])
     fake_mu, fake_logvar = encoder_forward(sd, arch, fake)                    # :604
@@ -260,13 +276,13 @@ def d_step(sd, arch: Arch, real: Tensor, noise: Tensor, z: Tensor, eps: Sequence
     if bootstrap:
         rec_rec = decoder_forward(sd, arch, z_rec, prefix="target_decoder")   # bootstrap :635
         rec_fake = decoder_forward(sd, arch, z_fake, prefix="target_decoder")
-        loss_rec_rec = rec_loss(rec, rec_rec, "mean")                         # bootstrap :638
-        loss_fake_rec = rec_loss(fake, rec_fake, "mean")
+        loss_rec_rec = rec_loss(rec, rec_rec, "mean", hp.loss_type)                         # bootstrap :638
+        loss_fake_rec = rec_loss(fake, rec_fake, "mean", hp.loss_type)
     else:
         rec_rec = decoder_forward(sd, arch, z_rec.detach())                   # :607
         rec_fake = decoder_forward(sd, arch, z_fake.detach())                 # :608
-        loss_rec_rec = rec_loss(rec.detach(), rec_rec, "mean")                # :610
-        loss_fake_rec = rec_loss(fake.detach(), rec_fake, "mean")             # :612
+        loss_rec_rec = rec_loss(rec.detach(), rec_rec, "mean", hp.loss_type)                # :610
+        loss_fake_rec = rec_loss(fake.detach(), rec_fake, "mean", hp.loss_type)             # :612
     lossD_rec_kl = calc_kl(rec_logvar, rec_mu, "mean")                        # :615
     lossD_fake_kl = calc_kl(fake_logvar, fake_mu, "mean")                     # :616
     lossD = hp.scale * (loss_rec * hp.beta_rec + (lossD_rec_kl + lossD_fake_kl) * 0.5 * hp.beta_kl
@@ -292,7 +308,7 @@ def vae_step(sd, arch: Arch, real: Tensor, eps: Tensor, hp: Hyper, bootstrap: bo
     mu, logvar = encoder_forward(sd, arch, real)
     z = reparameterize(mu, logvar, eps)
     rec = decoder_forward(sd, arch, z, prefix="target_decoder" if bootstrap else "decoder")
-    loss_rec = rec_loss(real, rec, "mean")
+    loss_rec = rec_loss(real, rec, "mean", hp.loss_type)
     loss_kl = calc_kl(logvar, mu, "mean")
     loss = hp.beta_rec * loss_rec + hp.beta_kl * loss_kl
     loss.backward()

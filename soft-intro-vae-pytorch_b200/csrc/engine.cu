@@ -127,6 +127,10 @@ struct sivae_engine {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool dp_overlap = true;
   bool reuse_dec = false;          // D half re-uses the E half's fake / rec decoder passes (SIVAE_REUSE_DEC=1 or sivae_set_option)
   bool e_dec_valid = false;        // dp[0] / dp[1] hold D(noise) / D(z) of the current decoder weights
+  int loss_type = SIVAE_LOSS_MSE_; // recon_loss_type of the step (sivae_set_recon_loss): mse | l1 | bce (:268-294)
+  // the 'mean' reduction of the l1 / bce branches divides by B*D, the mse branch by B (:282-291)
+  float mean_div() const { return loss_type == SIVAE_LOSS_MSE_ ? 1.f : 1.f / (float)((long long)cfg.cdim * cfg.image_size * cfg.image_size); }
+  int* bad_flag() const { return loss_type == SIVAE_LOSS_BCE_ ? reinterpret_cast<int*>(coef + 3 * (long long)cfg.max_batch) : nullptr; }
 };
 
 // -------------------------------------------------------------------------------------------------------------
@@ -1055,12 +1059,14 @@ extern "C" int sivae_e_step(sivae_engine* e, const float* real_nchw, const float
   launch_kl_reparam(E3.ml, eps3, E3.z, E3.kl, B, z, st);
   TRY(dec_forward(e, tn, D4, E3.z, B, true, false, st));              // rec_fake
   // losses :563-586
-  { ProfLoss pl(B, per, st); launch_mse3(e->real, D2.y, D3.y, D1.y, D4.y, e->mse, B, per, e->red, e->red_bytes, st); }
+  const int lt = e->loss_type;
+  const float md = e->mean_div();
+  { ProfLoss pl(B, per, st); launch_mse3(e->real, D2.y, D3.y, D1.y, D4.y, e->mse, B, per, e->red, e->red_bytes, st, lt, e->bad_flag()); }
   launch_e_loss_finalize(e->mse, E1.kl, E2.kl, E3.kl, B, hp->beta_kl, hp->beta_rec, hp->beta_neg, hp->scale, stats,
-                         e->coef, e->ckl_a, e->ckl_b, st);
-  const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
+                         e->coef, e->ckl_a, e->ckl_b, st, md, e->bad_flag());
+  const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B * md;
   launch_loss_seed(e->real, D2.y, D3.y, D1.y, D4.y, a_rec, e->coef + B, 0.f, e->coef + 2 * B, 0.f, /*rec not detached :573*/ true,
-                   e->d_rec, e->d_rec_rec, e->d_rec_fake, nullptr, B, per, st);
+                   e->d_rec, e->d_rec_rec, e->d_rec_fake, nullptr, B, per, st, lt);
   // backward :587-588 -- only the encoder accumulates parameter grads; decoders are dgrad-only
   cudaMemsetAsync(en.grads, 0, sizeof(float) * en.n_params, st);
   TRY(dec_backward(e, tn, D3, e->d_rec_rec, false, e->dz, B, st));
@@ -1127,14 +1133,16 @@ static int d_step_impl(sivae_engine* e, const float* eps, const sivae_hyper* hp,
   launch_kl_reparam(E5.ml, eps5, E5.z, E5.kl, B, z, st);
   TRY(dec_forward(e, tn, D7, E4.z, B, true, !boot, st));              // rec_rec :607 (bootstrap: frozen target decoder)
   TRY(dec_forward(e, tn, D8, E5.z, B, true, !boot, st));              // rec_fake :608
-  { ProfLoss pl(B, per, st); launch_mse3(e->real, D6.y, D7.y, D5.y, D8.y, e->mse, B, per, e->red, e->red_bytes, st); }
-  launch_d_loss_finalize(e->mse, E4.kl, E5.kl, B, hp->beta_kl, hp->beta_rec, hp->gamma_r, hp->scale, stats, st);
-  const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B;
-  const float a_t = hp->scale * hp->gamma_r * hp->beta_rec / (float)B;     // 2 * (scale * gamma_r/2 * beta_rec / B)
+  const int lt = e->loss_type;
+  const float md = e->mean_div();
+  { ProfLoss pl(B, per, st); launch_mse3(e->real, D6.y, D7.y, D5.y, D8.y, e->mse, B, per, e->red, e->red_bytes, st, lt, e->bad_flag()); }
+  launch_d_loss_finalize(e->mse, E4.kl, E5.kl, B, hp->beta_kl, hp->beta_rec, hp->gamma_r, hp->scale, stats, st, md, e->bad_flag());
+  const float a_rec = 2.f * hp->scale * hp->beta_rec / (float)B * md;
+  const float a_t = hp->scale * hp->gamma_r * hp->beta_rec / (float)B * md;     // 2 * (scale * gamma_r/2 * beta_rec / B)
   const float ckl = hp->scale * 0.5f * hp->beta_kl / (float)B;
   // standard: targets detached (:610-613); bootstrap: nothing detached (bootstrap :635-641)
   launch_loss_seed(e->real, D6.y, D7.y, D5.y, D8.y, a_rec, nullptr, a_t, nullptr, a_t, boot, e->d_rec, e->d_rec_rec,
-                   e->d_rec_fake, boot ? e->d_fake : nullptr, B, per, st);
+                   e->d_rec_fake, boot ? e->d_fake : nullptr, B, per, st, lt);
   cudaMemsetAsync(dn.grads, 0, sizeof(float) * dn.n_params, st);
   if (!boot) {
     TRY(dec_backward(e, dn, D7, e->d_rec_rec, true, nullptr, B, st));
@@ -1178,10 +1186,10 @@ extern "C" int sivae_vae_step(sivae_engine* e, const float* real_nchw, const flo
   TRY(enc_forward(e, en, E1, e->real, B, true, true, st));            // model(real_batch) :518
   launch_kl_reparam(E1.ml, eps, E1.z, E1.kl, B, z, st);
   TRY(dec_forward(e, dn, D1, E1.z, B, true, !boot, st));
-  launch_mse3(e->real, D1.y, nullptr, nullptr, nullptr, e->mse, B, per, e->red, e->red_bytes, st);
-  launch_vae_loss_finalize(e->mse, E1.kl, B, hp->beta_kl, hp->beta_rec, stats, st);
-  launch_loss_seed(e->real, D1.y, nullptr, nullptr, nullptr, 2.f * hp->beta_rec / (float)B, nullptr, 0.f, nullptr, 0.f, false,
-                   e->d_rec, nullptr, nullptr, nullptr, B, per, st);
+  launch_mse3(e->real, D1.y, nullptr, nullptr, nullptr, e->mse, B, per, e->red, e->red_bytes, st, e->loss_type, e->bad_flag());
+  launch_vae_loss_finalize(e->mse, E1.kl, B, hp->beta_kl, hp->beta_rec, stats, st, e->mean_div(), e->bad_flag());
+  launch_loss_seed(e->real, D1.y, nullptr, nullptr, nullptr, 2.f * hp->beta_rec / (float)B * e->mean_div(), nullptr, 0.f, nullptr, 0.f, false,
+                   e->d_rec, nullptr, nullptr, nullptr, B, per, st, e->loss_type);
   cudaMemsetAsync(en.grads, 0, sizeof(float) * en.n_params, st);
   if (!boot) cudaMemsetAsync(dn.grads, 0, sizeof(float) * dn.n_params, st);
   TRY(dec_backward(e, dn, D1, e->d_rec, !boot, e->dz, B, st));
@@ -1199,6 +1207,14 @@ extern "C" int sivae_set_reuse_decoder_passes(sivae_engine* e, int on) {
   return 0;
 }
 extern "C" int sivae_get_reuse_decoder_passes(const sivae_engine* e) { return e ? (e->reuse_dec ? 1 : 0) : -1; }
+// recon_loss_type kwarg of train_soft_intro_vae (:339) -> calc_reconstruction_loss(loss_type=...) at :563,573,576,599,610,612
+extern "C" int sivae_set_recon_loss(sivae_engine* e, int loss_type) {
+  if (!e) return fail(-1, "null engine");
+  if (loss_type < SIVAE_LOSS_MSE_ || loss_type > SIVAE_LOSS_BCE_) return fail(-2, "recon loss type must be SIVAE_LOSS_MSE / _L1 / _BCE");
+  e->loss_type = loss_type;
+  return 0;
+}
+extern "C" int sivae_get_recon_loss(const sivae_engine* e) { return e ? e->loss_type : -1; }
 
 extern "C" int sivae_adam_step(sivae_engine* e, int net, float lr, float grad_scale, void* stream) {
   Net* n = get_net(e, net);

@@ -1283,31 +1283,58 @@ __device__ __forceinline__ float sq4(float4 a, float4 b) {
   float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
   return fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
 }
+// per-element reconstruction error f(x = target, r = reconstruction) of calc_reconstruction_loss (:268-294) for the loss
+// types that go through F.l1_loss / F.binary_cross_entropy (:288-291).  bce: ATen's kernel, (x - 1) max(log1p(-r), -100)
+// - x max(log r, -100); a reconstruction outside [0, 1] is an error there (RuntimeError on CPU, device assert on CUDA): flagged.
+template <int LT> __device__ __forceinline__ float rec_elem(float x, float r, int& bad) {
+  if (LT == SIVAE_LOSS_L1_) return fabsf(r - x);
+  if (!(r >= 0.f && r <= 1.f)) bad = 1;
+  return (x - 1.f) * fmaxf(log1pf(-r), -100.f) - x * fmaxf(logf(r), -100.f);
+}
+template <int LT> __device__ __forceinline__ float rec_elem4(float4 x, float4 r, int& bad) {
+  return (rec_elem<LT>(x.x, r.x, bad) + rec_elem<LT>(x.y, r.y, bad)) + (rec_elem<LT>(x.z, r.z, bad) + rec_elem<LT>(x.w, r.w, bad));
+}
+// LT = SIVAE_LOSS_MSE_: the squared error (the only type the reference's CLI passes); _L1_ / _BCE_: see rec_elem
+template <int LT>
 __global__ void __launch_bounds__(256) k_mse3_partial(const float* __restrict__ real, const float* __restrict__ rec,
                                                       const float* __restrict__ rec_rec, const float* __restrict__ fake,
                                                       const float* __restrict__ rec_fake, float* __restrict__ part,
-                                                      long long per_sample, int nblk) {
+                                                      long long per_sample, int nblk, int* __restrict__ bad_flag) {
   const int b = blockIdx.y;
   const long long base = (long long)b * per_sample;
   const long long e0 = (long long)blockIdx.x * MSE_CHUNK;
   const long long e1 = min(per_sample, e0 + MSE_CHUNK);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  int bad = 0;
   const bool vec = ((per_sample & 3) == 0);
   if (vec) {
     for (long long e = e0 + 4 * threadIdx.x; e < e1; e += 4 * 256) {
       float4 r = __ldg(reinterpret_cast<const float4*>(rec + base + e));
-      if (real) s0 += sq4(r, __ldg(reinterpret_cast<const float4*>(real + base + e)));
-      if (rec_rec) s1 += sq4(__ldg(reinterpret_cast<const float4*>(rec_rec + base + e)), r);
-      if (fake) s2 += sq4(__ldg(reinterpret_cast<const float4*>(rec_fake + base + e)), __ldg(reinterpret_cast<const float4*>(fake + base + e)));
+      if (LT == SIVAE_LOSS_MSE_) {
+        if (real) s0 += sq4(r, __ldg(reinterpret_cast<const float4*>(real + base + e)));
+        if (rec_rec) s1 += sq4(__ldg(reinterpret_cast<const float4*>(rec_rec + base + e)), r);
+        if (fake) s2 += sq4(__ldg(reinterpret_cast<const float4*>(rec_fake + base + e)), __ldg(reinterpret_cast<const float4*>(fake + base + e)));
+      } else {      // (target, reconstruction) pairs of :563/:599, :573/:610, :576/:612
+        if (real) s0 += rec_elem4<LT>(__ldg(reinterpret_cast<const float4*>(real + base + e)), r, bad);
+        if (rec_rec) s1 += rec_elem4<LT>(r, __ldg(reinterpret_cast<const float4*>(rec_rec + base + e)), bad);
+        if (fake) s2 += rec_elem4<LT>(__ldg(reinterpret_cast<const float4*>(fake + base + e)), __ldg(reinterpret_cast<const float4*>(rec_fake + base + e)), bad);
+      }
     }
   } else {
     for (long long e = e0 + threadIdx.x; e < e1; e += 256) {
       float r = rec[base + e];
-      if (real) { float d = r - real[base + e]; s0 = fmaf(d, d, s0); }
-      if (rec_rec) { float d = rec_rec[base + e] - r; s1 = fmaf(d, d, s1); }
-      if (fake) { float d = rec_fake[base + e] - fake[base + e]; s2 = fmaf(d, d, s2); }
+      if (LT == SIVAE_LOSS_MSE_) {
+        if (real) { float d = r - real[base + e]; s0 = fmaf(d, d, s0); }
+        if (rec_rec) { float d = rec_rec[base + e] - r; s1 = fmaf(d, d, s1); }
+        if (fake) { float d = rec_fake[base + e] - fake[base + e]; s2 = fmaf(d, d, s2); }
+      } else {
+        if (real) s0 += rec_elem<LT>(real[base + e], r, bad);
+        if (rec_rec) s1 += rec_elem<LT>(r, rec_rec[base + e], bad);
+        if (fake) s2 += rec_elem<LT>(fake[base + e], rec_fake[base + e], bad);
+      }
     }
   }
+  if (LT == SIVAE_LOSS_BCE_ && bad && bad_flag) *bad_flag = 1;      // every writer stores the same value
   __shared__ float red[8][3];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1333,13 +1360,21 @@ __global__ void k_mse3_final(const float* __restrict__ part, float* __restrict__
   for (int k = 0; k < nblk; ++k) s += (double)part[((long long)b * nblk + k) * 3 + j];
   out[i] = (float)s;
 }
+// loss_type: SIVAE_LOSS_* (kernels.h); bad_flag (bce only, nullable): device int set to 1 if a reconstruction lies outside [0, 1]
 void launch_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
-                 float* out, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                 float* out, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st, int loss_type,
+                 int* bad_flag) {
   g_launches += 2;
   int nblk = mse_blocks_per_sample(per_sample);
   float* part = (float*)scratch;
   dim3 grid(nblk, B);
-  k_mse3_partial<<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, part, per_sample, nblk);
+  if (loss_type == SIVAE_LOSS_L1_)
+    k_mse3_partial<SIVAE_LOSS_L1_><<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, part, per_sample, nblk, nullptr);
+  else if (loss_type == SIVAE_LOSS_BCE_) {
+    if (bad_flag) cudaMemsetAsync(bad_flag, 0, sizeof(int), st);
+    k_mse3_partial<SIVAE_LOSS_BCE_><<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, part, per_sample, nblk, bad_flag);
+  } else
+    k_mse3_partial<SIVAE_LOSS_MSE_><<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, part, per_sample, nblk, nullptr);
   k_mse3_final<<<cdiv(B * 3, 128), 128, 0, st>>>(part, out, B, nblk);
 }
 
@@ -1405,7 +1440,8 @@ __device__ float block_sum_256(float v, float* sh) {
 __global__ void __launch_bounds__(256) k_e_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl_real,
                                                          const float* __restrict__ kl_rec, const float* __restrict__ kl_fake,
                                                          int B, float beta_kl, float beta_rec, float beta_neg, float scale,
-                                                         float* stats, float* coef, float* ckl_rec, float* ckl_fake) {
+                                                         float* stats, float* coef, float* ckl_rec, float* ckl_fake,
+                                                         float md, const int* __restrict__ bad) {
   __shared__ float sh[8];
   float s_r = 0.f, s_k = 0.f, s_er = 0.f, s_ef = 0.f;
   const float invB = 1.f / (float)B;
@@ -1422,7 +1458,8 @@ __global__ void __launch_bounds__(256) k_e_loss_finalize(const float* __restrict
     ckl_rec[b] = 0.25f * invB * er * (-2.f * scale * beta_neg);
     ckl_fake[b] = 0.25f * invB * ef * (-2.f * scale * beta_neg);
   }
-  float loss_rec = block_sum_256(s_r, sh) * invB;
+  // md: 1 for mse (mean over the batch of per-sample sums, :282-287); 1/D for l1 / bce (F.*_loss(reduction='mean'), :288-291)
+  float loss_rec = block_sum_256(s_r, sh) * invB * md;
   float kl = block_sum_256(s_k, sh) * invB;
   float e_rec = block_sum_256(s_er, sh) * invB;
   float e_fake = block_sum_256(s_ef, sh) * invB;
@@ -1430,54 +1467,82 @@ __global__ void __launch_bounds__(256) k_e_loss_finalize(const float* __restrict
     float lossE = scale * (beta_rec * loss_rec + beta_kl * kl) + 0.25f * (e_rec + e_fake);
     stats[0] = loss_rec; stats[1] = kl; stats[2] = e_rec; stats[3] = e_fake; stats[4] = lossE;
     stats[15] = (lossE != lossE) ? 1.f : 0.f;
+    stats[14] = (bad && *bad) ? 1.f : 0.f;       // bce: reconstruction outside [0, 1]
   }
 }
 void launch_e_loss_finalize(const float* mse, const float* kl_real, const float* kl_rec, const float* kl_fake, int B,
                             float beta_kl, float beta_rec, float beta_neg, float scale, float* stats, float* coef,
-                            float* ckl_rec, float* ckl_fake, cudaStream_t st) {
+                            float* ckl_rec, float* ckl_fake, cudaStream_t st, float mean_div, const int* bad_flag) {
   g_launches += 1;
-  k_e_loss_finalize<<<1, 256, 0, st>>>(mse, kl_real, kl_rec, kl_fake, B, beta_kl, beta_rec, beta_neg, scale, stats, coef, ckl_rec, ckl_fake);
+  k_e_loss_finalize<<<1, 256, 0, st>>>(mse, kl_real, kl_rec, kl_fake, B, beta_kl, beta_rec, beta_neg, scale, stats, coef, ckl_rec, ckl_fake,
+                                       mean_div, bad_flag);
 }
 __global__ void __launch_bounds__(256) k_d_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl_rec,
                                                          const float* __restrict__ kl_fake, int B, float beta_kl,
-                                                         float beta_rec, float gamma_r, float scale, float* stats) {
+                                                         float beta_rec, float gamma_r, float scale, float* stats,
+                                                         float md, const int* __restrict__ bad) {
   __shared__ float sh[8];
   float s_r = 0.f, s_rr = 0.f, s_rf = 0.f, s_kr = 0.f, s_kf = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) {
     s_r += mse[b * 3]; s_rr += mse[b * 3 + 1]; s_rf += mse[b * 3 + 2]; s_kr += kl_rec[b]; s_kf += kl_fake[b];
   }
   const float invB = 1.f / (float)B;
-  float loss_rec = block_sum_256(s_r, sh) * invB, lrr = block_sum_256(s_rr, sh) * invB, lrf = block_sum_256(s_rf, sh) * invB;
+  float loss_rec = block_sum_256(s_r, sh) * invB * md, lrr = block_sum_256(s_rr, sh) * invB * md, lrf = block_sum_256(s_rf, sh) * invB * md;
   float kr = block_sum_256(s_kr, sh) * invB, kf = block_sum_256(s_kf, sh) * invB;
   if (threadIdx.x == 0) {
     float lossD = scale * (loss_rec * beta_rec + (kr + kf) * 0.5f * beta_kl + gamma_r * 0.5f * beta_rec * (lrr + lrf));
     stats[5] = loss_rec; stats[6] = kr; stats[7] = kf; stats[8] = lrr; stats[9] = lrf; stats[10] = lossD;
     if (lossD != lossD) stats[15] = 1.f;
+    if (bad && *bad) stats[14] = 1.f;
   }
 }
 void launch_d_loss_finalize(const float* mse, const float* kl_rec, const float* kl_fake, int B, float beta_kl,
-                            float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st) {
+                            float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st, float mean_div,
+                            const int* bad_flag) {
   g_launches += 1;
-  k_d_loss_finalize<<<1, 256, 0, st>>>(mse, kl_rec, kl_fake, B, beta_kl, beta_rec, gamma_r, scale, stats);
+  k_d_loss_finalize<<<1, 256, 0, st>>>(mse, kl_rec, kl_fake, B, beta_kl, beta_rec, gamma_r, scale, stats, mean_div, bad_flag);
 }
 __global__ void __launch_bounds__(256) k_vae_loss_finalize(const float* __restrict__ mse, const float* __restrict__ kl,
-                                                           int B, float beta_kl, float beta_rec, float* stats) {
+                                                           int B, float beta_kl, float beta_rec, float* stats, float md,
+                                                           const int* __restrict__ bad) {
   __shared__ float sh[8];
   float s_r = 0.f, s_k = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) { s_r += mse[b * 3]; s_k += kl[b]; }
   const float invB = 1.f / (float)B;
-  float lr = block_sum_256(s_r, sh) * invB, lk = block_sum_256(s_k, sh) * invB;
+  float lr = block_sum_256(s_r, sh) * invB * md, lk = block_sum_256(s_k, sh) * invB;
   if (threadIdx.x == 0) {
     float loss = beta_rec * lr + beta_kl * lk;
     stats[11] = lr; stats[12] = lk; stats[13] = loss;
     stats[15] = (loss != loss) ? 1.f : 0.f;
+    stats[14] = (bad && *bad) ? 1.f : 0.f;
   }
 }
-void launch_vae_loss_finalize(const float* mse, const float* kl, int B, float beta_kl, float beta_rec, float* stats, cudaStream_t st) {
+void launch_vae_loss_finalize(const float* mse, const float* kl, int B, float beta_kl, float beta_rec, float* stats, cudaStream_t st,
+                              float mean_div, const int* bad_flag) {
   g_launches += 1;
-  k_vae_loss_finalize<<<1, 256, 0, st>>>(mse, kl, B, beta_kl, beta_rec, stats);
+  k_vae_loss_finalize<<<1, 256, 0, st>>>(mse, kl, B, beta_kl, beta_rec, stats, mean_div, bad_flag);
 }
 
+// Half the derivatives of the per-element reconstruction error f(x = target, r = reconstruction) -- "half" because the
+// coefficients a_* carry the factor 2 of d(r - x)^2 / dr (mse: g = r - x, gx = -g; both exact scalings):
+//   l1  (F.l1_loss backward = sign):                g = sign(r - x) / 2,                      gx = -g
+//   bce (ATen binary_cross_entropy_backward):       g = (r - x) / max((1 - r) r, 1e-12) / 2,  gx = -logit(r) / 2 (target grad)
+template <int LT> __device__ __forceinline__ float rec_g(float x, float r) {
+  if (LT == SIVAE_LOSS_L1_) { float d = r - x; return d > 0.f ? 0.5f : (d < 0.f ? -0.5f : 0.f); }
+  if (LT == SIVAE_LOSS_BCE_) return 0.5f * (r - x) / fmaxf((1.f - r) * r, 1e-12f);
+  return r - x;
+}
+template <int LT> __device__ __forceinline__ float rec_gx(float x, float r) {
+  if (LT == SIVAE_LOSS_BCE_) return 0.5f * (log1pf(-r) - logf(r));
+  return -rec_g<LT>(x, r);
+}
+template <int LT> __device__ __forceinline__ float4 rec_g4(float a, float4 x, float4 r) {
+  return make_float4(a * rec_g<LT>(x.x, r.x), a * rec_g<LT>(x.y, r.y), a * rec_g<LT>(x.z, r.z), a * rec_g<LT>(x.w, r.w));
+}
+template <int LT> __device__ __forceinline__ float4 rec_gx4(float a, float4 x, float4 r) {
+  return make_float4(a * rec_gx<LT>(x.x, r.x), a * rec_gx<LT>(x.y, r.y), a * rec_gx<LT>(x.z, r.z), a * rec_gx<LT>(x.w, r.w));
+}
+template <int LT>
 __global__ void __launch_bounds__(256) k_loss_seed(const float* __restrict__ real, const float* __restrict__ rec,
                                                    const float* __restrict__ rec_rec, const float* __restrict__ fake,
                                                    const float* __restrict__ rec_fake, float a_rec,
@@ -1493,32 +1558,55 @@ __global__ void __launch_bounds__(256) k_loss_seed(const float* __restrict__ rea
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample4; i += (long long)gridDim.x * blockDim.x) {
     float4 r = __ldg(reinterpret_cast<const float4*>(rec) + base + i);
     float4 x = __ldg(reinterpret_cast<const float4*>(real) + base + i);
-    float4 o = make_float4(a_rec * (r.x - x.x), a_rec * (r.y - x.y), a_rec * (r.z - x.z), a_rec * (r.w - x.w));
-    if (rec_rec) {
-      float4 q = __ldg(reinterpret_cast<const float4*>(rec_rec) + base + i);
-      float4 d = make_float4(a_t * (q.x - r.x), a_t * (q.y - r.y), a_t * (q.z - r.z), a_t * (q.w - r.w));
-      if (d_rec_rec) reinterpret_cast<float4*>(d_rec_rec)[base + i] = d;
-      if (tgt_rec) { o.x -= d.x; o.y -= d.y; o.z -= d.z; o.w -= d.w; }
-    }
-    if (d_rec) reinterpret_cast<float4*>(d_rec)[base + i] = o;
-    if (fake) {
-      float4 f = __ldg(reinterpret_cast<const float4*>(fake) + base + i);
-      float4 q = __ldg(reinterpret_cast<const float4*>(rec_fake) + base + i);
-      float4 d = make_float4(a_f * (q.x - f.x), a_f * (q.y - f.y), a_f * (q.z - f.z), a_f * (q.w - f.w));
-      if (d_rec_fake) reinterpret_cast<float4*>(d_rec_fake)[base + i] = d;
-      if (d_fake) reinterpret_cast<float4*>(d_fake)[base + i] = make_float4(-d.x, -d.y, -d.z, -d.w);
+    if (LT == SIVAE_LOSS_MSE_) {
+      float4 o = make_float4(a_rec * (r.x - x.x), a_rec * (r.y - x.y), a_rec * (r.z - x.z), a_rec * (r.w - x.w));
+      if (rec_rec) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(rec_rec) + base + i);
+        float4 d = make_float4(a_t * (q.x - r.x), a_t * (q.y - r.y), a_t * (q.z - r.z), a_t * (q.w - r.w));
+        if (d_rec_rec) reinterpret_cast<float4*>(d_rec_rec)[base + i] = d;
+        if (tgt_rec) { o.x -= d.x; o.y -= d.y; o.z -= d.z; o.w -= d.w; }
+      }
+      if (d_rec) reinterpret_cast<float4*>(d_rec)[base + i] = o;
+      if (fake) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(fake) + base + i);
+        float4 q = __ldg(reinterpret_cast<const float4*>(rec_fake) + base + i);
+        float4 d = make_float4(a_f * (q.x - f.x), a_f * (q.y - f.y), a_f * (q.z - f.z), a_f * (q.w - f.w));
+        if (d_rec_fake) reinterpret_cast<float4*>(d_rec_fake)[base + i] = d;
+        if (d_fake) reinterpret_cast<float4*>(d_fake)[base + i] = make_float4(-d.x, -d.y, -d.z, -d.w);
+      }
+    } else {
+      float4 o = rec_g4<LT>(a_rec, x, r);                            // d / d rec of f(real, rec)
+      if (rec_rec) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(rec_rec) + base + i);
+        if (d_rec_rec) reinterpret_cast<float4*>(d_rec_rec)[base + i] = rec_g4<LT>(a_t, r, q);     // f(rec, rec_rec) w.r.t. rec_rec
+        if (tgt_rec) { float4 t = rec_gx4<LT>(a_t, r, q); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }   // ... w.r.t. its target rec
+      }
+      if (d_rec) reinterpret_cast<float4*>(d_rec)[base + i] = o;
+      if (fake) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(fake) + base + i);
+        float4 q = __ldg(reinterpret_cast<const float4*>(rec_fake) + base + i);
+        if (d_rec_fake) reinterpret_cast<float4*>(d_rec_fake)[base + i] = rec_g4<LT>(a_f, f, q);
+        if (d_fake) reinterpret_cast<float4*>(d_fake)[base + i] = rec_gx4<LT>(a_f, f, q);
+      }
     }
   }
 }
 void launch_loss_seed(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
                       float a_rec, const float* a_t_arr, float a_t, const float* a_f_arr, float a_f, bool target_grad_rec,
                       float* d_rec, float* d_rec_rec, float* d_rec_fake, float* d_fake, int B, long long per_sample,
-                      cudaStream_t st) {
+                      cudaStream_t st, int loss_type) {
   g_launches += 1;
   long long ps4 = per_sample / 4;   // per_sample = cdim*S*S with even S: multiple of 4
   dim3 grid(min(cdiv(ps4, 256), 148u * 4), B);
-  k_loss_seed<<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, a_rec, a_t_arr, a_t, a_f_arr, a_f,
-                                    target_grad_rec ? 1 : 0, d_rec, d_rec_rec, d_rec_fake, d_fake, ps4);
+  if (loss_type == SIVAE_LOSS_L1_)
+    k_loss_seed<SIVAE_LOSS_L1_><<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, a_rec, a_t_arr, a_t, a_f_arr, a_f,
+                                                      target_grad_rec ? 1 : 0, d_rec, d_rec_rec, d_rec_fake, d_fake, ps4);
+  else if (loss_type == SIVAE_LOSS_BCE_)
+    k_loss_seed<SIVAE_LOSS_BCE_><<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, a_rec, a_t_arr, a_t, a_f_arr, a_f,
+                                                       target_grad_rec ? 1 : 0, d_rec, d_rec_rec, d_rec_fake, d_fake, ps4);
+  else
+    k_loss_seed<SIVAE_LOSS_MSE_><<<grid, 256, 0, st>>>(real, rec, rec_rec, fake, rec_fake, a_rec, a_t_arr, a_t, a_f_arr, a_f,
+                                                       target_grad_rec ? 1 : 0, d_rec, d_rec_rec, d_rec_fake, d_fake, ps4);
 }
 
 // =====================================================================================================

@@ -146,9 +146,15 @@ void launch_linear_wgrad(const float* x, const float* dy, float* dw, float* db, 
 void launch_relu_bwd(const float* y, float* dy, long long n, cudaStream_t st);
 
 // ---------------- losses ----------------
+// recon_loss_type of calc_reconstruction_loss (:268-294); = SIVAE_LOSS_* of include/sivae.h
+enum { SIVAE_LOSS_MSE_ = 0, SIVAE_LOSS_L1_ = 1, SIVAE_LOSS_BCE_ = 2 };
 size_t mse3_scratch_bytes(int B, long long per_sample);
+// per-sample SUMS over the image of the element error (mse: squared, l1: absolute, bce: binary cross entropy) for the pairs
+// (real, rec), (rec, rec_rec), (fake, rec_fake) = (target, reconstruction); bad_flag (bce, nullable): set to 1 if a
+// reconstruction lies outside [0, 1] (F.binary_cross_entropy raises there)
 void launch_mse3(const float* real, const float* rec, const float* rec_rec, const float* fake, const float* rec_fake,
-                 float* out /*[B][3]*/, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st);
+                 float* out /*[B][3]*/, int B, long long per_sample, void* scratch, size_t scratch_bytes, cudaStream_t st,
+                 int loss_type = SIVAE_LOSS_MSE_, int* bad_flag = nullptr);
 // mu_logvar [B][2z]; z = mu + eps*exp(.5 lv); kl[b] = -.5 sum(1 + lv - mu^2 - e^lv)
 void launch_kl_reparam(const float* mu_logvar, const float* eps, float* z, float* kl, int B, int zdim, cudaStream_t st);
 // d(mu_logvar)[B][2z] = dz-path + ckl[b]*KL-path.   dz may be null (no decoder path), ckl may be null
@@ -160,22 +166,27 @@ struct StepCoefs;   // device-side per-sample coefficients, see loss kernels
 void launch_e_loss_finalize(const float* mse, const float* kl_real, const float* kl_rec, const float* kl_fake, int B,
                             float beta_kl, float beta_rec, float beta_neg, float scale, float* stats,
                             float* coef /*[4][B]: c_rec, c_rr, c_rf, (unused)*/, float* ckl_rec, float* ckl_fake,
-                            cudaStream_t st);
+                            cudaStream_t st, float mean_div = 1.f, const int* bad_flag = nullptr);
+// mean_div: factor on the batch mean of the per-sample sums for the reduction='mean' terms: 1 (mse, :282-287) or
+// 1 / (cdim*S*S) (l1 / bce: F.*_loss(reduction='mean') divides by B*D, :288-291); bad_flag -> stats[14]
 // D-step scalar assembly (:599-620)
 void launch_d_loss_finalize(const float* mse, const float* kl_rec, const float* kl_fake, int B, float beta_kl,
-                            float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st);
+                            float beta_rec, float gamma_r, float scale, float* stats, cudaStream_t st, float mean_div = 1.f,
+                            const int* bad_flag = nullptr);
 // vae-step scalar assembly (:520-523)
 void launch_vae_loss_finalize(const float* mse, const float* kl, int B, float beta_kl, float beta_rec, float* stats,
-                              cudaStream_t st);
+                              cudaStream_t st, float mean_div = 1.f, const int* bad_flag = nullptr);
 // gradient seeds on images (NHWC, per_sample floats each):
 //   d_rec      = a_rec[b]*(rec-real) + a_t[b]*(rec_rec-rec)*(-1)      (a_* may be per-sample arrays or constants)
 //   d_rec_rec  = a_t[b]*(rec_rec-rec)
 //   d_rec_fake = a_f[b]*(rec_fake-fake);   d_fake = -a_f[b]*(rec_fake-fake) if d_fake != null
 // a_rec is a constant; a_t / a_f are per-sample arrays when *_arr != null else constants.
+// l1 / bce: (r - x) is replaced by half the element derivative w.r.t. the reconstruction, and the target-side terms (the
+// "* (-1)" above) by half the derivative w.r.t. the target (see rec_g / rec_gx in kernels.cu)
 void launch_loss_seed(const float* real, const float* rec, const float* rec_rec, const float* fake,
                       const float* rec_fake, float a_rec, const float* a_t_arr, float a_t, const float* a_f_arr,
                       float a_f, bool target_grad_rec, float* d_rec, float* d_rec_rec, float* d_rec_fake, float* d_fake,
-                      int B, long long per_sample, cudaStream_t st);
+                      int B, long long per_sample, cudaStream_t st, int loss_type = SIVAE_LOSS_MSE_);
 
 // ---------------- optimiser ----------------
 void launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float grad_scale,

@@ -112,6 +112,25 @@ class Engine:
     def reuse_decoder_passes(self, on):
         L.check(L.load().sivae_set_reuse_decoder_passes(self.handle, 1 if on else 0), "sivae_set_reuse_decoder_passes")
 
+    @property
+    def recon_loss(self):
+        """recon_loss_type of the step ('mse' | 'l1' | 'bce'; reference calc_reconstruction_loss :268-294)"""
+        code = L.load().sivae_get_recon_loss(self.handle)
+        return {v: k for k, v in L.LOSS_TYPES.items()}[code]
+
+    @recon_loss.setter
+    def recon_loss(self, loss_type):
+        if loss_type not in L.LOSS_TYPES:
+            raise NotImplementedError("recon_loss_type must be one of %s" % (sorted(L.LOSS_TYPES),))     # :292-293
+        if loss_type != self.recon_loss:
+            self.drop_graphs()                    # the loss kernels are baked into the captured step
+            L.check(L.load().sivae_set_recon_loss(self.handle, L.LOSS_TYPES[loss_type]), "sivae_set_recon_loss")
+
+    def check_loss_domain(self, stats_host):
+        """stats[14]: recon_loss_type='bce' saw a reconstruction outside [0, 1] -- F.binary_cross_entropy raises there"""
+        if bool(stats_host[14] != 0):
+            raise RuntimeError("all elements of input should be between 0 and 1")
+
     def drop_graphs(self):
         """Forget every captured step graph (pointers or derived-filter state they baked in are no longer valid)."""
         self._graphs = {}
@@ -163,6 +182,7 @@ class Engine:
         lib = L.load()
         steps = {net: lib.sivae_adam_get_step(self.handle, net) for net in self.mem}
         reuse = self.reuse_decoder_passes
+        loss = self.recon_loss
         lib.sivae_destroy(self.handle)
         self.cfg.max_batch = int(max_batch)
         self.handle = C.c_void_p()
@@ -173,6 +193,7 @@ class Engine:
         for net, s in steps.items():
             lib.sivae_adam_set_step(self.handle, net, s)
         self.reuse_decoder_passes = reuse
+        self.recon_loss = loss
         self._comm_world = 1        # the new handle is not attached to the process-global communicator yet (re-attached on next use)
 
     # ---- data parallel: the library-owned NCCL communicator ------------------------------------------------------

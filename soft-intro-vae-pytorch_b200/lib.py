@@ -10,6 +10,8 @@ LIB_PATH = os.environ.get("SIVAE_LIB_PATH") or os.path.join(_HERE, "libsivae_b20
 NET_ENCODER, NET_DECODER, NET_TARGET = 0, 1, 2
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05, CONV_TC3X, CONV_TF32 = 0, 1, 2, 3, 4
 T_CONV, T_BN_WEIGHT, T_BN_BIAS, T_LINEAR, T_BIAS = 0, 1, 2, 3, 4
+LOSS_MSE, LOSS_L1, LOSS_BCE = 0, 1, 2
+LOSS_TYPES = {"mse": LOSS_MSE, "l1": LOSS_L1, "bce": LOSS_BCE}      # recon_loss_type strings of the reference (:268-294)
 
 
 class Config(C.Structure):
@@ -52,6 +54,8 @@ _SIGS = {
     "sivae_vae_step": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Hyper), _P, _P]),
     "sivae_set_reuse_decoder_passes": (C.c_int, [_P, C.c_int]),
     "sivae_get_reuse_decoder_passes": (C.c_int, [_P]),
+    "sivae_set_recon_loss": (C.c_int, [_P, C.c_int]),
+    "sivae_get_recon_loss": (C.c_int, [_P]),
     "sivae_adam_step": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, _P]),
     "sivae_adam_set_step": (C.c_int, [_P, C.c_int, C.c_longlong]),
     "sivae_adam_get_step": (C.c_longlong, [_P, C.c_int]),

@@ -248,6 +248,7 @@ class SoftIntroVAE(nn.Module):
                     mem.v.copy_(old.mem[net_id].v.to(dev))
                     _L.load().sivae_adam_set_step(eng.handle, net_id, _L.load().sivae_adam_get_step(old.handle, net_id))
         if old is not None:
+            eng.recon_loss = old.recon_loss
             old.close()
         self._engine = eng
         eng.params_changed()
@@ -732,8 +733,8 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                   exit_on_negative_diff, num_epochs, num_vae, save_interval, recon_loss_type, beta_kl, beta_rec,
                   beta_neg, test_iter, seed, pretrained, device, num_row, gamma_r, with_fid):
     """shared driver of the standard and the bootstrap (copy_to_target_freq is not None) trainers"""
-    if recon_loss_type != "mse":
-        raise NotImplementedError("the B200 engine implements recon_loss_type='mse' (the only type the CLI passes)")
+    if recon_loss_type not in _L.LOSS_TYPES:
+        raise NotImplementedError                 # calc_reconstruction_loss :292-293
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("train_soft_intro_vae (B200 engine) needs device=torch.device('cuda:N'); no CPU fallback")
@@ -755,7 +756,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
         load_model(model, pretrained, device)
     if main:
         print(model)
-    model.reserve(batch_size)
+    model.reserve(batch_size).recon_loss = recon_loss_type      # 'mse' | 'l1' | 'bce' (:268-294), in every loss term of the step
     resumed_iter = 0
     if getattr(model, "_resume_state", None) is not None:
         # checkpoint written by this module: continue Adam, the RNG streams and the iteration counter where they stopped
@@ -805,6 +806,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
         sh_, ev_, epoch_, pbar_ = p
         ev_.synchronize()
         st = sh_.clone()
+        model._engine.check_loss_domain(st)                                 # bce outside [0, 1]: RuntimeError like F.binary_cross_entropy
         if bool(st[15] != 0):                                               # isnan(lossD) or isnan(lossE) (:625-626)
             raise SystemError
         kl_real, kl_fake, kl_rec, rec_err = st[1].item(), st[7].item(), st[6].item(), st[5].item()
@@ -847,6 +849,7 @@ def _run_training(model_cls, copy_to_target_freq, dataset, z_dim, lr_e, lr_d, ba
                 real_batch = batch.to(device, non_blocking=True)
                 e = torch.randn((b_size, z_dim), device=device)                     # the draw of reparameterize()
                 st = vae_iteration(model, real_batch, e, hp_vae, cur_lr_e, cur_lr_d).cpu()
+                model._engine.check_loss_domain(st)
                 if bool(st[15] != 0):
                     raise SystemError
                 pbar.set_description_str('epoch #{}'.format(epoch))

@@ -27,7 +27,7 @@ def make_inputs(cfg, batch, seed):
     return real, noise, eps
 
 
-DEFAULT_HP = dict(beta_kl=1.0, beta_rec=1.0, beta_neg=256.0, gamma_r=1e-8, lr_e=2e-4, lr_d=2e-4)
+DEFAULT_HP = dict(beta_kl=1.0, beta_rec=1.0, beta_neg=256.0, gamma_r=1e-8, lr_e=2e-4, lr_d=2e-4, loss_type="mse")
 
 
 def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=None, inputs=None, hp=None, device="cuda:0",
@@ -47,6 +47,7 @@ def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=N
     real, noise, eps = inputs if inputs is not None else make_inputs(cfg, batch, seed)
     real, noise, eps = real.to(device), noise.to(device), eps.to(device).contiguous()
     eng = model.reserve(batch)
+    eng.recon_loss = hp["loss_type"]
     h = E.make_hyper(hp["beta_kl"], hp["beta_rec"], hp["beta_neg"], hp["gamma_r"], hp["scale"])
     eng.e_step(real, noise, eps[:3].contiguous(), h)
     torch.cuda.synchronize()
@@ -71,7 +72,8 @@ def run_engine_iteration(cfg, batch, seed, backend=0, bootstrap=False, init_sd=N
     st = eng.stats.cpu()
     scal = dict(loss_rec_e=st[0].item(), lossE_real_kl=st[1].item(), expelbo_rec=st[2].item(), expelbo_fake=st[3].item(),
                 lossE=st[4].item(), loss_rec=st[5].item(), lossD_rec_kl=st[6].item(), lossD_fake_kl=st[7].item(),
-                loss_rec_rec=st[8].item(), loss_fake_rec=st[9].item(), lossD=st[10].item(), nan=st[15].item())
+                loss_rec_rec=st[8].item(), loss_fake_rec=st[9].item(), lossD=st[10].item(), nan=st[15].item(),
+                bce_domain=st[14].item())
     post = {k: v.detach().clone().cpu().contiguous() for k, v in model.state_dict().items()}
     return dict(scalars=scal, grads_e=grads_e, grads_d=grads_d, post=post, init=init, images_e=imgs_e, model=model,
                 enc_after_e=enc_after_e)
@@ -87,7 +89,7 @@ def run_oracle_iteration(cfg, batch, seed, bootstrap=False, init_sd=None, inputs
     real, noise, eps = inputs if inputs is not None else make_inputs(cfg, batch, seed)
     real, noise, eps = real.to(dtype), noise.to(dtype), [e.to(dtype) for e in eps]
     ohp = O.Hyper(beta_kl=hp["beta_kl"], beta_rec=hp["beta_rec"], beta_neg=hp["beta_neg"], gamma_r=hp["gamma_r"],
-                  scale=hp["scale"], lr_e=hp["lr_e"], lr_d=hp["lr_d"])
+                  scale=hp["scale"], lr_e=hp["lr_e"], lr_d=hp["lr_d"], loss_type=hp["loss_type"])
     scal, ge, gd, te, td = O.full_iteration(sd, arch, real, noise, eps, ohp, O.AdamState(), O.AdamState(), bootstrap)
     return dict(scalars=scal, grads_e=ge, grads_d=gd, post=sd, images_e=te)
 

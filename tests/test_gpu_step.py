@@ -104,6 +104,70 @@ def test_baseline_config_step_vs_oracle(name, cfg, batch, hp, bootstrap):
             noise=ora32)
 
 
+def _unit_range_decoder(sd):
+    """decoder outputs inside (0, 1), as F.binary_cross_entropy needs them: small `predict` filters around a bias of 0.5"""
+    sd = {k: v.clone() for k, v in sd.items()}
+    for p in ("decoder", "target_decoder"):
+        if p + ".main.predict.weight" in sd:
+            sd[p + ".main.predict.weight"] *= 0.05
+            sd[p + ".main.predict.bias"].fill_(0.5)
+    return sd
+
+
+@pytest.mark.parametrize("backend", [1, 0])
+@pytest.mark.parametrize("loss", ["l1", "bce"])
+def test_tiny_step_l1_bce_vs_reference_golden(loss, backend):
+    """recon_loss_type = 'l1' / 'bce' (calc_reconstruction_loss :288-291; 'mean' over B*D, per-sample sums in the exp-ELBO terms
+    :574-578) against the UNMODIFIED reference run with that kwarg (tests/golden/tiny_l1.pt, tiny_bce.pt)"""
+    g = torch.load(os.path.join(GOLD, "tiny_%s.pt" % loss), weights_only=False)
+    assert g["hyper"]["loss_type"] == loss
+    cfg = dict(g["arch"])
+    inputs = (g["real"], g["noise"], torch.stack(g["eps"]))
+    ora = run_oracle_iteration(cfg, g["batch"], g["seed"], init_sd=g["init"], inputs=inputs, hp=g["hyper"])
+    out = run_engine_iteration(cfg, g["batch"], g["seed"], backend=backend, init_sd=g["init"], inputs=inputs, hp=g["hyper"],
+                               teacher_enc=g["post"])
+    assert out["scalars"]["bce_domain"] == 0.0
+    for k, v in _golden_as_oracle(g).items():
+        assert out["scalars"][k] == pytest.approx(v, rel=TOL[backend]), k
+    ref = dict(scalars=ora["scalars"], grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
+    compare(out, ref, TOL[backend], label="tiny golden %s backend %d" % (loss, backend), tensor_tol=TTOL[backend], noise=ora)
+
+
+@pytest.mark.parametrize("loss,bootstrap", [("l1", False), ("bce", False), ("l1", True), ("bce", True)])
+def test_l1_bce_step_vs_oracle(loss, bootstrap):
+    """the default backend with the other reconstruction losses at the CIFAR architecture (BASELINE config C) against the fp64
+    oracle; the bootstrap cases exercise the derivative w.r.t. the (not detached) targets of the D half (bootstrap :635-641)"""
+    from oracle import sivae_oracle as O
+    cfg = dict(cdim=3, zdim=128, channels=[64, 128, 256], image_size=32)
+    hp = dict(loss_type=loss, gamma_r=1.0 if bootstrap else 1e-8)
+    init = O.make_state_dict(O.Arch(**cfg), seed=13, bootstrap=bootstrap)
+    if loss == "bce":
+        init = _unit_range_decoder(init)
+    ora = run_oracle_iteration(cfg, 8, seed=13, hp=hp, bootstrap=bootstrap, init_sd=init)
+    ora32 = run_oracle_iteration(cfg, 8, seed=13, hp=hp, bootstrap=bootstrap, init_sd=init, dtype=torch.float32)
+    out = run_engine_iteration(cfg, 8, seed=13, backend=0, hp=hp, bootstrap=bootstrap, init_sd=init, teacher_enc=ora["post"])
+    assert out["scalars"]["bce_domain"] == 0.0
+    compare(out, ora, 1e-4, label="config C %s%s, default backend vs fp64 oracle" % (loss, " bootstrap" if bootstrap else ""),
+            tensor_tol=TTOL[0], noise=ora32)
+
+
+def test_bce_outside_unit_range_is_flagged():
+    """a randomly initialised decoder has no output non-linearity (:158-159), so recon_loss_type='bce' meets reconstructions
+    outside [0, 1] at once: the reference raises inside F.binary_cross_entropy; the engine sets stats[14] and the Python
+    boundary turns it into the same RuntimeError"""
+    cfg = dict(cdim=3, zdim=16, channels=[32, 64], image_size=16)
+    out = run_engine_iteration(cfg, 4, seed=3, backend=0, hp=dict(loss_type="bce"))
+    assert out["scalars"]["bce_domain"] == 1.0
+    eng = out["model"]._engine
+    with pytest.raises(RuntimeError, match="between 0 and 1"):
+        eng.check_loss_domain(eng.stats.cpu())
+    assert eng.recon_loss == "bce"
+    eng.recon_loss = "mse"
+    assert eng.recon_loss == "mse"
+    with pytest.raises(NotImplementedError):
+        eng.recon_loss = "huber"
+
+
 def test_full_size_exact_path_vs_oracle():
     """the on-device exact path (conv_backend 1) at the H architecture against the fp64 oracle: pins the engine's orchestration
     at 6 stages / 256x256 (row-separable stem / predict, BN grids, offsets) independently of the tensor-core kernels"""

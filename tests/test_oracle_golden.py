@@ -26,9 +26,11 @@ def _relerr(a, b):
     return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
 
 
-@pytest.mark.parametrize("name,bootstrap", [("tiny_std.pt", False), ("tiny_bootstrap.pt", True)])
+@pytest.mark.parametrize("name,bootstrap", [("tiny_std.pt", False), ("tiny_bootstrap.pt", True),
+                                            ("tiny_l1.pt", False), ("tiny_bce.pt", False)])   # recon_loss_type l1 / bce (:288-291)
 def test_oracle_matches_reference_full(golden_dir, name, bootstrap):
     g = _load(golden_dir, name)
+    assert g["hyper"].get("loss_type", "mse") == {"tiny_l1.pt": "l1", "tiny_bce.pt": "bce"}.get(name, "mse")
     sd, scal, ge, gd = _run(g, bootstrap)
     s = g["scalars"]
     # same ops, same thread count => agreement to fp32 round-off
