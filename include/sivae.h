@@ -51,6 +51,10 @@ typedef struct {
   int max_batch;     /* largest batch the workspace is sized for */
   int variant;       /* 0 = standard, 1 = bootstrap (soft_intro_vae_bootstrap/...:192-217) */
   int conv_backend;  /* SIVAE_CONV_* */
+  int cond_dim;      /* 0 = unconditional; > 0: SoftIntroVAE(conditional=True, cond_dim): the encoder fc takes [features | cond]
+                        rows, the decoder fc [z | cond] rows (:106-109, :139-143).  Inference entry points only
+                        (sivae_encode_cond / sivae_decode_cond): the reference's training step passes no condition
+                        (:559-561), so a conditional model cannot be trained by it either (F.linear shape error) */
 } sivae_config;
 
 /* beta_kl, beta_rec, beta_neg, gamma_r kwargs (:340-341) and scale = 1/(ch*image_size^2) (:456) */
@@ -159,6 +163,13 @@ int sivae_iteration(sivae_engine* e, const float* real_nchw, const float* noise,
    train != 0 uses batch statistics and moves the running stats like the reference in model.train(). */
 int sivae_encode(sivae_engine* e, const float* x_nchw, int batch, float* mu, float* logvar, int train, void* stream);
 int sivae_decode(sivae_engine* e, int net, const float* z, int batch, float* out_nchw, int train, void* stream);
+/* the same for a conditional model (sivae_config.cond_dim > 0): Encoder.forward(x, o_cond) (:116-122) / Decoder.forward(z, y_cond)
+   (:161-169); cond: [B, cond_dim] device rows concatenated to the fc input.  The plain entry points above (and every training
+   step) FAIL on a conditional engine, as the reference's fc layers reject the un-concatenated input. */
+int sivae_encode_cond(sivae_engine* e, const float* x_nchw, const float* cond, int batch, float* mu, float* logvar, int train,
+                      void* stream);
+int sivae_decode_cond(sivae_engine* e, int net, const float* z, const float* cond, int batch, float* out_nchw, int train,
+                      void* stream);
 
 /* decoder outputs of the last half step as NCHW [B,cdim,S,S]: slot 0 = fake, 1 = rec, 2 = rec_rec, 3 = rec_fake
    (what the reference keeps in the Python variables of the same names, used for the sample grid :641-646) */

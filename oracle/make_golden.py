@@ -210,6 +210,7 @@ def main():
     torch.save(summarise(g), os.path.join(OUT, "cifar_std_summary.pt"))
     print("cifar_std", g["scalars"])
     extra_losses()
+    conditional_forward()
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:16])
@@ -232,7 +233,42 @@ def extra_losses():
         print("tiny_" + lt, g["scalars"])
 
 
-if __name__ == "__main__" and "--losses" in sys.argv:
+def conditional_forward(seed=0, batch=6, cond_dim=10):
+    """SoftIntroVAE(conditional=True) (:106-109, :139-143, :186-193): the UNMODIFIED reference model's train-mode and eval-mode
+    forward with a one-hot condition at the tiny architecture -- the only use the reference has for the branch (its training
+    step passes no condition)."""
+    ref = _import_reference("soft_intro_vae", "train_soft_intro_vae")
+    torch.set_num_threads(8)
+    torch.manual_seed(seed)
+    arch = dict(cdim=3, zdim=16, channels=[32, 64], image_size=16)
+    model = ref.SoftIntroVAE(conditional=True, cond_dim=cond_dim, **arch)
+    init = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(4321)
+    x = torch.rand(batch, 3, 16, 16, generator=g)
+    z = torch.randn(batch, 16, generator=g)
+    cond = torch.nn.functional.one_hot(torch.randint(0, cond_dim, (batch,), generator=g), cond_dim).float()
+    out = dict(arch=arch, cond_dim=cond_dim, seed=seed, init=init, x=x, z=z, cond=cond, torch_version=torch.__version__,
+               reference_commit="b6dbf16")
+    with torch.no_grad():
+        model.train()
+        mu, lv, _, y = model(x, o_cond=cond, deterministic=True)
+        out["train"] = dict(mu=mu.clone(), logvar=lv.clone(), y=y.clone(), sample=model.sample(z, y_cond=cond).clone())
+        out["post_train"] = {k: v.detach().clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+        model.eval()
+        mu, lv, _, y = model(x, o_cond=cond, deterministic=True)
+        out["eval"] = dict(mu=mu.clone(), logvar=lv.clone(), y=y.clone(), sample=model.sample(z, y_cond=cond).clone())
+        try:
+            model(x)                      # conditional model without a condition: fc shape error (:120)
+            out["uncond_error"] = None
+        except RuntimeError as ex:
+            out["uncond_error"] = str(ex)[:120]
+    torch.save(out, os.path.join(OUT, "tiny_cond.pt"))
+    print("tiny_cond", float(out["train"]["mu"].abs().sum()), float(out["eval"]["y"].abs().sum()), out["uncond_error"])
+
+
+if __name__ == "__main__" and "--cond" in sys.argv:
+    conditional_forward()
+elif __name__ == "__main__" and "--losses" in sys.argv:
     extra_losses()
 elif __name__ == "__main__" and "--toy" not in sys.argv:
     main()

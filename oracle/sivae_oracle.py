@@ -113,8 +113,10 @@ def residual_block(sd, p: str, x: Tensor, train: bool) -> Tensor:
     return F.leaky_relu(out + identity, LRELU_SLOPE)
 
 
-def encoder_forward(sd, arch: Arch, x: Tensor, train: bool = True, prefix: str = "encoder") -> Tuple[Tensor, Tensor]:
-    """Encoder.forward, :116-122 with `main` from :88-101."""
+def encoder_forward(sd, arch: Arch, x: Tensor, train: bool = True, prefix: str = "encoder",
+                    o_cond: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Encoder.forward, :116-122 with `main` from :88-101.  o_cond: the condition rows a conditional model concatenates
+    to the flattened features (:118-119; its fc is Linear(features + cond_dim, 2z), :106-107)."""
     m = prefix + ".main"
     y = F.conv2d(x, sd[m + ".0.weight"], None, 1, 2)
     y = F.leaky_relu(_bn(sd, m + ".1", y, train), LRELU_SLOPE)
@@ -125,14 +127,19 @@ def encoder_forward(sd, arch: Arch, x: Tensor, train: bool = True, prefix: str =
         if i < len(blocks) - 1:
             y = F.avg_pool2d(y, 2)
     y = y.reshape(x.size(0), -1)
+    if o_cond is not None:
+        y = torch.cat([y, o_cond], dim=1)
     y = F.linear(y, sd[prefix + ".fc.weight"], sd[prefix + ".fc.bias"])
     mu, logvar = y.chunk(2, dim=1)
     return mu, logvar
 
 
-def decoder_forward(sd, arch: Arch, z: Tensor, train: bool = True, prefix: str = "decoder") -> Tensor:
-    """Decoder.forward, :161-169 with `fc`/`main` from :145-159."""
+def decoder_forward(sd, arch: Arch, z: Tensor, train: bool = True, prefix: str = "decoder",
+                    y_cond: Optional[Tensor] = None) -> Tensor:
+    """Decoder.forward, :161-169 with `fc`/`main` from :145-159.  y_cond: condition rows concatenated to z (:163-165)."""
     z = z.reshape(z.size(0), -1)
+    if y_cond is not None:
+        z = torch.cat([z, y_cond.reshape(y_cond.size(0), -1)], dim=1)
     y = F.relu(F.linear(z, sd[prefix + ".fc.0.weight"], sd[prefix + ".fc.0.bias"]))
     y = y.reshape(z.size(0), *arch.conv_output_size())
     m = prefix + ".main"

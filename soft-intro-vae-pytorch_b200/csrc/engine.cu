@@ -115,6 +115,7 @@ struct sivae_engine {
   float *d_rec = nullptr, *d_rec_rec = nullptr, *d_rec_fake = nullptr, *d_fake = nullptr;
   float *dml = nullptr, *dz = nullptr, *dfeat = nullptr, *dfeat2 = nullptr, *coef = nullptr, *ckl_a = nullptr, *ckl_b = nullptr, *mse = nullptr;
   float *out_tmp = nullptr;
+  float *featc = nullptr, *zc = nullptr;   // conditional models: [feat | cond] and [z | cond] rows, the fc inputs of :118-119, :163-165
   void* sk = nullptr; size_t sk_bytes = 0;   // split-K partial tensor of the few-tile tensor-core convs
   float *rs = nullptr;             // scratch of the row-separable image-facing convs (B*S*S*32 floats)
   void* red = nullptr; size_t red_bytes = 0;
@@ -216,13 +217,13 @@ static void build_encoder(sivae_engine* e, Net& n) {
   add_block(n, "main.res_in_" + std::to_string(sz), b, cc, cc, sz, RS_NONE);
   n.blocks.push_back(b);
   e->C_last = cc; e->hw_last = sz; e->feat = (long long)cc * sz * sz;
-  add_lin(n, "fc", n.fc, (int)e->feat, 2 * c.zdim);
+  add_lin(n, "fc", n.fc, (int)e->feat + c.cond_dim, 2 * c.zdim);     // conditional: Linear(num_fc_features + cond_dim, 2z), :106-107
 }
 // Decoder.__init__ (:126-159) -- names count from 4, real size starts at conv_output_size
 static void build_decoder(sivae_engine* e, Net& n) {
   const sivae_config& c = e->cfg;
   n.enc = false; n.present = true;
-  add_lin(n, "fc.0", n.fc, c.zdim, (int)e->feat);
+  add_lin(n, "fc.0", n.fc, c.zdim + c.cond_dim, (int)e->feat);       // conditional: Linear(zdim + cond_dim, ...), :139-143
   int cc = c.channels[c.n_channels - 1];
   int name_sz = 4, real = e->hw_last;
   for (int i = c.n_channels - 1; i >= 0; --i) {
@@ -358,6 +359,7 @@ static size_t carve(sivae_engine* e, char* base) {
   long long img = B * S * S * c.cdim;
   e->d_rec = bp.take<float>(img); e->d_rec_rec = bp.take<float>(img); e->d_rec_fake = bp.take<float>(img); e->d_fake = bp.take<float>(img);
   e->out_tmp = bp.take<float>(img);
+  if (c.cond_dim > 0) { e->featc = bp.take<float>(B * (e->feat + c.cond_dim)); e->zc = bp.take<float>(B * (z + c.cond_dim)); }
   e->rs = bp.take<float>(B * S * S * 32);        // row-expanded image / 16-column partial image of the row-separable convs
   e->dml = bp.take<float>(B * 2 * z); e->dz = bp.take<float>(B * z);
   e->dfeat = bp.take<float>(B * e->feat); e->dfeat2 = bp.take<float>(B * e->feat);
@@ -642,7 +644,18 @@ static int block_forward(sivae_engine* e, Net& n, const Block& b, BlockAct& a, c
 
 // Encoder.forward (:116-122): img is NHWC [B,S,S,cdim]; result p.ml = [B,2z] (mu | logvar)
 // keep: the pass will be followed by a backward WITH parameter gradients (see block_forward)
-static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, int B, bool train, bool keep, cudaStream_t st) {
+// [a | b] rows: out[B][wa + wb] (torch.cat(dim=1) of :119, :165)
+static void concat_rows(const float* a, int wa, const float* b, int wb, float* out, int B, cudaStream_t st) {
+  const size_t pitch = sizeof(float) * (size_t)(wa + wb);
+  cudaMemcpy2DAsync(out, pitch, a, sizeof(float) * wa, sizeof(float) * wa, B, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpy2DAsync(out + wa, pitch, b, sizeof(float) * wb, sizeof(float) * wb, B, cudaMemcpyDeviceToDevice, st);
+}
+static const char* kCondMissing =
+    "conditional model called without a condition: its fc layer takes [features | cond_dim] rows (the reference raises the "
+    "matmul shape error of F.linear here, :118-120 / :163-166; its training step never passes one, :559-561)";
+// cond (conditional models only): [B, cond_dim] rows concatenated to the fc input (:118-119)
+static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, int B, bool train, bool keep, cudaStream_t st,
+                       const float* cond = nullptr) {
   const sivae_config& c = e->cfg;
   const int S = c.image_size;
   const bool sp = e->fsplit;
@@ -659,14 +672,26 @@ static int enc_forward(sivae_engine* e, Net& n, EncPass& p, const float* img, in
   }
   // .view(B, -1) of the NCHW tensor (:117)
   launch_nhwc_to_nchw(x, p.feat, B, e->C_last, e->hw_last, e->hw_last, st);
-  launch_linear_fwd(p.feat, n.params + n.fc.w_off, n.params + n.fc.b_off, p.ml, B, n.fc.fin, n.fc.fout, false, st);
+  const float* fc_in = p.feat;
+  if (c.cond_dim > 0) {
+    if (!cond) return fail(-7, kCondMissing);
+    concat_rows(p.feat, (int)e->feat, cond, c.cond_dim, e->featc, B, st);
+    fc_in = e->featc;
+  }
+  launch_linear_fwd(fc_in, n.params + n.fc.w_off, n.params + n.fc.b_off, p.ml, B, n.fc.fin, n.fc.fout, false, st);
   CHECK_CUDA_RET();
   return 0;
 }
 
 // Decoder.forward (:161-169): z [B,zdim] -> p.y NHWC [B,S,S,cdim]
-static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int B, bool train, bool keep, cudaStream_t st) {
+static int dec_forward(sivae_engine* e, Net& n, DecPass& p, const float* z, int B, bool train, bool keep, cudaStream_t st,
+                       const float* cond = nullptr) {
   const sivae_config& c = e->cfg;
+  if (c.cond_dim > 0) {                           // z = torch.cat([z, y_cond], dim=1), :163-165
+    if (!cond) return fail(-7, kCondMissing);
+    concat_rows(z, c.zdim, cond, c.cond_dim, e->zc, B, st);
+    z = e->zc;
+  }
   p.zin = z;
   launch_linear_fwd(z, n.params + n.fc.w_off, n.params + n.fc.b_off, p.h, B, n.fc.fin, n.fc.fout, true, st);
   launch_nchw_to_nhwc(p.h, p.x0, B, e->C_last, e->hw_last, e->hw_last, st);
@@ -788,6 +813,7 @@ extern "C" int sivae_create(const sivae_config* cfg, sivae_engine** out) {
     if (cfg->channels[i] < 4 || cfg->channels[i] % 4 != 0 || cfg->channels[i] > 1024) return fail(-2, "channels must be multiples of 4 in [4,1024]");
   if ((cfg->cdim * S * S) % 4 != 0) return fail(-2, "cdim*image_size^2 must be a multiple of 4");
   if (cfg->conv_backend < SIVAE_CONV_AUTO || cfg->conv_backend > SIVAE_CONV_TF32) return fail(-2, "bad conv_backend");
+  if (cfg->cond_dim < 0 || cfg->cond_dim > 65536) return fail(-2, "cond_dim must be in [0,65536] (0 = unconditional)");
   sivae_engine* e = new sivae_engine();
   e->cfg = *cfg;
   e->comp = cfg->conv_backend == SIVAE_CONV_TC3X;
@@ -1283,7 +1309,18 @@ extern "C" long long sivae_adam_get_step(const sivae_engine* e, int net) {
   return s;
 }
 
+static int encode_impl(sivae_engine* e, const float* x_nchw, const float* cond, int B, float* mu, float* logvar, int train, void* stream);
 extern "C" int sivae_encode(sivae_engine* e, const float* x_nchw, int B, float* mu, float* logvar, int train, void* stream) {
+  return encode_impl(e, x_nchw, nullptr, B, mu, logvar, train, stream);
+}
+// Encoder.forward(x, o_cond) of a conditional model (:116-122): cond = [B, cond_dim] device rows
+extern "C" int sivae_encode_cond(sivae_engine* e, const float* x_nchw, const float* cond, int B, float* mu, float* logvar, int train,
+                                 void* stream) {
+  if (!e || e->cfg.cond_dim <= 0) return fail(-2, "sivae_encode_cond needs an engine created with cond_dim > 0");
+  if (!cond) return fail(-1, "null argument");
+  return encode_impl(e, x_nchw, cond, B, mu, logvar, train, stream);
+}
+static int encode_impl(sivae_engine* e, const float* x_nchw, const float* cond, int B, float* mu, float* logvar, int train, void* stream) {
   TRY(check_ready(e, B));
   if (!x_nchw || !mu || !logvar) return fail(-1, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1292,13 +1329,24 @@ extern "C" int sivae_encode(sivae_engine* e, const float* x_nchw, int B, float* 
   TRY(refresh_derived(e, en, st));
   launch_nchw_to_nhwc(x_nchw, e->out_tmp, B, c.cdim, c.image_size, c.image_size, st);
   EncPass& p = e->ep[2];
-  TRY(enc_forward(e, en, p, e->out_tmp, B, train != 0, false, st));
+  TRY(enc_forward(e, en, p, e->out_tmp, B, train != 0, false, st, cond));
   cudaMemcpy2DAsync(mu, sizeof(float) * c.zdim, p.ml, sizeof(float) * 2 * c.zdim, sizeof(float) * c.zdim, B, cudaMemcpyDeviceToDevice, st);
   cudaMemcpy2DAsync(logvar, sizeof(float) * c.zdim, p.ml + c.zdim, sizeof(float) * 2 * c.zdim, sizeof(float) * c.zdim, B, cudaMemcpyDeviceToDevice, st);
   CHECK_CUDA_RET();
   return 0;
 }
+static int decode_impl(sivae_engine* e, int net, const float* z, const float* cond, int B, float* out_nchw, int train, void* stream);
 extern "C" int sivae_decode(sivae_engine* e, int net, const float* z, int B, float* out_nchw, int train, void* stream) {
+  return decode_impl(e, net, z, nullptr, B, out_nchw, train, stream);
+}
+// Decoder.forward(z, y_cond) of a conditional model (:161-169)
+extern "C" int sivae_decode_cond(sivae_engine* e, int net, const float* z, const float* cond, int B, float* out_nchw, int train,
+                                 void* stream) {
+  if (!e || e->cfg.cond_dim <= 0) return fail(-2, "sivae_decode_cond needs an engine created with cond_dim > 0");
+  if (!cond) return fail(-1, "null argument");
+  return decode_impl(e, net, z, cond, B, out_nchw, train, stream);
+}
+static int decode_impl(sivae_engine* e, int net, const float* z, const float* cond, int B, float* out_nchw, int train, void* stream) {
   TRY(check_ready(e, B));
   Net* n = get_net(e, net);
   if (!n || n->enc) return fail(-1, "bad decoder net id");
@@ -1307,7 +1355,7 @@ extern "C" int sivae_decode(sivae_engine* e, int net, const float* z, int B, flo
   const sivae_config& c = e->cfg;
   TRY(refresh_derived(e, *n, st));
   DecPass& p = e->dp[3];
-  TRY(dec_forward(e, *n, p, z, B, train != 0, false, st));
+  TRY(dec_forward(e, *n, p, z, B, train != 0, false, st, cond));
   launch_nhwc_to_nchw(p.y, out_nchw, B, c.cdim, c.image_size, c.image_size, st);
   CHECK_CUDA_RET();
   return 0;

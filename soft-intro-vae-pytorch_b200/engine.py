@@ -57,7 +57,8 @@ class NetMemory:
 class Engine:
     """One native engine instance bound to the modules of a SoftIntroVAE."""
 
-    def __init__(self, cdim, zdim, channels, image_size, max_batch, device, bootstrap=False, conv_backend=L.CONV_AUTO):
+    def __init__(self, cdim, zdim, channels, image_size, max_batch, device, bootstrap=False, conv_backend=L.CONV_AUTO,
+                 cond_dim=0):
         lib = L.load()
         if torch.device(device).type != "cuda":
             raise RuntimeError("the B200 engine runs on CUDA devices only (no CPU fallback); got %s" % (device,))
@@ -70,6 +71,7 @@ class Engine:
         self.cfg.max_batch = int(max_batch)
         self.cfg.variant = 1 if bootstrap else 0
         self.cfg.conv_backend = int(conv_backend)
+        self.cfg.cond_dim = int(cond_dim)          # 0 = unconditional; SoftIntroVAE(conditional=True, cond_dim) otherwise
         self.bootstrap = bootstrap
         self.handle = C.c_void_p()
         L.check(lib.sivae_create(C.byref(self.cfg), C.byref(self.handle)), "sivae_create")
@@ -291,19 +293,36 @@ class Engine:
         with torch.cuda.device(self.device):
             L.check(L.load().sivae_adam_step(self.handle, net, float(lr), float(grad_scale), _stream()), "sivae_adam_step")
 
-    def encode(self, x, train):
+    def _cond(self, cond, B):
+        """[B, cond_dim] float32 rows on the engine's device (the o_cond / y_cond argument of the reference's forward calls)"""
+        cond = cond.reshape(cond.size(0), -1).to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(cond.shape) != (B, self.cfg.cond_dim):
+            raise RuntimeError("condition of shape %s does not match [batch %d, cond_dim %d]" % (tuple(cond.shape), B, self.cfg.cond_dim))
+        return cond
+
+    def encode(self, x, train, cond=None):
         B = x.shape[0]
         mu = torch.empty(B, self.cfg.zdim, dtype=torch.float32, device=self.device)
         lv = torch.empty_like(mu)
         with torch.cuda.device(self.device):
-            L.check(L.load().sivae_encode(self.handle, L.ptr(x), B, L.ptr(mu), L.ptr(lv), 1 if train else 0, _stream()), "sivae_encode")
+            if cond is not None:
+                cond = self._cond(cond, B)
+                L.check(L.load().sivae_encode_cond(self.handle, L.ptr(x), L.ptr(cond), B, L.ptr(mu), L.ptr(lv), 1 if train else 0,
+                                                   _stream()), "sivae_encode_cond")
+            else:
+                L.check(L.load().sivae_encode(self.handle, L.ptr(x), B, L.ptr(mu), L.ptr(lv), 1 if train else 0, _stream()), "sivae_encode")
         return mu, lv
 
-    def decode(self, z, train, net=L.NET_DECODER):
+    def decode(self, z, train, net=L.NET_DECODER, cond=None):
         B = z.shape[0]
         out = torch.empty(B, self.cfg.cdim, self.cfg.image_size, self.cfg.image_size, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            L.check(L.load().sivae_decode(self.handle, net, L.ptr(z), B, L.ptr(out), 1 if train else 0, _stream()), "sivae_decode")
+            if cond is not None:
+                cond = self._cond(cond, B)
+                L.check(L.load().sivae_decode_cond(self.handle, net, L.ptr(z), L.ptr(cond), B, L.ptr(out), 1 if train else 0,
+                                                   _stream()), "sivae_decode_cond")
+            else:
+                L.check(L.load().sivae_decode(self.handle, net, L.ptr(z), B, L.ptr(out), 1 if train else 0, _stream()), "sivae_decode")
         return out
 
     def note_batch(self, B):

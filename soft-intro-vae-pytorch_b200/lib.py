@@ -16,7 +16,8 @@ LOSS_TYPES = {"mse": LOSS_MSE, "l1": LOSS_L1, "bce": LOSS_BCE}      # recon_loss
 
 class Config(C.Structure):
     _fields_ = [("cdim", C.c_int), ("zdim", C.c_int), ("image_size", C.c_int), ("n_channels", C.c_int),
-                ("channels", C.c_int * 16), ("max_batch", C.c_int), ("variant", C.c_int), ("conv_backend", C.c_int)]
+                ("channels", C.c_int * 16), ("max_batch", C.c_int), ("variant", C.c_int), ("conv_backend", C.c_int),
+                ("cond_dim", C.c_int)]
 
 
 class Hyper(C.Structure):
@@ -69,6 +70,8 @@ _SIGS = {
     "sivae_iteration": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(Hyper), C.c_float, C.c_float, _P, _P]),
     "sivae_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     "sivae_decode": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
+    "sivae_encode_cond": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    "sivae_decode_cond": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
     "sivae_launch_count": (C.c_ulonglong, []),
     "sivae_profile_enable": (C.c_int, [C.c_int]),
     "sivae_profile_read": (C.c_int, [C.POINTER(C.c_double)]),

@@ -103,8 +103,6 @@ class Encoder(_NetBase):
     def __init__(self, cdim=3, zdim=512, channels=(64, 128, 256, 512, 512, 512), image_size=256, conditional=False,
                  cond_dim=10):
         super().__init__()
-        if conditional:
-            raise NotImplementedError("conditional=True is not on the B200 hot path (never used by the reference driver)")
         self.zdim, self.cdim, self.image_size = zdim, cdim, image_size
         self.conditional, self.cond_dim = conditional, cond_dim
         channels = list(channels)
@@ -122,7 +120,8 @@ class Encoder(_NetBase):
         num_fc_features = int(np.prod(self.conv_output_size))
         print("conv shape: ", self.conv_output_size)
         print("num fc features: ", num_fc_features)
-        self.fc = nn.Linear(num_fc_features, 2 * zdim)
+        # conditional: the condition is concatenated to the flattened features in forward (:106-109, :118-119)
+        self.fc = nn.Linear(num_fc_features + (self.cond_dim if self.conditional else 0), 2 * zdim)
 
     def calc_conv_output_size(self):
         """The reference pushes a zero image through `main` in train mode here (:111-114).  The shape is computed
@@ -136,21 +135,23 @@ class Encoder(_NetBase):
 
     def forward(self, x, o_cond=None):
         owner, eng = self._eng(x.size(0))
-        return eng.encode(owner._as_input(x), self.training)
+        # :118-119 -- a conditional encoder called WITHOUT a condition fails in its fc layer in the reference (matmul shape
+        # error); the engine refuses the call the same way (RuntimeError)
+        cond = o_cond if (self.conditional and o_cond is not None) else None
+        return eng.encode(owner._as_input(x), self.training, cond=cond)
 
 
 class Decoder(_NetBase):
     def __init__(self, cdim=3, zdim=512, channels=(64, 128, 256, 512, 512, 512), image_size=256, conditional=False,
                  conv_input_size=None, cond_dim=10):
         super().__init__()
-        if conditional:
-            raise NotImplementedError("conditional=True is not on the B200 hot path (never used by the reference driver)")
         self.cdim, self.image_size, self.conditional, self.cond_dim = cdim, image_size, conditional, cond_dim
         channels = list(channels)
         cc = channels[-1]
         self.conv_input_size = conv_input_size
         num_fc_features = cc * 4 * 4 if conv_input_size is None else int(np.prod(conv_input_size))
-        self.fc = nn.Sequential(nn.Linear(zdim, num_fc_features), nn.ReLU(True))
+        # conditional: z is concatenated with the condition in forward (:139-143, :163-165)
+        self.fc = nn.Sequential(nn.Linear(zdim + (cond_dim if conditional else 0), num_fc_features), nn.ReLU(True))
         sz = 4
         self.main = nn.Sequential()
         for ch in channels[::-1]:
@@ -164,7 +165,8 @@ class Decoder(_NetBase):
     def forward(self, z, y_cond=None):
         owner, eng = self._eng(z.size(0))
         z = z.reshape(z.size(0), -1).to(device=eng.device, dtype=torch.float32).contiguous()
-        return eng.decode(z, self.training, net=self._net_id)
+        cond = y_cond if (self.conditional and y_cond is not None) else None
+        return eng.decode(z, self.training, net=self._net_id, cond=cond)
 
 
 class SoftIntroVAE(nn.Module):
@@ -175,7 +177,8 @@ class SoftIntroVAE(nn.Module):
                  cond_dim=10):
         super().__init__()
         self.zdim, self.conditional, self.cond_dim = zdim, conditional, cond_dim
-        self._arch = dict(cdim=cdim, zdim=zdim, channels=list(channels), image_size=image_size)
+        self._arch = dict(cdim=cdim, zdim=zdim, channels=list(channels), image_size=image_size,
+                          cond_dim=int(cond_dim) if conditional else 0)
         self._engine = None
         self._conv_backend = int(os.environ.get("SIVAE_CONV_BACKEND", _L.CONV_AUTO))
         self.encoder = Encoder(cdim, zdim, channels, image_size, conditional=conditional, cond_dim=cond_dim)
@@ -219,7 +222,7 @@ class SoftIntroVAE(nn.Module):
         old = self._engine
         a = self._arch
         eng = _E.Engine(a["cdim"], a["zdim"], a["channels"], a["image_size"], batch, dev, bootstrap=self._bootstrap,
-                        conv_backend=self._conv_backend)
+                        conv_backend=self._conv_backend, cond_dim=a["cond_dim"])
         with torch.no_grad():
             for net_id, mod in self._nets().items():
                 mem = eng.mem[net_id]
@@ -284,9 +287,9 @@ class SoftIntroVAE(nn.Module):
 
     # ---- reference API ------------------------------------------------------------------------------------
     def forward(self, x, o_cond=None, deterministic=False):
-        mu, logvar = self.encode(x)
+        mu, logvar = self.encode(x, o_cond=o_cond)            # :186-201: the condition reaches both fc layers
         z = mu if deterministic else reparameterize(mu, logvar)
-        y = self.decode(z)
+        y = self.decode(z, y_cond=o_cond)
         return mu, logvar, z, y
 
     def sample(self, z, y_cond=None):
@@ -298,10 +301,10 @@ class SoftIntroVAE(nn.Module):
         return self.decode(z, y_cond=y_cond)
 
     def encode(self, x, o_cond=None):
-        return self.encoder(x)
+        return self.encoder(x, o_cond=o_cond)
 
     def decode(self, z, y_cond=None):
-        return self.decoder(z)
+        return self.decoder(z, y_cond=y_cond)
 
 
 # ======================================================================================================

@@ -44,13 +44,13 @@ class SoftIntroVAE(_B.SoftIntroVAE):
         self._wire()
 
     def forward(self, x, o_cond=None, deterministic=False, target=True):
-        mu, logvar = self.encode(x)
+        mu, logvar = self.encode(x, o_cond=o_cond)
         z = mu if deterministic else reparameterize(mu, logvar)
-        y = self.decode_target(z) if target else self.decode(z)
+        y = self.decode_target(z, y_cond=o_cond) if target else self.decode(z, y_cond=o_cond)
         return mu, logvar, z, y
 
     def decode_target(self, z, y_cond=None):
-        return self.target_decoder(z)
+        return self.target_decoder(z, y_cond=y_cond)
 
 
 def train_soft_intro_vae(dataset='cifar10', z_dim=128, lr_e=2e-4, lr_d=2e-4, batch_size=128, num_workers=4,

@@ -34,6 +34,7 @@ def _engine_schema(cfg, variant=0):
     for i, ch in enumerate(cfg["channels"]):
         c.channels[i] = ch
     c.max_batch, c.variant, c.conv_backend = 4, variant, 0
+    c.cond_dim = cfg.get("cond_dim", 0)
     h = C.c_void_p()
     L.check(lib.sivae_create(C.byref(c), C.byref(h)), "create")
     out = {}
@@ -49,7 +50,9 @@ def _engine_schema(cfg, variant=0):
 
 @pytest.mark.parametrize("cfg", [dict(cdim=3, zdim=128, channels=[64, 128, 256], image_size=32),
                                  dict(cdim=3, zdim=512, channels=[64, 128, 256, 512, 512, 512], image_size=256),
-                                 dict(cdim=1, zdim=32, channels=[64, 128], image_size=28 + 4)])
+                                 dict(cdim=1, zdim=32, channels=[64, 128], image_size=28 + 4),
+                                 # celeb1024 (:405-417): 8 stages from 16 channels
+                                 dict(cdim=3, zdim=512, channels=[16, 32, 64, 128, 256, 512, 512, 512], image_size=1024)])
 def test_engine_schema_equals_reference_state_dict(cfg):
     """index / shape work must be bit-exact: names, order and shapes of every parameter"""
     from oracle import sivae_oracle as O
@@ -59,6 +62,21 @@ def test_engine_schema_equals_reference_state_dict(cfg):
     assert list(got.keys()) == list(want.keys())
     assert got == want
     assert ws > 0
+
+
+def test_conditional_engine_schema():
+    """cond_dim widens the two fc layers only (:106-109, :139-143)"""
+    cfg = dict(cdim=3, zdim=16, channels=[32, 64], image_size=16)
+    plain, _ = _engine_schema(cfg)
+    cond, _ = _engine_schema(dict(cfg, cond_dim=10))
+    assert list(plain.keys()) == list(cond.keys())
+    for k in plain:
+        if k == "encoder.fc.weight":
+            assert cond[k] == (32, 64 * 4 * 4 + 10) and plain[k] == (32, 1024)
+        elif k == "decoder.fc.0.weight":
+            assert cond[k] == (1024, 16 + 10) and plain[k] == (1024, 16)
+        else:
+            assert cond[k] == plain[k], k
 
 
 def test_create_rejects_bad_configs():
@@ -100,6 +118,19 @@ def test_model_init_is_bit_identical_to_reference(golden_dir):
     assert list(sd.keys()) == list(g["init"].keys())
     for k, v in g["init"].items():
         assert torch.equal(sd[k], v), k
+
+
+def test_conditional_model_init_is_bit_identical_to_reference(golden_dir):
+    """conditional=True widens both fc layers by cond_dim (:106-109, :139-143): same constructors in the same order"""
+    g = torch.load(os.path.join(golden_dir, "tiny_cond.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    model = M.SoftIntroVAE(conditional=True, cond_dim=g["cond_dim"], **g["arch"])
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g["init"].keys())
+    for k, v in g["init"].items():
+        assert sd[k].shape == v.shape and torch.equal(sd[k], v), k
+    assert model.conditional and model.cond_dim == g["cond_dim"] and model._arch["cond_dim"] == g["cond_dim"]
+    assert M.SoftIntroVAE(cdim=3, zdim=8, channels=[32, 32], image_size=8, conditional=False, cond_dim=10)._arch["cond_dim"] == 0
 
 
 def test_no_cpu_fallback():

@@ -295,6 +295,48 @@ def test_inference_api_train_and_eval():
         assert y.shape == (4, 3, 16, 16)
 
 
+@pytest.mark.parametrize("backend", [1, 0])
+def test_conditional_model_vs_reference_golden(backend):
+    """SoftIntroVAE(conditional=True, cond_dim=10) (:106-109, :118-119, :139-143, :163-165, :186-193): model(x, o_cond) and
+    model.sample(z, y_cond) through the engine in train and eval mode against the UNMODIFIED reference model
+    (tests/golden/tiny_cond.pt), BatchNorm buffers included; without a condition -- and in the training step, which passes
+    none (:559-561) -- the reference's fc layers reject the input, and so does the engine (RuntimeError)."""
+    import importlib
+    from tests.step_harness import PKG
+    M = importlib.import_module(PKG + ".train_soft_intro_vae")
+    E = importlib.import_module(PKG + ".engine")
+    g = torch.load(os.path.join(GOLD, "tiny_cond.pt"), weights_only=False)
+    torch.manual_seed(g["seed"])
+    model = M.SoftIntroVAE(conditional=True, cond_dim=g["cond_dim"], **g["arch"])
+    model._conv_backend = backend
+    model.load_state_dict(g["init"])
+    model = model.to("cuda:0")
+    x, z, cond = g["x"].cuda(), g["z"].cuda(), g["cond"].cuda()
+    rt, at = (1e-4, 1e-5) if backend == 1 else (2e-4, 2e-5)
+    for mode in ("train", "eval"):
+        model.train(mode == "train")
+        mu, lv, zz, y = model(x, o_cond=cond, deterministic=True)
+        smp = model.sample(z, y_cond=cond)
+        assert torch.equal(zz, mu) and y.shape == (x.size(0), 3, 16, 16)
+        for name, v in (("mu", mu), ("logvar", lv), ("y", y), ("sample", smp)):
+            assert torch.allclose(v.cpu(), g[mode][name], rtol=rt * 10 if name in ("y", "sample") else rt, atol=at * 10), (mode, name)
+        if mode == "train":
+            sd = model.state_dict()
+            for k, v in g["post_train"].items():
+                if v.is_floating_point():
+                    assert torch.allclose(sd[k].cpu(), v, rtol=1e-3, atol=1e-5), k
+                else:
+                    assert int(sd[k]) == int(v), k
+    with pytest.raises(RuntimeError, match="condition"):
+        model(x)                                              # reference: "mat1 and mat2 shapes cannot be multiplied"
+    with pytest.raises(RuntimeError, match="condition"):
+        model.sample(z)
+    eng = model._engine
+    h = E.make_hyper(1.0, 1.0, 256.0, 1e-8, 1.0 / (3 * 16 * 16))
+    with pytest.raises(RuntimeError, match="condition"):
+        eng.e_step(x, z, torch.randn(3, x.size(0), 16, device="cuda:0"), h)
+
+
 @pytest.mark.parametrize("backend", [1, 0, 3, 4])
 def test_tiny_bootstrap_step_vs_reference_golden(backend):
     """bootstrap variant (target decoder, nothing detached in the D half) vs the unmodified reference bootstrap trainer"""

@@ -88,3 +88,25 @@ def test_oracle_matches_reference_cifar_summary(golden_dir):
     for k, v in g["post_small"].items():
         if v.is_floating_point():
             assert torch.allclose(sd[k], v, rtol=1e-4, atol=1e-6), k
+
+
+def test_oracle_conditional_forward_matches_reference(golden_dir):
+    """SoftIntroVAE(conditional=True): fc over [features | cond] (:106-109, :118-119) and [z | cond] (:139-143, :163-165) --
+    the oracle's forward against the unmodified reference model in train and eval mode (tests/golden/tiny_cond.pt)"""
+    g = _load(golden_dir, "tiny_cond.pt")
+    torch.set_num_threads(8)
+    arch = O.Arch(**g["arch"])
+    sd = O.clone_sd(g["init"])
+    assert sd["encoder.fc.weight"].shape[1] == 64 * 4 * 4 + g["cond_dim"] and sd["decoder.fc.0.weight"].shape[1] == 16 + g["cond_dim"]
+    for mode in ("train", "eval"):
+        t = mode == "train"
+        with torch.no_grad():
+            mu, lv = O.encoder_forward(sd, arch, g["x"], train=t, o_cond=g["cond"])
+            y = O.decoder_forward(sd, arch, mu, train=t, y_cond=g["cond"])
+            smp = O.decoder_forward(sd, arch, g["z"], train=t, y_cond=g["cond"])
+        for name, v in (("mu", mu), ("logvar", lv), ("y", y), ("sample", smp)):
+            assert torch.allclose(v, g[mode][name], rtol=1e-5, atol=1e-6), (mode, name)
+        if t:
+            for k, v in g["post_train"].items():
+                assert torch.allclose(sd[k].to(v.dtype), v, rtol=1e-5, atol=1e-7), k
+    assert "shapes cannot be multiplied" in g["uncond_error"]       # what the reference does without a condition
