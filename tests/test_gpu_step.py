@@ -159,7 +159,11 @@ def test_tiny_step_l1_bce_vs_reference_golden(loss, backend):
     assert out["scalars"]["bce_domain"] == 0.0
     for k, v in _golden_as_oracle(g).items():
         assert out["scalars"][k] == pytest.approx(v, rel=TOL[backend]), k
-    ref = dict(scalars=ora["scalars"], grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
+    # D-half scalars: only against the golden's own logged values above -- the engine's D half runs on the REFERENCE's post-E-step
+    # encoder (teacher forcing), the fp64 oracle's on its own, and one Adam step turns round-off in a tiny gradient (l1: a
+    # sign) into an O(lr) weight difference (measured: lossD_fake_kl 2.9e-5 apart on the exact path)
+    e_half = ("loss_rec_e", "lossE_real_kl", "expelbo_rec", "expelbo_fake", "lossE")
+    ref = dict(scalars={k: ora["scalars"][k] for k in e_half}, grads_e=g["grads_e"], grads_d=g["grads_d"], post=g["post"])
     compare(out, ref, TOL[backend], label="tiny golden %s backend %d" % (loss, backend), tensor_tol=TTOL[backend], noise=ora)
 
 
