@@ -253,6 +253,16 @@ long long sivae_image_plan_bytes(int in_h, int in_w, int out_h, int out_w);
 int sivae_image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, long long plan_bytes, void* stream);
 int sivae_image_batch_u8(const unsigned char* src_hwc, const unsigned char* mirror, int batch, int in_h, int in_w,
                          int channels, int out_h, int out_w, const void* plan_dev, float* out_nchw, void* stream);
+/* load_image in full (dataset.py:12-47: mirror -> [resize to input size, :29-30] -> [ImageOps.crop, :32-44] -> resize to the
+   output size, :46): the resize reads the win_h x win_w window whose origin (x, y) inside each [src_h, src_w] source image is
+   win_xy[b] (device int32 [B][2]; NULL = the whole image) -- Pillow resamples the cropped COPY, so nothing outside the window
+   contributes -- mirrors it first when mirror[b] != 0, and writes EITHER out_nchw (float32 [B,C,out_h,out_w] = ToTensor) OR
+   out_u8_hwc (uint8 [B,out_h,out_w,C]: the intermediate image of the two-stage resize, fed to a second call).  plan = that of
+   (win_h, win_w) -> (out_h, out_w).  A mirror BEFORE a crop (:26-27 precede :32) is the crop window with its left / right
+   margins swapped, mirrored. */
+int sivae_image_batch_u8_ex(const unsigned char* src_hwc, const unsigned char* mirror, const int* win_xy, int batch, int src_h,
+                            int src_w, int channels, int win_h, int win_w, int out_h, int out_w, const void* plan_dev,
+                            float* out_nchw, unsigned char* out_u8_hwc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,38 @@ def load_image_tensor(img_u8, out_h, out_w, mirror):
     return (y.astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1).copy()
 
 
+def crop_margins(w, h, crop_w, crop_h, is_random_crop, rnd):
+    """dataset.py:32-43: the (left, top, right, bottom) borders ImageOps.crop removes.  rnd: Python's `random` module (or a
+    random.Random) -- the random crop draws cx1 then cy1 from it, after the mirror coin (:26)."""
+    if is_random_crop:
+        cx1 = rnd.randint(0, w - crop_w)
+        cx2 = w - crop_w - cx1
+        cy1 = rnd.randint(0, h - crop_h)
+        cy2 = h - crop_h - cy1
+    else:
+        cx2 = cx1 = int(round((w - crop_w) / 2.))
+        cy2 = cy1 = int(round((h - crop_h) / 2.))
+    return cx1, cy1, cx2, cy2
+
+
+def load_image_u8(img_u8, mirror, out_h, out_w, input_hw=None, margins=None):
+    """load_image in full (dataset.py:12-47) on decoded pixels: mirror (:26-27) -> optional resize to (input_h, input_w)
+    (:29-30) -> optional ImageOps.crop of the borders `margins` = (left, top, right, bottom) (:32-44) -> resize to
+    (out_h, out_w) (:46).  Every intermediate is an 8-bit image, as in Pillow.  uint8 [H,W,C] -> uint8 [out_h,out_w,C]"""
+    x = np.ascontiguousarray(img_u8[:, ::-1] if mirror else img_u8)
+    if input_hw is not None:
+        x = resize_bicubic_u8(x, int(input_hw[0]), int(input_hw[1]))
+    if margins is not None:
+        l, t, r, b = (int(v) for v in margins)
+        x = np.ascontiguousarray(x[t:x.shape[0] - b, l:x.shape[1] - r])
+    return resize_bicubic_u8(x, out_h, out_w)
+
+
+def to_tensor(img_u8):
+    """transforms.ToTensor (dataset.py:66-68): uint8 HWC -> float32 CHW / 255"""
+    return (img_u8.astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1).copy()
+
+
 def batch(images_u8, mirror_flags, out_h, out_w):
     """images_u8: [B,H,W,C] uint8 -> [B,C,out_h,out_w] float32"""
     return np.stack([load_image_tensor(im, out_h, out_w, bool(m)) for im, m in zip(images_u8, mirror_flags)])

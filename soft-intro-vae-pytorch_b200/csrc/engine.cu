@@ -1771,3 +1771,19 @@ extern "C" int sivae_image_batch_u8(const unsigned char* src_hwc, const unsigned
   if (r) return fail(r, cudaGetErrorString((cudaError_t)r));
   return 0;
 }
+// load_image in full (dataset.py:12-47): the resize reads the win_h x win_w window at win_xy[b] = (x, y) of each [src_h, src_w]
+// source image (ImageOps.crop, :32-44; win_xy == NULL: the whole image) and writes EITHER out_nchw (float32, = ToTensor of the
+// final image) OR out_u8_hwc (the 8-bit image itself: first stage of the two-stage resize, :29-30).  plan: (win_h, win_w) ->
+// (out_h, out_w).
+extern "C" int sivae_image_batch_u8_ex(const unsigned char* src_hwc, const unsigned char* mirror, const int* win_xy, int batch,
+                                       int src_h, int src_w, int channels, int win_h, int win_w, int out_h, int out_w,
+                                       const void* plan_dev, float* out_nchw, unsigned char* out_u8_hwc, void* stream) {
+  if (!src_hwc || !plan_dev || (!out_nchw && !out_u8_hwc)) return fail(-1, "null argument");
+  int r = launch_image_batch(src_hwc, mirror, batch, win_h, win_w, channels, out_h, out_w, plan_dev, out_nchw, (cudaStream_t)stream,
+                             src_h, src_w, win_xy, out_u8_hwc);
+  if (r == -2) return fail(-2, "bad image batch arguments (channels 1 or 3, batch <= 65535, source 4-byte aligned, window inside the "
+                               "source, exactly one output)");
+  if (r == -7) return fail(-7, "down-scaling factor too large for the shared-memory staging of the resize kernel");
+  if (r) return fail(r, cudaGetErrorString((cudaError_t)r));
+  return 0;
+}

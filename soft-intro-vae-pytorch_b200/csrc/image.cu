@@ -74,12 +74,17 @@ int resample_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::ve
 namespace {
 
 struct ImgArgs {
-  const unsigned char* src;      // [B][Hin][Win][CH] decoded pixels
+  const unsigned char* src;      // [B][src_h][src_w][CH] decoded pixels
   const unsigned char* src_end;  // one past the last source byte
-  const unsigned char* mirror;   // [B] flags (nullable): 1 = ImageOps.mirror before the resize
-  float* dst;                    // [B][CH][Hout][Wout]
+  const unsigned char* mirror;   // [B] flags (nullable): 1 = ImageOps.mirror of the WINDOW before the resize
+  const int* win_xy;             // [B][2] (nullable = 0,0): origin (x, y) of the Hin x Win window inside each source image --
+                                 // ImageOps.crop (dataset.py:32-44); the resize sees only the window, like Pillow's cropped copy
+  float* dst;                    // [B][CH][Hout][Wout] float32 = ToTensor, or (when dst_u8 != null, dst == null):
+  unsigned char* dst_u8;         // [B][Hout][Wout][CH] the 8-bit image itself (first stage of load_image's two-stage resize, :29-30)
   const int *bx, *kx, *by, *ky;  // device coefficient tables (plan)
   int B, Hin, Win, Hout, Wout, ksx, ksy, TW, TH, pitch_in, max_rows;
+  int src_pitch;                 // bytes per source row (src_w * CH)
+  long long img_stride;          // bytes per source image
 };
 
 __device__ __forceinline__ int clip8(int acc) {     // Resample.c clip8: saturating lookup of acc >> PRECISION_BITS
@@ -120,11 +125,12 @@ __device__ __forceinline__ void image_tile(const ImgArgs& a, unsigned char* img_
   const int y0 = by_s[0], y1 = by_s[2 * (th - 1)] + by_s[2 * (th - 1) + 1];
   const int span = x1 - x0, R = y1 - y0;
   const int sx0 = MIR ? a.Win - x1 : x0;                  // mirrored window [x0,x1) = source [Win-x1, Win-x0) reversed
-  const unsigned char* img = a.src + (size_t)b * a.Hin * a.Win * CH;
+  const int wx = a.win_xy ? a.win_xy[2 * b] : 0, wy = a.win_xy ? a.win_xy[2 * b + 1] : 0;
+  const int rowb = a.src_pitch;
+  const unsigned char* img = a.src + (size_t)b * a.img_stride + (size_t)wy * rowb + (size_t)wx * CH;   // origin of the crop window
   const int nbytes = span * CH;
-  const unsigned char* win = img + ((size_t)y0 * a.Win + sx0) * CH;               // first byte of the window's first row
+  const unsigned char* win = img + (size_t)y0 * rowb + (size_t)sx0 * CH;           // first byte of the tile window's first row
   const int g0 = (int)(reinterpret_cast<uintptr_t>(win) & 3);                      // its misalignment; row r: (g0 + r*rowb) & 3
-  const int rowb = a.Win * CH;
 
   // ---- stage: one warp per source row, aligned 32-bit words (the row start is rounded down to a word), asynchronous
   //      global->shared copies (LDGSTS): every row of the window is in flight at once, no register round trip --------------
@@ -209,9 +215,15 @@ __device__ __forceinline__ void image_tile(const ImgArgs& a, unsigned char* img_
           for (int c = 0; c < CH; ++c) acc[c] += (int)mp[k * mid_pitch + c] * coef[k];
         mp += 4 * mid_pitch;
       }
+      if (a.dst_u8) {                                     // the resized 8-bit image, HWC like the source (block-uniform branch)
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        a.dst[(((size_t)b * CH + c) * a.Hout + ty0 + yy) * a.Wout + tx0 + x] = __fdiv_rn((float)clip8(acc[c]), 255.f);   // ToTensor: .div(255)
+        for (int c = 0; c < CH; ++c)
+          a.dst_u8[(((size_t)b * a.Hout + ty0 + yy) * a.Wout + tx0 + x) * CH + c] = (unsigned char)clip8(acc[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          a.dst[(((size_t)b * CH + c) * a.Hout + ty0 + yy) * a.Wout + tx0 + x] = __fdiv_rn((float)clip8(acc[c]), 255.f);   // ToTensor: .div(255)
+      }
     }
   }
 }
@@ -290,15 +302,24 @@ int image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, cu
 }
 
 // returns 0, a cudaError_t (> 0), -2 (bad argument) or -7 (down-scaling factor too large for the shared-memory staging)
+// src: [B][src_h][src_w][ch]; the resize reads the in_h x in_w window at win_xy[b] (nullable: the whole image, then
+// src_h == in_h, src_w == in_w); exactly one of dst (float NCHW) / dst_u8 (8-bit NHWC) is written.  The plan is that of
+// (in_h, in_w) -> (out_h, out_w).  The caller guarantees that every window lies inside its image.
 int launch_image_batch(const unsigned char* src, const unsigned char* mirror, int B, int in_h, int in_w, int ch, int out_h,
-                       int out_w, const void* plan_dev, float* dst, cudaStream_t st) {
+                       int out_w, const void* plan_dev, float* dst, cudaStream_t st, int src_h, int src_w, const int* win_xy,
+                       unsigned char* dst_u8) {
+  if (src_h <= 0) src_h = in_h;
+  if (src_w <= 0) src_w = in_w;
   if (B < 1 || in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1 || (ch != 1 && ch != 3)) return -2;
   if (B > 65535 || (reinterpret_cast<uintptr_t>(src) & 3) != 0) return -2;
+  if (in_h > src_h || in_w > src_w || (dst == nullptr) == (dst_u8 == nullptr)) return -2;
+  if (!win_xy && (in_h != src_h || in_w != src_w)) return -2;
   const ImgPlan& p = get_plan(in_h, in_w, out_h, out_w);
   TileCfg t;
   if (!pick_tile(p, out_h, out_w, ch, &t)) return -7;
   ImgArgs a;
-  a.src = src; a.src_end = src + (size_t)B * in_h * in_w * ch; a.mirror = mirror; a.dst = dst;
+  a.src = src; a.src_end = src + (size_t)B * src_h * src_w * ch; a.mirror = mirror; a.dst = dst; a.dst_u8 = dst_u8;
+  a.win_xy = win_xy; a.src_pitch = src_w * ch; a.img_stride = (long long)src_h * src_w * ch;
   const int* d = static_cast<const int*>(plan_dev);
   a.bx = d; d += p.bx.size();
   a.kx = d; d += p.kx.size();

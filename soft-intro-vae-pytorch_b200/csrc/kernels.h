@@ -199,7 +199,10 @@ namespace sivae {
 int resample_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk);   // returns ksize
 size_t image_plan_bytes(int in_h, int in_w, int out_h, int out_w);
 int image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, cudaStream_t st);
+// src [B][src_h][src_w][ch]; the in_h x in_w window at win_xy[b] (nullable: whole image) is mirrored (flag) and resized to
+// out_h x out_w; writes dst (float32 NCHW = ToTensor) or dst_u8 (8-bit NHWC), exactly one non-null
 int launch_image_batch(const unsigned char* src, const unsigned char* mirror, int B, int in_h, int in_w, int ch, int out_h,
-                       int out_w, const void* plan_dev, float* dst, cudaStream_t st);
+                       int out_w, const void* plan_dev, float* dst, cudaStream_t st, int src_h = 0, int src_w = 0,
+                       const int* win_xy = nullptr, unsigned char* dst_u8 = nullptr);
 
 }  // namespace sivae

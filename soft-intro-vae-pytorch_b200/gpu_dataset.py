@@ -10,9 +10,11 @@ bicubic resize and ToTensor run for the whole batch in one CUDA kernel (``csrc/i
 ``sivae_image_batch_u8``), bit-exact with Pillow's fixed-point resampler and therefore with the tensor the reference's
 dataset returns (``tests/test_gpu_image.py``; oracle pinned in ``tests/test_image_oracle.py``).
 
-Same constructor signature as the reference class.  Supported: what the image configs pass
-(train_soft_intro_vae.py:388-392, 400-404, 415-417): ``input_height=None, crop_height=None``.  The two-stage resize and
-the crops of ``load_image`` raise ``NotImplementedError`` -- there is no CPU fallback on this path.
+Same constructor signature as the reference class, and all of ``load_image`` (dataset.py:12-47): what the image configs pass
+(train_soft_intro_vae.py:388-392, 400-404, 415-417: ``input_height=None, crop_height=None``) is ONE kernel launch per batch;
+``input_height`` (two-stage resize, :29-30) adds a first launch that writes the 8-bit intermediate image, ``crop_height``
+(random / centre ``ImageOps.crop``, :32-44) makes the last resize read a per-image window -- the random crop draws cx1, cy1
+from Python's ``random`` stream right after the mirror coin, as the reference does.  There is no CPU fallback on this path.
 """
 import ctypes as C
 import os
@@ -63,8 +65,11 @@ class ImageBatcher:
             self._plans[key] = p
         return p
 
-    def __call__(self, images_u8, mirror=None, out=None):
-        """images_u8: uint8 [B,H,W,C] (host or device); mirror: [B] flags or None -> float32 [B,C,out_h,out_w] on device"""
+    def __call__(self, images_u8, mirror=None, out=None, window=None, origins=None, as_u8=False):
+        """images_u8: uint8 [B,H,W,C] (host or device); mirror: [B] flags or None -> float32 [B,C,out_h,out_w] on device.
+        window = (win_h, win_w) + origins = int [B,2] (x, y): resize only that window of every image (ImageOps.crop,
+        dataset.py:32-44; the mirror flag then mirrors the WINDOW).  as_u8: return the resized 8-bit image itself, uint8
+        [B,out_h,out_w,C] (first stage of the two-stage resize, :29-30) instead of its ToTensor."""
         if images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
             raise ValueError("expected a uint8 [B,H,W,C] batch of decoded images")
         B, H, W, ch = images_u8.shape
@@ -73,26 +78,101 @@ class ImageBatcher:
         if mirror is not None:
             flags = torch.as_tensor(mirror).to(dtype=torch.uint8).to(self.device, non_blocking=True).contiguous()
         if out is None:
-            out = torch.empty(B, ch, self.out_h, self.out_w, dtype=torch.float32, device=self.device)
-        plan = self._plan(H, W)
+            out = (torch.empty(B, self.out_h, self.out_w, ch, dtype=torch.uint8, device=self.device) if as_u8 else
+                   torch.empty(B, ch, self.out_h, self.out_w, dtype=torch.float32, device=self.device))
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if window is None and not as_u8:
+            plan = self._plan(H, W)
+            with torch.cuda.device(self.device):
+                L.check(L.load().sivae_image_batch_u8(L.ptr(src), L.ptr(flags), B, H, W, ch, self.out_h, self.out_w, L.ptr(plan),
+                                                      L.ptr(out), stream), "sivae_image_batch_u8")
+            return out
+        wh, ww = (H, W) if window is None else (int(window[0]), int(window[1]))
+        xy = None
+        if window is not None:
+            o = torch.as_tensor(origins, dtype=torch.int32).reshape(B, 2)
+            if int(o.min()) < 0 or int(o[:, 0].max()) + ww > W or int(o[:, 1].max()) + wh > H:
+                raise ValueError("crop window outside the image")
+            xy = o.to(self.device, non_blocking=True).contiguous()
+        plan = self._plan(wh, ww)
         with torch.cuda.device(self.device):
-            L.check(L.load().sivae_image_batch_u8(L.ptr(src), L.ptr(flags), B, H, W, ch, self.out_h, self.out_w, L.ptr(plan),
-                                                  L.ptr(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
-                    "sivae_image_batch_u8")
+            L.check(L.load().sivae_image_batch_u8_ex(L.ptr(src), L.ptr(flags), L.ptr(xy), B, H, W, ch, wh, ww, self.out_h, self.out_w,
+                                                     L.ptr(plan), None if as_u8 else L.ptr(out), L.ptr(out) if as_u8 else None, stream),
+                    "sivae_image_batch_u8_ex")
         return out
 
 
+def _crop_margins(w, h, crop_w, crop_h, is_random_crop):
+    """dataset.py:32-43: borders (left, top, right, bottom) that ImageOps.crop removes; a random crop draws cx1 then cy1"""
+    if is_random_crop:
+        cx1 = random.randint(0, w - crop_w)
+        cx2 = w - crop_w - cx1
+        cy1 = random.randint(0, h - crop_h)
+        cy2 = h - crop_h - cy1
+    else:
+        cx2 = cx1 = int(round((w - crop_w) / 2.))
+        cy2 = cy1 = int(round((h - crop_h) / 2.))
+    return cx1, cy1, cx2, cy2
+
+
+class LoadSpec:
+    """the geometry arguments of load_image (dataset.py:12-19 incl. the width defaults) + the per-image random draws"""
+
+    def __init__(self, input_height, input_width, output_height, output_width, crop_height, crop_width, is_random_crop, is_mirror):
+        self.input_height = input_height
+        self.input_width = input_width if input_width is not None else input_height
+        self.output_height = output_height
+        self.output_width = output_width if output_width is not None else output_height
+        self.crop_height = crop_height
+        self.crop_width = crop_width if crop_width is not None else crop_height
+        self.is_random_crop, self.is_mirror = is_random_crop, is_mirror
+
+    def draw(self, h, w):
+        """-> (mirror flag, (left, top, right, bottom) borders or None) for a decoded image of h x w pixels, consuming Python's
+        `random` stream in load_image's order: mirror coin (:26), then the crop offsets (:35-38)"""
+        mirror = 1 if (self.is_mirror and random.randint(0, 1) == 0) else 0
+        margins = None
+        if self.crop_height is not None:
+            if self.input_height is not None:
+                h, w = self.input_height, self.input_width
+            margins = _crop_margins(w, h, self.crop_width, self.crop_height, self.is_random_crop)
+        return mirror, margins
+
+    def assemble(self, batchers, images_u8, mirror, margins, as_u8=False):
+        """batch of same-sized decoded images -> float32 [B,C,oh,ow] on the device (uint8 [B,oh,ow,C] with as_u8).
+        batchers: dict cache of ImageBatcher per output size."""
+        def bt(h, w):
+            key = (int(h), int(w))
+            if key not in batchers:
+                batchers[key] = ImageBatcher(h, w, batchers["device"])
+            return batchers[key]
+        x, flags = images_u8, mirror
+        if self.input_height is not None:                            # :29-30 -- the mirror (:26-27) happens before it
+            x = bt(self.input_height, self.input_width)(x, flags, as_u8=True)
+            flags = None
+        last = bt(self.output_height, self.output_width)
+        if margins is None:
+            return last(x, flags, as_u8=as_u8)
+        m = torch.as_tensor(margins, dtype=torch.int64).reshape(-1, 4)
+        H, W = x.shape[1], x.shape[2]
+        wh, ww = H - int(m[0, 1]) - int(m[0, 3]), W - int(m[0, 0]) - int(m[0, 2])
+        if not (bool((H - m[:, 1] - m[:, 3] == wh).all()) and bool((W - m[:, 0] - m[:, 2] == ww).all())):
+            raise ValueError("images of one group must share the crop size")
+        left = m[:, 0].clone()
+        if flags is not None:                                        # crop of the MIRRORED image = mirrored window whose
+            f = torch.as_tensor(flags).to(torch.bool).cpu()          # left border is the right border of the crop
+            left[f] = m[:, 2][f]
+        return last(x, flags, window=(wh, ww), origins=torch.stack([left, m[:, 1]], 1), as_u8=as_u8)
+
+
 class ImageDatasetFromFile(data.Dataset):
-    """Reference signature (dataset.py:50-53).  __getitem__ -> (uint8 [H,W,C] decoded pixels, mirror flag): the rest of
-    load_image + ToTensor happens per batch on the GPU (ImageBatcher / GpuImageLoader)."""
+    """Reference signature (dataset.py:50-53).  __getitem__ -> (uint8 [H,W,C] decoded pixels, mirror flag, crop borders): the
+    rest of load_image + ToTensor happens per batch on the GPU (LoadSpec.assemble / GpuImageLoader)."""
 
     def __init__(self, image_list, root_path,
                  input_height=128, input_width=None, output_height=128, output_width=None,
                  crop_height=None, crop_width=None, is_random_crop=False, is_mirror=True, is_gray=False):
         super(ImageDatasetFromFile, self).__init__()
-        if input_height is not None or input_width is not None or crop_height is not None or crop_width is not None:
-            raise NotImplementedError("GPU batch assembly covers input_height=None, crop_height=None (what the image "
-                                      "configs pass); the two-stage resize / crops of load_image are not implemented")
         self.image_filenames = image_list
         self.is_random_crop = is_random_crop
         self.is_mirror = is_mirror
@@ -104,25 +184,35 @@ class ImageDatasetFromFile(data.Dataset):
         self.crop_height = crop_height
         self.crop_width = crop_width
         self.is_gray = is_gray
+        self.spec = LoadSpec(input_height, input_width, output_height, output_width, crop_height, crop_width, is_random_crop,
+                             is_mirror)
 
     def __getitem__(self, index):
         a = decode_image(os.path.join(self.root_path, self.image_filenames[index]), self.is_gray)
-        mirror = 1 if (self.is_mirror and random.randint(0, 1) == 0) else 0      # dataset.py:26, same draw
-        return torch.from_numpy(a), mirror
+        mirror, margins = self.spec.draw(a.shape[0], a.shape[1])               # dataset.py:26, :35-38: same draws, same order
+        if margins is None:
+            return torch.from_numpy(a), mirror
+        return torch.from_numpy(a), mirror, margins
 
     def __len__(self):
         return len(self.image_filenames)
 
 
 def collate_decoded(samples):
-    """-> list of (indices, uint8 [b,H,W,C], flags [b]) groups, one per source geometry (usually exactly one)"""
+    """-> list of (indices, uint8 [b,H,W,C], flags [b], borders [b,4] or None) groups, one per source geometry and crop size
+    (usually exactly one)"""
     groups = {}
-    for i, (img, flag) in enumerate(samples):
-        groups.setdefault(tuple(img.shape), []).append((i, img, flag))
+    for i, smp in enumerate(samples):
+        img, flag = smp[0], smp[1]
+        m = smp[2] if len(smp) > 2 else None
+        key = tuple(img.shape) + ((m[0] + m[2], m[1] + m[3]) if m is not None else ())
+        groups.setdefault(key, []).append((i, img, flag, m))
     out = []
     for items in groups.values():
-        idx = torch.tensor([i for i, _, _ in items], dtype=torch.long)
-        out.append((idx, torch.stack([im for _, im, _ in items]), torch.tensor([f for _, _, f in items], dtype=torch.uint8)))
+        idx = torch.tensor([i for i, _, _, _ in items], dtype=torch.long)
+        borders = None if items[0][3] is None else torch.tensor([list(m) for _, _, _, m in items], dtype=torch.int64)
+        out.append((idx, torch.stack([im for _, im, _, _ in items]), torch.tensor([f for _, _, f, _ in items], dtype=torch.uint8),
+                    borders))
     return out
 
 
@@ -133,7 +223,10 @@ class GpuImageLoader:
     def __init__(self, loader, device):
         self.loader = loader
         ds = loader.dataset
+        self.spec = ds.spec
+        self.batchers = {"device": torch.device(device)}
         self.batcher = ImageBatcher(ds.output_height, ds.output_width, device)
+        self.batchers[(int(ds.output_height), int(ds.output_width))] = self.batcher
         self.dataset, self.batch_size = ds, loader.batch_size
 
     def __len__(self):
@@ -142,25 +235,24 @@ class GpuImageLoader:
     def __iter__(self):
         for groups in self.loader:
             if len(groups) == 1:
-                yield self.batcher(groups[0][1], groups[0][2])
+                yield self.spec.assemble(self.batchers, groups[0][1], groups[0][2], groups[0][3])
                 continue
             n = sum(g[0].numel() for g in groups)
             ch = groups[0][1].shape[-1]
             out = torch.empty(n, ch, self.batcher.out_h, self.batcher.out_w, dtype=torch.float32, device=self.batcher.device)
-            for idx, imgs, flags in groups:
-                out[idx.to(out.device)] = self.batcher(imgs, flags)
+            for idx, imgs, flags, borders in groups:
+                out[idx.to(out.device)] = self.spec.assemble(self.batchers, imgs, flags, borders)
             yield out
 
 
 def load_image(file_path, input_height=128, input_width=None, output_height=128, output_width=None,
                crop_height=None, crop_width=None, is_random_crop=True, is_mirror=True, is_gray=False, device="cuda:0"):
     """Reference signature (dataset.py:12-13) for single images; returns the PIL image the reference returns, computed on
-    the GPU.  Only the configuration the image configs use (input_height=None, crop_height=None) is implemented."""
+    the GPU (same draws from Python's `random`, same pixels)."""
     from PIL import Image
-    if input_height is not None or crop_height is not None:
-        raise NotImplementedError("load_image on the GPU path: input_height=None and crop_height=None only")
     a = decode_image(file_path, is_gray)
-    mirror = 1 if (is_mirror and random.randint(0, 1) == 0) else 0
-    t = ImageBatcher(output_height, output_width, device)(torch.from_numpy(a)[None], [mirror])[0]
-    u8 = torch.round(t * 255.0).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+    spec = LoadSpec(input_height, input_width, output_height, output_width, crop_height, crop_width, is_random_crop, is_mirror)
+    mirror, margins = spec.draw(a.shape[0], a.shape[1])
+    u8 = spec.assemble({"device": torch.device(device)}, torch.from_numpy(a)[None], [mirror],
+                       None if margins is None else [list(margins)], as_u8=True)[0].cpu().numpy()
     return Image.fromarray(u8[:, :, 0], 'L') if u8.shape[2] == 1 else Image.fromarray(u8, 'RGB')

@@ -73,6 +73,69 @@ def test_full_size_properties():
     assert np.array_equal(ident, (src[:2].astype(np.float32) / np.float32(255)).transpose(0, 3, 1, 2))
 
 
+GOLD_CROP = os.path.join(ROOT, "tests", "golden", "image_pipeline_crop.npz")
+
+
+def test_load_image_branches_vs_reference_golden(tmp_path):
+    """two-stage resize (dataset.py:29-30), random / centre crops (:32-44), grey images: files -> ImageDatasetFromFile with those
+    arguments -> GpuImageLoader == the tensors the UNMODIFIED reference dataset returned for the same `random` seed
+    (tests/golden/image_pipeline_crop.npz, oracle/make_image_golden.py --crop), bit for bit; load_image() returns the same
+    PIL image the reference's does"""
+    from PIL import Image
+    M = _mod()
+    z = np.load(GOLD_CROP)
+    for name in sorted({k.split("/")[0] for k in z.files}):
+        src, out_u8 = z[name + "/src"], z[name + "/out_u8"]
+        ih, iw, ch, cw, oh, ow, rnd, gray = (int(v) for v in z[name + "/args"])
+        names = []
+        for i, a in enumerate(src):
+            names.append("%s_%d.png" % (name, i))
+            Image.fromarray(a, "RGB").save(tmp_path / names[-1])
+        kw = dict(input_height=ih if ih > 0 else None, input_width=iw if iw > 0 else None, output_height=oh, output_width=ow,
+                  crop_height=ch if ch > 0 else None, crop_width=cw if cw > 0 else None, is_random_crop=bool(rnd), is_mirror=True,
+                  is_gray=bool(gray))
+        ds = M.ImageDatasetFromFile(names, str(tmp_path), **kw)
+        loader = M.GpuImageLoader(torch.utils.data.DataLoader(ds, batch_size=len(names), shuffle=False, num_workers=0,
+                                                              collate_fn=M.collate_decoded), "cuda:0")
+        random.seed(4321)
+        (got,) = list(loader)
+        assert got.is_cuda and np.array_equal(got.cpu().numpy(), out_u8.astype(np.float32) / np.float32(255.0)), name
+        random.seed(4321)
+        im = M.load_image(str(tmp_path / names[0]), **kw)
+        a0 = np.asarray(im)
+        a0 = a0[..., None] if a0.ndim == 2 else a0
+        assert np.array_equal(a0.transpose(2, 0, 1), out_u8[0]), name
+
+
+@pytest.mark.parametrize("ch", [3, 1])
+def test_window_and_u8_output_match_oracle(ch):
+    """the two generalisations of the kernel behind those branches, directly: per-image crop windows (corners, unaligned
+    origins, windows as large as the image) with and without mirroring, and the 8-bit NHWC output"""
+    rng = np.random.default_rng(77 + ch)
+    B, H, W = 6, 53, 71
+    src = rng.integers(0, 256, (B, H, W, ch), dtype=np.uint8)
+    src[:, :20, :30] = 255
+    src[:, 30:, 40:] = 0
+    wh, ww, oh, ow = 31, 45, 24, 56
+    origins = np.array([[0, 0], [W - ww, H - wh], [1, 2], [13, 7], [W - ww, 0], [3, H - wh]], dtype=np.int32)
+    mirror = np.array([0, 1, 1, 0, 1, 0], dtype=np.uint8)
+    bt = _mod().ImageBatcher(oh, ow, "cuda:0")
+    want_u8 = np.stack([IO.resize_bicubic_u8(np.ascontiguousarray(
+        (src[i, y:y + wh, x:x + ww][:, ::-1] if mirror[i] else src[i, y:y + wh, x:x + ww])), oh, ow)
+        for i, (x, y) in enumerate(origins)])
+    got = bt(torch.from_numpy(src), torch.from_numpy(mirror), window=(wh, ww), origins=torch.from_numpy(origins)).cpu().numpy()
+    assert np.array_equal(got, np.stack([IO.to_tensor(w) for w in want_u8]))
+    got8 = bt(torch.from_numpy(src), torch.from_numpy(mirror), window=(wh, ww), origins=torch.from_numpy(origins), as_u8=True)
+    assert got8.dtype == torch.uint8 and tuple(got8.shape) == (B, oh, ow, ch) and np.array_equal(got8.cpu().numpy(), want_u8)
+    # whole image as the window == the plain call; u8 output of the plain geometry
+    full = bt(torch.from_numpy(src), torch.from_numpy(mirror), window=(H, W), origins=np.zeros((B, 2), np.int32)).cpu().numpy()
+    assert np.array_equal(full, IO.batch(src, mirror, oh, ow))
+    full8 = bt(torch.from_numpy(src), torch.from_numpy(mirror), as_u8=True).cpu().numpy()
+    assert np.array_equal(full8, np.stack([IO.load_image_u8(src[i], bool(mirror[i]), oh, ow) for i in range(B)]))
+    with pytest.raises(ValueError, match="outside"):
+        bt(torch.from_numpy(src), None, window=(wh, ww), origins=np.array([[W - ww + 1, 0]] * B, np.int32))
+
+
 def test_downscale_beyond_staging_capacity_fails_loudly():
     src = torch.zeros(1, 4096, 8, 3, dtype=torch.uint8)
     with pytest.raises(RuntimeError, match="down-scaling factor too large"):

@@ -50,6 +50,60 @@ def test_oracle_matches_pillow(shape, ch):
         assert np.array_equal(got, (ref.astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1))
 
 
+GOLD_CROP = os.path.join(ROOT, "tests", "golden", "image_pipeline_crop.npz")
+
+
+def crop_cases():
+    """(name, src [n,H,W,3], mirror [n], margins [n,4], out_u8 [n,C,oh,ow], args) recorded from the unmodified reference
+    ImageDatasetFromFile with input_height / crop_* / is_random_crop / is_gray set (oracle/make_image_golden.py --crop)"""
+    z = np.load(GOLD_CROP)
+    out = []
+    for n in sorted({k.split("/")[0] for k in z.files}):
+        ih, iw, ch, cw, oh, ow, rnd, gray = (int(v) for v in z[n + "/args"])
+        out.append((n, z[n + "/src"], z[n + "/mirror"], z[n + "/margins"], z[n + "/out_u8"],
+                    dict(input_hw=(ih, iw) if ih > 0 else None, crop=(ch, cw) if ch > 0 else None, out_hw=(oh, ow),
+                         is_random_crop=bool(rnd), is_gray=bool(gray))))
+    return out
+
+
+def _gray(a):
+    from PIL import Image
+    return np.asarray(Image.fromarray(a, "RGB").convert("L"))[..., None]
+
+
+def test_oracle_load_image_branches_match_reference_golden():
+    """two-stage resize (dataset.py:29-30), random / centre ImageOps.crop (:32-44), grey conversion: the oracle's load_image_u8
+    on the recorded source pixels, mirror coins and crop margins == the tensors the unmodified reference dataset returned"""
+    cases = crop_cases()
+    assert len(cases) == 6 and any(c[5]["is_random_crop"] for c in cases) and any(c[5]["is_gray"] for c in cases)
+    for name, src, mirror, margins, out_u8, a in cases:
+        for i in range(len(src)):
+            img = _gray(src[i]) if a["is_gray"] else src[i]
+            got = IO.load_image_u8(img, bool(mirror[i]), a["out_hw"][0], a["out_hw"][1], input_hw=a["input_hw"],
+                                   margins=margins[i] if a["crop"] else None)
+            assert np.array_equal(got.transpose(2, 0, 1), out_u8[i]), (name, i)
+            assert np.array_equal(IO.to_tensor(got), out_u8[i].astype(np.float32) / np.float32(255.0))
+    # the centre crop keeps w - 2 round((w - crop) / 2) columns: 61 rows, crop 48 -> round(6.5) = 6 (banker's) -> 49 rows
+    n, _, _, margins, _, a = [c for c in cases if c[0] == "center_crop_odd"][0]
+    assert tuple(margins[0]) == (8, 6, 8, 6)
+
+
+def test_oracle_crop_margins_replay_the_reference_draws():
+    """IO.crop_margins consumes Python's `random` exactly like dataset.py:35-38 (after the mirror coin of :26)"""
+    import random
+    for name, src, mirror, margins, _, a in crop_cases():
+        if not a["crop"]:
+            continue
+        random.seed(4321)
+        h, w = src.shape[1:3]
+        if a["input_hw"]:
+            h, w = a["input_hw"]
+        for i in range(len(src)):
+            flag = 1 if random.randint(0, 1) == 0 else 0
+            m = IO.crop_margins(w, h, a["crop"][1], a["crop"][0], a["is_random_crop"], random)
+            assert flag == int(mirror[i]) and tuple(m) == tuple(int(v) for v in margins[i]), (name, i)
+
+
 @pytest.mark.parametrize("sizes", [(1024, 256), (178, 256), (218, 256), (256, 256), (37, 64), (300, 7), (5, 64), (1, 4), (1000, 33)])
 def test_cabi_coefficients_match_oracle(sizes):
     """sivae_resample_coeffs is host-only arithmetic (IEEE doubles in Pillow's operation order): runs without a GPU"""
@@ -89,7 +143,34 @@ def test_dataset_decodes_and_draws_the_mirror_coin_like_the_reference(tmp_path):
         assert img.dtype == torch.uint8 and np.array_equal(img.numpy(), a)
     groups = M.collate_decoded(items)
     assert len(groups) == 1 and groups[0][1].shape == src.shape and groups[0][2].tolist() == [int(m) for m in mirror]
-    with pytest.raises(NotImplementedError):
-        M.ImageDatasetFromFile(names, str(tmp_path), input_height=128)          # two-stage resize: not on this path
     with pytest.raises(RuntimeError):
         M.ImageBatcher(24, 24, "cpu")                                           # no CPU fallback
+
+
+def test_dataset_draws_crop_offsets_like_the_reference(tmp_path):
+    """host half of the crop / two-stage branches: per item the mirror coin and then cx1, cy1 of a random crop come out of
+    Python's `random` stream exactly as in the unmodified reference run that recorded the golden (dataset.py:26, :35-38)"""
+    import random
+
+    from PIL import Image
+    M = importlib.import_module(PKG + ".gpu_dataset")
+    for name, src, mirror, margins, _, a in crop_cases():
+        names = []
+        for i, im in enumerate(src):
+            names.append("%s_%d.png" % (name, i))
+            Image.fromarray(im, "RGB").save(tmp_path / names[-1])
+        kw = dict(input_height=a["input_hw"][0] if a["input_hw"] else None, input_width=a["input_hw"][1] if a["input_hw"] else None,
+                  output_height=a["out_hw"][0], output_width=a["out_hw"][1], crop_height=a["crop"][0] if a["crop"] else None,
+                  crop_width=a["crop"][1] if a["crop"] else None, is_random_crop=a["is_random_crop"], is_mirror=True,
+                  is_gray=a["is_gray"])
+        ds = M.ImageDatasetFromFile(names, str(tmp_path), **kw)
+        random.seed(4321)
+        items = [ds[i] for i in range(len(ds))]
+        assert [it[1] for it in items] == [int(m) for m in mirror], name
+        if a["crop"]:
+            assert [tuple(it[2]) for it in items] == [tuple(int(v) for v in m) for m in margins], name
+        else:
+            assert all(len(it) == 2 for it in items)
+        assert items[0][0].shape[2] == (1 if a["is_gray"] else 3)
+        groups = M.collate_decoded(items)
+        assert sum(g[0].numel() for g in groups) == len(items)
