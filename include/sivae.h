@@ -264,6 +264,19 @@ int sivae_image_batch_u8_ex(const unsigned char* src_hwc, const unsigned char* m
                             int src_w, int channels, int win_h, int win_w, int out_h, int out_w, const void* plan_dev,
                             float* out_nchw, unsigned char* out_u8_hwc, void* stream);
 
+/* RGB JPEG files (dataset.py:20-24: Image.open(file), mode RGB) decoded by nvJPEG -- the CUDA toolkit's LIBRARY,
+   resolved at run time with dlopen("libnvjpeg.so.12") (SIVAE_NVJPEG_LIB overrides) -- straight into the device batch
+   [B,height,width,3] that sivae_image_batch_u8 reads: Huffman decoding on the host inside nvJPEG,
+   IDCT / chroma upsampling / colour conversion on the GPU in stream order; returns after the stream has consumed the
+   compressed bytes.  data[i] / lengths[i]: HOST pointers and sizes of the compressed files, all of the same height x width.
+   OPT-IN and NOT bit-exact with the reference: Pillow decodes with libjpeg-turbo, whose IDCT / colour rounding and "fancy"
+   4:2:0 chroma upsampling differ from nvJPEG's by a few grey levels; the default loader therefore decodes with Pillow on the host.
+   Grey / CMYK files and is_gray data sets stay on the Pillow path.
+   -9: nvJPEG unavailable; -8: not a 3-component JPEG nvJPEG decodes, or size mismatch.  sivae_jpeg_info: header only. */
+int sivae_jpeg_info(const unsigned char* data, long long length, int* height, int* width, int* components);
+int sivae_jpeg_decode_batch(const unsigned char* const* data, const long long* lengths, int batch, int height, int width,
+                            unsigned char* out_hwc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ using namespace sivae;
 
 static thread_local std::string g_err;
 extern "C" const char* sivae_last_error(void) { return g_err.c_str(); }
-extern "C" int sivae_version(void) { return 100; }
+extern "C" int sivae_version(void) { return 200; }   // round 2: sivae_config grew (cond_dim), new entry points
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -1785,5 +1785,22 @@ extern "C" int sivae_image_batch_u8_ex(const unsigned char* src_hwc, const unsig
                                "source, exactly one output)");
   if (r == -7) return fail(-7, "down-scaling factor too large for the shared-memory staging of the resize kernel");
   if (r) return fail(r, cudaGetErrorString((cudaError_t)r));
+  return 0;
+}
+
+// ---- JPEG decode in front of the batch-assembly kernel (jpeg.cu): nvJPEG, opt-in ------------------------------------
+extern "C" int sivae_jpeg_info(const unsigned char* data, long long length, int* height, int* width, int* components) {
+  if (!data || length <= 0 || !height || !width || !components) return fail(-1, "null argument");
+  std::string msg;
+  int r = jpeg_info(data, length, height, width, components, &msg);
+  if (r) return fail(r, msg);
+  return 0;
+}
+extern "C" int sivae_jpeg_decode_batch(const unsigned char* const* data, const long long* lengths, int batch, int height, int width,
+                                       unsigned char* out_hwc, void* stream) {
+  if (!data || !lengths || !out_hwc || batch < 1 || height < 1 || width < 1) return fail(-1, "null / empty argument");
+  std::string msg;
+  int r = jpeg_decode_batch(data, lengths, batch, height, width, out_hwc, (cudaStream_t)stream, &msg);
+  if (r) return fail(r, msg);
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
+#include <string>
 
 namespace sivae {
 
@@ -193,6 +194,11 @@ void launch_adam(float* p, const float* g, float* m, float* v, long long n, floa
                  float b1, float b2, float eps, long long* step_dev, float* coef_dev, cudaStream_t st);
 
 // ---------------- image batch assembly (image.cu): mirror + Pillow-exact bicubic resize + ToTensor ----------------
+
+// ---------------- JPEG decode through nvJPEG (jpeg.cu; opt-in, not bit-exact with Pillow) ----------------
+int jpeg_decode_batch(const unsigned char* const* data, const long long* lengths, int batch, int height, int width,
+                      unsigned char* out_hwc, cudaStream_t st, std::string* msg);
+int jpeg_info(const unsigned char* data, long long length, int* height, int* width, int* components, std::string* msg);
 }  // namespace sivae
 #include <vector>
 namespace sivae {
@@ -204,5 +210,10 @@ int image_plan_init(int in_h, int in_w, int out_h, int out_w, void* plan_dev, cu
 int launch_image_batch(const unsigned char* src, const unsigned char* mirror, int B, int in_h, int in_w, int ch, int out_h,
                        int out_w, const void* plan_dev, float* dst, cudaStream_t st, int src_h = 0, int src_w = 0,
                        const int* win_xy = nullptr, unsigned char* dst_u8 = nullptr);
+
+// ---------------- JPEG decode through nvJPEG (jpeg.cu; opt-in, not bit-exact with Pillow) ----------------
+int jpeg_decode_batch(const unsigned char* const* data, const long long* lengths, int batch, int height, int width,
+                      unsigned char* out_hwc, cudaStream_t st, std::string* msg);
+int jpeg_info(const unsigned char* data, long long length, int* height, int* width, int* components, std::string* msg);
 
 }  // namespace sivae

@@ -27,6 +27,62 @@ import torch.utils.data as data
 from . import lib as L
 
 
+class EncodedJpeg:
+    """a JPEG file kept COMPRESSED by the dataset (SIVAE_GPU_JPEG=1): `data` = its bytes (1-D uint8 tensor), `shape` = the
+    (H, W, C) its decoded pixels will have.  Decoded per batch on the GPU by nvJPEG (decode_jpeg_batch)."""
+    __slots__ = ("data", "shape")
+
+    def __init__(self, data, shape):
+        self.data, self.shape = data, tuple(int(v) for v in shape)
+
+
+class EncodedBatch:
+    """same-sized EncodedJpeg items of one collated group"""
+    __slots__ = ("datas", "shape")
+
+    def __init__(self, datas, shape):
+        self.datas, self.shape = list(datas), tuple(shape)
+
+
+def gpu_jpeg_enabled():
+    """opt-in: JPEG files are decoded on the GPU by nvJPEG instead of by Pillow on the host.  NOT bit-exact with the reference's
+    loader (libjpeg-turbo and nvJPEG round the IDCT / colour conversion differently and up-sample 4:2:0 chroma differently; a few
+    grey levels) -- hence off by default."""
+    return os.environ.get("SIVAE_GPU_JPEG", "0") == "1"
+
+
+def encoded_jpeg(file_path, is_gray=False):
+    """-> EncodedJpeg if `file_path` is an RGB JPEG wanted as RGB (the `Image.open` of dataset.py:20-24 without a mode
+    conversion), else None: grey / CMYK files and is_gray data sets stay with Pillow.  Reads only the header."""
+    if is_gray or not file_path.lower().endswith((".jpg", ".jpeg")):
+        return None
+    from PIL import Image
+    with Image.open(file_path) as im:
+        if im.format != "JPEG" or im.mode != "RGB":
+            return None
+        w, h = im.size
+    return EncodedJpeg(torch.from_numpy(np.fromfile(file_path, dtype=np.uint8)), (h, w, 3))
+
+
+def decode_jpeg_batch(datas, shape, device):
+    """compressed JPEG files (1-D uint8 host tensors) of one size -> uint8 [B,H,W,C] on `device` (sivae_jpeg_decode_batch)"""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("decode_jpeg_batch runs on CUDA devices only; got %s" % (device,))
+    h, w, ch = shape
+    if ch != 3:
+        raise ValueError("decode_jpeg_batch decodes RGB JPEG files to [B,H,W,3]")
+    B = len(datas)
+    datas = [d.contiguous() for d in datas]
+    out = torch.empty(B, h, w, ch, dtype=torch.uint8, device=device)
+    ptrs = (C.c_void_p * B)(*[d.data_ptr() for d in datas])
+    lens = (C.c_longlong * B)(*[d.numel() for d in datas])
+    with torch.cuda.device(device):
+        L.check(L.load().sivae_jpeg_decode_batch(ptrs, lens, B, h, w, L.ptr(out),
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sivae_jpeg_decode_batch")
+    return out
+
+
 def decode_image(file_path, is_gray=False):
     """dataset.py:20-24: Image.open + mode conversion -> uint8 [H,W,C] (C = 3, or 1 for is_gray)"""
     from PIL import Image
@@ -188,11 +244,14 @@ class ImageDatasetFromFile(data.Dataset):
                              is_mirror)
 
     def __getitem__(self, index):
-        a = decode_image(os.path.join(self.root_path, self.image_filenames[index]), self.is_gray)
-        mirror, margins = self.spec.draw(a.shape[0], a.shape[1])               # dataset.py:26, :35-38: same draws, same order
+        path = os.path.join(self.root_path, self.image_filenames[index])
+        img = encoded_jpeg(path, self.is_gray) if gpu_jpeg_enabled() else None      # opt-in: stays compressed until the GPU
+        if img is None:
+            img = torch.from_numpy(decode_image(path, self.is_gray))
+        mirror, margins = self.spec.draw(img.shape[0], img.shape[1])           # dataset.py:26, :35-38: same draws, same order
         if margins is None:
-            return torch.from_numpy(a), mirror
-        return torch.from_numpy(a), mirror, margins
+            return img, mirror
+        return img, mirror, margins
 
     def __len__(self):
         return len(self.image_filenames)
@@ -205,14 +264,17 @@ def collate_decoded(samples):
     for i, smp in enumerate(samples):
         img, flag = smp[0], smp[1]
         m = smp[2] if len(smp) > 2 else None
-        key = tuple(img.shape) + ((m[0] + m[2], m[1] + m[3]) if m is not None else ())
+        key = (isinstance(img, EncodedJpeg),) + tuple(img.shape) + ((m[0] + m[2], m[1] + m[3]) if m is not None else ())
         groups.setdefault(key, []).append((i, img, flag, m))
     out = []
     for items in groups.values():
         idx = torch.tensor([i for i, _, _, _ in items], dtype=torch.long)
         borders = None if items[0][3] is None else torch.tensor([list(m) for _, _, _, m in items], dtype=torch.int64)
-        out.append((idx, torch.stack([im for _, im, _, _ in items]), torch.tensor([f for _, _, f, _ in items], dtype=torch.uint8),
-                    borders))
+        if isinstance(items[0][1], EncodedJpeg):
+            imgs = EncodedBatch([im.data for _, im, _, _ in items], items[0][1].shape)
+        else:
+            imgs = torch.stack([im for _, im, _, _ in items])
+        out.append((idx, imgs, torch.tensor([f for _, _, f, _ in items], dtype=torch.uint8), borders))
     return out
 
 
@@ -232,16 +294,20 @@ class GpuImageLoader:
     def __len__(self):
         return len(self.loader)
 
+    def _pixels(self, imgs):
+        """decoded uint8 [b,H,W,C] pixels of a group (compressed groups: nvJPEG on the device)"""
+        return decode_jpeg_batch(imgs.datas, imgs.shape, self.batcher.device) if isinstance(imgs, EncodedBatch) else imgs
+
     def __iter__(self):
         for groups in self.loader:
             if len(groups) == 1:
-                yield self.spec.assemble(self.batchers, groups[0][1], groups[0][2], groups[0][3])
+                yield self.spec.assemble(self.batchers, self._pixels(groups[0][1]), groups[0][2], groups[0][3])
                 continue
             n = sum(g[0].numel() for g in groups)
             ch = groups[0][1].shape[-1]
             out = torch.empty(n, ch, self.batcher.out_h, self.batcher.out_w, dtype=torch.float32, device=self.batcher.device)
             for idx, imgs, flags, borders in groups:
-                out[idx.to(out.device)] = self.spec.assemble(self.batchers, imgs, flags, borders)
+                out[idx.to(out.device)] = self.spec.assemble(self.batchers, self._pixels(imgs), flags, borders)
             yield out
 
 

@@ -97,6 +97,8 @@ _SIGS = {
     "sivae_image_plan_init": (C.c_int, [C.c_int] * 4 + [_P, C.c_longlong, _P]),
     "sivae_image_batch_u8": (C.c_int, [_P, _P] + [C.c_int] * 6 + [_P, _P, _P]),
     "sivae_image_batch_u8_ex": (C.c_int, [_P, _P, _P] + [C.c_int] * 8 + [_P, _P, _P, _P]),
+    "sivae_jpeg_info": (C.c_int, [_P, C.c_longlong, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sivae_jpeg_decode_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -136,6 +136,61 @@ def test_window_and_u8_output_match_oracle(ch):
         bt(torch.from_numpy(src), None, window=(wh, ww), origins=np.array([[W - ww + 1, 0]] * B, np.int32))
 
 
+def test_gpu_jpeg_decode_opt_in(tmp_path, monkeypatch):
+    """SIVAE_GPU_JPEG=1: JPEG files decoded by nvJPEG straight into the device batch the resize kernel reads.
+    nvJPEG is a library and NOT bit-exact with Pillow's libjpeg-turbo (IDCT / colour rounding, 4:2:0 chroma up-sampling), which
+    is why the path is opt-in: held here to a few grey levels on average against Pillow's decode of the same files; the
+    measured differences go to gpurun_out/jpeg_report.json"""
+    import ctypes as C
+    import json
+
+    from PIL import Image
+    M = _mod()
+    L = importlib.import_module(PKG + ".lib")
+    yy, xx = np.mgrid[0:96, 0:80].astype(np.float64)
+    smooth = [np.clip(np.stack([127 + 110 * np.sin(xx / (6.0 + c + i) + yy / 9.0) * np.cos(yy / (7.0 + 2 * c)) for c in range(3)], -1),
+                      0, 255).astype(np.uint8) for i in range(4)]
+    files = {"s444": [], "s420": []}
+    for i, a in enumerate(smooth):
+        for tag, sub in (("s444", 0), ("s420", 2)):
+            fn = "%s_%d.jpg" % (tag, i)
+            Image.fromarray(a, "RGB").save(tmp_path / fn, quality=92, subsampling=sub)
+            files[tag].append(fn)
+    raw0 = open(tmp_path / files["s444"][0], "rb").read()
+    h, w, c = C.c_int(), C.c_int(), C.c_int()
+    rc = L.load().sivae_jpeg_info((C.c_ubyte * len(raw0)).from_buffer_copy(raw0), len(raw0), C.byref(h), C.byref(w), C.byref(c))
+    if rc == -9:
+        pytest.skip("nvJPEG not available on this box: %s" % L.load().sivae_last_error().decode())
+    assert rc == 0 and (h.value, w.value, c.value) == (96, 80, 3)
+    report = {}
+    for tag, names in files.items():
+        datas = [torch.from_numpy(np.fromfile(tmp_path / n, dtype=np.uint8)) for n in names]
+        got = M.decode_jpeg_batch(datas, (96, 80, 3), "cuda:0")
+        assert got.dtype == torch.uint8 and tuple(got.shape) == (4, 96, 80, 3) and got.is_cuda
+        ref = np.stack([np.asarray(Image.open(tmp_path / n).convert("RGB")) for n in names])
+        d = np.abs(got.cpu().numpy().astype(np.int32) - ref.astype(np.int32))
+        report[tag] = dict(mean_abs=float(d.mean()), max_abs=int(d.max()), frac_equal=float((d == 0).mean()))
+        assert d.mean() < (3.0 if tag == "s444" else 10.0), (tag, report[tag])      # measured: see profiles/ jpeg report
+    with pytest.raises(RuntimeError, match="expected"):
+        M.decode_jpeg_batch([torch.from_numpy(np.fromfile(tmp_path / files["s444"][0], dtype=np.uint8))], (90, 80, 3), "cuda:0")
+    # the loader end to end: compressed files -> nvJPEG -> mirror / resize / ToTensor kernel, against the default (Pillow) decode
+    kw = dict(input_height=None, crop_height=None, output_height=32, is_mirror=True)
+    ds = M.ImageDatasetFromFile(files["s444"], str(tmp_path), **kw)
+    mk = lambda: M.GpuImageLoader(torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=0,
+                                                              collate_fn=M.collate_decoded), "cuda:0")
+    random.seed(2)
+    (base,) = list(mk())
+    monkeypatch.setenv("SIVAE_GPU_JPEG", "1")
+    random.seed(2)
+    (fast,) = list(mk())
+    assert fast.shape == base.shape == (4, 3, 32, 32)
+    report["loader_mean_abs"] = float((fast - base).abs().mean())
+    assert report["loader_mean_abs"] < 3.0 / 255
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "jpeg_report.json"), "w") as f:
+        json.dump(report, f)
+
+
 def test_downscale_beyond_staging_capacity_fails_loudly():
     src = torch.zeros(1, 4096, 8, 3, dtype=torch.uint8)
     with pytest.raises(RuntimeError, match="down-scaling factor too large"):

@@ -174,3 +174,44 @@ def test_dataset_draws_crop_offsets_like_the_reference(tmp_path):
         assert items[0][0].shape[2] == (1 if a["is_gray"] else 3)
         groups = M.collate_decoded(items)
         assert sum(g[0].numel() for g in groups) == len(items)
+
+
+def test_gpu_jpeg_opt_in_keeps_files_compressed_and_draws_unchanged(tmp_path, monkeypatch):
+    """SIVAE_GPU_JPEG=1 (host half): JPEG files stay compressed until the batch reaches the GPU (EncodedJpeg with the decoded
+    geometry from the header), other files are decoded as before, the `random` draws do not change, groups split by kind;
+    the C ABI reports nvJPEG as unavailable without a GPU instead of crashing"""
+    import ctypes as C
+    import pickle
+    import random
+
+    import torch
+    from PIL import Image
+    M = importlib.import_module(PKG + ".gpu_dataset")
+    L = importlib.import_module(PKG + ".lib")
+    rng = np.random.default_rng(5)
+    names = []
+    for i in range(3):
+        names.append("j%d.jpg" % i)
+        Image.fromarray(rng.integers(0, 256, (40, 56, 3), dtype=np.uint8), "RGB").save(tmp_path / names[-1], quality=90)
+    names.append("p.png")
+    Image.fromarray(rng.integers(0, 256, (40, 56, 3), dtype=np.uint8), "RGB").save(tmp_path / "p.png")
+    kw = dict(input_height=None, crop_height=32, crop_width=30, is_random_crop=True, output_height=16, is_mirror=True)
+    ds = M.ImageDatasetFromFile(names, str(tmp_path), **kw)
+    random.seed(9)
+    plain = [ds[i] for i in range(4)]
+    monkeypatch.setenv("SIVAE_GPU_JPEG", "1")
+    random.seed(9)
+    items = [ds[i] for i in range(4)]
+    assert [type(it[0]).__name__ for it in items] == ["EncodedJpeg"] * 3 + ["Tensor"]
+    assert all(tuple(a[0].shape) == tuple(b[0].shape) and a[1:] == b[1:] for a, b in zip(items, plain))
+    raw = open(tmp_path / "j0.jpg", "rb").read()
+    assert bytes(items[0][0].data.numpy().tobytes()) == raw
+    groups = M.collate_decoded(items)
+    assert sorted(type(g[1]).__name__ for g in groups) == ["EncodedBatch", "Tensor"]
+    pickle.loads(pickle.dumps(groups))                       # DataLoader workers ship the groups between processes
+    with pytest.raises(RuntimeError):
+        M.decode_jpeg_batch([items[0][0].data], items[0][0].shape, "cpu")
+    if not torch.cuda.is_available():
+        h, w, c = C.c_int(), C.c_int(), C.c_int()
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        assert L.load().sivae_jpeg_info(buf, len(raw), C.byref(h), C.byref(w), C.byref(c)) == -9
