@@ -215,3 +215,47 @@ def test_gpu_jpeg_opt_in_keeps_files_compressed_and_draws_unchanged(tmp_path, mo
         h, w, c = C.c_int(), C.c_int(), C.c_int()
         buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
         assert L.load().sivae_jpeg_info(buf, len(raw), C.byref(h), C.byref(w), C.byref(c)) == -9
+
+
+def test_load_spec_orchestration_on_an_oracle_backed_batcher(monkeypatch):
+    """LoadSpec.assemble (which launches, with which windows / flags, in which order) checked WITHOUT a GPU: ImageBatcher is
+    replaced by a stand-in that computes each launch with the numpy oracle, and the assembled batches must equal the tensors the
+    unmodified reference dataset returned (image_pipeline_crop.npz) -- in particular a crop of a MIRRORED image (dataset.py:26-27
+    precede :32-44) must come out as the mirrored window whose left border is the crop's right border"""
+    import torch
+    M = importlib.import_module(PKG + ".gpu_dataset")
+    calls = []
+
+    class FakeBatcher:
+        def __init__(self, out_h, out_w=None, device="cuda:0"):
+            self.out_h, self.out_w, self.device = int(out_h), int(out_w if out_w is not None else out_h), device
+
+        def __call__(self, images_u8, mirror=None, out=None, window=None, origins=None, as_u8=False):
+            imgs = images_u8.numpy()
+            B = imgs.shape[0]
+            flags = np.zeros(B, np.uint8) if mirror is None else np.asarray(torch.as_tensor(mirror)).astype(np.uint8)
+            calls.append((tuple(imgs.shape[1:3]), (self.out_h, self.out_w), window, bool(flags.any()), as_u8))
+            res = []
+            for i in range(B):
+                a = imgs[i]
+                if window is not None:
+                    x, y = (int(v) for v in torch.as_tensor(origins)[i])
+                    a = a[y:y + window[0], x:x + window[1]]
+                res.append(IO.load_image_u8(np.ascontiguousarray(a), bool(flags[i]), self.out_h, self.out_w))
+            res = np.stack(res)
+            return torch.from_numpy(res) if as_u8 else torch.from_numpy(np.stack([IO.to_tensor(r) for r in res]))
+
+    monkeypatch.setattr(M, "ImageBatcher", FakeBatcher)
+    for name, src, mirror, margins, out_u8, a in crop_cases():
+        imgs = np.stack([_gray(s_) for s_ in src]) if a["is_gray"] else src
+        spec = M.LoadSpec(a["input_hw"][0] if a["input_hw"] else None, a["input_hw"][1] if a["input_hw"] else None,
+                          a["out_hw"][0], a["out_hw"][1], a["crop"][0] if a["crop"] else None, a["crop"][1] if a["crop"] else None,
+                          a["is_random_crop"], True)
+        calls.clear()
+        got = spec.assemble({"device": "cpu"}, torch.from_numpy(imgs), torch.from_numpy(mirror),
+                            torch.from_numpy(margins.astype(np.int64)) if a["crop"] else None)
+        assert np.array_equal(got.numpy(), out_u8.astype(np.float32) / np.float32(255.0)), name
+        assert len(calls) == (2 if a["input_hw"] else 1), (name, calls)
+        if a["input_hw"]:
+            assert calls[0][4] and not calls[1][3]            # stage 1 writes the 8-bit image and carries the mirror; stage 2 none
+        assert (calls[-1][2] is not None) == bool(a["crop"])
