@@ -311,6 +311,57 @@ class GpuImageLoader:
             yield out
 
 
+def list_images_in_dir(path):
+    """dataset.py:84-93: the .jpg / .gif / .png files of a directory, in os.listdir order"""
+    return [os.path.join(path, f) for f in os.listdir(path) if os.path.splitext(f)[1].lower() in (".jpg", ".gif", ".png")]
+
+
+class DigitalMonstersDataset(data.Dataset):
+    """`monsters128` (dataset.py:96-149, train_soft_intro_vae.py:418-423): pokemon / digimon / nexomon sprites, resized by
+    load_image (no mirror, no crop) and augmented per item with torchvision's PIL transforms -- RandomAffine(0, translate = 5 px,
+    white fill), ColorJitter(hue=0.5), RandomHorizontalFlip -- before ToTensor.  Those augmentations draw from torch's CPU
+    generator and work on PIL images, so this data set stays on the host (a few thousand 128x128 sprites: not a loader
+    bottleneck); it exists here because the reference's own class no longer constructs under current torchvision
+    (`RandomAffine(fillcolor=...)` became `fill=` in 0.13) -- same transforms, same order, same draws."""
+
+    def __init__(self, root_path, input_height=None, input_width=None, output_height=128, output_width=None, is_gray=False,
+                 pokemon=True, digimon=True, nexomon=True):
+        super(DigitalMonstersDataset, self).__init__()
+        import torchvision.transforms as transforms
+        image_list = []
+        for wanted, label, sub in ((pokemon, "pokemon", ("pokemon",)), (digimon, "digimon", ("digimon", "200")),
+                                   (nexomon, "nexomon", ("nexomon",))):
+            if wanted:
+                print("collecting %s..." % label)
+                image_list.extend(list_images_in_dir(os.path.join(root_path, *sub)))
+        print(f'total images: {len(image_list)}')
+        self.image_filenames = image_list
+        self.input_height, self.input_width = input_height, input_width
+        self.output_height, self.output_width = output_height, output_width
+        self.root_path, self.is_gray = root_path, is_gray
+        self.input_transform = transforms.Compose([
+            transforms.RandomAffine(0, translate=(5 / output_height, 5 / output_height), fill=(255, 255, 255)),
+            transforms.ColorJitter(hue=0.5),
+            transforms.RandomHorizontalFlip(p=0.5),
+            transforms.ToTensor()])
+
+    def __getitem__(self, index):
+        from PIL import Image
+        # load_image(..., crop_height=None, is_mirror=False, is_gray=False), dataset.py:140-142, on the host
+        img = Image.open(self.image_filenames[index])
+        if img.mode != 'RGB':
+            img = img.convert('RGB')
+        ow = self.output_width if self.output_width is not None else self.output_height
+        if self.input_height is not None:
+            iw = self.input_width if self.input_width is not None else self.input_height
+            img = img.resize((iw, self.input_height), Image.BICUBIC)
+        img = img.resize((ow, self.output_height), Image.BICUBIC)
+        return self.input_transform(img)
+
+    def __len__(self):
+        return len(self.image_filenames)
+
+
 def load_image(file_path, input_height=128, input_width=None, output_height=128, output_width=None,
                crop_height=None, crop_width=None, is_random_crop=True, is_mirror=True, is_gray=False, device="cuda:0"):
     """Reference signature (dataset.py:12-13) for single images; returns the PIL image the reference returns, computed on

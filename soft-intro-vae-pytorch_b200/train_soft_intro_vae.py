@@ -517,7 +517,8 @@ def _build_dataset(dataset):
         ds = mod.ImageDatasetFromFile(names, root, input_height=None, crop_height=None, output_height=size, is_mirror=True)
         return ds, size, channels, 3, False
     if dataset == "monsters128":
-        ds = _reference_dataset_module().DigitalMonstersDataset(root_path='./monsters_ds/', output_height=128)
+        # host-side data set (torchvision PIL augmentations); the reference's own class does not construct under torchvision >= 0.13
+        ds = importlib.import_module(_PKG + ".gpu_dataset").DigitalMonstersDataset(root_path='./monsters_ds/', output_height=128)
         return ds, 128, [64, 128, 256, 512, 512], 3, False
     raise NotImplementedError("dataset is not supported")
 

@@ -259,3 +259,49 @@ def test_load_spec_orchestration_on_an_oracle_backed_batcher(monkeypatch):
         if a["input_hw"]:
             assert calls[0][4] and not calls[1][3]            # stage 1 writes the 8-bit image and carries the mirror; stage 2 none
         assert (calls[-1][2] is not None) == bool(a["crop"])
+
+
+def test_monsters_dataset_equals_the_reference_class(tmp_path, monkeypatch):
+    """`monsters128` (dataset.py:96-149): the drop-in DigitalMonstersDataset against the UNMODIFIED reference class, item by item
+    under the same torch seed (RandomAffine / ColorJitter / RandomHorizontalFlip draw from torch's generator).  The reference
+    class passes `fillcolor=` to RandomAffine, which torchvision renamed to `fill=` in 0.13 -- the only shim applied to it."""
+    import sys
+    import warnings
+
+    import torch
+    import torchvision.transforms as T
+    from PIL import Image
+    if not os.path.isdir("/root/reference/soft_intro_vae"):
+        pytest.skip("needs the reference tree (build container only)")
+    rng = np.random.default_rng(3)
+    for sub, n in (("pokemon", 3), (os.path.join("digimon", "200"), 2), ("nexomon", 2)):
+        os.makedirs(tmp_path / sub)
+        for i in range(n):
+            a = rng.integers(0, 256, (40 + 3 * i, 36 + 5 * i, 3), dtype=np.uint8)
+            Image.fromarray(a, "RGB").save(tmp_path / sub / ("m%d.png" % i))
+    (tmp_path / "pokemon" / "notes.txt").write_text("not an image")
+
+    class Affine(T.RandomAffine):
+        def __init__(self, degrees, translate=None, scale=None, shear=None, fillcolor=0, **kw):
+            super().__init__(degrees, translate=translate, scale=scale, shear=shear, fill=fillcolor, **kw)
+
+    warnings.simplefilter("ignore", SyntaxWarning)
+    sys.path.insert(0, "/root/reference/soft_intro_vae")
+    sys.modules.pop("dataset", None)
+    try:
+        import dataset as ref_dataset
+    finally:
+        sys.path.pop(0)
+    M = importlib.import_module(PKG + ".gpu_dataset")
+    root = str(tmp_path) + os.sep
+    ours = M.DigitalMonstersDataset(root_path=root, output_height=32)           # built on the unpatched torchvision
+    monkeypatch.setattr(ref_dataset.transforms, "RandomAffine", Affine)        # (ref_dataset.transforms IS torchvision.transforms)
+    ref = ref_dataset.DigitalMonstersDataset(root_path=root, output_height=32)
+    assert len(ref) == len(ours) == 7 and ref.image_filenames == ours.image_filenames
+    for i in range(len(ref)):
+        torch.manual_seed(100 + i)
+        want = ref[i]
+        torch.manual_seed(100 + i)
+        got = ours[i]
+        assert got.dtype == torch.float32 and got.shape == (3, 32, 32) and torch.equal(got, want), i
+    sys.modules.pop("dataset", None)
