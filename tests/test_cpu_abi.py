@@ -79,6 +79,31 @@ def test_conditional_engine_schema():
             assert cond[k] == plain[k], k
 
 
+def test_recon_loss_and_conditional_entry_points_validate_their_arguments():
+    """host-side argument checks of the round-2 entry points (no GPU work is enqueued before they fail)"""
+    lib = L.load()
+    c = L.Config()
+    c.cdim, c.zdim, c.image_size, c.n_channels, c.max_batch = 3, 16, 16, 2, 2
+    c.channels[0], c.channels[1] = 32, 64
+    h = C.c_void_p()
+    L.check(lib.sivae_create(C.byref(c), C.byref(h)), "create")
+    assert lib.sivae_get_recon_loss(h) == L.LOSS_MSE
+    assert lib.sivae_set_recon_loss(h, 7) != 0 and b"recon loss" in lib.sivae_last_error()
+    assert lib.sivae_set_recon_loss(h, L.LOSS_L1) == 0 and lib.sivae_get_recon_loss(h) == L.LOSS_L1
+    assert lib.sivae_set_recon_loss(h, L.LOSS_BCE) == 0 and lib.sivae_get_recon_loss(h) == L.LOSS_BCE
+    assert lib.sivae_set_recon_loss(None, L.LOSS_MSE) != 0 and lib.sivae_get_recon_loss(None) == -1
+    # the conditional entry points need an engine created with cond_dim > 0
+    assert lib.sivae_encode_cond(h, None, None, 1, None, None, 0, None) != 0 and b"cond_dim" in lib.sivae_last_error()
+    assert lib.sivae_decode_cond(h, 1, None, None, 1, None, 0, None) != 0 and b"cond_dim" in lib.sivae_last_error()
+    lib.sivae_destroy(h)
+    c.cond_dim = -1
+    assert lib.sivae_create(C.byref(c), C.byref(h)) != 0 and b"cond_dim" in lib.sivae_last_error()
+    # loader entry points: exactly one output, window inside the source
+    assert lib.sivae_image_batch_u8_ex(None, None, None, 1, 8, 8, 3, 8, 8, 4, 4, None, None, None, None) != 0
+    assert lib.sivae_jpeg_decode_batch(None, None, 0, 8, 8, None, None) != 0
+    assert L.LOSS_TYPES == {"mse": 0, "l1": 1, "bce": 2}
+
+
 def test_create_rejects_bad_configs():
     lib = L.load()
     c = L.Config()
