@@ -211,6 +211,7 @@ def main():
     print("cifar_std", g["scalars"])
     extra_losses()
     conditional_forward()
+    vae_warmups()
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:16])
@@ -266,7 +267,112 @@ def conditional_forward(seed=0, batch=6, cond_dim=10):
     print("tiny_cond", float(out["train"]["mu"].abs().sum()), float(out["eval"]["y"].abs().sum()), out["uncond_error"])
 
 
-if __name__ == "__main__" and "--cond" in sys.argv:
+def vae_warmup(subdir, modname, fn_name, out_name, extra_kwargs=None, batch=8, z_dim=16, seed=0):
+    """VAE warm-up iteration (`epoch < num_vae`, :512-540; bootstrap twin: decodes through the frozen target decoder) of the
+    UNMODIFIED reference trainer at the tiny architecture: num_vae = 1, num_epochs = 2 (with num_epochs = 1 the reference dies of a
+    NameError after the epoch -- `b_size` is only assigned in the introspective branch, :547 vs :678), everything recorded at the
+    FIRST tqdm `set_postfix` call, i.e. right after optimizer_e.step() / optimizer_d.step() of the warm-up iteration (:533-537)."""
+    ref = _import_reference(subdir, modname)
+    tiny = dict(channels=[32, 64], image_size=16)
+    rec = {"eps": [], "grads": [], "postfix": None}
+    holder = {}
+
+    class FakeCIFAR(torch.utils.data.Dataset):
+        def __init__(self, root=None, train=True, download=False, transform=None):
+            self.x = torch.rand(batch, 3, 16, 16, generator=torch.Generator().manual_seed(1234))
+
+        def __len__(self):
+            return len(self.x)
+
+        def __getitem__(self, i):
+            return self.x[i], 0
+
+    ref.CIFAR10 = FakeCIFAR
+    orig_init = ref.SoftIntroVAE.__init__
+
+    def patched_init(self, cdim=3, zdim=512, channels=(64, 128, 256, 512, 512, 512), image_size=256, **kw):
+        orig_init(self, cdim=cdim, zdim=zdim, channels=tiny["channels"], image_size=tiny["image_size"], **kw)
+        holder["model"] = self
+        holder["init"] = {k: v.detach().clone() for k, v in self.state_dict().items()}
+        holder["arch"] = dict(cdim=cdim, zdim=zdim, channels=list(tiny["channels"]), image_size=tiny["image_size"])
+
+    ref.SoftIntroVAE.__init__ = patched_init
+
+    def reparameterize(mu, logvar):
+        eps = torch.randn_like(logvar)
+        rec["eps"].append(eps.detach().clone())
+        return mu + eps * torch.exp(0.5 * logvar)
+
+    ref.reparameterize = reparameterize
+
+    class RecAdam(torch.optim.Adam):
+        def step(self, closure=None):
+            g = {}
+            for grp in self.param_groups:
+                for p in grp["params"]:
+                    g[id(p)] = None if p.grad is None else p.grad.detach().clone()
+            rec["grads"].append(g)
+            return super().step(closure)
+
+    ref.optim.Adam = RecAdam
+
+    class Bar:
+        def __init__(self, iterable=None, **k):
+            self.it = iterable
+
+        def __iter__(self):
+            for b in self.it:
+                if "real" not in rec:
+                    rec["real"] = b[0].detach().clone()
+                yield b
+
+        def set_description_str(self, *a, **k):
+            pass
+
+        def set_postfix(self, **k):
+            if rec["postfix"] is None:
+                rec["postfix"] = dict(k)
+                holder["post"] = {n: v.detach().clone() for n, v in holder["model"].state_dict().items()}
+
+        def close(self):
+            pass
+
+    ref.tqdm = Bar
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="sivae_golden_vae_")
+    os.chdir(tmp)
+    torch.set_num_threads(8)
+    try:
+        kwargs = dict(dataset="cifar10", z_dim=z_dim, batch_size=batch, num_workers=0, num_epochs=2, num_vae=1, beta_kl=0.7,
+                      beta_neg=256, beta_rec=1.3, device=torch.device("cpu"), seed=seed, test_iter=10 ** 9, save_interval=50,
+                      start_epoch=0, lr_e=2e-4, lr_d=2e-4)
+        kwargs.update(extra_kwargs or {})
+        getattr(ref, fn_name)(**kwargs)
+    finally:
+        ref.optim.Adam = torch.optim.Adam
+        os.chdir(cwd)
+    model = holder["model"]
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert set(rec["postfix"]) == {"r_loss", "kl"}, rec["postfix"]          # the warm-up branch's postfix (:536)
+    grads_e = {names[i]: g for i, g in rec["grads"][0].items() if g is not None}      # optimizer_e.step() (:533)
+    grads_d = {names[i]: g for i, g in rec["grads"][1].items() if g is not None}      # optimizer_d.step() (:534)
+    out = dict(arch=holder["arch"], batch=batch, seed=seed, hyper=dict(beta_kl=0.7, beta_rec=1.3), real=rec["real"], eps=rec["eps"][0],
+               init=holder["init"], post=holder["post"], grads_e=grads_e, grads_d=grads_d,
+               scalars=dict(r_loss=rec["postfix"]["r_loss"], kl=rec["postfix"]["kl"]), torch_version=torch.__version__,
+               threads=torch.get_num_threads(), reference_commit="b6dbf16")
+    torch.save(out, os.path.join(OUT, out_name))
+    print(out_name, out["scalars"], len(grads_e), "encoder /", len(grads_d), "decoder gradient tensors")
+
+
+def vae_warmups():
+    vae_warmup("soft_intro_vae", "train_soft_intro_vae", "train_soft_intro_vae", "tiny_vae_std.pt")
+    vae_warmup("soft_intro_vae_bootstrap", "train_soft_intro_vae_bootstrap", "train_soft_intro_vae", "tiny_vae_bootstrap.pt",
+               extra_kwargs=dict(gamma_r=1.0, copy_to_target_freq=1))
+
+
+if __name__ == "__main__" and "--vae" in sys.argv:
+    vae_warmups()
+elif __name__ == "__main__" and "--cond" in sys.argv:
     conditional_forward()
 elif __name__ == "__main__" and "--losses" in sys.argv:
     extra_losses()

@@ -110,3 +110,36 @@ def test_oracle_conditional_forward_matches_reference(golden_dir):
             for k, v in g["post_train"].items():
                 assert torch.allclose(sd[k].to(v.dtype), v, rtol=1e-5, atol=1e-7), k
     assert "shapes cannot be multiplied" in g["uncond_error"]       # what the reference does without a condition
+
+
+@pytest.mark.parametrize("name,bootstrap", [("tiny_vae_std.pt", False), ("tiny_vae_bootstrap.pt", True)])
+def test_oracle_vae_warmup_step_matches_reference(golden_dir, name, bootstrap):
+    """VAE warm-up iteration (`epoch < num_vae`, :512-540): the oracle's vae_step + both Adam steps against the UNMODIFIED
+    reference trainer run with num_vae = 1 (oracle/make_golden.py --vae).  Bootstrap: `model(real_batch)` decodes through the
+    frozen target decoder (bootstrap trainer :196-217), so the trainable decoder receives NO gradient and optimizer_d.step()
+    moves nothing -- recorded as an empty decoder-gradient set."""
+    g = _load(golden_dir, name)
+    torch.set_num_threads(g["threads"])
+    arch = O.Arch(**g["arch"])
+    sd = O.clone_sd(g["init"])
+    hp = O.Hyper(beta_kl=g["hyper"]["beta_kl"], beta_rec=g["hyper"]["beta_rec"])
+    scal, ge, gd = O.vae_step(sd, arch, g["real"], g["eps"], hp, bootstrap=bootstrap)
+    assert scal["loss_rec"] == pytest.approx(g["scalars"]["r_loss"], rel=1e-6)
+    assert scal["loss_kl"] == pytest.approx(g["scalars"]["kl"], rel=1e-6)
+    assert set(ge) == set(g["grads_e"]) and set(gd) == set(g["grads_d"])
+    assert (len(gd) == 0) == bootstrap
+    for k in ge:
+        assert _relerr(ge[k], g["grads_e"][k]) < 1e-5, k
+    for k in gd:
+        assert _relerr(gd[k], g["grads_d"][k]) < 1e-5, k
+    O.adam_update(sd, ge, O.AdamState(), 2e-4, hp)          # optimizer_e.step(), :533
+    O.adam_update(sd, gd, O.AdamState(), 2e-4, hp)          # optimizer_d.step(), :534 (bootstrap: nothing to move)
+    for k, v in g["post"].items():
+        if v.is_floating_point():
+            assert torch.allclose(sd[k], v, rtol=1e-5, atol=1e-7), k
+        else:
+            assert int(sd[k]) == int(v), k
+    if bootstrap:
+        for k, v in g["init"].items():
+            if k.startswith("decoder.") and v.is_floating_point() and "running" not in k:
+                assert torch.equal(g["post"][k], v), k      # the reference's own decoder did not move in the warm-up step
