@@ -212,6 +212,7 @@ def main():
     extra_losses()
     conditional_forward()
     vae_warmups()
+    helper_functions()
     for f in sorted(os.listdir(OUT)):
         p = os.path.join(OUT, f)
         print(f, os.path.getsize(p), hashlib.sha256(open(p, "rb").read()).hexdigest()[:16])
@@ -370,7 +371,30 @@ def vae_warmups():
                extra_kwargs=dict(gamma_r=1.0, copy_to_target_freq=1))
 
 
-if __name__ == "__main__" and "--vae" in sys.argv:
+def helper_functions():
+    """the tensor-level helpers of the reference module called directly with non-default arguments: calc_kl with an outlier
+    prior (mu_o, logvar_o; :231-251), calc_reconstruction_loss for every loss type x reduction (:268-294), reparameterize under
+    a fixed seed (:254-265) -> tests/golden/helpers.pt (a few kB)"""
+    ref = _import_reference("soft_intro_vae", "train_soft_intro_vae")
+    g = torch.Generator().manual_seed(99)
+    mu, lv = torch.randn(5, 7, generator=g), torch.randn(5, 7, generator=g) * 0.3
+    x, y = torch.rand(4, 3, 6, 6, generator=g), torch.rand(4, 3, 6, 6, generator=g)
+    out = dict(mu=mu, logvar=lv, x=x, recon=y, kl={}, rec={}, torch_version=torch.__version__, reference_commit="b6dbf16")
+    for red in ("sum", "mean", "none"):
+        out["kl"][("default", red)] = ref.calc_kl(lv, mu, reduce=red)
+        out["kl"][("outlier", red)] = ref.calc_kl(lv, mu, mu_o=0.3, logvar_o=-0.2, reduce=red)
+        out["kl"][("tensor_prior", red)] = ref.calc_kl(lv, mu, mu_o=torch.full((7,), 0.1), logvar_o=torch.full((7,), 0.4), reduce=red)
+        for lt in ("mse", "l1", "bce"):
+            out["rec"][(lt, red)] = ref.calc_reconstruction_loss(x, y, loss_type=lt, reduction=red)
+    torch.manual_seed(5)
+    out["reparam_seed5"] = ref.reparameterize(mu, lv)
+    torch.save(out, os.path.join(OUT, "helpers.pt"))
+    print("helpers.pt", os.path.getsize(os.path.join(OUT, "helpers.pt")), "bytes")
+
+
+if __name__ == "__main__" and "--helpers" in sys.argv:
+    helper_functions()
+elif __name__ == "__main__" and "--vae" in sys.argv:
     vae_warmups()
 elif __name__ == "__main__" and "--cond" in sys.argv:
     conditional_forward()

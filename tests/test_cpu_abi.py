@@ -181,6 +181,26 @@ def test_helpers_match_oracle():
     assert M.str_to_list("1,2,3") == [1, 2, 3] and M.is_image_file("a.png") and not M.is_image_file("a.txt")
 
 
+def test_helpers_match_reference_golden(golden_dir):
+    """the drop-in's tensor-level helpers against the UNMODIFIED reference functions (tests/golden/helpers.pt,
+    oracle/make_golden.py --helpers): calc_kl with scalar and tensor outlier priors, every loss type x reduction of
+    calc_reconstruction_loss (l1 / bce hand `reduction` to F.*_loss on the [B, D] views: 'none' is element-wise), reparameterize
+    under the same seed"""
+    g = torch.load(os.path.join(golden_dir, "helpers.pt"), weights_only=False)
+    mu, lv, x, y = g["mu"], g["logvar"], g["x"], g["recon"]
+    for (kind, red), want in g["kl"].items():
+        kw = {"default": {}, "outlier": dict(mu_o=0.3, logvar_o=-0.2),
+              "tensor_prior": dict(mu_o=torch.full((7,), 0.1), logvar_o=torch.full((7,), 0.4))}[kind]
+        got = M.calc_kl(lv, mu, reduce=red, **kw)
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-6, atol=1e-7), (kind, red)
+    for (lt, red), want in g["rec"].items():
+        got = M.calc_reconstruction_loss(x, y, loss_type=lt, reduction=red)
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-6, atol=1e-7), (lt, red)
+    assert g["rec"][("l1", "none")].shape == (4, 108) and g["rec"][("mse", "none")].shape == (4,)
+    torch.manual_seed(5)
+    assert torch.allclose(M.reparameterize(mu, lv), g["reparam_seed5"], rtol=1e-6, atol=1e-7)
+
+
 def test_bootstrap_model_init_is_bit_identical_to_reference(golden_dir):
     MB = importlib.import_module(PKG + ".train_soft_intro_vae_bootstrap")
     g = torch.load(os.path.join(golden_dir, "tiny_bootstrap.pt"), weights_only=False)
