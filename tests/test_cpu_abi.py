@@ -181,6 +181,19 @@ def test_helpers_match_oracle():
     assert M.str_to_list("1,2,3") == [1, 2, 3] and M.is_image_file("a.png") and not M.is_image_file("a.txt")
 
 
+def test_learning_rate_schedule_equals_multisteplr():
+    """a11: the reference builds MultiStepLR(milestones=(350,), gamma=0.1) on each optimiser (:453-454) and steps it once per epoch
+    (:649-650), counting from the run's first epoch whatever start_epoch is; the drop-in computes the same rate in closed form"""
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=2e-4)
+    sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=(350,), gamma=0.1)
+    for steps in range(0, 720):
+        assert M._milestone_lr(2e-4, steps) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12), steps
+        opt.step()
+        sch.step()
+    assert M._milestone_lr(1e-3, 349) == 1e-3 and M._milestone_lr(1e-3, 350) == pytest.approx(1e-4)
+
+
 def test_helpers_match_reference_golden(golden_dir):
     """the drop-in's tensor-level helpers against the UNMODIFIED reference functions (tests/golden/helpers.pt,
     oracle/make_golden.py --helpers): calc_kl with scalar and tensor outlier priors, every loss type x reduction of
