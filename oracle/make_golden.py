@@ -15,7 +15,13 @@ for exactly one introspective iteration on CPU, and recording everything at its 
 
 No reference source is copied: the reference module is imported from /root/reference and only its
 module globals are patched (dataset class, matplotlib stub, model hyper-parameters for the tiny
-config).  Usage:  python oracle/make_golden.py   (writes tests/golden/*.pt, ~6 MB total)
+config).  Usage:  python oracle/make_golden.py   (writes every tests/golden/*.pt, ~25 MB total), or one group:
+  --losses   tiny_l1.pt, tiny_bce.pt       the same iteration with recon_loss_type = 'l1' / 'bce' (:288-291)
+  --cond     tiny_cond.pt                  SoftIntroVAE(conditional=True) train / eval forward with a one-hot condition
+  --vae      tiny_vae_std.pt, tiny_vae_bootstrap.pt   the VAE warm-up iteration (epoch < num_vae, :512-540) of both trainers
+  --helpers  helpers.pt                    calc_kl / calc_reconstruction_loss / reparameterize called directly
+  --toy      toy2d.pt                      the 2-D trainer's printed log (BASELINE config 1)
+(the image-loader fixtures come from oracle/make_image_golden.py)
 """
 import hashlib
 import os
