@@ -10,7 +10,9 @@
  * Conventions
  *   - plain C types only; all tensor arguments are raw DEVICE pointers (fp32 unless noted) owned by the
  *     caller (torch allocations on the Python side).  The library never allocates or frees caller
- *     memory; its scratch lives in the caller-provided workspace (sivae_bind_workspace).
+ *     memory; its scratch lives in the caller-provided workspace (sivae_bind_workspace).  Two stated exceptions:
+ *     sivae_jpeg_decode_batch reads the COMPRESSED files from host pointers, and the libraries resolved at run time
+ *     (NCCL for the gradient all-reduce, nvJPEG for the opt-in decode) manage their own internal buffers.
  *   - every function returns 0 on success, <0 for an engine error, >0 for a cudaError_t; the text is
  *     available from sivae_last_error().  No C++ exception crosses the boundary.
  *   - all work is enqueued on the caller's stream (void* = cudaStream_t); nothing synchronises except
